@@ -1,0 +1,92 @@
+/*
+ * pmoe_b200 — C-ABI of the B200-native (sm_100a) hot path of mhnazeri/PMoE.
+ *
+ * The reference (pure PyTorch) has no FFI of its own: the interface each entry point replaces is
+ * the ATen operator the reference module dispatches to. Citations are `PMoE/<file>:<line>` in
+ * the reference tree. All pointers are DEVICE pointers owned by the caller (PyTorch's caching
+ * allocator on the Python side); the library never allocates or frees device memory and keeps
+ * no pointer past return. All launches go to the caller's stream; nothing synchronises.
+ * Return value: 0 = ok, negative = error (see pmoe_last_error()). No C++ exceptions cross here.
+ *
+ * Layout convention: activations are NHWC ("pixel-major") with the channel axis contiguous,
+ * described by a strided 4-D view so that channel slices (virtual concat, the PU-Net mask ring),
+ * spatial parity views (stride-2 convs) and pixel-shuffle views (ConvTranspose2d k2s2) need no
+ * copies.
+ */
+#ifndef PMOE_B200_H_
+#define PMOE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* pmoe_stream_t; /* cudaStream_t */
+
+enum { PMOE_OK = 0, PMOE_ERR_ARG = -1, PMOE_ERR_UNSUPPORTED = -2, PMOE_ERR_LAUNCH = -3, PMOE_ERR_DRIVER = -4 };
+enum { PMOE_F32 = 0, PMOE_BF16 = 1 };
+enum { PMOE_ACT_NONE = 0, PMOE_ACT_RELU = 1, PMOE_ACT_ELU = 2, PMOE_ACT_TANH = 3, PMOE_ACT_SIGMOID = 4 };
+
+/* Strided NHWC view; strides in ELEMENTS, channel stride is 1. */
+typedef struct PmoeView4 {
+  void* ptr;
+  int32_t n, h, w, c;
+  int64_t sn, sh, sw;
+} PmoeView4;
+
+#define PMOE_MAX_SRC 6
+#define PMOE_MAX_SEG 64
+
+/* One K-segment of the implicit GEMM: `nchunks` channel chunks of `ck` channels starting at
+ * channel c0 of source `src`, read at spatial offset (dh, dw) from the output pixel. */
+typedef struct PmoeSeg {
+  int8_t src, dh, dw, reserved;
+  uint16_t c0, nchunks;
+} PmoeSeg;
+
+/* Tensor-core implicit-GEMM convolution / linear layer (bf16 in, fp32 accumulate in TMEM, bf16 out).
+ * Replaces aten::convolution (+ folded/eval BatchNorm + ReLU + residual add) as used by
+ * conv3 (model/blocks/basics.py:48-59), EfficientConvBlock (:80-135), UNet (model/blocks/unet.py:50-95),
+ * torchvision BasicBlock (model/blocks/backbone.py:57-61), ConvTranspose2d k2s2 (unet.py:35-45) via
+ * four pixel-shuffle output views, and aten::linear of make_mlp (basics.py:11-45) as a 1x1 conv.
+ * out[n,h,w,co] = act( scale[co] * sum_seg sum_c src[seg.src][n,h+dh,w+dw,c0+c] * wpack[co,k] + shift[co] (+ residual) )
+ * with zero padding outside the source view. wpack is [cout_pad][ktot] bf16, k enumerating
+ * (segment, chunk, channel) in order. */
+typedef struct PmoeConvTc {
+  int32_t n_src;
+  PmoeView4 src[PMOE_MAX_SRC];
+  int32_t n_seg;
+  PmoeSeg seg[PMOE_MAX_SEG];
+  int32_t ck;       /* channel chunk: 16, 32 or 64 */
+  int32_t ktot;     /* = ck * sum(nchunks) */
+  int32_t cout_pad; /* rows of wpack; multiple of the N tile (16/32/64/128/256) */
+  const void* wpack;
+  PmoeView4 out; /* bf16; out.c = channels stored (<= cout_pad, multiple of 8) */
+  const float* scale; /* [cout_pad] or NULL (=1) */
+  const float* shift; /* [cout_pad] or NULL (=0) */
+  int32_t act;
+  PmoeView4 residual; /* bf16, ptr NULL = none; added before the activation */
+  float* stat_sum;    /* optional [cout_pad]: += sum over valid pixels of the raw accumulator   */
+  float* stat_sqsum;  /* optional [cout_pad]: += sum of squares (train-mode BN batch statistics) */
+  float* pool_sum;    /* optional [n][cout_pad]: += per-image sum of the stored output (ECA / avgpool) */
+} PmoeConvTc;
+
+int pmoe_conv_tc(const PmoeConvTc* desc, pmoe_stream_t stream);
+
+/* Library info / errors. */
+int pmoe_version(void);
+const char* pmoe_last_error(void);
+int pmoe_device_check(void); /* 0 iff device 0..current is sm_100 */
+
+/* Debug probe used by tests/ and by the round-1 descriptor study (profiles/): one CTA computes
+ * D[128,64] = A_view[128,64] * B[64,64]^T where A_view row m reads smem row
+ * start_row + (m/8)*group_rows + (m%8) of a SWIZZLE_128B tile of `rows` rows loaded by TMA. */
+int pmoe_dbg_umma_view(const void* a_bf16, int rows, const void* b_bf16, float* d_out, int start_row,
+                       int group_rows, int base_offset_mode, pmoe_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMOE_B200_H_ */

@@ -1,0 +1,483 @@
+"""TEST INFRASTRUCTURE — CPU oracle for the pmoe_b200 hot path. NOT product code.
+
+A functional (state-dict driven) fp32 PyTorch restatement of the reference algorithm. Only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this package; pmoe_b200/ never does. Every function cites the reference lines it restates
+(paths relative to /root/reference/PMoE). The restatement is pinned against outputs of the live
+reference (tests/golden/*.pt, produced by oracle/gen_golden.py) in tests/test_oracle_golden.py.
+
+Conventions: `sd` is a flat dict name -> tensor with the reference's state_dict keys, `p` a key
+prefix ending in '.', `train` selects BatchNorm batch statistics (running stats in `sd` are then
+updated in place exactly as nn.BatchNorm2d does).
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+
+# ------------------------------------------------------------------ blocks (model/blocks/basics.py)
+def batchnorm(x, sd, p, train):
+    """nn.BatchNorm{1,2}d defaults as instantiated at basics.py:34,52,55,103,124."""
+    if train and p + "num_batches_tracked" in sd:
+        sd[p + "num_batches_tracked"] += 1
+    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
+                        train, BN_MOMENTUM, BN_EPS)
+
+
+def conv3_block(x, sd, p, train, stride=1):
+    """basics.py:48-59 — (conv3x3 no-bias, BN, ReLU) twice."""
+    for a, b in (("0", "1"), ("3", "4")):
+        x = F.conv2d(x, sd[p + a + ".weight"], None, stride, 1)
+        x = torch.relu(batchnorm(x, sd, p + b + ".", train))
+    return x
+
+
+def eca_kernel_size(channels, gamma=2, b=1):
+    """basics.py:67-68."""
+    t = int(abs((math.log2(channels) + b) / gamma))
+    return t if t % 2 else t + 1
+
+
+def eca(x, w):
+    """basics.py:71-77 — channel attention: GAP -> conv1d over the channel axis -> sigmoid -> scale."""
+    k = w.shape[-1]
+    y = x.mean(dim=(2, 3))
+    y = F.conv1d(y.unsqueeze(1), w, None, 1, k // 2).squeeze(1)
+    return x * torch.sigmoid(y)[:, :, None, None]
+
+
+def eca_conv_block(x, sd, p, train, stride=1):
+    """basics.py:80-135 — EfficientConvBlock."""
+    x = eca(x, sd[p + "layer1.eca1.conv.weight"])
+    x = F.conv2d(x, sd[p + "layer1.conv1.0.weight"], None, stride, 1)
+    x = torch.relu(batchnorm(x, sd, p + "layer1.conv1.1.", train))
+    x = eca(x, sd[p + "layer2.eca2.conv.weight"])
+    x = F.conv2d(x, sd[p + "layer2.conv2.0.weight"], None, stride, 1)
+    return torch.relu(batchnorm(x, sd, p + "layer2.conv2.1.", train))
+
+
+def mlp_layout(dims, act, l_act=False, bn=True, dropout=0.0):
+    """basics.py:11-45 — the nn.Sequential index of every layer make_mlp creates."""
+    ops, idx = [], 0
+    n = len(dims) - 1
+    for i in range(n):
+        ops.append(("linear", idx, dims[i], dims[i + 1], not bn))
+        idx += 1
+        if i != n - 1:
+            if bn:
+                ops.append(("bn", idx, dims[i + 1]))
+                idx += 1
+            ops.append(("act", idx, act.lower()))
+            idx += 1
+            if dropout > 0.0:
+                ops.append(("dropout", idx, dropout))
+                idx += 1
+    if l_act:
+        ops.append(("act", idx, act.lower()))
+    return ops
+
+
+_ACTS = {"relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "elu": F.elu}
+
+
+def mlp(x, sd, p, cfg, train):
+    """basics.py:11-45 forward of the Sequential built by make_mlp(**cfg)."""
+    for op in mlp_layout(cfg["dims"], cfg["act"], cfg.get("l_act", False), cfg.get("bn", True), cfg.get("dropout", 0.0)):
+        if op[0] == "linear":
+            x = F.linear(x, sd[p + "%d.weight" % op[1]], sd.get(p + "%d.bias" % op[1]))
+        elif op[0] == "bn":
+            x = batchnorm(x, sd, p + "%d." % op[1], train)
+        elif op[0] == "act":
+            x = _ACTS[op[2]](x)
+        elif op[0] == "dropout":
+            x = F.dropout(x, op[2], train)
+    return x
+
+
+# ------------------------------------------------------------------ U-Net (model/blocks/unet.py:8-95)
+def unet(x, sd, p, train, inter_repr=False):
+    x1 = conv3_block(x, sd, p + "dwn_1.", train)
+    x2 = conv3_block(F.max_pool2d(x1, 2, 2), sd, p + "dwn_2.", train)
+    x3 = conv3_block(F.max_pool2d(x2, 2, 2), sd, p + "dwn_3.", train)
+    x4 = conv3_block(F.max_pool2d(x3, 2, 2), sd, p + "dwn_4.", train)
+    x5 = conv3_block(F.max_pool2d(x4, 2, 2), sd, p + "dwn_5.", train)
+    y = x5
+    for i, skip in ((1, x4), (2, x3), (3, x2), (4, x1)):
+        up = F.conv_transpose2d(y, sd[p + "up_%d.weight" % i], sd[p + "up_%d.bias" % i], stride=2)
+        # unet.py:72 output_size=skip.size(): pads bottom/right when the skip is odd-sized
+        dh, dw = skip.shape[-2] - up.shape[-2], skip.shape[-1] - up.shape[-1]
+        if dh or dw:
+            up = F.conv_transpose2d(y, sd[p + "up_%d.weight" % i], sd[p + "up_%d.bias" % i], stride=2,
+                                    output_padding=(dh, dw))
+        y = conv3_block(torch.cat([skip, up], 1), sd, p + "up_forw_%d." % i, train)  # skip first (unet.py:73)
+    out = F.conv2d(y, sd[p + "out.weight"], sd[p + "out.bias"])
+    if inter_repr:
+        return x5.mean(dim=(2, 3)), out
+    return out
+
+
+# ------------------------------------------------------------------ ResNet18 + ECA stem (backbone.py:48-72)
+RESNET18_LAYERS = ((64, 1), (128, 2), (256, 2), (512, 2))
+
+
+def resnet18_eca(x, sd, p, train):
+    """torchvision ResNet._forward_impl with conv1 := EfficientConvBlock and fc := Identity."""
+    x = eca_conv_block(x, sd, p + "conv1.", train)
+    x = torch.relu(batchnorm(x, sd, p + "bn1.", train))
+    x = F.max_pool2d(x, 3, 2, 1)
+    for li, (_, stride) in enumerate(RESNET18_LAYERS, start=1):
+        for bi in range(2):
+            q = p + "layer%d.%d." % (li, bi)
+            s = stride if bi == 0 else 1
+            idt = x
+            y = F.conv2d(x, sd[q + "conv1.weight"], None, s, 1)
+            y = torch.relu(batchnorm(y, sd, q + "bn1.", train))
+            y = F.conv2d(y, sd[q + "conv2.weight"], None, 1, 1)
+            y = batchnorm(y, sd, q + "bn2.", train)
+            if q + "downsample.0.weight" in sd:
+                idt = F.conv2d(x, sd[q + "downsample.0.weight"], None, s, 0)
+                idt = batchnorm(idt, sd, q + "downsample.1.", train)
+            x = torch.relu(y + idt)
+    return x.mean(dim=(2, 3))
+
+
+# ------------------------------------------------------------------ PU-Net (model/punet.py:75-120)
+def punet(imgs, sd, p, train, past_frames=4, future_frames=6, inter_repr=False, unet_inter_repr=False):
+    assert imgs.shape[-4] == past_frames
+    masks = [unet(imgs[:, i], sd, p + "unet.", train, unet_inter_repr) for i in range(past_frames)]
+    if future_frames == 0:
+        return masks[-1][0] if unet_inter_repr else masks[-1]
+    outs, inter = [], None
+    for _ in range(future_frames):
+        m = torch.cat(masks[-past_frames:], dim=-3)
+        m = eca_conv_block(m, sd, p + "entry_block.", train)
+        if inter_repr:
+            inter, m = unet(m, sd, p + "pred_unet.", train, True)
+        else:
+            m = unet(m, sd, p + "pred_unet.", train, False)
+        masks.append(m)
+        outs.append(m)
+    return inter if inter_repr else torch.stack(outs, dim=1)
+
+
+# ------------------------------------------------------------------ experts / mixtures (model/moe.py)
+def expert(images, speed, command, sd, p, cfg, train, alt=False):
+    """moe.py:74-101 (BaseExpert) / :113-128 (BaseExpertAlt) -> alpha, mean, std, pred_speed."""
+    s = mlp(speed, sd, p + "speed_encoder.", cfg["speed_encoder"], train)
+    c = mlp(command, sd, p + "command_encoder.", cfg["command_encoder"], train)
+    img = resnet18_eca(images.reshape(images.shape[0], -1, images.shape[-2], images.shape[-1]), sd, p + "backbone.", train)
+    feats = torch.cat([img, s, c], dim=-1)
+    pred_speed = mlp(feats, sd, p + "speed_pred.", cfg["speed_prediction"], train)
+    af = mlp(feats, sd, p + "action_features.", cfg["action_head"], train)
+    mean, std = F.linear(af, sd[p + "action_pred.weight"], sd[p + "action_pred.bias"]).split(2, dim=-1)
+    std = F.elu(std) + 1
+    if alt:
+        a = F.linear(feats, sd[p + "alpha.0.weight"], sd[p + "alpha.0.bias"])
+        alpha = F.linear(torch.relu(a), sd[p + "alpha.2.weight"], sd[p + "alpha.2.bias"])
+    else:
+        alpha = torch.relu(F.linear(af, sd[p + "alpha.weight"], sd[p + "alpha.bias"]))
+    return alpha, mean, std, pred_speed
+
+
+def moe(images, speed, command, sd, p, cfg, train):
+    """moe.py:140-158 -> (probs (B,K), mean (B,K,2), std (B,K,2), speeds (B,K,1))."""
+    outs = [expert(images, speed, command, sd, p + "moe.%d." % k, cfg, train, cfg["type"] == "moe_alt")
+            for k in range(cfg["n_experts"])]
+    probs = F.softmax(torch.cat([o[0] for o in outs], dim=1), dim=1)
+    return probs, torch.stack([o[1] for o in outs], 1), torch.stack([o[2] for o in outs], 1), torch.stack([o[3] for o in outs], 1)
+
+
+def moe_shared(images, speed, command, sd, p, cfg, train):
+    """moe.py:205-239 -> (probs (B,K), mean, std, pred_speed (B,1))."""
+    K = cfg["n_experts"]
+    s = mlp(speed, sd, p + "speed_encoder.", cfg["speed_encoder"], train)
+    c = mlp(command, sd, p + "command_encoder.", cfg["command_encoder"], train)
+    img = resnet18_eca(images.reshape(images.shape[0], -1, images.shape[-2], images.shape[-1]), sd, p + "backbone.", train)
+    feats = torch.cat([img, s, c], dim=-1)
+    pred_speed = mlp(feats, sd, p + "speed_pred.", cfg["speed_prediction"], train)
+    af = mlp(feats, sd, p + "action_features.", cfg["action_head"], train)
+    mean, std = F.linear(af, sd[p + "action_pred.weight"], sd[p + "action_pred.bias"]).view(af.shape[0], K, -1).split(2, dim=-1)
+    std = F.elu(std) + 1
+    probs = F.softmax(F.linear(af, sd[p + "alpha.weight"], sd[p + "alpha.bias"]), dim=1)
+    return probs, mean, std, pred_speed
+
+
+def mixture_log_prob(probs, mean, std, x):
+    """torch.distributions.MixtureSameFamily(Categorical(probs), Independent(Normal(mean,std),1)).log_prob
+    as called at trainer/loss.py:123 (torch 2.11 semantics: Categorical renormalises probs and uses
+    logits = log(clamp(p, eps, 1-eps)); log_softmax of those logits is taken again)."""
+    eps = torch.finfo(probs.dtype).eps
+    pn = probs / probs.sum(-1, keepdim=True)
+    logits = torch.log(pn.clamp(eps, 1 - eps))
+    log_mix = torch.log_softmax(logits, dim=-1)
+    xe = x.unsqueeze(-2)
+    comp = (-((xe - mean) ** 2) / (2 * std ** 2) - std.log() - 0.5 * math.log(2 * math.pi)).sum(-1)
+    return torch.logsumexp(comp + log_mix, dim=-1)
+
+
+def mixture_sample(probs, mean, std, generator=None):
+    """MixtureSameFamily.sample() (moe.py:177,352): Categorical index via multinomial, then a full
+    Normal draw of every component, gathered. RNG consumption order matches torch.distributions."""
+    idx = torch.multinomial(probs / probs.sum(-1, keepdim=True), 1, True, generator=generator)  # (B,1)
+    comp = torch.normal(mean, std, generator=generator)  # (B,K,2)
+    return comp.gather(1, idx.unsqueeze(-1).expand(-1, 1, comp.shape[-1])).squeeze(1), idx.squeeze(1)
+
+
+def punet_expert(images, speed, command, sd, p, cfg, train):
+    """moe.py:303-317 -> (tanh(action) (B,2), speed (B,1))."""
+    inter = cfg["type"] == "punet_inter"
+    pc = cfg["punet"]
+    s = mlp(speed, sd, p + "speed_encoder.", cfg["speed_encoder"], train)
+    c = mlp(command, sd, p + "command_encoder.", cfg["command_encoder"], train)
+    out = punet(images, sd, p + "punet.", train, pc["past_frames"], pc["future_frames"], inter, pc.get("unet_inter_repr", False))
+    if inter:
+        img = out
+    else:
+        img = resnet18_eca(out.reshape(out.shape[0], -1, out.shape[-2], out.shape[-1]), sd, p + "backbone.", train)
+    feats = torch.cat([img, s, c], dim=-1)
+    a = mlp(feats, sd, p + "action_pred.0.", cfg["action_head"], train)
+    a = F.linear(a, sd[p + "action_pred.1.weight"], sd[p + "action_pred.1.bias"])
+    return torch.tanh(a), mlp(feats, sd, p + "speed_pred.", cfg["speed_prediction"], train)
+
+
+def pmoe_combine(moe_actions, punet_actions, sd, p):
+    """moe.py:353-356."""
+    lat = F.linear(torch.cat([moe_actions[:, 0:1], punet_actions[:, 0:1]], -1), sd[p + "lat_weights.weight"], sd[p + "lat_weights.bias"])
+    lon = F.linear(torch.cat([moe_actions[:, 1:], punet_actions[:, 1:]], -1), sd[p + "long_weights.weight"], sd[p + "long_weights.bias"])
+    return torch.tanh(torch.cat([lat, lon], -1))
+
+
+# ------------------------------------------------------------------ losses (trainer/loss.py)
+def class_dice_weights(pred, target, eps=1e-6):
+    """loss.py:6-17 — 1 - dice per class from argmax predictions (no gradient)."""
+    nc = pred.shape[1]
+    pc = pred.argmax(1)
+    w = torch.ones(nc, dtype=torch.float32)
+    for c in range(nc):
+        pm, tm = pc == c, target == c
+        inter = (pm & tm).sum().float() + eps
+        union = pm.sum() + tm.sum() + eps
+        w[c] = 1 - 2 * inter / union
+    return w
+
+
+def tversky(pred, target, alpha=0.5, beta=0.5):
+    """loss.py:34-44."""
+    oh = F.one_hot(target, pred.shape[1]).movedim(-1, 1).to(pred.dtype)
+    pr = F.softmax(pred, 1)
+    dims = (0,) + tuple(range(2, target.dim() + 1))
+    tp = (pr * oh).sum(dims)
+    fp = (pr * (1 - oh)).sum(dims)
+    fn = ((1 - pr) * oh).sum(dims)
+    return 1 - (tp / (tp + alpha * fp + beta * fn)).mean()
+
+
+def ce_tversky(pred, target, wc=0.5, wt=0.5):
+    """loss.py:47-55."""
+    ce = F.cross_entropy(pred, target, weight=class_dice_weights(pred, target))
+    return wc * ce + wt * tversky(pred, target)
+
+
+def autoregressive_ce_tversky(inputs, targets):
+    """loss.py:86-118 with loss_type='tversky'."""
+    return sum(ce_tversky(inputs[:, t], targets[:, t]) for t in range(inputs.shape[1]))
+
+
+def moe_loss(probs, mean, std, speed_pred, actions_gt, speed_gt, coefs):
+    """loss.py:121-132 (speed_gt is (B,1); the reference unsqueezes it in place when speed_pred is 3-D)."""
+    nll = -mixture_log_prob(probs, mean, std, actions_gt).mean(0)
+    if speed_pred.dim() > 2:
+        sp = F.mse_loss(speed_pred, speed_gt.unsqueeze(1).expand_as(speed_pred)) / speed_pred.shape[1]
+    else:
+        sp = F.mse_loss(speed_pred, speed_gt)
+    return coefs[0] * nll + coefs[1] * sp
+
+
+def punet_loss(actions, speed_pred, actions_gt, speed_gt, coefs):
+    """loss.py:135-142."""
+    return coefs[0] * F.l1_loss(actions, actions_gt) + coefs[1] * F.mse_loss(speed_pred, speed_gt)
+
+
+def pmoe_loss(actions, actions_gt):
+    """loss.py:145-151."""
+    return F.l1_loss(actions, actions_gt)
+
+
+# ------------------------------------------------------------------ state-dict specs
+def _bn(spec, p, c):
+    spec[p + "weight"] = (c,)
+    spec[p + "bias"] = (c,)
+    spec[p + "running_mean"] = (c,)
+    spec[p + "running_var"] = (c,)
+    spec[p + "num_batches_tracked"] = ()
+
+
+def conv3_spec(spec, p, cin, cout):
+    spec[p + "0.weight"] = (cout, cin, 3, 3)
+    _bn(spec, p + "1.", cout)
+    spec[p + "3.weight"] = (cout, cout, 3, 3)
+    _bn(spec, p + "4.", cout)
+
+
+def eca_block_spec(spec, p, cin, cout, gamma=2, b=1):
+    spec[p + "layer1.eca1.conv.weight"] = (1, 1, eca_kernel_size(cin, gamma, b))
+    spec[p + "layer1.conv1.0.weight"] = (64, cin, 3, 3)
+    _bn(spec, p + "layer1.conv1.1.", 64)
+    spec[p + "layer2.eca2.conv.weight"] = (1, 1, eca_kernel_size(64, gamma, b))
+    spec[p + "layer2.conv2.0.weight"] = (cout, 64, 3, 3)
+    _bn(spec, p + "layer2.conv2.1.", cout)
+
+
+def unet_spec(spec, p, cin=3, cout=23):
+    for i, (a, b) in enumerate(((cin, 64), (64, 128), (128, 256), (256, 512), (512, 512)), start=1):
+        conv3_spec(spec, p + "dwn_%d." % i, a, b)
+    for i, (a, b) in enumerate(((512, 512), (512, 256), (256, 128), (128, 64)), start=1):
+        spec[p + "up_%d.weight" % i] = (a, b, 2, 2)
+        spec[p + "up_%d.bias" % i] = (b,)
+        conv3_spec(spec, p + "up_forw_%d." % i, 2 * b, b)
+    spec[p + "out.weight"] = (cout, 64, 1, 1)
+    spec[p + "out.bias"] = (cout,)
+
+
+def resnet18_spec(spec, p, cin, gamma=2, b=1):
+    eca_block_spec(spec, p + "conv1.", cin, 64, gamma, b)
+    _bn(spec, p + "bn1.", 64)
+    prev = 64
+    for li, (c, stride) in enumerate(RESNET18_LAYERS, start=1):
+        for bi in range(2):
+            q = p + "layer%d.%d." % (li, bi)
+            spec[q + "conv1.weight"] = (c, prev if bi == 0 else c, 3, 3)
+            _bn(spec, q + "bn1.", c)
+            spec[q + "conv2.weight"] = (c, c, 3, 3)
+            _bn(spec, q + "bn2.", c)
+            if bi == 0 and (stride != 1 or prev != c):
+                spec[q + "downsample.0.weight"] = (c, prev, 1, 1)
+                _bn(spec, q + "downsample.1.", c)
+        prev = c
+
+
+def mlp_spec(spec, p, cfg):
+    for op in mlp_layout(cfg["dims"], cfg["act"], cfg.get("l_act", False), cfg.get("bn", True), cfg.get("dropout", 0.0)):
+        if op[0] == "linear":
+            spec[p + "%d.weight" % op[1]] = (op[3], op[2])
+            if op[4]:
+                spec[p + "%d.bias" % op[1]] = (op[3],)
+        elif op[0] == "bn":
+            _bn(spec, p + "%d." % op[1], op[2])
+
+
+def expert_spec(spec, p, cfg, alt=False):
+    mlp_spec(spec, p + "speed_encoder.", cfg["speed_encoder"])
+    mlp_spec(spec, p + "command_encoder.", cfg["command_encoder"])
+    rgb = cfg["backbone"]["rgb"]
+    resnet18_spec(spec, p + "backbone.", cfg["backbone"]["n_frames"] * 3, rgb.get("gamma", 2), rgb.get("b", 1))
+    mlp_spec(spec, p + "speed_pred.", cfg["speed_prediction"])
+    mlp_spec(spec, p + "action_features.", cfg["action_head"])
+    d = cfg["action_head"]["dims"][-1]
+    if alt:
+        spec[p + "alpha.0.weight"], spec[p + "alpha.0.bias"] = (512, 1536), (512,)
+        spec[p + "alpha.2.weight"], spec[p + "alpha.2.bias"] = (1, 512), (1,)
+    else:
+        spec[p + "alpha.weight"], spec[p + "alpha.bias"] = (1, d), (1,)
+    spec[p + "action_pred.weight"], spec[p + "action_pred.bias"] = (4, d), (4,)
+
+
+def moe_spec(spec, p, cfg):
+    for k in range(cfg["n_experts"]):
+        expert_spec(spec, p + "moe.%d." % k, cfg, cfg["type"] == "moe_alt")
+
+
+def moe_shared_spec(spec, p, cfg):
+    K = cfg["n_experts"]
+    mlp_spec(spec, p + "speed_encoder.", cfg["speed_encoder"])
+    mlp_spec(spec, p + "command_encoder.", cfg["command_encoder"])
+    rgb = cfg["backbone"]["rgb"]
+    resnet18_spec(spec, p + "backbone.", cfg["backbone"]["n_frames"] * 3, rgb.get("gamma", 2), rgb.get("b", 1))
+    mlp_spec(spec, p + "speed_pred.", cfg["speed_prediction"])
+    mlp_spec(spec, p + "action_features.", cfg["action_head"])
+    d = cfg["action_head"]["dims"][-1]
+    spec[p + "alpha.weight"], spec[p + "alpha.bias"] = (K, d), (K,)
+    spec[p + "action_pred.weight"], spec[p + "action_pred.bias"] = (4 * K, d), (4 * K,)
+
+
+def punet_spec(spec, p, pc):
+    unet_spec(spec, p + "unet.", pc["in_features"], pc["num_classes"])
+    eca_block_spec(spec, p + "entry_block.", pc["past_frames"] * pc["num_classes"], pc["in_features"], pc.get("gamma", 2), pc.get("b", 1))
+    unet_spec(spec, p + "pred_unet.", pc["in_features"], pc["num_classes"])
+
+
+def punet_expert_spec(spec, p, cfg):
+    pc = cfg["punet"]
+    mlp_spec(spec, p + "speed_encoder.", cfg["speed_encoder"])
+    mlp_spec(spec, p + "command_encoder.", cfg["command_encoder"])
+    punet_spec(spec, p + "punet.", pc)
+    if cfg["type"] != "punet_inter":
+        rgb = cfg["backbone"]["rgb"]
+        resnet18_spec(spec, p + "backbone.", pc["future_frames"] * pc["num_classes"], rgb.get("gamma", 2), rgb.get("b", 1))
+    mlp_spec(spec, p + "speed_pred.", cfg["speed_prediction"])
+    mlp_spec(spec, p + "action_pred.0.", cfg["action_head"])
+    spec[p + "action_pred.1.weight"], spec[p + "action_pred.1.bias"] = (2, cfg["action_head"]["dims"][-1]), (2,)
+
+
+def pmoe_spec(spec, p, cfg):
+    moe_spec(spec, p + "moe.", cfg)
+    punet_expert_spec(spec, p + "punet.", cfg)
+    for n in ("lat_weights", "long_weights"):
+        spec[p + n + ".weight"], spec[p + n + ".bias"] = (1, 2), (1,)
+
+
+def make_spec(fn, *args):
+    spec = OrderedDict()
+    fn(spec, "", *args)
+    return spec
+
+
+def seeded_state_dict(spec, seed, w_gain=1.0):
+    """Deterministic, well-conditioned weights for a spec (He-scaled convs/linears, non-trivial BN
+    affine + running stats) — used by both the golden generator and the tests, so the big weight
+    tensors never need to be stored."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    for name, shape in spec.items():
+        leaf = name.rsplit(".", 1)[-1]
+        if leaf == "num_batches_tracked":
+            t = torch.zeros((), dtype=torch.int64)
+        elif leaf == "running_var":
+            t = torch.rand(shape, generator=g) * 0.5 + 0.75
+        elif leaf == "running_mean":
+            t = torch.randn(shape, generator=g) * 0.1
+        elif leaf == "weight" and len(shape) == 1:
+            t = torch.rand(shape, generator=g) * 0.5 + 0.75
+        elif leaf == "bias":
+            t = torch.randn(shape, generator=g) * 0.05
+        elif leaf == "weight" and len(shape) == 3:  # ECA conv1d
+            t = torch.randn(shape, generator=g) * 0.5
+        else:
+            if name.startswith("up_") or ".up_" in name:
+                fan_in = shape[0]  # ConvTranspose2d k2s2: each output pixel sees Cin inputs
+            else:
+                fan_in = 1
+                for s in shape[1:]:
+                    fan_in *= s
+            t = torch.randn(shape, generator=g) * (w_gain * (2.0 / max(fan_in, 1)) ** 0.5)
+        sd[name] = t
+    return sd
+
+
+DEFAULT_MODEL_CFG = {
+    # conf/stage_2.yaml:76-133 with pretrained=False and dropout disabled for parity runs
+    "type": "moe", "n_experts": 3, "loss_coefs": [0.7, 0.3], "exclude_freeze": [], "verbose": False,
+    "action_head": {"dims": [1536, 512, 512], "act": "elu", "l_act": True, "bn": False, "dropout": 0.0},
+    "speed_encoder": {"dims": [1, 512, 512], "act": "relu", "l_act": False, "bn": False, "dropout": 0.0},
+    "command_encoder": {"dims": [6, 512, 512], "act": "relu", "l_act": False, "bn": False, "dropout": 0.0},
+    "speed_prediction": {"dims": [1536, 512, 512, 1], "act": "relu", "l_act": False, "bn": False, "dropout": 0.0},
+    "backbone": {"type": "rgb", "n_frames": 4, "rgb": {"arch": "resnet18", "pretrained": False, "gamma": 2, "b": 1}},
+    "punet": {"past_frames": 4, "future_frames": 6, "in_features": 3, "num_classes": 23, "gamma": 2, "b": 1,
+              "unet_inter_repr": False, "model_name": "unet", "model_path": ""},
+    "pmoe": {"moe_dir": "", "punet_dir": ""}, "punet_path": "", "device": "cpu",
+}

@@ -1,0 +1,653 @@
+// Tensor-core implicit-GEMM convolution for sm_100a: TMA-staged NHWC tiles -> tcgen05.mma with the
+// fp32 accumulator in TMEM -> fused epilogue (per-channel affine = folded BN / bias, residual add,
+// activation, BN batch statistics, per-image channel sums for ECA / global avg-pool) -> bf16 NHWC
+// via TMA store.
+//
+// GEMM view: M = output pixels (one 128-row tile = a BH x BW spatial patch of one image),
+// N = output channels, K = list of "segments" (source view, spatial tap, channel range). The
+// segment list is what makes one kernel serve 3x3 / 1x1 convs, virtual concat of several sources
+// (U-Net skip connections, the PU-Net mask ring), stride-2 convs (parity views), ConvTranspose2d
+// k2s2 (pixel-shuffle output views), data-gradients (flipped taps) and linear layers (1x1 conv).
+// Zero padding comes from TMA out-of-bounds fill; partial tiles are clipped by the TMA store.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
+// Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+#include "host_util.h"
+#include "ptx.cuh"
+
+#include <initializer_list>
+#include <string.h>
+
+namespace pmoe {
+
+struct TcSeg {
+  int8_t src, dh, dw, pad;
+  uint16_t c0, nchunks;
+};
+
+struct alignas(64) ConvTcParams {
+  CUtensorMap tm_src[PMOE_MAX_SRC];
+  CUtensorMap tm_w;
+  CUtensorMap tm_out;
+  TcSeg seg[PMOE_MAX_SEG];
+  int n_seg, kiters;
+  int tiles_w, tiles_h, tiles_n, n_img;
+  int bw, bh, H, W;
+  long long total_tiles;
+  const float* scale;
+  const float* shift;
+  int act;
+  int res_c;
+  const __nv_bfloat16* res;
+  long long res_sn, res_sh, res_sw;
+  float* stat_sum;
+  float* stat_sq;
+  float* pool_sum;
+  int cout_pad;
+};
+
+constexpr int kMaxStatC = 512;
+constexpr int kNumThreads = 192;
+constexpr int kEpiThreads = 128;
+
+template <int BN, int CK>
+struct TcCfg {
+  static constexpr int OCW = BN < 64 ? BN : 64;   // channels per TMA store box
+  static constexpr int SUB = OCW < 32 ? OCW : 32; // columns per tcgen05.ld
+  static constexpr int A_BYTES = 128 * CK * 2;
+  static constexpr int B_BYTES = BN * CK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int OUT_BYTES = 128 * OCW * 2;
+  static constexpr int BUDGET = 196 * 1024;
+  static constexpr int STAGES_RAW = (BUDGET - 2 * OUT_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int PIPE_BYTES = ((STAGES * STAGE_BYTES + 1023) / 1024) * 1024;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr uint32_t LAYOUT = CK == 64 ? kLayoutSW128 : (CK == 32 ? kLayoutSW64 : kLayoutSW32);
+  static constexpr uint32_t SBO = 8 * CK * 2;  // 8 rows of one swizzle span
+  static constexpr int AUX_FLOATS = 3 * BN + 2 * kMaxStatC;
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + PIPE_BYTES + 2 * OUT_BYTES + AUX_FLOATS * 4 +
+                                    (2 * STAGES + 4) * 8 + 16;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case PMOE_ACT_RELU: return fmaxf(x, 0.f);
+    case PMOE_ACT_ELU: return x > 0.f ? x : expm1f(x);
+    case PMOE_ACT_TANH: return tanhf(x);
+    case PMOE_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+    default: return x;
+  }
+}
+
+// Column sums over the 32 rows held by a warp (row = lane, NC columns per lane) with a
+// transpose-reduce butterfly: 31 (NC=32) shuffles instead of 32*5. Lane c ends with column c.
+template <int NC>
+__device__ __forceinline__ float warp_col_sums(float (&v)[NC], int lane) {
+  if constexpr (NC == 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+  }
+#pragma unroll
+  for (int off = (NC == 32 ? 16 : 8); off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN, int CK>
+__global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  using C = TcCfg<BN, CK>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* pipe = smem;
+  uint8_t* out_stage = smem + C::PIPE_BYTES;
+  float* s_scale = reinterpret_cast<float*>(out_stage + 2 * C::OUT_BYTES);
+  float* s_shift = s_scale + BN;
+  float* s_pool = s_shift + BN;
+  float* s_sum = s_pool + BN;
+  float* s_sq = s_sum + kMaxStatC;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_sq + kMaxStatC);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&p.tm_w);
+    tma_prefetch_desc(&p.tm_out);
+    tma_prefetch_desc(&p.tm_src[0]);
+  }
+  if (warp == 2) {
+    tmem_alloc(s_tmem, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < BN; i += kNumThreads) s_pool[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * kMaxStatC; i += kNumThreads) s_sum[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  const long long G = gridDim.x;
+  const long long t_begin = (p.total_tiles * (long long)blockIdx.x) / G;
+  const long long t_end = (p.total_tiles * (long long)(blockIdx.x + 1)) / G;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (long long t = t_begin; t < t_end; ++t) {
+        const int nt = (int)(t % p.tiles_n);
+        const long long mt = t / p.tiles_n;
+        const int img = (int)(mt / tiles_per_img);
+        const int rem = (int)(mt % tiles_per_img);
+        const int h0 = (rem / p.tiles_w) * p.bh;
+        const int w0 = (rem % p.tiles_w) * p.bw;
+        int kofs = 0;
+        for (int sidx = 0; sidx < p.n_seg; ++sidx) {
+          const TcSeg sg = p.seg[sidx];
+          for (int c = 0; c < sg.nchunks; ++c) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* a_dst = pipe + stage * C::STAGE_BYTES;
+            mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.bw * p.bh * CK * 2 + C::B_BYTES));
+            tma_load_4d(a_dst, &p.tm_src[sg.src], &full_bar[stage], sg.c0 + c * CK, w0 + sg.dw, h0 + sg.dh, img);
+            tma_load_2d(a_dst + C::A_BYTES, &p.tm_w, &full_bar[stage], kofs, nt * BN);
+            kofs += CK;
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t titer = 0;
+      for (long long t = t_begin; t < t_end; ++t, ++titer) {
+        const uint32_t acc = titer & 1u;
+        const uint32_t acc_phase = (titer >> 1) & 1u;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int it = 0; it < p.kiters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(pipe + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < CK / 16; ++k) {
+            const uint64_t adesc = umma_desc_kmajor(a_addr + k * 32, C::SBO, C::LAYOUT);
+            const uint64_t bdesc = umma_desc_kmajor(b_addr + k * 32, C::SBO, C::LAYOUT);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int e = threadIdx.x - 64;         // 0..127
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;       // accumulator row == pixel index inside the tile
+    const bool issuer = (e == 0);
+    const int ti = row / p.bw, tj = row % p.bw;
+    const bool row_in_box = row < p.bw * p.bh;
+    constexpr int ROWB = C::OCW * 2;
+    constexpr uint32_t SWMASK = ROWB == 128 ? 7u : (ROWB == 64 ? 3u : 1u);
+    uint32_t titer = 0;
+    uint32_t nstore = 0;
+    for (long long t = t_begin; t < t_end; ++t, ++titer) {
+      const int nt = (int)(t % p.tiles_n);
+      const long long mt = t / p.tiles_n;
+      const int img = (int)(mt / tiles_per_img);
+      const int rem = (int)(mt % tiles_per_img);
+      const int h0 = (rem / p.tiles_w) * p.bh;
+      const int w0 = (rem % p.tiles_w) * p.bw;
+      const int n0 = nt * BN;
+      const bool valid = row_in_box && (h0 + ti < p.H) && (w0 + tj < p.W);
+      const uint32_t acc = titer & 1u;
+      const uint32_t acc_phase = (titer >> 1) & 1u;
+
+      for (int i = e; i < BN; i += kEpiThreads) {
+        s_scale[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.f;
+        s_shift[i] = p.shift ? __ldg(p.shift + n0 + i) : 0.f;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+
+      const __nv_bfloat16* res_row = nullptr;
+      if (p.res != nullptr && valid)
+        res_row = p.res + (long long)img * p.res_sn + (long long)(h0 + ti) * p.res_sh + (long long)(w0 + tj) * p.res_sw;
+
+#pragma unroll 1
+      for (int ch = 0; ch < BN / C::OCW; ++ch) {
+        uint8_t* obuf = out_stage + (nstore & 1u) * C::OUT_BYTES;
+        if (issuer) tma_store_wait_read<1>();  // the store that last used this buffer has drained
+        named_bar_sync(1, kEpiThreads);
+#pragma unroll
+        for (int sb = 0; sb < C::OCW / C::SUB; ++sb) {
+          const int cb = ch * C::OCW + sb * C::SUB;  // column offset inside the N tile
+          uint32_t raw[C::SUB];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cb;
+          if constexpr (C::SUB == 32) tmem_ld_32x32(taddr, raw);
+          else tmem_ld_32x16(taddr, raw);
+          tmem_ld_wait();
+          float y[C::SUB];
+#pragma unroll
+          for (int k = 0; k < C::SUB; ++k) y[k] = fmaf(__uint_as_float(raw[k]), s_scale[cb + k], s_shift[cb + k]);
+          if (p.stat_sum != nullptr) {
+            float a[C::SUB], b[C::SUB];
+#pragma unroll
+            for (int k = 0; k < C::SUB; ++k) {
+              const float f = valid ? __uint_as_float(raw[k]) : 0.f;
+              a[k] = f;
+              b[k] = f * f;
+            }
+            const float sa = warp_col_sums<C::SUB>(a, lane);
+            const float sq = warp_col_sums<C::SUB>(b, lane);
+            if (lane < C::SUB && n0 + cb + lane < kMaxStatC) {
+              atomicAdd(&s_sum[n0 + cb + lane], sa);
+              atomicAdd(&s_sq[n0 + cb + lane], sq);
+            }
+          }
+          if (res_row != nullptr) {
+#pragma unroll
+            for (int q = 0; q < C::SUB / 8; ++q) {
+              if (n0 + cb + q * 8 < p.res_c) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + cb + q * 8));
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float2 f2 = __bfloat1622float2(r2[u]);
+                  y[q * 8 + 2 * u] += f2.x;
+                  y[q * 8 + 2 * u + 1] += f2.y;
+                }
+              }
+            }
+          }
+          if (p.act != PMOE_ACT_NONE) {
+#pragma unroll
+            for (int k = 0; k < C::SUB; ++k) y[k] = apply_act(y[k], p.act);
+          }
+          // bf16 pack -> swizzled staging tile (row = pixel, ROWB bytes per row)
+#pragma unroll
+          for (int q = 0; q < C::SUB / 8; ++q) {
+            uint4 pk;
+            pk.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
+            pk.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
+            pk.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
+            pk.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
+            uint32_t off = (uint32_t)row * ROWB + (uint32_t)(sb * C::SUB + q * 8) * 2u;
+            off ^= ((off >> 7) & SWMASK) << 4;
+            *reinterpret_cast<uint4*>(obuf + off) = pk;
+          }
+          if (p.pool_sum != nullptr) {
+            // pool what is actually stored (bf16-rounded), masked to valid pixels
+            float a[C::SUB];
+#pragma unroll
+            for (int k = 0; k < C::SUB; ++k) a[k] = valid ? __bfloat162float(__float2bfloat16_rn(y[k])) : 0.f;
+            const float sa = warp_col_sums<C::SUB>(a, lane);
+            if (lane < C::SUB) atomicAdd(&s_pool[cb + lane], sa);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, kEpiThreads);
+        if (issuer) {
+          tma_store_4d(&p.tm_out, obuf, n0 + ch * C::OCW, w0, h0, img);
+          tma_store_commit();
+        }
+        ++nstore;
+      }
+      // accumulator stage fully read -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (p.pool_sum != nullptr) {
+        named_bar_sync(3, kEpiThreads);
+        for (int i = e; i < BN; i += kEpiThreads) {
+          const float v = s_pool[i];
+          if (v != 0.f) atomicAdd(p.pool_sum + (long long)img * p.cout_pad + n0 + i, v);
+          s_pool[i] = 0.f;
+        }
+      }
+    }
+    if (issuer) tma_store_wait_read<0>();
+    if (p.stat_sum != nullptr) {
+      named_bar_sync(3, kEpiThreads);
+      const int nc = p.cout_pad < kMaxStatC ? p.cout_pad : kMaxStatC;
+      for (int i = e; i < nc; i += kEpiThreads) {
+        atomicAdd(p.stat_sum + i, s_sum[i]);
+        atomicAdd(p.stat_sq + i, s_sq[i]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static void choose_tile(int H, int W, int* bh_out, int* bw_out) {
+  // fewest 128-row tiles first, then the smallest halo (squarer patches re-use more of L2)
+  long long best_tiles = -1, best_halo = 0;
+  int best_bw = 1, best_bh = 1;
+  const int wmax = W < 128 ? W : 128;
+  for (int bw = 1; bw <= wmax; ++bw) {
+    int bh = 128 / bw;
+    if (bh > H) bh = H;
+    if (bh < 1) continue;
+    const long long tiles = (long long)((W + bw - 1) / bw) * ((H + bh - 1) / bh);
+    const long long halo = (long long)(bw + 2) * (bh + 2);
+    if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && halo < best_halo)) {
+      best_tiles = tiles;
+      best_halo = halo;
+      best_bw = bw;
+      best_bh = bh;
+    }
+  }
+  *bh_out = best_bh;
+  *bw_out = best_bw;
+}
+
+static int make_view_tmap(CUtensorMap* tm, const PmoeView4& v, int box_c, int bw, int bh, CUtensorMapSwizzle swz,
+                          const char* what) {
+  if (((uintptr_t)v.ptr & 15) || (v.sw % 8) || (v.sh % 8) || (v.sn % 8) || (v.c % 8)) {
+    set_error("%s: view must be 16-byte aligned with strides/channels in multiples of 8 elements (ptr %p c %d sw %lld sh "
+              "%lld sn %lld)",
+              what, v.ptr, v.c, (long long)v.sw, (long long)v.sh, (long long)v.sn);
+    return PMOE_ERR_ARG;
+  }
+  const uint64_t dims[4] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.n};
+  const uint64_t strides[3] = {(uint64_t)v.sw * 2, (uint64_t)v.sh * 2, (uint64_t)v.sn * 2};
+  const uint32_t box[4] = {(uint32_t)box_c, (uint32_t)bw, (uint32_t)bh, 1u};
+  return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, v.ptr, dims, strides, box, swz);
+}
+
+static CUtensorMapSwizzle swizzle_for_bytes(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+template <int BN, int CK>
+static int launch_tc(const ConvTcParams& p, cudaStream_t stream) {
+  using C = TcCfg<BN, CK>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("conv_tc<%d,%d>: cannot reserve %d bytes of shared memory: %s", BN, CK, C::SMEM_BYTES, cudaGetErrorString(e));
+      return PMOE_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  long long grid = p.total_tiles < (long long)num_sms() ? p.total_tiles : (long long)num_sms();
+  conv_tc_kernel<BN, CK><<<(unsigned)grid, kNumThreads, C::SMEM_BYTES, stream>>>(p);
+  return check_launch("conv_tc");
+}
+
+template <int BN>
+static int launch_tc_ck(const ConvTcParams& p, int ck, cudaStream_t stream) {
+  switch (ck) {
+    case 64: return launch_tc<BN, 64>(p, stream);
+    case 32: return launch_tc<BN, 32>(p, stream);
+    case 16: return launch_tc<BN, 16>(p, stream);
+  }
+  set_error("conv_tc: ck must be 16, 32 or 64 (got %d)", ck);
+  return PMOE_ERR_ARG;
+}
+
+}  // namespace pmoe
+
+using namespace pmoe;
+
+extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!d || d->n_src < 1 || d->n_src > PMOE_MAX_SRC || d->n_seg < 1 || d->n_seg > PMOE_MAX_SEG || !d->wpack || !d->out.ptr) {
+    set_error("conv_tc: bad descriptor (n_src %d n_seg %d)", d ? d->n_src : -1, d ? d->n_seg : -1);
+    return PMOE_ERR_ARG;
+  }
+  if (d->ck != 16 && d->ck != 32 && d->ck != 64) {
+    set_error("conv_tc: ck must be 16, 32 or 64 (got %d)", d->ck);
+    return PMOE_ERR_ARG;
+  }
+  int bn = 0;
+  for (int cand : {256, 128, 64, 32, 16})
+    if (d->cout_pad % cand == 0) {
+      bn = cand;
+      break;
+    }
+  if (bn == 0 || d->cout_pad <= 0) {
+    set_error("conv_tc: cout_pad (%d) must be a positive multiple of 16", d->cout_pad);
+    return PMOE_ERR_ARG;
+  }
+  if ((d->stat_sum != nullptr) != (d->stat_sqsum != nullptr) || (d->stat_sum && d->cout_pad > kMaxStatC)) {
+    set_error("conv_tc: batch statistics need both buffers and cout_pad <= %d", kMaxStatC);
+    return PMOE_ERR_ARG;
+  }
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  const PmoeView4& o = d->out;
+  choose_tile(o.h, o.w, &p.bh, &p.bw);
+  p.H = o.h;
+  p.W = o.w;
+  p.n_img = o.n;
+  p.tiles_w = (o.w + p.bw - 1) / p.bw;
+  p.tiles_h = (o.h + p.bh - 1) / p.bh;
+  p.tiles_n = d->cout_pad / bn;
+  p.total_tiles = (long long)p.tiles_w * p.tiles_h * p.n_img * p.tiles_n;
+  if (p.total_tiles <= 0) {
+    set_error("conv_tc: empty output");
+    return PMOE_ERR_ARG;
+  }
+  int kiters = 0;
+  for (int i = 0; i < d->n_seg; ++i) {
+    const PmoeSeg& s = d->seg[i];
+    if (s.src < 0 || s.src >= d->n_src || s.nchunks == 0 || s.c0 + s.nchunks * d->ck > d->src[s.src].c) {
+      set_error("conv_tc: segment %d out of range (src %d c0 %d nchunks %d ck %d, source has %d channels)", i, s.src, s.c0,
+                s.nchunks, d->ck, (s.src >= 0 && s.src < d->n_src) ? d->src[s.src].c : -1);
+      return PMOE_ERR_ARG;
+    }
+    p.seg[i].src = s.src;
+    p.seg[i].dh = s.dh;
+    p.seg[i].dw = s.dw;
+    p.seg[i].c0 = s.c0;
+    p.seg[i].nchunks = s.nchunks;
+    kiters += s.nchunks;
+  }
+  if (kiters * d->ck != d->ktot) {
+    set_error("conv_tc: ktot %d does not match the segment list (%d chunks of %d)", d->ktot, kiters, d->ck);
+    return PMOE_ERR_ARG;
+  }
+  p.n_seg = d->n_seg;
+  p.kiters = kiters;
+  const CUtensorMapSwizzle swz_in = swizzle_for_bytes(d->ck * 2);
+  int rc;
+  for (int i = 0; i < d->n_src; ++i) {
+    if ((rc = make_view_tmap(&p.tm_src[i], d->src[i], d->ck, p.bw, p.bh, swz_in, "conv_tc source")) != PMOE_OK) return rc;
+  }
+  {
+    if ((uintptr_t)d->wpack & 15) {
+      set_error("conv_tc: wpack must be 16-byte aligned");
+      return PMOE_ERR_ARG;
+    }
+    const uint64_t dims[2] = {(uint64_t)d->ktot, (uint64_t)d->cout_pad};
+    const uint64_t strides[1] = {(uint64_t)d->ktot * 2};
+    const uint32_t box[2] = {(uint32_t)d->ck, (uint32_t)bn};
+    if ((rc = encode_tmap(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->wpack), dims, strides, box,
+                          swz_in)) != PMOE_OK)
+      return rc;
+  }
+  const int ocw = bn < 64 ? bn : 64;
+  if ((rc = make_view_tmap(&p.tm_out, o, ocw, p.bw, p.bh, swizzle_for_bytes(ocw * 2), "conv_tc output")) != PMOE_OK) return rc;
+  p.scale = d->scale;
+  p.shift = d->shift;
+  p.act = d->act;
+  if (d->residual.ptr) {
+    const PmoeView4& r = d->residual;
+    if (r.n != o.n || r.h != o.h || r.w != o.w || ((uintptr_t)r.ptr & 15) || (r.sw % 8) || (r.sh % 8) || (r.sn % 8)) {
+      set_error("conv_tc: residual view must match the output geometry and be 16-byte aligned");
+      return PMOE_ERR_ARG;
+    }
+    p.res = static_cast<const __nv_bfloat16*>(r.ptr);
+    p.res_sn = r.sn;
+    p.res_sh = r.sh;
+    p.res_sw = r.sw;
+    p.res_c = r.c;
+  }
+  p.stat_sum = d->stat_sum;
+  p.stat_sq = d->stat_sqsum;
+  p.pool_sum = d->pool_sum;
+  p.cout_pad = d->cout_pad;
+  switch (bn) {
+    case 256: return launch_tc_ck<256>(p, d->ck, stream);
+    case 128: return launch_tc_ck<128>(p, d->ck, stream);
+    case 64: return launch_tc_ck<64>(p, d->ck, stream);
+    case 32: return launch_tc_ck<32>(p, d->ck, stream);
+    default: return launch_tc_ck<16>(p, d->ck, stream);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ probe
+namespace pmoe {
+struct alignas(64) DbgParams {
+  CUtensorMap tm_a, tm_b;
+  int rows, start_row, group_rows, bo_mode;
+  float* d_out;
+};
+
+__global__ void __launch_bounds__(128, 1) dbg_umma_view_kernel(const __grid_constant__ DbgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;                // up to 384 rows * 128 B
+  uint8_t* sb = smem + 384 * 128;    // 64 rows * 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sb + 64 * 128);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(s_tmem, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(&bars[0], (uint32_t)(p.rows * 128 + 64 * 128));
+    // A is loaded in slabs of <=128 rows (box height limit is 256; keep it simple)
+    for (int r = 0; r < p.rows; r += 128) tma_load_2d(sa + r * 128, &p.tm_a, &bars[0], 0, r);
+    tma_load_2d(sb, &p.tm_b, &bars[0], 0, 0);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    const uint32_t a_addr = smem_u32(sa) + (uint32_t)p.start_row * 128u;
+    const uint32_t b_addr = smem_u32(sb);
+    const uint32_t bo = p.bo_mode == 1 ? ((a_addr >> 7) & 7u) : 0u;
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t adesc = umma_desc_kmajor(a_addr + k * 32, (uint32_t)p.group_rows * 128u, kLayoutSW128, bo);
+      const uint64_t bdesc = umma_desc_kmajor(b_addr + k * 32, 1024u, kLayoutSW128, 0);
+      umma_bf16(tmem_base, adesc, bdesc, idesc, k != 0 ? 1u : 0u);
+    }
+    umma_commit(&bars[1]);
+  }
+  __syncwarp();
+  mbar_wait(&bars[1], 0);
+  tc_fence_after();
+  for (int sbk = 0; sbk < 2; ++sbk) {
+    uint32_t raw[32];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + sbk * 32, raw);
+    tmem_ld_wait();
+    float* o = p.d_out + (warp * 32 + lane) * 64 + sbk * 32;
+    for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(raw[k]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+}  // namespace pmoe
+
+extern "C" int pmoe_dbg_umma_view(const void* a_bf16, int rows, const void* b_bf16, float* d_out, int start_row,
+                                  int group_rows, int base_offset_mode, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (rows < 128 || rows > 384 || rows % 128 != 0) {
+    set_error("dbg_umma_view: rows must be 128, 256 or 384");
+    return PMOE_ERR_ARG;
+  }
+  if (start_row + 15 * group_rows + 8 > rows) {
+    set_error("dbg_umma_view: view exceeds the loaded tile");
+    return PMOE_ERR_ARG;
+  }
+  DbgParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  {
+    const uint64_t dims[2] = {64, (uint64_t)rows};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {64, 128};
+    if ((rc = encode_tmap(&p.tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(a_bf16), dims, strides, box,
+                          CU_TENSOR_MAP_SWIZZLE_128B)) != PMOE_OK)
+      return rc;
+  }
+  {
+    const uint64_t dims[2] = {64, 64};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {64, 64};
+    if ((rc = encode_tmap(&p.tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(b_bf16), dims, strides, box,
+                          CU_TENSOR_MAP_SWIZZLE_128B)) != PMOE_OK)
+      return rc;
+  }
+  p.rows = rows;
+  p.start_row = start_row;
+  p.group_rows = group_rows;
+  p.bo_mode = base_offset_mode;
+  p.d_out = d_out;
+  const int smem_bytes = 1024 + 384 * 128 + 64 * 128 + 64;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(dbg_umma_view_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    configured = true;
+  }
+  dbg_umma_view_kernel<<<1, 128, smem_bytes, stream>>>(p);
+  return check_launch("dbg_umma_view");
+}

@@ -1,0 +1,106 @@
+"""Host-side wrappers over the C-ABI: weight packing, segment lists and launch helpers.
+
+Everything here prepares descriptors; all arithmetic happens in libpmoe_b200.so on the GPU.
+Activation tensors are NHWC torch tensors (N,H,W,Cpad) whose channel count is padded to a
+multiple of 16 with zeros (`pad_ch`).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT
+
+
+def pad_ch(c):
+    return (int(c) + 15) // 16 * 16
+
+
+def choose_ck(cpads):
+    for ck in (64, 32, 16):
+        if all(c % ck == 0 for c in cpads):
+            return ck
+    raise ValueError("channel counts must be multiples of 16: %r" % (cpads,))
+
+
+def cout_padded(cout):
+    """Rows of the packed weight: a multiple of the N tile the kernel will pick."""
+    c = pad_ch(cout)
+    if c > 256:
+        c = (c + 255) // 256 * 256
+    elif c > 128:
+        c = 256
+    elif c > 64:
+        c = 128
+    elif c > 32:
+        c = 64
+    return c
+
+
+def pack_conv_weight(w, src_channels, src_cpads, taps, cout_pad, dtype=torch.bfloat16):
+    """w: (Cout, sum(src_channels), R, S). Returns [cout_pad, ktot] with K enumerating
+    (tap, source, padded channel) — the order `conv_segments` emits."""
+    cout = w.shape[0]
+    cols = []
+    for (r, s) in taps:
+        c_begin = 0
+        for c, cp in zip(src_channels, src_cpads):
+            blk = w[:, c_begin:c_begin + c, r, s]
+            if cp > c:
+                blk = torch.nn.functional.pad(blk, (0, cp - c))
+            cols.append(blk)
+            c_begin += c
+    wp = torch.cat(cols, dim=1)
+    if cout_pad > cout:
+        wp = torch.nn.functional.pad(wp, (0, 0, 0, cout_pad - cout))
+    return wp.to(dtype).contiguous()
+
+
+def conv_segments(taps_dhdw, src_cpads, ck):
+    """[(src, dh, dw, c0, nchunks)] for each tap x source."""
+    segs = []
+    for (dh, dw) in taps_dhdw:
+        for i, cp in enumerate(src_cpads):
+            segs.append((i, dh, dw, 0, cp // ck))
+    return segs
+
+
+TAPS3 = [(r, s) for r in range(3) for s in range(3)]
+
+
+def pad_vec(v, n, fill=0.0):
+    out = torch.full((n,), fill, dtype=torch.float32, device=v.device)
+    out[: v.numel()] = v.float()
+    return out
+
+
+def conv_tc(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residual=None, stat_sum=None,
+            stat_sqsum=None, pool_sum=None, src_channels=None):
+    """Launch the tcgen05 implicit-GEMM kernel. srcs: list of NHWC bf16 tensors (views allowed);
+    out: NHWC bf16 tensor/view; wpack: [cout_pad, ktot] bf16."""
+    d = _lib.ConvTc()
+    assert 1 <= len(srcs) <= _lib.MAX_SRC and 1 <= len(segs) <= _lib.MAX_SEG, (len(srcs), len(segs))
+    d.n_src = len(srcs)
+    for i, s in enumerate(srcs):
+        _lib.require_cuda(s, "conv source")
+        assert s.dtype == torch.bfloat16
+        d.src[i] = _lib.view4(s, None if src_channels is None else src_channels[i])
+    d.n_seg = len(segs)
+    for i, (src, dh, dw, c0, nch) in enumerate(segs):
+        d.seg[i].src, d.seg[i].dh, d.seg[i].dw, d.seg[i].c0, d.seg[i].nchunks = src, dh, dw, c0, nch
+    d.ck = ck
+    d.ktot = wpack.shape[1]
+    d.cout_pad = wpack.shape[0]
+    assert wpack.dtype == torch.bfloat16 and wpack.is_contiguous()
+    d.wpack = wpack.data_ptr()
+    assert out.dtype == torch.bfloat16
+    d.out = _lib.view4(out)
+    d.scale = None if scale is None else scale.data_ptr()
+    d.shift = None if shift is None else shift.data_ptr()
+    d.act = ACT[act]
+    d.residual = _lib.view4(residual) if residual is not None else _lib.null_view()
+    d.stat_sum = None if stat_sum is None else stat_sum.data_ptr()
+    d.stat_sqsum = None if stat_sqsum is None else stat_sqsum.data_ptr()
+    d.pool_sum = None if pool_sum is None else pool_sum.data_ptr()
+    _lib.check(_lib.lib().pmoe_conv_tc(C.byref(d), _lib.stream_ptr()), "conv_tc")
+    return out

@@ -186,7 +186,8 @@ def expert(images, speed, command, sd, p, cfg, train, alt=False):
 
 def moe(images, speed, command, sd, p, cfg, train):
     """moe.py:140-158 -> (probs (B,K), mean (B,K,2), std (B,K,2), speeds (B,K,1))."""
-    outs = [expert(images, speed, command, sd, p + "moe.%d." % k, cfg, train, cfg["type"] == "moe_alt")
+    # moe.py:136: every type other than 'moe' (moe_alt, and PMoE's inner mixture) builds BaseExpertAlt
+    outs = [expert(images, speed, command, sd, p + "moe.%d." % k, cfg, train, cfg["type"] != "moe")
             for k in range(cfg["n_experts"])]
     probs = F.softmax(torch.cat([o[0] for o in outs], dim=1), dim=1)
     return probs, torch.stack([o[1] for o in outs], 1), torch.stack([o[2] for o in outs], 1), torch.stack([o[3] for o in outs], 1)
@@ -257,7 +258,7 @@ def class_dice_weights(pred, target, eps=1e-6):
     """loss.py:6-17 — 1 - dice per class from argmax predictions (no gradient)."""
     nc = pred.shape[1]
     pc = pred.argmax(1)
-    w = torch.ones(nc, dtype=torch.float32)
+    w = torch.ones(nc, dtype=pred.dtype)
     for c in range(nc):
         pm, tm = pc == c, target == c
         inter = (pm & tm).sum().float() + eps
@@ -270,7 +271,9 @@ def tversky(pred, target, alpha=0.5, beta=0.5):
     """loss.py:34-44."""
     oh = F.one_hot(target, pred.shape[1]).movedim(-1, 1).to(pred.dtype)
     pr = F.softmax(pred, 1)
-    dims = (0,) + tuple(range(2, target.dim() + 1))
+    # loss.py:40: range(2, target.ndimension()) with a (B,H,W) target is (0, 2) only — the sums run over
+    # batch and HEIGHT, leaving a (C, W) ratio map that is then averaged. Reproduced, not "fixed".
+    dims = (0,) + tuple(range(2, target.dim()))
     tp = (pr * oh).sum(dims)
     fp = (pr * (1 - oh)).sum(dims)
     fn = ((1 - pr) * oh).sum(dims)
@@ -389,7 +392,7 @@ def expert_spec(spec, p, cfg, alt=False):
 
 def moe_spec(spec, p, cfg):
     for k in range(cfg["n_experts"]):
-        expert_spec(spec, p + "moe.%d." % k, cfg, cfg["type"] == "moe_alt")
+        expert_spec(spec, p + "moe.%d." % k, cfg, cfg["type"] != "moe")
 
 
 def moe_shared_spec(spec, p, cfg):

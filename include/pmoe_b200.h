@@ -70,10 +70,37 @@ typedef struct PmoeConvTc {
   PmoeView4 residual; /* bf16, ptr NULL = none; added before the activation */
   float* stat_sum;    /* optional [cout_pad]: += sum over valid pixels of the raw accumulator   */
   float* stat_sqsum;  /* optional [cout_pad]: += sum of squares (train-mode BN batch statistics) */
-  float* pool_sum;    /* optional [n][cout_pad]: += per-image sum of the stored output (ECA / avgpool) */
+  float* pool_sum;    /* optional [n][pool_stride]: += per-image sum of the stored output (ECA / avgpool) */
+  int32_t pool_stride; /* row stride of pool_sum in floats; 0 = cout_pad */
 } PmoeConvTc;
 
 int pmoe_conv_tc(const PmoeConvTc* desc, pmoe_stream_t stream);
+
+/* ---- memory-bound kernels (eltwise.cu); dtype = PMOE_F32 | PMOE_BF16 of the NHWC views ------------- */
+/* Module boundary: the reference hands fp32 NCHW tensors to forward() (model/moe.py:90-93, punet.py:88). */
+int pmoe_nchw_to_nhwc(const float* src, int64_t sn, int64_t sc, int64_t sh, int64_t sw, int32_t c, const PmoeView4* dst,
+                      int32_t dst_dtype, pmoe_stream_t stream);
+int pmoe_nhwc_to_nchw(const PmoeView4* src, int32_t src_dtype, int32_t c, float* dst, int64_t dn, int64_t dc, int64_t dh,
+                      int64_t dw, pmoe_stream_t stream);
+/* nn.MaxPool2d(2,2) (unet.py:29) / MaxPool2d(3,2,1) (torchvision ResNet), optionally applying
+ * relu(scale*x+shift) on load (eval-mode bn1+relu of the ResNet stem, backbone.py:63). */
+int pmoe_maxpool(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, int32_t k, int32_t stride, int32_t pad,
+                 const float* scale, const float* shift, int32_t relu, pmoe_stream_t stream);
+/* EfficientBlock (basics.py:62-77): gate = sigmoid(conv1d_k(mean_hw(x))) from per-image channel sums. */
+int pmoe_eca_gate(const float* pool_sum, int64_t pool_stride, int32_t n, float inv_count, const float* w, int32_t k,
+                  int32_t groups, int32_t group_c, int32_t group_stride, float* gate, int64_t gate_stride,
+                  pmoe_stream_t stream);
+int pmoe_scale_channels(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, const float* gate, int64_t gate_stride,
+                        pmoe_stream_t stream);
+/* out[n][c] += sum over h,w (adaptive_avg_pool2d numerator, basics.py:72, unet.py:90). */
+int pmoe_channel_sums(const PmoeView4* src, int32_t dtype, float* out, int64_t out_stride, pmoe_stream_t stream);
+/* nn.BatchNorm2d training step (basics.py:52,55): batch stats from (sum, sumsq), running-stat update, fused affine. */
+int pmoe_bn_finalize(const float* sum, const float* sqsum, float count, int32_t c, int32_t c_pad, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* mean_out,
+                     float* rstd_out, float* scale, float* shift, pmoe_stream_t stream);
+/* y = act(scale[c]*x + shift[c] (+ residual)): BN apply + ReLU (+ BasicBlock residual add). */
+int pmoe_affine_act(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, const float* scale, const float* shift,
+                    const PmoeView4* residual, int32_t act, pmoe_stream_t stream);
 
 /* Library info / errors. */
 int pmoe_version(void);

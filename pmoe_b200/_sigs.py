@@ -1,4 +1,15 @@
-"""argtypes of the remaining C-ABI entry points (filled in as kernels land)."""
+"""argtypes of the C-ABI entry points other than pmoe_conv_tc (see include/pmoe_b200.h)."""
 import ctypes as C
 
-SIGS = {}
+vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+SIGS = {
+    "pmoe_nchw_to_nhwc": [vp, i64, i64, i64, i64, i32, vp, i32, vp],
+    "pmoe_nhwc_to_nchw": [vp, i32, i32, vp, i64, i64, i64, i64, vp],
+    "pmoe_maxpool": [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp],
+    "pmoe_eca_gate": [vp, i64, i32, f32, vp, i32, i32, i32, i32, vp, i64, vp],
+    "pmoe_scale_channels": [vp, vp, i32, vp, i64, vp],
+    "pmoe_channel_sums": [vp, i32, vp, i64, vp],
+    "pmoe_bn_finalize": [vp, vp, f32, i32, i32, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp],
+    "pmoe_affine_act": [vp, vp, i32, vp, vp, vp, i32, vp],
+}

@@ -44,6 +44,7 @@ struct alignas(64) ConvTcParams {
   float* stat_sq;
   float* pool_sum;
   int cout_pad;
+  int pool_stride;
 };
 
 constexpr int kMaxStatC = 512;
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         named_bar_sync(3, kEpiThreads);
         for (int i = e; i < BN; i += kEpiThreads) {
           const float v = s_pool[i];
-          if (v != 0.f) atomicAdd(p.pool_sum + (long long)img * p.cout_pad + n0 + i, v);
+          if (v != 0.f) atomicAdd(p.pool_sum + (long long)img * p.pool_stride + n0 + i, v);
           s_pool[i] = 0.f;
         }
       }
@@ -532,6 +533,7 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   p.stat_sq = d->stat_sqsum;
   p.pool_sum = d->pool_sum;
   p.cout_pad = d->cout_pad;
+  p.pool_stride = d->pool_stride > 0 ? d->pool_stride : d->cout_pad;
   switch (bn) {
     case 256: return launch_tc_ck<256>(p, d->ck, stream);
     case 128: return launch_tc_ck<128>(p, d->ck, stream);

@@ -1,0 +1,430 @@
+// Memory-bound (HBM roofline) kernels of the hot path: layout conversion at the module boundary,
+// max-pool, ECA gate + channel scale, BatchNorm finalize/apply (+residual, +ReLU). All operate on
+// strided NHWC views, 8 channels (16 B of bf16 / 32 B of fp32) per thread, grid-stride loops sized
+// to a multiple of the SM count.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace pmoe {
+
+// ---------------------------------------------------------------- 8-channel vector access
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 r;
+  r.x = pack_bf16x2(v[0], v[1]);
+  r.y = pack_bf16x2(v[2], v[3]);
+  r.z = pack_bf16x2(v[4], v[5]);
+  r.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+struct V4 {
+  void* ptr;
+  int n, h, w, c;
+  long long sn, sh, sw;
+};
+static V4 to_v4(const PmoeView4& v) { return V4{v.ptr, v.n, v.h, v.w, v.c, v.sn, v.sh, v.sw}; }
+
+static inline int grid_for(long long items, int threads) {
+  long long blocks = (items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+static int check_view(const PmoeView4* v, int dtype, const char* what) {
+  const int esz = dtype == PMOE_BF16 ? 2 : 4;
+  if (!v || !v->ptr || v->c % 8 || ((uintptr_t)v->ptr % 16) || (v->sw * esz) % 16 || (v->sh * esz) % 16 || (v->sn * esz) % 16) {
+    set_error("%s: view must be 16-byte aligned, channels a multiple of 8", what);
+    return PMOE_ERR_ARG;
+  }
+  return PMOE_OK;
+}
+
+// ---------------------------------------------------------------- NCHW fp32 -> NHWC (zero-padded channels)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, long long sn, long long sc, long long sh, long long sw,
+                                    int c, V4 dst) {
+  const int cg = dst.c / 8;
+  const long long total = (long long)dst.n * dst.h * dst.w * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    // pixel-major over threads: consecutive threads read consecutive w of one channel plane
+    const int g = (int)(i / ((long long)dst.n * dst.h * dst.w));
+    long long pix = i % ((long long)dst.n * dst.h * dst.w);
+    const int w = (int)(pix % dst.w);
+    pix /= dst.w;
+    const int h = (int)(pix % dst.h);
+    const int n = (int)(pix / dst.h);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = g * 8 + k;
+      v[k] = ch < c ? __ldg(src + n * sn + ch * sc + h * sh + w * sw) : 0.f;
+    }
+    store8(static_cast<T*>(dst.ptr) + n * dst.sn + h * dst.sh + w * dst.sw + g * 8, v);
+  }
+}
+
+// ---------------------------------------------------------------- NHWC -> NCHW fp32 (first c channels)
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(V4 src, int c, float* __restrict__ dst, long long dn, long long dc, long long dh,
+                                    long long dw) {
+  const int cg = (c + 7) / 8;
+  const long long npix = (long long)src.n * src.h * src.w;
+  const long long total = npix * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i / npix);
+    long long pix = i % npix;
+    const int w = (int)(pix % src.w);
+    pix /= src.w;
+    const int h = (int)(pix % src.h);
+    const int n = (int)(pix / src.h);
+    float v[8];
+    load8(static_cast<const T*>(src.ptr) + n * src.sn + h * src.sh + w * src.sw + g * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = g * 8 + k;
+      if (ch < c) dst[n * dn + ch * dc + h * dh + w * dw] = v[k];
+    }
+  }
+}
+
+// ---------------------------------------------------------------- max-pool (optional affine+ReLU on load)
+template <typename T>
+__global__ void maxpool_kernel(V4 src, V4 dst, int k, int stride, int pad, const float* __restrict__ scale,
+                               const float* __restrict__ shift, int relu) {
+  const int cg = dst.c / 8;
+  const long long total = (long long)dst.n * dst.h * dst.w * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long pix = i / cg;
+    const int ow = (int)(pix % dst.w);
+    pix /= dst.w;
+    const int oh = (int)(pix % dst.h);
+    const int n = (int)(pix / dst.h);
+    float sc[8], sf[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      sc[q] = scale ? __ldg(scale + g * 8 + q) : 1.f;
+      sf[q] = shift ? __ldg(shift + g * 8 + q) : 0.f;
+    }
+    float m[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+    for (int r = 0; r < k; ++r) {
+      const int ih = oh * stride - pad + r;
+      if (ih < 0 || ih >= src.h) continue;
+      for (int s = 0; s < k; ++s) {
+        const int iw = ow * stride - pad + s;
+        if (iw < 0 || iw >= src.w) continue;
+        float v[8];
+        load8(static_cast<const T*>(src.ptr) + n * src.sn + ih * src.sh + iw * src.sw + g * 8, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float x = fmaf(v[q], sc[q], sf[q]);
+          if (relu) x = fmaxf(x, 0.f);
+          m[q] = fmaxf(m[q], x);
+        }
+      }
+    }
+    store8(static_cast<T*>(dst.ptr) + n * dst.sn + oh * dst.sh + ow * dst.sw + g * 8, m);
+  }
+}
+
+// ---------------------------------------------------------------- ECA gate: sigmoid(conv1d_k(mean over HW))
+// Channels may be stored as `groups` blocks of `group_c` logical channels every `group_stride`
+// physical channels (the PU-Net mask ring stores 23 logits in 32-channel slots); the 1-D conv runs
+// over the LOGICAL channel axis with zero padding k/2 (basics.py:69,73).
+__global__ void eca_gate_kernel(const float* __restrict__ pool_sum, long long pool_stride, float inv_count,
+                                const float* __restrict__ w, int k, int groups, int group_c, int group_stride,
+                                float* __restrict__ gate, long long gate_stride) {
+  const int n = blockIdx.x;
+  const int L = groups * group_c;
+  for (int pc = threadIdx.x; pc < groups * group_stride; pc += blockDim.x) {
+    const int g = pc / group_stride, j = pc % group_stride;
+    float out = 0.f;
+    if (j < group_c) {
+      const int l = g * group_c + j;
+      float acc = 0.f;
+      for (int t = 0; t < k; ++t) {
+        const int ll = l + t - k / 2;
+        if (ll >= 0 && ll < L) {
+          const int p = (ll / group_c) * group_stride + (ll % group_c);
+          acc = fmaf(__ldg(w + t), __ldg(pool_sum + n * pool_stride + p) * inv_count, acc);
+        }
+      }
+      out = 1.f / (1.f + expf(-acc));
+    }
+    gate[n * gate_stride + pc] = out;
+  }
+}
+
+template <typename T>
+__global__ void scale_channels_kernel(V4 src, V4 dst, const float* __restrict__ gate, long long gate_stride) {
+  const int cg = dst.c / 8;
+  const long long total = (long long)dst.n * dst.h * dst.w * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long pix = i / cg;
+    const int w = (int)(pix % dst.w);
+    pix /= dst.w;
+    const int h = (int)(pix % dst.h);
+    const int n = (int)(pix / dst.h);
+    float v[8], s[8];
+    load8(static_cast<const T*>(src.ptr) + n * src.sn + h * src.sh + w * src.sw + g * 8, v);
+    load8(gate + n * gate_stride + g * 8, s);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] *= s[q];
+    store8(static_cast<T*>(dst.ptr) + n * dst.sn + h * dst.sh + w * dst.sw + g * 8, v);
+  }
+}
+
+// ---------------------------------------------------------------- per-(n,c) sums over HW (ECA / global avg-pool)
+template <typename T>
+__global__ void channel_sums_kernel(V4 src, float* __restrict__ out, long long out_stride, int rows_per_block) {
+  // grid: (ceil(h*w / rows_per_block), n); block: 256 threads = cg channel groups x (256/cg) pixel lanes
+  const int cg = src.c / 8;
+  const int lanes = blockDim.x / cg;
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+  const int n = blockIdx.y;
+  const long long hw = (long long)src.h * src.w;
+  const long long p0 = (long long)blockIdx.x * rows_per_block;
+  long long p1 = p0 + rows_per_block;
+  if (p1 > hw) p1 = hw;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (lane < lanes) {
+    for (long long p = p0 + lane; p < p1; p += lanes) {
+      const int h = (int)(p / src.w), w = (int)(p % src.w);
+      float v[8];
+      load8(static_cast<const T*>(src.ptr) + n * src.sn + h * src.sh + w * src.sw + g * 8, v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] += v[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) atomicAdd(out + n * out_stride + g * 8 + q, acc[q]);
+  }
+}
+
+// ---------------------------------------------------------------- BatchNorm (train): finalize + apply
+// Finalize: batch mean / biased var from (sum, sumsq), running-stat update exactly as
+// nn.BatchNorm2d (momentum 0.1, unbiased variance), and the fused affine (scale, shift).
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sq, float count, int c,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ scale,
+                                   float* __restrict__ shift, int c_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c_pad) return;
+  if (i >= c) {
+    if (scale) scale[i] = 0.f;
+    if (shift) shift[i] = 0.f;
+    if (mean_out) mean_out[i] = 0.f;
+    if (rstd_out) rstd_out[i] = 0.f;
+    return;
+  }
+  const double m = (double)sum[i] / count;
+  double var = (double)sq[i] / count - m * m;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * (float)m;
+    const double unbiased = count > 1.f ? var * count / (count - 1.0) : var;
+    running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unbiased;
+  }
+  const float g = gamma ? gamma[i] : 1.f, b = beta ? beta[i] : 0.f;
+  if (mean_out) mean_out[i] = (float)m;
+  if (rstd_out) rstd_out[i] = rstd;
+  if (scale) scale[i] = g * rstd;
+  if (shift) shift[i] = b - (float)m * g * rstd;
+}
+
+// y = act(scale[c]*x + shift[c] (+ residual))
+template <typename T>
+__global__ void affine_act_kernel(V4 src, V4 dst, const float* __restrict__ scale, const float* __restrict__ shift,
+                                  V4 res, int act) {
+  const int cg = dst.c / 8;
+  const long long total = (long long)dst.n * dst.h * dst.w * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long pix = i / cg;
+    const int w = (int)(pix % dst.w);
+    pix /= dst.w;
+    const int h = (int)(pix % dst.h);
+    const int n = (int)(pix / dst.h);
+    float v[8], sc[8], sf[8];
+    load8(static_cast<const T*>(src.ptr) + n * src.sn + h * src.sh + w * src.sw + g * 8, v);
+    load8(scale + g * 8, sc);
+    load8(shift + g * 8, sf);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = fmaf(v[q], sc[q], sf[q]);
+    if (res.ptr) {
+      float r[8];
+      load8(static_cast<const T*>(res.ptr) + n * res.sn + h * res.sh + w * res.sw + g * 8, r);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] += r[q];
+    }
+    if (act == PMOE_ACT_RELU) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+    }
+    store8(static_cast<T*>(dst.ptr) + n * dst.sn + h * dst.sh + w * dst.sw + g * 8, v);
+  }
+}
+
+}  // namespace pmoe
+
+using namespace pmoe;
+
+#define DISPATCH_DTYPE(dtype, ...)                       \
+  if ((dtype) == PMOE_BF16) {                            \
+    using T = __nv_bfloat16;                             \
+    __VA_ARGS__;                                         \
+  } else if ((dtype) == PMOE_F32) {                      \
+    using T = float;                                     \
+    __VA_ARGS__;                                         \
+  } else {                                               \
+    set_error("unsupported dtype %d", (int)(dtype));     \
+    return PMOE_ERR_ARG;                                 \
+  }
+
+extern "C" {
+
+int pmoe_nchw_to_nhwc(const float* src, int64_t sn, int64_t sc, int64_t sh, int64_t sw, int32_t c, const PmoeView4* dst,
+                      int32_t dst_dtype, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_view(dst, dst_dtype, "nchw_to_nhwc");
+  if (rc) return rc;
+  if (!src || c > dst->c) {
+    set_error("nchw_to_nhwc: bad source (c %d, dst.c %d)", c, dst ? dst->c : -1);
+    return PMOE_ERR_ARG;
+  }
+  const long long items = (long long)dst->n * dst->h * dst->w * (dst->c / 8);
+  DISPATCH_DTYPE(dst_dtype, (nchw_to_nhwc_kernel<T><<<grid_for(items, 256), 256, 0, stream>>>(src, sn, sc, sh, sw, c, to_v4(*dst))));
+  return check_launch("nchw_to_nhwc");
+}
+
+int pmoe_nhwc_to_nchw(const PmoeView4* src, int32_t src_dtype, int32_t c, float* dst, int64_t dn, int64_t dc, int64_t dh,
+                      int64_t dw, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_view(src, src_dtype, "nhwc_to_nchw");
+  if (rc) return rc;
+  if (!dst || c > src->c) {
+    set_error("nhwc_to_nchw: bad destination");
+    return PMOE_ERR_ARG;
+  }
+  const long long items = (long long)src->n * src->h * src->w * ((c + 7) / 8);
+  DISPATCH_DTYPE(src_dtype, (nhwc_to_nchw_kernel<T><<<grid_for(items, 256), 256, 0, stream>>>(to_v4(*src), c, dst, dn, dc, dh, dw)));
+  return check_launch("nhwc_to_nchw");
+}
+
+int pmoe_maxpool(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, int32_t k, int32_t stride, int32_t pad,
+                 const float* scale, const float* shift, int32_t relu, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_view(src, dtype, "maxpool src");
+  if (rc) return rc;
+  if ((rc = check_view(dst, dtype, "maxpool dst"))) return rc;
+  if (src->c < dst->c || src->n != dst->n || k < 1 || stride < 1) {
+    set_error("maxpool: geometry mismatch");
+    return PMOE_ERR_ARG;
+  }
+  const long long items = (long long)dst->n * dst->h * dst->w * (dst->c / 8);
+  DISPATCH_DTYPE(dtype, (maxpool_kernel<T><<<grid_for(items, 256), 256, 0, stream>>>(to_v4(*src), to_v4(*dst), k, stride, pad, scale, shift, relu)));
+  return check_launch("maxpool");
+}
+
+int pmoe_eca_gate(const float* pool_sum, int64_t pool_stride, int32_t n, float inv_count, const float* w, int32_t k,
+                  int32_t groups, int32_t group_c, int32_t group_stride, float* gate, int64_t gate_stride,
+                  pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!pool_sum || !w || !gate || n < 1 || k < 1 || groups < 1 || group_c > group_stride) {
+    set_error("eca_gate: bad arguments");
+    return PMOE_ERR_ARG;
+  }
+  eca_gate_kernel<<<n, 128, 0, stream>>>(pool_sum, pool_stride, inv_count, w, k, groups, group_c, group_stride, gate, gate_stride);
+  return check_launch("eca_gate");
+}
+
+int pmoe_scale_channels(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, const float* gate, int64_t gate_stride,
+                        pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_view(src, dtype, "scale_channels src");
+  if (rc) return rc;
+  if ((rc = check_view(dst, dtype, "scale_channels dst"))) return rc;
+  if (!gate || ((uintptr_t)gate % 16) || gate_stride % 4 || src->n != dst->n || src->h != dst->h || src->w != dst->w || src->c < dst->c) {
+    set_error("scale_channels: bad arguments");
+    return PMOE_ERR_ARG;
+  }
+  const long long items = (long long)dst->n * dst->h * dst->w * (dst->c / 8);
+  DISPATCH_DTYPE(dtype, (scale_channels_kernel<T><<<grid_for(items, 256), 256, 0, stream>>>(to_v4(*src), to_v4(*dst), gate, gate_stride)));
+  return check_launch("scale_channels");
+}
+
+int pmoe_channel_sums(const PmoeView4* src, int32_t dtype, float* out, int64_t out_stride, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_view(src, dtype, "channel_sums");
+  if (rc) return rc;
+  const int cg = src->c / 8;
+  if (!out || cg > 256) {
+    set_error("channel_sums: needs an output buffer and at most 2048 channels");
+    return PMOE_ERR_ARG;
+  }
+  const long long hw = (long long)src->h * src->w;
+  int rows = 1024;
+  dim3 grid((unsigned)((hw + rows - 1) / rows), (unsigned)src->n);
+  DISPATCH_DTYPE(dtype, (channel_sums_kernel<T><<<grid, 256, 0, stream>>>(to_v4(*src), out, out_stride, rows)));
+  return check_launch("channel_sums");
+}
+
+int pmoe_bn_finalize(const float* sum, const float* sqsum, float count, int32_t c, int32_t c_pad, const float* gamma,
+                     const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* mean_out,
+                     float* rstd_out, float* scale, float* shift, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!sum || !sqsum || c < 1 || c_pad < c || count <= 0) {
+    set_error("bn_finalize: bad arguments");
+    return PMOE_ERR_ARG;
+  }
+  bn_finalize_kernel<<<(c_pad + 127) / 128, 128, 0, stream>>>(sum, sqsum, count, c, gamma, beta, eps, momentum, running_mean,
+                                                              running_var, mean_out, rstd_out, scale, shift, c_pad);
+  return check_launch("bn_finalize");
+}
+
+int pmoe_affine_act(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, const float* scale, const float* shift,
+                    const PmoeView4* residual, int32_t act, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_view(src, dtype, "affine_act src");
+  if (rc) return rc;
+  if ((rc = check_view(dst, dtype, "affine_act dst"))) return rc;
+  if (!scale || !shift || ((uintptr_t)scale % 16) || ((uintptr_t)shift % 16)) {
+    set_error("affine_act: scale/shift required, 16-byte aligned");
+    return PMOE_ERR_ARG;
+  }
+  V4 res{nullptr, 0, 0, 0, 0, 0, 0, 0};
+  if (residual && residual->ptr) {
+    if ((rc = check_view(residual, dtype, "affine_act residual"))) return rc;
+    res = to_v4(*residual);
+  }
+  const long long items = (long long)dst->n * dst->h * dst->w * (dst->c / 8);
+  DISPATCH_DTYPE(dtype, (affine_act_kernel<T><<<grid_for(items, 256), 256, 0, stream>>>(to_v4(*src), to_v4(*dst), scale, shift, res, act)));
+  return check_launch("affine_act");
+}
+
+}  // extern "C"

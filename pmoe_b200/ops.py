@@ -8,7 +8,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib
+from . import _lib, profiler
 from ._lib import ACT
 
 
@@ -75,7 +75,7 @@ def pad_vec(v, n, fill=0.0):
 
 
 def conv_tc(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residual=None, stat_sum=None,
-            stat_sqsum=None, pool_sum=None, src_channels=None):
+            stat_sqsum=None, pool_sum=None, src_channels=None, pool_stride=0, flops=0.0, tag=""):
     """Launch the tcgen05 implicit-GEMM kernel. srcs: list of NHWC bf16 tensors (views allowed);
     out: NHWC bf16 tensor/view; wpack: [cout_pad, ktot] bf16."""
     d = _lib.ConvTc()
@@ -102,5 +102,8 @@ def conv_tc(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residu
     d.stat_sum = None if stat_sum is None else stat_sum.data_ptr()
     d.stat_sqsum = None if stat_sqsum is None else stat_sqsum.data_ptr()
     d.pool_sum = None if pool_sum is None else pool_sum.data_ptr()
-    _lib.check(_lib.lib().pmoe_conv_tc(C.byref(d), _lib.stream_ptr()), "conv_tc")
+    d.pool_stride = int(pool_stride) if pool_stride else (pool_sum.stride(0) if pool_sum is not None and pool_sum.dim() == 2 else 0)
+    fn = _lib.lib().pmoe_conv_tc
+    sp = _lib.stream_ptr()
+    _lib.check(profiler.launch("conv_tc", lambda: fn(C.byref(d), sp), flops, 0.0, tag), "conv_tc")
     return out

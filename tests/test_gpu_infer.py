@@ -1,0 +1,72 @@
+"""GPU parity of the eval-mode (inference) path against the CPU oracle and the reference goldens.
+bf16 storage / fp32 accumulate: tolerance 1e-2 normwise (BASELINE.json north_star)."""
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN, rel_err
+from oracle import functional as O
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 1e-2
+
+
+def load(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+def test_library_is_native():
+    from pmoe_b200 import _lib
+    l = _lib.lib()
+    assert l.pmoe_version() >= 100
+    _lib.check(l.pmoe_device_check(), "device_check")
+
+
+def test_unet_eval_vs_reference_golden():
+    from pmoe_b200.model.blocks.unet import UNet
+    g = load("unet_stage0.pt")
+    sd = O.seeded_state_dict(O.make_spec(O.unet_spec, 3, 23), g["seed"])
+    net = UNet(3, 23)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        out = net(g["img"].cuda()).cpu()
+    e = rel_err(out, g["logits_eval"])
+    print("unet eval rel err vs reference:", e)
+    assert out.shape == g["logits_eval"].shape
+    assert e < BF16_TOL
+    assert (out.argmax(1) == g["logits_eval"].argmax(1)).float().mean() > 0.97
+
+
+def test_unet_inter_repr_eval():
+    from pmoe_b200.model.blocks.unet import UNet
+    sd = O.seeded_state_dict(O.make_spec(O.unet_spec, 3, 23), 5)
+    net = UNet(3, 23, inter_repr=True)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    x = torch.rand(3, 3, 48, 64, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        inter, out = net(x.cuda())
+        ri, ro = O.unet(x, {k: v.clone() for k, v in sd.items()}, "", False, True)
+    assert rel_err(out.cpu(), ro) < BF16_TOL and rel_err(inter.cpu(), ri) < BF16_TOL
+
+
+def test_punet_eval_vs_reference_golden(tmp_path):
+    from pmoe_b200.model.punet import PredictiveUnet
+    g = load("punet_stage1.pt")
+    pc = dict(g["cfg"])
+    sd = O.seeded_state_dict(O.make_spec(O.punet_spec, pc), g["seed"])
+    ck = tmp_path / "unet.pth"
+    torch.save({"unet": {k[len("unet."):]: v for k, v in sd.items() if k.startswith("unet.")}}, ck)
+    pc["model_path"] = str(ck)
+    net = PredictiveUnet(**pc)
+    net.load_state_dict(sd, strict=True)
+    assert not any(p.requires_grad for p in net.unet.parameters())
+    net = net.cuda().eval()
+    with torch.no_grad():
+        out = net(g["imgs"].cuda()).cpu()
+    assert out.shape == (2, 3, 23, 64, 64)
+    e = rel_err(out[..., ::2, ::2], g["out_eval"])
+    print("punet eval rel err vs reference:", e)
+    assert e < BF16_TOL

@@ -76,6 +76,13 @@ typedef struct PmoeConvTc {
 
 int pmoe_conv_tc(const PmoeConvTc* desc, pmoe_stream_t stream);
 
+/* Same contract as pmoe_conv_tc on CUDA cores with fp32 FMA accumulation; dtype selects fp32 (the
+ * <=1e-4 parity mode: activations, wpack and out are float) or bf16 storage. */
+int pmoe_conv_simt(const PmoeConvTc* desc, int32_t dtype, pmoe_stream_t stream);
+/* Weight gradient of the same descriptor (aten::convolution_backward, weight half): desc->out is read as
+ * dy; dwpack[cout_pad][ktot] (fp32, packed K order of wpack) is ACCUMULATED into. */
+int pmoe_conv_wgrad_simt(const PmoeConvTc* desc, int32_t dtype, float* dwpack, pmoe_stream_t stream);
+
 /* ---- memory-bound kernels (eltwise.cu); dtype = PMOE_F32 | PMOE_BF16 of the NHWC views ------------- */
 /* Module boundary: the reference hands fp32 NCHW tensors to forward() (model/moe.py:90-93, punet.py:88). */
 int pmoe_nchw_to_nhwc(const float* src, int64_t sn, int64_t sc, int64_t sh, int64_t sw, int32_t c, const PmoeView4* dst,
@@ -101,6 +108,59 @@ int pmoe_bn_finalize(const float* sum, const float* sqsum, float count, int32_t 
 /* y = act(scale[c]*x + shift[c] (+ residual)): BN apply + ReLU (+ BasicBlock residual add). */
 int pmoe_affine_act(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, const float* scale, const float* shift,
                     const PmoeView4* residual, int32_t act, pmoe_stream_t stream);
+
+/* ---- backward halves (eltwise_bwd.cu) ------------------------------------------------------------- */
+/* dy = dz * act'(z); sum_dy[c] += sum dy, sum_dy_xhat[c] += sum dy*(x-mean)*rstd  (native_batch_norm_backward reductions) */
+int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
+                       const float* mean, const float* rstd, float* sum_dy, float* sum_dy_xhat, pmoe_stream_t stream);
+/* dx = gamma*rstd*(dy - sum_dy/N - xhat*sum_dy_xhat/N) (batch_stats) or dy*gamma (eval BN / plain);
+ * dres (optional) receives the masked dy for a residual branch. */
+int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
+                      const float* mean, const float* rstd, const float* gamma, const float* sum_dy,
+                      const float* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
+                      const PmoeView4* dres, int32_t accumulate_dres, pmoe_stream_t stream);
+int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* dx, int32_t dtype, int32_t k, int32_t stride,
+                     int32_t pad, int32_t accumulate, pmoe_stream_t stream);
+int pmoe_prod_channel_sums(const PmoeView4* a, const PmoeView4* b, int32_t dtype, float* out, int64_t out_stride,
+                           pmoe_stream_t stream);
+int pmoe_eca_gate_bwd(const float* dgate, int64_t dgate_stride, const float* gate, int64_t gate_stride, const float* pool_sum,
+                      int64_t pool_stride, int32_t n, float inv_count, const float* w, int32_t k, int32_t groups,
+                      int32_t group_c, int32_t group_stride, float* dmean, int64_t dmean_stride, float* dw,
+                      pmoe_stream_t stream);
+int pmoe_eca_bwd_apply(const PmoeView4* dout, int32_t dtype, const float* gate, int64_t gate_stride, const float* dmean,
+                       int64_t dmean_stride, const PmoeView4* dx, int32_t accumulate, pmoe_stream_t stream);
+/* dst (+)= alpha*src + bcast[n][c]: gradient accumulation and global-avg-pool backward. */
+int pmoe_axpy(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, float alpha, const float* bcast, int64_t bcast_stride,
+              int32_t accumulate, pmoe_stream_t stream);
+
+/* ---- MoE gating / mixture head and losses (heads.cu, segloss.cu) ---------------------------------- */
+/* softmax_K(alpha) (after ReLU for BaseExpert, model/moe.py:100,150-151), sigma = ELU(raw)+1 (moe.py:99), routing
+ * index = argmax_k. alpha/ap are the strided raw head outputs (element (b,k) at b*sb + k*sk). */
+int pmoe_gate_mixture_fwd(const void* alpha, int64_t a_sb, int64_t a_sk, const void* ap, int64_t p_sb, int64_t p_sk,
+                          int32_t dtype, int32_t B, int32_t K, int32_t relu_alpha, float* probs, float* mean, float* std,
+                          int64_t* route, pmoe_stream_t stream);
+int pmoe_gate_mixture_bwd(const float* dprobs, const float* dmean, const float* dstd, const float* probs, const float* std,
+                          const void* alpha, int64_t a_sb, int64_t a_sk, int32_t dtype, int32_t B, int32_t K,
+                          int32_t relu_alpha, void* dalpha, void* dap, int64_t p_sb, int64_t p_sk, pmoe_stream_t stream);
+/* moe_loss (trainer/loss.py:121-132): c0*NLL of the Gaussian mixture + c1*speed MSE(/K), with gradients. loss_out[3]
+ * (total, nll, speed) must be zeroed by the caller. */
+int pmoe_moe_loss(const float* probs, const float* mean, const float* std, const float* speed_pred, int32_t speed_k,
+                  const float* act_gt, const float* speed_gt, int32_t B, int32_t K, float c0, float c1, float* loss_out,
+                  float* dprobs, float* dmean, float* dstd, float* dspeed, float* logp_out, pmoe_stream_t stream);
+/* nn.Dropout (basics.py:39-40) with a stateless counter-based mask; call again on the gradient for backward. */
+int pmoe_dropout(const void* x, void* y, int32_t dtype, int64_t n, float p, uint64_t seed, pmoe_stream_t stream);
+/* nn.L1Loss / nn.MSELoss (loss.py:135-151): *loss += coef*mean(...), da = gradient. */
+int pmoe_l1_mse(const float* a, const float* b, int64_t n, int32_t is_mse, float coef, float* loss, float* da,
+                pmoe_stream_t stream);
+/* cross_entropy_tversky_weighted_loss (loss.py:47-55) fused: one read forward, one read + one write backward. */
+size_t pmoe_segloss_workspace_floats(int32_t C, int32_t W);
+int pmoe_segloss_fwd(const float* logits, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const int64_t* target, int64_t tb,
+                     int64_t th, int64_t tw, int32_t B, int32_t C, int32_t H, int32_t W, float wce, float wtv, float* workspace,
+                     float* loss_out, pmoe_stream_t stream);
+int pmoe_segloss_bwd(const float* logits, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const int64_t* target, int64_t tb,
+                     int64_t th, int64_t tw, int32_t B, int32_t C, int32_t H, int32_t W, float wce, const float* workspace,
+                     const float* grad_scale_dev, float grad_scale, float* dlogits, int64_t db, int64_t dc, int64_t dh,
+                     int64_t dw, int32_t accumulate, pmoe_stream_t stream);
 
 /* Library info / errors. */
 int pmoe_version(void);

@@ -63,6 +63,8 @@ def _declare(l):
     l.pmoe_device_check.restype = i32
     l.pmoe_conv_tc.argtypes = [C.POINTER(ConvTc), vp]
     l.pmoe_dbg_umma_view.argtypes = [vp, i32, vp, vp, i32, i32, i32, vp]
+    l.pmoe_segloss_workspace_floats.argtypes = [i32, i32]
+    l.pmoe_segloss_workspace_floats.restype = C.c_size_t
     from . import _sigs
     for name, argtypes in _sigs.SIGS.items():
         fn = getattr(l, name)

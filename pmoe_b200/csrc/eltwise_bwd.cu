@@ -1,0 +1,515 @@
+// Backward halves of the memory-bound kernels: activation / BatchNorm backward (two passes: per-channel
+// reductions, then the elementwise apply), max-pool backward (first-max tie rule of ATen), ECA backward,
+// gradient accumulation. Same conventions as eltwise.cu: strided NHWC views, 8 channels per thread.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace pmoe {
+
+__device__ __forceinline__ void bload8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void bload8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void bstore8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void bstore8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 r;
+  r.x = pack_bf16x2(v[0], v[1]);
+  r.y = pack_bf16x2(v[2], v[3]);
+  r.z = pack_bf16x2(v[4], v[5]);
+  r.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = r;
+}
+
+struct BV4 {
+  void* ptr;
+  int n, h, w, c;
+  long long sn, sh, sw;
+};
+static BV4 bv4(const PmoeView4* v) {
+  if (!v || !v->ptr) return BV4{nullptr, 0, 0, 0, 0, 0, 0, 0};
+  return BV4{v->ptr, v->n, v->h, v->w, v->c, v->sn, v->sh, v->sw};
+}
+template <typename T>
+__device__ __forceinline__ const T* at(const BV4& v, int n, int h, int w, int c) {
+  return static_cast<const T*>(v.ptr) + n * v.sn + h * v.sh + w * v.sw + c;
+}
+template <typename T>
+__device__ __forceinline__ T* at_mut(const BV4& v, int n, int h, int w, int c) {
+  return static_cast<T*>(v.ptr) + n * v.sn + h * v.sh + w * v.sw + c;
+}
+
+__device__ __forceinline__ float act_grad(float z, int act) {
+  switch (act) {
+    case PMOE_ACT_RELU: return z > 0.f ? 1.f : 0.f;
+    case PMOE_ACT_ELU: return z > 0.f ? 1.f : z + 1.f;  // z = exp(x)-1 for x<=0  ->  dz/dx = z+1
+    case PMOE_ACT_TANH: return 1.f - z * z;
+    case PMOE_ACT_SIGMOID: return z * (1.f - z);
+    default: return 1.f;
+  }
+}
+
+static inline int bgrid(long long items, int threads) {
+  long long blocks = (items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ---------------------------------------------------------------- pass 1: per-channel sums of dy and dy*xhat
+// dy = dz * act'(z). Block = cg channel groups x (256/cg) pixel lanes; each block walks a slab of pixels and
+// finishes with one atomicAdd per channel.
+template <typename T>
+__global__ void bn_bwd_reduce_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, float* __restrict__ sum_dy,
+                                     float* __restrict__ sum_dy_xhat, long long pix_per_block) {
+  const int cg = dz.c / 8;
+  const int lanes = blockDim.x / cg;
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+  if (lane >= lanes) return;
+  const long long npix = (long long)dz.n * dz.h * dz.w;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > npix) p1 = npix;
+  float m[8], r[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    m[q] = mean ? __ldg(mean + g * 8 + q) : 0.f;
+    r[q] = rstd ? __ldg(rstd + g * 8 + q) : 1.f;
+  }
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long p = p0 + lane; p < p1; p += lanes) {
+    const int w = (int)(p % dz.w);
+    const long long t = p / dz.w;
+    const int h = (int)(t % dz.h), n = (int)(t / dz.h);
+    float d[8], xv[8];
+    bload8(at<T>(dz, n, h, w, g * 8), d);
+    if (act != PMOE_ACT_NONE) {
+      float zv[8];
+      bload8(at<T>(z, n, h, w, g * 8), zv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) d[q] *= act_grad(zv[q], act);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] += d[q];
+    if (x.ptr) {
+      bload8(at<T>(x, n, h, w, g * 8), xv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) b[q] += d[q] * (xv[q] - m[q]) * r[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    atomicAdd(sum_dy + g * 8 + q, a[q]);
+    if (sum_dy_xhat) atomicAdd(sum_dy_xhat + g * 8 + q, b[q]);
+  }
+}
+
+// ---------------------------------------------------------------- pass 2: dx (and the masked dy for a residual branch)
+// batch-stat BN : dx = gamma*rstd * (dy - sum_dy/N - xhat*sum_dy_xhat/N)
+// eval BN / bias: dx = dy * scale (scale may be NULL = 1)
+template <typename T>
+__global__ void bn_bwd_apply_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                    const float* __restrict__ sum_dy, const float* __restrict__ sum_dy_xhat, float inv_n,
+                                    int batch_stats, BV4 dx, BV4 dres, int accumulate_dres) {
+  const int cg = dz.c / 8;
+  const long long total = (long long)dz.n * dz.h * dz.w * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long pix = i / cg;
+    const int w = (int)(pix % dz.w);
+    pix /= dz.w;
+    const int h = (int)(pix % dz.h);
+    const int n = (int)(pix / dz.h);
+    float d[8];
+    bload8(at<T>(dz, n, h, w, g * 8), d);
+    if (act != PMOE_ACT_NONE) {
+      float zv[8];
+      bload8(at<T>(z, n, h, w, g * 8), zv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) d[q] *= act_grad(zv[q], act);
+    }
+    if (dres.ptr) {
+      float o[8];
+      if (accumulate_dres) {
+        bload8(at<T>(dres, n, h, w, g * 8), o);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] += d[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = d[q];
+      }
+      bstore8(at_mut<T>(dres, n, h, w, g * 8), o);
+    }
+    if (dx.ptr) {
+      float o[8];
+      if (batch_stats) {
+        float xv[8];
+        bload8(at<T>(x, n, h, w, g * 8), xv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c = g * 8 + q;
+          const float r = __ldg(rstd + c);
+          const float xh = (xv[q] - __ldg(mean + c)) * r;
+          const float gm = gamma ? __ldg(gamma + c) : 1.f;
+          o[q] = gm * r * (d[q] - __ldg(sum_dy + c) * inv_n - xh * __ldg(sum_dy_xhat + c) * inv_n);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = d[q] * (gamma ? __ldg(gamma + g * 8 + q) : 1.f);
+      }
+      bstore8(at_mut<T>(dx, n, h, w, g * 8), o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- max-pool backward (gather form)
+// dx[i] = sum over windows w containing i of dy[w] * [i is the FIRST maximum of w in row-major scan order]
+template <typename T>
+__global__ void maxpool_bwd_kernel(BV4 x, BV4 dy, BV4 dx, int k, int stride, int pad, int accumulate) {
+  const int cg = dx.c / 8;
+  const long long total = (long long)dx.n * dx.h * dx.w * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long pix = i / cg;
+    const int iw = (int)(pix % dx.w);
+    pix /= dx.w;
+    const int ih = (int)(pix % dx.h);
+    const int n = (int)(pix / dx.h);
+    float xv[8], o[8];
+    bload8(at<T>(x, n, ih, iw, g * 8), xv);
+    if (accumulate) bload8(at<T>(dx, n, ih, iw, g * 8), o);
+    else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = 0.f;
+    }
+    // windows (oh, ow) with oh*stride - pad <= ih < oh*stride - pad + k
+    const int oh_lo = max(0, (ih + pad - k + stride) / stride), oh_hi = min(dy.h - 1, (ih + pad) / stride);
+    const int ow_lo = max(0, (iw + pad - k + stride) / stride), ow_hi = min(dy.w - 1, (iw + pad) / stride);
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        bool mine[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) mine[q] = true;
+        bool before = true;  // scanning positions that precede (ih, iw) in the window
+        for (int r = 0; r < k; ++r) {
+          const int yh = oh * stride - pad + r;
+          if (yh < 0 || yh >= x.h) continue;
+          for (int s = 0; s < k; ++s) {
+            const int yw = ow * stride - pad + s;
+            if (yw < 0 || yw >= x.w) continue;
+            if (yh == ih && yw == iw) {
+              before = false;
+              continue;
+            }
+            float v[8];
+            bload8(at<T>(x, n, yh, yw, g * 8), v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              // an earlier element wins ties; a later one must be strictly greater (NaN ignored)
+              if (before ? (v[q] >= xv[q]) : (v[q] > xv[q])) mine[q] = false;
+            }
+          }
+        }
+        float d[8];
+        bload8(at<T>(dy, n, oh, ow, g * 8), d);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (mine[q]) o[q] += d[q];
+      }
+    }
+    bstore8(at_mut<T>(dx, n, ih, iw, g * 8), o);
+  }
+}
+
+// ---------------------------------------------------------------- ECA backward
+// out = x * gate[n,c]. pass 1: dgate[n,c] = sum_hw dout*x (per-image channel sums of a product)
+template <typename T>
+__global__ void prod_channel_sums_kernel(BV4 a, BV4 b, float* __restrict__ out, long long out_stride, int rows_per_block) {
+  const int cg = a.c / 8;
+  const int lanes = blockDim.x / cg;
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+  if (lane >= lanes) return;
+  const int n = blockIdx.y;
+  const long long hw = (long long)a.h * a.w;
+  const long long p0 = (long long)blockIdx.x * rows_per_block;
+  long long p1 = p0 + rows_per_block;
+  if (p1 > hw) p1 = hw;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long p = p0 + lane; p < p1; p += lanes) {
+    const int h = (int)(p / a.w), w = (int)(p % a.w);
+    float u[8], v[8];
+    bload8(at<T>(a, n, h, w, g * 8), u);
+    bload8(at<T>(b, n, h, w, g * 8), v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] += u[q] * v[q];
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) atomicAdd(out + n * out_stride + g * 8 + q, acc[q]);
+}
+
+// tiny: gate = sigmoid(pre), pre = conv1d(mean). dpre = dgate*gate*(1-gate); dmean = corr(dpre, w) / count;
+// dw[t] += sum_{n,l} dpre[n,l] * mean[n, l+t-k/2]
+__global__ void eca_gate_bwd_kernel(const float* __restrict__ dgate, long long dgate_stride, const float* __restrict__ gate,
+                                    long long gate_stride, const float* __restrict__ pool_sum, long long pool_stride,
+                                    float inv_count, const float* __restrict__ w, int k, int groups, int group_c,
+                                    int group_stride, float* __restrict__ dmean, long long dmean_stride,
+                                    float* __restrict__ dw) {
+  const int n = blockIdx.x;
+  const int L = groups * group_c;
+  extern __shared__ float s_dpre[];  // L entries
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    const int p = (l / group_c) * group_stride + (l % group_c);
+    const float gt = gate[n * gate_stride + p];
+    s_dpre[l] = dgate[n * dgate_stride + p] * gt * (1.f - gt);
+  }
+  __syncthreads();
+  for (int pc = threadIdx.x; pc < groups * group_stride; pc += blockDim.x) {
+    const int g = pc / group_stride, j = pc % group_stride;
+    float acc = 0.f;
+    if (j < group_c) {
+      const int l = g * group_c + j;  // d mean[l] = sum_t w[t] * dpre[l - t + k/2]
+      for (int t = 0; t < k; ++t) {
+        const int lo = l - t + k / 2;
+        if (lo >= 0 && lo < L) acc = fmaf(w[t], s_dpre[lo], acc);
+      }
+    }
+    dmean[n * dmean_stride + pc] = acc * inv_count;
+  }
+  if (dw) {
+    for (int t = threadIdx.x; t < k; t += blockDim.x) {
+      float acc = 0.f;
+      for (int l = 0; l < L; ++l) {
+        const int ll = l + t - k / 2;
+        if (ll >= 0 && ll < L) {
+          const int p = (ll / group_c) * group_stride + (ll % group_c);
+          acc = fmaf(s_dpre[l], pool_sum[n * pool_stride + p] * inv_count, acc);
+        }
+      }
+      atomicAdd(dw + t, acc);
+    }
+  }
+}
+
+// pass 2: dx = dout*gate[n,c] + dmean[n,c]   (optionally accumulated into dx)
+template <typename T>
+__global__ void eca_bwd_apply_kernel(BV4 dout, const float* __restrict__ gate, long long gate_stride,
+                                     const float* __restrict__ dmean, long long dmean_stride, BV4 dx, int accumulate) {
+  const int cg = dx.c / 8;
+  const long long total = (long long)dx.n * dx.h * dx.w * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long pix = i / cg;
+    const int w = (int)(pix % dx.w);
+    pix /= dx.w;
+    const int h = (int)(pix % dx.h);
+    const int n = (int)(pix / dx.h);
+    float d[8], gt[8], dm[8], o[8];
+    bload8(at<T>(dout, n, h, w, g * 8), d);
+    bload8(gate + n * gate_stride + g * 8, gt);
+    bload8(dmean + n * dmean_stride + g * 8, dm);
+    if (accumulate) bload8(at<T>(dx, n, h, w, g * 8), o);
+    else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] += d[q] * gt[q] + dm[q];
+    bstore8(at_mut<T>(dx, n, h, w, g * 8), o);
+  }
+}
+
+// dst (+)= alpha * src [+ per-(n,c) broadcast term]  — gradient accumulation / avg-pool backward
+template <typename T>
+__global__ void axpy_kernel(BV4 src, BV4 dst, float alpha, const float* __restrict__ bcast, long long bcast_stride,
+                            int accumulate) {
+  const int cg = dst.c / 8;
+  const long long total = (long long)dst.n * dst.h * dst.w * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long pix = i / cg;
+    const int w = (int)(pix % dst.w);
+    pix /= dst.w;
+    const int h = (int)(pix % dst.h);
+    const int n = (int)(pix / dst.h);
+    float o[8];
+    if (accumulate) bload8(at<T>(dst, n, h, w, g * 8), o);
+    else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = 0.f;
+    }
+    if (src.ptr) {
+      float s[8];
+      bload8(at<T>(src, n, h, w, g * 8), s);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] += alpha * s[q];
+    }
+    if (bcast) {
+      float bq[8];
+      bload8(bcast + n * bcast_stride + g * 8, bq);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] += bq[q];
+    }
+    bstore8(at_mut<T>(dst, n, h, w, g * 8), o);
+  }
+}
+
+static int chk(const PmoeView4* v, int dtype, const char* what, bool optional = false) {
+  if (optional && (!v || !v->ptr)) return PMOE_OK;
+  const int esz = dtype == PMOE_BF16 ? 2 : 4;
+  if (!v || !v->ptr || v->c % 8 || ((uintptr_t)v->ptr % 16) || (v->sw * esz) % 16 || (v->sh * esz) % 16 || (v->sn * esz) % 16) {
+    set_error("%s: view must be 16-byte aligned, channels a multiple of 8", what);
+    return PMOE_ERR_ARG;
+  }
+  return PMOE_OK;
+}
+
+}  // namespace pmoe
+
+using namespace pmoe;
+
+#define BW_DISPATCH(dtype, ...)                      \
+  if ((dtype) == PMOE_BF16) {                        \
+    using T = __nv_bfloat16;                         \
+    __VA_ARGS__;                                     \
+  } else if ((dtype) == PMOE_F32) {                  \
+    using T = float;                                 \
+    __VA_ARGS__;                                     \
+  } else {                                           \
+    set_error("unsupported dtype %d", (int)(dtype)); \
+    return PMOE_ERR_ARG;                             \
+  }
+
+extern "C" {
+
+int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
+                       const float* mean, const float* rstd, float* sum_dy, float* sum_dy_xhat, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = chk(dz, dtype, "bn_bwd_reduce dz"))) return rc;
+  if ((rc = chk(z, dtype, "bn_bwd_reduce z", act == PMOE_ACT_NONE))) return rc;
+  if ((rc = chk(x, dtype, "bn_bwd_reduce x", true))) return rc;
+  const int cg = dz->c / 8;
+  if (!sum_dy || cg > 256 || (act != PMOE_ACT_NONE && (!z || !z->ptr))) {
+    set_error("bn_bwd_reduce: bad arguments");
+    return PMOE_ERR_ARG;
+  }
+  const long long npix = (long long)dz->n * dz->h * dz->w;
+  long long blocks = (long long)num_sms() * 8;
+  long long ppb = (npix + blocks - 1) / blocks;
+  if (ppb < 64) ppb = 64;
+  blocks = (npix + ppb - 1) / ppb;
+  BW_DISPATCH(dtype, (bn_bwd_reduce_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, sum_dy, sum_dy_xhat, ppb)));
+  return check_launch("bn_bwd_reduce");
+}
+
+int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
+                      const float* mean, const float* rstd, const float* gamma, const float* sum_dy,
+                      const float* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
+                      const PmoeView4* dres, int32_t accumulate_dres, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = chk(dz, dtype, "bn_bwd_apply dz"))) return rc;
+  if ((rc = chk(z, dtype, "bn_bwd_apply z", act == PMOE_ACT_NONE))) return rc;
+  if ((rc = chk(x, dtype, "bn_bwd_apply x", !batch_stats))) return rc;
+  if ((rc = chk(dx, dtype, "bn_bwd_apply dx", true))) return rc;
+  if ((rc = chk(dres, dtype, "bn_bwd_apply dres", true))) return rc;
+  if (batch_stats && (!mean || !rstd || !sum_dy || !sum_dy_xhat)) {
+    set_error("bn_bwd_apply: batch statistics mode needs mean/rstd/sums");
+    return PMOE_ERR_ARG;
+  }
+  const long long items = (long long)dz->n * dz->h * dz->w * (dz->c / 8);
+  BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T><<<bgrid(items, 256), 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres)));
+  return check_launch("bn_bwd_apply");
+}
+
+int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* dx, int32_t dtype, int32_t k, int32_t stride,
+                     int32_t pad, int32_t accumulate, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = chk(x, dtype, "maxpool_bwd x"))) return rc;
+  if ((rc = chk(dy, dtype, "maxpool_bwd dy"))) return rc;
+  if ((rc = chk(dx, dtype, "maxpool_bwd dx"))) return rc;
+  const long long items = (long long)dx->n * dx->h * dx->w * (dx->c / 8);
+  BW_DISPATCH(dtype, (maxpool_bwd_kernel<T><<<bgrid(items, 256), 256, 0, stream>>>(bv4(x), bv4(dy), bv4(dx), k, stride, pad, accumulate)));
+  return check_launch("maxpool_bwd");
+}
+
+int pmoe_prod_channel_sums(const PmoeView4* a, const PmoeView4* b, int32_t dtype, float* out, int64_t out_stride,
+                           pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = chk(a, dtype, "prod_channel_sums a"))) return rc;
+  if ((rc = chk(b, dtype, "prod_channel_sums b"))) return rc;
+  if (!out || a->c / 8 > 256) {
+    set_error("prod_channel_sums: bad arguments");
+    return PMOE_ERR_ARG;
+  }
+  const long long hw = (long long)a->h * a->w;
+  const int rows = 1024;
+  dim3 grid((unsigned)((hw + rows - 1) / rows), (unsigned)a->n);
+  BW_DISPATCH(dtype, (prod_channel_sums_kernel<T><<<grid, 256, 0, stream>>>(bv4(a), bv4(b), out, out_stride, rows)));
+  return check_launch("prod_channel_sums");
+}
+
+int pmoe_eca_gate_bwd(const float* dgate, int64_t dgate_stride, const float* gate, int64_t gate_stride, const float* pool_sum,
+                      int64_t pool_stride, int32_t n, float inv_count, const float* w, int32_t k, int32_t groups,
+                      int32_t group_c, int32_t group_stride, float* dmean, int64_t dmean_stride, float* dw,
+                      pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!dgate || !gate || !pool_sum || !w || !dmean || n < 1) {
+    set_error("eca_gate_bwd: bad arguments");
+    return PMOE_ERR_ARG;
+  }
+  eca_gate_bwd_kernel<<<n, 128, groups * group_c * sizeof(float), stream>>>(dgate, dgate_stride, gate, gate_stride, pool_sum,
+                                                                            pool_stride, inv_count, w, k, groups, group_c,
+                                                                            group_stride, dmean, dmean_stride, dw);
+  return check_launch("eca_gate_bwd");
+}
+
+int pmoe_eca_bwd_apply(const PmoeView4* dout, int32_t dtype, const float* gate, int64_t gate_stride, const float* dmean,
+                       int64_t dmean_stride, const PmoeView4* dx, int32_t accumulate, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = chk(dout, dtype, "eca_bwd_apply dout"))) return rc;
+  if ((rc = chk(dx, dtype, "eca_bwd_apply dx"))) return rc;
+  if (!gate || !dmean || ((uintptr_t)gate % 16) || ((uintptr_t)dmean % 16) || gate_stride % 4 || dmean_stride % 4) {
+    set_error("eca_bwd_apply: gate/dmean must be 16-byte aligned rows");
+    return PMOE_ERR_ARG;
+  }
+  const long long items = (long long)dx->n * dx->h * dx->w * (dx->c / 8);
+  BW_DISPATCH(dtype, (eca_bwd_apply_kernel<T><<<bgrid(items, 256), 256, 0, stream>>>(bv4(dout), gate, gate_stride, dmean, dmean_stride, bv4(dx), accumulate)));
+  return check_launch("eca_bwd_apply");
+}
+
+int pmoe_axpy(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, float alpha, const float* bcast, int64_t bcast_stride,
+              int32_t accumulate, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = chk(src, dtype, "axpy src", true))) return rc;
+  if ((rc = chk(dst, dtype, "axpy dst"))) return rc;
+  if (bcast && (((uintptr_t)bcast % 16) || bcast_stride % 4)) {
+    set_error("axpy: broadcast rows must be 16-byte aligned");
+    return PMOE_ERR_ARG;
+  }
+  const long long items = (long long)dst->n * dst->h * dst->w * (dst->c / 8);
+  BW_DISPATCH(dtype, (axpy_kernel<T><<<bgrid(items, 256), 256, 0, stream>>>(bv4(src), bv4(dst), alpha, bcast, bcast_stride, accumulate)));
+  return check_launch("axpy");
+}
+
+}  // extern "C"

@@ -7,7 +7,7 @@ affines are derived caches keyed on the parameters' versions — never part of t
 """
 import torch
 
-from . import nhwc, ops
+from . import config, nhwc, ops
 from .nhwc import Act
 from .ops import TAPS3, pad_ch
 
@@ -36,9 +36,9 @@ def folded_bn(bn, cout_pad):
 
 def packed_conv(conv, groups, group_pads, taps, cout_pad, name="w"):
     """conv.weight (Cout, sum(groups), R, S) -> [cout_pad, K] bf16 in (tap, group, padded channel) order."""
-    key = "%s_%s_%s_%d" % (name, "-".join(map(str, groups)), "-".join(map(str, group_pads)), cout_pad)
+    key = "%s_%s_%s_%d_%s" % (name, "-".join(map(str, groups)), "-".join(map(str, group_pads)), cout_pad, config.precision())
     return cached(conv, key, [conv.weight],
-                  lambda: ops.pack_conv_weight(conv.weight.detach().float(), groups, group_pads, taps, cout_pad))
+                  lambda: ops.pack_conv_weight(conv.weight.detach().float(), groups, group_pads, taps, cout_pad, config.act_dtype()))
 
 
 def padded_bias(mod, cout_pad):
@@ -72,9 +72,9 @@ def conv_eval(srcs, conv, bn=None, act=None, out=None, residual=None, pool=None,
         shift = padded_bias(conv, cop) if conv.bias is not None else None
     n, h, w, _ = srcs[0].t.shape
     if out is None:
-        out = torch.empty(n, h, w, pad_ch(cout), dtype=torch.bfloat16, device=srcs[0].t.device)
-    ops.conv_tc([a.t for a in srcs], wp, segs, ck, out, scale, shift, act, None if residual is None else residual.t,
-                None, None, pool, pool_stride=pool_stride,
+        out = torch.empty(n, h, w, pad_ch(cout), dtype=config.act_dtype(), device=srcs[0].t.device)
+    ops.conv([a.t for a in srcs], wp, segs, ck, out, scale=scale, shift=shift, act=act,
+             residual=None if residual is None else residual.t, pool_sum=pool, pool_stride=pool_stride,
                 flops=2.0 * n * h * w * cout * sum(glog) * len(taps), tag="%dx%d %d->%d k%d" % (h, w, sum(glog), cout, ksize))
     return Act(out, cout)
 
@@ -90,17 +90,17 @@ def conv_transpose_eval(up, x):
     cin, cout = up.weight.shape[0], up.weight.shape[1]
     cop = ops.cout_padded(cout)
     n, h, w, cp = x.t.shape
-    out = torch.empty(n, 2 * h, 2 * w, pad_ch(cout), dtype=torch.bfloat16, device=x.t.device)
+    out = torch.empty(n, 2 * h, 2 * w, pad_ch(cout), dtype=config.act_dtype(), device=x.t.device)
     ck = ops.choose_ck([cp])
     segs = ops.conv_segments([(0, 0)], [cp], ck)
     shift = padded_bias(up, cop)
     for a in range(2):
         for b in range(2):
-            wp = cached(up, "wq%d%d_%d_%d" % (a, b, cp, cop), [up.weight],
+            wp = cached(up, "wq%d%d_%d_%d_%s" % (a, b, cp, cop, config.precision()), [up.weight],
                         lambda: ops.pack_conv_weight(up.weight.detach().float()[:, :, a, b].t().reshape(cout, cin, 1, 1),
-                                                     [cin], [cp], [(0, 0)], cop))
-            ops.conv_tc([x.t], wp, segs, ck, out[:, a::2, b::2, :], None, shift, None,
-                        flops=2.0 * n * h * w * cin * cout, tag="convT %dx%d %d->%d" % (h, w, cin, cout))
+                                                     [cin], [cp], [(0, 0)], cop, config.act_dtype()))
+            ops.conv([x.t], wp, segs, ck, out[:, a::2, b::2, :], shift=shift,
+                     flops=2.0 * n * h * w * cin * cout, tag="convT %dx%d %d->%d" % (h, w, cin, cout))
     return Act(out, cout)
 
 
@@ -127,9 +127,9 @@ def unet_eval(net, x, out=None, out_pool=None, pool_stride=0, want_inter=False):
     cop = ops.cout_padded(ncls)
     wp = packed_conv(net.out, [64], [64], [(0, 0)], cop)
     if out is None:
-        out = torch.empty(n, h, w, pad_ch(ncls), dtype=torch.bfloat16, device=x.t.device)
-    ops.conv_tc([y.t], wp, ops.conv_segments([(0, 0)], [64], 64), 64, out, None, padded_bias(net.out, cop), None, None, None,
-                None, out_pool, pool_stride=pool_stride, flops=2.0 * n * h * w * 64 * ncls, tag="out1x1 %dx%d" % (h, w))
+        out = torch.empty(n, h, w, pad_ch(ncls), dtype=config.act_dtype(), device=x.t.device)
+    ops.conv([y.t], wp, ops.conv_segments([(0, 0)], [64], 64), 64, out, shift=padded_bias(net.out, cop), pool_sum=out_pool,
+             pool_stride=pool_stride, flops=2.0 * n * h * w * 64 * ncls, tag="out1x1 %dx%d" % (h, w))
     inter = None
     if want_inter:
         inter = inter_sum / float(x5.t.shape[1] * x5.t.shape[2])
@@ -165,11 +165,11 @@ def punet_eval(net, images):
     slot = pad_ch(ncls)
     dev = images.device
     nslots = P + max(Fu, 0)
-    ring = torch.empty(B, H, W, nslots * slot, dtype=torch.bfloat16, device=dev)
+    ring = torch.empty(B, H, W, nslots * slot, dtype=config.act_dtype(), device=dev)
     pools = torch.zeros(B, nslots * slot, dtype=torch.float32, device=dev)
     inter = None
     for t in range(P):
-        x = nhwc.from_nchw(images[:, t])
+        x = nhwc.from_nchw(images[:, t], dtype=config.act_dtype())
         _, it = unet_eval(net.unet, x, out=ring[..., t * slot:(t + 1) * slot], out_pool=pools[:, t * slot:],
                           pool_stride=nslots * slot, want_inter=(net.unet_inter_repr and Fu == 0 and t == P - 1))
         inter = it

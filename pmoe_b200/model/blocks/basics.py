@@ -9,7 +9,7 @@ from typing import List
 import torch
 import torch.nn as nn
 
-from ... import infer, nhwc, train
+from ... import config, infer, nhwc, train
 
 _ACT_NAMES = {"relu": "relu", "tanh": "tanh", "sigmoid": "sigmoid", "elu": "elu"}
 
@@ -53,11 +53,9 @@ class Conv3Block(nn.Sequential):
     """conv3 (basics.py:48-59): children 0,1,3,4 carry the parameters; 2,5 are the ReLU placeholders."""
 
     def forward(self, x):  # x: NCHW fp32 (stand-alone use); the enclosing networks call the NHWC paths directly
-        a = nhwc.from_nchw(x)
         if _grad_mode(self):
-            y = train.conv3_block(self, [a])
-        else:
-            y = infer.conv3_block_eval(self, [a])
+            return train.nhwc_module_forward(self, x, lambda tape, a: train.conv3_block(tape, self, [a])[0])
+        y = infer.conv3_block_eval(self, [nhwc.from_nchw(x, dtype=config.act_dtype())])
         return nhwc.to_nchw(y.t, y.c)
 
 
@@ -85,14 +83,12 @@ class EfficientBlock(nn.Module):
         self.conv = nn.Conv1d(1, 1, kernel_size=k, padding=int(k / 2), bias=False)
 
     def forward(self, x):
-        a = nhwc.from_nchw(x)
         if _grad_mode(self):
-            y = train.eca(self, a)
-        else:
-            sums = nhwc.channel_sums(a.t)
-            gate = nhwc.eca_gate(sums, a.t.shape[1] * a.t.shape[2], self.conv.weight, 1, a.c, a.cpad)
-            y = nhwc.Act(nhwc.scale_channels(a.t, gate), a.c)
-        return nhwc.to_nchw(y.t, y.c)
+            return train.nhwc_module_forward(self, x, lambda tape, a: train.eca_op(tape, self, a))
+        a = nhwc.from_nchw(x, dtype=config.act_dtype())
+        sums = nhwc.channel_sums(a.t)
+        gate = nhwc.eca_gate(sums, a.t.shape[1] * a.t.shape[2], self.conv.weight, 1, a.c, a.cpad)
+        return nhwc.to_nchw(nhwc.scale_channels(a.t, gate), a.c)
 
 
 class EfficientConvBlock(nn.Module):
@@ -113,10 +109,9 @@ class EfficientConvBlock(nn.Module):
                                     nn.BatchNorm2d(out_ch), nn.ReLU(inplace=True)))]))
 
     def forward(self, x):
-        a = nhwc.from_nchw(x)
         if _grad_mode(self):
-            y = train.eca_conv_block(self, a)
-        else:
-            sums = nhwc.channel_sums(a.t)
-            y = infer.eca_conv_block_eval(self, a.t, (1, a.c, a.cpad), sums, a.t.shape[1] * a.t.shape[2])
+            return train.nhwc_module_forward(self, x, lambda tape, a: train.eca_conv_block(tape, self, a))
+        a = nhwc.from_nchw(x, dtype=config.act_dtype())
+        sums = nhwc.channel_sums(a.t)
+        y = infer.eca_conv_block_eval(self, a.t, (1, a.c, a.cpad), sums, a.t.shape[1] * a.t.shape[2])
         return nhwc.to_nchw(y.t, y.c)

@@ -2,7 +2,7 @@
 import torch
 import torch.nn as nn
 
-from ... import infer, nhwc, train
+from ... import config, infer, nhwc, train
 from .basics import conv3, _grad_mode
 
 
@@ -26,13 +26,11 @@ class UNet(nn.Module):
 
     def forward(self, image):
         """image: fp32 (B,C,H,W) on the GPU -> logits (B,classes,H,W) [, after (B,512) if inter_repr]."""
-        x = nhwc.from_nchw(image)
         if _grad_mode(self):
-            logits, inter = train.unet(self, x, want_inter=self.inter_repr)
-            out = train.to_nchw(logits)
-        else:
-            logits, inter = infer.unet_eval(self, x, want_inter=self.inter_repr)
-            out = nhwc.to_nchw(logits.t, logits.c)
+            return train.unet_module_forward(self, image)
+        x = nhwc.from_nchw(image, dtype=config.act_dtype())
+        logits, inter = infer.unet_eval(self, x, want_inter=self.inter_repr)
+        out = nhwc.to_nchw(logits.t, logits.c)
         if self.inter_repr:
             return inter, out
         return out

@@ -29,5 +29,5 @@ class PredictiveUnet(nn.Module):
     def forward(self, img_list: torch.Tensor) -> torch.Tensor:
         assert img_list.shape[-4] == self.n_past_frames, "Number of images should match number of past frames"
         if _grad_mode(self):
-            return train.punet(self, img_list)
+            return train.punet_module_forward(self, img_list)
         return infer.punet_eval(self, img_list)

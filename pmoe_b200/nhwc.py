@@ -18,10 +18,10 @@ def dtype_code(t):
 
 class Act:
     """An NHWC activation: tensor (N,H,W,Cpad) with `c` logical channels; channels [c, Cpad) are zero."""
-    __slots__ = ("t", "c")
+    __slots__ = ("t", "c", "rg")
 
-    def __init__(self, t, c):
-        self.t, self.c = t, c
+    def __init__(self, t, c, rg=False):
+        self.t, self.c, self.rg = t, c, rg
 
     @property
     def shape(self):

@@ -74,16 +74,14 @@ def pad_vec(v, n, fill=0.0):
     return out
 
 
-def conv_tc(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residual=None, stat_sum=None,
-            stat_sqsum=None, pool_sum=None, src_channels=None, pool_stride=0, flops=0.0, tag=""):
-    """Launch the tcgen05 implicit-GEMM kernel. srcs: list of NHWC bf16 tensors (views allowed);
-    out: NHWC bf16 tensor/view; wpack: [cout_pad, ktot] bf16."""
+def _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum, stat_sqsum, pool_sum, src_channels,
+               pool_stride, dtype):
     d = _lib.ConvTc()
     assert 1 <= len(srcs) <= _lib.MAX_SRC and 1 <= len(segs) <= _lib.MAX_SEG, (len(srcs), len(segs))
     d.n_src = len(srcs)
     for i, s in enumerate(srcs):
         _lib.require_cuda(s, "conv source")
-        assert s.dtype == torch.bfloat16
+        assert s.dtype == dtype, (s.dtype, dtype)
         d.src[i] = _lib.view4(s, None if src_channels is None else src_channels[i])
     d.n_seg = len(segs)
     for i, (src, dh, dw, c0, nch) in enumerate(segs):
@@ -91,9 +89,9 @@ def conv_tc(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residu
     d.ck = ck
     d.ktot = wpack.shape[1]
     d.cout_pad = wpack.shape[0]
-    assert wpack.dtype == torch.bfloat16 and wpack.is_contiguous()
+    assert wpack.is_contiguous()
     d.wpack = wpack.data_ptr()
-    assert out.dtype == torch.bfloat16
+    assert out.dtype == dtype, (out.dtype, dtype)
     d.out = _lib.view4(out)
     d.scale = None if scale is None else scale.data_ptr()
     d.shift = None if shift is None else shift.data_ptr()
@@ -103,7 +101,51 @@ def conv_tc(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residu
     d.stat_sqsum = None if stat_sqsum is None else stat_sqsum.data_ptr()
     d.pool_sum = None if pool_sum is None else pool_sum.data_ptr()
     d.pool_stride = int(pool_stride) if pool_stride else (pool_sum.stride(0) if pool_sum is not None and pool_sum.dim() == 2 else 0)
+    return d
+
+
+def conv_tc(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residual=None, stat_sum=None,
+            stat_sqsum=None, pool_sum=None, src_channels=None, pool_stride=0, flops=0.0, tag=""):
+    """Launch the tcgen05 implicit-GEMM kernel. srcs: list of NHWC bf16 tensors (views allowed);
+    out: NHWC bf16 tensor/view; wpack: [cout_pad, ktot] bf16."""
+    assert wpack.dtype == torch.bfloat16
+    d = _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum, stat_sqsum, pool_sum, src_channels,
+                   pool_stride, torch.bfloat16)
     fn = _lib.lib().pmoe_conv_tc
     sp = _lib.stream_ptr()
     _lib.check(profiler.launch("conv_tc", lambda: fn(C.byref(d), sp), flops, 0.0, tag), "conv_tc")
     return out
+
+
+def conv_simt(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residual=None, stat_sum=None,
+              stat_sqsum=None, pool_sum=None, src_channels=None, pool_stride=0, flops=0.0, tag=""):
+    """CUDA-core twin of conv_tc (fp32 or bf16 storage, fp32 FMA accumulation)."""
+    dt = out.dtype
+    assert wpack.dtype == dt
+    d = _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum, stat_sqsum, pool_sum, src_channels,
+                   pool_stride, dt)
+    fn = _lib.lib().pmoe_conv_simt
+    sp = _lib.stream_ptr()
+    code = _lib.BF16 if dt == torch.bfloat16 else _lib.F32
+    _lib.check(profiler.launch("conv_simt", lambda: fn(C.byref(d), code, sp), flops, 0.0, tag), "conv_simt")
+    return out
+
+
+def conv(srcs, wpack, segs, ck, out, **kw):
+    """bf16 -> tensor cores, fp32 -> CUDA cores. Same arguments as conv_tc."""
+    from . import config
+    if out.dtype == torch.bfloat16 and not config.FORCE_SIMT:
+        return conv_tc(srcs, wpack, segs, ck, out, **kw)
+    return conv_simt(srcs, wpack, segs, ck, out, **kw)
+
+
+def conv_wgrad(srcs, segs, ck, dy, dwpack, flops=0.0, tag=""):
+    """dwpack[cout_pad, ktot] (fp32) += sum_pixels dy[p, co] * x_k[p] in the packed K order of the forward."""
+    dt = dy.dtype
+    d = _fill_desc(srcs, dwpack, segs, ck, dy, None, None, None, None, None, None, None, None, 0, dt)
+    assert dwpack.dtype == torch.float32
+    fn = _lib.lib().pmoe_conv_wgrad_simt
+    sp = _lib.stream_ptr()
+    code = _lib.BF16 if dt == torch.bfloat16 else _lib.F32
+    _lib.check(profiler.launch("conv_wgrad", lambda: fn(C.byref(d), code, dwpack.data_ptr(), sp), flops, 0.0, tag), "conv_wgrad")
+    return dwpack

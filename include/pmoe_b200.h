@@ -101,6 +101,8 @@ int pmoe_scale_channels(const PmoeView4* src, const PmoeView4* dst, int32_t dtyp
                         pmoe_stream_t stream);
 /* out[n][c] += sum over h,w (adaptive_avg_pool2d numerator, basics.py:72, unet.py:90). */
 int pmoe_channel_sums(const PmoeView4* src, int32_t dtype, float* out, int64_t out_stride, pmoe_stream_t stream);
+/* sum[c], sqsum[c] += over n,h,w (batch statistics of a BatchNorm not fed by a conv epilogue: ResNet bn1). */
+int pmoe_channel_stats(const PmoeView4* src, int32_t dtype, float* sum, float* sqsum, pmoe_stream_t stream);
 /* nn.BatchNorm2d training step (basics.py:52,55): batch stats from (sum, sumsq), running-stat update, fused affine. */
 int pmoe_bn_finalize(const float* sum, const float* sqsum, float count, int32_t c, int32_t c_pad, const float* gamma,
                      const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* mean_out,

@@ -10,6 +10,7 @@ SIGS = {
     "pmoe_eca_gate": [vp, i64, i32, f32, vp, i32, i32, i32, i32, vp, i64, vp],
     "pmoe_scale_channels": [vp, vp, i32, vp, i64, vp],
     "pmoe_channel_sums": [vp, i32, vp, i64, vp],
+    "pmoe_channel_stats": [vp, i32, vp, vp, vp],
     "pmoe_bn_finalize": [vp, vp, f32, i32, i32, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp, vp],
     "pmoe_affine_act": [vp, vp, i32, vp, vp, vp, i32, vp],
     "pmoe_conv_simt": [vp, i32, vp],

@@ -224,6 +224,38 @@ __global__ void channel_sums_kernel(V4 src, float* __restrict__ out, long long o
   }
 }
 
+// ---------------------------------------------------------------- per-channel sum / sum of squares over N,H,W
+// (batch statistics for a BatchNorm that does not directly follow one of our conv epilogues: ResNet bn1)
+template <typename T>
+__global__ void channel_stats_kernel(V4 src, float* __restrict__ sum, float* __restrict__ sq, long long pix_per_block) {
+  const int cg = src.c / 8;
+  const int lanes = blockDim.x / cg;
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+  if (lane >= lanes) return;
+  const long long npix = (long long)src.n * src.h * src.w;
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > npix) p1 = npix;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (long long p = p0 + lane; p < p1; p += lanes) {
+    const int w = (int)(p % src.w);
+    const long long t = p / src.w;
+    const int h = (int)(t % src.h), n = (int)(t / src.h);
+    float v[8];
+    load8(static_cast<const T*>(src.ptr) + n * src.sn + h * src.sh + w * src.sw + g * 8, v);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      a[q] += v[q];
+      b[q] += v[q] * v[q];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    atomicAdd(sum + g * 8 + q, a[q]);
+    atomicAdd(sq + g * 8 + q, b[q]);
+  }
+}
+
 // ---------------------------------------------------------------- BatchNorm (train): finalize + apply
 // Finalize: batch mean / biased var from (sum, sumsq), running-stat update exactly as
 // nn.BatchNorm2d (momentum 0.1, unbiased variance), and the fused affine (scale, shift).
@@ -392,6 +424,23 @@ int pmoe_channel_sums(const PmoeView4* src, int32_t dtype, float* out, int64_t o
   dim3 grid((unsigned)((hw + rows - 1) / rows), (unsigned)src->n);
   DISPATCH_DTYPE(dtype, (channel_sums_kernel<T><<<grid, 256, 0, stream>>>(to_v4(*src), out, out_stride, rows)));
   return check_launch("channel_sums");
+}
+
+int pmoe_channel_stats(const PmoeView4* src, int32_t dtype, float* sum, float* sqsum, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_view(src, dtype, "channel_stats");
+  if (rc) return rc;
+  if (!sum || !sqsum || src->c / 8 > 256) {
+    set_error("channel_stats: bad arguments");
+    return PMOE_ERR_ARG;
+  }
+  const long long npix = (long long)src->n * src->h * src->w;
+  long long blocks = (long long)num_sms() * 8;
+  long long ppb = (npix + blocks - 1) / blocks;
+  if (ppb < 64) ppb = 64;
+  blocks = (npix + ppb - 1) / ppb;
+  DISPATCH_DTYPE(dtype, (channel_stats_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(to_v4(*src), sum, sqsum, ppb)));
+  return check_launch("channel_stats");
 }
 
 int pmoe_bn_finalize(const float* sum, const float* sqsum, float count, int32_t c, int32_t c_pad, const float* gamma,

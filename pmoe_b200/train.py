@@ -75,59 +75,6 @@ def _any_rg(params):
 
 
 # ------------------------------------------------------------------------------------------------ weight packing
-def _layout_of(srcs, layouts):
-    """Per physical source: list of (logical, padded) channel groups."""
-    out = []
-    for i, a in enumerate(srcs):
-        out.append([(a.c, a.cpad)] if layouts is None or layouts[i] is None else list(layouts[i]))
-    return out
-
-
-def _pack_fwd(w, layouts, taps, cop, dtype):
-    glog = [g[0] for lay in layouts for g in lay]
-    gpad = [g[1] for lay in layouts for g in lay]
-    return ops.pack_conv_weight(w.detach().float(), glog, gpad, taps, cop, dtype)
-
-
-def _unpack_wgrad(dwp, w_shape, layouts, ntaps):
-    """[cop, ktot] packed gradient -> (cout, cin, R, S)."""
-    cout, cin, R, S = w_shape
-    gpad_total = sum(g[1] for lay in layouts for g in lay)
-    d = dwp[:cout].reshape(cout, ntaps, gpad_total)
-    parts, off = [], 0
-    for lay in layouts:
-        for (gl, gp) in lay:
-            parts.append(d[:, :, off:off + gl])
-            off += gp
-    d = torch.cat(parts, dim=2)  # (cout, ntaps, cin)
-    return d.permute(0, 2, 1).reshape(cout, cin, R, S)
-
-
-def _pack_dgrad(w, lay, cin_begin, taps, co_pad, dtype):
-    """Data-gradient weight for ONE physical source whose channels are laid out as `lay`:
-    rows = physical input channels, K = (tap, padded cout). Wd[p, t*co_pad+co] = w[co, ci(p), r_t, s_t]."""
-    cout = w.shape[0]
-    wf = w.detach().float()
-    rows = []
-    ci = cin_begin
-    for (gl, gp) in lay:
-        blk = wf[:, ci:ci + gl]                                   # (cout, gl, R, S)
-        blk = torch.stack([blk[:, :, r, s] for (r, s) in taps], 0)  # (ntaps, cout, gl)
-        blk = blk.permute(2, 0, 1)                                # (gl, ntaps, cout)
-        if co_pad > cout:
-            blk = torch.nn.functional.pad(blk, (0, co_pad - cout))
-        blk = blk.reshape(gl, len(taps) * co_pad)
-        if gp > gl:
-            blk = torch.nn.functional.pad(blk, (0, 0, 0, gp - gl))
-        rows.append(blk)
-        ci += gl
-    wd = torch.cat(rows, 0)
-    rows_pad = ops.cout_padded(wd.shape[0])
-    if rows_pad > wd.shape[0]:
-        wd = torch.nn.functional.pad(wd, (0, 0, 0, rows_pad - wd.shape[0]))
-    return wd.to(dtype).contiguous()
-
-
 # ------------------------------------------------------------------------------------------------ raw launch helpers
 def _bn_bwd_reduce(dz, z, x, act, mean, rstd, cpad):
     s1 = torch.zeros(cpad, dtype=torch.float32, device=dz.device)
@@ -181,59 +128,212 @@ def _grad_buffer(tape, act):
 
 
 # ------------------------------------------------------------------------------------------------ conv (+BN +act +residual)
+class Src:
+    """One physical K-source of a conv: `t` (NHWC tensor/view) belongs to Act `act`; it carries the weight's input
+    channels [cin0, cin0 + sum(logical)) laid out as `lay` = [(logical, padded)...]; `sel(g)` maps a gradient buffer
+    of `act` to the view that corresponds to `t` (identity unless `t` is a spatial parity view)."""
+    __slots__ = ("act", "t", "cin0", "lay", "sel")
+
+    def __init__(self, act, t=None, cin0=0, lay=None, sel=None):
+        self.act = act
+        self.t = act.t if t is None else t
+        self.cin0 = cin0
+        self.lay = [(act.c, self.t.shape[3])] if lay is None else list(lay)
+        self.sel = sel if sel is not None else (lambda g: g)
+
+    @property
+    def cpad(self):
+        return self.t.shape[3]
+
+    @property
+    def nlog(self):
+        return sum(g[0] for g in self.lay)
+
+
+def concat_sources(acts, layouts=None):
+    """Virtual channel concat: source i carries the next block of the weight's input channels."""
+    out, c0 = [], 0
+    for i, a in enumerate(acts):
+        s = Src(a, None, c0, None if layouts is None else layouts[i])
+        out.append(s)
+        c0 += s.nlog
+    return out
+
+
+def default_segdefs(nsrc, ksize):
+    pad = ksize // 2
+    return [(i, r - pad, s - pad, r, s) for r in range(ksize) for s in range(ksize) for i in range(nsrc)]
+
+
+def stride2_sources(x, ksize):
+    """Sources + segment definitions of a stride-2 conv (k=3,p=1 or k=1,p=0) as stride-1 taps over the four
+    spatial parity views of x (ih = 2*oh - pad + r)."""
+    views = {}
+    srcs, segdefs = [], []
+
+    def view(p, q):
+        if (p, q) not in views:
+            views[(p, q)] = len(srcs)
+            srcs.append(Src(x, x.t[:, p::2, q::2, :], 0, None, (lambda g, p=p, q=q: g[:, p::2, q::2, :])))
+        return views[(p, q)]
+
+    if ksize == 1:
+        segdefs.append((view(0, 0), 0, 0, 0, 0))
+    else:
+        par = {0: (1, -1), 1: (0, 0), 2: (1, 0)}  # tap r -> (row parity, row offset in that view)
+        for r in range(3):
+            for s in range(3):
+                (p, dh), (q, dw) = par[r], par[s]
+                segdefs.append((view(p, q), dh, dw, r, s))
+    return srcs, segdefs
+
+
+def _pack_cols(wf, src, r, s):
+    """(cout, padded channels of src) block of the weight for tap (r, s)."""
+    cols, ci = [], src.cin0
+    for (gl, gp) in src.lay:
+        blk = wf[:, ci:ci + gl, r, s]
+        if gp > gl:
+            blk = torch.nn.functional.pad(blk, (0, gp - gl))
+        cols.append(blk)
+        ci += gl
+    return cols
+
+
+def _pack_fwd(weight, srcs, segdefs, cop, dtype):
+    def build():
+        wf = weight.detach().float()
+        cols = []
+        for (i, _, _, r, s) in segdefs:
+            cols += _pack_cols(wf, srcs[i], r, s)
+        wp = torch.cat(cols, dim=1)
+        if cop > wp.shape[0]:
+            wp = torch.nn.functional.pad(wp, (0, 0, 0, cop - wp.shape[0]))
+        return wp.to(dtype).contiguous()
+    key = "f|%s|%s|%d|%s" % (";".join("%d:%s" % (x.cin0, x.lay) for x in srcs), segdefs, cop, dtype)
+    return _cached_pack(weight, key, build)
+
+
+def _owner(weight):
+    return getattr(weight, "owner", weight)
+
+
+def _cached_pack(weight, key, build):
+    weight = _owner(weight)
+    cache = weight.__dict__.setdefault("_pmoe_pack", {})
+    ver = (weight.data_ptr(), weight._version)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    val = build()
+    if len(cache) > 8:
+        cache.clear()
+    cache[key] = (ver, val)
+    return val
+
+
+def _unpack_wgrad(dwp, weight, srcs, segdefs):
+    cout = weight.shape[0]
+    gw = torch.zeros(weight.shape, dtype=torch.float32, device=dwp.device)
+    off = 0
+    for (i, _, _, r, s) in segdefs:
+        src = srcs[i]
+        ci, o = src.cin0, off
+        for (gl, gp) in src.lay:
+            gw[:, ci:ci + gl, r, s] += dwp[:cout, o:o + gl]
+            ci += gl
+            o += gp
+        off += src.cpad
+    return gw
+
+
+def _pack_dgrad(weight, src, segs_i, co_pad, dtype):
+    """rows = physical channels of `src`, K = (segment of this source, padded cout)."""
+    def build():
+        wf = weight.detach().float()
+        cout = wf.shape[0]
+        blocks = []
+        for (_, _, _, r, s) in segs_i:
+            blk = torch.cat(_pack_cols(wf, src, r, s), dim=1).t()  # (phys channels, cout)
+            if co_pad > cout:
+                blk = torch.nn.functional.pad(blk, (0, co_pad - cout))
+            blocks.append(blk)
+        wd = torch.cat(blocks, dim=1)
+        rows_pad = ops.cout_padded(wd.shape[0])
+        if rows_pad > wd.shape[0]:
+            wd = torch.nn.functional.pad(wd, (0, 0, 0, rows_pad - wd.shape[0]))
+        return wd.to(dtype).contiguous()
+    key = "d|%d:%s|%s|%d|%s" % (src.cin0, src.lay, segs_i, co_pad, dtype)
+    return _cached_pack(weight, key, build)
+
+
+def _bn_tail_forward(tape, bn, raw, ssum, ssq, count, cout, cstore, act, residual, out):
+    track = bn.track_running_stats and bn.running_mean is not None
+    mom = 0.1 if bn.momentum is None else bn.momentum
+    mean, rstd, scale, shift = nhwc.bn_finalize(ssum, ssq, count, cout, bn.weight.detach(), bn.bias.detach(), bn.eps, mom,
+                                                bn.running_mean if track else None, bn.running_var if track else None)
+    if track and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    z_t = out if out is not None else torch.empty(raw.shape, dtype=raw.dtype, device=raw.device)
+    nhwc.affine_act(raw, scale[:cstore], shift[:cstore], act, None if residual is None else residual.t, out=z_t)
+    return z_t, mean, rstd
+
+
+def _eval_affine(bn, bias, cout, cop):
+    if bn is not None:
+        def build():
+            scale = ops.pad_vec(bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps), cop, 0.0)
+            shift = ops.pad_vec(bn.bias.detach().float() - bn.running_mean.float() * scale[:cout], cop, 0.0)
+            return scale, shift
+        from .infer import cached
+        return cached(bn, "evalaff%d" % cop, [bn.weight, bn.bias, bn.running_mean, bn.running_var], build)
+    if bias is not None:
+        return None, ops.pad_vec(bias.detach(), cop, 0.0)
+    return None, None
+
+
 def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, want_pool=False, ksize=3, layouts=None,
-            taps=None, out=None, pool_out=None, pool_stride=0, tag=""):
-    """conv / linear layer over the virtual concat of `srcs`, followed by BatchNorm (batch statistics when
-    bn.training, folded running statistics otherwise), optional residual add and activation.
+            segdefs=None, out=None, pool_out=None, pool_stride=0, out_hw=None, tag=""):
+    """conv / linear layer over `srcs` (list of Act = virtual channel concat, or list of Src), followed by BatchNorm
+    (batch statistics when bn.training, folded running statistics otherwise), optional residual add and activation.
     Returns (Act z, pool_sum or None)."""
     dt = tape.dtype
+    if not isinstance(srcs[0], Src):
+        srcs = concat_sources(srcs, layouts)
     dev = srcs[0].t.device
     cout = weight.shape[0]
-    cop = ops.cout_padded(cout)
-    cstore = pad_ch(cout)
-    lays = _layout_of(srcs, layouts)
-    phys = [a.cpad for a in srcs]
+    cop, cstore = ops.cout_padded(cout), pad_ch(cout)
+    if segdefs is None:
+        segdefs = default_segdefs(len(srcs), ksize)
+    phys = [x.cpad for x in srcs]
     ck = ops.choose_ck(phys)
-    if taps is None:
-        taps = TAPS3 if ksize == 3 else [(0, 0)]
-    pad = ksize // 2
-    tap_off = [(r - pad, s - pad) for (r, s) in taps]
-    segs = ops.conv_segments(tap_off, phys, ck)
-    wp = _pack_fwd(weight, lays, taps, cop, dt)
+    segs = [(i, dh, dw, 0, phys[i] // ck) for (i, dh, dw, _, _) in segdefs]
+    wp = _pack_fwd(weight, srcs, segdefs, cop, dt)
     n, h, w, _ = srcs[0].t.shape
-    cin = weight.shape[1]
-    flops = 2.0 * n * h * w * cout * cin * len(taps)
+    if out_hw is not None:
+        h, w = out_hw
+    flops = 2.0 * n * h * w * cout * sum(srcs[i].nlog for (i, _, _, _, _) in segdefs)
     bn_train = bn is not None and bn.training
-    rg_in = any(_rg(a) for a in srcs) or _any_rg([weight, bias]) or (bn is not None and _any_rg([bn.weight, bn.bias])) \
+    rg_in = any(_rg(x.act) for x in srcs) or _any_rg([_owner(weight), bias]) or (bn is not None and _any_rg([bn.weight, bn.bias])) \
         or (residual is not None and _rg(residual))
     pool = None
     if want_pool:
         pool = pool_out if pool_out is not None else torch.zeros(n, cop, dtype=torch.float32, device=dev)
     raw = mean = rstd = gamma_p = scale = None
+    src_ts = [x.t for x in srcs]
     if bn_train:
         raw = torch.empty(n, h, w, cstore, dtype=dt, device=dev)
         ssum = torch.zeros(cop, dtype=torch.float32, device=dev)
         ssq = torch.zeros(cop, dtype=torch.float32, device=dev)
-        ops.conv([a.t for a in srcs], wp, segs, ck, raw, stat_sum=ssum, stat_sqsum=ssq, flops=flops, tag=tag)
-        track = bn.track_running_stats and bn.running_mean is not None
-        mom = 0.1 if bn.momentum is None else bn.momentum
-        mean, rstd, scale, shift = nhwc.bn_finalize(ssum, ssq, n * h * w, cout, bn.weight.detach(), bn.bias.detach(), bn.eps, mom,
-                                                    bn.running_mean if track else None, bn.running_var if track else None)
-        if track and bn.num_batches_tracked is not None:
-            bn.num_batches_tracked += 1
-        z_t = out if out is not None else torch.empty(n, h, w, cstore, dtype=dt, device=dev)
-        nhwc.affine_act(raw, scale[:cstore], shift[:cstore], act, None if residual is None else residual.t, out=z_t)
+        ops.conv(src_ts, wp, segs, ck, raw, stat_sum=ssum, stat_sqsum=ssq, flops=flops, tag=tag)
+        z_t, mean, rstd = _bn_tail_forward(tape, bn, raw, ssum, ssq, n * h * w, cout, cstore, act, residual, out)
         if want_pool:
             nhwc.channel_sums(z_t, out=pool)
         gamma_p = ops.pad_vec(bn.weight.detach(), cstore, 0.0)
     else:
-        if bn is not None:
-            scale = ops.pad_vec(bn.weight.detach().float() / torch.sqrt(bn.running_var.float() + bn.eps), cop, 0.0)
-            shift = ops.pad_vec(bn.bias.detach().float() - bn.running_mean.float() * scale[:cout], cop, 0.0)
-        else:
-            shift = ops.pad_vec(bias.detach(), cop, 0.0) if bias is not None else None
+        scale, shift = _eval_affine(bn, bias, cout, cop)
         z_t = out if out is not None else torch.empty(n, h, w, cstore, dtype=dt, device=dev)
-        ops.conv([a.t for a in srcs], wp, segs, ck, z_t, scale=scale, shift=shift, act=act,
+        ops.conv(src_ts, wp, segs, ck, z_t, scale=scale, shift=shift, act=act,
                  residual=None if residual is None else residual.t, pool_sum=pool, pool_stride=pool_stride, flops=flops, tag=tag)
     z = _new_act(tape, z_t, cout, rg_in)
     if not (tape.save and rg_in):
@@ -244,8 +344,7 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
         if dz is None:
             return
         z_saved = z_t if act not in (None, "none") else None
-        dres = None
-        acc_dres = False
+        dres, acc_dres = None, False
         if residual is not None and _rg(residual):
             dres, acc_dres = _grad_buffer(tape, residual)
         dy = torch.empty(n, h, w, cstore, dtype=dt, device=dev)  # gradient w.r.t. the raw conv output
@@ -264,21 +363,29 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
                           0.0, 0, dy, dres, acc_dres)
         if weight.requires_grad:
             dwp = torch.zeros(cop, wp.shape[1], dtype=torch.float32, device=dev)
-            ops.conv_wgrad([a.t for a in srcs], segs, ck, dy, dwp, flops=flops, tag="wgrad " + tag)
-            tape.add_pgrad(weight, _unpack_wgrad(dwp, weight.shape, lays, len(taps)))
-        # data gradients, one launch per physical source that needs them
+            ops.conv_wgrad(src_ts, segs, ck, dy, dwp, flops=flops, tag="wgrad " + tag)
+            tape.add_pgrad(_owner(weight), _unpack_wgrad(dwp, weight, srcs, segdefs))
+        # data gradients: one launch per physical source whose owner needs them
         ck_d = ops.choose_ck([cstore])
-        dtaps = [(-dh, -dw) for (dh, dw) in tap_off]
-        cin_begin = 0
-        for a, lay in zip(srcs, lays):
-            nlog = sum(g[0] for g in lay)
-            if _rg(a):
-                wd = _pack_dgrad(weight, lay, cin_begin, taps, cstore, dt)
-                dsegs = ops.conv_segments(dtaps, [cstore], ck_d)
-                g, existed = _grad_buffer(tape, a)
-                ops.conv([dy], wd, dsegs, ck_d, g, residual=g if existed else None,
-                         flops=2.0 * n * h * w * cout * nlog * len(taps), tag="dgrad " + tag)
-            cin_begin += nlog
+        pre = {id(x.act): (id(x.act) in tape.grads) for x in srcs}
+        for i, src in enumerate(srcs):
+            if not _rg(src.act):
+                continue
+            segs_i = [sd for sd in segdefs if sd[0] == i]
+            if not segs_i:
+                continue
+            wd = _pack_dgrad(weight, src, segs_i, cstore, dt)
+            dsegs = [(0, -dh, -dw, 0, cstore // ck_d) for (_, dh, dw, _, _) in segs_i]
+            k = id(src.act)
+            if k not in tape.grads:
+                g = torch.empty(src.act.t.shape, dtype=dt, device=dev)
+                if src.t.shape != src.act.t.shape:
+                    g.zero_()  # spatial parity views: pixels that no view of this conv covers must read as zero
+                tape.grads[k] = g
+            g = tape.grads[k]
+            gv = src.sel(g)
+            ops.conv([dy], wd, dsegs, ck_d, gv, residual=gv if pre[k] else None,
+                     flops=2.0 * n * h * w * cout * src.nlog * len(segs_i), tag="dgrad " + tag)
 
     tape.record(backward)
     return z, pool
@@ -449,6 +556,279 @@ def eca_conv_block(tape, blk, x, layout=None, pool_in=None, tag="eca_block"):
     return y
 
 
+# ------------------------------------------------------------------------------------------------ ResNet-18 with ECA stem
+def bn_act_op(tape, bn, x, act="relu", tag=""):
+    """Stand-alone BatchNorm2d (+activation) on an activation that is not a fresh conv output (ResNet bn1)."""
+    dt, dev = tape.dtype, x.t.device
+    n, h, w, cp = x.t.shape
+    c = x.c
+    rg = _rg(x) or _any_rg([bn.weight, bn.bias])
+    bn_train = bn.training
+    mean = rstd = gamma_p = scale = None
+    if bn_train:
+        ssum = torch.zeros(cp, dtype=torch.float32, device=dev)
+        ssq = torch.zeros(cp, dtype=torch.float32, device=dev)
+        v = view4(x.t)
+        check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(v), dtype_code(x.t), ssum.data_ptr(),
+                                                                                ssq.data_ptr(), stream_ptr())), "channel_stats")
+        z_t, mean, rstd = _bn_tail_forward(tape, bn, x.t, ssum, ssq, n * h * w, c, cp, act, None, None)
+        gamma_p = ops.pad_vec(bn.weight.detach(), cp, 0.0)
+    else:
+        scale, shift = _eval_affine(bn, None, c, cp)
+        z_t = nhwc.affine_act(x.t, scale, shift, act)
+    z = _new_act(tape, z_t, c, rg)
+    if tape.save and rg:
+        def backward():
+            dz = tape.grad_of(z)
+            if dz is None:
+                return
+            zs = z_t if act not in (None, "none") else None
+            g, existed = _grad_buffer(tape, x)
+            tmp = g if not existed else torch.empty_like(g)
+            if bn_train:
+                s1, s2 = _bn_bwd_reduce(dz, zs, x.t, act, mean, rstd, cp)
+                tape.add_pgrad(bn.weight, s2[:c])
+                tape.add_pgrad(bn.bias, s1[:c])
+                _bn_bwd_apply(dz, zs, x.t, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, tmp, None, False)
+            else:
+                if _any_rg([bn.weight, bn.bias]):
+                    raise NotImplementedError("pmoe_b200: gradients of BatchNorm affine parameters in eval mode are not supported")
+                _bn_bwd_apply(dz, zs, None, act, None, None, scale, None, None, 0.0, 0, tmp, None, False)
+            if existed:
+                _axpy(tmp, g, 1.0, None, True)
+        tape.record(backward)
+    return z
+
+
+def basic_block(tape, blk, x, stride, want_pool=False, tag=""):
+    """torchvision BasicBlock: relu(bn2(conv2(relu(bn1(conv1(x))))) + identity) with optional 1x1/s2 downsample."""
+    if stride == 1:
+        y, _ = conv_op(tape, [x], blk.conv1.weight, None, blk.bn1, "relu", tag=tag + ".conv1")
+    else:
+        srcs, segdefs = stride2_sources(x, 3)
+        oh, ow = srcs[0].t.shape[1], srcs[0].t.shape[2]
+        y, _ = conv_op(tape, srcs, blk.conv1.weight, None, blk.bn1, "relu", segdefs=segdefs, out_hw=(oh, ow), tag=tag + ".conv1")
+    idt = x
+    if blk.downsample is not None:
+        if stride == 1:
+            idt, _ = conv_op(tape, [x], blk.downsample[0].weight, None, blk.downsample[1], None, ksize=1, tag=tag + ".down")
+        else:
+            srcs, segdefs = stride2_sources(x, 1)
+            idt, _ = conv_op(tape, srcs, blk.downsample[0].weight, None, blk.downsample[1], None, segdefs=segdefs,
+                             out_hw=(srcs[0].t.shape[1], srcs[0].t.shape[2]), tag=tag + ".down")
+    return conv_op(tape, [y], blk.conv2.weight, None, blk.bn2, "relu", residual=idt, want_pool=want_pool, tag=tag + ".conv2")
+
+
+def resnet18_eca(tape, net, x, tag="backbone"):
+    """ResNet._forward_impl with conv1 := EfficientConvBlock, fc := Identity (backbone.py:48-72) -> FeatureVec (B,512)."""
+    if x.t.shape[1] % 32 or x.t.shape[2] % 32:
+        raise RuntimeError("pmoe_b200 ResNet backbone needs H and W divisible by 32 (got %dx%d)" % (x.t.shape[1], x.t.shape[2]))
+    return resnet18_after_stem(tape, net, eca_conv_block(tape, net.conv1, x, tag=tag + ".conv1"), tag)
+
+
+def resnet18_after_stem(tape, net, stem, tag="backbone"):
+    y = bn_act_op(tape, net.bn1, stem, "relu", tag=tag + ".bn1")
+    y = maxpool_op(tape, y, 3, 2, 1)
+    pool = None
+    layers = (net.layer1, net.layer2, net.layer3, net.layer4)
+    for li, layer in enumerate(layers, start=1):
+        for bi, blk in enumerate(layer):
+            last = li == len(layers) and bi == len(layer) - 1
+            y, pool = basic_block(tape, blk, y, blk.stride, want_pool=last, tag="%s.layer%d.%d" % (tag, li, bi))
+    return InterRepr(tape, y, pool)
+
+
+# ------------------------------------------------------------------------------------------------ MLP heads
+def vec_act(tape, value_f32, c, rg=False):
+    """(B, c) fp32 tensor -> Act of shape (1,1,B,cpad) in the tape dtype (rows = the GEMM's M axis)."""
+    B = value_f32.shape[0]
+    cp = pad_ch(c)
+    buf = torch.zeros(B, cp, dtype=torch.float32, device=value_f32.device)
+    buf[:, :c] = value_f32
+    t = torch.empty(1, 1, B, cp, dtype=tape.dtype, device=value_f32.device)
+    _axpy(None, t.view(B, 1, 1, cp), 1.0, buf, False)
+    return _new_act(tape, t, c, rg)
+
+
+def feature_act(tape, inter):
+    """InterRepr (pooled backbone features) -> Act usable as a linear-layer source, wired for backward."""
+    a = vec_act(tape, inter.value, inter.x5.c, _rg(inter.x5))
+    if tape.save and _rg(inter.x5):
+        def backward():
+            g = tape.grad_of(a)
+            if g is not None:
+                inter.backward(g.view(g.shape[2], g.shape[3])[:, :inter.x5.c])
+        tape.record(backward)
+    return a
+
+
+def dropout_op(tape, x, p, training):
+    if not training or p <= 0.0:
+        return x
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    y = torch.empty_like(x.t)
+    n = x.t.numel()
+    check(profiler.launch("dropout", lambda: lib().pmoe_dropout(x.t.data_ptr(), y.data_ptr(), dtype_code(y), n, float(p), seed,
+                                                                stream_ptr())), "dropout")
+    ya = _new_act(tape, y, x.c, _rg(x))
+    if tape.save and _rg(x):
+        def backward():
+            dy = tape.grad_of(ya)
+            if dy is None:
+                return
+            g, existed = _grad_buffer(tape, x)
+            tmp = g if not existed else torch.empty_like(g)
+            check(profiler.launch("dropout", lambda: lib().pmoe_dropout(dy.data_ptr(), tmp.data_ptr(), dtype_code(tmp), n, float(p),
+                                                                        seed, stream_ptr())), "dropout")
+            if existed:
+                _axpy(tmp, g, 1.0, None, True)
+        tape.record(backward)
+    return ya
+
+
+def linear_op(tape, srcs, lin, act=None, out=None, tag=""):
+    """nn.Linear over the virtual concat of `srcs` (Acts shaped (1,1,B,C)) as a 1x1 conv."""
+    w4 = lin.weight.view(lin.weight.shape[0], lin.weight.shape[1], 1, 1)
+    return conv_op(tape, srcs, _AsConv(lin, w4), lin.bias, None, act, ksize=1, out=out, tag=tag)[0]
+
+
+class _AsConv:
+    """Presents a Linear weight (out,in) as a (out,in,1,1) conv weight while gradients land on the real Parameter."""
+
+    def __init__(self, lin, w4):
+        self.lin, self.w4 = lin, w4
+        self.shape = w4.shape
+
+    @property
+    def requires_grad(self):
+        return self.lin.weight.requires_grad
+
+    def detach(self):
+        return self.w4.detach()
+
+    @property
+    def owner(self):  # the real Parameter: pack cache and gradients live there
+        return self.lin.weight
+
+
+def mlp(tape, seq, srcs, tag="mlp"):
+    """make_mlp Sequential (basics.py:11-45): Linear [+BatchNorm1d] + act [+Dropout] ..., last Linear [+act]."""
+    mods = list(seq)
+    x_srcs = srcs
+    i = 0
+    y = None
+    while i < len(mods):
+        m = mods[i]
+        if not isinstance(m, torch.nn.Linear):
+            raise RuntimeError("pmoe_b200 mlp: unexpected layer order at %d: %r" % (i, m))
+        j = i + 1
+        bn = None
+        act = None
+        drop = None
+        if j < len(mods) and isinstance(mods[j], torch.nn.BatchNorm1d):
+            bn = mods[j]
+            j += 1
+        if j < len(mods) and isinstance(mods[j], (torch.nn.ReLU, torch.nn.ELU, torch.nn.Tanh, torch.nn.Sigmoid)):
+            act = {torch.nn.ReLU: "relu", torch.nn.ELU: "elu", torch.nn.Tanh: "tanh", torch.nn.Sigmoid: "sigmoid"}[type(mods[j])]
+            j += 1
+        if j < len(mods) and isinstance(mods[j], torch.nn.Dropout):
+            drop = mods[j]
+            j += 1
+        w4 = m.weight.view(m.weight.shape[0], m.weight.shape[1], 1, 1)
+        y, _ = conv_op(tape, x_srcs, _AsConv(m, w4), m.bias, bn, act, ksize=1, tag="%s.%d" % (tag, i))
+        if drop is not None:
+            y = dropout_op(tape, y, drop.p, drop.training)
+        x_srcs = [y]
+        i = j
+    return y
+
+
+def vec_value(act):
+    """Act (1,1,B,cpad) -> fp32 (B, c)."""
+    return act.t.view(act.t.shape[2], act.t.shape[3])[:, :act.c].float()
+
+
+def seed_vec(tape, act, g):
+    """Install a (B, c) fp32 gradient for a vector Act."""
+    if g is None or not _rg(act):
+        return
+    B, cp = act.t.shape[2], act.t.shape[3]
+    buf = torch.zeros(B, cp, dtype=torch.float32, device=g.device)
+    buf[:, :act.c] = g
+    gt = torch.empty(1, 1, B, cp, dtype=act.t.dtype, device=g.device)
+    _axpy(None, gt.view(B, 1, 1, cp), 1.0, buf, False)
+    _accumulate(tape, act, gt)
+
+
+def expert_heads(tape, ex, img_feat, speed_a, cmd_a, alt, alpha_out, ap_out, speed_out, tag="expert"):
+    """BaseExpert / BaseExpertAlt after the backbone (moe.py:88-101, 113-128). The raw head outputs are written into
+    slices of shared (1,1,B,K*16) buffers so the gating kernel sees all experts at once."""
+    s = mlp(tape, ex.speed_encoder, [speed_a], tag + ".speed_encoder")
+    c = mlp(tape, ex.command_encoder, [cmd_a], tag + ".command_encoder")
+    feats = [img_feat, s, c]
+    sp = mlp_last_out(tape, ex.speed_pred, feats, speed_out, tag + ".speed_pred")
+    af = mlp(tape, ex.action_features, feats, tag + ".action_features")
+    ap = linear_op(tape, [af], ex.action_pred, None, out=ap_out, tag=tag + ".action_pred")
+    if alt:
+        a1 = linear_op(tape, feats, ex.alpha[0], "relu", tag=tag + ".alpha.0")
+        al = linear_op(tape, [a1], ex.alpha[2], None, out=alpha_out, tag=tag + ".alpha.2")
+    else:
+        al = linear_op(tape, [af], ex.alpha, None, out=alpha_out, tag=tag + ".alpha")  # ReLU applied by the gating kernel
+    return al, ap, sp
+
+
+def mlp_last_out(tape, seq, srcs, out, tag):
+    """mlp() whose final Linear writes into `out`."""
+    mods = list(seq)
+    last_lin = max(i for i, m in enumerate(mods) if isinstance(m, torch.nn.Linear))
+    if last_lin == 0:
+        return linear_op(tape, srcs, mods[0], None, out=out, tag=tag + ".0")
+    head = torch.nn.Sequential(*mods[:last_lin])
+    y = mlp(tape, head, srcs, tag)
+    if last_lin + 1 < len(mods):
+        raise RuntimeError("pmoe_b200: l_act on an output head is not supported")
+    return linear_op(tape, [y], mods[last_lin], None, out=out, tag="%s.%d" % (tag, last_lin))
+
+
+class GateMixture:
+    """softmax over expert logits + sigma = ELU+1 from the strided raw head outputs; backward to those outputs."""
+
+    def __init__(self, tape, alpha_acts, ap_acts, alpha_buf, ap_buf, B, K, relu_alpha, a_sk, p_sk):
+        self.tape, self.alpha_acts, self.ap_acts = tape, alpha_acts, ap_acts
+        self.alpha_buf, self.ap_buf, self.B, self.K, self.relu = alpha_buf, ap_buf, B, K, relu_alpha
+        self.a_sk, self.p_sk = a_sk, p_sk
+        dev = alpha_buf.device
+        self.probs = torch.empty(B, K, dtype=torch.float32, device=dev)
+        self.mean = torch.empty(B, K, 2, dtype=torch.float32, device=dev)
+        self.std = torch.empty(B, K, 2, dtype=torch.float32, device=dev)
+        self.route = torch.empty(B, dtype=torch.int64, device=dev)
+        a_sb, p_sb = alpha_buf.shape[3], ap_buf.shape[3]
+        check(profiler.launch("gate_mixture_fwd", lambda: lib().pmoe_gate_mixture_fwd(
+            alpha_buf.data_ptr(), a_sb, a_sk, ap_buf.data_ptr(), p_sb, p_sk, dtype_code(alpha_buf), B, K, int(relu_alpha),
+            self.probs.data_ptr(), self.mean.data_ptr(), self.std.data_ptr(), self.route.data_ptr(), stream_ptr())),
+            "gate_mixture_fwd")
+
+    def backward(self, dprobs, dmean, dstd):
+        tape = self.tape
+        if not any(_rg(a) for a in self.alpha_acts + self.ap_acts):
+            return
+        dalpha = torch.zeros_like(self.alpha_buf)
+        dap = torch.zeros_like(self.ap_buf)
+        f = lambda t: None if t is None else t.contiguous().float()
+        dprobs, dmean, dstd = f(dprobs), f(dmean), f(dstd)
+        a_sb, p_sb = self.alpha_buf.shape[3], self.ap_buf.shape[3]
+        check(profiler.launch("gate_mixture_bwd", lambda: lib().pmoe_gate_mixture_bwd(
+            _lib.ptr(dprobs), _lib.ptr(dmean), _lib.ptr(dstd), self.probs.data_ptr(), self.std.data_ptr(),
+            self.alpha_buf.data_ptr(), a_sb, self.a_sk, dtype_code(self.alpha_buf), self.B, self.K, int(self.relu),
+            dalpha.data_ptr(), dap.data_ptr(), p_sb, self.p_sk, stream_ptr())), "gate_mixture_bwd")
+        for k, a in enumerate(self.alpha_acts):
+            if _rg(a):
+                _accumulate_copy(tape, a, dalpha[..., k * self.a_sk:k * self.a_sk + a.t.shape[3]] if len(self.alpha_acts) > 1 else dalpha)
+        for k, a in enumerate(self.ap_acts):
+            if _rg(a):
+                _accumulate_copy(tape, a, dap[..., k * self.p_sk:k * self.p_sk + a.t.shape[3]] if len(self.ap_acts) > 1 else dap)
+
+
 # ------------------------------------------------------------------------------------------------ autograd bridge
 class TapeFunction(torch.autograd.Function):
     """forward(runner, *params): runner(tape) -> (list of output tensors, seed_fn). seed_fn(grad_outputs)
@@ -514,54 +894,66 @@ def unet_module_forward(net, image):
     return (outs[0], outs[1]) if net.inter_repr else outs[0]
 
 
-def punet_module_forward(net, images):
-    """PredictiveUnet.forward (punet.py:75-120) in the general path: every U-Net call is separate (train-mode
-    BatchNorm statistics are per call, as in the reference's Python loop)."""
+def punet_tape(tape, net, images):
+    """PredictiveUnet.forward (punet.py:75-120) on the tape. Every U-Net call is separate (train-mode BatchNorm
+    statistics are per call, as in the reference's Python loop). The deque of masks is a sliding window over one ring
+    buffer (B,H,W,(P+F)*slot). Returns dict(ring, pools, masks, futures, inter, slot, ncls)."""
     B, T, Cin, H, W = images.shape
     P, Fu = net.n_past_frames, net.n_future_frames
     ncls = net.unet.out.weight.shape[0]
     slot = pad_ch(ncls)
+    dev = images.device
+    nslots = P + max(Fu, 0)
+    ring = torch.zeros(B, H, W, nslots * slot, dtype=tape.dtype, device=dev)
+    pools = torch.zeros(B, nslots * slot, dtype=torch.float32, device=dev)
+    masks, futures, inter = [], [], None
+    for t in range(P):
+        x = nhwc.from_nchw(images[:, t], dtype=tape.dtype)
+        m, it = unet(tape, net.unet, x, out=ring[..., t * slot:(t + 1) * slot], out_pool=pools[:, t * slot:],
+                     pool_stride=nslots * slot, want_inter=(net.unet_inter_repr and Fu == 0 and t == P - 1), tag="unet")
+        masks.append(m)
+        inter = it
+    for f in range(Fu):
+        window = ring_window(tape, ring, masks[f:f + P], f * slot, slot, ncls)
+        e = eca_conv_block(tape, net.entry_block, window, (P, ncls, slot), pools[:, f * slot:(f + P) * slot], tag="entry")
+        m, inter = unet(tape, net.pred_unet, e, out=ring[..., (P + f) * slot:(P + f + 1) * slot],
+                        out_pool=pools[:, (P + f) * slot:], pool_stride=nslots * slot, want_inter=net.inter_repr,
+                        tag="pred_unet")
+        masks.append(m)
+        futures.append(m)
+    return {"ring": ring, "pools": pools, "masks": masks, "futures": futures, "inter": inter, "slot": slot, "ncls": ncls,
+            "P": P, "F": Fu}
+
+
+def ring_window(tape, ring, parts, c_begin, slot, ncls):
+    """A run of consecutive ring slots as ONE multi-group Act; its gradient is split back onto the slot Acts."""
+    n = len(parts)
+    window = _new_act(tape, ring[..., c_begin:c_begin + n * slot], n * ncls, any(_rg(m) for m in parts))
+    if tape.save and _rg(window):
+        def split_grad():
+            g = tape.grad_of(window)
+            if g is None:
+                return
+            for i, part in enumerate(parts):
+                if _rg(part):
+                    _accumulate_copy(tape, part, g[..., i * slot:(i + 1) * slot])
+        tape.record(split_grad)
+    return window
+
+
+def punet_module_forward(net, images):
+    B, T, Cin, H, W = images.shape
 
     def runner(tape):
-        dev = images.device
-        nslots = P + max(Fu, 0)
-        ring = torch.zeros(B, H, W, nslots * slot, dtype=tape.dtype, device=dev)
-        pools = torch.zeros(B, nslots * slot, dtype=torch.float32, device=dev)
-        masks = []
-        inter = None
-        for t in range(P):
-            x = nhwc.from_nchw(images[:, t], dtype=tape.dtype)
-            x.rg = False
-            m, it = unet(tape, net.unet, x, out=ring[..., t * slot:(t + 1) * slot], out_pool=pools[:, t * slot:],
-                         pool_stride=nslots * slot, want_inter=(net.unet_inter_repr and Fu == 0 and t == P - 1), tag="unet")
-            masks.append(m)
-            inter = it
+        r = punet_tape(tape, net, images)
+        ncls, Fu, masks, futures, inter = r["ncls"], r["F"], r["masks"], r["futures"], r["inter"]
         if Fu == 0:
             if net.unet_inter_repr:
                 return [inter.value], (lambda tp, g: inter.backward(g[0]) if g[0] is not None else None)
             return [nhwc.to_nchw(masks[-1].t, ncls)], (lambda tp, g: _seed_nchw(masks[-1])(tp, g[0]))
-        futures = []
-        for f in range(Fu):
-            window = _new_act(tape, ring[..., f * slot:(f + P) * slot], P * ncls, any(_rg(m) for m in masks[f:f + P]))
-            window_parts = masks[f:f + P]
-            if tape.save and _rg(window):
-                def split_grad(window=window, parts=window_parts):
-                    g = tape.grad_of(window)
-                    if g is None:
-                        return
-                    for i, part in enumerate(parts):
-                        if _rg(part):
-                            _accumulate_copy(tape, part, g[..., i * slot:(i + 1) * slot])
-                tape.record(split_grad)
-            e = eca_conv_block(tape, net.entry_block, window, (P, ncls, slot), pools[:, f * slot:(f + P) * slot], tag="entry")
-            m, inter = unet(tape, net.pred_unet, e, out=ring[..., (P + f) * slot:(P + f + 1) * slot],
-                            out_pool=pools[:, (P + f) * slot:], pool_stride=nslots * slot, want_inter=net.inter_repr,
-                            tag="pred_unet")
-            masks.append(m)
-            futures.append(m)
         if net.inter_repr:
             return [inter.value], (lambda tp, g: inter.backward(g[0]) if g[0] is not None else None)
-        out = torch.empty(B, Fu, ncls, H, W, dtype=torch.float32, device=dev)
+        out = torch.empty(B, Fu, ncls, H, W, dtype=torch.float32, device=images.device)
         for f, m in enumerate(futures):
             nhwc.to_nchw(m.t, ncls, out=out[:, f])
 

@@ -68,8 +68,8 @@ typedef struct PmoeConvTc {
   const float* shift; /* [cout_pad] or NULL (=0) */
   int32_t act;
   PmoeView4 residual; /* bf16, ptr NULL = none; added before the activation */
-  float* stat_sum;    /* optional [cout_pad]: += sum over valid pixels of the raw accumulator   */
-  float* stat_sqsum;  /* optional [cout_pad]: += sum of squares (train-mode BN batch statistics) */
+  double* stat_sum;   /* optional [cout_pad]: += sum over valid pixels of the raw accumulator (fp64 accumulation) */
+  double* stat_sqsum; /* optional [cout_pad]: += sum of squares (train-mode BN batch statistics)                 */
   float* pool_sum;    /* optional [n][pool_stride]: += per-image sum of the stored output (ECA / avgpool) */
   int32_t pool_stride; /* row stride of pool_sum in floats; 0 = cout_pad */
 } PmoeConvTc;
@@ -102,9 +102,9 @@ int pmoe_scale_channels(const PmoeView4* src, const PmoeView4* dst, int32_t dtyp
 /* out[n][c] += sum over h,w (adaptive_avg_pool2d numerator, basics.py:72, unet.py:90). */
 int pmoe_channel_sums(const PmoeView4* src, int32_t dtype, float* out, int64_t out_stride, pmoe_stream_t stream);
 /* sum[c], sqsum[c] += over n,h,w (batch statistics of a BatchNorm not fed by a conv epilogue: ResNet bn1). */
-int pmoe_channel_stats(const PmoeView4* src, int32_t dtype, float* sum, float* sqsum, pmoe_stream_t stream);
+int pmoe_channel_stats(const PmoeView4* src, int32_t dtype, double* sum, double* sqsum, pmoe_stream_t stream);
 /* nn.BatchNorm2d training step (basics.py:52,55): batch stats from (sum, sumsq), running-stat update, fused affine. */
-int pmoe_bn_finalize(const float* sum, const float* sqsum, float count, int32_t c, int32_t c_pad, const float* gamma,
+int pmoe_bn_finalize(const double* sum, const double* sqsum, float count, int32_t c, int32_t c_pad, const float* gamma,
                      const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* mean_out,
                      float* rstd_out, float* scale, float* shift, pmoe_stream_t stream);
 /* y = act(scale[c]*x + shift[c] (+ residual)): BN apply + ReLU (+ BasicBlock residual add). */
@@ -114,12 +114,12 @@ int pmoe_affine_act(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, c
 /* ---- backward halves (eltwise_bwd.cu) ------------------------------------------------------------- */
 /* dy = dz * act'(z); sum_dy[c] += sum dy, sum_dy_xhat[c] += sum dy*(x-mean)*rstd  (native_batch_norm_backward reductions) */
 int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
-                       const float* mean, const float* rstd, float* sum_dy, float* sum_dy_xhat, pmoe_stream_t stream);
+                       const float* mean, const float* rstd, double* sum_dy, double* sum_dy_xhat, pmoe_stream_t stream);
 /* dx = gamma*rstd*(dy - sum_dy/N - xhat*sum_dy_xhat/N) (batch_stats) or dy*gamma (eval BN / plain);
  * dres (optional) receives the masked dy for a residual branch. */
 int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
-                      const float* mean, const float* rstd, const float* gamma, const float* sum_dy,
-                      const float* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
+                      const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
+                      const double* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
                       const PmoeView4* dres, int32_t accumulate_dres, pmoe_stream_t stream);
 int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* dx, int32_t dtype, int32_t k, int32_t stride,
                      int32_t pad, int32_t accumulate, pmoe_stream_t stream);

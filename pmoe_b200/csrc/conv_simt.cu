@@ -32,8 +32,8 @@ struct SimtParams {
   const float* shift;
   int act;
   SimtView res;
-  float* stat_sum;
-  float* stat_sq;
+  double* stat_sum;
+  double* stat_sq;
   float* pool_sum;
   int pool_stride;
   int ph, pw, tiles_h, tiles_w;  // pixel patch of a tile
@@ -198,8 +198,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const __grid_constant__ 
     }
     __syncthreads();
     if (tid < 64 && n0 + tid < p.cout_pad) {
-      atomicAdd(p.stat_sum + n0 + tid, s_red[0][tid]);
-      atomicAdd(p.stat_sq + n0 + tid, s_red[1][tid]);
+      atomicAdd(p.stat_sum + n0 + tid, (double)s_red[0][tid]);
+      atomicAdd(p.stat_sq + n0 + tid, (double)s_red[1][tid]);
     }
     __syncthreads();
     if (tid < 64) s_red[0][tid] = 0.f;

@@ -16,6 +16,7 @@
 #include "ptx.cuh"
 
 #include <initializer_list>
+#include <stdlib.h>
 #include <string.h>
 
 namespace pmoe {
@@ -40,11 +41,15 @@ struct alignas(64) ConvTcParams {
   int res_c;
   const __nv_bfloat16* res;
   long long res_sn, res_sh, res_sw;
-  float* stat_sum;
-  float* stat_sq;
+  double* stat_sum;
+  double* stat_sq;
   float* pool_sum;
   int cout_pad;
   int pool_stride;
+  // resident-weight ("halo") variant
+  int halo_stages, w_slots, n_chunks;
+  long long m_tiles;
+  int out_bufs;  // staging buffers for the TMA store (2, or 1 when shared memory is tight)
 };
 
 constexpr int kMaxStatC = 512;
@@ -100,6 +105,190 @@ __device__ __forceinline__ float warp_col_sums(float (&v)[NC], int lane) {
     }
   }
   return v[0];
+}
+
+// Tile enumerators. StreamTiles: contiguous chunk of the (m, n) tile list per CTA (per-tap streaming kernel).
+// ResidentTiles: the CTA owns ONE n-tile (its weights stay in shared memory) and strides over the m-tiles.
+struct StreamTiles {
+  long long t_begin, t_end;
+  int tiles_per_img;
+  __device__ __forceinline__ bool get(const ConvTcParams& p, uint32_t iter, int& img, int& h0, int& w0, int& nt) const {
+    const long long t = t_begin + iter;
+    if (t >= t_end) return false;
+    nt = (int)(t % p.tiles_n);
+    const long long mt = t / p.tiles_n;
+    img = (int)(mt / tiles_per_img);
+    const int rem = (int)(mt % tiles_per_img);
+    h0 = (rem / p.tiles_w) * p.bh;
+    w0 = (rem % p.tiles_w) * p.bw;
+    return true;
+  }
+};
+struct ResidentTiles {
+  int nt_fixed, m_first, m_step, tiles_per_img;
+  long long m_tiles;
+  __device__ __forceinline__ bool get(const ConvTcParams& p, uint32_t iter, int& img, int& h0, int& w0, int& nt) const {
+    const long long mt = (long long)m_first + (long long)iter * m_step;
+    if (mt >= m_tiles) return false;
+    nt = nt_fixed;
+    img = (int)(mt / tiles_per_img);
+    const int rem = (int)(mt % tiles_per_img);
+    h0 = (rem / p.tiles_w) * p.bh;
+    w0 = (rem % p.tiles_w) * p.bw;
+    return true;
+  }
+};
+
+// Epilogue role (4 warps, threads 64..191): TMEM -> registers -> affine / residual / activation / statistics ->
+// swizzled bf16 staging tile -> TMA store. Shared by both main-loop variants.
+template <int BN, int OCW, int SUB, int OUT_BYTES, class Iter>
+__device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& it, uint8_t* out_stage, float* s_scale,
+                                             float* s_shift, float* s_pool, float* s_sum, float* s_sq, uint64_t* tfull_bar,
+                                             uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane) {
+  {
+    const int e = threadIdx.x - 64;         // 0..127
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;       // accumulator row == pixel index inside the tile
+    const bool issuer = (e == 0);
+    const int ti = row / p.bw, tj = row % p.bw;
+    const bool row_in_box = row < p.bw * p.bh;
+    constexpr int ROWB = OCW * 2;
+    constexpr uint32_t SWMASK = ROWB == 128 ? 7u : (ROWB == 64 ? 3u : 1u);
+    const int act = p.act;
+    uint32_t nstore = 0;
+    int img, h0, w0, nt;
+    for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
+      const int n0 = nt * BN;
+      const bool valid = row_in_box && (h0 + ti < p.H) && (w0 + tj < p.W);
+      const uint32_t acc = titer & 1u;
+      const uint32_t acc_phase = (titer >> 1) & 1u;
+
+      for (int i = e; i < BN; i += kEpiThreads) {
+        s_scale[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.f;
+        s_shift[i] = p.shift ? __ldg(p.shift + n0 + i) : 0.f;
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+
+      const __nv_bfloat16* res_row = nullptr;
+      if (p.res != nullptr && valid)
+        res_row = p.res + (long long)img * p.res_sn + (long long)(h0 + ti) * p.res_sh + (long long)(w0 + tj) * p.res_sw;
+
+#pragma unroll 1
+      for (int ch = 0; ch < BN / OCW; ++ch) {
+        uint8_t* obuf = out_stage + (p.out_bufs == 2 ? (nstore & 1u) : 0u) * OUT_BYTES;
+        if (issuer) {  // the store that last used this buffer has drained
+          if (p.out_bufs == 2) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
+        named_bar_sync(1, kEpiThreads);
+#pragma unroll
+        for (int sb = 0; sb < OCW / SUB; ++sb) {
+          const int cb = ch * OCW + sb * SUB;  // column offset inside the N tile
+          uint32_t raw[SUB];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cb;
+          if constexpr (SUB == 32) tmem_ld_32x32(taddr, raw);
+          else tmem_ld_32x16(taddr, raw);
+          tmem_ld_wait();
+          float y[SUB];
+#pragma unroll
+          for (int q = 0; q < SUB / 4; ++q) {  // per-channel affine, 128-bit broadcast reads of scale/shift
+            const float4 sc4 = *reinterpret_cast<const float4*>(s_scale + cb + 4 * q);
+            const float4 sh4 = *reinterpret_cast<const float4*>(s_shift + cb + 4 * q);
+            y[4 * q + 0] = fmaf(__uint_as_float(raw[4 * q + 0]), sc4.x, sh4.x);
+            y[4 * q + 1] = fmaf(__uint_as_float(raw[4 * q + 1]), sc4.y, sh4.y);
+            y[4 * q + 2] = fmaf(__uint_as_float(raw[4 * q + 2]), sc4.z, sh4.z);
+            y[4 * q + 3] = fmaf(__uint_as_float(raw[4 * q + 3]), sc4.w, sh4.w);
+          }
+          if (p.stat_sum != nullptr) {
+            float a[SUB], b[SUB];
+#pragma unroll
+            for (int k = 0; k < SUB; ++k) {
+              const float f = valid ? __uint_as_float(raw[k]) : 0.f;
+              a[k] = f;
+              b[k] = f * f;
+            }
+            const float sa = warp_col_sums<SUB>(a, lane);
+            const float sq = warp_col_sums<SUB>(b, lane);
+            if (lane < SUB && n0 + cb + lane < kMaxStatC) {
+              atomicAdd(&s_sum[n0 + cb + lane], sa);
+              atomicAdd(&s_sq[n0 + cb + lane], sq);
+            }
+          }
+          if (res_row != nullptr) {
+#pragma unroll
+            for (int q = 0; q < SUB / 8; ++q) {
+              if (n0 + cb + q * 8 < p.res_c) {
+                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + cb + q * 8));
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float2 f2 = __bfloat1622float2(r2[u]);
+                  y[q * 8 + 2 * u] += f2.x;
+                  y[q * 8 + 2 * u + 1] += f2.y;
+                }
+              }
+            }
+          }
+          if (act == PMOE_ACT_RELU) {  // the branch is uniform and hoisted out of the element loop
+#pragma unroll
+            for (int k = 0; k < SUB; ++k) y[k] = fmaxf(y[k], 0.f);
+          } else if (act != PMOE_ACT_NONE) {
+#pragma unroll
+            for (int k = 0; k < SUB; ++k) y[k] = apply_act(y[k], act);
+          }
+          // bf16 pack -> swizzled staging tile (row = pixel, ROWB bytes per row)
+#pragma unroll
+          for (int q = 0; q < SUB / 8; ++q) {
+            uint4 pk;
+            pk.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
+            pk.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
+            pk.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
+            pk.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
+            uint32_t off = (uint32_t)row * ROWB + (uint32_t)(sb * SUB + q * 8) * 2u;
+            off ^= ((off >> 7) & SWMASK) << 4;
+            *reinterpret_cast<uint4*>(obuf + off) = pk;
+          }
+          if (p.pool_sum != nullptr) {
+            // pool what is actually stored (bf16-rounded), masked to valid pixels
+            float a[SUB];
+#pragma unroll
+            for (int k = 0; k < SUB; ++k) a[k] = valid ? __bfloat162float(__float2bfloat16_rn(y[k])) : 0.f;
+            const float sa = warp_col_sums<SUB>(a, lane);
+            if (lane < SUB) atomicAdd(&s_pool[cb + lane], sa);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, kEpiThreads);
+        if (issuer) {
+          tma_store_4d(&p.tm_out, obuf, n0 + ch * OCW, w0, h0, img);
+          tma_store_commit();
+        }
+        ++nstore;
+      }
+      // accumulator stage fully read -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (p.pool_sum != nullptr) {
+        named_bar_sync(3, kEpiThreads);
+        for (int i = e; i < BN; i += kEpiThreads) {
+          const float v = s_pool[i];
+          if (v != 0.f) atomicAdd(p.pool_sum + (long long)img * p.pool_stride + n0 + i, v);
+          s_pool[i] = 0.f;
+        }
+      }
+    }
+    if (issuer) tma_store_wait_read<0>();
+    if (p.stat_sum != nullptr) {
+      named_bar_sync(3, kEpiThreads);
+      const int nc = p.cout_pad < kMaxStatC ? p.cout_pad : kMaxStatC;
+      for (int i = e; i < nc; i += kEpiThreads) {
+        atomicAdd(p.stat_sum + i, (double)s_sum[i]);
+        atomicAdd(p.stat_sq + i, (double)s_sq[i]);
+      }
+    }
+    }
 }
 
 template <int BN, int CK>
@@ -218,140 +407,155 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     }
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps)
-    const int e = threadIdx.x - 64;         // 0..127
-    const int quad = warp & 3;              // TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;       // accumulator row == pixel index inside the tile
-    const bool issuer = (e == 0);
-    const int ti = row / p.bw, tj = row % p.bw;
-    const bool row_in_box = row < p.bw * p.bh;
-    constexpr int ROWB = C::OCW * 2;
-    constexpr uint32_t SWMASK = ROWB == 128 ? 7u : (ROWB == 64 ? 3u : 1u);
-    uint32_t titer = 0;
-    uint32_t nstore = 0;
-    for (long long t = t_begin; t < t_end; ++t, ++titer) {
-      const int nt = (int)(t % p.tiles_n);
-      const long long mt = t / p.tiles_n;
-      const int img = (int)(mt / tiles_per_img);
-      const int rem = (int)(mt % tiles_per_img);
-      const int h0 = (rem / p.tiles_w) * p.bh;
-      const int w0 = (rem % p.tiles_w) * p.bw;
-      const int n0 = nt * BN;
-      const bool valid = row_in_box && (h0 + ti < p.H) && (w0 + tj < p.W);
-      const uint32_t acc = titer & 1u;
-      const uint32_t acc_phase = (titer >> 1) & 1u;
+    StreamTiles it{t_begin, t_end, tiles_per_img};
+    run_epilogue<BN, C::OCW, C::SUB, C::OUT_BYTES>(p, it, out_stage, s_scale, s_shift, s_pool, s_sum, s_sq, tfull_bar, tempty_bar,
+                                                   tmem_base, warp, lane);
+  }
 
-      for (int i = e; i < BN; i += kEpiThreads) {
-        s_scale[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.f;
-        s_shift[i] = p.shift ? __ldg(p.shift + n0 + i) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Resident-weight / halo variant for 3x3 stride-1 convolutions whose weight slice fits in shared memory.
+// One TMA brings the (16+2) x (8+2) input halo of a 16x8 output patch for a 64-channel chunk; the nine taps are nine
+// UMMA descriptor VIEWS of that halo tile (start row r*10+s, 8-row groups 10 rows apart — the swizzle is a function of
+// the absolute shared-memory address, so row-shifted views need no re-staging: profiles/r01_conv_bringup.json probe).
+// L2->SMEM traffic per tile drops from 9 x 16 KB to 23 KB per chunk, and the weights are fetched once per CTA.
+template <int BN>
+struct HaloCfg {
+  static constexpr int OCW = BN < 64 ? BN : 64;
+  static constexpr int SUB = OCW < 32 ? OCW : 32;
+  static constexpr int HALO_TX = 18 * 10 * 128;
+  static constexpr int HALO_BYTES = 23 * 1024;
+  static constexpr int WSLOT_BYTES = BN * 128;
+  static constexpr int OUT_BYTES = 128 * OCW * 2;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int AUX_FLOATS = 3 * BN + 2 * kMaxStatC;
+  static constexpr int MAX_STAGES = 6;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __grid_constant__ ConvTcParams p) {
+  using C = HaloCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wsm = smem;
+  uint8_t* halo = wsm + (size_t)p.w_slots * C::WSLOT_BYTES;
+  uint8_t* out_stage = halo + (size_t)p.halo_stages * C::HALO_BYTES;
+  float* s_scale = reinterpret_cast<float*>(out_stage + p.out_bufs * C::OUT_BYTES);
+  float* s_shift = s_scale + BN;
+  float* s_pool = s_shift + BN;
+  float* s_sum = s_pool + BN;
+  float* s_sq = s_sum + kMaxStatC;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_sq + kMaxStatC);
+  uint64_t* empty_bar = full_bar + C::MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + C::MAX_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* wfull_bar = tempty_bar + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(wfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::MAX_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    mbar_init(wfull_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&p.tm_w);
+    tma_prefetch_desc(&p.tm_out);
+    tma_prefetch_desc(&p.tm_src[0]);
+  }
+  if (warp == 2) {
+    tmem_alloc(s_tmem, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < BN; i += kNumThreads) s_pool[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * kMaxStatC; i += kNumThreads) s_sum[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  ResidentTiles it;
+  it.nt_fixed = (int)(blockIdx.x % p.tiles_n);
+  it.m_first = (int)(blockIdx.x / p.tiles_n);
+  it.m_step = (int)(gridDim.x / p.tiles_n);
+  it.tiles_per_img = p.tiles_w * p.tiles_h;
+  it.m_tiles = p.m_tiles;
+  int img, h0, w0, nt;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(wfull_bar, (uint32_t)(p.w_slots * C::WSLOT_BYTES));
+      for (int j = 0; j < p.w_slots; ++j) tma_load_2d(wsm + (size_t)j * C::WSLOT_BYTES, &p.tm_w, wfull_bar, j * 64, it.nt_fixed * BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
+        for (int g = 0; g < p.n_chunks; ++g) {
+          const TcSeg sg = p.seg[g];
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)C::HALO_TX);
+          tma_load_4d(halo + (size_t)stage * C::HALO_BYTES, &p.tm_src[sg.src], &full_bar[stage], sg.c0, w0 - 1, h0 - 1, img);
+          if (++stage == p.halo_stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
       }
-      mbar_wait(&tfull_bar[acc], acc_phase);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      mbar_wait(wfull_bar, 0);
       tc_fence_after();
-
-      const __nv_bfloat16* res_row = nullptr;
-      if (p.res != nullptr && valid)
-        res_row = p.res + (long long)img * p.res_sn + (long long)(h0 + ti) * p.res_sh + (long long)(w0 + tj) * p.res_sw;
-
-#pragma unroll 1
-      for (int ch = 0; ch < BN / C::OCW; ++ch) {
-        uint8_t* obuf = out_stage + (nstore & 1u) * C::OUT_BYTES;
-        if (issuer) tma_store_wait_read<1>();  // the store that last used this buffer has drained
-        named_bar_sync(1, kEpiThreads);
+      const uint32_t w_addr = smem_u32(wsm);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
+        const uint32_t acc = titer & 1u;
+        const uint32_t acc_phase = (titer >> 1) & 1u;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int g = 0; g < p.n_chunks; ++g) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t h_addr = smem_u32(halo + (size_t)stage * C::HALO_BYTES);
 #pragma unroll
-        for (int sb = 0; sb < C::OCW / C::SUB; ++sb) {
-          const int cb = ch * C::OCW + sb * C::SUB;  // column offset inside the N tile
-          uint32_t raw[C::SUB];
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cb;
-          if constexpr (C::SUB == 32) tmem_ld_32x32(taddr, raw);
-          else tmem_ld_32x16(taddr, raw);
-          tmem_ld_wait();
-          float y[C::SUB];
+          for (int t = 0; t < 9; ++t) {
+            const uint32_t a_tap = h_addr + (uint32_t)((t / 3) * 10 + (t % 3)) * 128u;
+            const uint32_t b_tap = w_addr + (uint32_t)(t * p.n_chunks + g) * (uint32_t)C::WSLOT_BYTES;
 #pragma unroll
-          for (int k = 0; k < C::SUB; ++k) y[k] = fmaf(__uint_as_float(raw[k]), s_scale[cb + k], s_shift[cb + k]);
-          if (p.stat_sum != nullptr) {
-            float a[C::SUB], b[C::SUB];
-#pragma unroll
-            for (int k = 0; k < C::SUB; ++k) {
-              const float f = valid ? __uint_as_float(raw[k]) : 0.f;
-              a[k] = f;
-              b[k] = f * f;
-            }
-            const float sa = warp_col_sums<C::SUB>(a, lane);
-            const float sq = warp_col_sums<C::SUB>(b, lane);
-            if (lane < C::SUB && n0 + cb + lane < kMaxStatC) {
-              atomicAdd(&s_sum[n0 + cb + lane], sa);
-              atomicAdd(&s_sq[n0 + cb + lane], sq);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t adesc = umma_desc_kmajor(a_tap + k * 32, 1280u, kLayoutSW128);
+              const uint64_t bdesc = umma_desc_kmajor(b_tap + k * 32, 1024u, kLayoutSW128);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (g | t | k) != 0 ? 1u : 0u);
             }
           }
-          if (res_row != nullptr) {
-#pragma unroll
-            for (int q = 0; q < C::SUB / 8; ++q) {
-              if (n0 + cb + q * 8 < p.res_c) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + cb + q * 8));
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float2 f2 = __bfloat1622float2(r2[u]);
-                  y[q * 8 + 2 * u] += f2.x;
-                  y[q * 8 + 2 * u + 1] += f2.y;
-                }
-              }
-            }
-          }
-          if (p.act != PMOE_ACT_NONE) {
-#pragma unroll
-            for (int k = 0; k < C::SUB; ++k) y[k] = apply_act(y[k], p.act);
-          }
-          // bf16 pack -> swizzled staging tile (row = pixel, ROWB bytes per row)
-#pragma unroll
-          for (int q = 0; q < C::SUB / 8; ++q) {
-            uint4 pk;
-            pk.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
-            pk.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
-            pk.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
-            pk.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
-            uint32_t off = (uint32_t)row * ROWB + (uint32_t)(sb * C::SUB + q * 8) * 2u;
-            off ^= ((off >> 7) & SWMASK) << 4;
-            *reinterpret_cast<uint4*>(obuf + off) = pk;
-          }
-          if (p.pool_sum != nullptr) {
-            // pool what is actually stored (bf16-rounded), masked to valid pixels
-            float a[C::SUB];
-#pragma unroll
-            for (int k = 0; k < C::SUB; ++k) a[k] = valid ? __bfloat162float(__float2bfloat16_rn(y[k])) : 0.f;
-            const float sa = warp_col_sums<C::SUB>(a, lane);
-            if (lane < C::SUB) atomicAdd(&s_pool[cb + lane], sa);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.halo_stages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
-        fence_proxy_async_smem();
-        named_bar_sync(2, kEpiThreads);
-        if (issuer) {
-          tma_store_4d(&p.tm_out, obuf, n0 + ch * C::OCW, w0, h0, img);
-          tma_store_commit();
-        }
-        ++nstore;
-      }
-      // accumulator stage fully read -> hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (p.pool_sum != nullptr) {
-        named_bar_sync(3, kEpiThreads);
-        for (int i = e; i < BN; i += kEpiThreads) {
-          const float v = s_pool[i];
-          if (v != 0.f) atomicAdd(p.pool_sum + (long long)img * p.pool_stride + n0 + i, v);
-          s_pool[i] = 0.f;
-        }
+        umma_commit(&tfull_bar[acc]);
       }
     }
-    if (issuer) tma_store_wait_read<0>();
-    if (p.stat_sum != nullptr) {
-      named_bar_sync(3, kEpiThreads);
-      const int nc = p.cout_pad < kMaxStatC ? p.cout_pad : kMaxStatC;
-      for (int i = e; i < nc; i += kEpiThreads) {
-        atomicAdd(p.stat_sum + i, s_sum[i]);
-        atomicAdd(p.stat_sq + i, s_sq[i]);
-      }
-    }
+  } else {
+    run_epilogue<BN, C::OCW, C::SUB, C::OUT_BYTES>(p, it, out_stage, s_scale, s_shift, s_pool, s_sum, s_sq, tfull_bar, tempty_bar,
+                                                   tmem_base, warp, lane);
   }
 
   tc_fence_before();
@@ -431,6 +635,36 @@ static int launch_tc_ck(const ConvTcParams& p, int ck, cudaStream_t stream) {
   return PMOE_ERR_ARG;
 }
 
+
+template <int BN>
+static int launch_halo(const ConvTcParams& p, int smem_bytes, cudaStream_t stream) {
+  static int configured = 0;
+  if (configured < smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) {
+      set_error("conv_tc_halo<%d>: cannot reserve %d bytes of shared memory: %s", BN, smem_bytes, cudaGetErrorString(e));
+      return PMOE_ERR_LAUNCH;
+    }
+    configured = smem_bytes;
+  }
+  long long per_n = num_sms() / p.tiles_n;
+  if (per_n > p.m_tiles) per_n = p.m_tiles;
+  if (per_n < 1) per_n = 1;
+  const unsigned grid = (unsigned)(per_n * p.tiles_n);
+  conv_tc_halo_kernel<BN><<<grid, kNumThreads, smem_bytes, stream>>>(p);
+  return check_launch("conv_tc_halo");
+}
+
+// 3x3 / stride 1 / pad 1 over whole sources in the canonical (tap, source) segment order?
+static bool is_canonical_3x3(const PmoeConvTc* d) {
+  if (d->ck != 64 || d->n_seg != 9 * d->n_src) return false;
+  for (int t = 0; t < 9; ++t)
+    for (int i = 0; i < d->n_src; ++i) {
+      const PmoeSeg& s = d->seg[t * d->n_src + i];
+      if (s.src != i || s.dh != t / 3 - 1 || s.dw != t % 3 - 1 || s.c0 != 0 || s.nchunks * 64 != d->src[i].c) return false;
+    }
+  return true;
+}
 }  // namespace pmoe
 
 using namespace pmoe;
@@ -462,7 +696,27 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
   const PmoeView4& o = d->out;
-  choose_tile(o.h, o.w, &p.bh, &p.bw);
+  // ---- resident-weight / halo variant when it applies
+  int halo_bn = 0, total_chunks = 0;
+  static const bool halo_off = getenv("PMOE_NO_HALO") != nullptr;
+  if (!halo_off && is_canonical_3x3(d) && o.h >= 18 && o.w >= 10) {
+    for (int i = 0; i < d->n_src; ++i) total_chunks += d->src[i].c / 64;
+    if (total_chunks <= PMOE_MAX_SEG) {
+      for (int cand : {128, 64, 32, 16})
+        if (d->cout_pad % cand == 0 && 9 * total_chunks * cand * 128 <= 144 * 1024) {
+          halo_bn = cand;
+          break;
+        }
+      if (halo_bn < 64 && d->cout_pad >= 64) halo_bn = 0;  // would starve the MMA: stream the taps instead
+    }
+  }
+  if (halo_bn) {
+    bn = halo_bn;
+    p.bh = 16;
+    p.bw = 8;
+  } else {
+    choose_tile(o.h, o.w, &p.bh, &p.bw);
+  }
   p.H = o.h;
   p.W = o.w;
   p.n_img = o.n;
@@ -498,7 +752,9 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   const CUtensorMapSwizzle swz_in = swizzle_for_bytes(d->ck * 2);
   int rc;
   for (int i = 0; i < d->n_src; ++i) {
-    if ((rc = make_view_tmap(&p.tm_src[i], d->src[i], d->ck, p.bw, p.bh, swz_in, "conv_tc source")) != PMOE_OK) return rc;
+    if ((rc = make_view_tmap(&p.tm_src[i], d->src[i], d->ck, halo_bn ? 10 : p.bw, halo_bn ? 18 : p.bh, swz_in,
+                             "conv_tc source")) != PMOE_OK)
+      return rc;
   }
   {
     if ((uintptr_t)d->wpack & 15) {
@@ -533,7 +789,43 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   p.stat_sq = d->stat_sqsum;
   p.pool_sum = d->pool_sum;
   p.cout_pad = d->cout_pad;
+  p.out_bufs = 2;
   p.pool_stride = d->pool_stride > 0 ? d->pool_stride : d->cout_pad;
+  if (halo_bn) {
+    int g = 0;
+    for (int i = 0; i < d->n_src; ++i)
+      for (int c = 0; c < d->src[i].c / 64; ++c, ++g) {
+        p.seg[g].src = (int8_t)i;
+        p.seg[g].dh = 0;
+        p.seg[g].dw = 0;
+        p.seg[g].c0 = (uint16_t)(c * 64);
+        p.seg[g].nchunks = 1;
+      }
+    p.n_chunks = total_chunks;
+    p.w_slots = 9 * total_chunks;
+    p.m_tiles = (long long)p.tiles_w * p.tiles_h * p.n_img;
+    const int ocw = halo_bn < 64 ? halo_bn : 64;
+    const int wbytes = p.w_slots * halo_bn * 128;
+    int fixed = 0, stages = 0;
+    for (p.out_bufs = 2; p.out_bufs >= 1; --p.out_bufs) {
+      fixed = 1024 + p.out_bufs * 128 * ocw * 2 + (3 * halo_bn + 2 * kMaxStatC) * 4 + (2 * 6 + 5) * 8 + 16;
+      stages = (227 * 1024 - fixed - wbytes) / (23 * 1024);
+      if (stages >= 3 || p.out_bufs == 1) break;
+    }
+    if (stages > 6) stages = 6;
+    if (stages >= 2) {
+      p.halo_stages = stages;
+      const int smem_bytes = fixed + wbytes + stages * 23 * 1024;
+      switch (halo_bn) {
+        case 128: return launch_halo<128>(p, smem_bytes, stream);
+        case 64: return launch_halo<64>(p, smem_bytes, stream);
+        case 32: return launch_halo<32>(p, smem_bytes, stream);
+        default: return launch_halo<16>(p, smem_bytes, stream);
+      }
+    }
+    set_error("conv_tc: internal error: halo variant selected without room for two stages");
+    return PMOE_ERR_ARG;
+  }
   switch (bn) {
     case 256: return launch_tc_ck<256>(p, d->ck, stream);
     case 128: return launch_tc_ck<128>(p, d->ck, stream);

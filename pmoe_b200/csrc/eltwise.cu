@@ -227,7 +227,7 @@ __global__ void channel_sums_kernel(V4 src, float* __restrict__ out, long long o
 // ---------------------------------------------------------------- per-channel sum / sum of squares over N,H,W
 // (batch statistics for a BatchNorm that does not directly follow one of our conv epilogues: ResNet bn1)
 template <typename T>
-__global__ void channel_stats_kernel(V4 src, float* __restrict__ sum, float* __restrict__ sq, long long pix_per_block) {
+__global__ void channel_stats_kernel(V4 src, double* __restrict__ sum, double* __restrict__ sq, long long pix_per_block) {
   const int cg = src.c / 8;
   const int lanes = blockDim.x / cg;
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
@@ -251,15 +251,15 @@ __global__ void channel_stats_kernel(V4 src, float* __restrict__ sum, float* __r
   }
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    atomicAdd(sum + g * 8 + q, a[q]);
-    atomicAdd(sq + g * 8 + q, b[q]);
+    atomicAdd(sum + g * 8 + q, (double)a[q]);
+    atomicAdd(sq + g * 8 + q, (double)b[q]);
   }
 }
 
 // ---------------------------------------------------------------- BatchNorm (train): finalize + apply
 // Finalize: batch mean / biased var from (sum, sumsq), running-stat update exactly as
 // nn.BatchNorm2d (momentum 0.1, unbiased variance), and the fused affine (scale, shift).
-__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sq, float count, int c,
+__global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sq, float count, int c,
                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                    float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ mean_out, float* __restrict__ rstd_out, float* __restrict__ scale,
@@ -273,8 +273,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
     if (rstd_out) rstd_out[i] = 0.f;
     return;
   }
-  const double m = (double)sum[i] / count;
-  double var = (double)sq[i] / count - m * m;
+  const double m = sum[i] / (double)count;
+  double var = sq[i] / (double)count - m * m;
   if (var < 0) var = 0;
   const float rstd = (float)(1.0 / sqrt(var + (double)eps));
   if (running_mean) {
@@ -426,7 +426,7 @@ int pmoe_channel_sums(const PmoeView4* src, int32_t dtype, float* out, int64_t o
   return check_launch("channel_sums");
 }
 
-int pmoe_channel_stats(const PmoeView4* src, int32_t dtype, float* sum, float* sqsum, pmoe_stream_t stream_) {
+int pmoe_channel_stats(const PmoeView4* src, int32_t dtype, double* sum, double* sqsum, pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc = check_view(src, dtype, "channel_stats");
   if (rc) return rc;
@@ -443,7 +443,7 @@ int pmoe_channel_stats(const PmoeView4* src, int32_t dtype, float* sum, float* s
   return check_launch("channel_stats");
 }
 
-int pmoe_bn_finalize(const float* sum, const float* sqsum, float count, int32_t c, int32_t c_pad, const float* gamma,
+int pmoe_bn_finalize(const double* sum, const double* sqsum, float count, int32_t c, int32_t c_pad, const float* gamma,
                      const float* beta, float eps, float momentum, float* running_mean, float* running_var, float* mean_out,
                      float* rstd_out, float* scale, float* shift, pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

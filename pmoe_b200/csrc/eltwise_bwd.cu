@@ -75,8 +75,8 @@ static inline int bgrid(long long items, int threads) {
 // finishes with one atomicAdd per channel.
 template <typename T>
 __global__ void bn_bwd_reduce_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* __restrict__ mean,
-                                     const float* __restrict__ rstd, float* __restrict__ sum_dy,
-                                     float* __restrict__ sum_dy_xhat, long long pix_per_block) {
+                                     const float* __restrict__ rstd, double* __restrict__ sum_dy,
+                                     double* __restrict__ sum_dy_xhat, long long pix_per_block) {
   const int cg = dz.c / 8;
   const int lanes = blockDim.x / cg;
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
@@ -114,8 +114,8 @@ __global__ void bn_bwd_reduce_kernel(BV4 dz, BV4 z, BV4 x, int act, const float*
   }
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    atomicAdd(sum_dy + g * 8 + q, a[q]);
-    if (sum_dy_xhat) atomicAdd(sum_dy_xhat + g * 8 + q, b[q]);
+    atomicAdd(sum_dy + g * 8 + q, (double)a[q]);
+    if (sum_dy_xhat) atomicAdd(sum_dy_xhat + g * 8 + q, (double)b[q]);
   }
 }
 
@@ -125,7 +125,7 @@ __global__ void bn_bwd_reduce_kernel(BV4 dz, BV4 z, BV4 x, int act, const float*
 template <typename T>
 __global__ void bn_bwd_apply_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* __restrict__ mean,
                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                    const float* __restrict__ sum_dy, const float* __restrict__ sum_dy_xhat, float inv_n,
+                                    const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat, float inv_n,
                                     int batch_stats, BV4 dx, BV4 dres, int accumulate_dres) {
   const int cg = dz.c / 8;
   const long long total = (long long)dz.n * dz.h * dz.w * cg;
@@ -167,7 +167,7 @@ __global__ void bn_bwd_apply_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* 
           const float r = __ldg(rstd + c);
           const float xh = (xv[q] - __ldg(mean + c)) * r;
           const float gm = gamma ? __ldg(gamma + c) : 1.f;
-          o[q] = gm * r * (d[q] - __ldg(sum_dy + c) * inv_n - xh * __ldg(sum_dy_xhat + c) * inv_n);
+          o[q] = gm * r * (d[q] - (float)(sum_dy[c] * (double)inv_n) - xh * (float)(sum_dy_xhat[c] * (double)inv_n));
         }
       } else {
 #pragma unroll
@@ -398,7 +398,7 @@ using namespace pmoe;
 extern "C" {
 
 int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
-                       const float* mean, const float* rstd, float* sum_dy, float* sum_dy_xhat, pmoe_stream_t stream_) {
+                       const float* mean, const float* rstd, double* sum_dy, double* sum_dy_xhat, pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc;
   if ((rc = chk(dz, dtype, "bn_bwd_reduce dz"))) return rc;
@@ -419,8 +419,8 @@ int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4*
 }
 
 int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
-                      const float* mean, const float* rstd, const float* gamma, const float* sum_dy,
-                      const float* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
+                      const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
+                      const double* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
                       const PmoeView4* dres, int32_t accumulate_dres, pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc;

@@ -77,8 +77,8 @@ def _any_rg(params):
 # ------------------------------------------------------------------------------------------------ weight packing
 # ------------------------------------------------------------------------------------------------ raw launch helpers
 def _bn_bwd_reduce(dz, z, x, act, mean, rstd, cpad):
-    s1 = torch.zeros(cpad, dtype=torch.float32, device=dz.device)
-    s2 = torch.zeros(cpad, dtype=torch.float32, device=dz.device) if x is not None else None
+    s1 = torch.zeros(cpad, dtype=torch.float64, device=dz.device)
+    s2 = torch.zeros(cpad, dtype=torch.float64, device=dz.device) if x is not None else None
     vdz = view4(dz)
     vz = view4(z) if z is not None else _lib.null_view()
     vx = view4(x) if x is not None else _lib.null_view()
@@ -323,8 +323,8 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
     src_ts = [x.t for x in srcs]
     if bn_train:
         raw = torch.empty(n, h, w, cstore, dtype=dt, device=dev)
-        ssum = torch.zeros(cop, dtype=torch.float32, device=dev)
-        ssq = torch.zeros(cop, dtype=torch.float32, device=dev)
+        ssum = torch.zeros(cop, dtype=torch.float64, device=dev)
+        ssq = torch.zeros(cop, dtype=torch.float64, device=dev)
         ops.conv(src_ts, wp, segs, ck, raw, stat_sum=ssum, stat_sqsum=ssq, flops=flops, tag=tag)
         z_t, mean, rstd = _bn_tail_forward(tape, bn, raw, ssum, ssq, n * h * w, cout, cstore, act, residual, out)
         if want_pool:
@@ -566,8 +566,8 @@ def bn_act_op(tape, bn, x, act="relu", tag=""):
     bn_train = bn.training
     mean = rstd = gamma_p = scale = None
     if bn_train:
-        ssum = torch.zeros(cp, dtype=torch.float32, device=dev)
-        ssq = torch.zeros(cp, dtype=torch.float32, device=dev)
+        ssum = torch.zeros(cp, dtype=torch.float64, device=dev)
+        ssq = torch.zeros(cp, dtype=torch.float64, device=dev)
         v = view4(x.t)
         check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(v), dtype_code(x.t), ssum.data_ptr(),
                                                                                 ssq.data_ptr(), stream_ptr())), "channel_stats")

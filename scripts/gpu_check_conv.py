@@ -68,8 +68,8 @@ def run_conv(name, B, H, W, cins, cout, k=3, act="relu", affine=True, residual=F
     if residual:
         resf = torch.randn(B, cout, H, W, generator=g).to(dev)
         res = to_nhwc_pad(resf, cstore)
-    ssum = torch.zeros(cop, device=dev) if stats else None
-    ssq = torch.zeros(cop, device=dev) if stats else None
+    ssum = torch.zeros(cop, device=dev, dtype=torch.float64) if stats else None
+    ssq = torch.zeros(cop, device=dev, dtype=torch.float64) if stats else None
     psum = torch.zeros(B, cop, device=dev) if pool else None
     sc = ops.pad_vec(scale, cop, 1.0) if affine else None
     sh = ops.pad_vec(shift, cop, 0.0) if affine else None
@@ -97,8 +97,8 @@ def run_conv(name, B, H, W, cins, cout, k=3, act="relu", affine=True, residual=F
     if stats:
         rs = raw.sum(dim=(0, 2, 3))
         rq = (raw * raw).sum(dim=(0, 2, 3))
-        rec["stat_sum_rel"] = ((ssum[:cout] - rs).norm() / (rs.norm() + 1e-12)).item()
-        rec["stat_sq_rel"] = ((ssq[:cout] - rq).norm() / (rq.norm() + 1e-12)).item()
+        rec["stat_sum_rel"] = ((ssum[:cout].float() - rs).norm() / (rs.norm() + 1e-12)).item()
+        rec["stat_sq_rel"] = ((ssq[:cout].float() - rq).norm() / (rq.norm() + 1e-12)).item()
     if pool:
         rp = got.sum(dim=(2, 3))
         rec["pool_rel"] = ((psum[:, :cout] - rp).norm() / (rp.norm() + 1e-12)).item()

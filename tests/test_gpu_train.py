@@ -47,38 +47,46 @@ def full_grad_errors(named_params, oracle_sd):
 
 
 def oracle_unet_step(g, sd):
+    """Oracle forward + backward of d(seg loss)/d(logits) taken at the oracle's own logits. Returns that upstream too."""
     sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("running_mean", "running_var")) else v.clone())
            for k, v in sd.items()}
     logits = O.unet(g["img"], sdg, "", True)
-    loss = O.ce_tversky(logits, g["mask"])
-    loss.backward()
-    return logits.detach(), sdg
+    up = upstream_seg_grad(logits, g["mask"])
+    logits.backward(gradient=up)
+    return logits.detach(), sdg, up
+
+
+def upstream_seg_grad(logits, mask):
+    """d(cross_entropy_tversky)/d(logits) evaluated on the CPU at the given logits. The dice weights inside that loss
+    come from an arg-max (loss.py:8-16), so a 1e-5 perturbation of the logits can flip a pixel and move every
+    gradient by ~1e-2: gradient parity therefore feeds the SAME upstream gradient to both implementations. The loss
+    kernels have their own parity test (test_gpu_moe.py::test_losses_vs_oracle)."""
+    leaf = logits.detach().clone().requires_grad_(True)
+    O.ce_tversky(leaf, mask).backward()
+    return leaf.grad
 
 
 def test_unet_stage0_train_step_fp32_vs_reference_golden():
-    """fp32 mode against the live-reference golden (B=2, 32x32): outputs, loss, every gradient, BN running stats."""
+    """fp32 mode against the live-reference golden (B=2, 32x32): outputs, every gradient, BN running stats."""
     from pmoe_b200 import config
     from pmoe_b200.model.blocks.unet import UNet
     g = load("unet_stage0.pt")
     sd = O.seeded_state_dict(O.make_spec(O.unet_spec, 3, 23), g["seed"])
+    up = upstream_seg_grad(g["logits_train"], g["mask"])  # exactly what the reference back-propagated
     with config.use_precision("fp32"):
         net = UNet(3, 23)
         net.load_state_dict(sd, strict=True)
         net = net.cuda().train()
         logits = net(g["img"].cuda())
-        loss = O.ce_tversky(logits.cpu(), g["mask"])
-        loss.backward()
+        logits.backward(gradient=up.cuda())
     e_out = rel_err(logits.detach().cpu(), g["logits_train"])
     wn, wv, n = grad_report(net.named_parameters(), g["grads"])
-    ref_logits, sdg = oracle_unet_step(g, sd)
-    errs = full_grad_errors(net.named_parameters(), sdg)
     bn_err = max(rel_err(net.state_dict()[k].float().cpu(), v.float()) for k, v in g["bn"].items() if v.is_floating_point())
-    print("\n[fp32] unet train: logits rel %.3e | loss %.6f vs %.6f | grad norm err %.3e (%s) | sample err %.3e (%s) | bn %.3e | worst grad %.3e"
-          % (e_out, loss.item(), g["loss"].item(), wn[0], wn[1], wv[0], wv[1], bn_err, max(errs.values())))
+    print("\n[fp32] unet train: logits rel %.3e | grad norm err %.3e (%s) | sample err %.3e (%s) | bn %.3e"
+          % (e_out, wn[0], wn[1], wv[0], wv[1], bn_err))
     assert n > 40
     assert e_out < 1e-4
-    assert abs(loss.item() - g["loss"].item()) < 1e-4
-    assert wn[0] < 1e-3 and wv[0] < 1e-3 and max(errs.values()) < 1e-3
+    assert wn[0] < 1e-3 and wv[0] < 1e-3
     assert bn_err < 1e-4
     assert int(net.state_dict()["dwn_1.1.num_batches_tracked"]) == 1
 
@@ -105,7 +113,8 @@ def test_bf16_noise_vs_tensor_core_path():
     x = torch.randn(4, 64, 32, 32, generator=torch.Generator().manual_seed(8))
     sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
     ref = O.conv3_block(x, sdg, "", True)
-    (ref ** 2).sum().backward()
+    upc = torch.randn(ref.shape, generator=torch.Generator().manual_seed(9))
+    ref.backward(gradient=upc)
     for simt in (False, True):
         config.FORCE_SIMT = simt
         try:
@@ -114,7 +123,7 @@ def test_bf16_noise_vs_tensor_core_path():
                 blk.load_state_dict(sd, strict=True)
                 blk = blk.cuda().train()
                 y = blk(x.cuda())
-                (y.cpu() ** 2).sum().backward()
+                y.backward(gradient=upc.cuda())
         finally:
             config.FORCE_SIMT = False
         ge = max(rel_err(p.grad.cpu(), sdg[n].grad) for n, p in blk.named_parameters())
@@ -122,7 +131,7 @@ def test_bf16_noise_vs_tensor_core_path():
     # (b) the full U-Net train step at two sizes
     for (B, H) in ((4, 64), (8, 128)):
         g, sdu = _unet_case(B, H, H)
-        ref_logits, sdg2 = oracle_unet_step(g, sdu)
+        ref_logits, sdg2, up2 = oracle_unet_step(g, sdu)
         for simt in (False, True):
             config.FORCE_SIMT = simt
             try:
@@ -131,7 +140,7 @@ def test_bf16_noise_vs_tensor_core_path():
                     net.load_state_dict(sdu, strict=True)
                     net = net.cuda().train()
                     logits = net(g["img"].cuda())
-                    O.ce_tversky(logits.cpu(), g["mask"]).backward()
+                    logits.backward(gradient=up2.cuda())
             finally:
                 config.FORCE_SIMT = False
             errs = sorted(full_grad_errors(net.named_parameters(), sdg2).values())
@@ -144,9 +153,9 @@ def test_bf16_noise_vs_tensor_core_path():
 
 
 def test_punet_stage1_train_step_fp32(tmp_path):
-    """PU-Net BPTT step in fp32 mode. This step is chaotic under train-mode BatchNorm (the CPU reference in fp32
-    and fp64 already differ by ~1e-2 on the last frame), so parity is asserted RELATIVE to the fp64 oracle:
-    the CUDA fp32 path must sit within a small factor of the CPU fp32 path's own distance to fp64."""
+    """PU-Net BPTT step in fp32 mode with a fixed upstream gradient. Ten chained U-Nets under train-mode BatchNorm
+    amplify rounding noise, so parity is asserted RELATIVE to the fp64 oracle: the CUDA fp32 path must sit within a
+    small factor of the CPU fp32 path's own distance to fp64."""
     from pmoe_b200 import config
     from pmoe_b200.model.punet import PredictiveUnet
     g = load("punet_stage1.pt")
@@ -155,15 +164,7 @@ def test_punet_stage1_train_step_fp32(tmp_path):
     ck = tmp_path / "unet.pth"
     torch.save({"unet": {k[len("unet."):]: v for k, v in sd.items() if k.startswith("unet.")}}, ck)
     pc["model_path"] = str(ck)
-    with config.use_precision("fp32"):
-        net = PredictiveUnet(**pc)
-        net.load_state_dict(sd, strict=True)
-        net = net.cuda().train()  # flips the frozen unet's BN back to batch statistics, like train_1.py:123
-        out = net(g["imgs"].cuda())
-        loss = O.autoregressive_ce_tversky(out.cpu(), g["masks"])
-        loss.backward()
-
-    def oracle(dtype):
+    def oracle(dtype, up=None):
         sdg = {}
         for k, v in sd.items():
             v = v.clone().to(dtype) if v.is_floating_point() else v.clone()
@@ -171,11 +172,22 @@ def test_punet_stage1_train_step_fp32(tmp_path):
                 v.requires_grad_(True)
             sdg[k] = v
         o = O.punet(g["imgs"].to(dtype), sdg, "", True, pc["past_frames"], pc["future_frames"])
-        O.autoregressive_ce_tversky(o, g["masks"]).backward()
-        return o.detach(), sdg
+        if up is None:
+            leaf = o.detach().clone().requires_grad_(True)
+            O.autoregressive_ce_tversky(leaf, g["masks"]).backward()
+            up = leaf.grad
+        o.backward(gradient=up.to(dtype))
+        return o.detach(), sdg, up
 
-    o64, sd64 = oracle(torch.float64)
-    o32, sd32 = oracle(torch.float32)
+    o64, sd64, up = oracle(torch.float64)
+    o32, sd32, _ = oracle(torch.float32, up)
+    with config.use_precision("fp32"):
+        net = PredictiveUnet(**pc)
+        net.load_state_dict(sd, strict=True)
+        net = net.cuda().train()  # flips the frozen unet's BN back to batch statistics, like train_1.py:123
+        out = net(g["imgs"].cuda())
+        out.backward(gradient=up.float().cuda())
+
     e_cuda, e_cpu = rel_err(out.detach().cpu(), o64), rel_err(o32, o64)
     gc, gp = {}, {}
     for name, p in net.named_parameters():

@@ -82,6 +82,10 @@ int pmoe_conv_simt(const PmoeConvTc* desc, int32_t dtype, pmoe_stream_t stream);
 /* Weight gradient of the same descriptor (aten::convolution_backward, weight half): desc->out is read as
  * dy; dwpack[cout_pad][ktot] (fp32, packed K order of wpack) is ACCUMULATED into. */
 int pmoe_conv_wgrad_simt(const PmoeConvTc* desc, int32_t dtype, float* dwpack, pmoe_stream_t stream);
+/* Tensor-core weight gradient (bf16 dy / activations, fp32 accumulation in TMEM, fp32 atomics into dwpack). Same contract
+ * as pmoe_conv_wgrad_simt with dtype = PMOE_BF16. Returns PMOE_ERR_UNSUPPORTED, launching nothing, when the descriptor is
+ * outside what the tensor-core kernels cover (the caller then uses pmoe_conv_wgrad_simt). */
+int pmoe_conv_wgrad_tc(const PmoeConvTc* desc, float* dwpack, pmoe_stream_t stream);
 
 /* ---- memory-bound kernels (eltwise.cu); dtype = PMOE_F32 | PMOE_BF16 of the NHWC views ------------- */
 /* Module boundary: the reference hands fp32 NCHW tensors to forward() (model/moe.py:90-93, punet.py:88). */

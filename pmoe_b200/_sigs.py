@@ -15,6 +15,7 @@ SIGS = {
     "pmoe_affine_act": [vp, vp, i32, vp, vp, vp, i32, vp],
     "pmoe_conv_simt": [vp, i32, vp],
     "pmoe_conv_wgrad_simt": [vp, i32, vp, vp],
+    "pmoe_conv_wgrad_tc": [vp, vp, vp],
     "pmoe_bn_bwd_reduce": [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp],
     "pmoe_bn_bwd_apply": [vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, f32, i32, vp, vp, i32, vp],
     "pmoe_maxpool_bwd": [vp, vp, vp, i32, i32, i32, i32, i32, vp],

@@ -144,8 +144,18 @@ def conv_wgrad(srcs, segs, ck, dy, dwpack, flops=0.0, tag=""):
     dt = dy.dtype
     d = _fill_desc(srcs, dwpack, segs, ck, dy, None, None, None, None, None, None, None, None, 0, dt)
     assert dwpack.dtype == torch.float32
-    fn = _lib.lib().pmoe_conv_wgrad_simt
     sp = _lib.stream_ptr()
+    from . import config
+    if dt == torch.bfloat16 and not config.FORCE_SIMT:
+        # tensor-core kernel first; PMOE_ERR_UNSUPPORTED (-2) means "shape not covered", nothing was launched
+        tc = _lib.lib().pmoe_conv_wgrad_tc
+        rc = profiler.launch("conv_wgrad_tc", lambda: tc(C.byref(d), dwpack.data_ptr(), sp), flops, 0.0, tag)
+        if rc == 0:
+            return dwpack
+        if rc != -2:
+            _lib.check(rc, "conv_wgrad_tc")
+        profiler.uncount()
+    fn = _lib.lib().pmoe_conv_wgrad_simt
     code = _lib.BF16 if dt == torch.bfloat16 else _lib.F32
     _lib.check(profiler.launch("conv_wgrad", lambda: fn(C.byref(d), code, dwpack.data_ptr(), sp), flops, 0.0, tag), "conv_wgrad")
     return dwpack

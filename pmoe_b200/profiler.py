@@ -13,6 +13,14 @@ def reset():
     _records = []
 
 
+def uncount():
+    """Take back the last launch() whose C-ABI call reported that it launched nothing."""
+    global _count
+    _count -= 1
+    if _events_on and _records:
+        _records.pop()
+
+
 def launch_count():
     return _count
 

@@ -97,6 +97,10 @@ int pmoe_nhwc_to_nchw(const PmoeView4* src, int32_t src_dtype, int32_t c, float*
  * relu(scale*x+shift) on load (eval-mode bn1+relu of the ResNet stem, backbone.py:63). */
 int pmoe_maxpool(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, int32_t k, int32_t stride, int32_t pad,
                  const float* scale, const float* shift, int32_t relu, pmoe_stream_t stream);
+/* Training-mode max-pool: also stores, per output element, the row-major window position (r*k+s) of the FIRST maximum
+ * (ATen's tie rule) in idx_out, a dense (n, oh, ow, dst.c) uint8 tensor consumed by pmoe_maxpool_bwd_idx. */
+int pmoe_maxpool_idx(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, int32_t k, int32_t stride, int32_t pad,
+                     uint8_t* idx_out, pmoe_stream_t stream);
 /* EfficientBlock (basics.py:62-77): gate = sigmoid(conv1d_k(mean_hw(x))) from per-image channel sums. */
 int pmoe_eca_gate(const float* pool_sum, int64_t pool_stride, int32_t n, float inv_count, const float* w, int32_t k,
                   int32_t groups, int32_t group_c, int32_t group_stride, float* gate, int64_t gate_stride,
@@ -127,6 +131,8 @@ int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* 
                       const PmoeView4* dres, int32_t accumulate_dres, pmoe_stream_t stream);
 int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* dx, int32_t dtype, int32_t k, int32_t stride,
                      int32_t pad, int32_t accumulate, pmoe_stream_t stream);
+int pmoe_maxpool_bwd_idx(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* dx, int32_t dtype, int32_t k,
+                         int32_t stride, int32_t pad, int32_t accumulate, pmoe_stream_t stream);
 int pmoe_prod_channel_sums(const PmoeView4* a, const PmoeView4* b, int32_t dtype, float* out, int64_t out_stride,
                            pmoe_stream_t stream);
 int pmoe_eca_gate_bwd(const float* dgate, int64_t dgate_stride, const float* gate, int64_t gate_stride, const float* pool_sum,
@@ -167,6 +173,27 @@ int pmoe_segloss_bwd(const float* logits, int64_t sb, int64_t sc, int64_t sh, in
                      int64_t th, int64_t tw, int32_t B, int32_t C, int32_t H, int32_t W, float wce, const float* workspace,
                      const float* grad_scale_dev, float grad_scale, float* dlogits, int64_t db, int64_t dc, int64_t dh,
                      int64_t dw, int32_t accumulate, pmoe_stream_t stream);
+
+/* ---- optimizer side (optim.cu): multi-tensor kernels over a DEVICE table of chunks ------------------------- */
+/* One chunk = up to 2^31-1 consecutive fp32 elements of one parameter with its gradient and Adam state. */
+typedef struct PmoeMtChunk {
+  float* p;    /* parameter            (mt_adam) */
+  float* g;    /* gradient             (all)     */
+  float* m;    /* exp_avg              (mt_adam) */
+  float* v;    /* exp_avg_sq           (mt_adam) */
+  float* vmax; /* max_exp_avg_sq       (mt_adam with amsgrad) */
+  int32_t n;
+  int32_t pad;
+} PmoeMtChunk;
+/* *sqnorm_accum += sum g^2 over all chunks: the global gradient norm of check_grad_norm (utils/nn.py:10-19) and of
+ * torch.nn.utils.clip_grad_norm_ (trainer/train_2.py:160-161) in one launch and no host sync. */
+int pmoe_mt_sqnorm(const PmoeMtChunk* chunks_dev, int32_t n_chunks, double* sqnorm_accum, pmoe_stream_t stream);
+/* g *= min(1, max_norm / (sqrt(*sqnorm) + 1e-6)) — clip_grad_norm_'s scaling, coefficient computed on the device. */
+int pmoe_mt_clip(const PmoeMtChunk* chunks_dev, int32_t n_chunks, const double* sqnorm, float max_norm, pmoe_stream_t stream);
+/* torch.optim.Adam(amsgrad) step (conf/stage_2.yaml:137-144, train_2.py:165) over all chunks; when sqnorm != NULL the
+ * clip coefficient is applied to the gradient on the fly (gradients themselves are left unscaled). */
+int pmoe_mt_adam(const PmoeMtChunk* chunks_dev, int32_t n_chunks, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int32_t step, int32_t amsgrad, const double* sqnorm, float max_norm, pmoe_stream_t stream);
 
 /* Library info / errors. */
 int pmoe_version(void);

@@ -7,6 +7,8 @@ SIGS = {
     "pmoe_nchw_to_nhwc": [vp, i64, i64, i64, i64, i32, vp, i32, vp],
     "pmoe_nhwc_to_nchw": [vp, i32, i32, vp, i64, i64, i64, i64, vp],
     "pmoe_maxpool": [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp],
+    "pmoe_maxpool_idx": [vp, vp, i32, i32, i32, i32, vp, vp],
+    "pmoe_maxpool_bwd_idx": [vp, vp, vp, i32, i32, i32, i32, i32, vp],
     "pmoe_eca_gate": [vp, i64, i32, f32, vp, i32, i32, i32, i32, vp, i64, vp],
     "pmoe_scale_channels": [vp, vp, i32, vp, i64, vp],
     "pmoe_channel_sums": [vp, i32, vp, i64, vp],
@@ -28,6 +30,9 @@ SIGS = {
     "pmoe_moe_loss": [vp, vp, vp, vp, i32, vp, vp, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp],
     "pmoe_dropout": [vp, vp, i32, i64, f32, C.c_uint64, vp],
     "pmoe_l1_mse": [vp, vp, i64, i32, f32, vp, vp, vp],
+    "pmoe_mt_sqnorm": [vp, i32, vp, vp],
+    "pmoe_mt_clip": [vp, i32, vp, f32, vp],
+    "pmoe_mt_adam": [vp, i32, f32, f32, f32, f32, f32, i32, i32, vp, f32, vp],
     "pmoe_segloss_fwd": [vp, i64, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, i32, f32, f32, vp, vp, vp],
     "pmoe_segloss_bwd": [vp, i64, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, i32, f32, vp, vp, f32, vp, i64, i64, i64, i64, i32, vp],
 }

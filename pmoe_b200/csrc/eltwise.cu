@@ -4,6 +4,7 @@
 // to a multiple of the SM count.
 #include "host_util.h"
 #include "ptx.cuh"
+#include "reduce.cuh"
 
 namespace pmoe {
 
@@ -111,7 +112,7 @@ __global__ void nhwc_to_nchw_kernel(V4 src, int c, float* __restrict__ dst, long
 // ---------------------------------------------------------------- max-pool (optional affine+ReLU on load)
 template <typename T>
 __global__ void maxpool_kernel(V4 src, V4 dst, int k, int stride, int pad, const float* __restrict__ scale,
-                               const float* __restrict__ shift, int relu) {
+                               const float* __restrict__ shift, int relu, uint8_t* __restrict__ idx_out) {
   const int cg = dst.c / 8;
   const long long total = (long long)dst.n * dst.h * dst.w * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -128,8 +129,12 @@ __global__ void maxpool_kernel(V4 src, V4 dst, int k, int stride, int pad, const
       sf[q] = shift ? __ldg(shift + g * 8 + q) : 0.f;
     }
     float m[8];
+    uint32_t arg[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) m[q] = -INFINITY;
+    for (int q = 0; q < 8; ++q) {
+      m[q] = -INFINITY;
+      arg[q] = 0;
+    }
     for (int r = 0; r < k; ++r) {
       const int ih = oh * stride - pad + r;
       if (ih < 0 || ih >= src.h) continue;
@@ -142,11 +147,20 @@ __global__ void maxpool_kernel(V4 src, V4 dst, int k, int stride, int pad, const
         for (int q = 0; q < 8; ++q) {
           float x = fmaf(v[q], sc[q], sf[q]);
           if (relu) x = fmaxf(x, 0.f);
-          m[q] = fmaxf(m[q], x);
+          if (x > m[q]) {  // the FIRST maximum in row-major window order wins (ATen max_pool2d tie rule)
+            m[q] = x;
+            arg[q] = (uint32_t)(r * k + s);
+          }
         }
       }
     }
     store8(static_cast<T*>(dst.ptr) + n * dst.sn + oh * dst.sh + ow * dst.sw + g * 8, m);
+    if (idx_out) {
+      uint2 pk;
+      pk.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      pk.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      *reinterpret_cast<uint2*>(idx_out + (((long long)n * dst.h + oh) * dst.w + ow) * dst.c + g * 8) = pk;
+    }
   }
 }
 
@@ -200,8 +214,9 @@ __global__ void scale_channels_kernel(V4 src, V4 dst, const float* __restrict__ 
 
 // ---------------------------------------------------------------- per-(n,c) sums over HW (ECA / global avg-pool)
 template <typename T>
-__global__ void channel_sums_kernel(V4 src, float* __restrict__ out, long long out_stride, int rows_per_block) {
+__global__ void __launch_bounds__(kRedThreads) channel_sums_kernel(V4 src, float* __restrict__ out, long long out_stride, int rows_per_block) {
   // grid: (ceil(h*w / rows_per_block), n); block: 256 threads = cg channel groups x (256/cg) pixel lanes
+  __shared__ float sm[kRedThreads * 8];
   const int cg = src.c / 8;
   const int lanes = blockDim.x / cg;
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
@@ -219,40 +234,53 @@ __global__ void channel_sums_kernel(V4 src, float* __restrict__ out, long long o
 #pragma unroll
       for (int q = 0; q < 8; ++q) acc[q] += v[q];
     }
+  }
+  float tot[kRedMaxIter];
+  block_channel_sum(acc, sm, cg, lanes, tot);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) atomicAdd(out + n * out_stride + g * 8 + q, acc[q]);
+  for (int j = 0; j < kRedMaxIter; ++j) {
+    const int c = threadIdx.x + j * kRedThreads;
+    if (c < cg * 8 && tot[j] != 0.f) atomicAdd(out + n * out_stride + c, tot[j]);
   }
 }
 
 // ---------------------------------------------------------------- per-channel sum / sum of squares over N,H,W
 // (batch statistics for a BatchNorm that does not directly follow one of our conv epilogues: ResNet bn1)
 template <typename T>
-__global__ void channel_stats_kernel(V4 src, double* __restrict__ sum, double* __restrict__ sq, long long pix_per_block) {
+__global__ void __launch_bounds__(kRedThreads) channel_stats_kernel(V4 src, double* __restrict__ sum, double* __restrict__ sq, long long pix_per_block) {
+  __shared__ float sm[kRedThreads * 8];
   const int cg = src.c / 8;
   const int lanes = blockDim.x / cg;
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
-  if (lane >= lanes) return;
   const long long npix = (long long)src.n * src.h * src.w;
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   long long p1 = p0 + pix_per_block;
   if (p1 > npix) p1 = npix;
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long p = p0 + lane; p < p1; p += lanes) {
-    const int w = (int)(p % src.w);
-    const long long t = p / src.w;
-    const int h = (int)(t % src.h), n = (int)(t / src.h);
-    float v[8];
-    load8(static_cast<const T*>(src.ptr) + n * src.sn + h * src.sh + w * src.sw + g * 8, v);
+  if (lane < lanes) {
+    for (long long p = p0 + lane; p < p1; p += lanes) {
+      const int w = (int)(p % src.w);
+      const long long t = p / src.w;
+      const int h = (int)(t % src.h), n = (int)(t / src.h);
+      float v[8];
+      load8(static_cast<const T*>(src.ptr) + n * src.sn + h * src.sh + w * src.sw + g * 8, v);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      a[q] += v[q];
-      b[q] += v[q] * v[q];
+      for (int q = 0; q < 8; ++q) {
+        a[q] += v[q];
+        b[q] += v[q] * v[q];
+      }
     }
   }
+  float ta[kRedMaxIter], tb[kRedMaxIter];
+  block_channel_sum(a, sm, cg, lanes, ta);
+  block_channel_sum(b, sm, cg, lanes, tb);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    atomicAdd(sum + g * 8 + q, (double)a[q]);
-    atomicAdd(sq + g * 8 + q, (double)b[q]);
+  for (int j = 0; j < kRedMaxIter; ++j) {
+    const int c = threadIdx.x + j * kRedThreads;
+    if (c < cg * 8) {
+      atomicAdd(sum + c, (double)ta[j]);
+      atomicAdd(sq + c, (double)tb[j]);
+    }
   }
 }
 
@@ -368,19 +396,32 @@ int pmoe_nhwc_to_nchw(const PmoeView4* src, int32_t src_dtype, int32_t c, float*
   return check_launch("nhwc_to_nchw");
 }
 
-int pmoe_maxpool(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, int32_t k, int32_t stride, int32_t pad,
-                 const float* scale, const float* shift, int32_t relu, pmoe_stream_t stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int maxpool_launch(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, int32_t k, int32_t stride, int32_t pad,
+                          const float* scale, const float* shift, int32_t relu, uint8_t* idx_out, cudaStream_t stream) {
   int rc = check_view(src, dtype, "maxpool src");
   if (rc) return rc;
   if ((rc = check_view(dst, dtype, "maxpool dst"))) return rc;
-  if (src->c < dst->c || src->n != dst->n || k < 1 || stride < 1) {
+  if (src->c < dst->c || src->n != dst->n || k < 1 || stride < 1 || k > 15 || ((uintptr_t)idx_out & 7)) {
     set_error("maxpool: geometry mismatch");
     return PMOE_ERR_ARG;
   }
   const long long items = (long long)dst->n * dst->h * dst->w * (dst->c / 8);
-  DISPATCH_DTYPE(dtype, (maxpool_kernel<T><<<grid_for(items, 256), 256, 0, stream>>>(to_v4(*src), to_v4(*dst), k, stride, pad, scale, shift, relu)));
+  DISPATCH_DTYPE(dtype, (maxpool_kernel<T><<<grid_for(items, 256), 256, 0, stream>>>(to_v4(*src), to_v4(*dst), k, stride, pad, scale, shift, relu, idx_out)));
   return check_launch("maxpool");
+}
+
+int pmoe_maxpool(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, int32_t k, int32_t stride, int32_t pad,
+                 const float* scale, const float* shift, int32_t relu, pmoe_stream_t stream_) {
+  return maxpool_launch(src, dst, dtype, k, stride, pad, scale, shift, relu, nullptr, static_cast<cudaStream_t>(stream_));
+}
+
+int pmoe_maxpool_idx(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, int32_t k, int32_t stride, int32_t pad,
+                     uint8_t* idx_out, pmoe_stream_t stream_) {
+  if (!idx_out) {
+    set_error("maxpool_idx: index buffer missing");
+    return PMOE_ERR_ARG;
+  }
+  return maxpool_launch(src, dst, dtype, k, stride, pad, nullptr, nullptr, 0, idx_out, static_cast<cudaStream_t>(stream_));
 }
 
 int pmoe_eca_gate(const float* pool_sum, int64_t pool_stride, int32_t n, float inv_count, const float* w, int32_t k,

@@ -3,6 +3,7 @@
 // gradient accumulation. Same conventions as eltwise.cu: strided NHWC views, 8 channels per thread.
 #include "host_util.h"
 #include "ptx.cuh"
+#include "reduce.cuh"
 
 namespace pmoe {
 
@@ -74,48 +75,56 @@ static inline int bgrid(long long items, int threads) {
 // dy = dz * act'(z). Block = cg channel groups x (256/cg) pixel lanes; each block walks a slab of pixels and
 // finishes with one atomicAdd per channel.
 template <typename T>
-__global__ void bn_bwd_reduce_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* __restrict__ mean,
+__global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, double* __restrict__ sum_dy,
                                      double* __restrict__ sum_dy_xhat, long long pix_per_block) {
+  __shared__ float sm[kRedThreads * 8];
   const int cg = dz.c / 8;
   const int lanes = blockDim.x / cg;
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
-  if (lane >= lanes) return;
   const long long npix = (long long)dz.n * dz.h * dz.w;
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   long long p1 = p0 + pix_per_block;
   if (p1 > npix) p1 = npix;
-  float m[8], r[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    m[q] = mean ? __ldg(mean + g * 8 + q) : 0.f;
-    r[q] = rstd ? __ldg(rstd + g * 8 + q) : 1.f;
-  }
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long p = p0 + lane; p < p1; p += lanes) {
-    const int w = (int)(p % dz.w);
-    const long long t = p / dz.w;
-    const int h = (int)(t % dz.h), n = (int)(t / dz.h);
-    float d[8], xv[8];
-    bload8(at<T>(dz, n, h, w, g * 8), d);
-    if (act != PMOE_ACT_NONE) {
-      float zv[8];
-      bload8(at<T>(z, n, h, w, g * 8), zv);
+  if (lane < lanes) {
+    float m[8], r[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) d[q] *= act_grad(zv[q], act);
+    for (int q = 0; q < 8; ++q) {
+      m[q] = mean ? __ldg(mean + g * 8 + q) : 0.f;
+      r[q] = rstd ? __ldg(rstd + g * 8 + q) : 1.f;
     }
+    for (long long p = p0 + lane; p < p1; p += lanes) {
+      const int w = (int)(p % dz.w);
+      const long long t = p / dz.w;
+      const int h = (int)(t % dz.h), n = (int)(t / dz.h);
+      float d[8], xv[8];
+      bload8(at<T>(dz, n, h, w, g * 8), d);
+      if (act != PMOE_ACT_NONE) {
+        float zv[8];
+        bload8(at<T>(z, n, h, w, g * 8), zv);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) a[q] += d[q];
-    if (x.ptr) {
-      bload8(at<T>(x, n, h, w, g * 8), xv);
+        for (int q = 0; q < 8; ++q) d[q] *= act_grad(zv[q], act);
+      }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) b[q] += d[q] * (xv[q] - m[q]) * r[q];
+      for (int q = 0; q < 8; ++q) a[q] += d[q];
+      if (x.ptr) {
+        bload8(at<T>(x, n, h, w, g * 8), xv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) b[q] += d[q] * (xv[q] - m[q]) * r[q];
+      }
     }
   }
+  float ta[kRedMaxIter], tb[kRedMaxIter];
+  block_channel_sum(a, sm, cg, lanes, ta);
+  if (sum_dy_xhat) block_channel_sum(b, sm, cg, lanes, tb);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    atomicAdd(sum_dy + g * 8 + q, (double)a[q]);
-    if (sum_dy_xhat) atomicAdd(sum_dy_xhat + g * 8 + q, (double)b[q]);
+  for (int j = 0; j < kRedMaxIter; ++j) {
+    const int c = threadIdx.x + j * kRedThreads;
+    if (c < cg * 8) {
+      atomicAdd(sum_dy + c, (double)ta[j]);
+      if (sum_dy_xhat) atomicAdd(sum_dy_xhat + c, (double)tb[j]);
+    }
   }
 }
 
@@ -237,30 +246,74 @@ __global__ void maxpool_bwd_kernel(BV4 x, BV4 dy, BV4 dx, int k, int stride, int
   }
 }
 
+// max-pool backward from the argmax codes the forward stored (pmoe_maxpool_idx): no re-scan of the windows.
+template <typename T>
+__global__ void maxpool_bwd_idx_kernel(BV4 dy, const uint8_t* __restrict__ idx, BV4 dx, int k, int stride, int pad, int accumulate) {
+  const int cg = dx.c / 8;
+  const long long total = (long long)dx.n * dx.h * dx.w * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % cg);
+    long long pix = i / cg;
+    const int iw = (int)(pix % dx.w);
+    pix /= dx.w;
+    const int ih = (int)(pix % dx.h);
+    const int n = (int)(pix / dx.h);
+    float o[8];
+    if (accumulate) bload8(at<T>(dx, n, ih, iw, g * 8), o);
+    else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = 0.f;
+    }
+    const int oh_lo = max(0, (ih + pad - k + stride) / stride), oh_hi = min(dy.h - 1, (ih + pad) / stride);
+    const int ow_lo = max(0, (iw + pad - k + stride) / stride), ow_hi = min(dy.w - 1, (iw + pad) / stride);
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+        const uint32_t code = (uint32_t)((ih - (oh * stride - pad)) * k + (iw - (ow * stride - pad)));
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx + (((long long)n * dy.h + oh) * dy.w + ow) * dy.c + g * 8));
+        float d[8];
+        bload8(at<T>(dy, n, oh, ow, g * 8), d);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t a = ((q < 4 ? pk.x : pk.y) >> (8 * (q & 3))) & 0xffu;
+          if (a == code) o[q] += d[q];
+        }
+      }
+    }
+    bstore8(at_mut<T>(dx, n, ih, iw, g * 8), o);
+  }
+}
+
 // ---------------------------------------------------------------- ECA backward
 // out = x * gate[n,c]. pass 1: dgate[n,c] = sum_hw dout*x (per-image channel sums of a product)
 template <typename T>
-__global__ void prod_channel_sums_kernel(BV4 a, BV4 b, float* __restrict__ out, long long out_stride, int rows_per_block) {
+__global__ void __launch_bounds__(kRedThreads) prod_channel_sums_kernel(BV4 a, BV4 b, float* __restrict__ out, long long out_stride, int rows_per_block) {
+  __shared__ float sm[kRedThreads * 8];
   const int cg = a.c / 8;
   const int lanes = blockDim.x / cg;
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
-  if (lane >= lanes) return;
   const int n = blockIdx.y;
   const long long hw = (long long)a.h * a.w;
   const long long p0 = (long long)blockIdx.x * rows_per_block;
   long long p1 = p0 + rows_per_block;
   if (p1 > hw) p1 = hw;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (long long p = p0 + lane; p < p1; p += lanes) {
-    const int h = (int)(p / a.w), w = (int)(p % a.w);
-    float u[8], v[8];
-    bload8(at<T>(a, n, h, w, g * 8), u);
-    bload8(at<T>(b, n, h, w, g * 8), v);
+  if (lane < lanes) {
+    for (long long p = p0 + lane; p < p1; p += lanes) {
+      const int h = (int)(p / a.w), w = (int)(p % a.w);
+      float u[8], v[8];
+      bload8(at<T>(a, n, h, w, g * 8), u);
+      bload8(at<T>(b, n, h, w, g * 8), v);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc[q] += u[q] * v[q];
+      for (int q = 0; q < 8; ++q) acc[q] += u[q] * v[q];
+    }
   }
+  float tot[kRedMaxIter];
+  block_channel_sum(acc, sm, cg, lanes, tot);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) atomicAdd(out + n * out_stride + g * 8 + q, acc[q]);
+  for (int j = 0; j < kRedMaxIter; ++j) {
+    const int c = threadIdx.x + j * kRedThreads;
+    if (c < cg * 8 && tot[j] != 0.f) atomicAdd(out + n * out_stride + c, tot[j]);
+  }
 }
 
 // tiny: gate = sigmoid(pre), pre = conv1d(mean). dpre = dgate*gate*(1-gate); dmean = corr(dpre, w) / count;
@@ -448,6 +501,21 @@ int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* d
   const long long items = (long long)dx->n * dx->h * dx->w * (dx->c / 8);
   BW_DISPATCH(dtype, (maxpool_bwd_kernel<T><<<bgrid(items, 256), 256, 0, stream>>>(bv4(x), bv4(dy), bv4(dx), k, stride, pad, accumulate)));
   return check_launch("maxpool_bwd");
+}
+
+int pmoe_maxpool_bwd_idx(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* dx, int32_t dtype, int32_t k,
+                         int32_t stride, int32_t pad, int32_t accumulate, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc;
+  if ((rc = chk(dy, dtype, "maxpool_bwd_idx dy"))) return rc;
+  if ((rc = chk(dx, dtype, "maxpool_bwd_idx dx"))) return rc;
+  if (!idx || ((uintptr_t)idx & 7) || dy->n != dx->n || dy->c != dx->c || k < 1 || stride < 1) {
+    set_error("maxpool_bwd_idx: bad arguments");
+    return PMOE_ERR_ARG;
+  }
+  const long long items = (long long)dx->n * dx->h * dx->w * (dx->c / 8);
+  BW_DISPATCH(dtype, (maxpool_bwd_idx_kernel<T><<<bgrid(items, 256), 256, 0, stream>>>(bv4(dy), idx, bv4(dx), k, stride, pad, accumulate)));
+  return check_launch("maxpool_bwd_idx");
 }
 
 int pmoe_prod_channel_sums(const PmoeView4* a, const PmoeView4* b, int32_t dtype, float* out, int64_t out_stride,

@@ -64,12 +64,18 @@ def to_nchw(t, c, out=None):
     return out
 
 
-def maxpool(x, k, stride, pad, scale=None, shift=None, relu=False):
+def maxpool(x, k, stride, pad, scale=None, shift=None, relu=False, want_idx=False):
+    """MaxPool2d on an NHWC Act. want_idx: also return the uint8 argmax codes (N,OH,OW,Cpad) for the backward."""
     n, h, w, cp = x.t.shape
     oh = (h + 2 * pad - k) // stride + 1
     ow = (w + 2 * pad - k) // stride + 1
     out = torch.empty(n, oh, ow, cp, dtype=x.t.dtype, device=x.t.device)
     vs, vd = view4(x.t), view4(out)
+    if want_idx:
+        idx = torch.empty(n, oh, ow, cp, dtype=torch.uint8, device=x.t.device)
+        check(profiler.launch("maxpool", lambda: lib().pmoe_maxpool_idx(C.byref(vs), C.byref(vd), dtype_code(out), k, stride, pad,
+                                                                        idx.data_ptr(), stream_ptr())), "maxpool_idx")
+        return Act(out, x.c), idx
     check(profiler.launch("maxpool", lambda: lib().pmoe_maxpool(C.byref(vs), C.byref(vd), dtype_code(out), k, stride, pad, _lib.ptr(scale), _lib.ptr(shift),
                              int(relu), stream_ptr())), "maxpool")
     return Act(out, x.c)

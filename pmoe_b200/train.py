@@ -392,17 +392,21 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
 
 
 def maxpool_op(tape, x, k, stride, pad):
-    y = nhwc.maxpool(x, k, stride, pad)
+    need_bwd = tape.save and _rg(x)
+    if need_bwd:
+        y, idx = nhwc.maxpool(x, k, stride, pad, want_idx=True)
+    else:
+        y = nhwc.maxpool(x, k, stride, pad)
     ya = _new_act(tape, y.t, x.c, _rg(x))
-    if tape.save and _rg(x):
+    if need_bwd:
         def backward():
             dy = tape.grad_of(ya)
             if dy is None:
                 return
             g, existed = _grad_buffer(tape, x)
-            vx, vdy, vdx = view4(x.t), view4(dy), view4(g)
-            check(profiler.launch("maxpool_bwd", lambda: lib().pmoe_maxpool_bwd(
-                C.byref(vx), C.byref(vdy), C.byref(vdx), dtype_code(g), k, stride, pad, int(existed), stream_ptr())), "maxpool_bwd")
+            vdy, vdx = view4(dy), view4(g)
+            check(profiler.launch("maxpool_bwd", lambda: lib().pmoe_maxpool_bwd_idx(
+                C.byref(vdy), idx.data_ptr(), C.byref(vdx), dtype_code(g), k, stride, pad, int(existed), stream_ptr())), "maxpool_bwd")
         tape.record(backward)
     return ya
 

@@ -67,10 +67,30 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
+def build_punet(seed=0):
+    """PredictiveUnet with seeded random-init weights (PyTorch default inits; there are no checkpoints offline). The
+    constructor loads its frozen U-Net from a checkpoint file exactly like the reference (punet.py:40-50), so a
+    seeded stage-0 checkpoint is synthesised first."""
+    import tempfile
+    from pmoe_b200.model.blocks.unet import UNet
+    from pmoe_b200.model.punet import PredictiveUnet
+    torch.manual_seed(seed)
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "unet.pth")
+        torch.save({"unet": UNet(3, 23).state_dict()}, ck)
+        net = PredictiveUnet(**dict(PUNET_CFG, model_path=ck))
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():  # non-trivial BatchNorm running statistics, as after training
+        for name, buf in net.named_buffers():
+            if name.endswith("running_mean"):
+                buf.copy_(torch.randn(buf.shape, generator=g) * 0.1)
+            elif name.endswith("running_var"):
+                buf.copy_(torch.rand(buf.shape, generator=g) * 0.5 + 0.75)
+    return net
+
+
 def build_punet_state(seed=0):
-    from oracle import functional as O  # weights only: a seeded, reference-shaped state_dict (random init, no checkpoints offline)
-    pc = dict(PUNET_CFG)
-    return O.seeded_state_dict(O.make_spec(O.punet_spec, pc), seed)
+    return {k: v.clone() for k, v in build_punet(seed).state_dict().items()}
 
 
 def synth_images(B, seed=1234):
@@ -128,22 +148,14 @@ def cpu_baseline_sample(batch=2, iters=1):
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
 def run_cuda(args, rank, world, local_rank):
-    import tempfile
     from pmoe_b200 import _lib, ops, profiler
-    from pmoe_b200.model.punet import PredictiveUnet
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.check(_lib.lib().pmoe_device_check(), "device_check")
     peaks = load_peaks()
     B = args.batch
-    sd = build_punet_state()
-    with tempfile.TemporaryDirectory() as td:
-        ck = os.path.join(td, "unet.pth")
-        torch.save({"unet": {k[5:]: v for k, v in sd.items() if k.startswith("unet.")}}, ck)
-        net = PredictiveUnet(**dict(PUNET_CFG, model_path=ck))
-    net.load_state_dict(sd, strict=True)
-    net = net.to(dev).eval()
+    net = build_punet().to(dev).eval()
 
     host_in = synth_images(B, seed=1234 + rank).pin_memory()
     x = host_in.to(dev, non_blocking=True)
@@ -196,6 +208,10 @@ def run_cuda(args, rank, world, local_rank):
         prof = profiler.summary()
         profiler.enable_events(False)
 
+    h2d_bytes, d2h_bytes = host_in.numel() * 4, host_out.numel() * 4
+    del net, x, y, host_out
+    torch.cuda.empty_cache()
+    train = None if args.no_train else run_train_leg(args, rank, world, dev)
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -213,10 +229,9 @@ def run_cuda(args, rank, world, local_rank):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "punet_infer (BASELINE configs[1]): PredictiveUnet 4->6 frames, 3x224x224, eval, random-init weights",
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": "replicas x%d" % world,
-                   "l2": "inputs (%.0f MB) and activations exceed the 126 MB L2 every step" % (host_in.numel() * 4 / 1e6),
+                   "l2": "inputs (%.0f MB) and activations exceed the 126 MB L2 every step" % (h2d_bytes / 1e6),
                    "whole_step_tflops": PUNET_GF_PER_SAMPLE * B / ms_step / 1e3},
-        "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": host_in.numel() * 4,
-                "d2h_bytes_per_step": host_out.numel() * 4},
+        "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "achieved": achieved,
@@ -226,9 +241,92 @@ def run_cuda(args, rank, world, local_rank):
                      "share_of_step": conv["ms"] / ms_step if ms_step > 0 else None,
                      "other_kernels_ms": {k: v["ms"] for k, v in prof.items() if k != "conv_tc"}},
     }
+    if train is not None:
+        line["train"] = train
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(args.cpu_batch, 1)
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ training leg
+MOE_FWD_GF = 17.963      # forward GFLOP per sample per expert (ResNet18-ECA @224^2 + heads)
+MOE_STEM_DGRAD_GF = 0.694  # the first conv needs no data gradient
+
+
+def run_train_leg(args, rank, world, dev):
+    """BASELINE configs[2]/3a: full mixture (K experts, each ResNet18-ECA encoder + gating + action/speed heads)
+    training step at a GLOBAL batch of --train-batch, batch-sharded over the ranks (strong scaling): forward, moe_loss,
+    backward with the bucketed gradient all-reduce overlapped, grad-norm clip folded into the fused Adam(amsgrad)
+    step. A rank whose shard exceeds --train-micro samples accumulates micro-batches (BatchNorm statistics are then
+    per micro-batch, exactly what the same shard split over more ranks computes)."""
+    from pmoe_b200 import conf, dp, loss as L, optim, profiler
+    from pmoe_b200.model.moe import get_model
+    K, Bg = args.train_experts, args.train_batch
+    if Bg % world:
+        return {"skipped": "global batch %d not divisible by %d ranks" % (Bg, world)}
+    per = Bg // world
+    micro = min(per, args.train_micro)
+    if per % micro:
+        return {"skipped": "per-rank batch %d not a multiple of the micro-batch %d" % (per, micro)}
+    torch.manual_seed(0)
+    cfg = conf.stage2_model_cfg("moe", K)
+    model = get_model(cfg).to(dev).train()
+    wrapped = dp.DataParallel(model) if world > 1 else model
+    opt = optim.FusedAdam([p for p in model.parameters() if p.requires_grad], lr=2e-4, betas=(0.9, 0.999), eps=1e-8, amsgrad=True)
+    g = torch.Generator().manual_seed(4321 + rank)
+    host = {"images": torch.rand(per, 4, 3, 224, 224, generator=g).pin_memory(),
+            "speed": (torch.rand(per, 1, generator=g) * 1.2).pin_memory(),
+            "command": torch.nn.functional.one_hot(torch.randint(0, 6, (per,), generator=g), 6).float().pin_memory(),
+            "control": (torch.rand(per, 2, generator=g) * 2 - 1).pin_memory(),
+            "target": torch.rand(per, 1, generator=g).pin_memory()}
+    n_micro = per // micro
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        total = None
+        for m in range(n_micro):
+            sl = slice(m * micro, (m + 1) * micro)
+            d = {k: v[sl].to(dev, non_blocking=True) for k, v in host.items()}  # H2D of this micro-batch: inside the timed region
+            dist_, sp = wrapped(d["images"], d["speed"], d["command"])
+            loss = L.moe_loss(dist_, sp, d["control"], d["target"], cfg.loss_coefs) / n_micro
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        opt.step(max_grad_norm=1.0)
+        return total
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        loss = step()
+    barrier()
+    profiler.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(1, min(args.steps, 3))
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    lv = float(loss.item())  # D2H read of the step's loss
+    e1.record()
+    barrier()
+    launches = profiler.launch_count()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+    ms_step = ms.item() / steps
+    gf = K * (3 * MOE_FWD_GF - MOE_STEM_DGRAD_GF)  # fwd + dgrad + wgrad per sample
+    out = {"metric": "train_samples_per_sec", "value": Bg / (ms_step / 1e3), "unit": "samples/s", "ms_per_step": ms_step,
+           "scaling": "strong", "workload": "moe K=%d ResNet18-ECA experts, fwd+moe_loss+bwd+allreduce+clip+Adam(amsgrad), bf16" % K,
+           "global_batch": Bg, "batch_per_gpu": per, "micro_batch": micro, "steps": steps, "loss": lv,
+           "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()), "gpu_launches": launches,
+           "tflops_per_gpu": gf * per / ms_step / 1e3, "params": sum(p.numel() for p in model.parameters())}
+    if world > 1 and getattr(wrapped, "last_stats", None):
+        out["allreduce"] = wrapped.last_stats
+    del model, wrapped, opt
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -240,6 +338,10 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=2, help="bounded CPU sample size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2])")
+    ap.add_argument("--train-batch", type=int, default=512, help="GLOBAL training batch, sharded over the ranks")
+    ap.add_argument("--train-experts", type=int, default=6)
+    ap.add_argument("--train-micro", type=int, default=128, help="largest micro-batch one rank runs at once")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

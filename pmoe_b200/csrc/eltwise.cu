@@ -318,27 +318,38 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
 }
 
 // y = act(scale[c]*x + shift[c] (+ residual))
-template <typename T>
-__global__ void affine_act_kernel(V4 src, V4 dst, const float* __restrict__ scale, const float* __restrict__ shift,
+template <typename T, bool FLAT>
+__global__ void __launch_bounds__(256) affine_act_kernel(V4 src, V4 dst, const float* __restrict__ scale, const float* __restrict__ shift,
                                   V4 res, int act) {
   const int cg = dst.c / 8;
   const long long total = (long long)dst.n * dst.h * dst.w * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    long long pix = i / cg;
-    const int w = (int)(pix % dst.w);
-    pix /= dst.w;
-    const int h = (int)(pix % dst.h);
-    const int n = (int)(pix / dst.h);
-    float v[8], sc[8], sf[8];
-    load8(static_cast<const T*>(src.ptr) + n * src.sn + h * src.sh + w * src.sw + g * 8, v);
-    load8(scale + g * 8, sc);
-    load8(shift + g * 8, sf);
+  const long long stride = (long long)gridDim.x * blockDim.x;  // a multiple of cg: one channel group per thread
+  const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int g = (int)(first % cg);
+  float sc[8], sf[8];
+  load8(scale + g * 8, sc);
+  load8(shift + g * 8, sf);
+  for (long long i = first; i < total; i += stride) {
+    long long o_s, o_d, o_r;
+    if (FLAT) {
+      o_s = o_d = o_r = i * 8;
+    } else {
+      long long pix = i / cg;
+      const int w = (int)(pix % dst.w);
+      pix /= dst.w;
+      const int h = (int)(pix % dst.h);
+      const int n = (int)(pix / dst.h);
+      o_s = n * src.sn + h * src.sh + w * src.sw + g * 8;
+      o_d = n * dst.sn + h * dst.sh + w * dst.sw + g * 8;
+      o_r = n * res.sn + h * res.sh + w * res.sw + g * 8;
+    }
+    float v[8];
+    load8(static_cast<const T*>(src.ptr) + o_s, v);
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = fmaf(v[q], sc[q], sf[q]);
     if (res.ptr) {
       float r[8];
-      load8(static_cast<const T*>(res.ptr) + n * res.sn + h * res.sh + w * res.sw + g * 8, r);
+      load8(static_cast<const T*>(res.ptr) + o_r, r);
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] += r[q];
     }
@@ -346,7 +357,7 @@ __global__ void affine_act_kernel(V4 src, V4 dst, const float* __restrict__ scal
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
     }
-    store8(static_cast<T*>(dst.ptr) + n * dst.sn + h * dst.sh + w * dst.sw + g * 8, v);
+    store8(static_cast<T*>(dst.ptr) + o_d, v);
   }
 }
 
@@ -513,7 +524,18 @@ int pmoe_affine_act(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, c
     res = to_v4(*residual);
   }
   const long long items = (long long)dst->n * dst->h * dst->w * (dst->c / 8);
-  DISPATCH_DTYPE(dtype, (affine_act_kernel<T><<<grid_for(items, 256), 256, 0, stream>>>(to_v4(*src), to_v4(*dst), scale, shift, res, act)));
+  const int cg = dst->c / 8;
+  int grid = grid_for(items, 256);
+  if (256 % cg != 0) grid = (grid + cg - 1) / cg * cg;
+  auto dense = [&](const PmoeView4* v) {
+    return !v || !v->ptr || (v->n == dst->n && v->h == dst->h && v->w == dst->w && v->c == dst->c && v->sw == v->c &&
+                             v->sh == (int64_t)v->w * v->c && v->sn == (int64_t)v->h * v->w * v->c);
+  };
+  if (dense(src) && dense(dst) && dense(residual)) {
+    DISPATCH_DTYPE(dtype, (affine_act_kernel<T, true><<<grid, 256, 0, stream>>>(to_v4(*src), to_v4(*dst), scale, shift, res, act)));
+  } else {
+    DISPATCH_DTYPE(dtype, (affine_act_kernel<T, false><<<grid, 256, 0, stream>>>(to_v4(*src), to_v4(*dst), scale, shift, res, act)));
+  }
   return check_launch("affine_act");
 }
 

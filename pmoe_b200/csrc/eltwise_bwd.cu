@@ -5,6 +5,8 @@
 #include "ptx.cuh"
 #include "reduce.cuh"
 
+#include <initializer_list>
+
 namespace pmoe {
 
 __device__ __forceinline__ void bload8(const float* p, float (&v)[8]) {
@@ -74,7 +76,7 @@ static inline int bgrid(long long items, int threads) {
 // ---------------------------------------------------------------- pass 1: per-channel sums of dy and dy*xhat
 // dy = dz * act'(z). Block = cg channel groups x (256/cg) pixel lanes; each block walks a slab of pixels and
 // finishes with one atomicAdd per channel.
-template <typename T>
+template <typename T, bool FLAT>
 __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, double* __restrict__ sum_dy,
                                      double* __restrict__ sum_dy_xhat, long long pix_per_block) {
@@ -95,21 +97,29 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(BV4 dz, BV4 
       r[q] = rstd ? __ldg(rstd + g * 8 + q) : 1.f;
     }
     for (long long p = p0 + lane; p < p1; p += lanes) {
-      const int w = (int)(p % dz.w);
-      const long long t = p / dz.w;
-      const int h = (int)(t % dz.h), n = (int)(t / dz.h);
+      long long o_dz, o_z, o_x;
+      if (FLAT) {
+        o_dz = o_z = o_x = (p * cg + g) * 8;
+      } else {
+        const int w = (int)(p % dz.w);
+        const long long t = p / dz.w;
+        const int h = (int)(t % dz.h), n = (int)(t / dz.h);
+        o_dz = n * dz.sn + h * dz.sh + w * dz.sw + g * 8;
+        o_z = n * z.sn + h * z.sh + w * z.sw + g * 8;
+        o_x = n * x.sn + h * x.sh + w * x.sw + g * 8;
+      }
       float d[8], xv[8];
-      bload8(at<T>(dz, n, h, w, g * 8), d);
+      bload8(static_cast<const T*>(dz.ptr) + o_dz, d);
       if (act != PMOE_ACT_NONE) {
         float zv[8];
-        bload8(at<T>(z, n, h, w, g * 8), zv);
+        bload8(static_cast<const T*>(z.ptr) + o_z, zv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) d[q] *= act_grad(zv[q], act);
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) a[q] += d[q];
       if (x.ptr) {
-        bload8(at<T>(x, n, h, w, g * 8), xv);
+        bload8(static_cast<const T*>(x.ptr) + o_x, xv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) b[q] += d[q] * (xv[q] - m[q]) * r[q];
       }
@@ -131,58 +141,86 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(BV4 dz, BV4 
 // ---------------------------------------------------------------- pass 2: dx (and the masked dy for a residual branch)
 // batch-stat BN : dx = gamma*rstd * (dy - sum_dy/N - xhat*sum_dy_xhat/N)
 // eval BN / bias: dx = dy * scale (scale may be NULL = 1)
-template <typename T>
-__global__ void bn_bwd_apply_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* __restrict__ mean,
+// FLAT: every view is a dense (n,h,w,c) tensor of the same shape -> item i lives at element offset 8*i in all of
+// them (no index arithmetic). The grid stride is a multiple of the channel-group count, so a thread keeps ONE channel
+// group for its whole loop and the per-channel constants are loaded once.
+template <typename T, bool FLAT>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* __restrict__ mean,
                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
                                     const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat, float inv_n,
                                     int batch_stats, BV4 dx, BV4 dres, int accumulate_dres) {
   const int cg = dz.c / 8;
   const long long total = (long long)dz.n * dz.h * dz.w * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    long long pix = i / cg;
-    const int w = (int)(pix % dz.w);
-    pix /= dz.w;
-    const int h = (int)(pix % dz.h);
-    const int n = (int)(pix / dz.h);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int g = (int)(first % cg);
+  float ka[8], km[8], kr[8], c1[8], c2[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = g * 8 + q;
+    const float gm = gamma ? __ldg(gamma + c) : 1.f;
+    if (batch_stats) {
+      kr[q] = __ldg(rstd + c);
+      km[q] = __ldg(mean + c);
+      ka[q] = gm * kr[q];
+      c1[q] = (float)(sum_dy[c] * (double)inv_n);
+      c2[q] = (float)(sum_dy_xhat[c] * (double)inv_n);
+    } else {
+      ka[q] = gm;
+      kr[q] = km[q] = c1[q] = c2[q] = 0.f;
+    }
+  }
+  for (long long i = first; i < total; i += stride) {
+    long long o_dz, o_z, o_x, o_dx, o_dr;
+    if (FLAT) {
+      o_dz = o_z = o_x = o_dx = o_dr = i * 8;
+    } else {
+      long long pix = i / cg;
+      const int w = (int)(pix % dz.w);
+      pix /= dz.w;
+      const int h = (int)(pix % dz.h);
+      const int n = (int)(pix / dz.h);
+      o_dz = n * dz.sn + h * dz.sh + w * dz.sw + g * 8;
+      o_z = n * z.sn + h * z.sh + w * z.sw + g * 8;
+      o_x = n * x.sn + h * x.sh + w * x.sw + g * 8;
+      o_dx = n * dx.sn + h * dx.sh + w * dx.sw + g * 8;
+      o_dr = n * dres.sn + h * dres.sh + w * dres.sw + g * 8;
+    }
     float d[8];
-    bload8(at<T>(dz, n, h, w, g * 8), d);
+    bload8(static_cast<const T*>(dz.ptr) + o_dz, d);
     if (act != PMOE_ACT_NONE) {
       float zv[8];
-      bload8(at<T>(z, n, h, w, g * 8), zv);
+      bload8(static_cast<const T*>(z.ptr) + o_z, zv);
 #pragma unroll
       for (int q = 0; q < 8; ++q) d[q] *= act_grad(zv[q], act);
     }
     if (dres.ptr) {
       float o[8];
       if (accumulate_dres) {
-        bload8(at<T>(dres, n, h, w, g * 8), o);
+        bload8(static_cast<const T*>(dres.ptr) + o_dr, o);
 #pragma unroll
         for (int q = 0; q < 8; ++q) o[q] += d[q];
       } else {
 #pragma unroll
         for (int q = 0; q < 8; ++q) o[q] = d[q];
       }
-      bstore8(at_mut<T>(dres, n, h, w, g * 8), o);
+      bstore8(static_cast<T*>(dres.ptr) + o_dr, o);
     }
     if (dx.ptr) {
       float o[8];
       if (batch_stats) {
         float xv[8];
-        bload8(at<T>(x, n, h, w, g * 8), xv);
+        bload8(static_cast<const T*>(x.ptr) + o_x, xv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int c = g * 8 + q;
-          const float r = __ldg(rstd + c);
-          const float xh = (xv[q] - __ldg(mean + c)) * r;
-          const float gm = gamma ? __ldg(gamma + c) : 1.f;
-          o[q] = gm * r * (d[q] - (float)(sum_dy[c] * (double)inv_n) - xh * (float)(sum_dy_xhat[c] * (double)inv_n));
+          const float xh = (xv[q] - km[q]) * kr[q];
+          o[q] = ka[q] * (d[q] - c1[q] - xh * c2[q]);
         }
       } else {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) o[q] = d[q] * (gamma ? __ldg(gamma + g * 8 + q) : 1.f);
+        for (int q = 0; q < 8; ++q) o[q] = d[q] * ka[q];
       }
-      bstore8(at_mut<T>(dx, n, h, w, g * 8), o);
+      bstore8(static_cast<T*>(dx.ptr) + o_dx, o);
     }
   }
 }
@@ -422,6 +460,26 @@ __global__ void axpy_kernel(BV4 src, BV4 dst, float alpha, const float* __restri
   }
 }
 
+// all non-null views dense (n,h,w,c) tensors of the reference view's shape?
+static bool all_flat(const PmoeView4* ref, std::initializer_list<const PmoeView4*> vs) {
+  for (const PmoeView4* v : vs) {
+    if (!v || !v->ptr) continue;
+    if (v->n != ref->n || v->h != ref->h || v->w != ref->w || v->c != ref->c || v->sw != v->c || v->sh != (int64_t)v->w * v->c ||
+        v->sn != (int64_t)v->h * v->w * v->c)
+      return false;
+  }
+  return true;
+}
+
+// grid whose total thread count is a multiple of the channel-group count (threads keep one channel group)
+static int grid_cg(long long items, int cg) {
+  int blocks = bgrid(items, 256);
+  if (256 % cg != 0) {  // odd group counts (e.g. 48 channels): make blocks * 256 a multiple of cg
+    blocks = (blocks + cg - 1) / cg * cg;
+  }
+  return blocks;
+}
+
 static int chk(const PmoeView4* v, int dtype, const char* what, bool optional = false) {
   if (optional && (!v || !v->ptr)) return PMOE_OK;
   const int esz = dtype == PMOE_BF16 ? 2 : 4;
@@ -467,7 +525,11 @@ int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4*
   long long ppb = (npix + blocks - 1) / blocks;
   if (ppb < 64) ppb = 64;
   blocks = (npix + ppb - 1) / ppb;
-  BW_DISPATCH(dtype, (bn_bwd_reduce_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, sum_dy, sum_dy_xhat, ppb)));
+  if (all_flat(dz, {dz, z, x})) {
+    BW_DISPATCH(dtype, (bn_bwd_reduce_kernel<T, true><<<(unsigned)blocks, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, sum_dy, sum_dy_xhat, ppb)));
+  } else {
+    BW_DISPATCH(dtype, (bn_bwd_reduce_kernel<T, false><<<(unsigned)blocks, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, sum_dy, sum_dy_xhat, ppb)));
+  }
   return check_launch("bn_bwd_reduce");
 }
 
@@ -487,7 +549,12 @@ int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* 
     return PMOE_ERR_ARG;
   }
   const long long items = (long long)dz->n * dz->h * dz->w * (dz->c / 8);
-  BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T><<<bgrid(items, 256), 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres)));
+  const int grid = grid_cg(items, dz->c / 8);
+  if (all_flat(dz, {dz, z, x, dx, dres})) {
+    BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T, true><<<grid, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres)));
+  } else {
+    BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T, false><<<grid, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres)));
+  }
   return check_launch("bn_bwd_apply");
 }
 

@@ -140,6 +140,7 @@ class DataParallel(torch.nn.Module):
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self.last_stats = None
         self._reduced = set()
+        self._bucketers = {}
         if dist.is_initialized() and dist.get_world_size(process_group) > 1:
             if broadcast:
                 with torch.no_grad():
@@ -158,7 +159,12 @@ class DataParallel(torch.nn.Module):
         p.grad.div_(world)
 
     def make_bucketer(self, params):
-        return GradBucketer(params, self.group, self.bucket_bytes)
+        key = tuple(id(p) for p in params if p.requires_grad)
+        b = self._bucketers.get(key)
+        if b is None:
+            b = self._bucketers[key] = GradBucketer(params, self.group, self.bucket_bytes)
+        b.reset()
+        return b
 
     def note_reduced(self, params, stats):
         self._reduced.update(id(p) for p in params)

@@ -12,7 +12,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib, config, nhwc, ops, profiler
+from . import _lib, config, dp, nhwc, ops, profiler
 from ._lib import ACT, check, lib, stream_ptr, view4
 from .nhwc import Act, dtype_code
 from .ops import TAPS3, pad_ch
@@ -28,6 +28,17 @@ class Tape:
         self.pgrads = {}            # id(param) -> fp32 gradient in the parameter's own layout
         self.params = {}            # id(param) -> param
         self.alive = []             # keeps Acts (and therefore their ids) alive until backward
+        self.pending = {}           # id(param) -> gradient contributions still to come (data-parallel overlap)
+        self.reported = set()
+        self.bucketer = None        # pmoe_b200.dp.GradBucketer during a data-parallel backward
+
+    def expect(self, *params):
+        """Forward-time announcement that a recorded backward closure will add_pgrad() to these parameters."""
+        if not self.save:
+            return
+        for p in params:
+            if p is not None and p.requires_grad:
+                self.pending[id(p)] = self.pending.get(id(p), 0) + 1
 
     def record(self, fn):
         if self.save:
@@ -51,6 +62,12 @@ class Tape:
             self.pgrads[k] = self.pgrads[k] + g
         else:
             self.pgrads[k] = g
+        left = self.pending.get(k, 0) - 1
+        self.pending[k] = left
+        if left == 0 and self.bucketer is not None:
+            # last contribution: hand the gradient to its all-reduce bucket while the tape keeps running
+            self.reported.add(k)
+            self.bucketer.ready(p, self.pgrads[k])
 
     def backward(self):
         for fn in reversed(self.ops):
@@ -58,6 +75,11 @@ class Tape:
         self.ops = []
         self.alive = []
         self.grads = {}
+        if self.bucketer is not None:  # gradients whose announced contributions did not all arrive
+            for k, g in self.pgrads.items():
+                if k not in self.reported:
+                    self.reported.add(k)
+                    self.bucketer.ready(self.params[k], g)
 
 
 def _new_act(tape, t, c, rg):
@@ -387,6 +409,11 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
             ops.conv([dy], wd, dsegs, ck_d, gv, residual=gv if pre[k] else None,
                      flops=2.0 * n * h * w * cout * src.nlog * len(segs_i), tag="dgrad " + tag)
 
+    if bn_train:
+        tape.expect(bn.weight, bn.bias)
+    else:
+        tape.expect(bias)
+    tape.expect(_owner(weight))
     tape.record(backward)
     return z, pool
 
@@ -461,6 +488,7 @@ def conv_transpose_op(tape, up, x, tag=""):
                 wd = torch.nn.functional.pad(wd, (0, 0, 0, rows - cin)).to(dt).contiguous()
                 g, existed = _grad_buffer(tape, x)
                 ops.conv(views, wd, dsegs, ck_d, g, residual=g if existed else None, flops=4 * flops, tag="dgrad convT " + tag)
+        tape.expect(bias, weight)
         tape.record(backward)
     return ya
 
@@ -498,6 +526,7 @@ def eca_op(tape, eca_mod, x, layout=None, pool_in=None):
                 check(profiler.launch("eca_bwd_apply", lambda: lib().pmoe_eca_bwd_apply(
                     C.byref(vd), dtype_code(dy), gate.data_ptr(), gate.stride(0), dmean.data_ptr(), dmean.stride(0), C.byref(vg),
                     int(existed), stream_ptr())), "eca_bwd_apply")
+        tape.expect(w)
         tape.record(backward)
     return ya
 
@@ -600,6 +629,8 @@ def bn_act_op(tape, bn, x, act="relu", tag=""):
                 _bn_bwd_apply(dz, zs, None, act, None, None, scale, None, None, 0.0, 0, tmp, None, False)
             if existed:
                 _axpy(tmp, g, 1.0, None, True)
+        if bn_train:
+            tape.expect(bn.weight, bn.bias)
         tape.record(backward)
     return z
 
@@ -844,15 +875,23 @@ class TapeFunction(torch.autograd.Function):
         tape = Tape(config.act_dtype(), save=any(p.requires_grad for p in params))
         outs, seed = runner(tape)
         ctx.tape, ctx.seed, ctx.plist = tape, seed, params
+        ctx.dp = dp.current()  # a pmoe_b200.dp.DataParallel wrapper when the model runs under one
         ctx.mark_non_differentiable(*[o for o in outs if not o.is_floating_point()])
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *gouts):
         tape = ctx.tape
+        if ctx.dp is not None:
+            tape.bucketer = ctx.dp.make_bucketer(ctx.plist)
         ctx.seed(tape, gouts)
         tape.backward()
-        grads = tuple(tape.pgrads.get(id(p)) if p.requires_grad else None for p in ctx.plist)
+        if tape.bucketer is not None:
+            reduced, stats = tape.bucketer.finish()
+            ctx.dp.note_reduced([p for p in ctx.plist if p.requires_grad], stats)
+            grads = tuple(reduced.get(id(p)) if p.requires_grad else None for p in ctx.plist)
+        else:
+            grads = tuple(tape.pgrads.get(id(p)) if p.requires_grad else None for p in ctx.plist)
         ctx.tape = None
         return (None,) + grads
 

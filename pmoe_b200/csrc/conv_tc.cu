@@ -29,7 +29,9 @@ struct TcSeg {
 struct alignas(64) ConvTcParams {
   CUtensorMap tm_src[PMOE_MAX_SRC];
   CUtensorMap tm_w;
-  CUtensorMap tm_out;
+  CUtensorMap tm_out[4];  // [0] = out; [1..3] = the extra output views of a multi-view launch (ConvTranspose2d k2s2)
+  int out_cols;           // GEMM columns per output view (0 = single view)
+  int tiles_n_varies;     // the N tile changes between a CTA's tiles (streaming kernel)
   TcSeg seg[PMOE_MAX_SEG];
   int n_seg, kiters;
   int tiles_w, tiles_h, tiles_n, n_img;
@@ -47,7 +49,7 @@ struct alignas(64) ConvTcParams {
   int cout_pad;
   int pool_stride;
   // resident-weight ("halo") variant
-  int halo_stages, w_slots, n_chunks;
+  int halo_stages, w_slots, n_chunks, w_bytes;
   long long m_tiles;
   int out_bufs;  // staging buffers for the TMA store (2, or 1 when shared memory is tight)
 };
@@ -75,6 +77,12 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = 1024 /*align slack*/ + PIPE_BYTES + 2 * OUT_BYTES + AUX_FLOATS * 4 +
                                     (2 * STAGES + 4) * 8 + 16;
 };
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   switch (act) {
@@ -155,6 +163,8 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
     constexpr int ROWB = OCW * 2;
     constexpr uint32_t SWMASK = ROWB == 128 ? 7u : (ROWB == 64 ? 3u : 1u);
     const int act = p.act;
+    const bool has_scale = p.scale != nullptr, has_shift = p.shift != nullptr;
+    const uint32_t sc_addr = smem_u32(s_scale), sh_addr = smem_u32(s_shift);
     uint32_t nstore = 0;
     int img, h0, w0, nt;
     for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
@@ -163,9 +173,11 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
       const uint32_t acc = titer & 1u;
       const uint32_t acc_phase = (titer >> 1) & 1u;
 
-      for (int i = e; i < BN; i += kEpiThreads) {
-        s_scale[i] = p.scale ? __ldg(p.scale + n0 + i) : 1.f;
-        s_shift[i] = p.shift ? __ldg(p.shift + n0 + i) : 0.f;
+      if (titer == 0 || p.tiles_n_varies) {  // resident kernels keep one N tile: load the per-channel affine once
+        for (int i = e; i < BN; i += kEpiThreads) {
+          if (has_scale) s_scale[i] = __ldg(p.scale + n0 + i);
+          if (has_shift) s_shift[i] = __ldg(p.shift + n0 + i);
+        }
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -192,13 +204,28 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
           tmem_ld_wait();
           float y[SUB];
 #pragma unroll
-          for (int q = 0; q < SUB / 4; ++q) {  // per-channel affine, 128-bit broadcast reads of scale/shift
-            const float4 sc4 = *reinterpret_cast<const float4*>(s_scale + cb + 4 * q);
-            const float4 sh4 = *reinterpret_cast<const float4*>(s_shift + cb + 4 * q);
-            y[4 * q + 0] = fmaf(__uint_as_float(raw[4 * q + 0]), sc4.x, sh4.x);
-            y[4 * q + 1] = fmaf(__uint_as_float(raw[4 * q + 1]), sc4.y, sh4.y);
-            y[4 * q + 2] = fmaf(__uint_as_float(raw[4 * q + 2]), sc4.z, sh4.z);
-            y[4 * q + 3] = fmaf(__uint_as_float(raw[4 * q + 3]), sc4.w, sh4.w);
+          for (int k = 0; k < SUB; ++k) y[k] = __uint_as_float(raw[k]);
+          // per-channel affine: 128-bit broadcast LDS of scale / shift, each only when present (eval-mode BN is
+          // folded into the packed weights by the host, so inference needs the shift alone)
+          if (has_scale) {
+#pragma unroll
+            for (int q = 0; q < SUB / 4; ++q) {
+              const float4 sc4 = lds128(sc_addr + (uint32_t)(cb + 4 * q) * 4u);
+              y[4 * q + 0] *= sc4.x;
+              y[4 * q + 1] *= sc4.y;
+              y[4 * q + 2] *= sc4.z;
+              y[4 * q + 3] *= sc4.w;
+            }
+          }
+          if (has_shift) {
+#pragma unroll
+            for (int q = 0; q < SUB / 4; ++q) {
+              const float4 sh4 = lds128(sh_addr + (uint32_t)(cb + 4 * q) * 4u);
+              y[4 * q + 0] += sh4.x;
+              y[4 * q + 1] += sh4.y;
+              y[4 * q + 2] += sh4.z;
+              y[4 * q + 3] += sh4.w;
+            }
           }
           if (p.stat_sum != nullptr) {
             float a[SUB], b[SUB];
@@ -261,7 +288,9 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
         fence_proxy_async_smem();
         named_bar_sync(2, kEpiThreads);
         if (issuer) {
-          tma_store_4d(&p.tm_out, obuf, n0 + ch * OCW, w0, h0, img);
+          const int col = n0 + ch * OCW;
+          if (p.out_cols > 0) tma_store_4d(&p.tm_out[col / p.out_cols], obuf, col % p.out_cols, w0, h0, img);
+          else tma_store_4d(&p.tm_out[0], obuf, col, w0, h0, img);
           tma_store_commit();
         }
         ++nstore;
@@ -323,7 +352,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     }
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_w);
-    tma_prefetch_desc(&p.tm_out);
+    tma_prefetch_desc(&p.tm_out[0]);
     tma_prefetch_desc(&p.tm_src[0]);
   }
   if (warp == 2) {
@@ -336,6 +365,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  if (tmem_base != 0u) {  // one CTA per SM and one allocation per CTA: the MMA issuer relies on base 0
+    if (threadIdx.x == 0) printf("pmoe conv_tc: unexpected TMEM base %u\n", tmem_base);
+    __trap();
+  }
+  const uint32_t pipe_addr = smem_u32(pipe);
 
   const long long G = gridDim.x;
   const long long t_begin = (p.total_tiles * (long long)blockIdx.x) / G;
@@ -376,6 +410,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      constexpr uint32_t desc_hi = umma_desc_hi(C::SBO, C::LAYOUT);
       int stage = 0;
       uint32_t phase = 0;
       uint32_t titer = 0;
@@ -384,18 +419,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         const uint32_t acc_phase = (titer >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = acc * BN;  // TMEM base is 0 (checked after the allocation)
         for (int it = 0; it < p.kiters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(pipe + stage * C::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + C::A_BYTES;
+          const uint32_t a_lo = umma_desc_lo(pipe_addr + (uint32_t)stage * C::STAGE_BYTES, 16u);
+          const uint32_t b_lo = a_lo + (C::A_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < CK / 16; ++k) {
-            const uint64_t adesc = umma_desc_kmajor(a_addr + k * 32, C::SBO, C::LAYOUT);
-            const uint64_t bdesc = umma_desc_kmajor(b_addr + k * 32, C::SBO, C::LAYOUT);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < CK / 16; ++k)
+            umma_bf16_split(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (it | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
           if (++stage == C::STAGES) {
             stage = 0;
@@ -427,26 +459,28 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
 // UMMA descriptor VIEWS of that halo tile (start row r*10+s, 8-row groups 10 rows apart — the swizzle is a function of
 // the absolute shared-memory address, so row-shifted views need no re-staging: profiles/r01_conv_bringup.json probe).
 // L2->SMEM traffic per tile drops from 9 x 16 KB to 23 KB per chunk, and the weights are fetched once per CTA.
-template <int BN>
+template <int BN, int CK>
 struct HaloCfg {
   static constexpr int OCW = BN < 64 ? BN : 64;
   static constexpr int SUB = OCW < 32 ? OCW : 32;
-  static constexpr int HALO_TX = 18 * 10 * 128;
-  static constexpr int HALO_BYTES = 23 * 1024;
-  static constexpr int WSLOT_BYTES = BN * 128;
+  static constexpr int ROWB = CK * 2;                                       // bytes per halo pixel row (one swizzle span)
+  static constexpr int HALO_TX = 18 * 10 * ROWB;
+  static constexpr int HALO_BYTES = ((HALO_TX + 1023) / 1024) * 1024;       // 23 KB at CK = 64
+  static constexpr int WSLOT_BYTES = BN * ROWB;
+  static constexpr uint32_t LAYOUT = CK == 64 ? kLayoutSW128 : (CK == 32 ? kLayoutSW64 : kLayoutSW32);
   static constexpr int OUT_BYTES = 128 * OCW * 2;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int AUX_FLOATS = 3 * BN + 2 * kMaxStatC;
   static constexpr int MAX_STAGES = 6;
 };
 
-template <int BN>
+template <int BN, int CK>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __grid_constant__ ConvTcParams p) {
-  using C = HaloCfg<BN>;
+  using C = HaloCfg<BN, CK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wsm = smem;
-  uint8_t* halo = wsm + (size_t)p.w_slots * C::WSLOT_BYTES;
+  uint8_t* halo = wsm + (size_t)p.w_bytes;
   uint8_t* out_stage = halo + (size_t)p.halo_stages * C::HALO_BYTES;
   float* s_scale = reinterpret_cast<float*>(out_stage + p.out_bufs * C::OUT_BYTES);
   float* s_shift = s_scale + BN;
@@ -474,7 +508,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
     mbar_init(wfull_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_w);
-    tma_prefetch_desc(&p.tm_out);
+    tma_prefetch_desc(&p.tm_out[0]);
     tma_prefetch_desc(&p.tm_src[0]);
   }
   if (warp == 2) {
@@ -487,6 +521,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  if (tmem_base != 0u) {
+    if (threadIdx.x == 0) printf("pmoe conv_tc_halo: unexpected TMEM base %u\n", tmem_base);
+    __trap();
+  }
 
   ResidentTiles it;
   it.nt_fixed = (int)(blockIdx.x % p.tiles_n);
@@ -499,7 +537,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(wfull_bar, (uint32_t)(p.w_slots * C::WSLOT_BYTES));
-      for (int j = 0; j < p.w_slots; ++j) tma_load_2d(wsm + (size_t)j * C::WSLOT_BYTES, &p.tm_w, wfull_bar, j * 64, it.nt_fixed * BN);
+      for (int j = 0; j < p.w_slots; ++j) tma_load_2d(wsm + (size_t)j * C::WSLOT_BYTES, &p.tm_w, wfull_bar, j * CK, it.nt_fixed * BN);
       int stage = 0;
       uint32_t phase = 0;
       for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
@@ -518,9 +556,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      constexpr uint32_t a_hi = umma_desc_hi(10u * C::ROWB, C::LAYOUT);  // 8-row groups of a halo view are 10 rows apart
+      constexpr uint32_t b_hi = umma_desc_hi(8u * C::ROWB, C::LAYOUT);
       mbar_wait(wfull_bar, 0);
       tc_fence_after();
-      const uint32_t w_addr = smem_u32(wsm);
+      const uint32_t w_lo = umma_desc_lo(smem_u32(wsm), 16u);
+      const uint32_t w_step = (uint32_t)p.n_chunks * (uint32_t)(C::WSLOT_BYTES >> 4);  // descriptor units between taps
+      const uint32_t halo_lo = umma_desc_lo(smem_u32(halo), 16u);
       int stage = 0;
       uint32_t phase = 0;
       for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
@@ -528,21 +570,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
         const uint32_t acc_phase = (titer >> 1) & 1u;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = acc * BN;  // TMEM base is 0 (checked after the allocation)
         for (int g = 0; g < p.n_chunks; ++g) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t h_addr = smem_u32(halo + (size_t)stage * C::HALO_BYTES);
+          const uint32_t h_lo = halo_lo + (uint32_t)stage * (uint32_t)(C::HALO_BYTES >> 4);
+          uint32_t b_lo = w_lo + (uint32_t)g * (uint32_t)(C::WSLOT_BYTES >> 4);
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
-            const uint32_t a_tap = h_addr + (uint32_t)((t / 3) * 10 + (t % 3)) * 128u;
-            const uint32_t b_tap = w_addr + (uint32_t)(t * p.n_chunks + g) * (uint32_t)C::WSLOT_BYTES;
+            const uint32_t a_lo = h_lo + (uint32_t)(((t / 3) * 10 + (t % 3)) * C::ROWB >> 4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t adesc = umma_desc_kmajor(a_tap + k * 32, 1280u, kLayoutSW128);
-              const uint64_t bdesc = umma_desc_kmajor(b_tap + k * 32, 1024u, kLayoutSW128);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, (g | t | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < CK / 16; ++k)
+              umma_bf16_split(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (g | t | k) != 0 ? 1u : 0u);
+            b_lo += w_step;
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == p.halo_stages) {
@@ -636,11 +676,11 @@ static int launch_tc_ck(const ConvTcParams& p, int ck, cudaStream_t stream) {
 }
 
 
-template <int BN>
+template <int BN, int CK>
 static int launch_halo(const ConvTcParams& p, int smem_bytes, cudaStream_t stream) {
   static int configured = 0;
   if (configured < smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN, CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
       set_error("conv_tc_halo<%d>: cannot reserve %d bytes of shared memory: %s", BN, smem_bytes, cudaGetErrorString(e));
       return PMOE_ERR_LAUNCH;
@@ -651,17 +691,26 @@ static int launch_halo(const ConvTcParams& p, int smem_bytes, cudaStream_t strea
   if (per_n > p.m_tiles) per_n = p.m_tiles;
   if (per_n < 1) per_n = 1;
   const unsigned grid = (unsigned)(per_n * p.tiles_n);
-  conv_tc_halo_kernel<BN><<<grid, kNumThreads, smem_bytes, stream>>>(p);
+  conv_tc_halo_kernel<BN, CK><<<grid, kNumThreads, smem_bytes, stream>>>(p);
   return check_launch("conv_tc_halo");
+}
+
+template <int BN>
+static int launch_halo_ck(const ConvTcParams& p, int ck, int smem_bytes, cudaStream_t stream) {
+  switch (ck) {
+    case 64: return launch_halo<BN, 64>(p, smem_bytes, stream);
+    case 32: return launch_halo<BN, 32>(p, smem_bytes, stream);
+    default: return launch_halo<BN, 16>(p, smem_bytes, stream);
+  }
 }
 
 // 3x3 / stride 1 / pad 1 over whole sources in the canonical (tap, source) segment order?
 static bool is_canonical_3x3(const PmoeConvTc* d) {
-  if (d->ck != 64 || d->n_seg != 9 * d->n_src) return false;
+  if ((d->ck != 64 && d->ck != 32 && d->ck != 16) || d->n_seg != 9 * d->n_src) return false;
   for (int t = 0; t < 9; ++t)
     for (int i = 0; i < d->n_src; ++i) {
       const PmoeSeg& s = d->seg[t * d->n_src + i];
-      if (s.src != i || s.dh != t / 3 - 1 || s.dw != t % 3 - 1 || s.c0 != 0 || s.nchunks * 64 != d->src[i].c) return false;
+      if (s.src != i || s.dh != t / 3 - 1 || s.dw != t % 3 - 1 || s.c0 != 0 || s.nchunks * d->ck != d->src[i].c) return false;
     }
   return true;
 }
@@ -700,10 +749,10 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   int halo_bn = 0, total_chunks = 0;
   static const bool halo_off = getenv("PMOE_NO_HALO") != nullptr;
   if (!halo_off && is_canonical_3x3(d) && o.h >= 18 && o.w >= 10) {
-    for (int i = 0; i < d->n_src; ++i) total_chunks += d->src[i].c / 64;
+    for (int i = 0; i < d->n_src; ++i) total_chunks += d->src[i].c / d->ck;
     if (total_chunks <= PMOE_MAX_SEG) {
       for (int cand : {128, 64, 32, 16})
-        if (d->cout_pad % cand == 0 && 9 * total_chunks * cand * 128 <= 144 * 1024) {
+        if (d->cout_pad % cand == 0 && 9 * total_chunks * cand * d->ck * 2 <= 144 * 1024) {
           halo_bn = cand;
           break;
         }
@@ -769,7 +818,24 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
       return rc;
   }
   const int ocw = bn < 64 ? bn : 64;
-  if ((rc = make_view_tmap(&p.tm_out, o, ocw, p.bw, p.bh, swizzle_for_bytes(ocw * 2), "conv_tc output")) != PMOE_OK) return rc;
+  if ((rc = make_view_tmap(&p.tm_out[0], o, ocw, p.bw, p.bh, swizzle_for_bytes(ocw * 2), "conv_tc output")) != PMOE_OK) return rc;
+  if (d->n_out_extra > 0) {
+    // multi-view launch: GEMM column n lands in view n / out_cols at channel n % out_cols
+    if (d->n_out_extra > 3 || d->out_cols <= 0 || d->out_cols % ocw != 0 || d->cout_pad != d->out_cols * (d->n_out_extra + 1) ||
+        d->residual.ptr || d->stat_sum || d->pool_sum || halo_bn) {
+      set_error("conv_tc: bad multi-view output (n_out_extra %d out_cols %d cout_pad %d)", d->n_out_extra, d->out_cols, d->cout_pad);
+      return PMOE_ERR_ARG;
+    }
+    for (int i = 0; i < d->n_out_extra; ++i) {
+      const PmoeView4& e = d->out_extra[i];
+      if (e.n != o.n || e.h != o.h || e.w != o.w) {
+        set_error("conv_tc: extra output view %d does not match the geometry of out", i);
+        return PMOE_ERR_ARG;
+      }
+      if ((rc = make_view_tmap(&p.tm_out[i + 1], e, ocw, p.bw, p.bh, swizzle_for_bytes(ocw * 2), "conv_tc extra output")) != PMOE_OK) return rc;
+    }
+    p.out_cols = d->out_cols;
+  }
   p.scale = d->scale;
   p.shift = d->shift;
   p.act = d->act;
@@ -794,38 +860,41 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   if (halo_bn) {
     int g = 0;
     for (int i = 0; i < d->n_src; ++i)
-      for (int c = 0; c < d->src[i].c / 64; ++c, ++g) {
+      for (int c = 0; c < d->src[i].c / d->ck; ++c, ++g) {
         p.seg[g].src = (int8_t)i;
         p.seg[g].dh = 0;
         p.seg[g].dw = 0;
-        p.seg[g].c0 = (uint16_t)(c * 64);
+        p.seg[g].c0 = (uint16_t)(c * d->ck);
         p.seg[g].nchunks = 1;
       }
     p.n_chunks = total_chunks;
     p.w_slots = 9 * total_chunks;
     p.m_tiles = (long long)p.tiles_w * p.tiles_h * p.n_img;
     const int ocw = halo_bn < 64 ? halo_bn : 64;
-    const int wbytes = p.w_slots * halo_bn * 128;
+    const int wbytes = ((p.w_slots * halo_bn * d->ck * 2 + 1023) / 1024) * 1024;  // halo stages stay 1 KB aligned
+    const int halo_bytes = ((18 * 10 * d->ck * 2 + 1023) / 1024) * 1024;
     int fixed = 0, stages = 0;
     for (p.out_bufs = 2; p.out_bufs >= 1; --p.out_bufs) {
       fixed = 1024 + p.out_bufs * 128 * ocw * 2 + (3 * halo_bn + 2 * kMaxStatC) * 4 + (2 * 6 + 5) * 8 + 16;
-      stages = (227 * 1024 - fixed - wbytes) / (23 * 1024);
+      stages = (227 * 1024 - fixed - wbytes) / halo_bytes;
       if (stages >= 3 || p.out_bufs == 1) break;
     }
     if (stages > 6) stages = 6;
     if (stages >= 2) {
       p.halo_stages = stages;
-      const int smem_bytes = fixed + wbytes + stages * 23 * 1024;
+      p.w_bytes = wbytes;
+      const int smem_bytes = fixed + wbytes + stages * halo_bytes;
       switch (halo_bn) {
-        case 128: return launch_halo<128>(p, smem_bytes, stream);
-        case 64: return launch_halo<64>(p, smem_bytes, stream);
-        case 32: return launch_halo<32>(p, smem_bytes, stream);
-        default: return launch_halo<16>(p, smem_bytes, stream);
+        case 128: return launch_halo_ck<128>(p, d->ck, smem_bytes, stream);
+        case 64: return launch_halo_ck<64>(p, d->ck, smem_bytes, stream);
+        case 32: return launch_halo_ck<32>(p, d->ck, smem_bytes, stream);
+        default: return launch_halo_ck<16>(p, d->ck, smem_bytes, stream);
       }
     }
     set_error("conv_tc: internal error: halo variant selected without room for two stages");
     return PMOE_ERR_ARG;
   }
+  p.tiles_n_varies = p.tiles_n > 1 ? 1 : 0;
   switch (bn) {
     case 256: return launch_tc_ck<256>(p, d->ck, stream);
     case 128: return launch_tc_ck<128>(p, d->ck, stream);

@@ -83,6 +83,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  if (tmem_base != 0u) {  // one CTA per SM, one allocation of all 512 columns: the MMA issuer relies on base 0
+    if (threadIdx.x == 0) printf("pmoe conv_wgrad_tc: unexpected TMEM base %u\n", tmem_base);
+    __trap();
+  }
 
   // decode the work unit of this CTA
   int u = blockIdx.x;
@@ -123,6 +127,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.N, 1, 1);
+      constexpr uint32_t kHiA = umma_desc_hi(1280u, kLayoutSW128);  // 8-pixel K groups of a halo view: 10 rows apart
+      constexpr uint32_t kHiB = umma_desc_hi(1024u, kLayoutSW128);
       int stage = 0;
       uint32_t phase = 0;
       bool first = true;
@@ -137,13 +143,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
           const int row0 = (t0 / 3) * 10 + (t0 % 3);
           const int row1 = (t1 / 3) * 10 + (t1 % 3);
           const uint32_t lbo = (uint32_t)(row1 - row0) * 128u;
-          const uint32_t d_tmem = tmem_base + (uint32_t)(pi * p.N);
+          const uint32_t d_tmem = (uint32_t)(pi * p.N);  // TMEM base is 0 (checked after the allocation)
+          const uint32_t a_lo = umma_desc_lo(halo + (uint32_t)row0 * 128u, lbo);
+          const uint32_t b_lo = umma_desc_lo(dyb, (uint32_t)kWgDyBlock);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {  // K = 16 pixels = patch rows 2j, 2j+1
-            const uint64_t adesc = umma_desc_mnmajor(halo + (uint32_t)(row0 + 20 * j) * 128u, lbo, 1280u);
-            const uint64_t bdesc = umma_desc_mnmajor(dyb + (uint32_t)j * 2048u, (uint32_t)kWgDyBlock, 1024u);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (first && j == 0) ? 0u : 1u);
-          }
+          for (int j = 0; j < 8; ++j)  // K = 16 pixels = patch rows 2j, 2j+1
+            umma_bf16_split(d_tmem, a_lo + (uint32_t)j * (20u * 128u >> 4), kHiA, b_lo + (uint32_t)j * (2048u >> 4), kHiB, idesc,
+                            (first && j == 0) ? 0u : 1u);
         }
         first = false;
         umma_commit(&empty_bar[stage]);
@@ -275,6 +281,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_stream_kernel(con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  if (tmem_base != 0u) {
+    if (threadIdx.x == 0) printf("pmoe conv_wgrad_tc_stream: unexpected TMEM base %u\n", tmem_base);
+    __trap();
+  }
 
   int u = blockIdx.x;
   const int split = u % p.splits;
@@ -324,6 +334,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_stream_kernel(con
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.N, 1, 1);
+      constexpr uint32_t kHiA = umma_desc_hi(8u * ROWB, LAYOUT);
+      constexpr uint32_t kHiB = umma_desc_hi(1024u, kLayoutSW128);
       int as = 0;
       uint32_t aphase = 0;
       uint32_t it = 0;
@@ -336,18 +348,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_stream_kernel(con
           mbar_wait(&a_full[as], aphase);
           tc_fence_after();
           const uint32_t ab = smem_u32(a_pipe + (size_t)as * kWgAStage);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(a * p.N);
+          const uint32_t d_tmem = (uint32_t)(a * p.N);  // TMEM base is 0 (checked after the allocation)
+          const uint32_t a_lo = umma_desc_lo(ab, (uint32_t)UNIT_BYTES);
+          const uint32_t b_lo = umma_desc_lo(dyb, (uint32_t)kWgDyBlock);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {  // K = 16 pixels per MMA
-            uint64_t adesc = 0;
-            adesc |= static_cast<uint64_t>(((ab + (uint32_t)j * 16u * ROWB) >> 4) & 0x3FFFu);
-            adesc |= static_cast<uint64_t>((UNIT_BYTES >> 4) & 0x3FFFu) << 16;
-            adesc |= static_cast<uint64_t>(((8u * ROWB) >> 4) & 0x3FFFu) << 32;
-            adesc |= static_cast<uint64_t>(1u) << 46;
-            adesc |= static_cast<uint64_t>(LAYOUT) << 61;
-            const uint64_t bdesc = umma_desc_mnmajor(dyb + (uint32_t)j * 2048u, (uint32_t)kWgDyBlock, 1024u);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (it | (uint32_t)j) != 0u ? 1u : 0u);
-          }
+          for (int j = 0; j < 8; ++j)  // K = 16 pixels per MMA
+            umma_bf16_split(d_tmem, a_lo + (uint32_t)j * (16u * ROWB >> 4), kHiA, b_lo + (uint32_t)j * (2048u >> 4), kHiB, idesc,
+                            (it | (uint32_t)j) != 0u ? 1u : 0u);
           umma_commit(&a_empty[as]);
           if (++as == p.a_stages) {
             as = 0;

@@ -34,11 +34,19 @@ def folded_bn(bn, cout_pad):
     return cached(bn, "fold%d" % cout_pad, [bn.weight, bn.bias, bn.running_mean, bn.running_var], build)
 
 
-def packed_conv(conv, groups, group_pads, taps, cout_pad, name="w"):
-    """conv.weight (Cout, sum(groups), R, S) -> [cout_pad, K] bf16 in (tap, group, padded channel) order."""
-    key = "%s_%s_%s_%d_%s" % (name, "-".join(map(str, groups)), "-".join(map(str, group_pads)), cout_pad, config.precision())
-    return cached(conv, key, [conv.weight],
-                  lambda: ops.pack_conv_weight(conv.weight.detach().float(), groups, group_pads, taps, cout_pad, config.act_dtype()))
+def packed_conv(conv, groups, group_pads, taps, cout_pad, name="w", bn=None):
+    """conv.weight (Cout, sum(groups), R, S) -> [cout_pad, K] bf16 in (tap, group, padded channel) order. With `bn`,
+    the eval-mode BatchNorm scale gamma/sqrt(var+eps) is folded into the rows (the epilogue then adds the shift only)."""
+    key = "%s_%s_%s_%d_%s_%s" % (name, "-".join(map(str, groups)), "-".join(map(str, group_pads)), cout_pad, config.precision(),
+                                 "bn" if bn is not None else "")
+    deps = [conv.weight] if bn is None else [conv.weight, bn.weight, bn.running_var]
+
+    def build():
+        w = conv.weight.detach().float()
+        if bn is not None:
+            w = w * (bn.weight.float() / torch.sqrt(bn.running_var.float() + bn.eps)).view(-1, 1, 1, 1)
+        return ops.pack_conv_weight(w, groups, group_pads, taps, cout_pad, config.act_dtype())
+    return cached(conv, key, deps, build)
 
 
 def padded_bias(mod, cout_pad):
@@ -63,12 +71,12 @@ def conv_eval(srcs, conv, bn=None, act=None, out=None, residual=None, pool=None,
     ck = ops.choose_ck(phys)
     taps = TAPS3 if ksize == 3 else [(0, 0)]
     pad = ksize // 2
-    wp = packed_conv(conv, glog, gpad, taps, cop)
+    wp = packed_conv(conv, glog, gpad, taps, cop, bn=bn)
     segs = ops.conv_segments([(r - pad, s - pad) for (r, s) in taps], phys, ck)
+    scale = None  # the BatchNorm scale lives in the packed weights
     if bn is not None:
-        scale, shift = folded_bn(bn, cop)
+        shift = folded_bn(bn, cop)[1]
     else:
-        scale = None
         shift = padded_bias(conv, cop) if conv.bias is not None else None
     n, h, w, _ = srcs[0].t.shape
     if out is None:
@@ -86,21 +94,28 @@ def conv3_block_eval(seq, srcs, pool=None):
 
 
 def conv_transpose_eval(up, x):
-    """nn.ConvTranspose2d(k=2, s=2) (unet.py:35-45): four 1x1 GEMMs, one per output pixel parity."""
+    """nn.ConvTranspose2d(k=2, s=2) (unet.py:35-45) as ONE GEMM with N = 4*Cout: column block q = 2a+b holds the
+    weights of output parity (a, b) and is stored into the pixel-shuffle view out[:, a::2, b::2, :]."""
     cin, cout = up.weight.shape[0], up.weight.shape[1]
-    cop = ops.cout_padded(cout)
     n, h, w, cp = x.t.shape
-    out = torch.empty(n, 2 * h, 2 * w, pad_ch(cout), dtype=config.act_dtype(), device=x.t.device)
+    cs = pad_ch(cout)
+    out = torch.empty(n, 2 * h, 2 * w, cs, dtype=config.act_dtype(), device=x.t.device)
     ck = ops.choose_ck([cp])
     segs = ops.conv_segments([(0, 0)], [cp], ck)
+    views = [out[:, a::2, b::2, :] for a in range(2) for b in range(2)]
+    if cs % 64 == 0:
+        wp, shift = cached(up, "wq4_%d_%d_%s" % (cp, cs, config.precision()), [up.weight, up.bias], lambda: ops.pack_convT_weight(up, cp, cs))
+        ops.conv([x.t], wp, segs, ck, views[0], shift=shift, out_extra=views[1:], out_cols=cs,
+                 flops=2.0 * n * h * w * cin * cout * 4, tag="convT %dx%d %d->%d" % (h, w, cin, cout))
+        return Act(out, cout)
+    cop = ops.cout_padded(cout)
     shift = padded_bias(up, cop)
-    for a in range(2):
-        for b in range(2):
-            wp = cached(up, "wq%d%d_%d_%d_%s" % (a, b, cp, cop, config.precision()), [up.weight],
-                        lambda: ops.pack_conv_weight(up.weight.detach().float()[:, :, a, b].t().reshape(cout, cin, 1, 1),
-                                                     [cin], [cp], [(0, 0)], cop, config.act_dtype()))
-            ops.conv([x.t], wp, segs, ck, out[:, a::2, b::2, :], shift=shift,
-                     flops=2.0 * n * h * w * cin * cout, tag="convT %dx%d %d->%d" % (h, w, cin, cout))
+    for q, (a, b) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        wp = cached(up, "wq%d%d_%d_%d_%s" % (a, b, cp, cop, config.precision()), [up.weight],
+                    lambda: ops.pack_conv_weight(up.weight.detach().float()[:, :, a, b].t().reshape(cout, cin, 1, 1),
+                                                 [cin], [cp], [(0, 0)], cop, config.act_dtype()))
+        ops.conv([x.t], wp, segs, ck, views[q], shift=shift,
+                 flops=2.0 * n * h * w * cin * cout, tag="convT %dx%d %d->%d" % (h, w, cin, cout))
     return Act(out, cout)
 
 

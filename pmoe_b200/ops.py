@@ -65,6 +65,22 @@ def conv_segments(taps_dhdw, src_cpads, ck):
     return segs
 
 
+def pack_convT_weight(up, cp, cs, dtype=None):
+    """ConvTranspose2d(k=2,s=2) weight (Cin, Cout, 2, 2) + bias -> ([4*cs, cp] packed weight, [4*cs] shift): row block
+    q = 2a+b carries W[:, :, a, b]^T (the GEMM of output parity (a, b)); the bias repeats per block."""
+    from . import config
+    dtype = config.act_dtype() if dtype is None else dtype
+    wf = up.weight.detach().float()
+    cin, cout = wf.shape[0], wf.shape[1]
+    wp = torch.zeros(4 * cs, cp, dtype=torch.float32, device=wf.device)
+    shift = torch.zeros(4 * cs, dtype=torch.float32, device=wf.device)
+    for q, (a, b) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+        wp[q * cs:q * cs + cout, :cin] = wf[:, :, a, b].t()
+        if up.bias is not None:
+            shift[q * cs:q * cs + cout] = up.bias.detach().float()
+    return wp.to(dtype).contiguous(), shift
+
+
 TAPS3 = [(r, s) for r in range(3) for s in range(3)]
 
 
@@ -75,7 +91,7 @@ def pad_vec(v, n, fill=0.0):
 
 
 def _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum, stat_sqsum, pool_sum, src_channels,
-               pool_stride, dtype):
+               pool_stride, dtype, out_extra=None, out_cols=0):
     d = _lib.ConvTc()
     assert 1 <= len(srcs) <= _lib.MAX_SRC and 1 <= len(segs) <= _lib.MAX_SEG, (len(srcs), len(segs))
     d.n_src = len(srcs)
@@ -101,16 +117,23 @@ def _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum
     d.stat_sqsum = None if stat_sqsum is None else stat_sqsum.data_ptr()
     d.pool_sum = None if pool_sum is None else pool_sum.data_ptr()
     d.pool_stride = int(pool_stride) if pool_stride else (pool_sum.stride(0) if pool_sum is not None and pool_sum.dim() == 2 else 0)
+    if out_extra:
+        assert len(out_extra) <= 3
+        d.n_out_extra = len(out_extra)
+        d.out_cols = int(out_cols)
+        for i, t in enumerate(out_extra):
+            assert t.dtype == dtype
+            d.out_extra[i] = _lib.view4(t)
     return d
 
 
 def conv_tc(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residual=None, stat_sum=None,
-            stat_sqsum=None, pool_sum=None, src_channels=None, pool_stride=0, flops=0.0, tag=""):
+            stat_sqsum=None, pool_sum=None, src_channels=None, pool_stride=0, flops=0.0, tag="", out_extra=None, out_cols=0):
     """Launch the tcgen05 implicit-GEMM kernel. srcs: list of NHWC bf16 tensors (views allowed);
     out: NHWC bf16 tensor/view; wpack: [cout_pad, ktot] bf16."""
     assert wpack.dtype == torch.bfloat16
     d = _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum, stat_sqsum, pool_sum, src_channels,
-                   pool_stride, torch.bfloat16)
+                   pool_stride, torch.bfloat16, out_extra, out_cols)
     fn = _lib.lib().pmoe_conv_tc
     sp = _lib.stream_ptr()
     _lib.check(profiler.launch("conv_tc", lambda: fn(C.byref(d), sp), flops, 0.0, tag), "conv_tc")
@@ -118,10 +141,17 @@ def conv_tc(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residu
 
 
 def conv_simt(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residual=None, stat_sum=None,
-              stat_sqsum=None, pool_sum=None, src_channels=None, pool_stride=0, flops=0.0, tag=""):
+              stat_sqsum=None, pool_sum=None, src_channels=None, pool_stride=0, flops=0.0, tag="", out_extra=None, out_cols=0):
     """CUDA-core twin of conv_tc (fp32 or bf16 storage, fp32 FMA accumulation)."""
     dt = out.dtype
     assert wpack.dtype == dt
+    if out_extra:
+        # multi-view outputs are a tensor-core-kernel feature: one launch per view here
+        cols = int(out_cols)
+        for q, view in enumerate([out] + list(out_extra)):
+            conv_simt(srcs, wpack[q * cols:(q + 1) * cols], segs, ck, view, None if scale is None else scale[q * cols:(q + 1) * cols],
+                      None if shift is None else shift[q * cols:(q + 1) * cols], act, flops=flops / (len(out_extra) + 1), tag=tag)
+        return out
     d = _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum, stat_sqsum, pool_sum, src_channels,
                    pool_stride, dt)
     fn = _lib.lib().pmoe_conv_simt

@@ -447,14 +447,19 @@ def conv_transpose_op(tape, up, x, tag=""):
     n, h, w, cp = x.t.shape
     ck = ops.choose_ck([cp])
     segs = ops.conv_segments([(0, 0)], [cp], ck)
-    shift = ops.pad_vec(bias.detach(), cop, 0.0)
     out = torch.empty(n, 2 * h, 2 * w, cstore, dtype=dt, device=dev)
     wf = weight.detach().float()
     flops = 2.0 * n * h * w * cin * cout
-    for a in range(2):
-        for b in range(2):
+    views = [out[:, a::2, b::2, :] for a in range(2) for b in range(2)]
+    if cstore % 64 == 0:  # one GEMM with N = 4*Cout, column block q stored into pixel-shuffle view q
+        wp4 = _cached_pack(weight, "T4|%d|%d|%s" % (cp, cstore, dt), lambda: ops.pack_convT_weight(up, cp, cstore, dt)[0])
+        shift4 = ops.pad_vec(bias.detach(), cstore, 0.0).repeat(4)
+        ops.conv([x.t], wp4, segs, ck, views[0], shift=shift4, out_extra=views[1:], out_cols=cstore, flops=4 * flops, tag="convT " + tag)
+    else:
+        shift = ops.pad_vec(bias.detach(), cop, 0.0)
+        for q, (a, b) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
             wp = ops.pack_conv_weight(wf[:, :, a, b].t().reshape(cout, cin, 1, 1), [x.c], [cp], [(0, 0)], cop, dt)
-            ops.conv([x.t], wp, segs, ck, out[:, a::2, b::2, :], shift=shift, flops=flops, tag="convT " + tag)
+            ops.conv([x.t], wp, segs, ck, views[q], shift=shift, flops=flops, tag="convT " + tag)
     rg = _rg(x) or _any_rg([weight, bias])
     ya = _new_act(tape, out, cout, rg)
     if tape.save and rg:

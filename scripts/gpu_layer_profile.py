@@ -4,11 +4,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 from pmoe_b200 import profiler
-from pmoe_b200.model.punet import PredictiveUnet
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-sd = bench.build_punet_state()
-torch.save({"unet": {k[5:]: v for k, v in sd.items() if k.startswith("unet.")}}, "/tmp/unet.pth")
-net = PredictiveUnet(**dict(bench.PUNET_CFG, model_path="/tmp/unet.pth")); net.load_state_dict(sd); net = net.cuda().eval()
+net = bench.build_punet().cuda().eval()
 x = torch.rand(B, 4, 3, 224, 224, device="cuda")
 with torch.no_grad():
     for _ in range(2): net(x)

@@ -35,9 +35,11 @@ def load(name):
     return torch.load(os.path.join(GOLDEN, name), weights_only=False)
 
 
-def grad_report(named_params, golden_grads):
+def grad_report(named_params, golden_grads, skip=()):
     worst_norm, worst_val, n = (0.0, ""), (0.0, ""), 0
     for name, p in named_params:
+        if any(s_ in name for s_ in skip):
+            continue
         if name not in golden_grads:
             assert p.grad is None or p.grad.abs().sum().item() == 0, "unexpected gradient for " + name
             continue
@@ -89,8 +91,37 @@ def test_moe_fp32_vs_reference_golden(mtype):
           % (mtype, e_p, e_lp, lossv.item(), g["loss"].item(), wn[0], wn[1], wv[0], wv[1], bn_err, n))
     assert e_p < 1e-4 and e_lp < 1e-4
     assert abs(lossv.item() - g["loss"].item()) < 1e-4 * max(1.0, abs(g["loss"].item()))
-    # the ECA conv1d weights (3-5 numbers fed by global pools) are the worst-conditioned gradients of the model
-    assert wn[0] < 2e-2 and wv[0] < 2e-2
+    # Gradient parity. Train-mode BatchNorm after every conv makes several gradients the small remainder of large
+    # cancelling sums (worst: the 3-5 ECA conv1d weights, whose common channel scale the following BN removes), so the
+    # fp32 CPU reference itself is only reproducible to ~1e-2 on them across summation orders. The bound is therefore
+    # taken RELATIVE to an fp64 evaluation of the same step: the CUDA fp32 path must sit within a small factor of the
+    # CPU fp32 path's own distance to fp64 (and within a loose absolute bound of the live-reference golden).
+    assert wn[0] < 5e-2 and wv[0] < 5e-2
+
+    def oracle_grads(dtype):
+        sdg = {}
+        for k, v in sd.items():
+            v = v.clone().to(dtype) if v.is_floating_point() else v.clone()
+            if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+                v.requires_grad_(True)
+            sdg[k] = v
+        fn = O.moe_shared if mtype == "moe_shared" else O.moe
+        o = fn(g["images"].to(dtype), g["speed"].to(dtype), g["command"].to(dtype), sdg, "", g["cfg"], True)
+        O.moe_loss(o[0], o[1], o[2], o[3], g["control"].to(dtype), g["target_speed"].to(dtype), g["cfg"]["loss_coefs"]).backward()
+        return sdg
+
+    sd64, sd32 = oracle_grads(torch.float64), oracle_grads(torch.float32)
+    gc, gp = {}, {}
+    for name, prm in model.named_parameters():
+        if sd64[name].grad is None:
+            continue
+        gc[name] = rel_err(prm.grad.cpu(), sd64[name].grad)
+        gp[name] = rel_err(sd32[name].grad, sd64[name].grad)
+    wc, wp = max(gc.values()), max(gp.values())
+    mc, mp = sorted(gc.values())[len(gc) // 2], sorted(gp.values())[len(gp) // 2]
+    print("   vs fp64 oracle: grads median cuda %.2e / cpu-fp32 %.2e | worst cuda %.2e (%s) / cpu-fp32 %.2e (%s)"
+          % (mc, mp, wc, max(gc, key=gc.get), wp, max(gp, key=gp.get)))
+    assert mc < 4 * mp + 1e-5 and wc < 6 * wp + 1e-3
     assert bn_err < 1e-4
     if mtype != "moe_shared":
         assert tuple(ts.shape) == (ts.shape[0], 1, 1)  # loss.py:127 in-place unsqueeze_ reproduced

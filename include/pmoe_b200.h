@@ -78,6 +78,14 @@ typedef struct PmoeConvTc {
   int32_t n_out_extra;
   int32_t out_cols;
   PmoeView4 out_extra[3];
+  /* Optional fused nn.MaxPool2d(2,2) (unet.py:29) of the stored output: (n, H/2, W/2, >= out.c) bf16 view, H and W
+   * even. PMOE_ERR_UNSUPPORTED if the geometry does not allow it (the caller then runs pmoe_maxpool). */
+  PmoeView4 pool2_out;
+  /* Optional fp32 NCHW copy of output channels [0, nchw_c) (the module boundary hands fp32 NCHW logits back,
+   * punet.py:118-120); strides in elements. */
+  float* nchw_out;
+  int64_t nchw_sn, nchw_sc, nchw_sh, nchw_sw;
+  int32_t nchw_c;
 } PmoeConvTc;
 
 int pmoe_conv_tc(const PmoeConvTc* desc, pmoe_stream_t stream);
@@ -139,11 +147,11 @@ int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* d
                      int32_t pad, int32_t accumulate, pmoe_stream_t stream);
 int pmoe_maxpool_bwd_idx(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* dx, int32_t dtype, int32_t k,
                          int32_t stride, int32_t pad, int32_t accumulate, pmoe_stream_t stream);
-int pmoe_prod_channel_sums(const PmoeView4* a, const PmoeView4* b, int32_t dtype, float* out, int64_t out_stride,
+int pmoe_prod_channel_sums(const PmoeView4* a, const PmoeView4* b, int32_t dtype, double* out, int64_t out_stride,
                            pmoe_stream_t stream);
-int pmoe_eca_gate_bwd(const float* dgate, int64_t dgate_stride, const float* gate, int64_t gate_stride, const float* pool_sum,
+int pmoe_eca_gate_bwd(const double* dgate, int64_t dgate_stride, const float* gate, int64_t gate_stride, const float* pool_sum,
                       int64_t pool_stride, int32_t n, float inv_count, const float* w, int32_t k, int32_t groups,
-                      int32_t group_c, int32_t group_stride, float* dmean, int64_t dmean_stride, float* dw,
+                      int32_t group_c, int32_t group_stride, float* dmean, int64_t dmean_stride, double* dw,
                       pmoe_stream_t stream);
 int pmoe_eca_bwd_apply(const PmoeView4* dout, int32_t dtype, const float* gate, int64_t gate_stride, const float* dmean,
                        int64_t dmean_stride, const PmoeView4* dx, int32_t accumulate, pmoe_stream_t stream);
@@ -198,8 +206,8 @@ int pmoe_mt_sqnorm(const PmoeMtChunk* chunks_dev, int32_t n_chunks, double* sqno
 int pmoe_mt_clip(const PmoeMtChunk* chunks_dev, int32_t n_chunks, const double* sqnorm, float max_norm, pmoe_stream_t stream);
 /* torch.optim.Adam(amsgrad) step (conf/stage_2.yaml:137-144, train_2.py:165) over all chunks; when sqnorm != NULL the
  * clip coefficient is applied to the gradient on the fly (gradients themselves are left unscaled). */
-int pmoe_mt_adam(const PmoeMtChunk* chunks_dev, int32_t n_chunks, float lr, float beta1, float beta2, float eps,
-                 float weight_decay, int32_t step, int32_t amsgrad, const double* sqnorm, float max_norm, pmoe_stream_t stream);
+int pmoe_mt_adam(const PmoeMtChunk* chunks_dev, int32_t n_chunks, double lr, double beta1, double beta2, double eps,
+                 double weight_decay, int32_t step, int32_t amsgrad, const double* sqnorm, float max_norm, pmoe_stream_t stream);
 
 /* Library info / errors. */
 int pmoe_version(void);

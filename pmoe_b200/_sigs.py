@@ -32,7 +32,7 @@ SIGS = {
     "pmoe_l1_mse": [vp, vp, i64, i32, f32, vp, vp, vp],
     "pmoe_mt_sqnorm": [vp, i32, vp, vp],
     "pmoe_mt_clip": [vp, i32, vp, f32, vp],
-    "pmoe_mt_adam": [vp, i32, f32, f32, f32, f32, f32, i32, i32, vp, f32, vp],
+    "pmoe_mt_adam": [vp, i32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, i32, i32, vp, f32, vp],
     "pmoe_segloss_fwd": [vp, i64, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, i32, f32, f32, vp, vp, vp],
     "pmoe_segloss_bwd": [vp, i64, i64, i64, i64, vp, i64, i64, i64, i32, i32, i32, i32, f32, vp, vp, f32, vp, i64, i64, i64, i64, i32, vp],
 }

@@ -29,9 +29,21 @@ struct TcSeg {
 struct alignas(64) ConvTcParams {
   CUtensorMap tm_src[PMOE_MAX_SRC];
   CUtensorMap tm_w;
-  CUtensorMap tm_out[4];  // [0] = out; [1..3] = the extra output views of a multi-view launch (ConvTranspose2d k2s2)
+  // Output views: [0] = out; [1..3] = the extra views of a multi-view launch (ConvTranspose2d k2s2). The epilogue
+  // stores straight from registers (each thread owns one pixel row: 32-byte st.global.v8), so no staging tile.
+  CUtensorMap tm_out[4];
+  int out_c;              // channels stored per view
+  int out_bufs;           // staging buffers for the TMA store (2, or 1 when shared memory is tight)
   int out_cols;           // GEMM columns per output view (0 = single view)
   int tiles_n_varies;     // the N tile changes between a CTA's tiles (streaming kernel)
+  // fused 2x2/stride-2 max-pool of the stored output (eval-mode U-Net encoder, unet.py:29)
+  __nv_bfloat16* pool2_ptr;
+  long long pool2_sn, pool2_sh, pool2_sw;
+  int pool2_align32;
+  // optional fp32 NCHW copy of the first nchw_c output channels (the module boundary, punet.py:118-120)
+  float* nchw_ptr;
+  long long nchw_sn, nchw_sc, nchw_sh, nchw_sw;
+  int nchw_c;
   TcSeg seg[PMOE_MAX_SEG];
   int n_seg, kiters;
   int tiles_w, tiles_h, tiles_n, n_img;
@@ -51,12 +63,12 @@ struct alignas(64) ConvTcParams {
   // resident-weight ("halo") variant
   int halo_stages, w_slots, n_chunks, w_bytes;
   long long m_tiles;
-  int out_bufs;  // staging buffers for the TMA store (2, or 1 when shared memory is tight)
 };
 
 constexpr int kMaxStatC = 512;
-constexpr int kNumThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;               // two warps per TMEM lane quadrant: they split the columns of a tile
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kNumThreads = 64 + kEpiThreads;
 
 template <int BN, int CK>
 struct TcCfg {
@@ -66,15 +78,16 @@ struct TcCfg {
   static constexpr int B_BYTES = BN * CK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int OUT_BYTES = 128 * OCW * 2;
-  static constexpr int BUDGET = 196 * 1024;
-  static constexpr int STAGES_RAW = (BUDGET - 2 * OUT_BYTES) / STAGE_BYTES;
+  static constexpr int OUT_BUFS = (BN >= 256 && CK == 64) ? 1 : 2;  // one staging tile buys the 4th pipeline stage at BN = 256
+  static constexpr int BUDGET = 210 * 1024;
+  static constexpr int STAGES_RAW = (BUDGET - OUT_BUFS * OUT_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int PIPE_BYTES = ((STAGES * STAGE_BYTES + 1023) / 1024) * 1024;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr uint32_t LAYOUT = CK == 64 ? kLayoutSW128 : (CK == 32 ? kLayoutSW64 : kLayoutSW32);
   static constexpr uint32_t SBO = 8 * CK * 2;  // 8 rows of one swizzle span
   static constexpr int AUX_FLOATS = 3 * BN + 2 * kMaxStatC;
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + PIPE_BYTES + 2 * OUT_BYTES + AUX_FLOATS * 4 +
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + PIPE_BYTES + OUT_BUFS * OUT_BYTES + AUX_FLOATS * 4 +
                                     (2 * STAGES + 4) * 8 + 16;
 };
 
@@ -147,177 +160,228 @@ struct ResidentTiles {
   }
 };
 
-// Epilogue role (4 warps, threads 64..191): TMEM -> registers -> affine / residual / activation / statistics ->
-// swizzled bf16 staging tile -> TMA store. Shared by both main-loop variants.
+__device__ __forceinline__ void stg256(void* ptr, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void stg128(void* ptr, const uint32_t* v) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+// 16 consecutive bf16 channels (8 packed words) to a 16-byte aligned address
+__device__ __forceinline__ void store16(__nv_bfloat16* ptr, const uint32_t* v, bool align32) {
+  if (align32) {
+    stg256(ptr, v);
+  } else {
+    stg128(ptr, v);
+    stg128(ptr + 8, v + 4);
+  }
+}
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
+// Epilogue role (8 warps, threads 64..319): TMEM -> registers -> affine / residual / activation / statistics -> bf16 ->
+// swizzled staging tile -> TMA store. Two warps share each TMEM lane quadrant and split every 64-column chunk between
+// them (32 columns each), so the dependent LDTM -> math -> pack chain of a tile runs on two warps per scheduler. The
+// main store goes through shared memory + TMA because 32 rows x 32 B register stores are one L1 transaction per row:
+// measured 2-2.5x slower than the bulk store on the write-heavy 224^2 layers. Optional extras ride on the registers: a
+// fused 2x2 max-pool (two warp shuffles: the window partners are lanes l^1 and l^bw), an fp32 NCHW copy at the module
+// boundary, BN batch statistics and per-image channel sums. Shared by both main-loop variants.
 template <int BN, int OCW, int SUB, int OUT_BYTES, class Iter>
-__device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& it, uint8_t* out_stage, float* s_scale,
-                                             float* s_shift, float* s_pool, float* s_sum, float* s_sq, uint64_t* tfull_bar,
-                                             uint64_t* tempty_bar, uint32_t tmem_base, int warp, int lane) {
-  {
-    const int e = threadIdx.x - 64;         // 0..127
-    const int quad = warp & 3;              // TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;       // accumulator row == pixel index inside the tile
-    const bool issuer = (e == 0);
-    const int ti = row / p.bw, tj = row % p.bw;
-    const bool row_in_box = row < p.bw * p.bh;
-    constexpr int ROWB = OCW * 2;
-    constexpr uint32_t SWMASK = ROWB == 128 ? 7u : (ROWB == 64 ? 3u : 1u);
-    const int act = p.act;
-    const bool has_scale = p.scale != nullptr, has_shift = p.shift != nullptr;
-    const uint32_t sc_addr = smem_u32(s_scale), sh_addr = smem_u32(s_shift);
-    uint32_t nstore = 0;
-    int img, h0, w0, nt;
-    for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
-      const int n0 = nt * BN;
-      const bool valid = row_in_box && (h0 + ti < p.H) && (w0 + tj < p.W);
-      const uint32_t acc = titer & 1u;
-      const uint32_t acc_phase = (titer >> 1) & 1u;
+__device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& it, uint8_t* out_stage, float* s_scale, float* s_shift,
+                                             float* s_pool, float* s_sum, float* s_sq, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                             int warp, int lane) {
+  const int e = threadIdx.x - 64;         // 0..kEpiThreads-1
+  const int quad = warp & 3;              // TMEM lane quadrant this warp may read (warp id % 4)
+  const int half = (warp - 2) >> 2;       // which of the quadrant's two warps
+  const int row = quad * 32 + lane;       // accumulator row == pixel index inside the tile
+  const bool issuer = (e == 0);
+  const int ti = row / p.bw, tj = row % p.bw;
+  const bool row_in_box = row < p.bw * p.bh;
+  constexpr int ROWB = OCW * 2;
+  constexpr uint32_t SWMASK = ROWB == 128 ? 7u : (ROWB == 64 ? 3u : 1u);
+  constexpr int NSB = OCW / SUB;          // 32-column blocks per chunk: 2 (one per warp of the pair) or 1
+  const bool worker = half < NSB;         // with a single block per chunk the second warp only keeps the barriers
+  const int act = p.act;
+  const bool has_scale = p.scale != nullptr, has_shift = p.shift != nullptr;
+  const uint32_t sc_addr = smem_u32(s_scale), sh_addr = smem_u32(s_shift);
+  const bool pool_owner = ((ti | tj) & 1) == 0;  // this lane holds the top-left pixel of a 2x2 pooling window
+  uint32_t nstore = 0;
+  int img, h0, w0, nt;
+  for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
+    const int n0 = nt * BN;
+    const int oh = h0 + ti, ow = w0 + tj;
+    const bool valid = row_in_box && oh < p.H && ow < p.W;
+    const uint32_t acc = titer & 1u;
+    const uint32_t acc_phase = (titer >> 1) & 1u;
 
-      if (titer == 0 || p.tiles_n_varies) {  // resident kernels keep one N tile: load the per-channel affine once
-        for (int i = e; i < BN; i += kEpiThreads) {
-          if (has_scale) s_scale[i] = __ldg(p.scale + n0 + i);
-          if (has_shift) s_shift[i] = __ldg(p.shift + n0 + i);
-        }
+    if (titer == 0 || p.tiles_n_varies) {  // resident kernels keep one N tile: the per-channel affine is loaded once
+      // (all reads of the previous tile's values happened before its last named barrier 2)
+      for (int i = e; i < BN; i += kEpiThreads) {
+        if (has_scale) s_scale[i] = __ldg(p.scale + n0 + i);
+        if (has_shift) s_shift[i] = __ldg(p.shift + n0 + i);
       }
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
+    }
+    mbar_wait(&tfull_bar[acc], acc_phase);
+    tc_fence_after();
 
-      const __nv_bfloat16* res_row = nullptr;
-      if (p.res != nullptr && valid)
-        res_row = p.res + (long long)img * p.res_sn + (long long)(h0 + ti) * p.res_sh + (long long)(w0 + tj) * p.res_sw;
+    const __nv_bfloat16* res_row = nullptr;
+    if (p.res != nullptr && valid) res_row = p.res + (long long)img * p.res_sn + (long long)oh * p.res_sh + (long long)ow * p.res_sw;
 
 #pragma unroll 1
-      for (int ch = 0; ch < BN / OCW; ++ch) {
-        uint8_t* obuf = out_stage + (p.out_bufs == 2 ? (nstore & 1u) : 0u) * OUT_BYTES;
-        if (issuer) {  // the store that last used this buffer has drained
-          if (p.out_bufs == 2) tma_store_wait_read<1>();
-          else tma_store_wait_read<0>();
+    for (int ch = 0; ch < BN / OCW; ++ch) {
+      uint8_t* obuf = out_stage + (p.out_bufs == 2 ? (nstore & 1u) : 0u) * OUT_BYTES;
+      if (issuer) {  // the store that last used this buffer has drained
+        if (p.out_bufs == 2) tma_store_wait_read<1>();
+        else tma_store_wait_read<0>();
+      }
+      named_bar_sync(1, kEpiThreads);
+      if (worker) {
+        const int cb = ch * OCW + half * SUB;  // column offset inside the N tile
+        uint32_t raw[SUB];
+        const uint32_t taddr = ((uint32_t)(quad * 32) << 16) + acc * BN + cb;  // TMEM base is 0
+        if constexpr (SUB == 32) tmem_ld_32x32(taddr, raw);
+        else tmem_ld_32x16(taddr, raw);
+        tmem_ld_wait();
+        float y[SUB];
+#pragma unroll
+        for (int k = 0; k < SUB; ++k) y[k] = __uint_as_float(raw[k]);
+        // per-channel affine: 128-bit broadcast LDS of scale / shift, each only when present (eval-mode BN is folded
+        // into the packed weights by the host, so inference needs the shift alone)
+        if (has_scale) {
+#pragma unroll
+          for (int q = 0; q < SUB / 4; ++q) {
+            const float4 sc4 = lds128(sc_addr + (uint32_t)(cb + 4 * q) * 4u);
+            y[4 * q + 0] *= sc4.x;
+            y[4 * q + 1] *= sc4.y;
+            y[4 * q + 2] *= sc4.z;
+            y[4 * q + 3] *= sc4.w;
+          }
         }
-        named_bar_sync(1, kEpiThreads);
+        if (has_shift) {
 #pragma unroll
-        for (int sb = 0; sb < OCW / SUB; ++sb) {
-          const int cb = ch * OCW + sb * SUB;  // column offset inside the N tile
-          uint32_t raw[SUB];
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + cb;
-          if constexpr (SUB == 32) tmem_ld_32x32(taddr, raw);
-          else tmem_ld_32x16(taddr, raw);
-          tmem_ld_wait();
-          float y[SUB];
-#pragma unroll
-          for (int k = 0; k < SUB; ++k) y[k] = __uint_as_float(raw[k]);
-          // per-channel affine: 128-bit broadcast LDS of scale / shift, each only when present (eval-mode BN is
-          // folded into the packed weights by the host, so inference needs the shift alone)
-          if (has_scale) {
-#pragma unroll
-            for (int q = 0; q < SUB / 4; ++q) {
-              const float4 sc4 = lds128(sc_addr + (uint32_t)(cb + 4 * q) * 4u);
-              y[4 * q + 0] *= sc4.x;
-              y[4 * q + 1] *= sc4.y;
-              y[4 * q + 2] *= sc4.z;
-              y[4 * q + 3] *= sc4.w;
-            }
+          for (int q = 0; q < SUB / 4; ++q) {
+            const float4 sh4 = lds128(sh_addr + (uint32_t)(cb + 4 * q) * 4u);
+            y[4 * q + 0] += sh4.x;
+            y[4 * q + 1] += sh4.y;
+            y[4 * q + 2] += sh4.z;
+            y[4 * q + 3] += sh4.w;
           }
-          if (has_shift) {
+        }
+        if (p.stat_sum != nullptr) {
+          float a[SUB], b[SUB];
 #pragma unroll
-            for (int q = 0; q < SUB / 4; ++q) {
-              const float4 sh4 = lds128(sh_addr + (uint32_t)(cb + 4 * q) * 4u);
-              y[4 * q + 0] += sh4.x;
-              y[4 * q + 1] += sh4.y;
-              y[4 * q + 2] += sh4.z;
-              y[4 * q + 3] += sh4.w;
-            }
+          for (int k = 0; k < SUB; ++k) {
+            const float f = valid ? __uint_as_float(raw[k]) : 0.f;
+            a[k] = f;
+            b[k] = f * f;
           }
-          if (p.stat_sum != nullptr) {
-            float a[SUB], b[SUB];
-#pragma unroll
-            for (int k = 0; k < SUB; ++k) {
-              const float f = valid ? __uint_as_float(raw[k]) : 0.f;
-              a[k] = f;
-              b[k] = f * f;
-            }
-            const float sa = warp_col_sums<SUB>(a, lane);
-            const float sq = warp_col_sums<SUB>(b, lane);
-            if (lane < SUB && n0 + cb + lane < kMaxStatC) {
-              atomicAdd(&s_sum[n0 + cb + lane], sa);
-              atomicAdd(&s_sq[n0 + cb + lane], sq);
-            }
+          const float sa = warp_col_sums<SUB>(a, lane);
+          const float sq = warp_col_sums<SUB>(b, lane);
+          if (lane < SUB && n0 + cb + lane < kMaxStatC) {
+            atomicAdd(&s_sum[n0 + cb + lane], sa);
+            atomicAdd(&s_sq[n0 + cb + lane], sq);
           }
-          if (res_row != nullptr) {
+        }
+        if (res_row != nullptr) {
 #pragma unroll
-            for (int q = 0; q < SUB / 8; ++q) {
-              if (n0 + cb + q * 8 < p.res_c) {
-                const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + cb + q * 8));
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+          for (int q = 0; q < SUB / 8; ++q) {
+            if (n0 + cb + q * 8 < p.res_c) {
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(res_row + n0 + cb + q * 8));
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float2 f2 = __bfloat1622float2(r2[u]);
-                  y[q * 8 + 2 * u] += f2.x;
-                  y[q * 8 + 2 * u + 1] += f2.y;
-                }
+              for (int u = 0; u < 4; ++u) {
+                const float2 f2 = __bfloat1622float2(r2[u]);
+                y[q * 8 + 2 * u] += f2.x;
+                y[q * 8 + 2 * u + 1] += f2.y;
               }
             }
           }
-          if (act == PMOE_ACT_RELU) {  // the branch is uniform and hoisted out of the element loop
+        }
+        if (act == PMOE_ACT_RELU) {  // the branch is uniform and hoisted out of the element loop
 #pragma unroll
-            for (int k = 0; k < SUB; ++k) y[k] = fmaxf(y[k], 0.f);
-          } else if (act != PMOE_ACT_NONE) {
+          for (int k = 0; k < SUB; ++k) y[k] = fmaxf(y[k], 0.f);
+        } else if (act != PMOE_ACT_NONE) {
 #pragma unroll
-            for (int k = 0; k < SUB; ++k) y[k] = apply_act(y[k], act);
+          for (int k = 0; k < SUB; ++k) y[k] = apply_act(y[k], act);
+        }
+        // bf16 pack -> swizzled staging tile (row = pixel, ROWB bytes per row)
+        uint32_t pk[SUB / 2];
+#pragma unroll
+        for (int k = 0; k < SUB / 2; ++k) pk[k] = pack_bf16x2(y[2 * k], y[2 * k + 1]);
+#pragma unroll
+        for (int q = 0; q < SUB / 8; ++q) {
+          uint32_t off = (uint32_t)row * ROWB + (uint32_t)(half * SUB + q * 8) * 2u;
+          off ^= ((off >> 7) & SWMASK) << 4;
+          *reinterpret_cast<uint4*>(obuf + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+        const int col = n0 + cb;
+        if (p.pool2_ptr != nullptr) {
+          // 2x2 max over pixels (ti, tj), (ti, tj^1), (ti^1, tj), (ti^1, tj^1) = lanes l, l^1, l^bw, l^bw^1 (bw is a
+          // power of two <= 16 and the tile origin is even, both guaranteed by the host)
+          uint32_t m[SUB / 2];
+#pragma unroll
+          for (int k = 0; k < SUB / 2; ++k) {
+            const uint32_t v = bf16x2_max(pk[k], __shfl_xor_sync(0xffffffffu, pk[k], 1));
+            m[k] = bf16x2_max(v, __shfl_xor_sync(0xffffffffu, v, p.bw));
           }
-          // bf16 pack -> swizzled staging tile (row = pixel, ROWB bytes per row)
+          if (valid && pool_owner) {
+            __nv_bfloat16* prow = p.pool2_ptr + (long long)img * p.pool2_sn + (long long)(oh >> 1) * p.pool2_sh +
+                                  (long long)(ow >> 1) * p.pool2_sw + col;
 #pragma unroll
-          for (int q = 0; q < SUB / 8; ++q) {
-            uint4 pk;
-            pk.x = pack_bf16x2(y[q * 8 + 0], y[q * 8 + 1]);
-            pk.y = pack_bf16x2(y[q * 8 + 2], y[q * 8 + 3]);
-            pk.z = pack_bf16x2(y[q * 8 + 4], y[q * 8 + 5]);
-            pk.w = pack_bf16x2(y[q * 8 + 6], y[q * 8 + 7]);
-            uint32_t off = (uint32_t)row * ROWB + (uint32_t)(sb * SUB + q * 8) * 2u;
-            off ^= ((off >> 7) & SWMASK) << 4;
-            *reinterpret_cast<uint4*>(obuf + off) = pk;
-          }
-          if (p.pool_sum != nullptr) {
-            // pool what is actually stored (bf16-rounded), masked to valid pixels
-            float a[SUB];
-#pragma unroll
-            for (int k = 0; k < SUB; ++k) a[k] = valid ? __bfloat162float(__float2bfloat16_rn(y[k])) : 0.f;
-            const float sa = warp_col_sums<SUB>(a, lane);
-            if (lane < SUB) atomicAdd(&s_pool[cb + lane], sa);
+            for (int q = 0; q < SUB / 16; ++q)
+              if (col + q * 16 < p.out_c) store16(prow + q * 16, m + q * 8, p.pool2_align32 != 0);
           }
         }
-        fence_proxy_async_smem();
-        named_bar_sync(2, kEpiThreads);
-        if (issuer) {
-          const int col = n0 + ch * OCW;
-          if (p.out_cols > 0) tma_store_4d(&p.tm_out[col / p.out_cols], obuf, col % p.out_cols, w0, h0, img);
-          else tma_store_4d(&p.tm_out[0], obuf, col, w0, h0, img);
-          tma_store_commit();
+        if (p.nchw_ptr != nullptr && valid) {
+          float* nrow = p.nchw_ptr + (long long)img * p.nchw_sn + (long long)oh * p.nchw_sh + (long long)ow * p.nchw_sw;
+#pragma unroll
+          for (int k = 0; k < SUB; ++k)
+            if (col + k < p.nchw_c) nrow[(long long)(col + k) * p.nchw_sc] = y[k];
         }
-        ++nstore;
+        if (p.pool_sum != nullptr) {
+          // pool what is actually stored (bf16-rounded), masked to valid pixels
+          float a[SUB];
+#pragma unroll
+          for (int k = 0; k < SUB; ++k) a[k] = valid ? __bfloat162float(__float2bfloat16_rn(y[k])) : 0.f;
+          const float sa = warp_col_sums<SUB>(a, lane);
+          if (lane < SUB) atomicAdd(&s_pool[cb + lane], sa);
+        }
       }
-      // accumulator stage fully read -> hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (p.pool_sum != nullptr) {
-        named_bar_sync(3, kEpiThreads);
-        for (int i = e; i < BN; i += kEpiThreads) {
-          const float v = s_pool[i];
-          if (v != 0.f) atomicAdd(p.pool_sum + (long long)img * p.pool_stride + n0 + i, v);
-          s_pool[i] = 0.f;
-        }
+      fence_proxy_async_smem();
+      named_bar_sync(2, kEpiThreads);
+      if (issuer) {
+        const int col = n0 + ch * OCW;
+        if (p.out_cols > 0) tma_store_4d(&p.tm_out[col / p.out_cols], obuf, col % p.out_cols, w0, h0, img);
+        else tma_store_4d(&p.tm_out[0], obuf, col, w0, h0, img);
+        tma_store_commit();
       }
+      ++nstore;
     }
-    if (issuer) tma_store_wait_read<0>();
-    if (p.stat_sum != nullptr) {
+    // accumulator stage fully read -> hand it back to the MMA warp
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    if (p.pool_sum != nullptr) {
       named_bar_sync(3, kEpiThreads);
-      const int nc = p.cout_pad < kMaxStatC ? p.cout_pad : kMaxStatC;
-      for (int i = e; i < nc; i += kEpiThreads) {
-        atomicAdd(p.stat_sum + i, (double)s_sum[i]);
-        atomicAdd(p.stat_sq + i, (double)s_sq[i]);
+      for (int i = e; i < BN; i += kEpiThreads) {
+        const float v = s_pool[i];
+        if (v != 0.f) atomicAdd(p.pool_sum + (long long)img * p.pool_stride + n0 + i, v);
+        s_pool[i] = 0.f;
       }
     }
+  }
+  if (issuer) tma_store_wait_read<0>();
+  if (p.stat_sum != nullptr) {
+    named_bar_sync(3, kEpiThreads);
+    const int nc = p.cout_pad < kMaxStatC ? p.cout_pad : kMaxStatC;
+    for (int i = e; i < nc; i += kEpiThreads) {
+      atomicAdd(p.stat_sum + i, (double)s_sum[i]);
+      atomicAdd(p.stat_sq + i, (double)s_sq[i]);
     }
+  }
 }
 
 template <int BN, int CK>
@@ -327,7 +391,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* pipe = smem;
   uint8_t* out_stage = smem + C::PIPE_BYTES;
-  float* s_scale = reinterpret_cast<float*>(out_stage + 2 * C::OUT_BYTES);
+  float* s_scale = reinterpret_cast<float*>(out_stage + C::OUT_BUFS * C::OUT_BYTES);
   float* s_shift = s_scale + BN;
   float* s_pool = s_shift + BN;
   float* s_sum = s_pool + BN;
@@ -348,11 +412,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], kEpiWarps);
     }
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_w);
-    tma_prefetch_desc(&p.tm_out[0]);
     tma_prefetch_desc(&p.tm_src[0]);
   }
   if (warp == 2) {
@@ -441,7 +504,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     // ------------------------------------------------------------------ epilogue (4 warps)
     StreamTiles it{t_begin, t_end, tiles_per_img};
     run_epilogue<BN, C::OCW, C::SUB, C::OUT_BYTES>(p, it, out_stage, s_scale, s_shift, s_pool, s_sum, s_sq, tfull_bar, tempty_bar,
-                                                   tmem_base, warp, lane);
+                                                   warp, lane);
   }
 
   tc_fence_before();
@@ -463,12 +526,12 @@ template <int BN, int CK>
 struct HaloCfg {
   static constexpr int OCW = BN < 64 ? BN : 64;
   static constexpr int SUB = OCW < 32 ? OCW : 32;
+  static constexpr int OUT_BYTES = 128 * OCW * 2;
   static constexpr int ROWB = CK * 2;                                       // bytes per halo pixel row (one swizzle span)
   static constexpr int HALO_TX = 18 * 10 * ROWB;
   static constexpr int HALO_BYTES = ((HALO_TX + 1023) / 1024) * 1024;       // 23 KB at CK = 64
   static constexpr int WSLOT_BYTES = BN * ROWB;
   static constexpr uint32_t LAYOUT = CK == 64 ? kLayoutSW128 : (CK == 32 ? kLayoutSW64 : kLayoutSW32);
-  static constexpr int OUT_BYTES = 128 * OCW * 2;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int AUX_FLOATS = 3 * BN + 2 * kMaxStatC;
   static constexpr int MAX_STAGES = 6;
@@ -503,12 +566,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], kEpiWarps);
     }
     mbar_init(wfull_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_w);
-    tma_prefetch_desc(&p.tm_out[0]);
     tma_prefetch_desc(&p.tm_src[0]);
   }
   if (warp == 2) {
@@ -595,7 +657,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
     }
   } else {
     run_epilogue<BN, C::OCW, C::SUB, C::OUT_BYTES>(p, it, out_stage, s_scale, s_shift, s_pool, s_sum, s_sq, tfull_bar, tempty_bar,
-                                                   tmem_base, warp, lane);
+                                                   warp, lane);
   }
 
   tc_fence_before();
@@ -660,7 +722,9 @@ static int launch_tc(const ConvTcParams& p, cudaStream_t stream) {
     configured = true;
   }
   long long grid = p.total_tiles < (long long)num_sms() ? p.total_tiles : (long long)num_sms();
-  conv_tc_kernel<BN, CK><<<(unsigned)grid, kNumThreads, C::SMEM_BYTES, stream>>>(p);
+  ConvTcParams q = p;
+  q.out_bufs = C::OUT_BUFS;
+  conv_tc_kernel<BN, CK><<<(unsigned)grid, kNumThreads, C::SMEM_BYTES, stream>>>(q);
   return check_launch("conv_tc");
 }
 
@@ -763,6 +827,9 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
     bn = halo_bn;
     p.bh = 16;
     p.bw = 8;
+  } else if (d->pool2_out.ptr) {
+    p.bw = 8;  // the fused max-pool finds its window partners with lane shuffles: power-of-two tile width
+    p.bh = 16;
   } else {
     choose_tile(o.h, o.w, &p.bh, &p.bw);
   }
@@ -817,24 +884,52 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
                           swz_in)) != PMOE_OK)
       return rc;
   }
+  auto view_ok = [&](const PmoeView4& v, int esz) {
+    return v.ptr && !((uintptr_t)v.ptr & 15) && (v.sw * esz) % 16 == 0 && (v.sh * esz) % 16 == 0 && (v.sn * esz) % 16 == 0;
+  };
+  auto view_a32 = [&](const PmoeView4& v) { return !((uintptr_t)v.ptr & 31) && v.sw % 16 == 0 && v.sh % 16 == 0 && v.sn % 16 == 0; };
   const int ocw = bn < 64 ? bn : 64;
   if ((rc = make_view_tmap(&p.tm_out[0], o, ocw, p.bw, p.bh, swizzle_for_bytes(ocw * 2), "conv_tc output")) != PMOE_OK) return rc;
+  p.out_c = o.c;
+  p.out_bufs = 2;
   if (d->n_out_extra > 0) {
     // multi-view launch: GEMM column n lands in view n / out_cols at channel n % out_cols
     if (d->n_out_extra > 3 || d->out_cols <= 0 || d->out_cols % ocw != 0 || d->cout_pad != d->out_cols * (d->n_out_extra + 1) ||
-        d->residual.ptr || d->stat_sum || d->pool_sum || halo_bn) {
+        d->residual.ptr || d->stat_sum || d->pool_sum || d->pool2_out.ptr || d->nchw_out || halo_bn) {
       set_error("conv_tc: bad multi-view output (n_out_extra %d out_cols %d cout_pad %d)", d->n_out_extra, d->out_cols, d->cout_pad);
       return PMOE_ERR_ARG;
     }
     for (int i = 0; i < d->n_out_extra; ++i) {
       const PmoeView4& e = d->out_extra[i];
-      if (e.n != o.n || e.h != o.h || e.w != o.w) {
-        set_error("conv_tc: extra output view %d does not match the geometry of out", i);
+      if (e.n != o.n || e.h != o.h || e.w != o.w || e.c != o.c) {
+        set_error("conv_tc: extra output view %d does not match out", i);
         return PMOE_ERR_ARG;
       }
       if ((rc = make_view_tmap(&p.tm_out[i + 1], e, ocw, p.bw, p.bh, swizzle_for_bytes(ocw * 2), "conv_tc extra output")) != PMOE_OK) return rc;
     }
     p.out_cols = d->out_cols;
+  }
+  if (d->pool2_out.ptr) {
+    const PmoeView4& q = d->pool2_out;
+    const bool pow2 = p.bw == 2 || p.bw == 4 || p.bw == 8 || p.bw == 16;
+    if (!pow2 || (p.bh & 1) || (o.h & 1) || (o.w & 1) || q.n != o.n || q.h != o.h / 2 || q.w != o.w / 2 || q.c < o.c || !view_ok(q, 2)) {
+      set_error("conv_tc: fused 2x2 max-pool needs even H/W, a (n, H/2, W/2, >=c) view and a power-of-two tile width (bw %d bh %d)", p.bw, p.bh);
+      return PMOE_ERR_UNSUPPORTED;
+    }
+    p.pool2_ptr = static_cast<__nv_bfloat16*>(q.ptr);
+    p.pool2_sn = q.sn;
+    p.pool2_sh = q.sh;
+    p.pool2_sw = q.sw;
+    p.pool2_align32 = view_a32(q) && o.c % 16 == 0;
+    (void)view_ok;
+  }
+  if (d->nchw_out) {
+    p.nchw_ptr = d->nchw_out;
+    p.nchw_sn = d->nchw_sn;
+    p.nchw_sc = d->nchw_sc;
+    p.nchw_sh = d->nchw_sh;
+    p.nchw_sw = d->nchw_sw;
+    p.nchw_c = d->nchw_c;
   }
   p.scale = d->scale;
   p.shift = d->shift;
@@ -855,7 +950,6 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   p.stat_sq = d->stat_sqsum;
   p.pool_sum = d->pool_sum;
   p.cout_pad = d->cout_pad;
-  p.out_bufs = 2;
   p.pool_stride = d->pool_stride > 0 ? d->pool_stride : d->cout_pad;
   if (halo_bn) {
     int g = 0;
@@ -870,12 +964,12 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
     p.n_chunks = total_chunks;
     p.w_slots = 9 * total_chunks;
     p.m_tiles = (long long)p.tiles_w * p.tiles_h * p.n_img;
-    const int ocw = halo_bn < 64 ? halo_bn : 64;
     const int wbytes = ((p.w_slots * halo_bn * d->ck * 2 + 1023) / 1024) * 1024;  // halo stages stay 1 KB aligned
     const int halo_bytes = ((18 * 10 * d->ck * 2 + 1023) / 1024) * 1024;
+    const int ocw_h = halo_bn < 64 ? halo_bn : 64;
     int fixed = 0, stages = 0;
     for (p.out_bufs = 2; p.out_bufs >= 1; --p.out_bufs) {
-      fixed = 1024 + p.out_bufs * 128 * ocw * 2 + (3 * halo_bn + 2 * kMaxStatC) * 4 + (2 * 6 + 5) * 8 + 16;
+      fixed = 1024 + p.out_bufs * 128 * ocw_h * 2 + (3 * halo_bn + 2 * kMaxStatC) * 4 + (2 * 6 + 5) * 8 + 16;
       stages = (227 * 1024 - fixed - wbytes) / halo_bytes;
       if (stages >= 3 || p.out_bufs == 1) break;
     }

@@ -329,6 +329,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(V4 src, V4 dst, const f
   float sc[8], sf[8];
   load8(scale + g * 8, sc);
   load8(shift + g * 8, sf);
+#pragma unroll 2
   for (long long i = first; i < total; i += stride) {
     long long o_s, o_d, o_r;
     if (FLAT) {

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(BV4 dz, BV4 
       m[q] = mean ? __ldg(mean + g * 8 + q) : 0.f;
       r[q] = rstd ? __ldg(rstd + g * 8 + q) : 1.f;
     }
+#pragma unroll 4
     for (long long p = p0 + lane; p < p1; p += lanes) {
       long long o_dz, o_z, o_x;
       if (FLAT) {
@@ -113,8 +114,13 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(BV4 dz, BV4 
       if (act != PMOE_ACT_NONE) {
         float zv[8];
         bload8(static_cast<const T*>(z.ptr) + o_z, zv);
+        if (act == PMOE_ACT_RELU) {  // uniform branch hoisted out of the element loop (a per-element switch is ~10x the code)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) d[q] *= act_grad(zv[q], act);
+          for (int q = 0; q < 8; ++q) d[q] = zv[q] > 0.f ? d[q] : 0.f;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) d[q] *= act_grad(zv[q], act);
+        }
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) a[q] += d[q];
@@ -170,6 +176,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BV4 dz, BV4 z, BV4 x,
       kr[q] = km[q] = c1[q] = c2[q] = 0.f;
     }
   }
+#pragma unroll 2
   for (long long i = first; i < total; i += stride) {
     long long o_dz, o_z, o_x, o_dx, o_dr;
     if (FLAT) {
@@ -191,8 +198,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BV4 dz, BV4 z, BV4 x,
     if (act != PMOE_ACT_NONE) {
       float zv[8];
       bload8(static_cast<const T*>(z.ptr) + o_z, zv);
+      if (act == PMOE_ACT_RELU) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) d[q] *= act_grad(zv[q], act);
+        for (int q = 0; q < 8; ++q) d[q] = zv[q] > 0.f ? d[q] : 0.f;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) d[q] *= act_grad(zv[q], act);
+      }
     }
     if (dres.ptr) {
       float o[8];
@@ -324,7 +336,7 @@ __global__ void maxpool_bwd_idx_kernel(BV4 dy, const uint8_t* __restrict__ idx, 
 // ---------------------------------------------------------------- ECA backward
 // out = x * gate[n,c]. pass 1: dgate[n,c] = sum_hw dout*x (per-image channel sums of a product)
 template <typename T>
-__global__ void __launch_bounds__(kRedThreads) prod_channel_sums_kernel(BV4 a, BV4 b, float* __restrict__ out, long long out_stride, int rows_per_block) {
+__global__ void __launch_bounds__(kRedThreads) prod_channel_sums_kernel(BV4 a, BV4 b, double* __restrict__ out, long long out_stride, int rows_per_block) {
   __shared__ float sm[kRedThreads * 8];
   const int cg = a.c / 8;
   const int lanes = blockDim.x / cg;
@@ -350,46 +362,48 @@ __global__ void __launch_bounds__(kRedThreads) prod_channel_sums_kernel(BV4 a, B
 #pragma unroll
   for (int j = 0; j < kRedMaxIter; ++j) {
     const int c = threadIdx.x + j * kRedThreads;
-    if (c < cg * 8 && tot[j] != 0.f) atomicAdd(out + n * out_stride + c, tot[j]);
+    if (c < cg * 8 && tot[j] != 0.f) atomicAdd(out + n * out_stride + c, (double)tot[j]);  // cross-block sum in fp64
   }
 }
 
 // tiny: gate = sigmoid(pre), pre = conv1d(mean). dpre = dgate*gate*(1-gate); dmean = corr(dpre, w) / count;
 // dw[t] += sum_{n,l} dpre[n,l] * mean[n, l+t-k/2]
-__global__ void eca_gate_bwd_kernel(const float* __restrict__ dgate, long long dgate_stride, const float* __restrict__ gate,
+// The ECA gate sits in front of a BatchNorm, which cancels a common channel scale: dgate and dw are small remainders of
+// large cancelling sums, so this (tiny) kernel keeps them in fp64.
+__global__ void eca_gate_bwd_kernel(const double* __restrict__ dgate, long long dgate_stride, const float* __restrict__ gate,
                                     long long gate_stride, const float* __restrict__ pool_sum, long long pool_stride,
                                     float inv_count, const float* __restrict__ w, int k, int groups, int group_c,
                                     int group_stride, float* __restrict__ dmean, long long dmean_stride,
-                                    float* __restrict__ dw) {
+                                    double* __restrict__ dw) {
   const int n = blockIdx.x;
   const int L = groups * group_c;
-  extern __shared__ float s_dpre[];  // L entries
+  extern __shared__ double s_dpre[];  // L entries
   for (int l = threadIdx.x; l < L; l += blockDim.x) {
     const int p = (l / group_c) * group_stride + (l % group_c);
-    const float gt = gate[n * gate_stride + p];
-    s_dpre[l] = dgate[n * dgate_stride + p] * gt * (1.f - gt);
+    const double gt = (double)gate[n * gate_stride + p];
+    s_dpre[l] = dgate[n * dgate_stride + p] * gt * (1.0 - gt);
   }
   __syncthreads();
   for (int pc = threadIdx.x; pc < groups * group_stride; pc += blockDim.x) {
     const int g = pc / group_stride, j = pc % group_stride;
-    float acc = 0.f;
+    double acc = 0.0;
     if (j < group_c) {
       const int l = g * group_c + j;  // d mean[l] = sum_t w[t] * dpre[l - t + k/2]
       for (int t = 0; t < k; ++t) {
         const int lo = l - t + k / 2;
-        if (lo >= 0 && lo < L) acc = fmaf(w[t], s_dpre[lo], acc);
+        if (lo >= 0 && lo < L) acc += (double)w[t] * s_dpre[lo];
       }
     }
-    dmean[n * dmean_stride + pc] = acc * inv_count;
+    dmean[n * dmean_stride + pc] = (float)(acc * (double)inv_count);
   }
   if (dw) {
     for (int t = threadIdx.x; t < k; t += blockDim.x) {
-      float acc = 0.f;
+      double acc = 0.0;
       for (int l = 0; l < L; ++l) {
         const int ll = l + t - k / 2;
         if (ll >= 0 && ll < L) {
           const int p = (ll / group_c) * group_stride + (ll % group_c);
-          acc = fmaf(s_dpre[l], pool_sum[n * pool_stride + p] * inv_count, acc);
+          acc += s_dpre[l] * ((double)pool_sum[n * pool_stride + p] * (double)inv_count);
         }
       }
       atomicAdd(dw + t, acc);
@@ -585,7 +599,7 @@ int pmoe_maxpool_bwd_idx(const PmoeView4* dy, const uint8_t* idx, const PmoeView
   return check_launch("maxpool_bwd_idx");
 }
 
-int pmoe_prod_channel_sums(const PmoeView4* a, const PmoeView4* b, int32_t dtype, float* out, int64_t out_stride,
+int pmoe_prod_channel_sums(const PmoeView4* a, const PmoeView4* b, int32_t dtype, double* out, int64_t out_stride,
                            pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc;
@@ -602,16 +616,16 @@ int pmoe_prod_channel_sums(const PmoeView4* a, const PmoeView4* b, int32_t dtype
   return check_launch("prod_channel_sums");
 }
 
-int pmoe_eca_gate_bwd(const float* dgate, int64_t dgate_stride, const float* gate, int64_t gate_stride, const float* pool_sum,
+int pmoe_eca_gate_bwd(const double* dgate, int64_t dgate_stride, const float* gate, int64_t gate_stride, const float* pool_sum,
                       int64_t pool_stride, int32_t n, float inv_count, const float* w, int32_t k, int32_t groups,
-                      int32_t group_c, int32_t group_stride, float* dmean, int64_t dmean_stride, float* dw,
+                      int32_t group_c, int32_t group_stride, float* dmean, int64_t dmean_stride, double* dw,
                       pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!dgate || !gate || !pool_sum || !w || !dmean || n < 1) {
     set_error("eca_gate_bwd: bad arguments");
     return PMOE_ERR_ARG;
   }
-  eca_gate_bwd_kernel<<<n, 128, groups * group_c * sizeof(float), stream>>>(dgate, dgate_stride, gate, gate_stride, pool_sum,
+  eca_gate_bwd_kernel<<<n, 128, groups * group_c * sizeof(double), stream>>>(dgate, dgate_stride, gate, gate_stride, pool_sum,
                                                                             pool_stride, inv_count, w, k, groups, group_c,
                                                                             group_stride, dmean, dmean_stride, dw);
   return check_launch("eca_gate_bwd");

@@ -74,18 +74,18 @@ __global__ void __launch_bounds__(256) mt_scale_kernel(const MtChunk* __restrict
 }
 
 struct AdamArgs {
-  float lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2_sqrt, max_norm;
+  float step_size, beta1, beta2, om_beta1, om_beta2, eps, weight_decay, bias_c2_sqrt, max_norm;
   int amsgrad;
 };
 
 template <bool VEC>
 __device__ __forceinline__ void adam_chunk(const MtChunk& ch, const AdamArgs& a, float coef) {
-  const float step_size = a.lr / a.bias_c1;
+  const float step_size = a.step_size;
   auto upd = [&](float& p, float g, float& m, float& v, float& vm) {
     g *= coef;
     if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);
-    m = m + (g - m) * (1.f - a.beta1);                 // exp_avg.lerp_(grad, 1 - beta1)
-    v = fmaf(g * g, 1.f - a.beta2, v * a.beta2);       // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    m = m + (g - m) * a.om_beta1;                   // exp_avg.lerp_(grad, 1 - beta1)
+    v = fmaf(g * g, a.om_beta2, v * a.beta2);       // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
     float vv = v;
     if (a.amsgrad) {
       vm = fmaxf(vm, v);
@@ -170,8 +170,8 @@ extern "C" int pmoe_mt_clip(const PmoeMtChunk* chunks_dev, int32_t n_chunks, con
   return check_launch("mt_clip");
 }
 
-extern "C" int pmoe_mt_adam(const PmoeMtChunk* chunks_dev, int32_t n_chunks, float lr, float beta1, float beta2, float eps,
-                            float weight_decay, int32_t step, int32_t amsgrad, const double* sqnorm, float max_norm,
+extern "C" int pmoe_mt_adam(const PmoeMtChunk* chunks_dev, int32_t n_chunks, double lr, double beta1, double beta2, double eps,
+                            double weight_decay, int32_t step, int32_t amsgrad, const double* sqnorm, float max_norm,
                             pmoe_stream_t stream_) {
   if (n_chunks <= 0) return PMOE_OK;
   if (!chunks_dev || step < 1) {
@@ -179,13 +179,16 @@ extern "C" int pmoe_mt_adam(const PmoeMtChunk* chunks_dev, int32_t n_chunks, flo
     return PMOE_ERR_ARG;
   }
   AdamArgs a;
-  a.lr = lr;
-  a.beta1 = beta1;
-  a.beta2 = beta2;
-  a.eps = eps;
-  a.weight_decay = weight_decay;
-  a.bias_c1 = (float)(1.0 - pow((double)beta1, (double)step));
-  a.bias_c2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  // hyper-parameters arrive as doubles (Python floats) and are rounded once, like torch's scalar arguments:
+  // float(1 - 0.999) is 0.001f, while 1.f - 0.999f is 1.3e-5 off it
+  a.beta1 = (float)beta1;
+  a.beta2 = (float)beta2;
+  a.om_beta1 = (float)(1.0 - beta1);
+  a.om_beta2 = (float)(1.0 - beta2);
+  a.eps = (float)eps;
+  a.weight_decay = (float)weight_decay;
+  a.step_size = (float)(lr / (1.0 - pow(beta1, (double)step)));
+  a.bias_c2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
   a.max_norm = sqnorm ? max_norm : 0.f;
   a.amsgrad = amsgrad;
   mt_adam_kernel<<<mt_grid(n_chunks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(reinterpret_cast<const MtChunk*>(chunks_dev),

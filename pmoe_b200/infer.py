@@ -54,7 +54,12 @@ def padded_bias(mod, cout_pad):
 
 
 # ------------------------------------------------------------------------------- layers
-def conv_eval(srcs, conv, bn=None, act=None, out=None, residual=None, pool=None, pool_stride=0, groups=None, ksize=3):
+def _tc():
+    return config.precision() == "bf16" and not config.FORCE_SIMT
+
+
+def conv_eval(srcs, conv, bn=None, act=None, out=None, residual=None, pool=None, pool_stride=0, groups=None, ksize=3,
+              pool2=False):
     """srcs: list of Act (virtual concat along channels). groups: optional [(logical, padded)] layout of
     the channel axis when one physical source carries several padded groups (the PU-Net mask ring)."""
     cout = conv.weight.shape[0]
@@ -81,16 +86,23 @@ def conv_eval(srcs, conv, bn=None, act=None, out=None, residual=None, pool=None,
     n, h, w, _ = srcs[0].t.shape
     if out is None:
         out = torch.empty(n, h, w, pad_ch(cout), dtype=config.act_dtype(), device=srcs[0].t.device)
+    pooled = None
+    kw = {}
+    if pool2 and _tc():  # MaxPool2d(2,2) of this output rides the conv epilogue (unet.py:29)
+        pooled = torch.empty(n, h // 2, w // 2, out.shape[3], dtype=out.dtype, device=out.device)
+        kw["pool2_out"] = pooled
     ops.conv([a.t for a in srcs], wp, segs, ck, out, scale=scale, shift=shift, act=act,
              residual=None if residual is None else residual.t, pool_sum=pool, pool_stride=pool_stride,
-                flops=2.0 * n * h * w * cout * sum(glog) * len(taps), tag="%dx%d %d->%d k%d" % (h, w, sum(glog), cout, ksize))
+             flops=2.0 * n * h * w * cout * sum(glog) * len(taps), tag="%dx%d %d->%d k%d" % (h, w, sum(glog), cout, ksize), **kw)
+    if pool2:
+        return Act(out, cout), (Act(pooled, cout) if pooled is not None else nhwc.maxpool(Act(out, cout), 2, 2, 0))
     return Act(out, cout)
 
 
-def conv3_block_eval(seq, srcs, pool=None):
-    """conv3 (basics.py:48-59) in eval mode: two fused conv+BN+ReLU launches."""
+def conv3_block_eval(seq, srcs, pool=None, pool2=False):
+    """conv3 (basics.py:48-59) in eval mode: two fused conv+BN+ReLU launches; pool2 also returns MaxPool2d(2,2)(out)."""
     y = conv_eval(srcs, seq[0], seq[1], "relu")
-    return conv_eval([y], seq[3], seq[4], "relu", pool=pool)
+    return conv_eval([y], seq[3], seq[4], "relu", pool=pool, pool2=pool2)
 
 
 def conv_transpose_eval(up, x):
@@ -119,20 +131,20 @@ def conv_transpose_eval(up, x):
     return Act(out, cout)
 
 
-def unet_eval(net, x, out=None, out_pool=None, pool_stride=0, want_inter=False):
+def unet_eval(net, x, out=None, out_pool=None, pool_stride=0, want_inter=False, nchw_out=None):
     """UNet.forward (unet.py:50-95) in eval mode. x: Act (N,H,W,16). Logits go to `out` (NHWC bf16
     view with >= 32 channels) if given. Returns (Act logits, inter or None)."""
     n, h, w, _ = x.t.shape
     if h % 16 or w % 16:
         raise RuntimeError("pmoe_b200 UNet needs H and W divisible by 16 (got %dx%d)" % (h, w))
-    x1 = conv3_block_eval(net.dwn_1, [x])
-    x2 = conv3_block_eval(net.dwn_2, [nhwc.maxpool(x1, 2, 2, 0)])
-    x3 = conv3_block_eval(net.dwn_3, [nhwc.maxpool(x2, 2, 2, 0)])
-    x4 = conv3_block_eval(net.dwn_4, [nhwc.maxpool(x3, 2, 2, 0)])
+    x1, p1 = conv3_block_eval(net.dwn_1, [x], pool2=True)
+    x2, p2 = conv3_block_eval(net.dwn_2, [p1], pool2=True)
+    x3, p3 = conv3_block_eval(net.dwn_3, [p2], pool2=True)
+    x4, p4 = conv3_block_eval(net.dwn_4, [p3], pool2=True)
     inter_sum = None
     if want_inter:
         inter_sum = torch.zeros(n, 512, dtype=torch.float32, device=x.t.device)
-    x5 = conv3_block_eval(net.dwn_5, [nhwc.maxpool(x4, 2, 2, 0)], pool=inter_sum)
+    x5 = conv3_block_eval(net.dwn_5, [p4], pool=inter_sum)
     y = x5
     for up, fwd, skip in ((net.up_1, net.up_forw_1, x4), (net.up_2, net.up_forw_2, x3), (net.up_3, net.up_forw_3, x2),
                           (net.up_4, net.up_forw_4, x1)):
@@ -143,8 +155,11 @@ def unet_eval(net, x, out=None, out_pool=None, pool_stride=0, want_inter=False):
     wp = packed_conv(net.out, [64], [64], [(0, 0)], cop)
     if out is None:
         out = torch.empty(n, h, w, pad_ch(ncls), dtype=config.act_dtype(), device=x.t.device)
+    kw = {"nchw_out": nchw_out} if (nchw_out is not None and _tc()) else {}
     ops.conv([y.t], wp, ops.conv_segments([(0, 0)], [64], 64), 64, out, shift=padded_bias(net.out, cop), pool_sum=out_pool,
-             pool_stride=pool_stride, flops=2.0 * n * h * w * 64 * ncls, tag="out1x1 %dx%d" % (h, w))
+             pool_stride=pool_stride, flops=2.0 * n * h * w * 64 * ncls, tag="out1x1 %dx%d" % (h, w), **kw)
+    if nchw_out is not None and not kw:
+        nhwc.to_nchw(out, ncls, out=nchw_out)
     inter = None
     if want_inter:
         inter = inter_sum / float(x5.t.shape[1] * x5.t.shape[2])
@@ -192,14 +207,14 @@ def punet_eval(net, images):
         if net.unet_inter_repr:
             return inter
         return nhwc.to_nchw(ring[..., (P - 1) * slot:P * slot], ncls)
+    out = None if net.inter_repr else torch.empty(B, Fu, ncls, H, W, dtype=torch.float32, device=dev)
     for f in range(Fu):
         window = ring[..., f * slot:(f + P) * slot]
         m = eca_conv_block_eval(net.entry_block, window, (P, ncls, slot), pools[:, f * slot:(f + P) * slot], H * W)
+        # the fp32 NCHW logits the module returns are written by the same epilogue that fills the ring slot
         _, inter = unet_eval(net.pred_unet, m, out=ring[..., (P + f) * slot:(P + f + 1) * slot],
-                             out_pool=pools[:, (P + f) * slot:], pool_stride=nslots * slot, want_inter=net.inter_repr)
+                             out_pool=pools[:, (P + f) * slot:], pool_stride=nslots * slot, want_inter=net.inter_repr,
+                             nchw_out=None if out is None else out[:, f])
     if net.inter_repr:
         return inter
-    out = torch.empty(B, Fu, ncls, H, W, dtype=torch.float32, device=dev)
-    for f in range(Fu):
-        nhwc.to_nchw(ring[..., (P + f) * slot:(P + f + 1) * slot], ncls, out=out[:, f])
     return out

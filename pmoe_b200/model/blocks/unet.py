@@ -29,8 +29,9 @@ class UNet(nn.Module):
         if _grad_mode(self):
             return train.unet_module_forward(self, image)
         x = nhwc.from_nchw(image, dtype=config.act_dtype())
-        logits, inter = infer.unet_eval(self, x, want_inter=self.inter_repr)
-        out = nhwc.to_nchw(logits.t, logits.c)
+        n, _, h, w = image.shape
+        out = torch.empty(n, self.out.weight.shape[0], h, w, dtype=torch.float32, device=image.device)
+        _, inter = infer.unet_eval(self, x, want_inter=self.inter_repr, nchw_out=out)
         if self.inter_repr:
             return inter, out
         return out

@@ -91,7 +91,7 @@ def pad_vec(v, n, fill=0.0):
 
 
 def _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum, stat_sqsum, pool_sum, src_channels,
-               pool_stride, dtype, out_extra=None, out_cols=0):
+               pool_stride, dtype, out_extra=None, out_cols=0, pool2_out=None, nchw_out=None):
     d = _lib.ConvTc()
     assert 1 <= len(srcs) <= _lib.MAX_SRC and 1 <= len(segs) <= _lib.MAX_SEG, (len(srcs), len(segs))
     d.n_src = len(srcs)
@@ -124,16 +124,26 @@ def _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum
         for i, t in enumerate(out_extra):
             assert t.dtype == dtype
             d.out_extra[i] = _lib.view4(t)
+    if pool2_out is not None:
+        assert pool2_out.dtype == dtype
+        d.pool2_out = _lib.view4(pool2_out)
+    if nchw_out is not None:  # fp32 (N, C, H, W) tensor/view
+        assert nchw_out.dtype == torch.float32 and nchw_out.dim() == 4
+        d.nchw_out = nchw_out.data_ptr()
+        d.nchw_sn, d.nchw_sc, d.nchw_sh, d.nchw_sw = nchw_out.stride()
+        d.nchw_c = nchw_out.shape[1]
     return d
 
 
 def conv_tc(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residual=None, stat_sum=None,
-            stat_sqsum=None, pool_sum=None, src_channels=None, pool_stride=0, flops=0.0, tag="", out_extra=None, out_cols=0):
+            stat_sqsum=None, pool_sum=None, src_channels=None, pool_stride=0, flops=0.0, tag="", out_extra=None, out_cols=0,
+            pool2_out=None, nchw_out=None):
     """Launch the tcgen05 implicit-GEMM kernel. srcs: list of NHWC bf16 tensors (views allowed);
-    out: NHWC bf16 tensor/view; wpack: [cout_pad, ktot] bf16."""
+    out: NHWC bf16 tensor/view; wpack: [cout_pad, ktot] bf16. pool2_out: optional fused MaxPool2d(2,2) of the output;
+    nchw_out: optional fp32 NCHW copy of the first channels."""
     assert wpack.dtype == torch.bfloat16
     d = _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum, stat_sqsum, pool_sum, src_channels,
-                   pool_stride, torch.bfloat16, out_extra, out_cols)
+                   pool_stride, torch.bfloat16, out_extra, out_cols, pool2_out, nchw_out)
     fn = _lib.lib().pmoe_conv_tc
     sp = _lib.stream_ptr()
     _lib.check(profiler.launch("conv_tc", lambda: fn(C.byref(d), sp), flops, 0.0, tag), "conv_tc")
@@ -141,10 +151,12 @@ def conv_tc(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residu
 
 
 def conv_simt(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, residual=None, stat_sum=None,
-              stat_sqsum=None, pool_sum=None, src_channels=None, pool_stride=0, flops=0.0, tag="", out_extra=None, out_cols=0):
+              stat_sqsum=None, pool_sum=None, src_channels=None, pool_stride=0, flops=0.0, tag="", out_extra=None, out_cols=0,
+              pool2_out=None, nchw_out=None):
     """CUDA-core twin of conv_tc (fp32 or bf16 storage, fp32 FMA accumulation)."""
     dt = out.dtype
     assert wpack.dtype == dt
+    assert pool2_out is None and nchw_out is None, "fused pool / NCHW copy are tensor-core-kernel features"
     if out_extra:
         # multi-view outputs are a tensor-core-kernel feature: one launch per view here
         cols = int(out_cols)

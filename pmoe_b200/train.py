@@ -513,12 +513,12 @@ def eca_op(tape, eca_mod, x, layout=None, pool_in=None):
             dy = tape.grad_of(ya)
             if dy is None:
                 return
-            dgate = torch.zeros(n, cp, dtype=torch.float32, device=dy.device)
+            dgate = torch.zeros(n, cp, dtype=torch.float64, device=dy.device)  # cancelling sums: kept in fp64
             va, vb = view4(dy), view4(x.t)
             check(profiler.launch("prod_channel_sums", lambda: lib().pmoe_prod_channel_sums(
                 C.byref(va), C.byref(vb), dtype_code(dy), dgate.data_ptr(), dgate.stride(0), stream_ptr())), "prod_channel_sums")
             dmean = torch.empty(n, cp, dtype=torch.float32, device=dy.device)
-            dw = torch.zeros(w.numel(), dtype=torch.float32, device=dy.device)
+            dw = torch.zeros(w.numel(), dtype=torch.float64, device=dy.device)
             wf = w.detach().reshape(-1)
             check(profiler.launch("eca_gate_bwd", lambda: lib().pmoe_eca_gate_bwd(
                 dgate.data_ptr(), dgate.stride(0), gate.data_ptr(), gate.stride(0), sums.data_ptr(), sums.stride(0), n,

@@ -121,6 +121,8 @@ def test_moe_fp32_vs_reference_golden(mtype):
     mc, mp = sorted(gc.values())[len(gc) // 2], sorted(gp.values())[len(gp) // 2]
     print("   vs fp64 oracle: grads median cuda %.2e / cpu-fp32 %.2e | worst cuda %.2e (%s) / cpu-fp32 %.2e (%s)"
           % (mc, mp, wc, max(gc, key=gc.get), wp, max(gp, key=gp.get)))
+    for nm in sorted(gc, key=gc.get, reverse=True)[:4]:
+        print("      %-52s cuda %.2e  cpu-fp32 %.2e  |g| %.2e" % (nm, gc[nm], gp[nm], sd64[nm].grad.norm().item()))
     assert mc < max(4 * mp, 1e-4) and wc < 6 * wp + 1e-3  # typical gradient within north_star's 1e-4; worst within the reference's own noise
     assert bn_err < 1e-4
     if mtype != "moe_shared":

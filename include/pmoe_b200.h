@@ -89,6 +89,11 @@ typedef struct PmoeConvTc {
 } PmoeConvTc;
 
 int pmoe_conv_tc(const PmoeConvTc* desc, pmoe_stream_t stream);
+/* Tuning aid: when set (device array of 16 x #CTAs uint64, zeroed by the caller), every pmoe_conv_tc launch records per-CTA
+ * cycle counters: [0] producer waits for a free stage, [1] MMA waits for TMA data, [2] MMA waits for a free accumulator,
+ * [3] MMA thread total, [4] epilogue waits for the accumulator, [5] epilogue total, [6] epilogue waits for its staging
+ * buffer, [7] tiles. NULL switches it off (the default). */
+int pmoe_conv_tc_set_debug(unsigned long long* counters_dev);
 
 /* Same contract as pmoe_conv_tc on CUDA cores with fp32 FMA accumulation; dtype selects fp32 (the
  * <=1e-4 parity mode: activations, wpack and out are float) or bf16 storage. */

@@ -4,6 +4,7 @@ import ctypes as C
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 SIGS = {
+    "pmoe_conv_tc_set_debug": [vp],
     "pmoe_nchw_to_nhwc": [vp, i64, i64, i64, i64, i32, vp, i32, vp],
     "pmoe_nhwc_to_nchw": [vp, i32, i32, vp, i64, i64, i64, i64, vp],
     "pmoe_maxpool": [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp],

@@ -63,6 +63,26 @@ struct alignas(64) ConvTcParams {
   // resident-weight ("halo") variant
   int halo_stages, w_slots, n_chunks, w_bytes;
   long long m_tiles;
+  int feat;                 // compile-time epilogue variant to use (-1 = generic)
+  unsigned long long* dbg;  // optional per-CTA cycle counters (pmoe_conv_tc_set_debug): who waits for whom
+};
+
+// cycle accounting for tuning (8 counters per CTA): 0 producer waits for a free stage, 1 MMA waits for TMA data,
+// 2 MMA waits for a free accumulator (= epilogue too slow), 3 MMA thread total, 4 epilogue waits for the accumulator
+// (= main loop too slow), 5 epilogue total, 6 epilogue waits for its staging buffer (TMA store drain), 7 tiles.
+constexpr int kDbgSlots = 16;  // counters per CTA; 8..12: epilogue phases (barrier 1, TMEM load, math+staging, fence+barrier 2, store issue)
+struct DbgClock {
+  unsigned long long* base;
+  long long acc[8];
+  __device__ __forceinline__ DbgClock(unsigned long long* b) : base(b), acc{0, 0, 0, 0, 0, 0, 0, 0} {}
+  __device__ __forceinline__ long long now() const { return base ? clock64() : 0; }
+  __device__ __forceinline__ void add(int i, long long t0) {
+    if (base) acc[i] += clock64() - t0;
+  }
+  __device__ __forceinline__ void flush(int slot0, int n) {
+    if (base)
+      for (int i = 0; i < n; ++i) base[blockIdx.x * kDbgSlots + slot0 + i] = (unsigned long long)acc[i];
+  }
 };
 
 constexpr int kMaxStatC = 512;
@@ -73,7 +93,7 @@ constexpr int kNumThreads = 64 + kEpiThreads;
 template <int BN, int CK>
 struct TcCfg {
   static constexpr int OCW = BN < 64 ? BN : 64;   // channels per TMA store box
-  static constexpr int SUB = OCW < 32 ? OCW : 32; // columns per tcgen05.ld
+  static constexpr int SUB = OCW == 32 ? 16 : (OCW < 32 ? OCW : 32);  // columns per tcgen05.ld (32-wide chunks: one half per warp)
   static constexpr int A_BYTES = 128 * CK * 2;
   static constexpr int B_BYTES = BN * CK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -133,6 +153,7 @@ __device__ __forceinline__ float warp_col_sums(float (&v)[NC], int lane) {
 struct StreamTiles {
   long long t_begin, t_end;
   int tiles_per_img;
+  __device__ __forceinline__ int nt_last(const ConvTcParams& p) const { return (int)((t_end - 1) % p.tiles_n); }
   __device__ __forceinline__ bool get(const ConvTcParams& p, uint32_t iter, int& img, int& h0, int& w0, int& nt) const {
     const long long t = t_begin + iter;
     if (t >= t_end) return false;
@@ -145,12 +166,13 @@ struct StreamTiles {
     return true;
   }
 };
-struct ResidentTiles {
-  int nt_fixed, m_first, m_step, tiles_per_img;
-  long long m_tiles;
+struct ResidentTiles {  // a contiguous run of m-tiles per CTA: an image boundary is crossed at most a few times
+  int nt_fixed, tiles_per_img;
+  long long m_first, m_end;
+  __device__ __forceinline__ int nt_last(const ConvTcParams&) const { return nt_fixed; }
   __device__ __forceinline__ bool get(const ConvTcParams& p, uint32_t iter, int& img, int& h0, int& w0, int& nt) const {
-    const long long mt = (long long)m_first + (long long)iter * m_step;
-    if (mt >= m_tiles) return false;
+    const long long mt = m_first + (long long)iter;
+    if (mt >= m_end) return false;
     nt = nt_fixed;
     img = (int)(mt / tiles_per_img);
     const int rem = (int)(mt % tiles_per_img);
@@ -189,7 +211,12 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 // measured 2-2.5x slower than the bulk store on the write-heavy 224^2 layers. Optional extras ride on the registers: a
 // fused 2x2 max-pool (two warp shuffles: the window partners are lanes l^1 and l^bw), an fp32 NCHW copy at the module
 // boundary, BN batch statistics and per-image channel sums. Shared by both main-loop variants.
-template <int BN, int OCW, int SUB, int OUT_BYTES, class Iter>
+// FEAT < 0: every optional feature is a run-time flag (generic). FEAT >= 0: the feature set is fixed at compile time
+// (kFeatShift | kFeatRelu | kFeatStats | kFeatPool2; no scale / residual / other activations / NCHW copy / channel
+// sums), which turns the per-element path into straight-line code (~3 instead of ~11 instructions per element: the
+// epilogue, not the tensor core, was the limit of the 64-channel layers).
+constexpr int kFeatShift = 1, kFeatRelu = 2, kFeatStats = 4, kFeatPool2 = 8;
+template <int BN, int OCW, int SUB, int OUT_BYTES, int FEAT, class Iter>
 __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& it, uint8_t* out_stage, float* s_scale, float* s_shift,
                                              float* s_pool, float* s_sum, float* s_sq, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                              int warp, int lane) {
@@ -197,21 +224,52 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
   const int quad = warp & 3;              // TMEM lane quadrant this warp may read (warp id % 4)
   const int half = (warp - 2) >> 2;       // which of the quadrant's two warps
   const int row = quad * 32 + lane;       // accumulator row == pixel index inside the tile
+  // Two store issuers (one per staging buffer, in different warps): issuing a bulk tensor store costs its thread ~200
+  // cycles, which would otherwise serialise consecutive chunks.
   const bool issuer = (e == 0);
+  const bool issuer_b = (e == 128);
   const int ti = row / p.bw, tj = row % p.bw;
   const bool row_in_box = row < p.bw * p.bh;
   constexpr int ROWB = OCW * 2;
   constexpr uint32_t SWMASK = ROWB == 128 ? 7u : (ROWB == 64 ? 3u : 1u);
   constexpr int NSB = OCW / SUB;          // 32-column blocks per chunk: 2 (one per warp of the pair) or 1
   const bool worker = half < NSB;         // with a single block per chunk the second warp only keeps the barriers
-  const int act = p.act;
-  const bool has_scale = p.scale != nullptr, has_shift = p.shift != nullptr;
+  constexpr bool kGen = FEAT < 0;
+  const int act = kGen ? p.act : ((FEAT & kFeatRelu) ? PMOE_ACT_RELU : PMOE_ACT_NONE);
+  const bool has_scale = kGen && p.scale != nullptr;
+  const bool has_shift = kGen ? (p.shift != nullptr) : (FEAT & kFeatShift) != 0;
+  const bool has_stats = kGen ? (p.stat_sum != nullptr) : (FEAT & kFeatStats) != 0;
+  const bool has_pool2 = kGen ? (p.pool2_ptr != nullptr) : (FEAT & kFeatPool2) != 0;
+  const bool has_res = kGen && p.res != nullptr;
+  const bool has_nchw = kGen && p.nchw_ptr != nullptr;
+  const bool has_poolsum = kGen && p.pool_sum != nullptr;
   const uint32_t sc_addr = smem_u32(s_scale), sh_addr = smem_u32(s_shift);
   const bool pool_owner = ((ti | tj) & 1) == 0;  // this lane holds the top-left pixel of a 2x2 pooling window
+  // Per-image channel sums (ECA / avg-pool numerators): with one chunk per tile each thread keeps running sums of its own
+  // row in registers and reduces them across the warp only when the image changes (tiles of a CTA are contiguous).
+  const bool defer_pool = (BN / OCW) == 1 && !p.tiles_n_varies;
+  float psum[SUB];
+#pragma unroll
+  for (int k = 0; k < SUB; ++k) psum[k] = 0.f;
+  int pimg = -1;
+  auto flush_pool = [&](int image, int n0_) {
+    const float sa = warp_col_sums<SUB>(psum, lane);
+    if (lane < SUB && sa != 0.f) atomicAdd(p.pool_sum + (long long)image * p.pool_stride + n0_ + half * SUB + lane, sa);
+#pragma unroll
+    for (int k = 0; k < SUB; ++k) psum[k] = 0.f;
+  };
   uint32_t nstore = 0;
+  DbgClock dc(issuer ? p.dbg : nullptr);
+  const long long t_start = dc.now();
+  uint32_t ntiles = 0;
   int img, h0, w0, nt;
   for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
+    ++ntiles;
     const int n0 = nt * BN;
+    if (defer_pool && has_poolsum && worker && img != pimg) {
+      if (pimg >= 0) flush_pool(pimg, n0);
+      pimg = img;
+    }
     const int oh = h0 + ti, ow = w0 + tj;
     const bool valid = row_in_box && oh < p.H && ow < p.W;
     const uint32_t acc = titer & 1u;
@@ -224,20 +282,28 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
         if (has_shift) s_shift[i] = __ldg(p.shift + n0 + i);
       }
     }
+    const long long wt = dc.now();
     mbar_wait(&tfull_bar[acc], acc_phase);
+    dc.add(0, wt);
     tc_fence_after();
 
     const __nv_bfloat16* res_row = nullptr;
-    if (p.res != nullptr && valid) res_row = p.res + (long long)img * p.res_sn + (long long)oh * p.res_sh + (long long)ow * p.res_sw;
+    if (has_res && valid) res_row = p.res + (long long)img * p.res_sn + (long long)oh * p.res_sh + (long long)ow * p.res_sw;
 
 #pragma unroll 1
     for (int ch = 0; ch < BN / OCW; ++ch) {
-      uint8_t* obuf = out_stage + (p.out_bufs == 2 ? (nstore & 1u) : 0u) * OUT_BYTES;
-      if (issuer) {  // the store that last used this buffer has drained
-        if (p.out_bufs == 2) tma_store_wait_read<1>();
-        else tma_store_wait_read<0>();
+      const uint32_t buf = p.out_bufs == 2 ? (nstore & 1u) : 0u;
+      uint8_t* obuf = out_stage + buf * OUT_BYTES;
+      const bool my_store = buf == 0 ? issuer : issuer_b;
+      if (my_store) {  // the store that last used this buffer (always issued by this thread) has drained
+        const long long ws = dc.now();
+        tma_store_wait_read<0>();
+        dc.add(2, ws);
       }
+      const long long tb1 = dc.now();
       named_bar_sync(1, kEpiThreads);
+      dc.add(3, tb1);
+      const long long tld = dc.now();
       if (worker) {
         const int cb = ch * OCW + half * SUB;  // column offset inside the N tile
         uint32_t raw[SUB];
@@ -245,6 +311,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
         if constexpr (SUB == 32) tmem_ld_32x32(taddr, raw);
         else tmem_ld_32x16(taddr, raw);
         tmem_ld_wait();
+        dc.add(4, tld);
         float y[SUB];
 #pragma unroll
         for (int k = 0; k < SUB; ++k) y[k] = __uint_as_float(raw[k]);
@@ -270,7 +337,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
             y[4 * q + 3] += sh4.w;
           }
         }
-        if (p.stat_sum != nullptr) {
+        if (has_stats) {
           float a[SUB], b[SUB];
 #pragma unroll
           for (int k = 0; k < SUB; ++k) {
@@ -285,7 +352,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
             atomicAdd(&s_sq[n0 + cb + lane], sq);
           }
         }
-        if (res_row != nullptr) {
+        if (has_res && res_row != nullptr) {
 #pragma unroll
           for (int q = 0; q < SUB / 8; ++q) {
             if (n0 + cb + q * 8 < p.res_c) {
@@ -318,7 +385,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
           *reinterpret_cast<uint4*>(obuf + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
         const int col = n0 + cb;
-        if (p.pool2_ptr != nullptr) {
+        if (has_pool2) {
           // 2x2 max over pixels (ti, tj), (ti, tj^1), (ti^1, tj), (ti^1, tj^1) = lanes l, l^1, l^bw, l^bw^1 (bw is a
           // power of two <= 16 and the tile origin is even, both guaranteed by the host)
           uint32_t m[SUB / 2];
@@ -335,36 +402,48 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
               if (col + q * 16 < p.out_c) store16(prow + q * 16, m + q * 8, p.pool2_align32 != 0);
           }
         }
-        if (p.nchw_ptr != nullptr && valid) {
+        if (has_nchw && valid) {
           float* nrow = p.nchw_ptr + (long long)img * p.nchw_sn + (long long)oh * p.nchw_sh + (long long)ow * p.nchw_sw;
 #pragma unroll
           for (int k = 0; k < SUB; ++k)
             if (col + k < p.nchw_c) nrow[(long long)(col + k) * p.nchw_sc] = y[k];
         }
-        if (p.pool_sum != nullptr) {
+        if (has_poolsum) {
           // pool what is actually stored (bf16-rounded), masked to valid pixels
-          float a[SUB];
+          if (defer_pool) {
+            if (valid) {
 #pragma unroll
-          for (int k = 0; k < SUB; ++k) a[k] = valid ? __bfloat162float(__float2bfloat16_rn(y[k])) : 0.f;
-          const float sa = warp_col_sums<SUB>(a, lane);
-          if (lane < SUB) atomicAdd(&s_pool[cb + lane], sa);
+              for (int k = 0; k < SUB; ++k) psum[k] += __bfloat162float(__float2bfloat16_rn(y[k]));
+            }
+          } else {
+            float a[SUB];
+#pragma unroll
+            for (int k = 0; k < SUB; ++k) a[k] = valid ? __bfloat162float(__float2bfloat16_rn(y[k])) : 0.f;
+            const float sa = warp_col_sums<SUB>(a, lane);
+            if (lane < SUB) atomicAdd(&s_pool[cb + lane], sa);
+          }
         }
       }
+      dc.add(5, tld);  // TMEM load + math + staging (+ extras)
+      const long long tf = dc.now();
       fence_proxy_async_smem();
       named_bar_sync(2, kEpiThreads);
-      if (issuer) {
+      dc.add(6, tf);
+      const long long ti_ = dc.now();
+      if (my_store) {
         const int col = n0 + ch * OCW;
         if (p.out_cols > 0) tma_store_4d(&p.tm_out[col / p.out_cols], obuf, col % p.out_cols, w0, h0, img);
         else tma_store_4d(&p.tm_out[0], obuf, col, w0, h0, img);
         tma_store_commit();
       }
+      dc.add(7, ti_);
       ++nstore;
     }
     // accumulator stage fully read -> hand it back to the MMA warp
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-    if (p.pool_sum != nullptr) {
+    if (has_poolsum && !defer_pool) {
       named_bar_sync(3, kEpiThreads);
       for (int i = e; i < BN; i += kEpiThreads) {
         const float v = s_pool[i];
@@ -373,8 +452,15 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
       }
     }
   }
-  if (issuer) tma_store_wait_read<0>();
-  if (p.stat_sum != nullptr) {
+  if (defer_pool && has_poolsum && worker && pimg >= 0) flush_pool(pimg, it.nt_last(p) * BN);
+  if (issuer || issuer_b) tma_store_wait_read<0>();
+  if (issuer && p.dbg) {
+    dc.add(1, t_start);
+    dc.flush(4, 3);
+    p.dbg[blockIdx.x * kDbgSlots + 7] = ntiles;
+    for (int i = 3; i < 8; ++i) p.dbg[blockIdx.x * kDbgSlots + 5 + i] = (unsigned long long)dc.acc[i];
+  }
+  if (has_stats) {
     named_bar_sync(3, kEpiThreads);
     const int nc = p.cout_pad < kMaxStatC ? p.cout_pad : kMaxStatC;
     for (int i = e; i < nc; i += kEpiThreads) {
@@ -384,7 +470,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
   }
 }
 
-template <int BN, int CK>
+template <int BN, int CK, int FEAT>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   using C = TcCfg<BN, CK>;
   extern __shared__ uint8_t smem_raw[];
@@ -442,6 +528,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      DbgClock dc(p.dbg);
       int stage = 0;
       uint32_t phase = 0;
       for (long long t = t_begin; t < t_end; ++t) {
@@ -455,7 +542,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         for (int sidx = 0; sidx < p.n_seg; ++sidx) {
           const TcSeg sg = p.seg[sidx];
           for (int c = 0; c < sg.nchunks; ++c) {
+            const long long w0c = dc.now();
             mbar_wait(&empty_bar[stage], phase ^ 1u);
+            dc.add(0, w0c);
             uint8_t* a_dst = pipe + stage * C::STAGE_BYTES;
             mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.bw * p.bh * CK * 2 + C::B_BYTES));
             tma_load_4d(a_dst, &p.tm_src[sg.src], &full_bar[stage], sg.c0 + c * CK, w0 + sg.dw, h0 + sg.dh, img);
@@ -468,43 +557,52 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           }
         }
       }
+      dc.flush(0, 1);
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (converged warp, elected lane issues)
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       constexpr uint32_t desc_hi = umma_desc_hi(C::SBO, C::LAYOUT);
+      DbgClock dc(lane == 0 ? p.dbg : nullptr);
+      const long long t_start = dc.now();
       int stage = 0;
       uint32_t phase = 0;
       uint32_t titer = 0;
       for (long long t = t_begin; t < t_end; ++t, ++titer) {
         const uint32_t acc = titer & 1u;
         const uint32_t acc_phase = (titer >> 1) & 1u;
+        const long long wa = dc.now();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        dc.add(1, wa);
         tc_fence_after();
         const uint32_t d_tmem = acc * BN;  // TMEM base is 0 (checked after the allocation)
         for (int it = 0; it < p.kiters; ++it) {
+          const long long wf = dc.now();
           mbar_wait(&full_bar[stage], phase);
+          dc.add(0, wf);
           tc_fence_after();
           const uint32_t a_lo = umma_desc_lo(pipe_addr + (uint32_t)stage * C::STAGE_BYTES, 16u);
           const uint32_t b_lo = a_lo + (C::A_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < CK / 16; ++k)
-            umma_bf16_split(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (it | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+            umma_bf16_elect(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit_elect(&empty_bar[stage]);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[acc]);
+        umma_commit_elect(&tfull_bar[acc]);
       }
+      dc.add(2, t_start);
+      dc.flush(1, 3);
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
+    // ------------------------------------------------------------------ epilogue (8 warps)
     StreamTiles it{t_begin, t_end, tiles_per_img};
-    run_epilogue<BN, C::OCW, C::SUB, C::OUT_BYTES>(p, it, out_stage, s_scale, s_shift, s_pool, s_sum, s_sq, tfull_bar, tempty_bar,
-                                                   warp, lane);
+    run_epilogue<BN, C::OCW, C::SUB, C::OUT_BYTES, FEAT>(p, it, out_stage, s_scale, s_shift, s_pool, s_sum, s_sq, tfull_bar,
+                                                         tempty_bar, warp, lane);
   }
 
   tc_fence_before();
@@ -525,7 +623,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
 template <int BN, int CK>
 struct HaloCfg {
   static constexpr int OCW = BN < 64 ? BN : 64;
-  static constexpr int SUB = OCW < 32 ? OCW : 32;
+  static constexpr int SUB = OCW == 32 ? 16 : (OCW < 32 ? OCW : 32);
   static constexpr int OUT_BYTES = 128 * OCW * 2;
   static constexpr int ROWB = CK * 2;                                       // bytes per halo pixel row (one swizzle span)
   static constexpr int HALO_TX = 18 * 10 * ROWB;
@@ -537,7 +635,7 @@ struct HaloCfg {
   static constexpr int MAX_STAGES = 6;
 };
 
-template <int BN, int CK>
+template <int BN, int CK, int FEAT>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __grid_constant__ ConvTcParams p) {
   using C = HaloCfg<BN, CK>;
   extern __shared__ uint8_t smem_raw[];
@@ -590,22 +688,27 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
 
   ResidentTiles it;
   it.nt_fixed = (int)(blockIdx.x % p.tiles_n);
-  it.m_first = (int)(blockIdx.x / p.tiles_n);
-  it.m_step = (int)(gridDim.x / p.tiles_n);
+  {
+    const long long c = blockIdx.x / p.tiles_n, per_n = gridDim.x / p.tiles_n;
+    it.m_first = (p.m_tiles * c) / per_n;
+    it.m_end = (p.m_tiles * (c + 1)) / per_n;
+  }
   it.tiles_per_img = p.tiles_w * p.tiles_h;
-  it.m_tiles = p.m_tiles;
   int img, h0, w0, nt;
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(wfull_bar, (uint32_t)(p.w_slots * C::WSLOT_BYTES));
       for (int j = 0; j < p.w_slots; ++j) tma_load_2d(wsm + (size_t)j * C::WSLOT_BYTES, &p.tm_w, wfull_bar, j * CK, it.nt_fixed * BN);
+      DbgClock dc(p.dbg);
       int stage = 0;
       uint32_t phase = 0;
       for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
         for (int g = 0; g < p.n_chunks; ++g) {
           const TcSeg sg = p.seg[g];
+          const long long w0c = dc.now();
           mbar_wait(&empty_bar[stage], phase ^ 1u);
+          dc.add(0, w0c);
           mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)C::HALO_TX);
           tma_load_4d(halo + (size_t)stage * C::HALO_BYTES, &p.tm_src[sg.src], &full_bar[stage], sg.c0, w0 - 1, h0 - 1, img);
           if (++stage == p.halo_stages) {
@@ -614,9 +717,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
           }
         }
       }
+      dc.flush(0, 1);
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // converged warp: every lane runs the loop, the elected lane issues (see umma_bf16_elect)
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       constexpr uint32_t a_hi = umma_desc_hi(10u * C::ROWB, C::LAYOUT);  // 8-row groups of a halo view are 10 rows apart
       constexpr uint32_t b_hi = umma_desc_hi(8u * C::ROWB, C::LAYOUT);
@@ -625,16 +729,22 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
       const uint32_t w_lo = umma_desc_lo(smem_u32(wsm), 16u);
       const uint32_t w_step = (uint32_t)p.n_chunks * (uint32_t)(C::WSLOT_BYTES >> 4);  // descriptor units between taps
       const uint32_t halo_lo = umma_desc_lo(smem_u32(halo), 16u);
+      DbgClock dc(lane == 0 ? p.dbg : nullptr);
+      const long long t_start = dc.now();
       int stage = 0;
       uint32_t phase = 0;
       for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
         const uint32_t acc = titer & 1u;
         const uint32_t acc_phase = (titer >> 1) & 1u;
+        const long long wa = dc.now();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        dc.add(1, wa);
         tc_fence_after();
         const uint32_t d_tmem = acc * BN;  // TMEM base is 0 (checked after the allocation)
         for (int g = 0; g < p.n_chunks; ++g) {
+          const long long wf = dc.now();
           mbar_wait(&full_bar[stage], phase);
+          dc.add(0, wf);
           tc_fence_after();
           const uint32_t h_lo = halo_lo + (uint32_t)stage * (uint32_t)(C::HALO_BYTES >> 4);
           uint32_t b_lo = w_lo + (uint32_t)g * (uint32_t)(C::WSLOT_BYTES >> 4);
@@ -643,21 +753,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
             const uint32_t a_lo = h_lo + (uint32_t)(((t / 3) * 10 + (t % 3)) * C::ROWB >> 4);
 #pragma unroll
             for (int k = 0; k < CK / 16; ++k)
-              umma_bf16_split(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (g | t | k) != 0 ? 1u : 0u);
+              umma_bf16_elect(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (g | t | k) != 0 ? 1u : 0u);
             b_lo += w_step;
           }
-          umma_commit(&empty_bar[stage]);
+          umma_commit_elect(&empty_bar[stage]);
           if (++stage == p.halo_stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[acc]);
+        umma_commit_elect(&tfull_bar[acc]);
       }
+      dc.add(2, t_start);
+      dc.flush(1, 3);
     }
   } else {
-    run_epilogue<BN, C::OCW, C::SUB, C::OUT_BYTES>(p, it, out_stage, s_scale, s_shift, s_pool, s_sum, s_sq, tfull_bar, tempty_bar,
-                                                   warp, lane);
+    run_epilogue<BN, C::OCW, C::SUB, C::OUT_BYTES, FEAT>(p, it, out_stage, s_scale, s_shift, s_pool, s_sum, s_sq, tfull_bar,
+                                                         tempty_bar, warp, lane);
   }
 
   tc_fence_before();
@@ -709,12 +821,12 @@ static CUtensorMapSwizzle swizzle_for_bytes(int bytes) {
   return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-template <int BN, int CK>
-static int launch_tc(const ConvTcParams& p, cudaStream_t stream) {
+template <int BN, int CK, int FEAT>
+static int launch_tc_feat(const ConvTcParams& p, cudaStream_t stream) {
   using C = TcCfg<BN, CK>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, CK, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error("conv_tc<%d,%d>: cannot reserve %d bytes of shared memory: %s", BN, CK, C::SMEM_BYTES, cudaGetErrorString(e));
       return PMOE_ERR_LAUNCH;
@@ -724,8 +836,24 @@ static int launch_tc(const ConvTcParams& p, cudaStream_t stream) {
   long long grid = p.total_tiles < (long long)num_sms() ? p.total_tiles : (long long)num_sms();
   ConvTcParams q = p;
   q.out_bufs = C::OUT_BUFS;
-  conv_tc_kernel<BN, CK><<<(unsigned)grid, kNumThreads, C::SMEM_BYTES, stream>>>(q);
+  conv_tc_kernel<BN, CK, FEAT><<<(unsigned)grid, kNumThreads, C::SMEM_BYTES, stream>>>(q);
   return check_launch("conv_tc");
+}
+
+// Specialised epilogues exist for the hot shapes (64-channel chunks, N tile >= 64); everything else is generic.
+template <int BN, int CK>
+static int launch_tc(const ConvTcParams& p, cudaStream_t stream) {
+  if constexpr (CK == 64 && BN >= 64) {
+    switch (p.feat) {
+      case 0: return launch_tc_feat<BN, CK, 0>(p, stream);
+      case kFeatShift: return launch_tc_feat<BN, CK, kFeatShift>(p, stream);
+      case kFeatShift | kFeatRelu: return launch_tc_feat<BN, CK, kFeatShift | kFeatRelu>(p, stream);
+      case kFeatShift | kFeatRelu | kFeatPool2: return launch_tc_feat<BN, CK, kFeatShift | kFeatRelu | kFeatPool2>(p, stream);
+      case kFeatStats: return launch_tc_feat<BN, CK, kFeatStats>(p, stream);
+      default: break;
+    }
+  }
+  return launch_tc_feat<BN, CK, -1>(p, stream);
 }
 
 template <int BN>
@@ -740,11 +868,11 @@ static int launch_tc_ck(const ConvTcParams& p, int ck, cudaStream_t stream) {
 }
 
 
-template <int BN, int CK>
-static int launch_halo(const ConvTcParams& p, int smem_bytes, cudaStream_t stream) {
+template <int BN, int CK, int FEAT>
+static int launch_halo_feat(const ConvTcParams& p, int smem_bytes, cudaStream_t stream) {
   static int configured = 0;
   if (configured < smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN, CK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<BN, CK, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
       set_error("conv_tc_halo<%d>: cannot reserve %d bytes of shared memory: %s", BN, smem_bytes, cudaGetErrorString(e));
       return PMOE_ERR_LAUNCH;
@@ -755,8 +883,22 @@ static int launch_halo(const ConvTcParams& p, int smem_bytes, cudaStream_t strea
   if (per_n > p.m_tiles) per_n = p.m_tiles;
   if (per_n < 1) per_n = 1;
   const unsigned grid = (unsigned)(per_n * p.tiles_n);
-  conv_tc_halo_kernel<BN, CK><<<grid, kNumThreads, smem_bytes, stream>>>(p);
+  conv_tc_halo_kernel<BN, CK, FEAT><<<grid, kNumThreads, smem_bytes, stream>>>(p);
   return check_launch("conv_tc_halo");
+}
+
+template <int BN, int CK>
+static int launch_halo(const ConvTcParams& p, int smem_bytes, cudaStream_t stream) {
+  if constexpr (BN >= 64 && (CK == 64 || CK == 16)) {
+    switch (p.feat) {
+      case 0: return launch_halo_feat<BN, CK, 0>(p, smem_bytes, stream);
+      case kFeatShift | kFeatRelu: return launch_halo_feat<BN, CK, kFeatShift | kFeatRelu>(p, smem_bytes, stream);
+      case kFeatShift | kFeatRelu | kFeatPool2: return launch_halo_feat<BN, CK, kFeatShift | kFeatRelu | kFeatPool2>(p, smem_bytes, stream);
+      case kFeatStats: return launch_halo_feat<BN, CK, kFeatStats>(p, smem_bytes, stream);
+      default: break;
+    }
+  }
+  return launch_halo_feat<BN, CK, -1>(p, smem_bytes, stream);
 }
 
 template <int BN>
@@ -781,6 +923,12 @@ static bool is_canonical_3x3(const PmoeConvTc* d) {
 }  // namespace pmoe
 
 using namespace pmoe;
+
+static unsigned long long* g_conv_dbg = nullptr;
+extern "C" int pmoe_conv_tc_set_debug(unsigned long long* counters_dev) {
+  g_conv_dbg = counters_dev;  // NULL switches the accounting off; otherwise >= 16 * #CTAs counters, zeroed by the caller
+  return PMOE_OK;
+}
 
 extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -931,6 +1079,7 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
     p.nchw_sw = d->nchw_sw;
     p.nchw_c = d->nchw_c;
   }
+  p.dbg = g_conv_dbg;
   p.scale = d->scale;
   p.shift = d->shift;
   p.act = d->act;
@@ -951,6 +1100,11 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   p.pool_sum = d->pool_sum;
   p.cout_pad = d->cout_pad;
   p.pool_stride = d->pool_stride > 0 ? d->pool_stride : d->cout_pad;
+  p.feat = -1;
+  if (!d->scale && !d->residual.ptr && !d->pool_sum && !d->nchw_out &&
+      (d->act == PMOE_ACT_NONE || d->act == PMOE_ACT_RELU))
+    p.feat = (d->shift ? kFeatShift : 0) | (d->act == PMOE_ACT_RELU ? kFeatRelu : 0) | (d->stat_sum ? kFeatStats : 0) |
+             (d->pool2_out.ptr ? kFeatPool2 : 0);
   if (halo_bn) {
     int g = 0;
     for (int i = 0; i < d->n_src; ++i)

@@ -115,9 +115,12 @@ def conv_transpose_eval(up, x):
     ck = ops.choose_ck([cp])
     segs = ops.conv_segments([(0, 0)], [cp], ck)
     views = [out[:, a::2, b::2, :] for a in range(2) for b in range(2)]
-    if cs % 64 == 0:
+    if cs % 64 == 0 and _tc():
+        # column blocks (2a, 2a+1) = the two horizontal parities of output row 2h+a are adjacent pixels: seen as ONE
+        # (n, h, w, 2*cs) tensor per row parity a, whose pixel rows are 2*cs contiguous channels -> two plain views
         wp, shift = cached(up, "wq4_%d_%d_%s" % (cp, cs, config.precision()), [up.weight, up.bias], lambda: ops.pack_convT_weight(up, cp, cs))
-        ops.conv([x.t], wp, segs, ck, views[0], shift=shift, out_extra=views[1:], out_cols=cs,
+        rows = out.view(n, h, 2, w, 2 * cs)
+        ops.conv([x.t], wp, segs, ck, rows[:, :, 0], shift=shift, out_extra=[rows[:, :, 1]], out_cols=2 * cs,
                  flops=2.0 * n * h * w * cin * cout * 4, tag="convT %dx%d %d->%d" % (h, w, cin, cout))
         return Act(out, cout)
     cop = ops.cout_padded(cout)

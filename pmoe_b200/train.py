@@ -451,10 +451,13 @@ def conv_transpose_op(tape, up, x, tag=""):
     wf = weight.detach().float()
     flops = 2.0 * n * h * w * cin * cout
     views = [out[:, a::2, b::2, :] for a in range(2) for b in range(2)]
-    if cstore % 64 == 0:  # one GEMM with N = 4*Cout, column block q stored into pixel-shuffle view q
+    if cstore % 64 == 0 and dt == torch.bfloat16 and not config.FORCE_SIMT:
+        # one GEMM with N = 4*Cout; column blocks (2a, 2a+1) land in the (n, h, w, 2*C) view of output rows 2h+a
         wp4 = _cached_pack(weight, "T4|%d|%d|%s" % (cp, cstore, dt), lambda: ops.pack_convT_weight(up, cp, cstore, dt)[0])
         shift4 = ops.pad_vec(bias.detach(), cstore, 0.0).repeat(4)
-        ops.conv([x.t], wp4, segs, ck, views[0], shift=shift4, out_extra=views[1:], out_cols=cstore, flops=4 * flops, tag="convT " + tag)
+        rows = out.view(n, h, 2, w, 2 * cstore)
+        ops.conv([x.t], wp4, segs, ck, rows[:, :, 0], shift=shift4, out_extra=[rows[:, :, 1]], out_cols=2 * cstore, flops=4 * flops,
+                 tag="convT " + tag)
     else:
         shift = ops.pad_vec(bias.detach(), cop, 0.0)
         for q, (a, b) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):

@@ -62,8 +62,10 @@ struct alignas(64) ConvTcParams {
   int pool_stride;
   // resident-weight ("halo") variant
   int halo_stages, w_slots, n_chunks, w_bytes;
+  int stream_w;  // halo kernel with the weight tiles streamed through a ring of w_slots stages instead of resident
   long long m_tiles;
   int feat;                 // compile-time epilogue variant to use (-1 = generic)
+  int pair;                 // streaming kernel launched as clusters of 2 with weight-tile multicast
   unsigned long long* dbg;  // optional per-CTA cycle counters (pmoe_conv_tc_set_debug): who waits for whom
 };
 
@@ -153,13 +155,14 @@ __device__ __forceinline__ float warp_col_sums(float (&v)[NC], int lane) {
 struct StreamTiles {
   long long t_begin, t_end;
   int tiles_per_img;
+  int mt_mul, mt_add;  // cluster pairs: the two CTAs of a pair take m-tiles 2i and 2i+1 of the same n-tile sequence
   __device__ __forceinline__ int nt_last(const ConvTcParams& p) const { return (int)((t_end - 1) % p.tiles_n); }
   __device__ __forceinline__ bool get(const ConvTcParams& p, uint32_t iter, int& img, int& h0, int& w0, int& nt) const {
     const long long t = t_begin + iter;
     if (t >= t_end) return false;
     nt = (int)(t % p.tiles_n);
-    const long long mt = t / p.tiles_n;
-    img = (int)(mt / tiles_per_img);
+    const long long mt = (t / p.tiles_n) * mt_mul + mt_add;
+    img = (int)(mt / tiles_per_img);  // >= n_img for the padding tile of an odd pair: loads read zeros, stores are clipped
     const int rem = (int)(mt % tiles_per_img);
     h0 = (rem / p.tiles_w) * p.bh;
     w0 = (rem % p.tiles_w) * p.bw;
@@ -215,7 +218,7 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 // (kFeatShift | kFeatRelu | kFeatStats | kFeatPool2; no scale / residual / other activations / NCHW copy / channel
 // sums), which turns the per-element path into straight-line code (~3 instead of ~11 instructions per element: the
 // epilogue, not the tensor core, was the limit of the 64-channel layers).
-constexpr int kFeatShift = 1, kFeatRelu = 2, kFeatStats = 4, kFeatPool2 = 8;
+constexpr int kFeatShift = 1, kFeatRelu = 2, kFeatStats = 4, kFeatPool2 = 8, kFeatPoolSum = 16, kFeatNchw = 32;
 template <int BN, int OCW, int SUB, int OUT_BYTES, int FEAT, class Iter>
 __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& it, uint8_t* out_stage, float* s_scale, float* s_shift,
                                              float* s_pool, float* s_sum, float* s_sq, uint64_t* tfull_bar, uint64_t* tempty_bar,
@@ -241,8 +244,8 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
   const bool has_stats = kGen ? (p.stat_sum != nullptr) : (FEAT & kFeatStats) != 0;
   const bool has_pool2 = kGen ? (p.pool2_ptr != nullptr) : (FEAT & kFeatPool2) != 0;
   const bool has_res = kGen && p.res != nullptr;
-  const bool has_nchw = kGen && p.nchw_ptr != nullptr;
-  const bool has_poolsum = kGen && p.pool_sum != nullptr;
+  const bool has_nchw = kGen ? (p.nchw_ptr != nullptr) : (FEAT & kFeatNchw) != 0;
+  const bool has_poolsum = kGen ? (p.pool_sum != nullptr) : (FEAT & kFeatPoolSum) != 0;
   const uint32_t sc_addr = smem_u32(s_scale), sh_addr = smem_u32(s_shift);
   const bool pool_owner = ((ti | tj) & 1) == 0;  // this lane holds the top-left pixel of a 2x2 pooling window
   // Per-image channel sums (ECA / avg-pool numerators): with one chunk per tile each thread keeps running sums of its own
@@ -271,7 +274,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
       pimg = img;
     }
     const int oh = h0 + ti, ow = w0 + tj;
-    const bool valid = row_in_box && oh < p.H && ow < p.W;
+    const bool valid = row_in_box && oh < p.H && ow < p.W && img < p.n_img;
     const uint32_t acc = titer & 1u;
     const uint32_t acc_phase = (titer >> 1) & 1u;
 
@@ -491,10 +494,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
+  // Cluster pairs (p.pair): the two CTAs run the same (n-tile, K) sequence on neighbouring m-tiles; each loads HALF of
+  // every weight tile and multicasts it to both, halving the L2 -> SM weight traffic that bounds the K >= 1152 layers.
+  const bool pair = p.pair != 0;
+  const uint32_t crank = pair ? cluster_ctarank() : 0u;
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], pair ? 2 : 1);  // both consumers release a stage that the peer's multicast writes
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -512,6 +519,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   for (int i = threadIdx.x; i < 2 * kMaxStatC; i += kNumThreads) s_sum[i] = 0.f;
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();  // the peer's barriers exist before anything remote can reach them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   if (tmem_base != 0u) {  // one CTA per SM and one allocation per CTA: the MMA issuer relies on base 0
@@ -520,10 +528,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   }
   const uint32_t pipe_addr = smem_u32(pipe);
 
-  const long long G = gridDim.x;
-  const long long t_begin = (p.total_tiles * (long long)blockIdx.x) / G;
-  const long long t_end = (p.total_tiles * (long long)(blockIdx.x + 1)) / G;
-  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  StreamTiles it;
+  {
+    const long long G = pair ? gridDim.x / 2 : gridDim.x;      // work units are split over CTAs, or over pairs
+    const long long b = pair ? blockIdx.x / 2 : blockIdx.x;
+    it.t_begin = (p.total_tiles * b) / G;
+    it.t_end = (p.total_tiles * (b + 1)) / G;
+    it.tiles_per_img = p.tiles_w * p.tiles_h;
+    it.mt_mul = pair ? 2 : 1;
+    it.mt_add = (int)crank;
+  }
+  int img, h0, w0, nt;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -531,13 +546,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       DbgClock dc(p.dbg);
       int stage = 0;
       uint32_t phase = 0;
-      for (long long t = t_begin; t < t_end; ++t) {
-        const int nt = (int)(t % p.tiles_n);
-        const long long mt = t / p.tiles_n;
-        const int img = (int)(mt / tiles_per_img);
-        const int rem = (int)(mt % tiles_per_img);
-        const int h0 = (rem / p.tiles_w) * p.bh;
-        const int w0 = (rem % p.tiles_w) * p.bw;
+      for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
         int kofs = 0;
         for (int sidx = 0; sidx < p.n_seg; ++sidx) {
           const TcSeg sg = p.seg[sidx];
@@ -548,7 +557,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
             uint8_t* a_dst = pipe + stage * C::STAGE_BYTES;
             mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(p.bw * p.bh * CK * 2 + C::B_BYTES));
             tma_load_4d(a_dst, &p.tm_src[sg.src], &full_bar[stage], sg.c0 + c * CK, w0 + sg.dw, h0 + sg.dh, img);
-            tma_load_2d(a_dst + C::A_BYTES, &p.tm_w, &full_bar[stage], kofs, nt * BN);
+            if (pair)  // my half of the weight tile, to both CTAs (the other half arrives from the peer)
+              tma_load_2d_mc(a_dst + C::A_BYTES + crank * (C::B_BYTES / 2), &p.tm_w, &full_bar[stage], kofs,
+                             nt * BN + (int)crank * (BN / 2), (uint16_t)3);
+            else
+              tma_load_2d(a_dst + C::A_BYTES, &p.tm_w, &full_bar[stage], kofs, nt * BN);
             kofs += CK;
             if (++stage == C::STAGES) {
               stage = 0;
@@ -568,8 +581,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       const long long t_start = dc.now();
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t titer = 0;
-      for (long long t = t_begin; t < t_end; ++t, ++titer) {
+      for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
         const uint32_t acc = titer & 1u;
         const uint32_t acc_phase = (titer >> 1) & 1u;
         const long long wa = dc.now();
@@ -577,7 +589,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         dc.add(1, wa);
         tc_fence_after();
         const uint32_t d_tmem = acc * BN;  // TMEM base is 0 (checked after the allocation)
-        for (int it = 0; it < p.kiters; ++it) {
+        for (int ki = 0; ki < p.kiters; ++ki) {
           const long long wf = dc.now();
           mbar_wait(&full_bar[stage], phase);
           dc.add(0, wf);
@@ -586,8 +598,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           const uint32_t b_lo = a_lo + (C::A_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < CK / 16; ++k)
-            umma_bf16_elect(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (it | k) != 0 ? 1u : 0u);
-          umma_commit_elect(&empty_bar[stage]);
+            umma_bf16_elect(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, (ki | k) != 0 ? 1u : 0u);
+          if (pair) umma_commit_mc_elect(&empty_bar[stage], (uint16_t)3);
+          else umma_commit_elect(&empty_bar[stage]);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -600,13 +613,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     }
   } else {
     // ------------------------------------------------------------------ epilogue (8 warps)
-    StreamTiles it{t_begin, t_end, tiles_per_img};
     run_epilogue<BN, C::OCW, C::SUB, C::OUT_BYTES, FEAT>(p, it, out_stage, s_scale, s_shift, s_pool, s_sum, s_sq, tfull_bar,
                                                          tempty_bar, warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();  // the peer may still arrive on this CTA's barriers until it is done as well
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -620,6 +633,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
 // UMMA descriptor VIEWS of that halo tile (start row r*10+s, 8-row groups 10 rows apart — the swizzle is a function of
 // the absolute shared-memory address, so row-shifted views need no re-staging: profiles/r01_conv_bringup.json probe).
 // L2->SMEM traffic per tile drops from 9 x 16 KB to 23 KB per chunk, and the weights are fetched once per CTA.
+constexpr int kMaxWStages = 8;
 template <int BN, int CK>
 struct HaloCfg {
   static constexpr int OCW = BN < 64 ? BN : 64;
@@ -653,7 +667,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
   uint64_t* tfull_bar = empty_bar + C::MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* wfull_bar = tempty_bar + 2;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(wfull_bar + 1);
+  uint64_t* wb_full = wfull_bar + 1;            // streamed-weight ring (p.stream_w): one barrier pair per weight stage
+  uint64_t* wb_empty = wb_full + kMaxWStages;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(wb_empty + kMaxWStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -661,6 +677,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
     for (int s = 0; s < C::MAX_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < kMaxWStages; ++s) {
+      mbar_init(&wb_full[s], 1);
+      mbar_init(&wb_empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
@@ -697,7 +717,45 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
   int img, h0, w0, nt;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && p.stream_w) {
+      // Weights too large to stay resident: the (tap, chunk) weight tiles stream through a ring of p.w_slots stages while
+      // the halo tiles keep their own ring, one chunk ahead. Per 64-channel chunk the SM receives 23 KB of input instead of
+      // 9 x 16 KB: the K >= 1152 layers are bound by the bytes an SM can take in per cycle, not by L2 or the tensor core.
+      DbgClock dc(p.dbg);
+      int hs = 0, ws = 0;
+      uint32_t hphase = 0, wphase = 0;
+      auto issue_halo = [&](uint32_t titer_, int g_) {
+        int img_, h0_, w0_, nt_;
+        if (!it.get(p, titer_, img_, h0_, w0_, nt_)) return;
+        const TcSeg sg = p.seg[g_];
+        const long long w0c = dc.now();
+        mbar_wait(&empty_bar[hs], hphase ^ 1u);
+        dc.add(0, w0c);
+        mbar_arrive_expect_tx(&full_bar[hs], (uint32_t)C::HALO_TX);
+        tma_load_4d(halo + (size_t)hs * C::HALO_BYTES, &p.tm_src[sg.src], &full_bar[hs], sg.c0, w0_ - 1, h0_ - 1, img_);
+        if (++hs == p.halo_stages) {
+          hs = 0;
+          hphase ^= 1u;
+        }
+      };
+      issue_halo(0, 0);
+      for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
+        for (int g = 0; g < p.n_chunks; ++g) {
+          if (g + 1 < p.n_chunks) issue_halo(titer, g + 1);  // keep the input one chunk ahead of the weights
+          else issue_halo(titer + 1, 0);
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&wb_empty[ws], wphase ^ 1u);
+            mbar_arrive_expect_tx(&wb_full[ws], (uint32_t)C::WSLOT_BYTES);
+            tma_load_2d(wsm + (size_t)ws * C::WSLOT_BYTES, &p.tm_w, &wb_full[ws], (t * p.n_chunks + g) * CK, it.nt_fixed * BN);
+            if (++ws == p.w_slots) {
+              ws = 0;
+              wphase ^= 1u;
+            }
+          }
+        }
+      }
+      dc.flush(0, 1);
+    } else if (lane == 0) {
       mbar_arrive_expect_tx(wfull_bar, (uint32_t)(p.w_slots * C::WSLOT_BYTES));
       for (int j = 0; j < p.w_slots; ++j) tma_load_2d(wsm + (size_t)j * C::WSLOT_BYTES, &p.tm_w, wfull_bar, j * CK, it.nt_fixed * BN);
       DbgClock dc(p.dbg);
@@ -720,7 +778,58 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
       dc.flush(0, 1);
     }
   } else if (warp == 1) {
-    {  // converged warp: every lane runs the loop, the elected lane issues (see umma_bf16_elect)
+    if (p.stream_w) {  // converged warp; weights arrive through the ring
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      constexpr uint32_t a_hi = umma_desc_hi(10u * C::ROWB, C::LAYOUT);
+      constexpr uint32_t b_hi = umma_desc_hi(8u * C::ROWB, C::LAYOUT);
+      const uint32_t w_lo = umma_desc_lo(smem_u32(wsm), 16u);
+      const uint32_t halo_lo = umma_desc_lo(smem_u32(halo), 16u);
+      DbgClock dc(lane == 0 ? p.dbg : nullptr);
+      const long long t_start = dc.now();
+      int hs = 0, ws = 0;
+      uint32_t hphase = 0, wphase = 0;
+      for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
+        const uint32_t acc = titer & 1u;
+        const uint32_t acc_phase = (titer >> 1) & 1u;
+        const long long wa = dc.now();
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        dc.add(1, wa);
+        tc_fence_after();
+        const uint32_t d_tmem = acc * BN;
+        for (int g = 0; g < p.n_chunks; ++g) {
+          const long long wf = dc.now();
+          mbar_wait(&full_bar[hs], hphase);
+          dc.add(0, wf);
+          tc_fence_after();
+          const uint32_t h_lo = halo_lo + (uint32_t)hs * (uint32_t)(C::HALO_BYTES >> 4);
+#pragma unroll 1
+          for (int t = 0; t < 9; ++t) {
+            const long long wf2 = dc.now();
+            mbar_wait(&wb_full[ws], wphase);
+            dc.add(0, wf2);
+            tc_fence_after();
+            const uint32_t a_lo = h_lo + (uint32_t)(((t / 3) * 10 + (t % 3)) * C::ROWB >> 4);
+            const uint32_t b_lo = w_lo + (uint32_t)ws * (uint32_t)(C::WSLOT_BYTES >> 4);
+#pragma unroll
+            for (int k = 0; k < CK / 16; ++k)
+              umma_bf16_elect(d_tmem, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, (g | t | k) != 0 ? 1u : 0u);
+            umma_commit_elect(&wb_empty[ws]);
+            if (++ws == p.w_slots) {
+              ws = 0;
+              wphase ^= 1u;
+            }
+          }
+          umma_commit_elect(&empty_bar[hs]);
+          if (++hs == p.halo_stages) {
+            hs = 0;
+            hphase ^= 1u;
+          }
+        }
+        umma_commit_elect(&tfull_bar[acc]);
+      }
+      dc.add(2, t_start);
+      dc.flush(1, 3);
+    } else {  // converged warp: every lane runs the loop, the elected lane issues (see umma_bf16_elect)
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       constexpr uint32_t a_hi = umma_desc_hi(10u * C::ROWB, C::LAYOUT);  // 8-row groups of a halo view are 10 rows apart
       constexpr uint32_t b_hi = umma_desc_hi(8u * C::ROWB, C::LAYOUT);
@@ -836,6 +945,29 @@ static int launch_tc_feat(const ConvTcParams& p, cudaStream_t stream) {
   long long grid = p.total_tiles < (long long)num_sms() ? p.total_tiles : (long long)num_sms();
   ConvTcParams q = p;
   q.out_bufs = C::OUT_BUFS;
+  if (p.pair) {
+    // clusters of two CTAs; total_tiles counts pair units here
+    long long pairs = p.total_tiles < (long long)(num_sms() / 2) ? p.total_tiles : (long long)(num_sms() / 2);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(2 * pairs), 1, 1);
+    cfg.blockDim = dim3(kNumThreads, 1, 1);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, CK, FEAT>, q);
+    if (e != cudaSuccess) {
+      set_error("conv_tc<%d,%d>: cluster launch failed: %s", BN, CK, cudaGetErrorString(e));
+      return PMOE_ERR_LAUNCH;
+    }
+    return check_launch("conv_tc");
+  }
   conv_tc_kernel<BN, CK, FEAT><<<(unsigned)grid, kNumThreads, C::SMEM_BYTES, stream>>>(q);
   return check_launch("conv_tc");
 }
@@ -843,6 +975,13 @@ static int launch_tc_feat(const ConvTcParams& p, cudaStream_t stream) {
 // Specialised epilogues exist for the hot shapes (64-channel chunks, N tile >= 64); everything else is generic.
 template <int BN, int CK>
 static int launch_tc(const ConvTcParams& p, cudaStream_t stream) {
+  if constexpr (CK == 64 && BN == 32) {  // the U-Net's 1x1 output conv: bias + per-image sums (+ fp32 NCHW copy)
+    switch (p.feat) {
+      case kFeatShift | kFeatPoolSum: return launch_tc_feat<BN, CK, kFeatShift | kFeatPoolSum>(p, stream);
+      case kFeatShift | kFeatPoolSum | kFeatNchw: return launch_tc_feat<BN, CK, kFeatShift | kFeatPoolSum | kFeatNchw>(p, stream);
+      default: break;
+    }
+  }
   if constexpr (CK == 64 && BN >= 64) {
     switch (p.feat) {
       case 0: return launch_tc_feat<BN, CK, 0>(p, stream);
@@ -894,6 +1033,7 @@ static int launch_halo(const ConvTcParams& p, int smem_bytes, cudaStream_t strea
       case 0: return launch_halo_feat<BN, CK, 0>(p, smem_bytes, stream);
       case kFeatShift | kFeatRelu: return launch_halo_feat<BN, CK, kFeatShift | kFeatRelu>(p, smem_bytes, stream);
       case kFeatShift | kFeatRelu | kFeatPool2: return launch_halo_feat<BN, CK, kFeatShift | kFeatRelu | kFeatPool2>(p, smem_bytes, stream);
+      case kFeatShift | kFeatRelu | kFeatPoolSum: return launch_halo_feat<BN, CK, kFeatShift | kFeatRelu | kFeatPoolSum>(p, smem_bytes, stream);
       case kFeatStats: return launch_halo_feat<BN, CK, kFeatStats>(p, smem_bytes, stream);
       default: break;
     }
@@ -969,6 +1109,11 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
           break;
         }
       if (halo_bn < 64 && d->cout_pad >= 64) halo_bn = 0;  // would starve the MMA: stream the taps instead
+      static const bool wstream_off = getenv("PMOE_NO_WSTREAM") != nullptr;
+      if (!halo_bn && !wstream_off && d->ck == 64 && d->cout_pad % 128 == 0) {
+        halo_bn = d->cout_pad % 256 == 0 ? 256 : 128;  // halo input tiles + weight tiles streamed through a ring
+        p.stream_w = 1;
+      }
     }
   }
   if (halo_bn) {
@@ -1027,7 +1172,14 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
     }
     const uint64_t dims[2] = {(uint64_t)d->ktot, (uint64_t)d->cout_pad};
     const uint64_t strides[1] = {(uint64_t)d->ktot * 2};
-    const uint32_t box[2] = {(uint32_t)d->ck, (uint32_t)bn};
+    // measured: the multicast halves the L2 reads but not the bytes each SM takes in, which is what bounds these layers
+    // (the halo + streamed-weights kernel fixes that instead) -> opt-in only
+    static const bool pair_off = getenv("PMOE_PAIR") == nullptr;
+    const long long m_tiles_all = (long long)p.tiles_w * p.tiles_h * p.n_img;
+    p.pair = (!pair_off && !halo_bn && d->ck == 64 && (bn == 128 || bn == 256) && kiters >= 9 && m_tiles_all >= 4 &&
+              num_sms() % 2 == 0) ? 1 : 0;
+    if (p.pair) p.total_tiles = ((m_tiles_all + 1) / 2) * p.tiles_n;
+    const uint32_t box[2] = {(uint32_t)d->ck, (uint32_t)(p.pair ? bn / 2 : bn)};
     if ((rc = encode_tmap(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->wpack), dims, strides, box,
                           swz_in)) != PMOE_OK)
       return rc;
@@ -1101,10 +1253,9 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   p.cout_pad = d->cout_pad;
   p.pool_stride = d->pool_stride > 0 ? d->pool_stride : d->cout_pad;
   p.feat = -1;
-  if (!d->scale && !d->residual.ptr && !d->pool_sum && !d->nchw_out &&
-      (d->act == PMOE_ACT_NONE || d->act == PMOE_ACT_RELU))
+  if (!d->scale && !d->residual.ptr && (d->act == PMOE_ACT_NONE || d->act == PMOE_ACT_RELU))
     p.feat = (d->shift ? kFeatShift : 0) | (d->act == PMOE_ACT_RELU ? kFeatRelu : 0) | (d->stat_sum ? kFeatStats : 0) |
-             (d->pool2_out.ptr ? kFeatPool2 : 0);
+             (d->pool2_out.ptr ? kFeatPool2 : 0) | (d->pool_sum ? kFeatPoolSum : 0) | (d->nchw_out ? kFeatNchw : 0);
   if (halo_bn) {
     int g = 0;
     for (int i = 0; i < d->n_src; ++i)
@@ -1118,14 +1269,30 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
     p.n_chunks = total_chunks;
     p.w_slots = 9 * total_chunks;
     p.m_tiles = (long long)p.tiles_w * p.tiles_h * p.n_img;
-    const int wbytes = ((p.w_slots * halo_bn * d->ck * 2 + 1023) / 1024) * 1024;  // halo stages stay 1 KB aligned
     const int halo_bytes = ((18 * 10 * d->ck * 2 + 1023) / 1024) * 1024;
     const int ocw_h = halo_bn < 64 ? halo_bn : 64;
+    const int bar_bytes = (2 * 6 + 5 + 2 * kMaxWStages) * 8 + 16;
+    int wbytes = ((p.w_slots * halo_bn * d->ck * 2 + 1023) / 1024) * 1024;  // halo stages stay 1 KB aligned
     int fixed = 0, stages = 0;
-    for (p.out_bufs = 2; p.out_bufs >= 1; --p.out_bufs) {
-      fixed = 1024 + p.out_bufs * 128 * ocw_h * 2 + (3 * halo_bn + 2 * kMaxStatC) * 4 + (2 * 6 + 5) * 8 + 16;
-      stages = (227 * 1024 - fixed - wbytes) / halo_bytes;
-      if (stages >= 3 || p.out_bufs == 1) break;
+    if (p.stream_w) {
+      // three halo stages, one (N = 256) or two staging tiles, the rest of shared memory for the weight ring
+      p.out_bufs = halo_bn >= 256 ? 1 : 2;
+      fixed = 1024 + p.out_bufs * 128 * ocw_h * 2 + (3 * halo_bn + 2 * kMaxStatC) * 4 + bar_bytes;
+      stages = 3;
+      int ws = (227 * 1024 - fixed - stages * halo_bytes) / (halo_bn * 128);
+      if (ws > kMaxWStages) ws = kMaxWStages;
+      if (ws < 3) {
+        set_error("conv_tc: internal error: no room for the weight ring");
+        return PMOE_ERR_ARG;
+      }
+      p.w_slots = ws;
+      wbytes = ws * halo_bn * 128;
+    } else {
+      for (p.out_bufs = 2; p.out_bufs >= 1; --p.out_bufs) {
+        fixed = 1024 + p.out_bufs * 128 * ocw_h * 2 + (3 * halo_bn + 2 * kMaxStatC) * 4 + bar_bytes;
+        stages = (227 * 1024 - fixed - wbytes) / halo_bytes;
+        if (stages >= 3 || p.out_bufs == 1) break;
+      }
     }
     if (stages > 6) stages = 6;
     if (stages >= 2) {
@@ -1133,6 +1300,7 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
       p.w_bytes = wbytes;
       const int smem_bytes = fixed + wbytes + stages * halo_bytes;
       switch (halo_bn) {
+        case 256: return launch_halo_ck<256>(p, d->ck, smem_bytes, stream);
         case 128: return launch_halo_ck<128>(p, d->ck, smem_bytes, stream);
         case 64: return launch_halo_ck<64>(p, d->ck, smem_bytes, stream);
         case 32: return launch_halo_ck<32>(p, d->ck, smem_bytes, stream);

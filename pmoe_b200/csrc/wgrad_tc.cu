@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // converged warp: every lane runs the loop, the elected lane issues (see umma_bf16_elect)
       const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.N, 1, 1);
       constexpr uint32_t kHiA = umma_desc_hi(1280u, kLayoutSW128);  // 8-pixel K groups of a halo view: 10 rows apart
       constexpr uint32_t kHiB = umma_desc_hi(1024u, kLayoutSW128);
@@ -148,17 +148,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
           const uint32_t b_lo = umma_desc_lo(dyb, (uint32_t)kWgDyBlock);
 #pragma unroll
           for (int j = 0; j < 8; ++j)  // K = 16 pixels = patch rows 2j, 2j+1
-            umma_bf16_split(d_tmem, a_lo + (uint32_t)j * (20u * 128u >> 4), kHiA, b_lo + (uint32_t)j * (2048u >> 4), kHiB, idesc,
+            umma_bf16_elect(d_tmem, a_lo + (uint32_t)j * (20u * 128u >> 4), kHiA, b_lo + (uint32_t)j * (2048u >> 4), kHiB, idesc,
                             (first && j == 0) ? 0u : 1u);
         }
         first = false;
-        umma_commit(&empty_bar[stage]);
+        umma_commit_elect(&empty_bar[stage]);
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1u;
         }
       }
-      umma_commit(done_bar);
+      umma_commit_elect(done_bar);
     }
   } else {
     // epilogue: accumulator row m = (tap of the pair) * 64 + input channel; column = output channel
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_stream_kernel(con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // converged warp: every lane runs the loop, the elected lane issues (see umma_bf16_elect)
       const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.N, 1, 1);
       constexpr uint32_t kHiA = umma_desc_hi(8u * ROWB, LAYOUT);
       constexpr uint32_t kHiB = umma_desc_hi(1024u, kLayoutSW128);
@@ -353,17 +353,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_stream_kernel(con
           const uint32_t b_lo = umma_desc_lo(dyb, (uint32_t)kWgDyBlock);
 #pragma unroll
           for (int j = 0; j < 8; ++j)  // K = 16 pixels per MMA
-            umma_bf16_split(d_tmem, a_lo + (uint32_t)j * (16u * ROWB >> 4), kHiA, b_lo + (uint32_t)j * (2048u >> 4), kHiB, idesc,
+            umma_bf16_elect(d_tmem, a_lo + (uint32_t)j * (16u * ROWB >> 4), kHiA, b_lo + (uint32_t)j * (2048u >> 4), kHiB, idesc,
                             (it | (uint32_t)j) != 0u ? 1u : 0u);
-          umma_commit(&a_empty[as]);
+          umma_commit_elect(&a_empty[as]);
           if (++as == p.a_stages) {
             as = 0;
             aphase ^= 1u;
           }
         }
-        umma_commit(&dy_empty[ds]);
+        umma_commit_elect(&dy_empty[ds]);
       }
-      umma_commit(done_bar);
+      umma_commit_elect(done_bar);
     }
   } else {
     mbar_wait(done_bar, 0);

@@ -86,6 +86,9 @@ typedef struct PmoeConvTc {
   float* nchw_out;
   int64_t nchw_sn, nchw_sc, nchw_sh, nchw_sw;
   int32_t nchw_c;
+  /* > 0: wpack holds one [cout_pad][ktot] weight set per image, this many elements apart (EfficientBlock's gate folded
+   * into the next conv: pmoe_gate_weights). Only the resident 3x3 kernel supports it (else PMOE_ERR_UNSUPPORTED). */
+  int64_t wpack_img_stride;
 } PmoeConvTc;
 
 int pmoe_conv_tc(const PmoeConvTc* desc, pmoe_stream_t stream);
@@ -124,6 +127,10 @@ int pmoe_maxpool_idx(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, 
 int pmoe_eca_gate(const float* pool_sum, int64_t pool_stride, int32_t n, float inv_count, const float* w, int32_t k,
                   int32_t groups, int32_t group_c, int32_t group_stride, float* gate, int64_t gate_stride,
                   pmoe_stream_t stream);
+/* out[n][co][k] = wpack[co][k] * gate[n][k % cphys] (bf16): the conv of x * gate[n, c] as a conv of x with per-image weights
+ * (cphys = physical channels per tap of the packed K axis). Replaces the scale pass of EfficientBlock (basics.py:76). */
+int pmoe_gate_weights(const void* wpack, const float* gate, int64_t gate_stride, int32_t n, int32_t cout_pad, int32_t ktot,
+                      int32_t cphys, void* out, pmoe_stream_t stream);
 int pmoe_scale_channels(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, const float* gate, int64_t gate_stride,
                         pmoe_stream_t stream);
 /* out[n][c] += sum over h,w (adaptive_avg_pool2d numerator, basics.py:72, unet.py:90). */

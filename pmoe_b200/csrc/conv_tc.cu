@@ -62,6 +62,7 @@ struct alignas(64) ConvTcParams {
   int pool_stride;
   // resident-weight ("halo") variant
   int halo_stages, w_slots, n_chunks, w_bytes;
+  int w_per_img;  // resident halo kernel: one weight set per image (ECA gate folded into the weights), tm_w is 3-D
   int stream_w;  // halo kernel with the weight tiles streamed through a ring of w_slots stages instead of resident
   long long m_tiles;
   int feat;                 // compile-time epilogue variant to use (-1 = generic)
@@ -667,7 +668,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
   uint64_t* tfull_bar = empty_bar + C::MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* wfull_bar = tempty_bar + 2;
-  uint64_t* wb_full = wfull_bar + 1;            // streamed-weight ring (p.stream_w): one barrier pair per weight stage
+  uint64_t* wfree_bar = wfull_bar + 1;          // per-image weights: the MMA warp is done with the resident set
+  uint64_t* wb_full = wfree_bar + 1;            // streamed-weight ring (p.stream_w): one barrier pair per weight stage
   uint64_t* wb_empty = wb_full + kMaxWStages;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(wb_empty + kMaxWStages);
 
@@ -687,6 +689,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
       mbar_init(&tempty_bar[a], kEpiWarps);
     }
     mbar_init(wfull_bar, 1);
+    mbar_init(wfree_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_w);
     tma_prefetch_desc(&p.tm_src[0]);
@@ -756,12 +759,25 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
       }
       dc.flush(0, 1);
     } else if (lane == 0) {
-      mbar_arrive_expect_tx(wfull_bar, (uint32_t)(p.w_slots * C::WSLOT_BYTES));
-      for (int j = 0; j < p.w_slots; ++j) tma_load_2d(wsm + (size_t)j * C::WSLOT_BYTES, &p.tm_w, wfull_bar, j * CK, it.nt_fixed * BN);
+      if (!p.w_per_img) {
+        mbar_arrive_expect_tx(wfull_bar, (uint32_t)(p.w_slots * C::WSLOT_BYTES));
+        for (int j = 0; j < p.w_slots; ++j) tma_load_2d(wsm + (size_t)j * C::WSLOT_BYTES, &p.tm_w, wfull_bar, j * CK, it.nt_fixed * BN);
+      }
       DbgClock dc(p.dbg);
       int stage = 0;
       uint32_t phase = 0;
+      int w_img = -1;
+      uint32_t w_loads = 0;
       for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
+        if (p.w_per_img && img != w_img) {
+          // a new image: its own (ECA-gated) weight set replaces the resident one once the MMA warp has released it
+          if (w_loads > 0) mbar_wait(wfree_bar, (w_loads - 1) & 1u);
+          mbar_arrive_expect_tx(wfull_bar, (uint32_t)(p.w_slots * C::WSLOT_BYTES));
+          for (int j = 0; j < p.w_slots; ++j)
+            tma_load_3d(wsm + (size_t)j * C::WSLOT_BYTES, &p.tm_w, wfull_bar, j * CK, it.nt_fixed * BN, img);
+          w_img = img;
+          ++w_loads;
+        }
         for (int g = 0; g < p.n_chunks; ++g) {
           const TcSeg sg = p.seg[g];
           const long long w0c = dc.now();
@@ -833,8 +849,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       constexpr uint32_t a_hi = umma_desc_hi(10u * C::ROWB, C::LAYOUT);  // 8-row groups of a halo view are 10 rows apart
       constexpr uint32_t b_hi = umma_desc_hi(8u * C::ROWB, C::LAYOUT);
-      mbar_wait(wfull_bar, 0);
-      tc_fence_after();
+      if (!p.w_per_img) {
+        mbar_wait(wfull_bar, 0);
+        tc_fence_after();
+      }
       const uint32_t w_lo = umma_desc_lo(smem_u32(wsm), 16u);
       const uint32_t w_step = (uint32_t)p.n_chunks * (uint32_t)(C::WSLOT_BYTES >> 4);  // descriptor units between taps
       const uint32_t halo_lo = umma_desc_lo(smem_u32(halo), 16u);
@@ -842,7 +860,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
       const long long t_start = dc.now();
       int stage = 0;
       uint32_t phase = 0;
+      int w_img = -1;
+      uint32_t w_loads = 0;
       for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
+        if (p.w_per_img && img != w_img) {
+          mbar_wait(wfull_bar, w_loads & 1u);
+          tc_fence_after();
+          w_img = img;
+          ++w_loads;
+        }
         const uint32_t acc = titer & 1u;
         const uint32_t acc_phase = (titer >> 1) & 1u;
         const long long wa = dc.now();
@@ -872,6 +898,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
           }
         }
         umma_commit_elect(&tfull_bar[acc]);
+        if (p.w_per_img) {  // last tile of this image for this CTA: the producer may bring the next image's weights
+          int img2, h2, w2, n2;
+          if (it.get(p, titer + 1, img2, h2, w2, n2) && img2 != img) umma_commit_elect(wfree_bar);
+        }
       }
       dc.add(2, t_start);
       dc.flush(1, 3);
@@ -1170,19 +1200,34 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
       set_error("conv_tc: wpack must be 16-byte aligned");
       return PMOE_ERR_ARG;
     }
-    const uint64_t dims[2] = {(uint64_t)d->ktot, (uint64_t)d->cout_pad};
-    const uint64_t strides[1] = {(uint64_t)d->ktot * 2};
-    // measured: the multicast halves the L2 reads but not the bytes each SM takes in, which is what bounds these layers
-    // (the halo + streamed-weights kernel fixes that instead) -> opt-in only
-    static const bool pair_off = getenv("PMOE_PAIR") == nullptr;
-    const long long m_tiles_all = (long long)p.tiles_w * p.tiles_h * p.n_img;
-    p.pair = (!pair_off && !halo_bn && d->ck == 64 && (bn == 128 || bn == 256) && kiters >= 9 && m_tiles_all >= 4 &&
-              num_sms() % 2 == 0) ? 1 : 0;
-    if (p.pair) p.total_tiles = ((m_tiles_all + 1) / 2) * p.tiles_n;
-    const uint32_t box[2] = {(uint32_t)d->ck, (uint32_t)(p.pair ? bn / 2 : bn)};
-    if ((rc = encode_tmap(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->wpack), dims, strides, box,
-                          swz_in)) != PMOE_OK)
-      return rc;
+    if (d->wpack_img_stride > 0) {
+      // one weight set per image (ECA gate folded in): only the resident halo kernel reloads weights per image
+      if (!halo_bn || p.stream_w || d->wpack_img_stride < (int64_t)d->cout_pad * d->ktot || (d->wpack_img_stride % 8)) {
+        set_error("conv_tc: per-image weights need the resident 3x3 kernel (halo_bn %d stream_w %d)", halo_bn, p.stream_w);
+        return PMOE_ERR_UNSUPPORTED;
+      }
+      const uint64_t dims[3] = {(uint64_t)d->ktot, (uint64_t)d->cout_pad, (uint64_t)o.n};
+      const uint64_t strides[2] = {(uint64_t)d->ktot * 2, (uint64_t)d->wpack_img_stride * 2};
+      const uint32_t box[3] = {(uint32_t)d->ck, (uint32_t)bn, 1u};
+      if ((rc = encode_tmap(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->wpack), dims, strides, box,
+                            swz_in)) != PMOE_OK)
+        return rc;
+      p.w_per_img = 1;
+    } else {
+      const uint64_t dims[2] = {(uint64_t)d->ktot, (uint64_t)d->cout_pad};
+      const uint64_t strides[1] = {(uint64_t)d->ktot * 2};
+      static const bool pair_off = getenv("PMOE_PAIR") == nullptr;
+      // measured: the multicast halves the L2 reads but not the bytes each SM takes in, which is what bounds these layers
+      // (the halo + streamed-weights kernel fixes that instead) -> opt-in only
+      const long long m_tiles_all = (long long)p.tiles_w * p.tiles_h * p.n_img;
+      p.pair = (!pair_off && !halo_bn && d->ck == 64 && (bn == 128 || bn == 256) && kiters >= 9 && m_tiles_all >= 4 &&
+                num_sms() % 2 == 0) ? 1 : 0;
+      if (p.pair) p.total_tiles = ((m_tiles_all + 1) / 2) * p.tiles_n;
+      const uint32_t box[2] = {(uint32_t)d->ck, (uint32_t)(p.pair ? bn / 2 : bn)};
+      if ((rc = encode_tmap(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->wpack), dims, strides, box,
+                            swz_in)) != PMOE_OK)
+        return rc;
+    }
   }
   auto view_ok = [&](const PmoeView4& v, int esz) {
     return v.ptr && !((uintptr_t)v.ptr & 15) && (v.sw * esz) % 16 == 0 && (v.sh * esz) % 16 == 0 && (v.sn * esz) % 16 == 0;
@@ -1271,7 +1316,7 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
     p.m_tiles = (long long)p.tiles_w * p.tiles_h * p.n_img;
     const int halo_bytes = ((18 * 10 * d->ck * 2 + 1023) / 1024) * 1024;
     const int ocw_h = halo_bn < 64 ? halo_bn : 64;
-    const int bar_bytes = (2 * 6 + 5 + 2 * kMaxWStages) * 8 + 16;
+    const int bar_bytes = (2 * 6 + 6 + 2 * kMaxWStages) * 8 + 16;
     int wbytes = ((p.w_slots * halo_bn * d->ck * 2 + 1023) / 1024) * 1024;  // halo stages stay 1 KB aligned
     int fixed = 0, stages = 0;
     if (p.stream_w) {

@@ -284,6 +284,24 @@ __global__ void __launch_bounds__(kRedThreads) channel_stats_kernel(V4 src, doub
   }
 }
 
+// ---------------------------------------------------------------- ECA gate folded into per-image conv weights
+// out[n][co][k] = w[co][k] * gate[n][k % cphys]: x * gate followed by a conv equals the conv with per-image weights whose
+// input-channel columns carry the gate, so the full-resolution "scale the tensor" pass (1 read + 1 write of a 224^2
+// activation) becomes a rewrite of a few hundred KB of weights.
+__global__ void gate_weights_kernel(const __nv_bfloat16* __restrict__ w, const float* __restrict__ gate, long long gate_stride,
+                                    int cphys, long long per_img, int ktot, __nv_bfloat16* __restrict__ out) {
+  const int n = blockIdx.y;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < per_img; i += (long long)gridDim.x * blockDim.x * 8) {
+    const int k = (int)(i % ktot);  // ktot % 8 == 0 and cphys % 8 == 0: the 8 elements share a row and a gate run
+    float v[8], g[8];
+    load8(w + i, v);
+    load8(gate + n * gate_stride + (k % cphys), g);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] *= g[q];
+    store8(out + (long long)n * per_img + i, v);
+  }
+}
+
 // ---------------------------------------------------------------- BatchNorm (train): finalize + apply
 // Finalize: batch mean / biased var from (sum, sumsq), running-stat update exactly as
 // nn.BatchNorm2d (momentum 0.1, unbiased variance), and the fused affine (scale, shift).
@@ -446,6 +464,22 @@ int pmoe_eca_gate(const float* pool_sum, int64_t pool_stride, int32_t n, float i
   }
   eca_gate_kernel<<<n, 128, 0, stream>>>(pool_sum, pool_stride, inv_count, w, k, groups, group_c, group_stride, gate, gate_stride);
   return check_launch("eca_gate");
+}
+
+int pmoe_gate_weights(const void* wpack, const float* gate, int64_t gate_stride, int32_t n, int32_t cout_pad, int32_t ktot,
+                      int32_t cphys, void* out, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!wpack || !gate || !out || n < 1 || cout_pad < 1 || ktot % 8 || cphys % 8 || ktot % cphys || gate_stride % 4 ||
+      ((uintptr_t)wpack & 15) || ((uintptr_t)out & 15) || ((uintptr_t)gate & 15)) {
+    set_error("gate_weights: bad arguments");
+    return PMOE_ERR_ARG;
+  }
+  const long long per_img = (long long)cout_pad * ktot;
+  dim3 grid((unsigned)((per_img / 8 + 255) / 256), (unsigned)n);
+  if (grid.x > 1024) grid.x = 1024;
+  gate_weights_kernel<<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(wpack), gate, gate_stride, cphys, per_img, ktot,
+                                               static_cast<__nv_bfloat16*>(out));
+  return check_launch("gate_weights");
 }
 
 int pmoe_scale_channels(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, const float* gate, int64_t gate_stride,

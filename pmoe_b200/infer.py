@@ -59,7 +59,7 @@ def _tc():
 
 
 def conv_eval(srcs, conv, bn=None, act=None, out=None, residual=None, pool=None, pool_stride=0, groups=None, ksize=3,
-              pool2=False):
+              pool2=False, gate=None):
     """srcs: list of Act (virtual concat along channels). groups: optional [(logical, padded)] layout of
     the channel axis when one physical source carries several padded groups (the PU-Net mask ring)."""
     cout = conv.weight.shape[0]
@@ -77,6 +77,9 @@ def conv_eval(srcs, conv, bn=None, act=None, out=None, residual=None, pool=None,
     taps = TAPS3 if ksize == 3 else [(0, 0)]
     pad = ksize // 2
     wp = packed_conv(conv, glog, gpad, taps, cop, bn=bn)
+    if gate is not None:  # per-image weights carrying an ECA gate over the (single) source's physical channels
+        assert len(srcs) == 1
+        wp = ops.gate_weights(wp, gate, phys[0])
     segs = ops.conv_segments([(r - pad, s - pad) for (r, s) in taps], phys, ck)
     scale = None  # the BatchNorm scale lives in the packed weights
     if bn is not None:
@@ -172,12 +175,20 @@ def unet_eval(net, x, out=None, out_pool=None, pool_stride=0, want_inter=False, 
 def eca_conv_block_eval(blk, x_t, groups, pool_in, hw):
     """EfficientConvBlock (basics.py:80-135) in eval mode.
     x_t: NHWC bf16 tensor/view; groups = (n_groups, logical, slot) channel layout; pool_in: fp32 per-image
-    channel sums of x_t (N, n_groups*slot) — produced for free by the epilogue that wrote x_t."""
+    channel sums of x_t (N, n_groups*slot) — produced for free by the epilogue that wrote x_t.
+    On the tensor-core path the two ECA gates never touch the activations: conv(x * gate) = conv with per-image weights
+    W[co][k] * gate[n][ci(k)], so only the (small) packed weights are rewritten per image."""
     ng, gl, gs = groups
     gate1 = nhwc.eca_gate(pool_in, hw, blk.layer1.eca1.conv.weight, ng, gl, gs)
-    xs = nhwc.scale_channels(x_t, gate1)
     n = x_t.shape[0]
     pool64 = torch.zeros(n, 64, dtype=torch.float32, device=x_t.device)
+    fold = _tc() and x_t.shape[3] % 64 == 0 and x_t.shape[1] >= 18 and x_t.shape[2] >= 10
+    if fold:
+        c1 = conv_eval([Act(x_t, ng * gl)], blk.layer1.conv1[0], blk.layer1.conv1[1], "relu", pool=pool64, groups=[(gl, gs)] * ng,
+                       gate=gate1)
+        gate2 = nhwc.eca_gate(pool64, hw, blk.layer2.eca2.conv.weight, 1, 64, 64)
+        return conv_eval([c1], blk.layer2.conv2[0], blk.layer2.conv2[1], "relu", gate=gate2)
+    xs = nhwc.scale_channels(x_t, gate1)
     c1 = conv_eval([Act(xs, ng * gl)], blk.layer1.conv1[0], blk.layer1.conv1[1], "relu", pool=pool64,
                    groups=[(gl, gs)] * ng)
     gate2 = nhwc.eca_gate(pool64, hw, blk.layer2.eca2.conv.weight, 1, 64, 64)

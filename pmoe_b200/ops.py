@@ -103,9 +103,12 @@ def _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum
     for i, (src, dh, dw, c0, nch) in enumerate(segs):
         d.seg[i].src, d.seg[i].dh, d.seg[i].dw, d.seg[i].c0, d.seg[i].nchunks = src, dh, dw, c0, nch
     d.ck = ck
+    assert wpack.is_contiguous()
+    if wpack.dim() == 3:  # (n_img, cout_pad, ktot): one weight set per image (gate_weights)
+        d.wpack_img_stride = wpack.stride(0)
+        wpack = wpack[0]
     d.ktot = wpack.shape[1]
     d.cout_pad = wpack.shape[0]
-    assert wpack.is_contiguous()
     d.wpack = wpack.data_ptr()
     assert out.dtype == dtype, (out.dtype, dtype)
     d.out = _lib.view4(out)
@@ -170,6 +173,16 @@ def conv_simt(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, resi
     sp = _lib.stream_ptr()
     code = _lib.BF16 if dt == torch.bfloat16 else _lib.F32
     _lib.check(profiler.launch("conv_simt", lambda: fn(C.byref(d), code, sp), flops, 0.0, tag), "conv_simt")
+    return out
+
+
+def gate_weights(wpack, gate, cphys):
+    """(cout_pad, ktot) bf16 packed weights x (N, >= cphys) fp32 gate -> (N, cout_pad, ktot) per-image weights."""
+    n = gate.shape[0]
+    out = torch.empty(n, wpack.shape[0], wpack.shape[1], dtype=wpack.dtype, device=wpack.device)
+    _lib.check(profiler.launch("gate_weights", lambda: _lib.lib().pmoe_gate_weights(
+        wpack.data_ptr(), gate.data_ptr(), gate.stride(0), n, wpack.shape[0], wpack.shape[1], cphys, out.data_ptr(), _lib.stream_ptr())),
+        "gate_weights")
     return out
 
 

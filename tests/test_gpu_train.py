@@ -86,7 +86,14 @@ def test_unet_stage0_train_step_fp32_vs_reference_golden():
           % (e_out, wn[0], wn[1], wv[0], wv[1], bn_err))
     assert n > 40
     assert e_out < 1e-4
-    assert wn[0] < 1e-3 and wv[0] < 1e-3
+    # Typical gradient error is ~5e-6. The bound is 5e-3 because the step is not a continuous function of its rounding:
+    # batch statistics are summed with atomics, so the forward differs by ~2e-6 run to run, and a pre-activation within
+    # that distance of 0 flips its ReLU mask, which moves a BatchNorm bias gradient (a cancelling sum over 512 pixels) by
+    # ~1e-3 — scripts/gpu_determinism.py shows the two modes; the CPU reference sits in one of them by the same chance.
+    assert wn[0] < 5e-3 and wv[0] < 5e-3
+    errs = sorted(abs(p.grad.detach().double().norm().item() - g["grads"][nm]["norm"]) / max(g["grads"][nm]["norm"], 1e-8)
+                  for nm, p in net.named_parameters() if nm in g["grads"])
+    assert errs[len(errs) // 2] < 1e-4
     assert bn_err < 1e-4
     assert int(net.state_dict()["dwn_1.1.num_batches_tracked"]) == 1
 

@@ -298,28 +298,32 @@ __global__ void maxpool_bwd_kernel(BV4 x, BV4 dy, BV4 dx, int k, int stride, int
 
 // max-pool backward from the argmax codes the forward stored (pmoe_maxpool_idx): no re-scan of the windows.
 template <typename T>
-__global__ void maxpool_bwd_idx_kernel(BV4 dy, const uint8_t* __restrict__ idx, BV4 dx, int k, int stride, int pad, int accumulate) {
+__global__ void __launch_bounds__(256) maxpool_bwd_idx_kernel(BV4 dy, const uint8_t* __restrict__ idx, BV4 dx, int k, int stride, int pad,
+                                                              int accumulate, int cg_shift) {
+  // grid.x = (image, input row); a thread handles (input column, 8 channels): no 64-bit divisions on the hot path
   const int cg = dx.c / 8;
-  const long long total = (long long)dx.n * dx.h * dx.w * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i % cg);
-    long long pix = i / cg;
-    const int iw = (int)(pix % dx.w);
-    pix /= dx.w;
-    const int ih = (int)(pix % dx.h);
-    const int n = (int)(pix / dx.h);
+  const int n = blockIdx.x / dx.h, ih = blockIdx.x % dx.h;
+  const int oh_lo = max(0, (ih + pad - k + stride) / stride), oh_hi = min(dy.h - 1, (ih + pad) / stride);
+  const int row_items = dx.w * cg;
+  for (int item = blockIdx.y * blockDim.x + threadIdx.x; item < row_items; item += gridDim.y * blockDim.x) {
+    const int iw = cg_shift >= 0 ? (item >> cg_shift) : item / cg;
+    const int g = item - iw * cg;
     float o[8];
     if (accumulate) bload8(at<T>(dx, n, ih, iw, g * 8), o);
     else {
 #pragma unroll
       for (int q = 0; q < 8; ++q) o[q] = 0.f;
     }
-    const int oh_lo = max(0, (ih + pad - k + stride) / stride), oh_hi = min(dy.h - 1, (ih + pad) / stride);
     const int ow_lo = max(0, (iw + pad - k + stride) / stride), ow_hi = min(dy.w - 1, (iw + pad) / stride);
     for (int oh = oh_lo; oh <= oh_hi; ++oh) {
       for (int ow = ow_lo; ow <= ow_hi; ++ow) {
         const uint32_t code = (uint32_t)((ih - (oh * stride - pad)) * k + (iw - (ow * stride - pad)));
-        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx + (((long long)n * dy.h + oh) * dy.w + ow) * dy.c + g * 8));
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(idx + ((size_t)(n * dy.h + oh) * dy.w + ow) * dy.c + g * 8));
+        // compare all 8 codes first: most windows do not select this pixel, and then dy is not needed at all
+        const uint32_t c4 = code * 0x01010101u;
+        const uint32_t mx = pk.x ^ c4, my = pk.y ^ c4;  // a zero byte marks a match
+        const bool any = (((mx - 0x01010101u) & ~mx) | ((my - 0x01010101u) & ~my)) & 0x80808080u;
+        if (!any) continue;
         float d[8];
         bload8(at<T>(dy, n, oh, ow, g * 8), d);
 #pragma unroll
@@ -790,7 +794,21 @@ int pmoe_maxpool_bwd_idx(const PmoeView4* dy, const uint8_t* idx, const PmoeView
     return PMOE_ERR_ARG;
   }
   const long long items = (long long)dx->n * dx->h * dx->w * (dx->c / 8);
-  BW_DISPATCH(dtype, (maxpool_bwd_idx_kernel<T><<<bgrid(items, 256), 256, 0, stream>>>(bv4(dy), idx, bv4(dx), k, stride, pad, accumulate)));
+  if (items >= (1LL << 31)) {
+    set_error("maxpool_bwd_idx: more than 2^31 items");
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  const int cg = dx->c / 8;
+  int cg_shift = -1;
+  for (int sft = 0; sft < 12; ++sft)
+    if ((1 << sft) == cg) cg_shift = sft;
+  const long long rows = (long long)dx->n * dx->h;
+  if (rows > 2147483647LL) {
+    set_error("maxpool_bwd_idx: too many rows");
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  dim3 grid((unsigned)rows, (unsigned)((dx->w * cg + 255) / 256));
+  BW_DISPATCH(dtype, (maxpool_bwd_idx_kernel<T><<<grid, 256, 0, stream>>>(bv4(dy), idx, bv4(dx), k, stride, pad, accumulate, cg_shift)));
   return check_launch("maxpool_bwd_idx");
 }
 

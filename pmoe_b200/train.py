@@ -393,7 +393,9 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
         for i, src in enumerate(srcs):
             if not _rg(src.act):
                 continue
-            segs_i = [sd for sd in segdefs if sd[0] == i]
+            # taps in REVERSE order: the data gradient reads dy at (-dh, -dw), so this enumerates the offsets in the
+            # canonical (-1,-1) .. (1,1) order the resident / halo tensor-core kernels recognise
+            segs_i = [sd for sd in segdefs if sd[0] == i][::-1]
             if not segs_i:
                 continue
             wd = _pack_dgrad(weight, src, segs_i, cstore, dt)

@@ -27,6 +27,21 @@ PUNET_CFG = dict(past_frames=4, future_frames=6, in_features=3, num_classes=23, 
                  unet_inter_repr=False, model_name="unet")
 
 
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full summary (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_conv_tc_full.json")
+    try:
+        d = json.load(open(p))
+        l = d["launches"][0]
+        unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(l[k]["value"].replace(",", "")) * unit[l[k]["unit"]]
+        return tot, "%s — %s (profiles/r01_conv_tc_full.json)" % (l["kernel"], d.get("note", ""))
+    except Exception:
+        return None, None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -183,19 +198,43 @@ def run_cuda(args, rank, world, local_rank):
         launches = profiler.launch_count()
         ms_total = e0.elapsed_time(e1)
 
-        # end-to-end through the module API with host buffers: H2D of the pinned input and D2H of the
-        # full fp32 logits every step.
-        for _ in range(1):
-            y = net(host_in.to(dev, non_blocking=True))
-            host_out.copy_(y, non_blocking=True)
-        barrier()
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        esteps = max(1, min(args.steps, 3))
-        e2.record()
-        for _ in range(esteps):
+        # end-to-end through the module API with host buffers: every step copies its input from pinned host memory and
+        # its full fp32 output back to pinned host memory. The device->host copy of step i runs on a second stream while
+        # step i+1 computes (two output buffers on each side), as a serving loop would pipeline it; all copies of all
+        # timed steps complete inside the timed region.
+        copy_stream = torch.cuda.Stream(device=dev)
+        try:
+            host_out2 = torch.empty_like(host_out).pin_memory()
+        except RuntimeError:
+            host_out2 = host_out
+        houts = [host_out, host_out2]
+
+        pending, copied = [None, None], [None, None]
+
+        def e2e_step(i):
+            j = i % 2
+            if copied[j] is not None:  # the output buffer of two steps ago may be recycled once its copy has finished
+                torch.cuda.current_stream().wait_event(copied[j])
             xin = host_in.to(dev, non_blocking=True)
             y = net(xin)
-            host_out.copy_(y, non_blocking=True)
+            pending[j] = y
+            done = torch.cuda.Event()
+            done.record()
+            copy_stream.wait_event(done)
+            with torch.cuda.stream(copy_stream):
+                houts[j].copy_(y, non_blocking=True)
+                copied[j] = torch.cuda.Event()
+                copied[j].record()
+
+        e2e_step(0)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        esteps = max(2, min(args.steps, 4))
+        e2.record()
+        for i in range(esteps):
+            e2e_step(i)
+        torch.cuda.current_stream().wait_stream(copy_stream)  # the last result has landed in host memory
         e3.record()
         barrier()
         ms_e2e = e2.elapsed_time(e3)
@@ -209,7 +248,7 @@ def run_cuda(args, rank, world, local_rank):
         profiler.enable_events(False)
 
     h2d_bytes, d2h_bytes = host_in.numel() * 4, host_out.numel() * 4
-    del net, x, y, host_out
+    del net, x, y, host_out, host_out2, houts, pending
     torch.cuda.empty_cache()
     train = None if args.no_train else run_train_leg(args, rank, world, dev)
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
@@ -236,7 +275,8 @@ def run_cuda(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
-                     "peak_source": "%s bf16_tflops_sustained" % peaks["src"], "traffic": None,
+                     "peak_source": "%s bf16_tflops_sustained" % peaks["src"], "traffic": load_traffic()[0],
+                     "traffic_launch": load_traffic()[1],
                      "launches_per_step": conv["launches"], "kernel_ms_per_step": conv["ms"],
                      "share_of_step": conv["ms"] / ms_step if ms_step > 0 else None,
                      "other_kernels_ms": {k: v["ms"] for k, v in prof.items() if k != "conv_tc"}},
@@ -281,7 +321,7 @@ def run_train_leg(args, rank, world, dev):
             "target": torch.rand(per, 1, generator=g).pin_memory()}
     n_micro = per // micro
 
-    def step():
+    def eager_step():
         opt.zero_grad(set_to_none=True)
         total = None
         for m in range(n_micro):
@@ -293,6 +333,58 @@ def run_train_leg(args, rank, world, dev):
             total = loss.detach() if total is None else total + loss.detach()
         opt.step(max_grad_norm=1.0)
         return total
+
+    # CUDA graph of forward + loss + backward of one micro-batch (single GPU): the ~4400 kernel launches of a 6-expert
+    # micro-step are issued by ONE graph launch, so the step no longer depends on how fast this box's host cores run the
+    # Python tape (measured 110-550 ms of host time per micro-step across boxes vs ~125 ms of kernels). Inputs are copied
+    # into static device buffers, gradients accumulate in place across the micro-batches, the fused Adam step stays eager.
+    graph, static, mode = None, None, "eager"
+    if world == 1 and not args.no_graph:
+        try:
+            torch.distributions.Distribution.set_default_validate_args(False)  # argument validation synchronises
+            from pmoe_b200 import train as _train
+            _train.DROPOUT_STEP = torch.zeros(1, dtype=torch.int64, device=dev)  # bumped before every replay: fresh dropout masks
+            static = {k: torch.empty((micro,) + tuple(v.shape[1:]), dtype=v.dtype, device=dev) for k, v in host.items()}
+            for k, v in host.items():
+                static[k].copy_(v[:micro])
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up on the capture stream: lazy initialisation, caches, allocator pool
+                    opt.zero_grad(set_to_none=True)
+                    dist_, sp = model(static["images"], static["speed"], static["command"])
+                    (L.moe_loss(dist_, sp, static["control"], static["target"].clone(), cfg.loss_coefs) / n_micro).backward()
+            torch.cuda.current_stream().wait_stream(side)
+            for p in model.parameters():  # static, zeroed .grad: the captured AccumulateGrad adds in place
+                if p.grad is not None:
+                    p.grad.zero_()
+            graph = torch.cuda.CUDAGraph()
+            profiler.reset()
+            with torch.cuda.graph(graph):
+                dist_, sp = model(static["images"], static["speed"], static["command"])
+                static_loss = L.moe_loss(dist_, sp, static["control"], static["target"].clone(), cfg.loss_coefs) / n_micro
+                static_loss.backward()
+            launches_per_micro = profiler.launch_count()
+            mode = "cuda_graph"
+        except Exception as ex:  # capture is an optimisation: fall back to the eager tape
+            graph, mode = None, "eager (graph capture failed: %s)" % str(ex).splitlines()[0][:120]
+            _train.DROPOUT_STEP = None
+            torch.cuda.synchronize()
+
+    def graph_step():
+        torch._foreach_zero_([p.grad for p in model.parameters() if p.grad is not None])
+        total = None
+        for m in range(n_micro):
+            sl = slice(m * micro, (m + 1) * micro)
+            for k, v in host.items():
+                static[k].copy_(v[sl], non_blocking=True)  # H2D of this micro-batch: inside the timed region
+            _train.DROPOUT_STEP.add_(1)
+            graph.replay()
+            total = static_loss.detach().clone() if total is None else total + static_loss.detach()
+        opt.step(max_grad_norm=1.0)
+        return total
+
+    step = graph_step if graph is not None else eager_step
 
     def barrier():
         if world > 1:
@@ -312,6 +404,8 @@ def run_train_leg(args, rank, world, dev):
     e1.record()
     barrier()
     launches = profiler.launch_count()
+    if graph is not None:  # launches inside graph replays are not seen by the Python-side counter
+        launches += launches_per_micro * n_micro * steps
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
@@ -319,12 +413,14 @@ def run_train_leg(args, rank, world, dev):
     gf = K * (3 * MOE_FWD_GF - MOE_STEM_DGRAD_GF)  # fwd + dgrad + wgrad per sample
     out = {"metric": "train_samples_per_sec", "value": Bg / (ms_step / 1e3), "unit": "samples/s", "ms_per_step": ms_step,
            "scaling": "strong", "workload": "moe K=%d ResNet18-ECA experts, fwd+moe_loss+bwd+allreduce+clip+Adam(amsgrad), bf16" % K,
-           "global_batch": Bg, "batch_per_gpu": per, "micro_batch": micro, "steps": steps, "loss": lv,
+           "global_batch": Bg, "batch_per_gpu": per, "micro_batch": micro, "steps": steps, "loss": lv, "launch_mode": mode,
            "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()), "gpu_launches": launches,
            "tflops_per_gpu": gf * per / ms_step / 1e3, "params": sum(p.numel() for p in model.parameters())}
     if world > 1 and getattr(wrapped, "last_stats", None):
         out["allreduce"] = wrapped.last_stats
-    del model, wrapped, opt
+    del model, wrapped, opt, graph
+    if static is not None:
+        _train.DROPOUT_STEP = None
     torch.cuda.empty_cache()
     return out
 
@@ -342,6 +438,7 @@ def main():
     ap.add_argument("--train-batch", type=int, default=512, help="GLOBAL training batch, sharded over the ranks")
     ap.add_argument("--train-experts", type=int, default=6)
     ap.add_argument("--train-micro", type=int, default=128, help="largest micro-batch one rank runs at once")
+    ap.add_argument("--no-graph", action="store_true", help="training leg: issue every launch from Python instead of one CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -87,8 +87,13 @@ typedef struct PmoeConvTc {
   int64_t nchw_sn, nchw_sc, nchw_sh, nchw_sw;
   int32_t nchw_c;
   /* > 0: wpack holds one [cout_pad][ktot] weight set per image, this many elements apart (EfficientBlock's gate folded
-   * into the next conv: pmoe_gate_weights). Only the resident 3x3 kernel supports it (else PMOE_ERR_UNSUPPORTED). */
+   * into the next conv: pmoe_gate_weights; grouped expert layers). Not supported by the streamed-weights 3x3 kernel
+   * (PMOE_ERR_UNSUPPORTED). */
   int64_t wpack_img_stride;
+  /* > 0: shift has one [cout_pad] row per image, this many floats apart. With wpack_img_stride this makes the call a
+   * GROUPED GEMM: source/out views carry one expert per "image", each with its own weights and bias (the K experts'
+   * equally-shaped Linear layers of model/moe.py:53-72 in one launch). */
+  int64_t shift_img_stride;
 } PmoeConvTc;
 
 int pmoe_conv_tc(const PmoeConvTc* desc, pmoe_stream_t stream);
@@ -187,6 +192,10 @@ int pmoe_moe_loss(const float* probs, const float* mean, const float* std, const
                   float* dprobs, float* dmean, float* dstd, float* dspeed, float* logp_out, pmoe_stream_t stream);
 /* nn.Dropout (basics.py:39-40) with a stateless counter-based mask; call again on the gradient for backward. */
 int pmoe_dropout(const void* x, void* y, int32_t dtype, int64_t n, float p, uint64_t seed, pmoe_stream_t stream);
+/* Same mask generator seeded from DEVICE memory (*seed_dev mixed with the per-layer salt): a training step captured in a
+ * CUDA graph draws fresh masks on every replay when the caller bumps the counter between replays. */
+int pmoe_dropout_dev(const void* x, void* y, int32_t dtype, int64_t n, float p, uint64_t salt, const uint64_t* seed_dev,
+                     pmoe_stream_t stream);
 /* nn.L1Loss / nn.MSELoss (loss.py:135-151): *loss += coef*mean(...), da = gradient. */
 int pmoe_l1_mse(const float* a, const float* b, int64_t n, int32_t is_mse, float coef, float* loss, float* da,
                 pmoe_stream_t stream);

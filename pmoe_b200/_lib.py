@@ -38,7 +38,7 @@ class ConvTc(C.Structure):
                 ("pool_sum", C.c_void_p), ("pool_stride", C.c_int32), ("n_out_extra", C.c_int32), ("out_cols", C.c_int32),
                 ("out_extra", View4 * 3), ("pool2_out", View4), ("nchw_out", C.c_void_p), ("nchw_sn", C.c_int64),
                 ("nchw_sc", C.c_int64), ("nchw_sh", C.c_int64), ("nchw_sw", C.c_int64), ("nchw_c", C.c_int32),
-                ("wpack_img_stride", C.c_int64)]
+                ("wpack_img_stride", C.c_int64), ("shift_img_stride", C.c_int64)]
 
 
 def lib():

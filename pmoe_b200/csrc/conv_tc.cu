@@ -62,7 +62,8 @@ struct alignas(64) ConvTcParams {
   int pool_stride;
   // resident-weight ("halo") variant
   int halo_stages, w_slots, n_chunks, w_bytes;
-  int w_per_img;  // resident halo kernel: one weight set per image (ECA gate folded into the weights), tm_w is 3-D
+  long long shift_img_stride;  // > 0: shift (bias) has one row per image (grouped expert layers: image = expert)
+  int w_per_img;  // one weight set per image (tm_w is 3-D): resident halo kernel (ECA gate folded in) or streaming kernel (grouped experts) (ECA gate folded into the weights), tm_w is 3-D
   int stream_w;  // halo kernel with the weight tiles streamed through a ring of w_slots stages instead of resident
   long long m_tiles;
   int feat;                 // compile-time epilogue variant to use (-1 = generic)
@@ -263,6 +264,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
     for (int k = 0; k < SUB; ++k) psum[k] = 0.f;
   };
   uint32_t nstore = 0;
+  int shift_img = -1;
   DbgClock dc(issuer ? p.dbg : nullptr);
   const long long t_start = dc.now();
   uint32_t ntiles = 0;
@@ -279,11 +281,14 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
     const uint32_t acc = titer & 1u;
     const uint32_t acc_phase = (titer >> 1) & 1u;
 
-    if (titer == 0 || p.tiles_n_varies) {  // resident kernels keep one N tile: the per-channel affine is loaded once
+    if (titer == 0 || p.tiles_n_varies || (p.shift_img_stride > 0 && img != shift_img)) {
+      // resident kernels keep one N tile: the per-channel affine is loaded once
       // (all reads of the previous tile's values happened before its last named barrier 2)
+      shift_img = img;
+      const long long so = p.shift_img_stride > 0 && img < p.n_img ? (long long)img * p.shift_img_stride : 0;
       for (int i = e; i < BN; i += kEpiThreads) {
         if (has_scale) s_scale[i] = __ldg(p.scale + n0 + i);
-        if (has_shift) s_shift[i] = __ldg(p.shift + n0 + i);
+        if (has_shift) s_shift[i] = __ldg(p.shift + so + n0 + i);
       }
     }
     const long long wt = dc.now();
@@ -561,6 +566,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
             if (pair)  // my half of the weight tile, to both CTAs (the other half arrives from the peer)
               tma_load_2d_mc(a_dst + C::A_BYTES + crank * (C::B_BYTES / 2), &p.tm_w, &full_bar[stage], kofs,
                              nt * BN + (int)crank * (BN / 2), (uint16_t)3);
+            else if (p.w_per_img)  // grouped layers: the "image" index selects the expert's weights
+              tma_load_3d(a_dst + C::A_BYTES, &p.tm_w, &full_bar[stage], kofs, nt * BN, img);
             else
               tma_load_2d(a_dst + C::A_BYTES, &p.tm_w, &full_bar[stage], kofs, nt * BN);
             kofs += CK;
@@ -1202,8 +1209,8 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
     }
     if (d->wpack_img_stride > 0) {
       // one weight set per image (ECA gate folded in): only the resident halo kernel reloads weights per image
-      if (!halo_bn || p.stream_w || d->wpack_img_stride < (int64_t)d->cout_pad * d->ktot || (d->wpack_img_stride % 8)) {
-        set_error("conv_tc: per-image weights need the resident 3x3 kernel (halo_bn %d stream_w %d)", halo_bn, p.stream_w);
+      if (p.stream_w || d->wpack_img_stride < (int64_t)d->cout_pad * d->ktot || (d->wpack_img_stride % 8)) {
+        set_error("conv_tc: per-image weights are not supported by the streamed-weights 3x3 kernel (or bad stride)");
         return PMOE_ERR_UNSUPPORTED;
       }
       const uint64_t dims[3] = {(uint64_t)d->ktot, (uint64_t)d->cout_pad, (uint64_t)o.n};
@@ -1277,6 +1284,7 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
     p.nchw_c = d->nchw_c;
   }
   p.dbg = g_conv_dbg;
+  p.shift_img_stride = d->shift_img_stride;
   p.scale = d->scale;
   p.shift = d->shift;
   p.act = d->act;

@@ -220,7 +220,9 @@ __device__ __forceinline__ uint32_t mix32(uint64_t x) {
   return (uint32_t)x;
 }
 template <typename T>
-__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, float p, unsigned long long seed) {
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, float p, unsigned long long seed,
+                               const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev) seed += *seed_dev * 0xD1B54A32D192ED03ULL;  // step counter in device memory: fresh masks under CUDA-graph replay
   const uint32_t thresh = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
   const float scale = 1.f / (1.f - p);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -306,7 +308,24 @@ int pmoe_moe_loss(const float* probs, const float* mean, const float* std, const
   return check_launch("moe_loss");
 }
 
+static int dropout_launch(const void* x, void* y, int32_t dtype, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev,
+                          pmoe_stream_t stream_);
+
 int pmoe_dropout(const void* x, void* y, int32_t dtype, int64_t n, float p, uint64_t seed, pmoe_stream_t stream_) {
+  return dropout_launch(x, y, dtype, n, p, seed, nullptr, stream_);
+}
+
+int pmoe_dropout_dev(const void* x, void* y, int32_t dtype, int64_t n, float p, uint64_t salt, const uint64_t* seed_dev,
+                     pmoe_stream_t stream_) {
+  if (!seed_dev) {
+    set_error("dropout_dev: device seed missing");
+    return PMOE_ERR_ARG;
+  }
+  return dropout_launch(x, y, dtype, n, p, salt, seed_dev, stream_);
+}
+
+static int dropout_launch(const void* x, void* y, int32_t dtype, int64_t n, float p, uint64_t seed, const uint64_t* seed_dev,
+                          pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !y || n < 1 || p < 0.f || p >= 1.f) {
     set_error("dropout: bad arguments");
@@ -316,9 +335,11 @@ int pmoe_dropout(const void* x, void* y, int32_t dtype, int64_t n, float p, uint
   if (bl > (long long)num_sms() * 16) bl = (long long)num_sms() * 16;
   if (dtype == PMOE_BF16)
     dropout_kernel<__nv_bfloat16><<<(unsigned)bl, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x),
-                                                                    static_cast<__nv_bfloat16*>(y), n, p, seed);
+                                                                    static_cast<__nv_bfloat16*>(y), n, p, seed,
+                                                                    reinterpret_cast<const unsigned long long*>(seed_dev));
   else
-    dropout_kernel<float><<<(unsigned)bl, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(y), n, p, seed);
+    dropout_kernel<float><<<(unsigned)bl, 256, 0, stream>>>(static_cast<const float*>(x), static_cast<float*>(y), n, p, seed,
+                                                            reinterpret_cast<const unsigned long long*>(seed_dev));
   return check_launch("dropout");
 }
 

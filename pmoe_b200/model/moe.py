@@ -87,6 +87,19 @@ def _run_experts(owner, experts, images, speed, command, alt, softmax=True):
         alpha_buf = torch.zeros(1, 1, B, K * 16, dtype=tape.dtype, device=dev)
         ap_buf = torch.zeros(1, 1, B, K * 16, dtype=tape.dtype, device=dev)
         sp_buf = torch.zeros(1, 1, B, K * 16, dtype=tape.dtype, device=dev)
+        if train.grouped_supported(experts, alt):
+            # encoders per expert, then ALL experts' heads with one launch per layer (grouped GEMM over the expert axis)
+            feats = [train.feature_act(tape, train.resnet18_eca(tape, ex.backbone, x, tag="moe.%d.backbone" % k))
+                     for k, ex in enumerate(experts)]
+            al, ap, sp = train.expert_heads_grouped(tape, experts, feats, speed_a, cmd_a, alt)
+            gm = train.GateMixture(tape, [al], [ap], al.t, ap.t, B, K, relu_alpha=not alt, a_sk=B * 16, p_sk=B * 16)
+            speeds = sp.t.view(K, B, 16)[:, :, :1].permute(1, 0, 2).float().contiguous()
+
+            def seed(tp, g):
+                gm.backward(g[0], g[1], g[2])
+                if g[3] is not None:
+                    train.seed_stacked(tp, sp, g[3])
+            return [gm.probs, gm.mean, gm.std, speeds, gm.route], seed
         als, aps, sps = [], [], []
         for k, ex in enumerate(experts):
             feat = train.resnet18_eca(tape, ex.backbone, x, tag="moe.%d.backbone" % k)

@@ -114,6 +114,8 @@ def _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum
     d.out = _lib.view4(out)
     d.scale = None if scale is None else scale.data_ptr()
     d.shift = None if shift is None else shift.data_ptr()
+    if shift is not None and shift.dim() == 2:  # (n_img, cout_pad): one bias row per image / expert
+        d.shift_img_stride = shift.stride(0)
     d.act = ACT[act]
     d.residual = _lib.view4(residual) if residual is not None else _lib.null_view()
     d.stat_sum = None if stat_sum is None else stat_sum.data_ptr()

@@ -707,14 +707,26 @@ def feature_act(tape, inter):
     return a
 
 
+DROPOUT_STEP = None  # optional device int64 step counter: masks are seeded from it (CUDA-graph friendly, see bench.py)
+
+
 def dropout_op(tape, x, p, training):
     if not training or p <= 0.0:
         return x
     seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     y = torch.empty_like(x.t)
     n = x.t.numel()
-    check(profiler.launch("dropout", lambda: lib().pmoe_dropout(x.t.data_ptr(), y.data_ptr(), dtype_code(y), n, float(p), seed,
-                                                                stream_ptr())), "dropout")
+    step_dev = DROPOUT_STEP
+
+    def run(src, dst):
+        if step_dev is not None:
+            check(profiler.launch("dropout", lambda: lib().pmoe_dropout_dev(src.data_ptr(), dst.data_ptr(), dtype_code(dst), n, float(p), seed,
+                                                                            step_dev.data_ptr(), stream_ptr())), "dropout")
+        else:
+            check(profiler.launch("dropout", lambda: lib().pmoe_dropout(src.data_ptr(), dst.data_ptr(), dtype_code(dst), n, float(p), seed,
+                                                                        stream_ptr())), "dropout")
+
+    run(x.t, y)
     ya = _new_act(tape, y, x.c, _rg(x))
     if tape.save and _rg(x):
         def backward():
@@ -723,8 +735,7 @@ def dropout_op(tape, x, p, training):
                 return
             g, existed = _grad_buffer(tape, x)
             tmp = g if not existed else torch.empty_like(g)
-            check(profiler.launch("dropout", lambda: lib().pmoe_dropout(dy.data_ptr(), tmp.data_ptr(), dtype_code(tmp), n, float(p),
-                                                                        seed, stream_ptr())), "dropout")
+            run(dy, tmp)  # the same mask (same salt, same step counter) applied to the gradient
             if existed:
                 _axpy(tmp, g, 1.0, None, True)
         tape.record(backward)
@@ -805,6 +816,18 @@ def seed_vec(tape, act, g):
     _accumulate(tape, act, gt)
 
 
+def seed_stacked(tape, act, g_bk):
+    """Install a (B, K, c) fp32 gradient for a stacked (K,1,B,cpad) Act."""
+    if g_bk is None or not _rg(act):
+        return
+    K, _, B, cp = act.t.shape
+    buf = torch.zeros(K, B, cp, dtype=torch.float32, device=g_bk.device)
+    buf[:, :, :act.c] = g_bk.permute(1, 0, 2)
+    gt = torch.empty(K, 1, B, cp, dtype=act.t.dtype, device=g_bk.device)
+    _axpy(None, gt.view(K * B, 1, 1, cp), 1.0, buf.view(K * B, cp), False)
+    _accumulate(tape, act, gt)
+
+
 def expert_heads(tape, ex, img_feat, speed_a, cmd_a, alt, alpha_out, ap_out, speed_out, tag="expert"):
     """BaseExpert / BaseExpertAlt after the backbone (moe.py:88-101, 113-128). The raw head outputs are written into
     slices of shared (1,1,B,K*16) buffers so the gating kernel sees all experts at once."""
@@ -833,6 +856,191 @@ def mlp_last_out(tape, seq, srcs, out, tag):
     if last_lin + 1 < len(mods):
         raise RuntimeError("pmoe_b200: l_act on an output head is not supported")
     return linear_op(tape, [y], mods[last_lin], None, out=out, tag="%s.%d" % (tag, last_lin))
+
+
+# ------------------------------------------------------------------------------------------------ grouped expert heads
+# The K experts of MixtureOfExperts carry identically shaped head MLPs (moe.py:53-72). Instead of K launches per Linear,
+# the experts become the "image" axis of ONE launch: activations are stacked (K,1,B,C), the library picks expert e's
+# weights and bias for the tiles of image e (PmoeConvTc.wpack_img_stride / shift_img_stride). Forward and data gradient
+# are grouped; the weight gradient runs per expert on the views of the stacked tensors.
+def _grouped_pack(lins, srcs, cop, dt, kind):
+    """Stack the per-expert packed weights; cached on the first expert's weight, keyed on every expert's version."""
+    w0 = lins[0].weight
+    vers = tuple((l.weight.data_ptr(), l.weight._version) for l in lins)
+    cache = w0.__dict__.setdefault("_pmoe_gpack", {})
+    key = (kind, tuple((x.cin0, tuple(x.lay)) for x in srcs), cop, str(dt))
+    hit = cache.get(key)
+    if hit is not None and hit[0] == vers:
+        return hit[1]
+    packs = []
+    for l in lins:
+        w4 = l.weight.detach().float().view(l.weight.shape[0], l.weight.shape[1], 1, 1)
+        if kind == "f":
+            cols = []
+            for x in srcs:
+                cols += _pack_cols(w4, x, 0, 0)
+            wp = torch.cat(cols, dim=1)
+            if cop > wp.shape[0]:
+                wp = torch.nn.functional.pad(wp, (0, 0, 0, cop - wp.shape[0]))
+        else:  # data gradient of source `srcs[0]`: rows = its physical channels, K = padded cout
+            blk = torch.cat(_pack_cols(w4, srcs[0], 0, 0), dim=1).t()
+            blk = torch.nn.functional.pad(blk, (0, cop - blk.shape[1]))
+            rows = ops.cout_padded(blk.shape[0])
+            wp = torch.nn.functional.pad(blk, (0, 0, 0, rows - blk.shape[0]))
+        packs.append(wp.to(dt))
+    val = torch.stack(packs).contiguous()
+    if len(cache) > 8:
+        cache.clear()
+    cache[key] = (vers, val)
+    return val
+
+
+def grouped_linear_op(tape, srcs, lins, act=None, tag=""):
+    """K Linear layers of equal shape over stacked inputs: srcs = Acts of shape (K,1,B,C) (virtual concat along C)."""
+    dt = tape.dtype
+    K = len(lins)
+    srcs = concat_sources(srcs)
+    dev = srcs[0].t.device
+    cout = lins[0].weight.shape[0]
+    cop, cstore = ops.cout_padded(cout), pad_ch(cout)
+    phys = [x.cpad for x in srcs]
+    ck = ops.choose_ck(phys)
+    segs = [(i, 0, 0, 0, phys[i] // ck) for i in range(len(srcs))]
+    wp = _grouped_pack(lins, srcs, cop, dt, "f")
+    B = srcs[0].t.shape[2]
+    has_bias = lins[0].bias is not None
+    shift = None
+    if has_bias:
+        shift = torch.zeros(K, cop, dtype=torch.float32, device=dev)
+        shift[:, :cout] = torch.stack([l.bias.detach().float() for l in lins])
+    z_t = torch.empty(K, 1, B, cstore, dtype=dt, device=dev)
+    flops = 2.0 * K * B * cout * sum(x.nlog for x in srcs)
+    ops.conv([x.t for x in srcs], wp, segs, ck, z_t, shift=shift, act=act, flops=flops, tag="grouped " + tag)
+    params = [l.weight for l in lins] + [l.bias for l in lins if l.bias is not None]
+    rg = any(_rg(x.act) for x in srcs) or _any_rg(params)
+    z = _new_act(tape, z_t, cout, rg)
+    if not (tape.save and rg):
+        return z
+
+    def backward():
+        dz = tape.grad_of(z)
+        if dz is None:
+            return
+        z_saved = z_t if act not in (None, "none") else None
+        dy = torch.empty(K, 1, B, cstore, dtype=dt, device=dev)
+        _bn_bwd_apply(dz, z_saved, None, act, None, None, None, None, None, 0.0, 0, dy, None, False)
+        for e, lin in enumerate(lins):
+            if lin.bias is not None and lin.bias.requires_grad:
+                s1, _ = _bn_bwd_reduce(dy[e:e + 1], None, None, None, None, None, cstore)
+                tape.add_pgrad(lin.bias, s1[:cout])
+            if lin.weight.requires_grad:
+                dwp = torch.zeros(cop, wp.shape[2], dtype=torch.float32, device=dev)
+                ops.conv_wgrad([x.t[e:e + 1] for x in srcs], segs, ck, dy[e:e + 1], dwp, flops=flops / K, tag="wgrad grouped " + tag)
+                gw = torch.empty(lin.weight.shape, dtype=torch.float32, device=dev)
+                off = 0
+                for x in srcs:
+                    ci, o = x.cin0, off
+                    for (gl, gp) in x.lay:
+                        gw[:, ci:ci + gl] = dwp[:cout, o:o + gl]
+                        ci += gl
+                        o += gp
+                    off += x.cpad
+                tape.add_pgrad(lin.weight, gw)
+        ck_d = ops.choose_ck([cstore])
+        for x in srcs:
+            if not _rg(x.act):
+                continue
+            wd = _grouped_pack(lins, [x], cstore, dt, "d")
+            g, existed = _grad_buffer(tape, x.act)
+            ops.conv([dy], wd, [(0, 0, 0, 0, cstore // ck_d)], ck_d, g, residual=g if existed else None,
+                     flops=2.0 * K * B * cout * x.nlog, tag="dgrad grouped " + tag)
+
+    for lin in lins:
+        tape.expect(lin.bias, lin.weight)
+    tape.record(backward)
+    return z
+
+
+GROUPED_HEADS = True  # tests switch this off to compare against the per-expert launches
+
+
+def grouped_supported(experts, alt):
+    """Grouped heads need the tensor-core path and the plain MLP structure (Linear [+act] [+Dropout], no BatchNorm1d)."""
+    if not GROUPED_HEADS or config.precision() != "bf16" or config.FORCE_SIMT or len(experts) < 2:
+        return False
+    for ex in experts:
+        for seq in (ex.speed_encoder, ex.command_encoder, ex.speed_pred, ex.action_features):
+            if any(isinstance(m, torch.nn.BatchNorm1d) for m in seq):
+                return False
+    return True
+
+
+def grouped_mlp(tape, seqs, srcs, tag="mlp"):
+    """make_mlp Sequentials of K experts (same structure) over stacked inputs."""
+    mods0 = list(seqs[0])
+    x_srcs, y, i = srcs, None, 0
+    while i < len(mods0):
+        if not isinstance(mods0[i], torch.nn.Linear):
+            raise RuntimeError("pmoe_b200 grouped mlp: unexpected layer order at %d: %r" % (i, mods0[i]))
+        j = i + 1
+        act = drop = None
+        if j < len(mods0) and isinstance(mods0[j], (torch.nn.ReLU, torch.nn.ELU, torch.nn.Tanh, torch.nn.Sigmoid)):
+            act = {torch.nn.ReLU: "relu", torch.nn.ELU: "elu", torch.nn.Tanh: "tanh", torch.nn.Sigmoid: "sigmoid"}[type(mods0[j])]
+            j += 1
+        if j < len(mods0) and isinstance(mods0[j], torch.nn.Dropout):
+            drop = mods0[j]
+            j += 1
+        y = grouped_linear_op(tape, x_srcs, [list(sq)[i] for sq in seqs], act, tag="%s.%d" % (tag, i))
+        if drop is not None:
+            y = dropout_op(tape, y, drop.p, drop.training)
+        x_srcs = [y]
+        i = j
+    return y
+
+
+def stack_acts(tape, acts):
+    """K Acts of shape (1,1,B,C) -> one Act (K,1,B,C); the gradient of the stack flows back to each part."""
+    K = len(acts)
+    t = torch.empty(K, 1, acts[0].t.shape[2], acts[0].t.shape[3], dtype=acts[0].t.dtype, device=acts[0].t.device)
+    for e, a in enumerate(acts):
+        _axpy(a.t, t[e:e + 1], 1.0, None, False)
+    st = _new_act(tape, t, acts[0].c, any(_rg(a) for a in acts))
+    if tape.save and _rg(st):
+        def backward():
+            g = tape.grad_of(st)
+            if g is None:
+                return
+            for e, a in enumerate(acts):
+                if _rg(a):
+                    _accumulate_copy(tape, a, g[e:e + 1])
+        tape.record(backward)
+    return st
+
+
+def broadcast_act(tape, a, K):
+    """The same (1,1,B,C) input for every expert as a (K,1,B,C) Act (inputs: no gradient)."""
+    t = a.t.expand(K, -1, -1, -1).contiguous()
+    return _new_act(tape, t, a.c, False)
+
+
+def expert_heads_grouped(tape, experts, img_feats, speed_a, cmd_a, alt):
+    """All experts' heads (moe.py:88-101 / 113-128) with one launch per layer. Returns stacked (K,1,B,16) Acts of the raw
+    alpha, action_pred and speed_pred outputs."""
+    K = len(experts)
+    feat = stack_acts(tape, img_feats)
+    s = grouped_mlp(tape, [ex.speed_encoder for ex in experts], [broadcast_act(tape, speed_a, K)], "speed_encoder")
+    c = grouped_mlp(tape, [ex.command_encoder for ex in experts], [broadcast_act(tape, cmd_a, K)], "command_encoder")
+    feats = [feat, s, c]
+    sp = grouped_mlp(tape, [ex.speed_pred for ex in experts], feats, "speed_pred")
+    af = grouped_mlp(tape, [ex.action_features for ex in experts], feats, "action_features")
+    ap = grouped_linear_op(tape, [af], [ex.action_pred for ex in experts], None, tag="action_pred")
+    if alt:
+        a1 = grouped_linear_op(tape, feats, [ex.alpha[0] for ex in experts], "relu", tag="alpha.0")
+        al = grouped_linear_op(tape, [a1], [ex.alpha[2] for ex in experts], None, tag="alpha.2")
+    else:
+        al = grouped_linear_op(tape, [af], [ex.alpha for ex in experts], None, tag="alpha")  # ReLU applied by the gating kernel
+    return al, ap, sp
+
 
 
 class GateMixture:
@@ -875,6 +1083,8 @@ class GateMixture:
 
 
 # ------------------------------------------------------------------------------------------------ autograd bridge
+import os as _os
+DIRECT_GRADS = _os.environ.get("PMOE_DIRECT_GRADS", "0") == "1"
 class TapeFunction(torch.autograd.Function):
     """forward(runner, *params): runner(tape) -> (list of output tensors, seed_fn). seed_fn(grad_outputs)
     installs the output gradients into the tape; backward then replays the tape and returns the parameter
@@ -903,6 +1113,17 @@ class TapeFunction(torch.autograd.Function):
         else:
             grads = tuple(tape.pgrads.get(id(p)) if p.requires_grad else None for p in ctx.plist)
         ctx.tape = None
+        if DIRECT_GRADS and ctx.dp is None:
+            # hand the gradients to .grad ourselves: the engine would clone each of the ~500 tensors it cannot steal
+            with torch.no_grad():
+                for p, g in zip(ctx.plist, grads):
+                    if g is None:
+                        continue
+                    if p.grad is None:
+                        p.grad = g
+                    else:
+                        p.grad.add_(g)
+            return (None,) * (len(ctx.plist) + 1)
         return (None,) + grads
 
 

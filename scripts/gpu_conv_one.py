@@ -13,7 +13,8 @@ cop = ops.cout_padded(cout)
 wp = ops.pack_conv_weight(w, [cin], cp, ops.TAPS3, cop)
 segs = ops.conv_segments([(r - 1, s - 1) for (r, s) in ops.TAPS3], cp, ck)
 out = torch.empty(B, H, H, ops.pad_ch(cout), dtype=torch.bfloat16, device=dev)
-sc = torch.ones(cop, device=dev); sh = torch.zeros(cop, device=dev)
+sc = None  # eval-mode BN scale lives in the packed weights: the same specialised epilogue (shift + ReLU) the model runs
+sh = torch.zeros(cop, device=dev)
 for _ in range(3):
     ops.conv_tc([x], wp, segs, ck, out, sc, sh, "relu")
 torch.cuda.synchronize()

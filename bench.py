@@ -334,12 +334,12 @@ def run_train_leg(args, rank, world, dev):
         opt.step(max_grad_norm=1.0)
         return total
 
-    # CUDA graph of forward + loss + backward of one micro-batch (single GPU): the ~4400 kernel launches of a 6-expert
+    # CUDA graph of forward + loss + backward (+ gradient all-reduce) of one micro-batch: the ~4400 kernel launches of a 6-expert
     # micro-step are issued by ONE graph launch, so the step no longer depends on how fast this box's host cores run the
     # Python tape (measured 110-550 ms of host time per micro-step across boxes vs ~125 ms of kernels). Inputs are copied
     # into static device buffers, gradients accumulate in place across the micro-batches, the fused Adam step stays eager.
     graph, static, mode = None, None, "eager"
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:
         try:
             torch.distributions.Distribution.set_default_validate_args(False)  # argument validation synchronises
             from pmoe_b200 import train as _train
@@ -352,7 +352,7 @@ def run_train_leg(args, rank, world, dev):
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up on the capture stream: lazy initialisation, caches, allocator pool
                     opt.zero_grad(set_to_none=True)
-                    dist_, sp = model(static["images"], static["speed"], static["command"])
+                    dist_, sp = wrapped(static["images"], static["speed"], static["command"])
                     (L.moe_loss(dist_, sp, static["control"], static["target"].clone(), cfg.loss_coefs) / n_micro).backward()
             torch.cuda.current_stream().wait_stream(side)
             for p in model.parameters():  # static, zeroed .grad: the captured AccumulateGrad adds in place
@@ -360,8 +360,8 @@ def run_train_leg(args, rank, world, dev):
                     p.grad.zero_()
             graph = torch.cuda.CUDAGraph()
             profiler.reset()
-            with torch.cuda.graph(graph):
-                dist_, sp = model(static["images"], static["speed"], static["command"])
+            with torch.cuda.graph(graph):  # under DP the bucketed NCCL all-reduces of the tape are captured as well
+                dist_, sp = wrapped(static["images"], static["speed"], static["command"])
                 static_loss = L.moe_loss(dist_, sp, static["control"], static["target"].clone(), cfg.loss_coefs) / n_micro
                 static_loss.backward()
             launches_per_micro = profiler.launch_count()

@@ -154,18 +154,20 @@ __device__ __forceinline__ float warp_col_sums(float (&v)[NC], int lane) {
 
 // Tile enumerators. StreamTiles: contiguous chunk of the (m, n) tile list per CTA (per-tap streaming kernel).
 // ResidentTiles: the CTA owns ONE n-tile (its weights stay in shared memory) and strides over the m-tiles.
+// All tile arithmetic is 32-bit on purpose: a 64-bit division is a subroutine CALL, and a call inside the lane-0 producer
+// branch makes ptxas give up on proving the MMA warp converged (it then emits an ELECT + R2UR waterfall per MMA).
 struct StreamTiles {
-  long long t_begin, t_end;
+  int t_begin, t_end;
   int tiles_per_img;
   int mt_mul, mt_add;  // cluster pairs: the two CTAs of a pair take m-tiles 2i and 2i+1 of the same n-tile sequence
-  __device__ __forceinline__ int nt_last(const ConvTcParams& p) const { return (int)((t_end - 1) % p.tiles_n); }
+  __device__ __forceinline__ int nt_last(const ConvTcParams& p) const { return (t_end - 1) % p.tiles_n; }
   __device__ __forceinline__ bool get(const ConvTcParams& p, uint32_t iter, int& img, int& h0, int& w0, int& nt) const {
-    const long long t = t_begin + iter;
+    const int t = t_begin + (int)iter;
     if (t >= t_end) return false;
-    nt = (int)(t % p.tiles_n);
-    const long long mt = (t / p.tiles_n) * mt_mul + mt_add;
-    img = (int)(mt / tiles_per_img);  // >= n_img for the padding tile of an odd pair: loads read zeros, stores are clipped
-    const int rem = (int)(mt % tiles_per_img);
+    nt = t % p.tiles_n;
+    const int mt = (t / p.tiles_n) * mt_mul + mt_add;
+    img = mt / tiles_per_img;  // >= n_img for the padding tile of an odd pair: loads read zeros, stores are clipped
+    const int rem = mt % tiles_per_img;
     h0 = (rem / p.tiles_w) * p.bh;
     w0 = (rem % p.tiles_w) * p.bw;
     return true;
@@ -173,14 +175,14 @@ struct StreamTiles {
 };
 struct ResidentTiles {  // a contiguous run of m-tiles per CTA: an image boundary is crossed at most a few times
   int nt_fixed, tiles_per_img;
-  long long m_first, m_end;
+  int m_first, m_end;
   __device__ __forceinline__ int nt_last(const ConvTcParams&) const { return nt_fixed; }
   __device__ __forceinline__ bool get(const ConvTcParams& p, uint32_t iter, int& img, int& h0, int& w0, int& nt) const {
-    const long long mt = m_first + (long long)iter;
+    const int mt = m_first + (int)iter;
     if (mt >= m_end) return false;
     nt = nt_fixed;
-    img = (int)(mt / tiles_per_img);
-    const int rem = (int)(mt % tiles_per_img);
+    img = mt / tiles_per_img;
+    const int rem = mt % tiles_per_img;
     h0 = (rem / p.tiles_w) * p.bh;
     w0 = (rem % p.tiles_w) * p.bw;
     return true;
@@ -497,7 +499,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform: role branches stay convergent
   const int lane = threadIdx.x & 31;
 
   // Cluster pairs (p.pair): the two CTAs run the same (n-tile, K) sequence on neighbouring m-tiles; each loads HALF of
@@ -528,8 +530,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   if (pair) cluster_sync_all();  // the peer's barriers exist before anything remote can reach them
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  if (tmem_base != 0u) {  // one CTA per SM and one allocation per CTA: the MMA issuer relies on base 0
-    if (threadIdx.x == 0) printf("pmoe conv_tc: unexpected TMEM base %u\n", tmem_base);
+  if (__any_sync(0xffffffffu, tmem_base != 0u)) {  // one CTA per SM, one allocation per CTA: the MMA issuer relies on base 0
+    if (threadIdx.x == 0) printf("pmoe conv_tc: unexpected TMEM base %u\n", tmem_base);  // (warp-uniform condition, see the halo kernel)
     __trap();
   }
   const uint32_t pipe_addr = smem_u32(pipe);
@@ -538,8 +540,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   {
     const long long G = pair ? gridDim.x / 2 : gridDim.x;      // work units are split over CTAs, or over pairs
     const long long b = pair ? blockIdx.x / 2 : blockIdx.x;
-    it.t_begin = (p.total_tiles * b) / G;
-    it.t_end = (p.total_tiles * (b + 1)) / G;
+    it.t_begin = (int)((p.total_tiles * b) / G);
+    it.t_end = (int)((p.total_tiles * (b + 1)) / G);
     it.tiles_per_img = p.tiles_w * p.tiles_h;
     it.mt_mul = pair ? 2 : 1;
     it.mt_add = (int)crank;
@@ -593,13 +595,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         const uint32_t acc = titer & 1u;
         const uint32_t acc_phase = (titer >> 1) & 1u;
         const long long wa = dc.now();
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1u);
         dc.add(1, wa);
         tc_fence_after();
         const uint32_t d_tmem = acc * BN;  // TMEM base is 0 (checked after the allocation)
         for (int ki = 0; ki < p.kiters; ++ki) {
           const long long wf = dc.now();
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_warp(&full_bar[stage], phase);
           dc.add(0, wf);
           tc_fence_after();
           const uint32_t a_lo = umma_desc_lo(pipe_addr + (uint32_t)stage * C::STAGE_BYTES, 16u);
@@ -680,7 +682,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
   uint64_t* wb_empty = wb_full + kMaxWStages;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(wb_empty + kMaxWStages);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform: role branches stay convergent
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::MAX_STAGES; ++s) {
@@ -711,17 +713,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  if (tmem_base != 0u) {
-    if (threadIdx.x == 0) printf("pmoe conv_tc_halo: unexpected TMEM base %u\n", tmem_base);
-    __trap();
+  if (__any_sync(0xffffffffu, tmem_base != 0u)) {  // warp-uniform on purpose: a thread-dependent trap is a possible partial exit,
+    if (threadIdx.x == 0) printf("pmoe conv_tc_halo: unexpected TMEM base %u\n", tmem_base);  // after which ptxas cannot prove
+    __trap();                                                                                // the MMA warp converged
   }
 
   ResidentTiles it;
   it.nt_fixed = (int)(blockIdx.x % p.tiles_n);
   {
     const long long c = blockIdx.x / p.tiles_n, per_n = gridDim.x / p.tiles_n;
-    it.m_first = (p.m_tiles * c) / per_n;
-    it.m_end = (p.m_tiles * (c + 1)) / per_n;
+    it.m_first = (int)((p.m_tiles * c) / per_n);
+    it.m_end = (int)((p.m_tiles * (c + 1)) / per_n);
   }
   it.tiles_per_img = p.tiles_w * p.tiles_h;
   int img, h0, w0, nt;
@@ -815,20 +817,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
         const uint32_t acc = titer & 1u;
         const uint32_t acc_phase = (titer >> 1) & 1u;
         const long long wa = dc.now();
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1u);
         dc.add(1, wa);
         tc_fence_after();
         const uint32_t d_tmem = acc * BN;
         for (int g = 0; g < p.n_chunks; ++g) {
           const long long wf = dc.now();
-          mbar_wait(&full_bar[hs], hphase);
+          mbar_wait_warp(&full_bar[hs], hphase);
           dc.add(0, wf);
           tc_fence_after();
           const uint32_t h_lo = halo_lo + (uint32_t)hs * (uint32_t)(C::HALO_BYTES >> 4);
 #pragma unroll 1
           for (int t = 0; t < 9; ++t) {
             const long long wf2 = dc.now();
-            mbar_wait(&wb_full[ws], wphase);
+            mbar_wait_warp(&wb_full[ws], wphase);
             dc.add(0, wf2);
             tc_fence_after();
             const uint32_t a_lo = h_lo + (uint32_t)(((t / 3) * 10 + (t % 3)) * C::ROWB >> 4);
@@ -857,7 +859,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
       constexpr uint32_t a_hi = umma_desc_hi(10u * C::ROWB, C::LAYOUT);  // 8-row groups of a halo view are 10 rows apart
       constexpr uint32_t b_hi = umma_desc_hi(8u * C::ROWB, C::LAYOUT);
       if (!p.w_per_img) {
-        mbar_wait(wfull_bar, 0);
+        mbar_wait_warp(wfull_bar, 0);
         tc_fence_after();
       }
       const uint32_t w_lo = umma_desc_lo(smem_u32(wsm), 16u);
@@ -871,7 +873,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
       uint32_t w_loads = 0;
       for (uint32_t titer = 0; it.get(p, titer, img, h0, w0, nt); ++titer) {
         if (p.w_per_img && img != w_img) {
-          mbar_wait(wfull_bar, w_loads & 1u);
+          mbar_wait_warp(wfull_bar, w_loads & 1u);
           tc_fence_after();
           w_img = img;
           ++w_loads;
@@ -879,13 +881,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
         const uint32_t acc = titer & 1u;
         const uint32_t acc_phase = (titer >> 1) & 1u;
         const long long wa = dc.now();
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+        mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1u);
         dc.add(1, wa);
         tc_fence_after();
         const uint32_t d_tmem = acc * BN;  // TMEM base is 0 (checked after the allocation)
         for (int g = 0; g < p.n_chunks; ++g) {
           const long long wf = dc.now();
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_warp(&full_bar[stage], phase);
           dc.add(0, wf);
           tc_fence_after();
           const uint32_t h_lo = halo_lo + (uint32_t)stage * (uint32_t)(C::HALO_BYTES >> 4);
@@ -926,6 +928,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
   }
 }
 
+#ifdef PMOE_KERNELS_ONLY  // codegen experiments instantiate single kernels from another translation unit
+}  // namespace pmoe
+#else
 // ------------------------------------------------------------------------------------------ host
 static void choose_tile(int H, int W, int* bh_out, int* bw_out) {
   // fewest 128-row tiles first, then the smallest halo (squarer patches re-use more of L2)
@@ -1147,7 +1152,10 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
         }
       if (halo_bn < 64 && d->cout_pad >= 64) halo_bn = 0;  // would starve the MMA: stream the taps instead
       static const bool wstream_off = getenv("PMOE_NO_WSTREAM") != nullptr;
-      if (!halo_bn && !wstream_off && d->ck == 64 && d->cout_pad % 128 == 0) {
+      // An N = 64 tile is bound by shared-memory operand reads (A 4 KB + B 2 KB per K=16 step: ~60 clk measured against 32 on
+      // the tensor pipe), so when cout allows N >= 128 the weights are streamed through a ring rather than kept resident at
+      // N = 64 (measured: 112x112 256->128 at N = 128 streams at 1.4 PFLOP/s). Per-image weights need the resident variant.
+      if (halo_bn < 128 && !wstream_off && d->ck == 64 && d->cout_pad % 128 == 0 && d->wpack_img_stride <= 0) {
         halo_bn = d->cout_pad % 256 == 0 ? 256 : 128;  // halo input tiles + weight tiles streamed through a ring
         p.stream_w = 1;
       }
@@ -1172,6 +1180,10 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   p.total_tiles = (long long)p.tiles_w * p.tiles_h * p.n_img * p.tiles_n;
   if (p.total_tiles <= 0) {
     set_error("conv_tc: empty output");
+    return PMOE_ERR_ARG;
+  }
+  if (p.total_tiles > 0x3fffffffLL) {  // the device-side tile arithmetic is 32-bit
+    set_error("conv_tc: too many tiles");
     return PMOE_ERR_ARG;
   }
   int kiters = 0;
@@ -1483,3 +1495,4 @@ extern "C" int pmoe_dbg_umma_view(const void* a_bf16, int rows, const void* b_bf
   dbg_umma_view_kernel<<<1, 128, smem_bytes, stream>>>(p);
   return check_launch("dbg_umma_view");
 }
+#endif  // PMOE_KERNELS_ONLY

@@ -56,6 +56,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait executed by a whole converged warp with a WARP-UNIFORM loop condition (vote): the compiler's uniformity analysis
+// then keeps the code after the wait in uniform control flow, so the MMA issuer's descriptor arithmetic stays in uniform
+// registers (UIADD3 -> UTCHMMA) instead of vector registers + R2UR + ELECT per MMA.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+  const long long t0 = clock64();
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if (clock64() - t0 > 4000000000LL) {
+      if ((threadIdx.x & 31) == 0)
+        printf("pmoe: mbarrier wait timed out (block %d warp %d parity %u)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), parity);
+      __trap();
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

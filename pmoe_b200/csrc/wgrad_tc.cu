@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
   uint64_t* done_bar = empty_bar + kWgMaxStages;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(done_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches below stay convergent for ptxas
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWgMaxStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -83,7 +84,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  if (tmem_base != 0u) {  // one CTA per SM, one allocation of all 512 columns: the MMA issuer relies on base 0
+  // one CTA per SM, one allocation of all 512 columns: the MMA issuer relies on base 0. The condition is warp-uniform on
+  // purpose: a thread-dependent trap is a possible partial exit after which ptxas cannot prove the MMA warp converged.
+  if (__any_sync(0xffffffffu, tmem_base != 0u)) {
     if (threadIdx.x == 0) printf("pmoe conv_wgrad_tc: unexpected TMEM base %u\n", tmem_base);
     __trap();
   }
@@ -96,8 +99,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
   u /= p.n_groups;
   const int g = u % p.n_chunks;
   const int nt = u / p.n_chunks;
-  const long long t_begin = (p.m_tiles * split) / p.splits;
-  const long long t_end = (p.m_tiles * (split + 1)) / p.splits;
+  // 32-bit tile arithmetic below: a 64-bit division is a subroutine call, and a call inside the lane-0 producer branch
+  // makes ptxas give up on proving the MMA warp converged
+  const int t_begin = (int)((p.m_tiles * split) / p.splits);
+  const int t_end = (int)((p.m_tiles * (split + 1)) / p.splits);
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int npairs = p.group_pairs[grp];
   const int pair0 = p.group_first[grp];
@@ -108,9 +113,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long t = t_begin; t < t_end; ++t) {
-        const int img = (int)(t / tiles_per_img);
-        const int rem = (int)(t % tiles_per_img);
+      for (int t = t_begin; t < t_end; ++t) {
+        const int img = t / tiles_per_img;
+        const int rem = t % tiles_per_img;
         const int h0 = (rem / p.tiles_w) * 16, w0 = (rem % p.tiles_w) * 8;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* st = pipe + (size_t)stage * stage_bytes;
@@ -132,8 +137,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_kernel(const __gr
       int stage = 0;
       uint32_t phase = 0;
       bool first = true;
-      for (long long t = t_begin; t < t_end; ++t) {
-        mbar_wait(&full_bar[stage], phase);
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait_warp(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t halo = smem_u32(pipe + (size_t)stage * stage_bytes);
         const uint32_t dyb = halo + kWgHaloBytes;
@@ -251,7 +256,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_stream_kernel(con
   uint64_t* done_bar = dy_empty + 2;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(done_bar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role branches below stay convergent for ptxas
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kWgMaxStages; ++s) {
       mbar_init(&a_full[s], 1);
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_stream_kernel(con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  if (tmem_base != 0u) {
+  if (__any_sync(0xffffffffu, tmem_base != 0u)) {  // warp-uniform condition (see conv_wgrad_tc_kernel)
     if (threadIdx.x == 0) printf("pmoe conv_wgrad_tc_stream: unexpected TMEM base %u\n", tmem_base);
     __trap();
   }
@@ -291,8 +297,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_stream_kernel(con
   u /= p.splits;
   const int grp = u % p.n_groups;
   const int nt = u / p.n_groups;
-  const long long t_begin = (p.m_tiles * split) / p.splits;
-  const long long t_end = (p.m_tiles * (split + 1)) / p.splits;
+  // 32-bit tile arithmetic below: a 64-bit division is a subroutine call, and a call inside the lane-0 producer branch
+  // makes ptxas give up on proving the MMA warp converged
+  const int t_begin = (int)((p.m_tiles * split) / p.splits);
+  const int t_end = (int)((p.m_tiles * (split + 1)) / p.splits);
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int unit0 = grp * p.n_acc * UPM;
   int n_acc = (p.n_units - unit0 + UPM - 1) / UPM;  // accumulators with at least one live unit
@@ -305,9 +313,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_stream_kernel(con
       int as = 0;
       uint32_t aphase = 0;
       uint32_t it = 0;
-      for (long long t = t_begin; t < t_end; ++t, ++it) {
-        const int img = (int)(t / tiles_per_img);
-        const int rem = (int)(t % tiles_per_img);
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int img = t / tiles_per_img;
+        const int rem = t % tiles_per_img;
         const int h0 = (rem / p.tiles_w) * p.bh, w0 = (rem % p.tiles_w) * p.bw;
         const uint32_t ds = it & 1u, dphase = (it >> 1) & 1u;
         mbar_wait(&dy_empty[ds], dphase ^ 1u);
@@ -339,13 +347,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_stream_kernel(con
       int as = 0;
       uint32_t aphase = 0;
       uint32_t it = 0;
-      for (long long t = t_begin; t < t_end; ++t, ++it) {
+      for (int t = t_begin; t < t_end; ++t, ++it) {
         const uint32_t ds = it & 1u, dphase = (it >> 1) & 1u;
-        mbar_wait(&dy_full[ds], dphase);
+        mbar_wait_warp(&dy_full[ds], dphase);
         tc_fence_after();
         const uint32_t dyb = smem_u32(dy_pipe + ds * dy_stage_bytes);
         for (int a = 0; a < n_acc; ++a) {
-          mbar_wait(&a_full[as], aphase);
+          mbar_wait_warp(&a_full[as], aphase);
           tc_fence_after();
           const uint32_t ab = smem_u32(a_pipe + (size_t)as * kWgAStage);
           const uint32_t d_tmem = (uint32_t)(a * p.N);  // TMEM base is 0 (checked after the allocation)

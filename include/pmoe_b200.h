@@ -151,15 +151,20 @@ int pmoe_affine_act(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, c
                     const PmoeView4* residual, int32_t act, pmoe_stream_t stream);
 
 /* ---- backward halves (eltwise_bwd.cu) ------------------------------------------------------------- */
-/* dy = dz * act'(z); sum_dy[c] += sum dy, sum_dy_xhat[c] += sum dy*(x-mean)*rstd  (native_batch_norm_backward reductions) */
+/* dy = dz * act'(z); sum_dy[c] += sum dy, sum_dy_xhat[c] += sum dy*(x-mean)*rstd  (native_batch_norm_backward reductions).
+ * fwd_scale/fwd_shift (optional): with act = RELU and a null z view the mask is recomputed as fmaf(x, fwd_scale[c],
+ * fwd_shift[c]) > 0 — exactly what pmoe_affine_act evaluated in the forward — so the saved output is not read at all
+ * (contiguous bf16 only; PMOE_ERR_UNSUPPORTED otherwise). */
 int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
-                       const float* mean, const float* rstd, double* sum_dy, double* sum_dy_xhat, pmoe_stream_t stream);
+                       const float* mean, const float* rstd, double* sum_dy, double* sum_dy_xhat, const float* fwd_scale,
+                       const float* fwd_shift, pmoe_stream_t stream);
 /* dx = gamma*rstd*(dy - sum_dy/N - xhat*sum_dy_xhat/N) (batch_stats) or dy*gamma (eval BN / plain);
- * dres (optional) receives the masked dy for a residual branch. */
+ * dres (optional) receives the masked dy for a residual branch. fwd_scale/fwd_shift: as in pmoe_bn_bwd_reduce. */
 int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
                       const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
                       const double* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
-                      const PmoeView4* dres, int32_t accumulate_dres, pmoe_stream_t stream);
+                      const PmoeView4* dres, int32_t accumulate_dres, const float* fwd_scale, const float* fwd_shift,
+                      pmoe_stream_t stream);
 int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* dx, int32_t dtype, int32_t k, int32_t stride,
                      int32_t pad, int32_t accumulate, pmoe_stream_t stream);
 int pmoe_maxpool_bwd_idx(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* dx, int32_t dtype, int32_t k,

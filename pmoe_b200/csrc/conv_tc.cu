@@ -932,8 +932,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_halo_kernel(const __gr
 }  // namespace pmoe
 #else
 // ------------------------------------------------------------------------------------------ host
-static void choose_tile(int H, int W, int* bh_out, int* bw_out) {
-  // fewest 128-row tiles first, then the smallest halo (squarer patches re-use more of L2)
+static void choose_tile(int H, int W, int* bh_out, int* bw_out, bool prefer_rows = false) {
+  // fewest 128-row tiles first, then the smallest halo (squarer patches re-use more of L2). prefer_rows: the epilogue also
+  // writes fp32 NCHW straight from registers, one pixel per lane, so a 32-pixel-wide patch makes every warp store one
+  // contiguous 128-byte row per channel instead of four 32-byte pieces.
   long long best_tiles = -1, best_halo = 0;
   int best_bw = 1, best_bh = 1;
   const int wmax = W < 128 ? W : 128;
@@ -942,7 +944,7 @@ static void choose_tile(int H, int W, int* bh_out, int* bw_out) {
     if (bh > H) bh = H;
     if (bh < 1) continue;
     const long long tiles = (long long)((W + bw - 1) / bw) * ((H + bh - 1) / bh);
-    const long long halo = (long long)(bw + 2) * (bh + 2);
+    const long long halo = prefer_rows ? (bw == 32 ? 0 : 1000 + (bw > 32 ? bw - 32 : 32 - bw)) : (long long)(bw + 2) * (bh + 2);
     if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && halo < best_halo)) {
       best_tiles = tiles;
       best_halo = halo;
@@ -1169,7 +1171,7 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
     p.bw = 8;  // the fused max-pool finds its window partners with lane shuffles: power-of-two tile width
     p.bh = 16;
   } else {
-    choose_tile(o.h, o.w, &p.bh, &p.bw);
+    choose_tile(o.h, o.w, &p.bh, &p.bw, d->nchw_out != nullptr);
   }
   p.H = o.h;
   p.W = o.w;

@@ -500,15 +500,26 @@ __device__ __forceinline__ uint4 f32_to_bf16x8(const float (&v)[8]) {
   return r;
 }
 
+// ACT: 0 = no activation, 1 = ReLU mask read from the saved output z, 2 = ReLU mask recomputed from x with the forward's own
+// scale/shift (fmaf(x, scale, shift) > 0 is bit-for-bit what affine_act computed before its max(.,0)), which saves the read of z.
 template <int ACT, bool HAS_X>
 __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_fast_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z,
                                                                          const uint4* __restrict__ x, long long npix, int cg,
                                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                          double* __restrict__ sum_dy, double* __restrict__ sum_dy_xhat,
-                                                                         long long pix_per_block) {
+                                                                         long long pix_per_block, const float* __restrict__ fwd_scale,
+                                                                         const float* __restrict__ fwd_shift) {
   __shared__ float sm[kRedThreads * 8];
   const int lanes = blockDim.x / cg;
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+  float msc[8], msh[8];
+  if (ACT == 2) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      msc[q] = __ldg(fwd_scale + g * 8 + q);
+      msh[q] = __ldg(fwd_shift + g * 8 + q);
+    }
+  }
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   long long p1 = p0 + pix_per_block;
   if (p1 > npix) p1 = npix;
@@ -522,24 +533,27 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_fast_kernel(const u
         const bool ok = pp < p1;
         const long long off = ok ? pp * cg + g : p * cg + g;
         rd[u] = ok ? __ldg(dz + off) : make_uint4(0u, 0u, 0u, 0u);
-        if (ACT) rz[u] = __ldg(z + off);
-        if (HAS_X) rx[u] = __ldg(x + off);
+        if (ACT == 1) rz[u] = __ldg(z + off);
+        if (HAS_X || ACT == 2) rx[u] = __ldg(x + off);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        float d[8];
+        float d[8], xv[8];
         bf16x8_to_f32(rd[u], d);
-        if (ACT) {
+        if (HAS_X || ACT == 2) bf16x8_to_f32(rx[u], xv);
+        if (ACT == 1) {
           float zv[8];
           bf16x8_to_f32(rz[u], zv);
 #pragma unroll
           for (int q = 0; q < 8; ++q) d[q] = zv[q] > 0.f ? d[q] : 0.f;
         }
+        if (ACT == 2) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) d[q] = fmaf(xv[q], msc[q], msh[q]) > 0.f ? d[q] : 0.f;
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q) a[q] += d[q];
         if (HAS_X) {
-          float xv[8];
-          bf16x8_to_f32(rx[u], xv);
 #pragma unroll
           for (int q = 0; q < 8; ++q) b[q] = fmaf(d[q], xv[q], b[q]);
         }
@@ -566,10 +580,19 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(const uint4* __r
                                                                 int accumulate_dres, long long total, int cg,
                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                 const float* __restrict__ gamma, const double* __restrict__ sum_dy,
-                                                                const double* __restrict__ sum_dy_xhat, float inv_n) {
+                                                                const double* __restrict__ sum_dy_xhat, float inv_n,
+                                                                const float* __restrict__ fwd_scale, const float* __restrict__ fwd_shift) {
   const long long stride = (long long)gridDim.x * blockDim.x;  // a multiple of cg: one channel group per thread
   const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int g = (int)(first % cg);
+  float msc[8], msh[8];  // ACT == 2: ReLU mask recomputed from x (see bn_bwd_reduce_fast_kernel)
+  if (ACT == 2) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      msc[q] = __ldg(fwd_scale + g * 8 + q);
+      msh[q] = __ldg(fwd_shift + g * 8 + q);
+    }
+  }
   // dx = gamma*rstd*(d - c1 - (x - mean)*rstd*c2) = A*d + B*x + C
   float A[8], Bc[8], Cc[8];
 #pragma unroll
@@ -596,21 +619,26 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(const uint4* __r
       ok[u] = ii < total;
       const long long off = ok[u] ? ii : i;
       rd[u] = __ldg(dz + off);
-      if (ACT) rz[u] = __ldg(z + off);
-      if (BATCH) rx[u] = __ldg(x + off);
+      if (ACT == 1) rz[u] = __ldg(z + off);
+      if (BATCH || ACT == 2) rx[u] = __ldg(x + off);
       if (dres != nullptr && accumulate_dres) ro[u] = dres[off];
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (!ok[u]) continue;
       const long long ii = i + (long long)u * stride;
-      float d[8];
+      float d[8], xv[8];
       bf16x8_to_f32(rd[u], d);
-      if (ACT) {
+      if (BATCH || ACT == 2) bf16x8_to_f32(rx[u], xv);
+      if (ACT == 1) {
         float zv[8];
         bf16x8_to_f32(rz[u], zv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) d[q] = zv[q] > 0.f ? d[q] : 0.f;
+      }
+      if (ACT == 2) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) d[q] = fmaf(xv[q], msc[q], msh[q]) > 0.f ? d[q] : 0.f;
       }
       if (dres != nullptr) {
         float o[8];
@@ -627,8 +655,6 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(const uint4* __r
       if (dx != nullptr) {
         float o[8];
         if (BATCH) {
-          float xv[8];
-          bf16x8_to_f32(rx[u], xv);
 #pragma unroll
           for (int q = 0; q < 8; ++q) o[q] = fmaf(A[q], d[q], fmaf(Bc[q], xv[q], Cc[q]));
         } else {
@@ -690,14 +716,17 @@ using namespace pmoe;
 extern "C" {
 
 int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
-                       const float* mean, const float* rstd, double* sum_dy, double* sum_dy_xhat, pmoe_stream_t stream_) {
+                       const float* mean, const float* rstd, double* sum_dy, double* sum_dy_xhat, const float* fwd_scale,
+                       const float* fwd_shift, pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc;
+  // mask_x: no saved output given; the ReLU mask is recomputed from x with the forward's scale/shift
+  const bool mask_x = act == PMOE_ACT_RELU && (!z || !z->ptr) && x && x->ptr && fwd_scale && fwd_shift;
   if ((rc = chk(dz, dtype, "bn_bwd_reduce dz"))) return rc;
-  if ((rc = chk(z, dtype, "bn_bwd_reduce z", act == PMOE_ACT_NONE))) return rc;
+  if ((rc = chk(z, dtype, "bn_bwd_reduce z", act == PMOE_ACT_NONE || mask_x))) return rc;
   if ((rc = chk(x, dtype, "bn_bwd_reduce x", true))) return rc;
   const int cg = dz->c / 8;
-  if (!sum_dy || cg > 256 || (act != PMOE_ACT_NONE && (!z || !z->ptr))) {
+  if (!sum_dy || cg > 256 || (act != PMOE_ACT_NONE && !mask_x && (!z || !z->ptr))) {
     set_error("bn_bwd_reduce: bad arguments");
     return PMOE_ERR_ARG;
   }
@@ -709,16 +738,22 @@ int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4*
   const bool flat = all_flat(dz, {dz, z, x});
   if (flat && dtype == PMOE_BF16 && (act == PMOE_ACT_NONE || act == PMOE_ACT_RELU) && (!sum_dy_xhat || (x && x->ptr && mean && rstd))) {
     const uint4* pdz = static_cast<const uint4*>(dz->ptr);
-    const uint4* pz = act ? static_cast<const uint4*>(z->ptr) : nullptr;
+    const uint4* pz = (act && !mask_x) ? static_cast<const uint4*>(z->ptr) : nullptr;
     const bool has_x = sum_dy_xhat != nullptr;
-    const uint4* px = has_x ? static_cast<const uint4*>(x->ptr) : nullptr;
-#define PMOE_RED_FAST(A, X) bn_bwd_reduce_fast_kernel<A, X><<<(unsigned)blocks, 256, 0, stream>>>(pdz, pz, px, npix, cg, mean, rstd, sum_dy, sum_dy_xhat, ppb)
-    if (act && has_x) PMOE_RED_FAST(1, true);
+    const uint4* px = (has_x || mask_x) ? static_cast<const uint4*>(x->ptr) : nullptr;
+#define PMOE_RED_FAST(A, X) bn_bwd_reduce_fast_kernel<A, X><<<(unsigned)blocks, 256, 0, stream>>>(pdz, pz, px, npix, cg, mean, rstd, sum_dy, sum_dy_xhat, ppb, fwd_scale, fwd_shift)
+    if (mask_x && has_x) PMOE_RED_FAST(2, true);
+    else if (mask_x) PMOE_RED_FAST(2, false);
+    else if (act && has_x) PMOE_RED_FAST(1, true);
     else if (act) PMOE_RED_FAST(1, false);
     else if (has_x) PMOE_RED_FAST(0, true);
     else PMOE_RED_FAST(0, false);
 #undef PMOE_RED_FAST
     return check_launch("bn_bwd_reduce");
+  }
+  if (mask_x) {
+    set_error("bn_bwd_reduce: the mask-from-x form needs contiguous bf16 tensors");
+    return PMOE_ERR_UNSUPPORTED;
   }
   if (flat) {
     BW_DISPATCH(dtype, (bn_bwd_reduce_kernel<T, true><<<(unsigned)blocks, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, sum_dy, sum_dy_xhat, ppb)));
@@ -731,11 +766,13 @@ int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4*
 int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
                       const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
                       const double* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
-                      const PmoeView4* dres, int32_t accumulate_dres, pmoe_stream_t stream_) {
+                      const PmoeView4* dres, int32_t accumulate_dres, const float* fwd_scale, const float* fwd_shift,
+                      pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc;
+  const bool mask_x = act == PMOE_ACT_RELU && (!z || !z->ptr) && x && x->ptr && fwd_scale && fwd_shift;
   if ((rc = chk(dz, dtype, "bn_bwd_apply dz"))) return rc;
-  if ((rc = chk(z, dtype, "bn_bwd_apply z", act == PMOE_ACT_NONE))) return rc;
+  if ((rc = chk(z, dtype, "bn_bwd_apply z", act == PMOE_ACT_NONE || mask_x))) return rc;
   if ((rc = chk(x, dtype, "bn_bwd_apply x", !batch_stats))) return rc;
   if ((rc = chk(dx, dtype, "bn_bwd_apply dx", true))) return rc;
   if ((rc = chk(dres, dtype, "bn_bwd_apply dres", true))) return rc;
@@ -748,20 +785,26 @@ int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* 
   const bool flat_all = all_flat(dz, {dz, z, x, dx, dres});
   if (flat_all && dtype == PMOE_BF16 && (act == PMOE_ACT_NONE || act == PMOE_ACT_RELU)) {
     const uint4* pdz = static_cast<const uint4*>(dz->ptr);
-    const uint4* pz = act ? static_cast<const uint4*>(z->ptr) : nullptr;
-    const uint4* px = batch_stats ? static_cast<const uint4*>(x->ptr) : nullptr;
+    const uint4* pz = (act && !mask_x) ? static_cast<const uint4*>(z->ptr) : nullptr;
+    const uint4* px = (batch_stats || mask_x) ? static_cast<const uint4*>(x->ptr) : nullptr;
     uint4* pdx = (dx && dx->ptr) ? static_cast<uint4*>(dx->ptr) : nullptr;
     uint4* pdr = (dres && dres->ptr) ? static_cast<uint4*>(dres->ptr) : nullptr;
     const int cg = dz->c / 8;
     int g4 = (grid + 3) / 4;  // four items per thread and iteration
     if (256 % cg != 0) g4 = (g4 + cg - 1) / cg * cg;
-#define PMOE_APPLY_FAST(A, B) bn_bwd_apply_fast_kernel<A, B><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n)
-    if (act && batch_stats) PMOE_APPLY_FAST(1, true);
+#define PMOE_APPLY_FAST(A, B) bn_bwd_apply_fast_kernel<A, B><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, fwd_scale, fwd_shift)
+    if (mask_x && batch_stats) PMOE_APPLY_FAST(2, true);
+    else if (mask_x) PMOE_APPLY_FAST(2, false);
+    else if (act && batch_stats) PMOE_APPLY_FAST(1, true);
     else if (act) PMOE_APPLY_FAST(1, false);
     else if (batch_stats) PMOE_APPLY_FAST(0, true);
     else PMOE_APPLY_FAST(0, false);
 #undef PMOE_APPLY_FAST
     return check_launch("bn_bwd_apply");
+  }
+  if (mask_x) {
+    set_error("bn_bwd_apply: the mask-from-x form needs contiguous bf16 tensors");
+    return PMOE_ERR_UNSUPPORTED;
   }
   if (flat_all) {
     BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T, true><<<grid, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres)));

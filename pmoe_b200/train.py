@@ -98,28 +98,37 @@ def _any_rg(params):
 
 # ------------------------------------------------------------------------------------------------ weight packing
 # ------------------------------------------------------------------------------------------------ raw launch helpers
-def _bn_bwd_reduce(dz, z, x, act, mean, rstd, cpad):
+def _mask_from_x(dz, x, act, fwd):
+    """The ReLU mask can be recomputed from the pre-BN tensor with the forward's own scale/shift (one tensor read less per
+    pass) when the fast contiguous-bf16 kernels apply."""
+    return (fwd is not None and act == "relu" and x is not None and dz.dtype == torch.bfloat16 and dz.is_contiguous()
+            and x.is_contiguous() and x.shape == dz.shape)
+
+
+def _bn_bwd_reduce(dz, z, x, act, mean, rstd, cpad, fwd=None):
     s1 = torch.zeros(cpad, dtype=torch.float64, device=dz.device)
     s2 = torch.zeros(cpad, dtype=torch.float64, device=dz.device) if x is not None else None
+    mx = _mask_from_x(dz, x, act, fwd)
     vdz = view4(dz)
-    vz = view4(z) if z is not None else _lib.null_view()
+    vz = view4(z) if (z is not None and not mx) else _lib.null_view()
     vx = view4(x) if x is not None else _lib.null_view()
     check(profiler.launch("bn_bwd_reduce", lambda: lib().pmoe_bn_bwd_reduce(
         C.byref(vdz), C.byref(vz), C.byref(vx), dtype_code(dz), ACT[act], _lib.ptr(mean), _lib.ptr(rstd), s1.data_ptr(),
-        _lib.ptr(s2), stream_ptr())), "bn_bwd_reduce")
+        _lib.ptr(s2), _lib.ptr(fwd[0] if mx else None), _lib.ptr(fwd[1] if mx else None), stream_ptr())), "bn_bwd_reduce")
     return s1, s2
 
 
-def _bn_bwd_apply(dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, batch_stats, dx, dres, acc_dres):
+def _bn_bwd_apply(dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, batch_stats, dx, dres, acc_dres, fwd=None):
+    mx = _mask_from_x(dz, x, act, fwd) and (dx is None or dx.is_contiguous()) and (dres is None or dres.is_contiguous())
     vdz = view4(dz)
-    vz = view4(z) if z is not None else _lib.null_view()
+    vz = view4(z) if (z is not None and not mx) else _lib.null_view()
     vx = view4(x) if x is not None else _lib.null_view()
     vdx = view4(dx) if dx is not None else _lib.null_view()
     vdr = view4(dres) if dres is not None else _lib.null_view()
     check(profiler.launch("bn_bwd_apply", lambda: lib().pmoe_bn_bwd_apply(
         C.byref(vdz), C.byref(vz), C.byref(vx), dtype_code(dz), ACT[act], _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma),
         _lib.ptr(s1), _lib.ptr(s2), float(inv_n), int(batch_stats), C.byref(vdx), C.byref(vdr), int(acc_dres),
-        stream_ptr())), "bn_bwd_apply")
+        _lib.ptr(fwd[0] if mx else None), _lib.ptr(fwd[1] if mx else None), stream_ptr())), "bn_bwd_apply")
 
 
 def _axpy(src, dst, alpha=1.0, bcast=None, accumulate=False):
@@ -298,7 +307,8 @@ def _bn_tail_forward(tape, bn, raw, ssum, ssq, count, cout, cstore, act, residua
         bn.num_batches_tracked += 1
     z_t = out if out is not None else torch.empty(raw.shape, dtype=raw.dtype, device=raw.device)
     nhwc.affine_act(raw, scale[:cstore], shift[:cstore], act, None if residual is None else residual.t, out=z_t)
-    return z_t, mean, rstd
+    # (scale, shift) let the backward recompute the ReLU mask from `raw` instead of reading z (not with a residual add)
+    return z_t, mean, rstd, ((scale, shift) if residual is None else None)
 
 
 def _eval_affine(bn, bias, cout, cop):
@@ -341,14 +351,14 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
     pool = None
     if want_pool:
         pool = pool_out if pool_out is not None else torch.zeros(n, cop, dtype=torch.float32, device=dev)
-    raw = mean = rstd = gamma_p = scale = None
+    raw = mean = rstd = gamma_p = scale = fwd_aff = None
     src_ts = [x.t for x in srcs]
     if bn_train:
         raw = torch.empty(n, h, w, cstore, dtype=dt, device=dev)
         ssum = torch.zeros(cop, dtype=torch.float64, device=dev)
         ssq = torch.zeros(cop, dtype=torch.float64, device=dev)
         ops.conv(src_ts, wp, segs, ck, raw, stat_sum=ssum, stat_sqsum=ssq, flops=flops, tag=tag)
-        z_t, mean, rstd = _bn_tail_forward(tape, bn, raw, ssum, ssq, n * h * w, cout, cstore, act, residual, out)
+        z_t, mean, rstd, fwd_aff = _bn_tail_forward(tape, bn, raw, ssum, ssq, n * h * w, cout, cstore, act, residual, out)
         if want_pool:
             nhwc.channel_sums(z_t, out=pool)
         gamma_p = ops.pad_vec(bn.weight.detach(), cstore, 0.0)
@@ -371,10 +381,10 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
             dres, acc_dres = _grad_buffer(tape, residual)
         dy = torch.empty(n, h, w, cstore, dtype=dt, device=dev)  # gradient w.r.t. the raw conv output
         if bn_train:
-            s1, s2 = _bn_bwd_reduce(dz, z_saved, raw, act, mean, rstd, cstore)
+            s1, s2 = _bn_bwd_reduce(dz, z_saved, raw, act, mean, rstd, cstore, fwd=fwd_aff)
             tape.add_pgrad(bn.weight, s2[:cout])
             tape.add_pgrad(bn.bias, s1[:cout])
-            _bn_bwd_apply(dz, z_saved, raw, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, dy, dres, acc_dres)
+            _bn_bwd_apply(dz, z_saved, raw, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, dy, dres, acc_dres, fwd=fwd_aff)
         else:
             if bn is not None and _any_rg([bn.weight, bn.bias]):
                 raise NotImplementedError("pmoe_b200: gradients of BatchNorm affine parameters in eval mode are not supported")
@@ -607,14 +617,14 @@ def bn_act_op(tape, bn, x, act="relu", tag=""):
     c = x.c
     rg = _rg(x) or _any_rg([bn.weight, bn.bias])
     bn_train = bn.training
-    mean = rstd = gamma_p = scale = None
+    mean = rstd = gamma_p = scale = fwd_aff = None
     if bn_train:
         ssum = torch.zeros(cp, dtype=torch.float64, device=dev)
         ssq = torch.zeros(cp, dtype=torch.float64, device=dev)
         v = view4(x.t)
         check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(v), dtype_code(x.t), ssum.data_ptr(),
                                                                                 ssq.data_ptr(), stream_ptr())), "channel_stats")
-        z_t, mean, rstd = _bn_tail_forward(tape, bn, x.t, ssum, ssq, n * h * w, c, cp, act, None, None)
+        z_t, mean, rstd, fwd_aff = _bn_tail_forward(tape, bn, x.t, ssum, ssq, n * h * w, c, cp, act, None, None)
         gamma_p = ops.pad_vec(bn.weight.detach(), cp, 0.0)
     else:
         scale, shift = _eval_affine(bn, None, c, cp)
@@ -629,10 +639,10 @@ def bn_act_op(tape, bn, x, act="relu", tag=""):
             g, existed = _grad_buffer(tape, x)
             tmp = g if not existed else torch.empty_like(g)
             if bn_train:
-                s1, s2 = _bn_bwd_reduce(dz, zs, x.t, act, mean, rstd, cp)
+                s1, s2 = _bn_bwd_reduce(dz, zs, x.t, act, mean, rstd, cp, fwd=fwd_aff)
                 tape.add_pgrad(bn.weight, s2[:c])
                 tape.add_pgrad(bn.bias, s1[:c])
-                _bn_bwd_apply(dz, zs, x.t, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, tmp, None, False)
+                _bn_bwd_apply(dz, zs, x.t, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, tmp, None, False, fwd=fwd_aff)
             else:
                 if _any_rg([bn.weight, bn.bias]):
                     raise NotImplementedError("pmoe_b200: gradients of BatchNorm affine parameters in eval mode are not supported")

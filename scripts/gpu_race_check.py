@@ -26,7 +26,7 @@ for dtype in (torch.float32, torch.bfloat16):
             s2 = torch.zeros(c, dtype=torch.float64, device="cuda")
             vdz, vz, vx = view4(dz), view4(z), view4(x)
             check(lib().pmoe_bn_bwd_reduce(C.byref(vdz), C.byref(vz), C.byref(vx), dtype_code(dz), 1, mean.data_ptr(), rstd.data_ptr(),
-                                           s1.data_ptr(), s2.data_ptr(), stream_ptr()), "reduce")
+                                           s1.data_ptr(), s2.data_ptr(), None, None, stream_ptr()), "reduce")
             st1 = torch.zeros(c, dtype=torch.float64, device="cuda")
             st2 = torch.zeros(c, dtype=torch.float64, device="cuda")
             check(lib().pmoe_channel_stats(C.byref(vx), dtype_code(x), st1.data_ptr(), st2.data_ptr(), stream_ptr()), "stats")

@@ -164,6 +164,72 @@ __global__ void maxpool_kernel(V4 src, V4 dst, int k, int stride, int pad, const
   }
 }
 
+// Contiguous bf16, compile-time window: one block row per (image, output row), 32-bit index arithmetic only, all K*K window
+// loads issued before the first compare. Same tie rule and argmax codes as maxpool_kernel.
+__device__ __forceinline__ void pool_bf16x8(const uint4& r, float (&v)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    v[2 * q] = __uint_as_float(w[q] << 16);
+    v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+  }
+}
+template <int K, int S, int P, bool IDX>
+__global__ void __launch_bounds__(256) maxpool_fast_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint2* __restrict__ idx_out,
+                                                           int H, int W, int OH, int OW, int cg, int cg_shift) {
+  const int n = blockIdx.x / OH, oh = blockIdx.x - n * OH;
+  const int row_items = OW * cg;
+  const uint4* img = src + (size_t)n * H * W * cg;
+  for (int item = blockIdx.y * blockDim.x + threadIdx.x; item < row_items; item += gridDim.y * blockDim.x) {
+    const int ow = cg_shift >= 0 ? (item >> cg_shift) : item / cg;
+    const int g = item - ow * cg;
+    uint4 raw[K * K];
+    bool ok[K * K];
+#pragma unroll
+    for (int r = 0; r < K; ++r) {
+      const int ih = oh * S - P + r;
+#pragma unroll
+      for (int c = 0; c < K; ++c) {
+        const int iw = ow * S - P + c;
+        ok[r * K + c] = ih >= 0 && ih < H && iw >= 0 && iw < W;
+        if (ok[r * K + c]) raw[r * K + c] = __ldg(img + ((size_t)ih * W + iw) * cg + g);
+      }
+    }
+    float m[8];
+    uint32_t arg[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      m[q] = -INFINITY;
+      arg[q] = 0;
+    }
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) {
+      if (!ok[t]) continue;
+      float v[8];
+      pool_bf16x8(raw[t], v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (v[q] > m[q]) {  // the FIRST maximum in row-major window order wins (ATen max_pool2d tie rule)
+          m[q] = v[q];
+          arg[q] = (uint32_t)t;
+        }
+    }
+    const size_t o = ((size_t)blockIdx.x * OW + ow) * cg + g;
+    uint4 pr;
+    pr.x = pack_bf16x2(m[0], m[1]);
+    pr.y = pack_bf16x2(m[2], m[3]);
+    pr.z = pack_bf16x2(m[4], m[5]);
+    pr.w = pack_bf16x2(m[6], m[7]);
+    dst[o] = pr;
+    if (IDX) {
+      uint2 pk;
+      pk.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      pk.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      idx_out[o] = pk;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- ECA gate: sigmoid(conv1d_k(mean over HW))
 // Channels may be stored as `groups` blocks of `group_c` logical channels every `group_stride`
 // physical channels (the PU-Net mask ring stores 23 logits in 32-channel slots); the 1-D conv runs
@@ -436,6 +502,28 @@ static int maxpool_launch(const PmoeView4* src, const PmoeView4* dst, int32_t dt
     return PMOE_ERR_ARG;
   }
   const long long items = (long long)dst->n * dst->h * dst->w * (dst->c / 8);
+  const auto flat = [](const PmoeView4* v) {
+    return v->sw == v->c && v->sh == (int64_t)v->w * v->c && v->sn == (int64_t)v->h * v->w * v->c;
+  };
+  const bool k3 = k == 3 && stride == 2 && pad == 1, k2 = k == 2 && stride == 2 && pad == 0;
+  if (dtype == PMOE_BF16 && !scale && !shift && !relu && (k3 || k2) && flat(src) && flat(dst) && src->c == dst->c &&
+      (long long)dst->n * dst->h < 2147483647LL && (long long)src->h * src->w * src->c < 2147483647LL) {
+    const int cg = dst->c / 8;
+    int cg_shift = -1;
+    for (int sft = 0; sft < 12; ++sft)
+      if ((1 << sft) == cg) cg_shift = sft;
+    const dim3 grid((unsigned)(dst->n * dst->h), (unsigned)((dst->w * cg + 255) / 256));
+    const uint4* ps = static_cast<const uint4*>(src->ptr);
+    uint4* pd = static_cast<uint4*>(dst->ptr);
+    uint2* pi = reinterpret_cast<uint2*>(idx_out);
+#define PMOE_POOL_FAST(K, S, P, I) maxpool_fast_kernel<K, S, P, I><<<grid, 256, 0, stream>>>(ps, pd, pi, src->h, src->w, dst->h, dst->w, cg, cg_shift)
+    if (k3 && idx_out) PMOE_POOL_FAST(3, 2, 1, true);
+    else if (k3) PMOE_POOL_FAST(3, 2, 1, false);
+    else if (idx_out) PMOE_POOL_FAST(2, 2, 0, true);
+    else PMOE_POOL_FAST(2, 2, 0, false);
+#undef PMOE_POOL_FAST
+    return check_launch("maxpool");
+  }
   DISPATCH_DTYPE(dtype, (maxpool_kernel<T><<<grid_for(items, 256), 256, 0, stream>>>(to_v4(*src), to_v4(*dst), k, stride, pad, scale, shift, relu, idx_out)));
   return check_launch("maxpool");
 }

@@ -500,6 +500,63 @@ __device__ __forceinline__ uint4 f32_to_bf16x8(const float (&v)[8]) {
   return r;
 }
 
+// Contiguous bf16, compile-time window (3x3/s2/p1 and 2x2/s2): at most WN x WN windows cover an input pixel; their argmax
+// codes and upstream gradients are all loaded before the first compare, indices are 32-bit, no divisions by run-time values.
+template <int K, int S, int P>
+__global__ void __launch_bounds__(256) maxpool_bwd_fast_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
+                                                               uint4* __restrict__ dx, int H, int W, int OH, int OW, int cg,
+                                                               int cg_shift, int accumulate) {
+  constexpr int WN = (K + S - 1) / S;  // windows per axis that can contain one input pixel
+  const int n = blockIdx.x / H, ih = blockIdx.x - n * H;
+  const int row_items = W * cg;
+  const int oh_hi = (ih + P) / S;
+  for (int item = blockIdx.y * blockDim.x + threadIdx.x; item < row_items; item += gridDim.y * blockDim.x) {
+    const int iw = cg_shift >= 0 ? (item >> cg_shift) : item / cg;
+    const int g = item - iw * cg;
+    const int ow_hi = (iw + P) / S;
+    uint2 code[WN * WN];
+    uint4 grad[WN * WN];
+    uint32_t want[WN * WN];
+    bool ok[WN * WN];
+#pragma unroll
+    for (int a = 0; a < WN; ++a) {
+      const int oh = oh_hi - a, r = ih + P - oh * S;  // row of this pixel inside window oh
+#pragma unroll
+      for (int b = 0; b < WN; ++b) {
+        const int ow = ow_hi - b, c = iw + P - ow * S;
+        const int t = a * WN + b;
+        ok[t] = oh >= 0 && oh < OH && ow >= 0 && ow < OW && r < K && c < K;
+        want[t] = (uint32_t)(r * K + c);
+        if (ok[t]) {
+          const size_t o = (((size_t)n * OH + oh) * OW + ow) * cg + g;
+          code[t] = __ldg(idx + o);
+          grad[t] = __ldg(dy + o);
+        }
+      }
+    }
+    const size_t od = ((size_t)blockIdx.x * W + iw) * cg + g;
+    float o[8];
+    if (accumulate) bf16x8_to_f32(dx[od], o);
+    else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < WN * WN; ++t) {
+      if (!ok[t]) continue;
+      float d[8];
+      bf16x8_to_f32(grad[t], d);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t a = ((q < 4 ? code[t].x : code[t].y) >> (8 * (q & 3))) & 0xffu;
+        if (a == want[t]) o[q] += d[q];
+      }
+    }
+    dx[od] = f32_to_bf16x8(o);
+  }
+}
+
+
 // ACT: 0 = no activation, 1 = ReLU mask read from the saved output z, 2 = ReLU mask recomputed from x with the forward's own
 // scale/shift (fmaf(x, scale, shift) > 0 is bit-for-bit what affine_act computed before its max(.,0)), which saves the read of z.
 template <int ACT, bool HAS_X>
@@ -851,6 +908,15 @@ int pmoe_maxpool_bwd_idx(const PmoeView4* dy, const uint8_t* idx, const PmoeView
     return PMOE_ERR_UNSUPPORTED;
   }
   dim3 grid((unsigned)rows, (unsigned)((dx->w * cg + 255) / 256));
+  const bool k3 = k == 3 && stride == 2 && pad == 1, k2 = k == 2 && stride == 2 && pad == 0;
+  if (dtype == PMOE_BF16 && (k3 || k2) && all_flat(dx, {dx}) && all_flat(dy, {dy})) {
+    const uint4* pdy = static_cast<const uint4*>(dy->ptr);
+    const uint2* pidx = reinterpret_cast<const uint2*>(idx);
+    uint4* pdx = static_cast<uint4*>(dx->ptr);
+    if (k3) maxpool_bwd_fast_kernel<3, 2, 1><<<grid, 256, 0, stream>>>(pdy, pidx, pdx, dx->h, dx->w, dy->h, dy->w, cg, cg_shift, accumulate);
+    else maxpool_bwd_fast_kernel<2, 2, 0><<<grid, 256, 0, stream>>>(pdy, pidx, pdx, dx->h, dx->w, dy->h, dy->w, cg, cg_shift, accumulate);
+    return check_launch("maxpool_bwd_idx");
+  }
   BW_DISPATCH(dtype, (maxpool_bwd_idx_kernel<T><<<grid, 256, 0, stream>>>(bv4(dy), idx, bv4(dx), k, stride, pad, accumulate, cg_shift)));
   return check_launch("maxpool_bwd_idx");
 }

@@ -235,6 +235,29 @@ int pmoe_mt_clip(const PmoeMtChunk* chunks_dev, int32_t n_chunks, const double* 
 int pmoe_mt_adam(const PmoeMtChunk* chunks_dev, int32_t n_chunks, double lr, double beta1, double beta2, double eps,
                  double weight_decay, int32_t step, int32_t amsgrad, const double* sqnorm, float max_norm, pmoe_stream_t stream);
 
+/* torch.optim.RMSprop step (conf/stage_2.yaml:147-153, train_2.py:67-71) over all chunks. Chunk fields: m = square_avg,
+ * v = momentum_buffer (NULL when momentum == 0), vmax = grad_avg (NULL unless centered); sqnorm/max_norm as in pmoe_mt_adam. */
+int pmoe_mt_rmsprop(const PmoeMtChunk* chunks_dev, int32_t n_chunks, double lr, double alpha, double eps, double weight_decay,
+                    double momentum, const double* sqnorm, float max_norm, pmoe_stream_t stream);
+/* torch.optim.swa_utils.AveragedModel.update_parameters, default avg_fn (train_2.py:119-121,179-187):
+ * chunk.p (averaged) += (chunk.g (current model parameter) - chunk.p) / (n_averaged + 1). */
+int pmoe_mt_swa_update(const PmoeMtChunk* chunks_dev, int32_t n_chunks, int64_t n_averaged, pmoe_stream_t stream);
+
+/* ---- input pipeline (preproc.cu) — SURVEY.md §8f rank 1 ------------------------------------------------------- */
+/* The reference dataset's eval-mode transform for every decoded frame, on the device and bit for bit:
+ * Crop rows [crop_top, hs - crop_bottom) (augmenter.py:43-49) -> torchvision Resize((out_h, out_w)) on a PIL image = Pillow's
+ * antialiased two-pass BILINEAR resample in 22-bit fixed point with a uint8 intermediate (data_loader.py:275-281) ->
+ * ToTensor (/255, data_loader.py:281) -> frames stacked (data_loader.py:288-300).
+ * src: (n, hs, ws, 3) uint8 RGB, contiguous. hbounds/hcoef (out_w x 2, out_w x hksize) and vbounds/vcoef are Pillow's
+ * precompute_coeffs + normalize_coeffs_8bpc tables (built by pmoe_b200/preproc.py). lut255[v] = (float)v / 255.
+ * tmp: (n, hs - crop_top - crop_bottom, out_w, 3) uint8 scratch. dst (optional): fp32, element (i, c, y, x) at
+ * i*dst_sn + c*dst_sc + y*dst_sh + x*dst_sw (NCHW for the module API). dst_u8 (optional): (n, out_h, out_w, 3) uint8. */
+int pmoe_preprocess_frames(const uint8_t* src, int32_t n, int32_t hs, int32_t ws, int32_t crop_top, int32_t crop_bottom,
+                           int32_t out_h, int32_t out_w, const int32_t* hbounds, const int32_t* hcoef, int32_t hksize,
+                           const int32_t* vbounds, const int32_t* vcoef, int32_t vksize, const float* lut255, uint8_t* tmp,
+                           float* dst, int64_t dst_sn, int64_t dst_sc, int64_t dst_sh, int64_t dst_sw, uint8_t* dst_u8,
+                           pmoe_stream_t stream);
+
 /* Library info / errors. */
 int pmoe_version(void);
 const char* pmoe_last_error(void);

@@ -138,6 +138,57 @@ __global__ void __launch_bounds__(256) mt_adam_kernel(const MtChunk* __restrict_
   }
 }
 
+
+// torch.optim.RMSprop (conf/stage_2.yaml:147-153: centered, alpha 0.99, momentum 0) over all chunks. Chunk fields:
+// p = parameter, g = gradient, m = square_avg, v = momentum_buffer (or null), vmax = grad_avg (centered, or null).
+struct RmsArgs {
+  float lr, alpha, om_alpha, eps, weight_decay, momentum, max_norm;
+};
+__global__ void __launch_bounds__(256) mt_rmsprop_kernel(const MtChunk* __restrict__ chunks, int n_chunks, const RmsArgs a,
+                                                         const double* sqnorm) {
+  const float coef = clip_coef_of(sqnorm, a.max_norm);
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const MtChunk ch = chunks[c];
+    for (int i = threadIdx.x; i < ch.n; i += blockDim.x) {
+      float p = ch.p[i];
+      float g = ch.g[i] * coef;
+      if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);
+      const float sq = fmaf(a.om_alpha * g, g, ch.m[i] * a.alpha);  // square_avg.mul_(alpha).addcmul_(g, g, value=1-alpha)
+      ch.m[i] = sq;
+      float avg;
+      if (ch.vmax) {  // centered: grad_avg.lerp_(g, 1-alpha); avg = sqrt(square_avg - grad_avg^2)
+        const float ga0 = ch.vmax[i];
+        const float ga = fmaf(a.om_alpha, g - ga0, ga0);
+        ch.vmax[i] = ga;
+        avg = sqrtf(fmaf(-ga, ga, sq));
+      } else {
+        avg = sqrtf(sq);
+      }
+      avg += a.eps;
+      if (ch.v) {  // momentum: buf.mul_(momentum).addcdiv_(g, avg); p.add_(buf, alpha=-lr)
+        const float buf = fmaf(ch.v[i], a.momentum, g / avg);
+        ch.v[i] = buf;
+        p = fmaf(-a.lr, buf, p);
+      } else {
+        p = fmaf(-a.lr, g / avg, p);  // p.addcdiv_(g, avg, value=-lr)
+      }
+      ch.p[i] = p;
+    }
+  }
+}
+
+// torch.optim.swa_utils.AveragedModel.update_parameters with the default avg_fn (train_2.py:119-121, 179-187):
+// p_swa += (p_model - p_swa) / (n_averaged + 1). Chunk fields: p = averaged parameter, g = current model parameter.
+__global__ void __launch_bounds__(256) mt_swa_kernel(const MtChunk* __restrict__ chunks, int n_chunks, float denom) {
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const MtChunk ch = chunks[c];
+    for (int i = threadIdx.x; i < ch.n; i += blockDim.x) {
+      const float avg = ch.p[i];
+      ch.p[i] = avg + (ch.g[i] - avg) / denom;
+    }
+  }
+}
+
 static int mt_grid(int n_chunks) {
   const int cap = num_sms() * 8;
   return n_chunks < cap ? n_chunks : cap;
@@ -194,4 +245,35 @@ extern "C" int pmoe_mt_adam(const PmoeMtChunk* chunks_dev, int32_t n_chunks, dou
   mt_adam_kernel<<<mt_grid(n_chunks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(reinterpret_cast<const MtChunk*>(chunks_dev),
                                                                                     n_chunks, a, sqnorm);
   return check_launch("mt_adam");
+}
+
+extern "C" int pmoe_mt_rmsprop(const PmoeMtChunk* chunks_dev, int32_t n_chunks, double lr, double alpha, double eps, double weight_decay,
+                               double momentum, const double* sqnorm, float max_norm, pmoe_stream_t stream_) {
+  if (n_chunks <= 0) return PMOE_OK;
+  if (!chunks_dev) {
+    set_error("mt_rmsprop: null chunk table");
+    return PMOE_ERR_ARG;
+  }
+  RmsArgs a;
+  a.lr = (float)lr;
+  a.alpha = (float)alpha;
+  a.om_alpha = (float)(1.0 - alpha);
+  a.eps = (float)eps;
+  a.weight_decay = (float)weight_decay;
+  a.momentum = (float)momentum;
+  a.max_norm = max_norm;
+  mt_rmsprop_kernel<<<mt_grid(n_chunks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(reinterpret_cast<const MtChunk*>(chunks_dev),
+                                                                                       n_chunks, a, sqnorm);
+  return check_launch("mt_rmsprop");
+}
+
+extern "C" int pmoe_mt_swa_update(const PmoeMtChunk* chunks_dev, int32_t n_chunks, int64_t n_averaged, pmoe_stream_t stream_) {
+  if (n_chunks <= 0) return PMOE_OK;
+  if (!chunks_dev || n_averaged < 0) {
+    set_error("mt_swa_update: bad arguments");
+    return PMOE_ERR_ARG;
+  }
+  mt_swa_kernel<<<mt_grid(n_chunks), 256, 0, static_cast<cudaStream_t>(stream_)>>>(reinterpret_cast<const MtChunk*>(chunks_dev), n_chunks,
+                                                                                   (float)(n_averaged + 1));
+  return check_launch("mt_swa_update");
 }

@@ -132,3 +132,77 @@ class FusedAdam(torch.optim.Optimizer):
                 step_no, int(group["amsgrad"]), None if sq is None else sq.data_ptr(), float(max_grad_norm or 0.0), stream_ptr())),
                 "mt_adam")
         return loss
+
+
+class FusedRMSprop(torch.optim.Optimizer):
+    """torch.optim.RMSprop(params, lr, alpha, eps, weight_decay, momentum, centered) — the reference's alternative
+    optimizer (train_2.py:67-71, conf/stage_2.yaml:147-153: centered, alpha 0.99) — with a single-launch step. State
+    names (`square_avg`, `grad_avg`, `momentum_buffer`, `step`) are torch's, so optimizer checkpoints interchange.
+    step(max_grad_norm=...) folds clip_grad_norm_ into the update like FusedAdam."""
+
+    def __init__(self, params, lr=1e-2, alpha=0.99, eps=1e-8, weight_decay=0.0, momentum=0.0, centered=False):
+        super().__init__(params, dict(lr=lr, alpha=alpha, eps=eps, weight_decay=weight_decay, momentum=momentum, centered=centered))
+        self._tables = {}
+
+    @torch.no_grad()
+    def step(self, closure=None, max_grad_norm=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        sq = None
+        if max_grad_norm is not None:
+            sq, _, _ = grad_sqnorm([p for g in self.param_groups for p in g["params"]])
+        for gi, group in enumerate(self.param_groups):
+            rows = []
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                _flat_f32(p, "parameter")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0)
+                    st["square_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    if group["momentum"] > 0:
+                        st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    if group["centered"]:
+                        st["grad_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                rows.append((p, _flat_f32(p.grad, "gradient"), st["square_avg"], st.get("momentum_buffer"), st.get("grad_avg")))
+            if not rows:
+                continue
+            dev = rows[0][0].device
+            tdev, n = self._tables.setdefault((gi, dev), ChunkTable()).get(rows, dev)
+            check(profiler.launch("mt_rmsprop", lambda: lib().pmoe_mt_rmsprop(
+                tdev.data_ptr(), n, float(group["lr"]), float(group["alpha"]), float(group["eps"]), float(group["weight_decay"]),
+                float(group["momentum"]), None if sq is None else sq.data_ptr(), float(max_grad_norm or 0.0), stream_ptr())),
+                "mt_rmsprop")
+        return loss
+
+
+class AveragedModel(torch.optim.swa_utils.AveragedModel):
+    """torch.optim.swa_utils.AveragedModel (train_2.py:119-121) whose update_parameters (train_2.py:179-187) runs as ONE
+    multi-tensor launch over all parameters instead of one lerp per parameter tensor. Default averaging only
+    (equal-weight running mean, parameters only — what the reference constructs); anything else defers to torch."""
+
+    def __init__(self, model, device=None, avg_fn=None, multi_avg_fn=None, use_buffers=False):
+        super().__init__(model, device, avg_fn, multi_avg_fn, use_buffers)
+        self._fused = avg_fn is None and multi_avg_fn is None and not use_buffers
+        self._table = ChunkTable()
+
+    @torch.no_grad()
+    def update_parameters(self, model):
+        mine, theirs = list(self.module.parameters()), list(model.parameters())
+        ok = self._fused and all(a.is_cuda and b.is_cuda and a.dtype == torch.float32 and b.dtype == torch.float32
+                                 and a.is_contiguous() and b.is_contiguous() for a, b in zip(mine, theirs))
+        if not ok:
+            return super().update_parameters(model)
+        n_avg = int(self.n_averaged.item())   # once per epoch
+        if n_avg == 0:
+            torch._foreach_copy_(mine, theirs)
+        else:
+            dev = mine[0].device
+            tdev, n = self._table.get([(a, b.detach(), None, None, None) for a, b in zip(mine, theirs)], dev)
+            check(profiler.launch("mt_swa_update", lambda: lib().pmoe_mt_swa_update(tdev.data_ptr(), n, n_avg, stream_ptr())),
+                  "mt_swa_update")
+        self.n_averaged += 1

@@ -79,3 +79,45 @@ def test_fused_adam_with_folded_clip_equals_clip_then_step():
     oa.step(max_grad_norm=1.0)
     for pa, pb in zip(a, b):
         assert rel_err(pa.detach().cpu(), pb.detach()) < 1e-6
+
+
+@pytest.mark.parametrize("centered,momentum,wd", [(True, 0.0, 0.0), (False, 0.9, 1e-3), (True, 0.5, 1e-4)])
+def test_fused_rmsprop_matches_torch_rmsprop(centered, momentum, wd):
+    """conf/stage_2.yaml:147-153 (centered, alpha 0.99, momentum 0) and the other branches of torch.optim.RMSprop."""
+    from pmoe_b200.optim import FusedRMSprop
+    g = torch.Generator().manual_seed(3)
+    shapes = [(257,), (64, 33), (3, 5, 7), (100000,)]
+    ps_a = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    ps_b = [torch.nn.Parameter(p.detach().clone()) for p in ps_a]
+    kw = dict(lr=2e-4, alpha=0.99, eps=1e-8, weight_decay=wd, momentum=momentum, centered=centered)
+    oa, ob = FusedRMSprop(ps_a, **kw), torch.optim.RMSprop(ps_b, **kw)
+    for it in range(5):
+        for a, b in zip(ps_a, ps_b):
+            gr = torch.randn(a.shape, generator=g).cuda() * (0.1 + it)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+    for a, b in zip(ps_a, ps_b):
+        assert ((a - b).abs().max() / b.abs().max()).item() < 1e-6
+    for a, b in zip(ps_a, ps_b):
+        for k in ("square_avg", "grad_avg", "momentum_buffer"):
+            if k in ob.state[b]:
+                ref = ob.state[b][k]
+                assert ((oa.state[a][k] - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item() < 1e-5, k
+
+
+def test_fused_averaged_model_matches_torch_swa():
+    """train_2.py:119-121,179-187: AveragedModel(model) + update_parameters once per epoch."""
+    from pmoe_b200.optim import AveragedModel
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.ReLU(), torch.nn.Linear(53, 11)).cuda()
+    mine, ref = AveragedModel(net), torch.optim.swa_utils.AveragedModel(net)
+    for it in range(4):
+        with torch.no_grad():
+            for p in net.parameters():
+                p.add_(torch.randn_like(p) * 0.1)
+        mine.update_parameters(net)
+        ref.update_parameters(net)
+    assert int(mine.n_averaged) == int(ref.n_averaged) == 4
+    for a, b in zip(mine.module.parameters(), ref.module.parameters()):
+        assert ((a - b).abs().max() / b.abs().max()).item() < 1e-6

@@ -47,6 +47,20 @@ def _mixture(probs, mean, std):
     return D.MixtureSameFamily(D.Categorical(probs), D.Independent(D.Normal(mean, std), 1))
 
 
+@torch.no_grad()
+def sample_mixture(probs, mean, std):
+    """One draw per row from MixtureSameFamily(Categorical(probs), Independent(Normal(mean, std), 1)) — what the reference's
+    `sample()` returns (moe.py:127-133) — written without torch.distributions: component k by inverse CDF of one uniform,
+    then mean[k] + std[k] * eps. Same distribution, but no host synchronisation (torch.normal validates `std >= 0` with an
+    `.item()`, which also forbids CUDA-graph capture of the B = 1 agent tick)."""
+    B, K = probs.shape
+    u = torch.rand(B, 1, device=probs.device, dtype=probs.dtype)
+    k = (u >= probs.cumsum(-1)).sum(-1).clamp_(max=K - 1)                      # (B,)
+    idx = k.view(B, 1, 1).expand(B, 1, mean.shape[-1])
+    m, s = mean.gather(1, idx).squeeze(1), std.gather(1, idx).squeeze(1)
+    return m + s * torch.randn_like(m)
+
+
 class BaseExpert(nn.Module):
     """Parameter container of one expert (moe.py:50-72). Runs only inside a mixture's tape."""
     alt = False
@@ -141,7 +155,7 @@ class MixtureOfExperts(nn.Module):
 
     def sample(self, images, speed, command) -> torch.Tensor:
         probs, mean, std, _, _ = self.components(images, speed, command)
-        return _mixture(probs, mean, std).sample()
+        return sample_mixture(probs, mean, std)
 
 
 class MixtureOfExpertsShared(nn.Module):
@@ -189,7 +203,7 @@ class MixtureOfExpertsShared(nn.Module):
 
     def sample(self, images, speed, command) -> torch.Tensor:
         probs, mean, std, _, _ = self.components(images, speed, command)
-        return _mixture(probs, mean, std).sample()
+        return sample_mixture(probs, mean, std)
 
 
 class PUNetExpert(nn.Module):
@@ -262,8 +276,8 @@ class PMoE(nn.Module):
 
     def forward(self, images, speed, command):
         punet_actions, _ = self.punet(images.clone(), speed.clone(), command.clone())
-        dists, _ = self.moe(images, speed, command)
-        moe_actions = dists.sample()  # no gradient into the mixture (sample() runs under no_grad)
+        probs, mean, std, _, _ = self.moe.components(images, speed, command)
+        moe_actions = sample_mixture(probs, mean, std)  # dists.sample() of the reference: no gradient into the mixture
         # the 2->1 combiners are 8 FLOPs per sample: left to ATen on the GPU
         lat = self.lat_weights(torch.cat([moe_actions[:, 0:1], punet_actions[:, 0:1]], dim=-1))
         lon = self.long_weights(torch.cat([moe_actions[:, 1:], punet_actions[:, 1:]], dim=-1))

@@ -125,25 +125,42 @@ def unet(x, sd, p, train, inter_repr=False):
 RESNET18_LAYERS = ((64, 1), (128, 2), (256, 2), (512, 2))
 
 
-def resnet18_eca(x, sd, p, train):
-    """torchvision ResNet._forward_impl with conv1 := EfficientConvBlock and fc := Identity."""
+RESNET_BLOCKS = {"resnet18": ("basic", (2, 2, 2, 2)), "resnet34": ("basic", (3, 4, 6, 3)), "resnet50": ("bottleneck", (3, 4, 6, 3))}
+
+
+def resnet_eca(x, sd, p, train, arch="resnet18"):
+    """torchvision ResNet._forward_impl with conv1 := EfficientConvBlock and fc := Identity (512 features) or
+    Linear(fc.in_features, 512) (backbone.py:48-72: resnet18/34 BasicBlock, resnet50 Bottleneck with the stride on the 3x3)."""
+    kind, blocks = RESNET_BLOCKS[arch]
     x = eca_conv_block(x, sd, p + "conv1.", train)
     x = torch.relu(batchnorm(x, sd, p + "bn1.", train))
     x = F.max_pool2d(x, 3, 2, 1)
-    for li, (_, stride) in enumerate(RESNET18_LAYERS, start=1):
-        for bi in range(2):
+    for li, ((_, stride), nb) in enumerate(zip(RESNET18_LAYERS, blocks), start=1):
+        for bi in range(nb):
             q = p + "layer%d.%d." % (li, bi)
             s = stride if bi == 0 else 1
             idt = x
-            y = F.conv2d(x, sd[q + "conv1.weight"], None, s, 1)
-            y = torch.relu(batchnorm(y, sd, q + "bn1.", train))
-            y = F.conv2d(y, sd[q + "conv2.weight"], None, 1, 1)
-            y = batchnorm(y, sd, q + "bn2.", train)
+            if kind == "basic":
+                y = F.conv2d(x, sd[q + "conv1.weight"], None, s, 1)
+                y = torch.relu(batchnorm(y, sd, q + "bn1.", train))
+                y = F.conv2d(y, sd[q + "conv2.weight"], None, 1, 1)
+                y = batchnorm(y, sd, q + "bn2.", train)
+            else:
+                y = torch.relu(batchnorm(F.conv2d(x, sd[q + "conv1.weight"]), sd, q + "bn1.", train))
+                y = torch.relu(batchnorm(F.conv2d(y, sd[q + "conv2.weight"], None, s, 1), sd, q + "bn2.", train))
+                y = batchnorm(F.conv2d(y, sd[q + "conv3.weight"]), sd, q + "bn3.", train)
             if q + "downsample.0.weight" in sd:
                 idt = F.conv2d(x, sd[q + "downsample.0.weight"], None, s, 0)
                 idt = batchnorm(idt, sd, q + "downsample.1.", train)
             x = torch.relu(y + idt)
-    return x.mean(dim=(2, 3))
+    x = x.mean(dim=(2, 3))
+    if p + "fc.weight" in sd:
+        x = F.linear(x, sd[p + "fc.weight"], sd[p + "fc.bias"])
+    return x
+
+
+def resnet18_eca(x, sd, p, train):
+    return resnet_eca(x, sd, p, train, "resnet18")
 
 
 # ------------------------------------------------------------------ PU-Net (model/punet.py:75-120)
@@ -347,21 +364,38 @@ def unet_spec(spec, p, cin=3, cout=23):
     spec[p + "out.bias"] = (cout,)
 
 
-def resnet18_spec(spec, p, cin, gamma=2, b=1):
+def resnet_spec(spec, p, cin, gamma=2, b=1, arch="resnet18"):
+    kind, blocks = RESNET_BLOCKS[arch]
+    exp = 1 if kind == "basic" else 4
     eca_block_spec(spec, p + "conv1.", cin, 64, gamma, b)
     _bn(spec, p + "bn1.", 64)
     prev = 64
-    for li, (c, stride) in enumerate(RESNET18_LAYERS, start=1):
-        for bi in range(2):
+    for li, ((c, stride), nb) in enumerate(zip(RESNET18_LAYERS, blocks), start=1):
+        for bi in range(nb):
             q = p + "layer%d.%d." % (li, bi)
-            spec[q + "conv1.weight"] = (c, prev if bi == 0 else c, 3, 3)
-            _bn(spec, q + "bn1.", c)
-            spec[q + "conv2.weight"] = (c, c, 3, 3)
-            _bn(spec, q + "bn2.", c)
-            if bi == 0 and (stride != 1 or prev != c):
-                spec[q + "downsample.0.weight"] = (c, prev, 1, 1)
-                _bn(spec, q + "downsample.1.", c)
-        prev = c
+            if kind == "basic":
+                spec[q + "conv1.weight"] = (c, prev, 3, 3)
+                _bn(spec, q + "bn1.", c)
+                spec[q + "conv2.weight"] = (c, c, 3, 3)
+                _bn(spec, q + "bn2.", c)
+            else:
+                spec[q + "conv1.weight"] = (c, prev, 1, 1)
+                _bn(spec, q + "bn1.", c)
+                spec[q + "conv2.weight"] = (c, c, 3, 3)
+                _bn(spec, q + "bn2.", c)
+                spec[q + "conv3.weight"] = (c * exp, c, 1, 1)
+                _bn(spec, q + "bn3.", c * exp)
+            if bi == 0 and (stride != 1 or prev != c * exp):
+                spec[q + "downsample.0.weight"] = (c * exp, prev, 1, 1)
+                _bn(spec, q + "downsample.1.", c * exp)
+            prev = c * exp
+    if prev != 512:
+        spec[p + "fc.weight"] = (512, prev)
+        spec[p + "fc.bias"] = (512,)
+
+
+def resnet18_spec(spec, p, cin, gamma=2, b=1):
+    resnet_spec(spec, p, cin, gamma, b, "resnet18")
 
 
 def mlp_spec(spec, p, cfg):

@@ -1,0 +1,42 @@
+"""TEST INFRASTRUCTURE — goldens for the other backbone architectures the reference's factory accepts
+(PMoE/model/blocks/backbone.py:13-72: resnet34, resnet50) from the LIVE reference: `get_backbone(arch, ...)` with seeded
+weights (oracle.functional.seeded_state_dict, loaded strict=True — which also pins the state_dict contract), eval forward,
+one train-mode forward + backward (sum of features against a fixed cotangent). Writes tests/golden/backbone_<arch>.pt.
+Run in the build container only:  python oracle/gen_backbone_golden.py"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import functional as O  # noqa: E402
+from oracle.gen_golden import import_reference, grad_summary, bn_summary  # noqa: E402
+
+
+def main():
+    import_reference()
+    from model.blocks.backbone import get_backbone
+    for arch, seed in (("resnet34", 31), ("resnet50", 32)):
+        spec = O.make_spec(O.resnet_spec, 12, 2, 1, arch)
+        sd = O.seeded_state_dict(spec, seed)
+        net = get_backbone(arch=arch, n_frames=4, pretrained=False, gamma=2, b=1, n_channels=3)
+        net.load_state_dict(sd, strict=True)
+        g = torch.Generator().manual_seed(100 + seed)
+        x = torch.rand(2, 12, 64, 64, generator=g)
+        cot = torch.randn(2, 512, generator=g) * 1e-2
+        net.eval()
+        with torch.no_grad():
+            f_eval = net(x)
+        net.train()
+        f_train = net(x)
+        (f_train * cot).sum().backward()
+        out = {"arch": arch, "seed": seed, "x": x, "cot": cot, "feat_eval": f_eval, "feat_train": f_train.detach(),
+               "grads": grad_summary(net.named_parameters()), "bn": bn_summary(net.state_dict()),
+               "keys": {k: list(v.shape) for k, v in net.state_dict().items()}}
+        torch.save(out, os.path.join(ROOT, "tests", "golden", "backbone_%s.pt" % arch))
+        print(arch, "features", tuple(f_eval.shape), "params", sum(p.numel() for p in net.parameters()))
+
+
+if __name__ == "__main__":
+    main()

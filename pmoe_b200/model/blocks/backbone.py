@@ -1,8 +1,9 @@
 """Backbone factory with the reference's signature (reference: PMoE/model/blocks/backbone.py:13-72).
 
-`resnet18` is the conf default (conf/stage_2.yaml:111) and the only architecture implemented on the B200
-kernels so far; the module reproduces torchvision's ResNet-18 state_dict keys with `conv1` replaced by an
-EfficientConvBlock and `fc` by Identity, so reference checkpoints load with strict=True.
+`resnet18` is the conf default (conf/stage_2.yaml:111); `resnet34` (BasicBlock, [3,4,6,3]) and `resnet50` (Bottleneck,
+[3,4,6,3], fc := Linear(2048, 512)) are the other ResNets `_get_resnet` accepts. The modules reproduce torchvision's
+state_dict keys with `conv1` replaced by an EfficientConvBlock and `fc` by Identity / Linear, so reference checkpoints load
+with strict=True. The mobilenet family (depthwise convolutions, hard-swish, squeeze-excite) is not built.
 """
 import torch
 import torch.nn as nn
@@ -27,37 +28,67 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
 
-class ResNet18ECA(nn.Module):
-    def __init__(self, in_ch, gamma=2, b=1):
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1):
         super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)   # torchvision v1.5: stride on the 3x3
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = None
+        if stride != 1 or inplanes != planes * 4:
+            self.downsample = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
+        self.stride = stride
+
+
+_ARCH = {"resnet18": (BasicBlock, (2, 2, 2, 2)), "resnet34": (BasicBlock, (3, 4, 6, 3)), "resnet50": (Bottleneck, (3, 4, 6, 3))}
+
+
+class ResNet18ECA(nn.Module):
+    """ResNet-18/34/50 with the EfficientConvBlock stem (the class keeps its first name; `arch` selects the stages)."""
+
+    def __init__(self, in_ch, gamma=2, b=1, arch="resnet18"):
+        super().__init__()
+        block, counts = _ARCH[arch]
         self.conv1 = EfficientConvBlock(in_ch=in_ch, out_ch=64, gamma=gamma, b=b)
         self.bn1 = nn.BatchNorm2d(64)
         self.relu = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
         planes = 64
-        for i, (c, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2)), start=1):
-            setattr(self, "layer%d" % i, nn.Sequential(BasicBlock(planes, c, stride), BasicBlock(c, c, 1)))
-            planes = c
+        for i, ((c, stride), nb) in enumerate(zip(((64, 1), (128, 2), (256, 2), (512, 2)), counts), start=1):
+            blocks = [block(planes, c, stride)]
+            planes = c * block.expansion
+            blocks += [block(planes, c, 1) for _ in range(nb - 1)]
+            setattr(self, "layer%d" % i, nn.Sequential(*blocks))
         self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
-        self.fc = nn.Identity()
+        self.fc = nn.Identity() if planes == 512 else nn.Linear(planes, 512)   # backbone.py:66-69
 
     def forward(self, x):
         """x: fp32 (B, C, H, W) on the GPU -> (B, 512) features."""
         def runner(tape):
             a = nhwc.from_nchw(x, dtype=tape.dtype)
-            feat = train.resnet18_eca(tape, self, a)
-            return [feat.value], (lambda tp, g: feat.backward(g[0]) if g[0] is not None else None)
+            feat = train.backbone_features(tape, self, a)
+
+            def seed(tp, g):
+                if g[0] is not None:
+                    train.seed_vec(tp, feat, g[0])
+            return [train.vec_value(feat)], seed
         return train.run(self, runner)[0]
 
 
 def get_backbone(arch: str = "resnet18", n_frames: int = 4, pretrained: bool = False, gamma: int = 2, b: int = 1,
                  n_channels: int = 3):
-    if arch.lower() != "resnet18":
-        raise NotImplementedError("pmoe_b200 get_backbone: only 'resnet18' (the conf default) runs on the B200 kernels; got %r" % arch)
+    if arch.lower() not in _ARCH:
+        raise NotImplementedError("pmoe_b200 get_backbone: resnet18 / resnet34 / resnet50 run on the B200 kernels; got %r" % arch)
     if pretrained:
         raise RuntimeError("pmoe_b200 get_backbone: pretrained=True needs the ImageNet download (no network here); load a "
                            "checkpoint with load_state_dict instead and pass pretrained=False")
-    return ResNet18ECA(n_frames * n_channels, gamma, b)
+    return ResNet18ECA(n_frames * n_channels, gamma, b, arch.lower())
 
 
 def get_unet(*args, **kwargs):

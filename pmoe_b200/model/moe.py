@@ -103,8 +103,7 @@ def _run_experts(owner, experts, images, speed, command, alt, softmax=True):
         sp_buf = torch.zeros(1, 1, B, K * 16, dtype=tape.dtype, device=dev)
         if train.grouped_supported(experts, alt):
             # encoders per expert, then ALL experts' heads with one launch per layer (grouped GEMM over the expert axis)
-            feats = [train.feature_act(tape, train.resnet18_eca(tape, ex.backbone, x, tag="moe.%d.backbone" % k))
-                     for k, ex in enumerate(experts)]
+            feats = [train.backbone_features(tape, ex.backbone, x, tag="moe.%d.backbone" % k) for k, ex in enumerate(experts)]
             al, ap, sp = train.expert_heads_grouped(tape, experts, feats, speed_a, cmd_a, alt)
             gm = train.GateMixture(tape, [al], [ap], al.t, ap.t, B, K, relu_alpha=not alt, a_sk=B * 16, p_sk=B * 16)
             speeds = sp.t.view(K, B, 16)[:, :, :1].permute(1, 0, 2).float().contiguous()
@@ -116,8 +115,7 @@ def _run_experts(owner, experts, images, speed, command, alt, softmax=True):
             return [gm.probs, gm.mean, gm.std, speeds, gm.route], seed
         als, aps, sps = [], [], []
         for k, ex in enumerate(experts):
-            feat = train.resnet18_eca(tape, ex.backbone, x, tag="moe.%d.backbone" % k)
-            fa = train.feature_act(tape, feat)
+            fa = train.backbone_features(tape, ex.backbone, x, tag="moe.%d.backbone" % k)
             sl = slice(k * 16, (k + 1) * 16)
             al, ap, sp = train.expert_heads(tape, ex, fa, speed_a, cmd_a, alt, alpha_buf[..., sl], ap_buf[..., sl], sp_buf[..., sl],
                                             tag="moe.%d" % k)
@@ -180,7 +178,7 @@ class MixtureOfExpertsShared(nn.Module):
             x = nhwc.from_nchw(images.reshape(B, -1, images.shape[-2], images.shape[-1]), dtype=tape.dtype)
             speed_a = train.vec_act(tape, speed.reshape(B, -1).float(), 1)
             cmd_a = train.vec_act(tape, command.reshape(B, -1).float(), command.reshape(B, -1).shape[1])
-            feat = train.feature_act(tape, train.resnet18_eca(tape, self.backbone, x))
+            feat = train.backbone_features(tape, self.backbone, x)
             s = train.mlp(tape, self.speed_encoder, [speed_a], "speed_encoder")
             c = train.mlp(tape, self.command_encoder, [cmd_a], "command_encoder")
             feats = [feat, s, c]
@@ -239,7 +237,7 @@ class PUNetExpert(nn.Module):
                 fut = train.ring_window(tape, r["ring"], r["futures"], P * slot, slot, ncls)
                 stem = train.eca_conv_block(tape, self.backbone.conv1, fut, (Fu, ncls, slot), r["pools"][:, P * slot:(P + Fu) * slot],
                                             tag="backbone.conv1")
-                img = train.feature_act(tape, train.resnet18_after_stem(tape, self.backbone, stem))
+                img = train.backbone_head(tape, self.backbone, train.resnet18_after_stem(tape, self.backbone, stem))
             feats = [img, s, c]
             af = train.mlp(tape, self.action_pred[0], feats, "action_pred.0")
             act = train.linear_op(tape, [af], self.action_pred[1], "tanh", tag="action_pred.1")

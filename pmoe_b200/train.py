@@ -357,7 +357,13 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
         raw = torch.empty(n, h, w, cstore, dtype=dt, device=dev)
         ssum = torch.zeros(cop, dtype=torch.float64, device=dev)
         ssq = torch.zeros(cop, dtype=torch.float64, device=dev)
-        ops.conv(src_ts, wp, segs, ck, raw, stat_sum=ssum, stat_sqsum=ssq, flops=flops, tag=tag)
+        if cop <= 512:
+            ops.conv(src_ts, wp, segs, ck, raw, stat_sum=ssum, stat_sqsum=ssq, flops=flops, tag=tag)
+        else:  # the epilogue keeps its per-channel partial sums in shared memory for at most 512 channels (resnet50: 1024/2048)
+            ops.conv(src_ts, wp, segs, ck, raw, flops=flops, tag=tag)
+            vr = view4(raw)
+            check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(vr), dtype_code(raw), ssum.data_ptr(),
+                                                                                    ssq.data_ptr(), stream_ptr())), "channel_stats")
         z_t, mean, rstd, fwd_aff = _bn_tail_forward(tape, bn, raw, ssum, ssq, n * h * w, cout, cstore, act, residual, out)
         if want_pool:
             nhwc.channel_sums(z_t, out=pool)
@@ -674,8 +680,30 @@ def basic_block(tape, blk, x, stride, want_pool=False, tag=""):
     return conv_op(tape, [y], blk.conv2.weight, None, blk.bn2, "relu", residual=idt, want_pool=want_pool, tag=tag + ".conv2")
 
 
+def bottleneck_block(tape, blk, x, stride, want_pool=False, tag=""):
+    """torchvision Bottleneck (resnet50, v1.5: the stride sits on the 3x3): relu(bn3(conv3(relu(bn2(conv2(relu(bn1(conv1 x)))))))
+    + identity)."""
+    y, _ = conv_op(tape, [x], blk.conv1.weight, None, blk.bn1, "relu", ksize=1, tag=tag + ".conv1")
+    if stride == 1:
+        y, _ = conv_op(tape, [y], blk.conv2.weight, None, blk.bn2, "relu", tag=tag + ".conv2")
+    else:
+        srcs, segdefs = stride2_sources(y, 3)
+        y, _ = conv_op(tape, srcs, blk.conv2.weight, None, blk.bn2, "relu", segdefs=segdefs,
+                       out_hw=(srcs[0].t.shape[1], srcs[0].t.shape[2]), tag=tag + ".conv2")
+    idt = x
+    if blk.downsample is not None:
+        if stride == 1:
+            idt, _ = conv_op(tape, [x], blk.downsample[0].weight, None, blk.downsample[1], None, ksize=1, tag=tag + ".down")
+        else:
+            srcs, segdefs = stride2_sources(x, 1)
+            idt, _ = conv_op(tape, srcs, blk.downsample[0].weight, None, blk.downsample[1], None, segdefs=segdefs,
+                             out_hw=(srcs[0].t.shape[1], srcs[0].t.shape[2]), tag=tag + ".down")
+    return conv_op(tape, [y], blk.conv3.weight, None, blk.bn3, "relu", residual=idt, want_pool=want_pool, ksize=1, tag=tag + ".conv3")
+
+
 def resnet18_eca(tape, net, x, tag="backbone"):
-    """ResNet._forward_impl with conv1 := EfficientConvBlock, fc := Identity (backbone.py:48-72) -> FeatureVec (B,512)."""
+    """ResNet._forward_impl with conv1 := EfficientConvBlock up to the global average pool (backbone.py:48-72; resnet18/34
+    BasicBlock or resnet50 Bottleneck stages) -> InterRepr (B, 512 * expansion). `backbone_features` adds the fc."""
     if x.t.shape[1] % 32 or x.t.shape[2] % 32:
         raise RuntimeError("pmoe_b200 ResNet backbone needs H and W divisible by 32 (got %dx%d)" % (x.t.shape[1], x.t.shape[2]))
     return resnet18_after_stem(tape, net, eca_conv_block(tape, net.conv1, x, tag=tag + ".conv1"), tag)
@@ -689,8 +717,23 @@ def resnet18_after_stem(tape, net, stem, tag="backbone"):
     for li, layer in enumerate(layers, start=1):
         for bi, blk in enumerate(layer):
             last = li == len(layers) and bi == len(layer) - 1
-            y, pool = basic_block(tape, blk, y, blk.stride, want_pool=last, tag="%s.layer%d.%d" % (tag, li, bi))
+            block = bottleneck_block if hasattr(blk, "conv3") else basic_block
+            y, pool = block(tape, blk, y, blk.stride, want_pool=last, tag="%s.layer%d.%d" % (tag, li, bi))
     return InterRepr(tape, y, pool)
+
+
+def backbone_head(tape, net, inter, tag="backbone"):
+    """Pooled features -> the 512-vector Act the heads consume: Identity for resnet18/34, Linear(2048, 512) for resnet50
+    (backbone.py:66-69)."""
+    a = feature_act(tape, inter)
+    fc = getattr(net, "fc", None)
+    if isinstance(fc, torch.nn.Linear):
+        a = linear_op(tape, [a], fc, None, tag=tag + ".fc")
+    return a
+
+
+def backbone_features(tape, net, x, tag="backbone"):
+    return backbone_head(tape, net, resnet18_eca(tape, net, x, tag), tag)
 
 
 # ------------------------------------------------------------------------------------------------ MLP heads

@@ -174,7 +174,7 @@ def run_cuda(args, rank, world, local_rank):
 
     host_in = synth_images(B, seed=1234 + rank).pin_memory()
     x = host_in.to(dev, non_blocking=True)
-    host_out = torch.empty(B, 6, 23, 224, 224, dtype=torch.float32).pin_memory()
+    host_out = None
 
     def barrier():
         if world > 1:
@@ -204,8 +204,11 @@ def run_cuda(args, rank, world, local_rank):
         # timed steps complete inside the timed region.
         copy_stream = torch.cuda.Stream(device=dev)   # device -> host
         h2d_stream = torch.cuda.Stream(device=dev)    # host -> device: the input of step i+1 is uploaded while step i computes
+        from pmoe_b200.infer import pinned_output_like
+        del host_out
+        host_out = pinned_output_like(B, 6, 23, 224, 224)   # frame-major pinned buffers: each future frame is one async copy
         try:
-            host_out2 = torch.empty_like(host_out).pin_memory()
+            host_out2 = pinned_output_like(B, 6, 23, 224, 224)
         except RuntimeError:
             host_out2 = host_out
         houts = [host_out, host_out2]
@@ -231,14 +234,14 @@ def run_cuda(args, rank, world, local_rank):
             cur.wait_event(uploaded[j])
             if not last:
                 upload(i + 1)
-            y = net(xbufs[j])
-            consumed[j] = torch.cuda.Event()
+            # serving form of the module call: every future frame's logits leave for the pinned host buffer on copy_stream as
+            # soon as the U-Net pass that wrote them is done (PredictiveUnet.forward(..., host_out=, copy_stream=))
+            y = net(xbufs[j], host_out=houts[j], copy_stream=copy_stream)
+            consumed[j] = torch.cuda.Event(enable_timing=True)
             consumed[j].record()
             pending[j] = y
-            copy_stream.wait_event(consumed[j])
             with torch.cuda.stream(copy_stream):
-                houts[j].copy_(y, non_blocking=True)
-                copied[j] = torch.cuda.Event()
+                copied[j] = torch.cuda.Event(enable_timing=True)
                 copied[j].record()
 
         upload(0)
@@ -251,11 +254,20 @@ def run_cuda(args, rank, world, local_rank):
         e2.record()
         h2d_stream.wait_event(e2)  # the first upload belongs to the timed region
         upload(0)
+        marks = []
         for i in range(esteps):
             e2e_step(i, i == esteps - 1)
+            marks.append((consumed[i % 2], copied[i % 2]))
         torch.cuda.current_stream().wait_stream(copy_stream)  # the last result has landed in host memory
         e3.record()
         barrier()
+        if os.environ.get("PMOE_E2E_DEBUG") and rank == 0:  # timeline of the pipelined steps (ms since the start event)
+            for i, (c_ev, d_ev) in enumerate(marks):
+                try:
+                    print("e2e step %d: compute done at %.1f ms, output on host at %.1f ms" % (i, e2.elapsed_time(c_ev), e2.elapsed_time(d_ev)),
+                          file=sys.stderr, flush=True)
+                except Exception as ex:
+                    print("e2e timeline unavailable:", ex, file=sys.stderr)
         ms_e2e = e2.elapsed_time(e3)
 
         # per-launch CUDA-event pass over one extra step (not part of the timed region): time and
@@ -266,7 +278,7 @@ def run_cuda(args, rank, world, local_rank):
         prof = profiler.summary()
         profiler.enable_events(False)
 
-    h2d_bytes, d2h_bytes = host_in.numel() * 4, host_out.numel() * 4
+    h2d_bytes, d2h_bytes = host_in.numel() * 4, B * 6 * 23 * 224 * 224 * 4
     del net, x, y, host_out, host_out2, houts, pending, xbufs
     torch.cuda.empty_cache()
     train = None if args.no_train else run_train_leg(args, rank, world, dev)

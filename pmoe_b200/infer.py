@@ -196,7 +196,13 @@ def eca_conv_block_eval(blk, x_t, groups, pool_in, hw):
     return conv_eval([Act(c1s, 64)], blk.layer2.conv2[0], blk.layer2.conv2[1], "relu")
 
 
-def punet_eval(net, images):
+def pinned_output_like(B, Fu, ncls, H, W):
+    """Pinned host buffer for `PredictiveUnet.forward(..., host_out=)`: logically (B, F, classes, H, W) like the module's
+    output, stored frame-major so that one future frame of the whole batch is one contiguous block (one plain async copy)."""
+    return torch.empty(Fu, B, ncls, H, W, dtype=torch.float32).pin_memory().permute(1, 0, 2, 3, 4)
+
+
+def punet_eval(net, images, host_out=None, copy_stream=None):
     """PredictiveUnet.forward (punet.py:75-120) in eval mode. images: fp32 (B,T,C,H,W) on the GPU.
     The deque of the last `past_frames` masks is a sliding 4-slot window over one ring buffer
     (B,H,W,(T+F)*32): every U-Net writes its logits into its slot, and the entry block reads the window
@@ -221,7 +227,13 @@ def punet_eval(net, images):
         if net.unet_inter_repr:
             return inter
         return nhwc.to_nchw(ring[..., (P - 1) * slot:P * slot], ncls)
-    out = None if net.inter_repr else torch.empty(B, Fu, ncls, H, W, dtype=torch.float32, device=dev)
+    # frame-major storage, returned as the (B, F, classes, H, W) view the reference's torch.stack(dim=1) has: each frame of
+    # the batch is one contiguous block, which is what lets it leave for the host while the next U-Net pass runs
+    out = None if net.inter_repr else torch.empty(Fu, B, ncls, H, W, dtype=torch.float32, device=dev).permute(1, 0, 2, 3, 4)
+    if host_out is not None:
+        if out is None or not host_out.is_pinned() or tuple(host_out.shape) != tuple(out.shape) or not host_out[:, 0].is_contiguous():
+            raise RuntimeError("pmoe_b200 punet_eval: host_out must come from infer.pinned_output_like(B, F, classes, H, W)")
+        copy_stream = copy_stream if copy_stream is not None else torch.cuda.Stream(device=dev)
     for f in range(Fu):
         window = ring[..., f * slot:(f + P) * slot]
         m = eca_conv_block_eval(net.entry_block, window, (P, ncls, slot), pools[:, f * slot:(f + P) * slot], H * W)
@@ -229,6 +241,12 @@ def punet_eval(net, images):
         _, inter = unet_eval(net.pred_unet, m, out=ring[..., (P + f) * slot:(P + f + 1) * slot],
                              out_pool=pools[:, (P + f) * slot:], pool_stride=nslots * slot, want_inter=net.inter_repr,
                              nchw_out=None if out is None else out[:, f])
+        if host_out is not None:
+            ready = torch.cuda.Event()
+            ready.record()
+            copy_stream.wait_event(ready)
+            with torch.cuda.stream(copy_stream):
+                host_out[:, f].copy_(out[:, f], non_blocking=True)
     if net.inter_repr:
         return inter
     return out

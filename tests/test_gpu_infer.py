@@ -74,6 +74,18 @@ def test_punet_eval_vs_reference_golden(tmp_path):
     # test_unet_eval_vs_reference_golden); the same path in fp32 mode matches to 1e-5 (test_gpu_blocks.py), so the
     # bound below is the bf16 round-off budget of the chain, not slack for logic errors.
     assert per_frame[0] < 2.5 * BF16_TOL and e < 5 * BF16_TOL
+    # serving extension: the same call streaming every future frame into a pinned host buffer while later frames compute
+    from pmoe_b200.infer import pinned_output_like
+    host = pinned_output_like(2, 3, 23, 64, 64)
+    host.fill_(float("nan"))
+    cs = torch.cuda.Stream()
+    with torch.no_grad():
+        dev_out = net(g["imgs"].cuda(), host_out=host, copy_stream=cs)
+    cs.synchronize()
+    assert dev_out.shape == host.shape == out.shape
+    assert torch.equal(host, dev_out.cpu()) and torch.equal(dev_out.cpu(), out)
+    with pytest.raises(RuntimeError):
+        net(g["imgs"].cuda(), host_out=torch.empty(2, 3, 23, 64, 64))     # not pinned / not frame-major
 
 
 @pytest.mark.parametrize("B,H,W", [(1, 16, 16), (1, 80, 48), (3, 48, 144), (5, 112, 16)])

@@ -214,6 +214,18 @@ int pmoe_segloss_bwd(const float* logits, int64_t sb, int64_t sc, int64_t sh, in
                      const float* grad_scale_dev, float grad_scale, float* dlogits, int64_t db, int64_t dc, int64_t dh,
                      int64_t dw, int32_t accumulate, pmoe_stream_t stream);
 
+/* Losses against the one-hot of an int64 class map (onehot_loss.cu). mode 0: nn.L1Loss, 1: nn.MSELoss — the 'l1' / 'l2'
+ * variants of AutoregressiveCriterion (trainer/loss.py:93-96,109-116, which scatter_ a one-hot tensor first); mode 2: the
+ * last-frame L1 + gradient-difference terms of l1_gdl (loss.py:58-83). sums2: two doubles of scratch; *loss_out is written.
+ * The backward writes dlogits = *grad_scale_dev * d loss / d logits (any strides). */
+int pmoe_onehot_loss_fwd(const float* logits, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const int64_t* target, int64_t tb,
+                         int64_t th, int64_t tw, int32_t B, int32_t C, int32_t H, int32_t W, int32_t mode, double* sums2,
+                         float* loss_out, pmoe_stream_t stream);
+int pmoe_onehot_loss_bwd(const float* logits, int64_t sb, int64_t sc, int64_t sh, int64_t sw, const int64_t* target, int64_t tb,
+                         int64_t th, int64_t tw, int32_t B, int32_t C, int32_t H, int32_t W, int32_t mode,
+                         const float* grad_scale_dev, float* dlogits, int64_t db, int64_t dc, int64_t dh, int64_t dw,
+                         pmoe_stream_t stream);
+
 /* ---- optimizer side (optim.cu): multi-tensor kernels over a DEVICE table of chunks ------------------------- */
 /* One chunk = up to 2^31-1 consecutive fp32 elements of one parameter with its gradient and Adam state. */
 typedef struct PmoeMtChunk {

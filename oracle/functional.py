@@ -121,6 +121,25 @@ def unet(x, sd, p, train, inter_repr=False):
     return out
 
 
+def unet_eca(x, sd, p, train, inter_repr=False):
+    """model/blocks/unet.py:98-185 — narrower U-Net (32..512) with an ECA gate on the pooled x_4 before dwn_5 (:160) and
+    on every decoder concat before its conv3 (:165-178). NB inter_repr pools the POST-dwn_5 tensor (:182-184)."""
+    x1 = conv3_block(x, sd, p + "dwn_1.", train)
+    x2 = conv3_block(F.max_pool2d(x1, 2, 2), sd, p + "dwn_2.", train)
+    x3 = conv3_block(F.max_pool2d(x2, 2, 2), sd, p + "dwn_3.", train)
+    x4 = conv3_block(F.max_pool2d(x3, 2, 2), sd, p + "dwn_4.", train)
+    x5 = conv3_block(eca(F.max_pool2d(x4, 2, 2), sd[p + "eca_0.conv.weight"]), sd, p + "dwn_5.", train)
+    y = x5
+    for i, skip in ((1, x4), (2, x3), (3, x2), (4, x1)):
+        up = F.conv_transpose2d(y, sd[p + "up_%d.weight" % i], sd[p + "up_%d.bias" % i], stride=2)
+        cat = torch.cat([skip, up], 1)
+        y = conv3_block(eca(cat, sd[p + "eca_%d.conv.weight" % i]), sd, p + "up_forw_%d." % i, train)
+    out = F.conv2d(y, sd[p + "out.weight"], sd[p + "out.bias"])
+    if inter_repr:
+        return x5.mean(dim=(2, 3)), out
+    return out
+
+
 # ------------------------------------------------------------------ ResNet18 + ECA stem (backbone.py:48-72)
 RESNET18_LAYERS = ((64, 1), (128, 2), (256, 2), (512, 2))
 
@@ -303,6 +322,37 @@ def ce_tversky(pred, target, wc=0.5, wt=0.5):
     return wc * ce + wt * tversky(pred, target)
 
 
+def dice_score(pred, target, eps=1e-6):
+    """loss.py:20-31 — per-class dice of the argmax prediction (validation metric; = 1 - class_dice weights)."""
+    return 1 - class_dice_weights(pred, target, eps)
+
+
+def l1_gdl(inputs, targets):
+    """loss.py:58-83 — L1 + gradient-difference loss on the LAST frame: raw logits against the one-hot target (the softmax
+    at :66 is computed and never used). Differences run against a zero row/column appended at the bottom/right (:67-68);
+    the gdl term is summed over (H, W) and averaged over (B, C) (:79), the L1 term is a plain mean (:81)."""
+    x = inputs[:, -1]
+    oh = F.one_hot(targets[:, -1], x.shape[1]).movedim(-1, 1).to(x.dtype)
+
+    def dv(t):
+        tp = F.pad(t, (0, 0, 0, 1))
+        return (tp[..., 1:, :] - tp[..., :-1, :]).abs()
+
+    def dh(t):
+        tp = F.pad(t, (0, 1, 0, 0))
+        return (tp[..., :-1] - tp[..., 1:]).abs()
+
+    gdl = ((dv(oh) - dv(x)).abs() + (dh(oh) - dh(x)).abs()).sum(dim=(-2, -1)).mean()
+    return (x - oh).abs().mean() + gdl
+
+
+def autoregressive_onehot(inputs, targets, loss_type):
+    """loss.py:86-118 with loss_type 'l1' / 'l2': per-frame nn.L1Loss / nn.MSELoss against the one-hot targets."""
+    oh = F.one_hot(targets, inputs.shape[2]).movedim(-1, 2).to(inputs.dtype)
+    fn = F.l1_loss if loss_type == "l1" else F.mse_loss
+    return sum(fn(inputs[:, t], oh[:, t]) for t in range(inputs.shape[1]))
+
+
 def autoregressive_ce_tversky(inputs, targets):
     """loss.py:86-118 with loss_type='tversky'."""
     return sum(ce_tversky(inputs[:, t], targets[:, t]) for t in range(inputs.shape[1]))
@@ -361,6 +411,20 @@ def unet_spec(spec, p, cin=3, cout=23):
         spec[p + "up_%d.bias" % i] = (b,)
         conv3_spec(spec, p + "up_forw_%d." % i, 2 * b, b)
     spec[p + "out.weight"] = (cout, 64, 1, 1)
+    spec[p + "out.bias"] = (cout,)
+
+
+def unet_eca_spec(spec, p, cin=3, cout=23, gamma=2, b=1):
+    """unet.py:111-138 (module registration order)."""
+    for i, (a, c) in enumerate(((cin, 32), (32, 64), (64, 128), (128, 256), (256, 512)), start=1):
+        conv3_spec(spec, p + "dwn_%d." % i, a, c)
+    spec[p + "eca_0.conv.weight"] = (1, 1, eca_kernel_size(512, gamma, b))
+    for i, (a, c) in enumerate(((512, 256), (256, 128), (128, 64), (64, 32)), start=1):
+        spec[p + "up_%d.weight" % i] = (a, c, 2, 2)
+        spec[p + "up_%d.bias" % i] = (c,)
+        spec[p + "eca_%d.conv.weight" % i] = (1, 1, eca_kernel_size(2 * c, gamma, b))
+        conv3_spec(spec, p + "up_forw_%d." % i, 2 * c, c)
+    spec[p + "out.weight"] = (cout, 32, 1, 1)
     spec[p + "out.bias"] = (cout,)
 
 

@@ -165,7 +165,7 @@ __global__ void segloss_finalize_kernel(float* __restrict__ ws, int C, int W, fl
     s.scalars[2] = tv;
     loss_out[1] = s.scalars[1];
     loss_out[2] = tv;
-    loss_out[0] = wce * s.scalars[1] + wtv * tv;
+    loss_out[0] = (wce != 0.f ? wce * s.scalars[1] : 0.f) + wtv * tv;  // tversky_loss alone: CE weight 0
   }
 }
 
@@ -201,7 +201,7 @@ __global__ void segloss_bwd_kernel(const float* __restrict__ logits, long long s
       }
     const float inv = 1.f / se;
     const int y = (int)target[b * tb + h * th + w * tw];
-    const float wy = (y >= 0 && y < C) ? s.weight[y] * inv_den * wce : 0.f;
+    const float wy = (y >= 0 && y < C && wce != 0.f) ? s.weight[y] * inv_den * wce : 0.f;
     // g_c = dL/dp_c (Tversky part); CE part handled in closed form: wy * (p - onehot)
     float dot = 0.f;
     float g[kMaxClasses];

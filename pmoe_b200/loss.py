@@ -112,17 +112,99 @@ def cross_entropy_tversky_weighted_loss(pred, target, cross_entropy_weight=0.5, 
     return _SegLossFn.apply(pred, target, cross_entropy_weight, tversky_weight)
 
 
+class _OneHotLossFn(torch.autograd.Function):
+    """L1 / MSE / L1+gradient-difference of fp32 NCHW logits against the one-hot of an int64 class map (onehot_loss.cu)."""
+
+    @staticmethod
+    def forward(ctx, pred, target, mode):
+        _lib.require_cuda(pred, "pred")
+        if pred.dtype != torch.float32:
+            pred = pred.float()
+        B, Cc, H, W = pred.shape
+        tgt = target if target.dtype == torch.int64 else target.long()
+        sums = torch.empty(2, dtype=torch.float64, device=pred.device)
+        out = torch.empty(1, dtype=torch.float32, device=pred.device)
+        check(profiler.launch("onehot_loss_fwd", lambda: lib().pmoe_onehot_loss_fwd(
+            pred.data_ptr(), pred.stride(0), pred.stride(1), pred.stride(2), pred.stride(3), tgt.data_ptr(), tgt.stride(0),
+            tgt.stride(1), tgt.stride(2), B, Cc, H, W, int(mode), sums.data_ptr(), out.data_ptr(), stream_ptr())),
+            "onehot_loss_fwd")
+        ctx.save_for_backward(pred, tgt)
+        ctx.mode = int(mode)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, tgt = ctx.saved_tensors
+        B, Cc, H, W = pred.shape
+        d = torch.empty_like(pred, memory_format=torch.contiguous_format)
+        gs = g.detach().reshape(1).float().contiguous()
+        check(profiler.launch("onehot_loss_bwd", lambda: lib().pmoe_onehot_loss_bwd(
+            pred.data_ptr(), pred.stride(0), pred.stride(1), pred.stride(2), pred.stride(3), tgt.data_ptr(), tgt.stride(0),
+            tgt.stride(1), tgt.stride(2), B, Cc, H, W, ctx.mode, gs.data_ptr(), d.data_ptr(), d.stride(0), d.stride(1),
+            d.stride(2), d.stride(3), stream_ptr())), "onehot_loss_bwd")
+        return d, None, None
+
+
+def l1_gdl(inputs: torch.Tensor, targets: torch.Tensor):
+    """loss.py:58-83: L1 + gradient-difference loss of the LAST frame's raw logits against the one-hot target.
+    inputs (B,T,C,H,W) fp32, targets (B,T,H,W) int64."""
+    return _OneHotLossFn.apply(inputs[:, -1], targets[:, -1], 2)
+
+
+def _class_counts(pred, target):
+    """The per-class dice weights 1 - 2(|P∩T|+eps)/(|P|+|T|+eps) of loss.py:6-17 from the fused forward pass."""
+    _lib.require_cuda(pred, "pred")
+    if pred.dtype != torch.float32:
+        pred = pred.float()
+    B, Cc, H, W = pred.shape
+    tgt = target if target.dtype == torch.int64 else target.long()
+    ws = torch.empty(lib().pmoe_segloss_workspace_floats(Cc, W), dtype=torch.float32, device=pred.device)
+    out = torch.zeros(3, dtype=torch.float32, device=pred.device)
+    check(profiler.launch("segloss_fwd", lambda: lib().pmoe_segloss_fwd(
+        pred.data_ptr(), pred.stride(0), pred.stride(1), pred.stride(2), pred.stride(3), tgt.data_ptr(), tgt.stride(0),
+        tgt.stride(1), tgt.stride(2), B, Cc, H, W, 0.5, 0.5, ws.data_ptr(), out.data_ptr(), stream_ptr())), "segloss_fwd")
+    return ws[4 * Cc:5 * Cc]
+
+
+@torch.no_grad()
+def class_dice(pred, target, epsilon=1e-6):
+    """loss.py:6-17: 1 - dice per class of the argmax prediction (the CE weights), one pass instead of a 23-iteration loop."""
+    if epsilon != 1e-6:
+        raise NotImplementedError("pmoe_b200 class_dice: epsilon is fixed at the reference default 1e-6")
+    return _class_counts(pred.detach(), target).clone()
+
+
+@torch.no_grad()
+def dice_score(pred, target, epsilon=1e-6):
+    """loss.py:20-31: per-class dice of the argmax prediction — the validation metric of train_0.py:230 / train_1.py:249."""
+    if epsilon != 1e-6:
+        raise NotImplementedError("pmoe_b200 dice_score: epsilon is fixed at the reference default 1e-6")
+    return 1.0 - _class_counts(pred.detach(), target)
+
+
+def tversky_loss(pred, target, alpha=0.5, beta=0.5):
+    """loss.py:34-44 on its own: the Tversky half of the fused kernel (CE weight 0)."""
+    if alpha != 0.5 or beta != 0.5:
+        raise NotImplementedError("pmoe_b200 tversky_loss: alpha = beta = 0.5 (the only values the reference uses)")
+    return _SegLossFn.apply(pred, target, 0.0, 1.0)
+
+
 class AutoregressiveCriterion(nn.Module):
-    """Per-frame sum of the segmentation loss with BPTT (loss.py:86-118). Only loss_type='tversky' (the reference
-    default and the one stage 1 uses) runs on the fused kernels."""
+    """Per-frame sum of the per-frame loss with BPTT (loss.py:86-118): 'tversky' (reference default, the fused dice-weighted
+    CE + Tversky kernels), 'l1' / 'l2' (nn.L1Loss / nn.MSELoss against the one-hot target, fused: no one-hot tensor)."""
 
     def __init__(self, n_target_frames: int = 1, loss_type: str = "tversky"):
         super().__init__()
-        if loss_type != "tversky":
-            raise NotImplementedError("pmoe_b200 AutoregressiveCriterion: only loss_type='tversky' is implemented")
         self.n_target_frames = n_target_frames
         self.loss_type = loss_type
-        self.loss = cross_entropy_tversky_weighted_loss
+        if loss_type == "l1":
+            self.loss = lambda x, t: _OneHotLossFn.apply(x, t, 0)
+        elif loss_type == "l2":
+            self.loss = lambda x, t: _OneHotLossFn.apply(x, t, 1)
+        elif loss_type == "tversky":
+            self.loss = cross_entropy_tversky_weighted_loss
+        else:
+            raise ValueError(f"Unknown loss type {loss_type}, supported ones are L1, L2, and tversky")
 
     def forward(self, inputs, targets):
         assert inputs.size(1) == self.n_target_frames

@@ -586,6 +586,54 @@ def unet(tape, net, x, out=None, out_pool=None, pool_stride=0, want_inter=False,
     return logits, inter
 
 
+def concat_op(tape, acts):
+    """torch.cat(acts, 1) as ONE physical NHWC tensor (needed where an op — the ECA gates of UNetECA, unet.py:165-178 —
+    acts across the channel boundary of the concatenation). Every part must have an unpadded channel count (multiple of 16)."""
+    for a in acts:
+        if a.c != a.cpad:
+            raise RuntimeError("pmoe_b200 concat_op: every part needs a multiple of 16 channels (got %d)" % a.c)
+    n, h, w, _ = acts[0].t.shape
+    ctot = sum(a.c for a in acts)
+    t = torch.empty(n, h, w, ctot, dtype=acts[0].t.dtype, device=acts[0].t.device)
+    c0 = 0
+    for a in acts:
+        _axpy(a.t, t[..., c0:c0 + a.c], 1.0, None, False)
+        c0 += a.c
+    ya = _new_act(tape, t, ctot, any(_rg(a) for a in acts))
+    if tape.save and _rg(ya):
+        def backward():
+            g = tape.grad_of(ya)
+            if g is None:
+                return
+            c0 = 0
+            for a in acts:
+                if _rg(a):
+                    _accumulate_copy(tape, a, g[..., c0:c0 + a.c])
+                c0 += a.c
+        tape.record(backward)
+    return ya
+
+
+def unet_eca(tape, net, x, want_inter=False, tag="unet_eca"):
+    """UNetECA.forward (unet.py:140-185). Returns (Act logits, InterRepr of the dwn_5 output or None)."""
+    n, h, w, _ = x.t.shape
+    if h % 16 or w % 16:
+        raise RuntimeError("pmoe_b200 UNetECA needs H and W divisible by 16 (got %dx%d)" % (h, w))
+    x1, _ = conv3_block(tape, net.dwn_1, [x], tag=tag + ".dwn_1")
+    x2, _ = conv3_block(tape, net.dwn_2, [maxpool_op(tape, x1, 2, 2, 0)], tag=tag + ".dwn_2")
+    x3, _ = conv3_block(tape, net.dwn_3, [maxpool_op(tape, x2, 2, 2, 0)], tag=tag + ".dwn_3")
+    x4, _ = conv3_block(tape, net.dwn_4, [maxpool_op(tape, x3, 2, 2, 0)], tag=tag + ".dwn_4")
+    p4 = eca_op(tape, net.eca_0, maxpool_op(tape, x4, 2, 2, 0))
+    x5, pool5 = conv3_block(tape, net.dwn_5, [p4], want_pool=want_inter, tag=tag + ".dwn_5")
+    y = x5
+    for i, skip in enumerate((x4, x3, x2, x1), start=1):
+        u = conv_transpose_op(tape, getattr(net, "up_%d" % i), y, tag=tag + ".up_%d" % i)
+        cat = eca_op(tape, getattr(net, "eca_%d" % i), concat_op(tape, [skip, u]))  # skip first (unet.py:164)
+        y, _ = conv3_block(tape, getattr(net, "up_forw_%d" % i), [cat], tag=tag + ".up_forw_%d" % i)
+    logits, _ = conv_op(tape, [y], net.out.weight, net.out.bias, None, None, ksize=1, tag=tag + ".out")
+    return logits, (InterRepr(tape, x5, pool5) if want_inter else None)
+
+
 class InterRepr:
     """adaptive_avg_pool2d(x_5, 1).flatten(1) (unet.py:89-92) with its backward into x_5."""
 
@@ -1202,12 +1250,14 @@ def _seed_nchw(act):
     return seed
 
 
-def unet_module_forward(net, image):
+def unet_module_forward(net, image, body=None):
     """UNet.forward for the module API: image fp32 NCHW -> logits fp32 NCHW (and pooled bottleneck)."""
+    body = unet if body is None else body
+
     def runner(tape):
         x = nhwc.from_nchw(image, dtype=tape.dtype)
         x.rg = False
-        logits, inter = unet(tape, net, x, want_inter=net.inter_repr)
+        logits, inter = body(tape, net, x, want_inter=net.inter_repr)
         out = nhwc.to_nchw(logits.t, logits.c)
         seed_logits = _seed_nchw(logits)
         if net.inter_repr:

@@ -3,7 +3,8 @@
 `resnet18` is the conf default (conf/stage_2.yaml:111); `resnet34` (BasicBlock, [3,4,6,3]) and `resnet50` (Bottleneck,
 [3,4,6,3], fc := Linear(2048, 512)) are the other ResNets `_get_resnet` accepts. The modules reproduce torchvision's
 state_dict keys with `conv1` replaced by an EfficientConvBlock and `fc` by Identity / Linear, so reference checkpoints load
-with strict=True. The mobilenet family (depthwise convolutions, hard-swish, squeeze-excite) is not built.
+with strict=True. `get_unet` builds the 'segmentation' backbone (entry block + U-Net). The mobilenet family (depthwise convolutions,
+hard-swish, squeeze-excite) is not built yet: `get_backbone` raises for it.
 """
 import torch
 import torch.nn as nn
@@ -91,6 +92,15 @@ def get_backbone(arch: str = "resnet18", n_frames: int = 4, pretrained: bool = F
     return ResNet18ECA(n_frames * n_channels, gamma, b, arch.lower())
 
 
-def get_unet(*args, **kwargs):
-    raise NotImplementedError("pmoe_b200: the 'segmentation' backbone type is broken in the reference itself "
-                              "(model/moe.py:95 concatenates the tuple returned by get_unet(inter_repr=True))")
+def get_unet(model_dir: str, inter_repr: bool = True, n_frames: int = 4, gamma: int = 2, b: int = 1, n_channels: int = 3):
+    """backbone.py:28-45: EfficientConvBlock(n_frames*n_channels -> 3) followed by a U-Net whose weights come from
+    `model_dir` (strict=False, exactly as the reference loads them). NB with inter_repr=True the Sequential returns the
+    tuple (bottleneck, logits); the reference's own experts then fail at `torch.cat` (model/moe.py:95) — that caller-side
+    defect is not papered over here, the factory itself behaves like the reference's."""
+    from pathlib import Path
+    from .unet import UNet
+    model = UNet(gamma=gamma, b=b, inter_repr=inter_repr)
+    state_dict = torch.load(Path(model_dir).resolve(), map_location="cpu")
+    model.load_state_dict(state_dict, strict=False)
+    entry_block = EfficientConvBlock(in_ch=n_frames * n_channels, out_ch=3, gamma=gamma, b=b)
+    return nn.Sequential(entry_block, model)

@@ -49,7 +49,7 @@ def from_nchw(x, dtype=torch.bfloat16, out=None):
         out = torch.empty(n, h, w, pad_ch(c), dtype=dtype, device=x.device)
     v = view4(out)
     check(profiler.launch("nchw_to_nhwc", lambda: lib().pmoe_nchw_to_nhwc(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), x.stride(3), c, C.byref(v),
-                                  dtype_code(out), stream_ptr())), "nchw_to_nhwc")
+                                  dtype_code(out), stream_ptr()), io=(x, out)), "nchw_to_nhwc")
     return Act(out, c)
 
 
@@ -60,7 +60,7 @@ def to_nchw(t, c, out=None):
         out = torch.empty(n, c, h, w, dtype=torch.float32, device=t.device)
     v = view4(t)
     check(profiler.launch("nhwc_to_nchw", lambda: lib().pmoe_nhwc_to_nchw(C.byref(v), dtype_code(t), c, out.data_ptr(), out.stride(0), out.stride(1), out.stride(2),
-                                  out.stride(3), stream_ptr())), "nhwc_to_nchw")
+                                  out.stride(3), stream_ptr()), io=(t[..., :c], out)), "nhwc_to_nchw")
     return out
 
 
@@ -74,10 +74,10 @@ def maxpool(x, k, stride, pad, scale=None, shift=None, relu=False, want_idx=Fals
     if want_idx:
         idx = torch.empty(n, oh, ow, cp, dtype=torch.uint8, device=x.t.device)
         check(profiler.launch("maxpool", lambda: lib().pmoe_maxpool_idx(C.byref(vs), C.byref(vd), dtype_code(out), k, stride, pad,
-                                                                        idx.data_ptr(), stream_ptr())), "maxpool_idx")
+                                                                        idx.data_ptr(), stream_ptr()), io=(x.t, out, idx)), "maxpool_idx")
         return Act(out, x.c), idx
     check(profiler.launch("maxpool", lambda: lib().pmoe_maxpool(C.byref(vs), C.byref(vd), dtype_code(out), k, stride, pad, _lib.ptr(scale), _lib.ptr(shift),
-                             int(relu), stream_ptr())), "maxpool")
+                             int(relu), stream_ptr()), io=(x.t, out)), "maxpool")
     return Act(out, x.c)
 
 
@@ -86,7 +86,7 @@ def channel_sums(t, out=None):
     if out is None:
         out = torch.zeros(n, cp, dtype=torch.float32, device=t.device)
     v = view4(t)
-    check(profiler.launch("channel_sums", lambda: lib().pmoe_channel_sums(C.byref(v), dtype_code(t), out.data_ptr(), out.stride(0), stream_ptr())), "channel_sums")
+    check(profiler.launch("channel_sums", lambda: lib().pmoe_channel_sums(C.byref(v), dtype_code(t), out.data_ptr(), out.stride(0), stream_ptr()), io=(t,)), "channel_sums")
     return out
 
 
@@ -104,7 +104,7 @@ def scale_channels(t, gate, out=None):
     if out is None:
         out = torch.empty(t.shape, dtype=t.dtype, device=t.device)
     vs, vd = view4(t), view4(out)
-    check(profiler.launch("scale_channels", lambda: lib().pmoe_scale_channels(C.byref(vs), C.byref(vd), dtype_code(t), gate.data_ptr(), gate.stride(0), stream_ptr())), "scale_channels")
+    check(profiler.launch("scale_channels", lambda: lib().pmoe_scale_channels(C.byref(vs), C.byref(vd), dtype_code(t), gate.data_ptr(), gate.stride(0), stream_ptr()), io=(t, out)), "scale_channels")
     return out
 
 
@@ -127,5 +127,5 @@ def affine_act(t, scale, shift, act=None, residual=None, out=None):
     vs, vd = view4(t), view4(out)
     vr = view4(residual) if residual is not None else _lib.null_view()
     check(profiler.launch("affine_act", lambda: lib().pmoe_affine_act(C.byref(vs), C.byref(vd), dtype_code(t), scale.data_ptr(), shift.data_ptr(), C.byref(vr),
-                                ACT[act], stream_ptr())), "affine_act")
+                                ACT[act], stream_ptr()), io=(t, out, residual)), "affine_act")
     return out

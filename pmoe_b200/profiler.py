@@ -32,11 +32,18 @@ def enable_events(on):
         _records = []
 
 
-def launch(kind, fn, flops=0.0, nbytes=0.0, tag=""):
+def io_bytes(io):
+    """Algorithmic bytes of a memory-bound launch: every listed tensor/view read or written once at its storage dtype."""
+    return float(sum(t.numel() * t.element_size() for t in io if t is not None))
+
+
+def launch(kind, fn, flops=0.0, nbytes=0.0, tag="", io=None):
     global _count
     _count += 1
     if not _events_on:
         return fn()
+    if io is not None:
+        nbytes = io_bytes(io)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     rc = fn()

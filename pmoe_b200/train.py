@@ -114,7 +114,8 @@ def _bn_bwd_reduce(dz, z, x, act, mean, rstd, cpad, fwd=None):
     vx = view4(x) if x is not None else _lib.null_view()
     check(profiler.launch("bn_bwd_reduce", lambda: lib().pmoe_bn_bwd_reduce(
         C.byref(vdz), C.byref(vz), C.byref(vx), dtype_code(dz), ACT[act], _lib.ptr(mean), _lib.ptr(rstd), s1.data_ptr(),
-        _lib.ptr(s2), _lib.ptr(fwd[0] if mx else None), _lib.ptr(fwd[1] if mx else None), stream_ptr())), "bn_bwd_reduce")
+        _lib.ptr(s2), _lib.ptr(fwd[0] if mx else None), _lib.ptr(fwd[1] if mx else None), stream_ptr()),
+        io=(dz, None if (z is None or mx) else z, x)), "bn_bwd_reduce")
     return s1, s2
 
 
@@ -128,7 +129,8 @@ def _bn_bwd_apply(dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, batch_stats, 
     check(profiler.launch("bn_bwd_apply", lambda: lib().pmoe_bn_bwd_apply(
         C.byref(vdz), C.byref(vz), C.byref(vx), dtype_code(dz), ACT[act], _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma),
         _lib.ptr(s1), _lib.ptr(s2), float(inv_n), int(batch_stats), C.byref(vdx), C.byref(vdr), int(acc_dres),
-        _lib.ptr(fwd[0] if mx else None), _lib.ptr(fwd[1] if mx else None), stream_ptr())), "bn_bwd_apply")
+        _lib.ptr(fwd[0] if mx else None), _lib.ptr(fwd[1] if mx else None), stream_ptr()),
+        io=(dz, None if (z is None or mx) else z, x, dx, dres, dres if (acc_dres and dres is not None) else None)), "bn_bwd_apply")
 
 
 def _axpy(src, dst, alpha=1.0, bcast=None, accumulate=False):
@@ -136,7 +138,7 @@ def _axpy(src, dst, alpha=1.0, bcast=None, accumulate=False):
     vd = view4(dst)
     check(profiler.launch("axpy", lambda: lib().pmoe_axpy(
         C.byref(vs), C.byref(vd), dtype_code(dst), float(alpha), _lib.ptr(bcast), 0 if bcast is None else bcast.stride(0),
-        int(accumulate), stream_ptr())), "axpy")
+        int(accumulate), stream_ptr()), io=(src, dst, dst if accumulate else None)), "axpy")
 
 
 def _accumulate(tape, act, g):
@@ -363,7 +365,7 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
             ops.conv(src_ts, wp, segs, ck, raw, flops=flops, tag=tag)
             vr = view4(raw)
             check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(vr), dtype_code(raw), ssum.data_ptr(),
-                                                                                    ssq.data_ptr(), stream_ptr())), "channel_stats")
+                                                                                    ssq.data_ptr(), stream_ptr()), io=(raw,)), "channel_stats")
         z_t, mean, rstd, fwd_aff = _bn_tail_forward(tape, bn, raw, ssum, ssq, n * h * w, cout, cstore, act, residual, out)
         if want_pool:
             nhwc.channel_sums(z_t, out=pool)
@@ -451,7 +453,8 @@ def maxpool_op(tape, x, k, stride, pad):
             g, existed = _grad_buffer(tape, x)
             vdy, vdx = view4(dy), view4(g)
             check(profiler.launch("maxpool_bwd", lambda: lib().pmoe_maxpool_bwd_idx(
-                C.byref(vdy), idx.data_ptr(), C.byref(vdx), dtype_code(g), k, stride, pad, int(existed), stream_ptr())), "maxpool_bwd")
+                C.byref(vdy), idx.data_ptr(), C.byref(vdx), dtype_code(g), k, stride, pad, int(existed), stream_ptr()),
+                io=(dy, idx, g, g if existed else None)), "maxpool_bwd")
         tape.record(backward)
     return ya
 
@@ -537,7 +540,7 @@ def eca_op(tape, eca_mod, x, layout=None, pool_in=None):
             dgate = torch.zeros(n, cp, dtype=torch.float64, device=dy.device)  # cancelling sums: kept in fp64
             va, vb = view4(dy), view4(x.t)
             check(profiler.launch("prod_channel_sums", lambda: lib().pmoe_prod_channel_sums(
-                C.byref(va), C.byref(vb), dtype_code(dy), dgate.data_ptr(), dgate.stride(0), stream_ptr())), "prod_channel_sums")
+                C.byref(va), C.byref(vb), dtype_code(dy), dgate.data_ptr(), dgate.stride(0), stream_ptr()), io=(dy, x.t)), "prod_channel_sums")
             dmean = torch.empty(n, cp, dtype=torch.float32, device=dy.device)
             dw = torch.zeros(w.numel(), dtype=torch.float64, device=dy.device)
             wf = w.detach().reshape(-1)
@@ -551,7 +554,7 @@ def eca_op(tape, eca_mod, x, layout=None, pool_in=None):
                 vd, vg = view4(dy), view4(g)
                 check(profiler.launch("eca_bwd_apply", lambda: lib().pmoe_eca_bwd_apply(
                     C.byref(vd), dtype_code(dy), gate.data_ptr(), gate.stride(0), dmean.data_ptr(), dmean.stride(0), C.byref(vg),
-                    int(existed), stream_ptr())), "eca_bwd_apply")
+                    int(existed), stream_ptr()), io=(dy, g, g if existed else None)), "eca_bwd_apply")
         tape.expect(w)
         tape.record(backward)
     return ya
@@ -677,7 +680,7 @@ def bn_act_op(tape, bn, x, act="relu", tag=""):
         ssq = torch.zeros(cp, dtype=torch.float64, device=dev)
         v = view4(x.t)
         check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(v), dtype_code(x.t), ssum.data_ptr(),
-                                                                                ssq.data_ptr(), stream_ptr())), "channel_stats")
+                                                                                ssq.data_ptr(), stream_ptr()), io=(x.t,)), "channel_stats")
         z_t, mean, rstd, fwd_aff = _bn_tail_forward(tape, bn, x.t, ssum, ssq, n * h * w, c, cp, act, None, None)
         gamma_p = ops.pad_vec(bn.weight.detach(), cp, 0.0)
     else:

@@ -58,18 +58,28 @@ profiler.enable_events(False)
 by = {}
 for kind, t, f, b, tag in recs:
     key = kind if kind not in ("conv_tc", "conv_simt", "conv_wgrad", "conv_wgrad_tc") else kind + (" wgrad" if tag.startswith("wgrad") else (" dgrad" if tag.startswith("dgrad") else ""))
-    d = by.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0})
+    d = by.setdefault(key, {"ms": 0.0, "n": 0, "flops": 0.0, "bytes": 0.0})
     d["ms"] += t
     d["n"] += 1
     d["flops"] += f
+    d["bytes"] += b
+HBM_PEAK = 6551.0
+try:
+    HBM_PEAK = float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
 tot = sum(d["ms"] for d in by.values())
 rows = sorted(by.items(), key=lambda kv: -kv[1]["ms"])
 print("step %.2f ms (%.1f samples/s), loss %.4f; sum of kernel times %.2f ms over %d launches" % (ms, B / ms * 1e3, loss.item(), tot, len(recs)))
 for k, d in rows:
-    print("%-24s %8.3f ms %5.1f%% n=%4d %8.1f TF" % (k, d["ms"], 100 * d["ms"] / tot, d["n"], d["flops"] / max(d["ms"], 1e-9) / 1e9))
+    d["tflops"] = d["flops"] / max(d["ms"], 1e-9) / 1e9
+    d["gbs"] = d["bytes"] / max(d["ms"], 1e-9) / 1e6   # algorithmic bytes (each operand once) / time
+    d["hbm_frac"] = d["gbs"] / HBM_PEAK if d["bytes"] else None
+    print("%-24s %8.3f ms %5.1f%% n=%4d %8.1f TF %8.0f GB/s %s" % (k, d["ms"], 100 * d["ms"] / tot, d["n"], d["tflops"], d["gbs"],
+                                                               ("%.0f%% of HBM peak" % (100 * d["hbm_frac"])) if d["bytes"] else ""))
 # slowest individual launches
 top = sorted(recs, key=lambda r: -r[1])[:25]
 for kind, t, f, b, tag in top:
-    print("  %-16s %-44s %7.3f ms %8.1f TF" % (kind, tag, t, f / max(t, 1e-9) / 1e9))
+    print("  %-16s %-44s %7.3f ms %8.1f TF %8.0f GB/s" % (kind, tag, t, f / max(t, 1e-9) / 1e9, b / max(t, 1e-9) / 1e6))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump({"ms_per_step": ms, "batch": B, "k": args.k, "rows": rows, "top": top}, open("gpurun_out/train_profile.json", "w"), indent=1)
+json.dump({"ms_per_step": ms, "batch": B, "k": args.k, "hbm_peak_gbs": HBM_PEAK, "rows": rows, "top": top}, open("gpurun_out/train_profile.json", "w"), indent=1)

@@ -97,3 +97,31 @@ def test_gpu_backbones_vs_live_reference(arch):
             fb = net(g["x"].cuda()).float().cpu()
     print("[%s bf16] eval features %.2e" % (arch, _rel(fb, g["feat_eval"])))
     assert _rel(fb, g["feat_eval"]) < 2e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("inter", [False, True])
+def test_gpu_get_unet_segmentation_backbone(tmp_path, inter):
+    """backbone.py:28-45 (`get_unet`): entry EfficientConvBlock(12 -> 3) + U-Net loaded from `model_dir` with strict=False;
+    inter_repr=True returns the (bottleneck, logits) tuple like the reference's Sequential. Checked against the oracle's
+    composition of the same two restatements (each pinned against the live reference on its own)."""
+    from pmoe_b200 import config
+    from pmoe_b200.model.blocks.backbone import get_unet
+    usd = O.seeded_state_dict(O.make_spec(O.unet_spec, 3, 23), 51)
+    esd = O.seeded_state_dict(O.make_spec(O.eca_block_spec, 12, 3), 52)
+    path = str(tmp_path / "unet.pth")
+    torch.save(usd, path)
+    x = torch.rand(2, 12, 32, 32, generator=torch.Generator().manual_seed(53))
+    with torch.no_grad():
+        ref = O.unet(O.eca_conv_block(x, dict(esd), "", False), dict(usd), "", False, inter)
+    with config.use_precision("fp32"):
+        net = get_unet(path, inter_repr=inter, n_frames=4, gamma=2, b=1)
+        assert [k for k in net.state_dict()] == ["0." + k for k in esd] + ["1." + k for k in usd]
+        net[0].load_state_dict(esd, strict=True)
+        net = net.cuda().eval()
+        with torch.no_grad():
+            got = net(x.cuda())
+    if inter:
+        assert isinstance(got, tuple) and _rel(got[0].cpu(), ref[0]) < 1e-4 and _rel(got[1].cpu(), ref[1]) < 1e-4
+    else:
+        assert _rel(got.cpu(), ref) < 1e-4

@@ -149,6 +149,14 @@ int pmoe_bn_finalize(const double* sum, const double* sqsum, float count, int32_
 /* y = act(scale[c]*x + shift[c] (+ residual)): BN apply + ReLU (+ BasicBlock residual add). */
 int pmoe_affine_act(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, const float* scale, const float* shift,
                     const PmoeView4* residual, int32_t act, pmoe_stream_t stream);
+/* The same affine + activation on dense bf16 tensors, fused with the statistics of the STORED output that a following layer
+ * needs (each would otherwise re-read the tensor): pool_sum (N, pool_stride) fp32 per-image channel sums (ECA gate /
+ * avg-pool numerators, basics.py:71) and/or out_sum / out_sqsum per-channel fp64 sums for a BatchNorm that follows directly
+ * (torchvision ResNet bn1 after the stem, backbone.py:57-61). Accumulates into zero-initialised buffers. Returns
+ * PMOE_ERR_UNSUPPORTED for strided / fp32 views (callers then use pmoe_affine_act + pmoe_channel_sums / _stats). */
+int pmoe_affine_act_stats(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, const float* scale, const float* shift,
+                          int32_t act, float* pool_sum, int64_t pool_stride, double* out_sum, double* out_sqsum,
+                          pmoe_stream_t stream);
 
 /* ---- backward halves (eltwise_bwd.cu) ------------------------------------------------------------- */
 /* dy = dz * act'(z); sum_dy[c] += sum dy, sum_dy_xhat[c] += sum dy*(x-mean)*rstd  (native_batch_norm_backward reductions).

@@ -219,10 +219,9 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 // fused 2x2 max-pool (two warp shuffles: the window partners are lanes l^1 and l^bw), an fp32 NCHW copy at the module
 // boundary, BN batch statistics and per-image channel sums. Shared by both main-loop variants.
 // FEAT < 0: every optional feature is a run-time flag (generic). FEAT >= 0: the feature set is fixed at compile time
-// (kFeatShift | kFeatRelu | kFeatStats | kFeatPool2; no scale / residual / other activations / NCHW copy / channel
-// sums), which turns the per-element path into straight-line code (~3 instead of ~11 instructions per element: the
+// (kFeatShift | kFeatRelu | kFeatStats | kFeatPool2 | kFeatPoolSum | kFeatNchw | kFeatRes; no scale / other activations), which turns the per-element path into straight-line code (~3 instead of ~11 instructions per element: the
 // epilogue, not the tensor core, was the limit of the 64-channel layers).
-constexpr int kFeatShift = 1, kFeatRelu = 2, kFeatStats = 4, kFeatPool2 = 8, kFeatPoolSum = 16, kFeatNchw = 32;
+constexpr int kFeatShift = 1, kFeatRelu = 2, kFeatStats = 4, kFeatPool2 = 8, kFeatPoolSum = 16, kFeatNchw = 32, kFeatRes = 64;
 template <int BN, int OCW, int SUB, int OUT_BYTES, int FEAT, class Iter>
 __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& it, uint8_t* out_stage, float* s_scale, float* s_shift,
                                              float* s_pool, float* s_sum, float* s_sq, uint64_t* tfull_bar, uint64_t* tempty_bar,
@@ -247,7 +246,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
   const bool has_shift = kGen ? (p.shift != nullptr) : (FEAT & kFeatShift) != 0;
   const bool has_stats = kGen ? (p.stat_sum != nullptr) : (FEAT & kFeatStats) != 0;
   const bool has_pool2 = kGen ? (p.pool2_ptr != nullptr) : (FEAT & kFeatPool2) != 0;
-  const bool has_res = kGen && p.res != nullptr;
+  const bool has_res = kGen ? (p.res != nullptr) : (FEAT & kFeatRes) != 0;
   const bool has_nchw = kGen ? (p.nchw_ptr != nullptr) : (FEAT & kFeatNchw) != 0;
   const bool has_poolsum = kGen ? (p.pool_sum != nullptr) : (FEAT & kFeatPoolSum) != 0;
   const uint32_t sc_addr = smem_u32(s_scale), sh_addr = smem_u32(s_shift);
@@ -265,6 +264,12 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
 #pragma unroll
     for (int k = 0; k < SUB; ++k) psum[k] = 0.f;
   };
+  // BN batch statistics under the same condition: per-thread running sums of the thread's own row (raw accumulator and
+  // its square), one transpose-reduce per CTA instead of two per tile (62 shuffles + 64 shared-memory atomics per warp and
+  // tile were ~25 % of the epilogue of the 224^2 training layers).
+  float ssa[SUB], ssb[SUB];
+#pragma unroll
+  for (int k = 0; k < SUB; ++k) ssa[k] = ssb[k] = 0.f;
   uint32_t nstore = 0;
   int shift_img = -1;
   DbgClock dc(issuer ? p.dbg : nullptr);
@@ -349,18 +354,29 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
           }
         }
         if (has_stats) {
-          float a[SUB], b[SUB];
+          if (defer_pool) {
+            if (valid) {
 #pragma unroll
-          for (int k = 0; k < SUB; ++k) {
-            const float f = valid ? __uint_as_float(raw[k]) : 0.f;
-            a[k] = f;
-            b[k] = f * f;
-          }
-          const float sa = warp_col_sums<SUB>(a, lane);
-          const float sq = warp_col_sums<SUB>(b, lane);
-          if (lane < SUB && n0 + cb + lane < kMaxStatC) {
-            atomicAdd(&s_sum[n0 + cb + lane], sa);
-            atomicAdd(&s_sq[n0 + cb + lane], sq);
+              for (int k = 0; k < SUB; ++k) {
+                const float f = __uint_as_float(raw[k]);
+                ssa[k] += f;
+                ssb[k] = fmaf(f, f, ssb[k]);
+              }
+            }
+          } else {
+            float a[SUB], b[SUB];
+#pragma unroll
+            for (int k = 0; k < SUB; ++k) {
+              const float f = valid ? __uint_as_float(raw[k]) : 0.f;
+              a[k] = f;
+              b[k] = f * f;
+            }
+            const float sa = warp_col_sums<SUB>(a, lane);
+            const float sq = warp_col_sums<SUB>(b, lane);
+            if (lane < SUB && n0 + cb + lane < kMaxStatC) {
+              atomicAdd(&s_sum[n0 + cb + lane], sa);
+              atomicAdd(&s_sq[n0 + cb + lane], sq);
+            }
           }
         }
         if (has_res && res_row != nullptr) {
@@ -470,6 +486,15 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
     dc.flush(4, 3);
     p.dbg[blockIdx.x * kDbgSlots + 7] = ntiles;
     for (int i = 3; i < 8; ++i) p.dbg[blockIdx.x * kDbgSlots + 5 + i] = (unsigned long long)dc.acc[i];
+  }
+  if (has_stats && defer_pool && worker && ntiles > 0) {
+    const int col = it.nt_last(p) * BN + half * SUB + lane;  // one chunk per tile and one n-tile per CTA
+    const float sa = warp_col_sums<SUB>(ssa, lane);
+    const float sq = warp_col_sums<SUB>(ssb, lane);
+    if (lane < SUB && col < kMaxStatC) {
+      atomicAdd(&s_sum[col], sa);
+      atomicAdd(&s_sq[col], sq);
+    }
   }
   if (has_stats) {
     named_bar_sync(3, kEpiThreads);
@@ -1033,6 +1058,8 @@ static int launch_tc(const ConvTcParams& p, cudaStream_t stream) {
       case kFeatShift | kFeatRelu: return launch_tc_feat<BN, CK, kFeatShift | kFeatRelu>(p, stream);
       case kFeatShift | kFeatRelu | kFeatPool2: return launch_tc_feat<BN, CK, kFeatShift | kFeatRelu | kFeatPool2>(p, stream);
       case kFeatStats: return launch_tc_feat<BN, CK, kFeatStats>(p, stream);
+      case kFeatRes: return launch_tc_feat<BN, CK, kFeatRes>(p, stream);  // data gradient accumulated into an existing buffer
+      case kFeatShift | kFeatRelu | kFeatRes: return launch_tc_feat<BN, CK, kFeatShift | kFeatRelu | kFeatRes>(p, stream);
       default: break;
     }
   }
@@ -1079,6 +1106,8 @@ static int launch_halo(const ConvTcParams& p, int smem_bytes, cudaStream_t strea
       case kFeatShift | kFeatRelu | kFeatPool2: return launch_halo_feat<BN, CK, kFeatShift | kFeatRelu | kFeatPool2>(p, smem_bytes, stream);
       case kFeatShift | kFeatRelu | kFeatPoolSum: return launch_halo_feat<BN, CK, kFeatShift | kFeatRelu | kFeatPoolSum>(p, smem_bytes, stream);
       case kFeatStats: return launch_halo_feat<BN, CK, kFeatStats>(p, smem_bytes, stream);
+      case kFeatRes: return launch_halo_feat<BN, CK, kFeatRes>(p, smem_bytes, stream);  // dgrad into a fan-out point (ResNet skip)
+      case kFeatShift | kFeatRelu | kFeatRes: return launch_halo_feat<BN, CK, kFeatShift | kFeatRelu | kFeatRes>(p, smem_bytes, stream);
       default: break;
     }
   }
@@ -1320,9 +1349,10 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   p.cout_pad = d->cout_pad;
   p.pool_stride = d->pool_stride > 0 ? d->pool_stride : d->cout_pad;
   p.feat = -1;
-  if (!d->scale && !d->residual.ptr && (d->act == PMOE_ACT_NONE || d->act == PMOE_ACT_RELU))
+  if (!d->scale && (d->act == PMOE_ACT_NONE || d->act == PMOE_ACT_RELU))
     p.feat = (d->shift ? kFeatShift : 0) | (d->act == PMOE_ACT_RELU ? kFeatRelu : 0) | (d->stat_sum ? kFeatStats : 0) |
-             (d->pool2_out.ptr ? kFeatPool2 : 0) | (d->pool_sum ? kFeatPoolSum : 0) | (d->nchw_out ? kFeatNchw : 0);
+             (d->pool2_out.ptr ? kFeatPool2 : 0) | (d->pool_sum ? kFeatPoolSum : 0) | (d->nchw_out ? kFeatNchw : 0) |
+             (d->residual.ptr ? kFeatRes : 0);
   if (halo_bn) {
     int g = 0;
     for (int i = 0; i < d->n_src; ++i)

@@ -446,6 +446,101 @@ __global__ void __launch_bounds__(256) affine_act_kernel(V4 src, V4 dst, const f
   }
 }
 
+
+// ---------------------------------------------------------------- fast paths: dense bf16, 4 x 16-byte loads in flight per thread
+// The generic reduction kernels above issue one load per loop trip behind a 64-bit div/mod and sit at 40-55 % of the HBM
+// peak; these are their contiguous-bf16 forms (straight-line, no index arithmetic).
+// MODE 0: per-image channel sums (fp32), MODE 1: per-channel sum and sum of squares over every pixel (fp64).
+// AFFINE: y = act(scale*x + shift) is computed, stored, and the statistics are those of the STORED (bf16-rounded) y —
+// the fused form of affine_act followed by channel_sums (ECA / avg-pool numerators) and/or channel_stats (a BatchNorm that
+// follows directly: ResNet bn1 after the stem block), which would each re-read the tensor.
+template <bool AFFINE, bool RELU, bool POOL, bool STATS>
+__global__ void __launch_bounds__(kRedThreads) act_reduce_fast_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long pix_per_img,
+                                                                      int cg, const float* __restrict__ scale,
+                                                                      const float* __restrict__ shift, float* __restrict__ pool,
+                                                                      long long pool_stride, double* __restrict__ osum,
+                                                                      double* __restrict__ osq, long long pix_per_block) {
+  __shared__ float sm[kRedThreads * 8];
+  const int lanes = blockDim.x / cg;
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+  const int n = blockIdx.y;
+  const uint4* xi = x + (size_t)n * pix_per_img * cg;
+  uint4* yi = AFFINE ? y + (size_t)n * pix_per_img * cg : nullptr;
+  float sc[8], sf[8];
+  if (AFFINE) {
+    load8(scale + g * 8, sc);
+    load8(shift + g * 8, sf);
+  }
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > pix_per_img) p1 = pix_per_img;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (lane < lanes) {
+    for (long long p = p0 + lane; p < p1; p += 4LL * lanes) {
+      uint4 r[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long pp = p + (long long)u * lanes;
+        ok[u] = pp < p1;
+        r[u] = ok[u] ? __ldg(xi + pp * cg + g) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        float v[8];
+        pool_bf16x8(r[u], v);
+        if (AFFINE) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            v[q] = fmaf(v[q], sc[q], sf[q]);
+            if (RELU) v[q] = fmaxf(v[q], 0.f);
+          }
+          uint4 o;
+          o.x = pack_bf16x2(v[0], v[1]);
+          o.y = pack_bf16x2(v[2], v[3]);
+          o.z = pack_bf16x2(v[4], v[5]);
+          o.w = pack_bf16x2(v[6], v[7]);
+          yi[(p + (long long)u * lanes) * cg + g] = o;
+          pool_bf16x8(o, v);  // statistics of what is stored
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          a[q] += v[q];
+          if (STATS) b[q] = fmaf(v[q], v[q], b[q]);
+        }
+      }
+    }
+  }
+  float ta[kRedMaxIter], tb[kRedMaxIter];
+  block_channel_sum(a, sm, cg, lanes, ta);
+  if (STATS) block_channel_sum(b, sm, cg, lanes, tb);
+#pragma unroll
+  for (int j = 0; j < kRedMaxIter; ++j) {
+    const int c = threadIdx.x + j * kRedThreads;
+    if (c < cg * 8) {
+      if (POOL && ta[j] != 0.f) atomicAdd(pool + n * pool_stride + c, ta[j]);
+      if (STATS) {
+        atomicAdd(osum + c, (double)ta[j]);
+        atomicAdd(osq + c, (double)tb[j]);
+      }
+    }
+  }
+}
+
+static bool dense_view(const PmoeView4* v) {
+  return v && v->ptr && v->sw == v->c && v->sh == (int64_t)v->w * v->c && v->sn == (int64_t)v->h * v->w * v->c;
+}
+// grid (x blocks per image, images): ~8 CTAs per SM overall, at least 64 pixels per block
+static dim3 reduce_grid(long long pix_per_img, int n, long long* ppb_out) {
+  long long want = ((long long)num_sms() * 8 + n - 1) / n;
+  long long ppb = (pix_per_img + want - 1) / want;
+  if (ppb < 64) ppb = 64;
+  *ppb_out = ppb;
+  return dim3((unsigned)((pix_per_img + ppb - 1) / ppb), (unsigned)n);
+}
+
+
 }  // namespace pmoe
 
 using namespace pmoe;
@@ -595,6 +690,13 @@ int pmoe_channel_sums(const PmoeView4* src, int32_t dtype, float* out, int64_t o
     return PMOE_ERR_ARG;
   }
   const long long hw = (long long)src->h * src->w;
+  if (dtype == PMOE_BF16 && dense_view(src)) {
+    long long ppb;
+    const dim3 grid = reduce_grid(hw, src->n, &ppb);
+    act_reduce_fast_kernel<false, false, true, false><<<grid, kRedThreads, 0, stream>>>(
+        static_cast<const uint4*>(src->ptr), nullptr, hw, cg, nullptr, nullptr, out, out_stride, nullptr, nullptr, ppb);
+    return check_launch("channel_sums");
+  }
   int rows = 1024;
   dim3 grid((unsigned)((hw + rows - 1) / rows), (unsigned)src->n);
   DISPATCH_DTYPE(dtype, (channel_sums_kernel<T><<<grid, 256, 0, stream>>>(to_v4(*src), out, out_stride, rows)));
@@ -610,6 +712,13 @@ int pmoe_channel_stats(const PmoeView4* src, int32_t dtype, double* sum, double*
     return PMOE_ERR_ARG;
   }
   const long long npix = (long long)src->n * src->h * src->w;
+  if (dtype == PMOE_BF16 && dense_view(src)) {
+    long long ppb1;
+    const dim3 grid = reduce_grid(npix, 1, &ppb1);  // dense: the batch is one long image
+    act_reduce_fast_kernel<false, false, false, true><<<grid, kRedThreads, 0, stream>>>(
+        static_cast<const uint4*>(src->ptr), nullptr, npix, src->c / 8, nullptr, nullptr, nullptr, 0, sum, sqsum, ppb1);
+    return check_launch("channel_stats");
+  }
   long long blocks = (long long)num_sms() * 8;
   long long ppb = (npix + blocks - 1) / blocks;
   if (ppb < 64) ppb = 64;
@@ -660,6 +769,38 @@ int pmoe_affine_act(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, c
     DISPATCH_DTYPE(dtype, (affine_act_kernel<T, false><<<grid, 256, 0, stream>>>(to_v4(*src), to_v4(*dst), scale, shift, res, act)));
   }
   return check_launch("affine_act");
+}
+
+int pmoe_affine_act_stats(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, const float* scale, const float* shift,
+                          int32_t act, float* pool_sum, int64_t pool_stride, double* out_sum, double* out_sqsum,
+                          pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_view(src, dtype, "affine_act_stats src");
+  if (rc) return rc;
+  if ((rc = check_view(dst, dtype, "affine_act_stats dst"))) return rc;
+  if (!scale || !shift || ((uintptr_t)scale % 16) || ((uintptr_t)shift % 16) || (out_sum != nullptr) != (out_sqsum != nullptr) ||
+      (!pool_sum && !out_sum) || src->c / 8 > 256) {
+    set_error("affine_act_stats: scale/shift (16-byte aligned) and at least one statistics output are required");
+    return PMOE_ERR_ARG;
+  }
+  if (dtype != PMOE_BF16 || !dense_view(src) || !dense_view(dst) || src->n != dst->n || src->h != dst->h || src->w != dst->w ||
+      src->c != dst->c || (act != PMOE_ACT_NONE && act != PMOE_ACT_RELU)) {
+    set_error("affine_act_stats: dense bf16 tensors of one shape, ReLU or no activation");
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  const long long hw = (long long)src->h * src->w;
+  long long ppb;
+  const dim3 grid = reduce_grid(hw, src->n, &ppb);
+  const uint4* px = static_cast<const uint4*>(src->ptr);
+  uint4* py = static_cast<uint4*>(dst->ptr);
+  const int cg = src->c / 8;
+#define PMOE_AAS(R, P, S) act_reduce_fast_kernel<true, R, P, S><<<grid, kRedThreads, 0, stream>>>(px, py, hw, cg, scale, shift, pool_sum, pool_stride, out_sum, out_sqsum, ppb)
+  const bool relu = act == PMOE_ACT_RELU;
+  if (pool_sum && out_sum) { if (relu) PMOE_AAS(true, true, true); else PMOE_AAS(false, true, true); }
+  else if (pool_sum) { if (relu) PMOE_AAS(true, true, false); else PMOE_AAS(false, true, false); }
+  else { if (relu) PMOE_AAS(true, false, true); else PMOE_AAS(false, false, true); }
+#undef PMOE_AAS
+  return check_launch("affine_act_stats");
 }
 
 }  // extern "C"

@@ -557,6 +557,110 @@ __global__ void __launch_bounds__(256) maxpool_bwd_fast_kernel(const uint4* __re
 }
 
 
+// MaxPool2d(3, 2, 1) backward for even H and W (the ResNet stem pool): one thread per horizontally adjacent input pixel PAIR
+// (even, odd) and channel group. The even pixel lies in column-window j only (at column 1), the odd pixel in windows j
+// (column 2) and j+1 (column 0); the input row lies in one row-window (even rows) or two (odd rows) — a block-uniform
+// branch. So every (code, gradient) pair that is loaded is used, the wanted argmax codes are constants, and the byte
+// compares run four channels at a time (__vcmpeq4 + two byte permutes give the bf16x2 masks). The general kernel above
+// spends ~4x the instructions (every thread walks 2x2 windows, a quarter of which apply) and was issue-bound at 32 % of HBM.
+__device__ __forceinline__ void add_masked(float (&o)[8], const uint2& code, const uint4& grad, uint32_t want) {
+  const uint32_t w4 = want * 0x01010101u;
+  const uint32_t m0 = __vcmpeq4(code.x, w4), m1 = __vcmpeq4(code.y, w4);
+  const uint32_t gq[4] = {grad.x & __byte_perm(m0, 0u, 0x1100u), grad.y & __byte_perm(m0, 0u, 0x3322u),
+                          grad.z & __byte_perm(m1, 0u, 0x1100u), grad.w & __byte_perm(m1, 0u, 0x3322u)};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    o[2 * q] += __uint_as_float(gq[q] << 16);
+    o[2 * q + 1] += __uint_as_float(gq[q] & 0xffff0000u);
+  }
+}
+__global__ void __launch_bounds__(256) maxpool3s2_bwd_pair_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
+                                                                  uint4* __restrict__ dx, int H, int W, int OH, int OW, int cg,
+                                                                  int cg_shift, int accumulate) {
+  const int n = blockIdx.x / H, ih = blockIdx.x - n * H;
+  const int items = (W >> 1) * cg;
+  const bool odd = (ih & 1) != 0;
+  const int oh0 = ih >> 1;                  // row-window that holds this row at r = 1 (even row) or r = 2 (odd row)
+  const uint32_t r0 = odd ? 6u : 3u;        // r * 3
+  const bool two = odd && (oh0 + 1 < OH);   // odd rows are also row 0 of the window below
+  for (int item = blockIdx.y * blockDim.x + threadIdx.x; item < items; item += gridDim.y * blockDim.x) {
+    const int j = cg_shift >= 0 ? (item >> cg_shift) : item / cg;
+    const int g = item - j * cg;
+    const bool right = j + 1 < OW;
+    const size_t oa = (((size_t)n * OH + oh0) * OW + j) * cg + g;
+    const size_t oc = oa + (size_t)OW * cg;
+    const uint2 zc = make_uint2(0xffffffffu, 0xffffffffu);  // code 255 never matches
+    const uint4 zg = make_uint4(0u, 0u, 0u, 0u);
+    const uint2 cA = __ldg(idx + oa);
+    const uint4 gA = __ldg(dy + oa);
+    const uint2 cB = right ? __ldg(idx + oa + cg) : zc;
+    const uint4 gB = right ? __ldg(dy + oa + cg) : zg;
+    const uint2 cC = two ? __ldg(idx + oc) : zc;
+    const uint4 gC = two ? __ldg(dy + oc) : zg;
+    const uint2 cD = (two && right) ? __ldg(idx + oc + cg) : zc;
+    const uint4 gD = (two && right) ? __ldg(dy + oc + cg) : zg;
+    const size_t od = ((size_t)blockIdx.x * W + 2 * j) * cg + g;
+    float o0[8], o1[8];
+    if (accumulate) {
+      bf16x8_to_f32(dx[od], o0);
+      bf16x8_to_f32(dx[od + cg], o1);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o0[q] = o1[q] = 0.f;
+    }
+    add_masked(o0, cA, gA, r0 + 1u);
+    add_masked(o1, cA, gA, r0 + 2u);
+    add_masked(o1, cB, gB, r0);
+    if (two) {
+      add_masked(o0, cC, gC, 1u);
+      add_masked(o1, cC, gC, 2u);
+      add_masked(o1, cD, gD, 0u);
+    }
+    dx[od] = f32_to_bf16x8(o0);
+    dx[od + cg] = f32_to_bf16x8(o1);
+  }
+}
+
+// dx (+)= dout * gate[n, c] + dmean[n, c] on dense bf16: grid (x, n), one channel group per thread, gate / dmean in
+// registers, four 16-byte loads in flight (the generic kernel: one load behind a div/mod chain, 61 % of HBM).
+template <bool ACC>
+__global__ void __launch_bounds__(256) eca_bwd_apply_fast_kernel(const uint4* __restrict__ dout, uint4* __restrict__ dx,
+                                                                 long long per_img, int cg, const float* __restrict__ gate,
+                                                                 long long gate_stride, const float* __restrict__ dmean,
+                                                                 long long dmean_stride) {
+  const int n = blockIdx.y;
+  const long long stride = (long long)gridDim.x * blockDim.x;  // a multiple of cg
+  const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int g = (int)(first % cg);
+  float gt[8], dm[8];
+  bload8(gate + n * gate_stride + g * 8, gt);
+  bload8(dmean + n * dmean_stride + g * 8, dm);
+  const uint4* src = dout + (size_t)n * per_img;
+  uint4* dst = dx + (size_t)n * per_img;
+  for (long long i = first; i < per_img; i += 4 * stride) {
+    uint4 r[4], ro[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long ii = i + (long long)u * stride;
+      ok[u] = ii < per_img;
+      const long long off = ok[u] ? ii : i;
+      r[u] = __ldg(src + off);
+      if (ACC) ro[u] = dst[off];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      float d[8], o[8];
+      bf16x8_to_f32(r[u], d);
+      if (ACC) bf16x8_to_f32(ro[u], o);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) o[q] = fmaf(d[q], gt[q], dm[q]) + (ACC ? o[q] : 0.f);
+      dst[i + (long long)u * stride] = f32_to_bf16x8(o);
+    }
+  }
+}
+
 // ACT: 0 = no activation, 1 = ReLU mask read from the saved output z, 2 = ReLU mask recomputed from x with the forward's own
 // scale/shift (fmaf(x, scale, shift) > 0 is bit-for-bit what affine_act computed before its max(.,0)), which saves the read of z.
 template <int ACT, bool HAS_X>
@@ -913,7 +1017,10 @@ int pmoe_maxpool_bwd_idx(const PmoeView4* dy, const uint8_t* idx, const PmoeView
     const uint4* pdy = static_cast<const uint4*>(dy->ptr);
     const uint2* pidx = reinterpret_cast<const uint2*>(idx);
     uint4* pdx = static_cast<uint4*>(dx->ptr);
-    if (k3) maxpool_bwd_fast_kernel<3, 2, 1><<<grid, 256, 0, stream>>>(pdy, pidx, pdx, dx->h, dx->w, dy->h, dy->w, cg, cg_shift, accumulate);
+    if (k3 && dx->h % 2 == 0 && dx->w % 2 == 0 && dy->h == dx->h / 2 && dy->w == dx->w / 2) {
+      dim3 gp((unsigned)rows, (unsigned)(((dx->w / 2) * cg + 255) / 256));
+      maxpool3s2_bwd_pair_kernel<<<gp, 256, 0, stream>>>(pdy, pidx, pdx, dx->h, dx->w, dy->h, dy->w, cg, cg_shift, accumulate);
+    } else if (k3) maxpool_bwd_fast_kernel<3, 2, 1><<<grid, 256, 0, stream>>>(pdy, pidx, pdx, dx->h, dx->w, dy->h, dy->w, cg, cg_shift, accumulate);
     else maxpool_bwd_fast_kernel<2, 2, 0><<<grid, 256, 0, stream>>>(pdy, pidx, pdx, dx->h, dx->w, dy->h, dy->w, cg, cg_shift, accumulate);
     return check_launch("maxpool_bwd_idx");
   }
@@ -964,6 +1071,21 @@ int pmoe_eca_bwd_apply(const PmoeView4* dout, int32_t dtype, const float* gate, 
     return PMOE_ERR_ARG;
   }
   const long long items = (long long)dx->n * dx->h * dx->w * (dx->c / 8);
+  if (dtype == PMOE_BF16 && all_flat(dx, {dx, dout}) && dx->n <= 65535) {
+    const int cg = dx->c / 8;
+    const long long per_img = (long long)dx->h * dx->w * cg;
+    long long bx = (per_img + 4 * 256 - 1) / (4 * 256);
+    const long long cap = ((long long)num_sms() * 16 + dx->n - 1) / dx->n;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    if (256 % cg != 0) bx = (bx + cg - 1) / cg * cg;
+    dim3 grid((unsigned)bx, (unsigned)dx->n);
+    const uint4* pd = static_cast<const uint4*>(dout->ptr);
+    uint4* px = static_cast<uint4*>(dx->ptr);
+    if (accumulate) eca_bwd_apply_fast_kernel<true><<<grid, 256, 0, stream>>>(pd, px, per_img, cg, gate, gate_stride, dmean, dmean_stride);
+    else eca_bwd_apply_fast_kernel<false><<<grid, 256, 0, stream>>>(pd, px, per_img, cg, gate, gate_stride, dmean, dmean_stride);
+    return check_launch("eca_bwd_apply");
+  }
   BW_DISPATCH(dtype, (eca_bwd_apply_kernel<T><<<bgrid(items, 256), 256, 0, stream>>>(bv4(dout), gate, gate_stride, dmean, dmean_stride, bv4(dx), accumulate)));
   return check_launch("eca_bwd_apply");
 }

@@ -18,10 +18,11 @@ def dtype_code(t):
 
 class Act:
     """An NHWC activation: tensor (N,H,W,Cpad) with `c` logical channels; channels [c, Cpad) are zero."""
-    __slots__ = ("t", "c", "rg")
+    __slots__ = ("t", "c", "rg", "stats")
 
     def __init__(self, t, c, rg=False):
         self.t, self.c, self.rg = t, c, rg
+        self.stats = None   # (sum, sum of squares) per channel, fp64, when the producing kernel already reduced them
 
     @property
     def shape(self):
@@ -129,3 +130,19 @@ def affine_act(t, scale, shift, act=None, residual=None, out=None):
     check(profiler.launch("affine_act", lambda: lib().pmoe_affine_act(C.byref(vs), C.byref(vd), dtype_code(t), scale.data_ptr(), shift.data_ptr(), C.byref(vr),
                                 ACT[act], stream_ptr()), io=(t, out, residual)), "affine_act")
     return out
+
+
+def affine_act_stats(t, scale, shift, act, out, pool=None, pool_stride=0, out_stats=None):
+    """affine_act fused with the statistics of the stored output a following layer needs: `pool` (N, >=C) fp32 per-image
+    channel sums and/or `out_stats` = (sum, sqsum) fp64 per channel (both accumulate into zeroed buffers). Dense bf16 only:
+    returns False (nothing launched) when the tensors do not qualify, and the caller runs the separate kernels."""
+    if t.dtype != torch.bfloat16 or not t.is_contiguous() or not out.is_contiguous() or act not in (None, "none", "relu") \
+            or t.shape[3] // 8 > 256:
+        return False
+    vs, vd = view4(t), view4(out)
+    check(profiler.launch("affine_act", lambda: lib().pmoe_affine_act_stats(
+        C.byref(vs), C.byref(vd), dtype_code(t), scale.data_ptr(), shift.data_ptr(), ACT[act], _lib.ptr(pool),
+        (pool.stride(0) if pool_stride == 0 else pool_stride) if pool is not None else 0,
+        _lib.ptr(out_stats[0] if out_stats else None), _lib.ptr(out_stats[1] if out_stats else None), stream_ptr()),
+        io=(t, out)), "affine_act_stats")
+    return True

@@ -300,7 +300,7 @@ def _pack_dgrad(weight, src, segs_i, co_pad, dtype):
     return _cached_pack(weight, key, build)
 
 
-def _bn_tail_forward(tape, bn, raw, ssum, ssq, count, cout, cstore, act, residual, out):
+def _bn_tail_forward(tape, bn, raw, ssum, ssq, count, cout, cstore, act, residual, out, pool=None, out_stats=None):
     track = bn.track_running_stats and bn.running_mean is not None
     mom = 0.1 if bn.momentum is None else bn.momentum
     mean, rstd, scale, shift = nhwc.bn_finalize(ssum, ssq, count, cout, bn.weight.detach(), bn.bias.detach(), bn.eps, mom,
@@ -308,7 +308,19 @@ def _bn_tail_forward(tape, bn, raw, ssum, ssq, count, cout, cstore, act, residua
     if track and bn.num_batches_tracked is not None:
         bn.num_batches_tracked += 1
     z_t = out if out is not None else torch.empty(raw.shape, dtype=raw.dtype, device=raw.device)
-    nhwc.affine_act(raw, scale[:cstore], shift[:cstore], act, None if residual is None else residual.t, out=z_t)
+    fused = False
+    if (pool is not None or out_stats is not None) and residual is None:
+        # the statistics of the output that the next layer needs (ECA / avg-pool sums, a directly following BatchNorm) ride on
+        # the pass that writes it
+        fused = nhwc.affine_act_stats(raw, scale[:cstore], shift[:cstore], act, z_t, pool, 0, out_stats)
+    if not fused:
+        nhwc.affine_act(raw, scale[:cstore], shift[:cstore], act, None if residual is None else residual.t, out=z_t)
+        if pool is not None:
+            nhwc.channel_sums(z_t, out=pool)
+        if out_stats is not None:
+            v = view4(z_t)
+            check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(
+                C.byref(v), dtype_code(z_t), out_stats[0].data_ptr(), out_stats[1].data_ptr(), stream_ptr()), io=(z_t,)), "channel_stats")
     # (scale, shift) let the backward recompute the ReLU mask from `raw` instead of reading z (not with a residual add)
     return z_t, mean, rstd, ((scale, shift) if residual is None else None)
 
@@ -327,7 +339,7 @@ def _eval_affine(bn, bias, cout, cop):
 
 
 def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, want_pool=False, ksize=3, layouts=None,
-            segdefs=None, out=None, pool_out=None, pool_stride=0, out_hw=None, tag=""):
+            segdefs=None, out=None, pool_out=None, pool_stride=0, out_hw=None, tag="", want_out_stats=False):
     """conv / linear layer over `srcs` (list of Act = virtual channel concat, or list of Src), followed by BatchNorm
     (batch statistics when bn.training, folded running statistics otherwise), optional residual add and activation.
     Returns (Act z, pool_sum or None)."""
@@ -353,7 +365,7 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
     pool = None
     if want_pool:
         pool = pool_out if pool_out is not None else torch.zeros(n, cop, dtype=torch.float32, device=dev)
-    raw = mean = rstd = gamma_p = scale = fwd_aff = None
+    raw = mean = rstd = gamma_p = scale = fwd_aff = out_stats = None
     src_ts = [x.t for x in srcs]
     if bn_train:
         raw = torch.empty(n, h, w, cstore, dtype=dt, device=dev)
@@ -366,9 +378,10 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
             vr = view4(raw)
             check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(vr), dtype_code(raw), ssum.data_ptr(),
                                                                                     ssq.data_ptr(), stream_ptr()), io=(raw,)), "channel_stats")
-        z_t, mean, rstd, fwd_aff = _bn_tail_forward(tape, bn, raw, ssum, ssq, n * h * w, cout, cstore, act, residual, out)
-        if want_pool:
-            nhwc.channel_sums(z_t, out=pool)
+        if want_out_stats:
+            out_stats = (torch.zeros(cstore, dtype=torch.float64, device=dev), torch.zeros(cstore, dtype=torch.float64, device=dev))
+        z_t, mean, rstd, fwd_aff = _bn_tail_forward(tape, bn, raw, ssum, ssq, n * h * w, cout, cstore, act, residual, out,
+                                                    pool=pool if want_pool else None, out_stats=out_stats)
         gamma_p = ops.pad_vec(bn.weight.detach(), cstore, 0.0)
     else:
         scale, shift = _eval_affine(bn, bias, cout, cop)
@@ -376,6 +389,7 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
         ops.conv(src_ts, wp, segs, ck, z_t, scale=scale, shift=shift, act=act,
                  residual=None if residual is None else residual.t, pool_sum=pool, pool_stride=pool_stride, flops=flops, tag=tag)
     z = _new_act(tape, z_t, cout, rg_in)
+    z.stats = out_stats
     if not (tape.save and rg_in):
         return z, pool
 
@@ -655,14 +669,15 @@ class InterRepr:
         _axpy(None, buf, 1.0, gb, existed)
 
 
-def eca_conv_block(tape, blk, x, layout=None, pool_in=None, tag="eca_block"):
+def eca_conv_block(tape, blk, x, layout=None, pool_in=None, tag="eca_block", want_out_stats=False):
     """EfficientConvBlock (basics.py:80-135). layout = (groups, logical, slot) of x's channel axis."""
     xs = eca_op(tape, blk.layer1.eca1, x, layout, pool_in)
     lay = None if layout is None else [[(layout[1], layout[2])] * layout[0]]
     c1, pool64 = conv_op(tape, [xs], blk.layer1.conv1[0].weight, None, blk.layer1.conv1[1], "relu", want_pool=True,
                          layouts=lay, tag=tag + ".conv1")
     c1s = eca_op(tape, blk.layer2.eca2, c1, None, pool64)
-    y, _ = conv_op(tape, [c1s], blk.layer2.conv2[0].weight, None, blk.layer2.conv2[1], "relu", tag=tag + ".conv2")
+    y, _ = conv_op(tape, [c1s], blk.layer2.conv2[0].weight, None, blk.layer2.conv2[1], "relu", tag=tag + ".conv2",
+                   want_out_stats=want_out_stats)
     return y
 
 
@@ -676,11 +691,14 @@ def bn_act_op(tape, bn, x, act="relu", tag=""):
     bn_train = bn.training
     mean = rstd = gamma_p = scale = fwd_aff = None
     if bn_train:
-        ssum = torch.zeros(cp, dtype=torch.float64, device=dev)
-        ssq = torch.zeros(cp, dtype=torch.float64, device=dev)
-        v = view4(x.t)
-        check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(v), dtype_code(x.t), ssum.data_ptr(),
-                                                                                ssq.data_ptr(), stream_ptr()), io=(x.t,)), "channel_stats")
+        if x.stats is not None and x.stats[0].numel() == cp:
+            ssum, ssq = x.stats    # reduced by the kernel that wrote x (conv_op(want_out_stats=True))
+        else:
+            ssum = torch.zeros(cp, dtype=torch.float64, device=dev)
+            ssq = torch.zeros(cp, dtype=torch.float64, device=dev)
+            v = view4(x.t)
+            check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(v), dtype_code(x.t), ssum.data_ptr(),
+                                                                                    ssq.data_ptr(), stream_ptr()), io=(x.t,)), "channel_stats")
         z_t, mean, rstd, fwd_aff = _bn_tail_forward(tape, bn, x.t, ssum, ssq, n * h * w, c, cp, act, None, None)
         gamma_p = ops.pad_vec(bn.weight.detach(), cp, 0.0)
     else:
@@ -757,7 +775,8 @@ def resnet18_eca(tape, net, x, tag="backbone"):
     BasicBlock or resnet50 Bottleneck stages) -> InterRepr (B, 512 * expansion). `backbone_features` adds the fc."""
     if x.t.shape[1] % 32 or x.t.shape[2] % 32:
         raise RuntimeError("pmoe_b200 ResNet backbone needs H and W divisible by 32 (got %dx%d)" % (x.t.shape[1], x.t.shape[2]))
-    return resnet18_after_stem(tape, net, eca_conv_block(tape, net.conv1, x, tag=tag + ".conv1"), tag)
+    stem = eca_conv_block(tape, net.conv1, x, tag=tag + ".conv1", want_out_stats=net.bn1.training)  # bn1 follows directly
+    return resnet18_after_stem(tape, net, stem, tag)
 
 
 def resnet18_after_stem(tape, net, stem, tag="backbone"):

@@ -468,7 +468,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2])")
     ap.add_argument("--train-batch", type=int, default=512, help="GLOBAL training batch, sharded over the ranks")
     ap.add_argument("--train-experts", type=int, default=6)
-    ap.add_argument("--train-micro", type=int, default=128, help="largest micro-batch one rank runs at once")
+    ap.add_argument("--train-micro", type=int, default=256, help="largest micro-batch one rank runs at once")
     ap.add_argument("--no-graph", action="store_true", help="training leg: issue every launch from Python instead of one CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -300,6 +300,40 @@ def _pack_dgrad(weight, src, segs_i, co_pad, dtype):
     return _cached_pack(weight, key, build)
 
 
+FUSE_STRIDE2_DGRAD = True  # tests switch it off to compare against the one-launch-per-parity-view form
+_S2_TAP = {(0, 0): 1, (1, 0): 2, (1, 1): 0}  # (output parity, shift into dy) -> kernel tap of a k3/s2/p1 conv
+
+
+def _stride2_dgrad_fused(tape, x, weight, dy, co_pad, ck_d, n, oh, ow, flops, tag):
+    """Data gradient of a 3x3 / stride-2 / pad-1 conv in ONE launch (instead of one per spatial parity view of x, each a
+    small-K, store-bound GEMM): dx[2i+a, 2j+b, :] = sum over the shifts (dh, dw) in {0,1}^2 of dy[i+dh, j+dw, :] @ W[tap(a,dh),
+    tap(b,dw)] — a GEMM over the dy grid with K = 4 shifts x Cout and N = 4 parities x Cin (7 of the 16 blocks are zero), whose
+    column blocks (2a, 2a+1) are the (n, i, j, 2*Cin) view of the output rows 2i+a (the ConvTranspose2d store path)."""
+    cs = x.cpad
+    shifts = ((0, 0), (0, 1), (1, 0), (1, 1))
+
+    def build():
+        wf = weight.detach().float()
+        cout, cin = wf.shape[0], wf.shape[1]
+        rows = []
+        for a in range(2):
+            for b in range(2):
+                cols = []
+                for (dh, dw) in shifts:
+                    blk = torch.zeros(cs, co_pad, dtype=torch.float32, device=wf.device)
+                    if (a, dh) in _S2_TAP and (b, dw) in _S2_TAP:
+                        blk[:cin, :cout] = wf[:, :, _S2_TAP[(a, dh)], _S2_TAP[(b, dw)]].t()
+                    cols.append(blk)
+                rows.append(torch.cat(cols, 1))
+        return torch.cat(rows, 0).to(dy.dtype).contiguous()  # (4*cs, 4*co_pad)
+    wd4 = _cached_pack(weight, "s2d4|%d|%d|%s" % (cs, co_pad, dy.dtype), build)
+    g = torch.empty(x.t.shape, dtype=dy.dtype, device=dy.device)   # every pixel of every parity is written
+    tape.grads[id(x)] = g
+    dsegs = [(0, dh, dw, 0, co_pad // ck_d) for (dh, dw) in shifts]
+    rows = g.view(n, oh, 2, ow, 2 * cs)
+    ops.conv([dy], wd4, dsegs, ck_d, rows[:, :, 0], out_extra=[rows[:, :, 1]], out_cols=2 * cs, flops=flops, tag="dgrad " + tag)
+
+
 def _bn_tail_forward(tape, bn, raw, ssum, ssq, count, cout, cstore, act, residual, out, pool=None, out_stats=None):
     track = bn.track_running_stats and bn.running_mean is not None
     mom = 0.1 if bn.momentum is None else bn.momentum
@@ -339,7 +373,7 @@ def _eval_affine(bn, bias, cout, cop):
 
 
 def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, want_pool=False, ksize=3, layouts=None,
-            segdefs=None, out=None, pool_out=None, pool_stride=0, out_hw=None, tag="", want_out_stats=False):
+            segdefs=None, out=None, pool_out=None, pool_stride=0, out_hw=None, tag="", want_out_stats=False, stride2_of=None):
     """conv / linear layer over `srcs` (list of Act = virtual channel concat, or list of Src), followed by BatchNorm
     (batch statistics when bn.training, folded running statistics otherwise), optional residual add and activation.
     Returns (Act z, pool_sum or None)."""
@@ -422,6 +456,10 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
         # data gradients: one launch per physical source whose owner needs them
         ck_d = ops.choose_ck([cstore])
         pre = {id(x.act): (id(x.act) in tape.grads) for x in srcs}
+        if (FUSE_STRIDE2_DGRAD and stride2_of is not None and ksize == 3 and len(srcs) == 4 and _rg(stride2_of) and id(stride2_of) not in tape.grads
+                and dt == torch.bfloat16 and not config.FORCE_SIMT and stride2_of.cpad % 64 == 0 and stride2_of.c == stride2_of.cpad):
+            _stride2_dgrad_fused(tape, stride2_of, weight, dy, cstore, ck_d, n, h, w, flops, tag)
+            return
         for i, src in enumerate(srcs):
             if not _rg(src.act):
                 continue
@@ -731,13 +769,9 @@ def bn_act_op(tape, bn, x, act="relu", tag=""):
 
 
 def basic_block(tape, blk, x, stride, want_pool=False, tag=""):
-    """torchvision BasicBlock: relu(bn2(conv2(relu(bn1(conv1(x))))) + identity) with optional 1x1/s2 downsample."""
-    if stride == 1:
-        y, _ = conv_op(tape, [x], blk.conv1.weight, None, blk.bn1, "relu", tag=tag + ".conv1")
-    else:
-        srcs, segdefs = stride2_sources(x, 3)
-        oh, ow = srcs[0].t.shape[1], srcs[0].t.shape[2]
-        y, _ = conv_op(tape, srcs, blk.conv1.weight, None, blk.bn1, "relu", segdefs=segdefs, out_hw=(oh, ow), tag=tag + ".conv1")
+    """torchvision BasicBlock: relu(bn2(conv2(relu(bn1(conv1(x))))) + identity) with optional 1x1/s2 downsample. The
+    downsample is recorded BEFORE conv1, so in the backward conv1's data gradient comes first and can write the whole of
+    dx in one launch (`_stride2_dgrad_fused`); the downsample then accumulates into its parity view."""
     idt = x
     if blk.downsample is not None:
         if stride == 1:
@@ -746,6 +780,13 @@ def basic_block(tape, blk, x, stride, want_pool=False, tag=""):
             srcs, segdefs = stride2_sources(x, 1)
             idt, _ = conv_op(tape, srcs, blk.downsample[0].weight, None, blk.downsample[1], None, segdefs=segdefs,
                              out_hw=(srcs[0].t.shape[1], srcs[0].t.shape[2]), tag=tag + ".down")
+    if stride == 1:
+        y, _ = conv_op(tape, [x], blk.conv1.weight, None, blk.bn1, "relu", tag=tag + ".conv1")
+    else:
+        srcs, segdefs = stride2_sources(x, 3)
+        oh, ow = srcs[0].t.shape[1], srcs[0].t.shape[2]
+        y, _ = conv_op(tape, srcs, blk.conv1.weight, None, blk.bn1, "relu", segdefs=segdefs, out_hw=(oh, ow), tag=tag + ".conv1",
+                       stride2_of=x)
     return conv_op(tape, [y], blk.conv2.weight, None, blk.bn2, "relu", residual=idt, want_pool=want_pool, tag=tag + ".conv2")
 
 
@@ -758,7 +799,7 @@ def bottleneck_block(tape, blk, x, stride, want_pool=False, tag=""):
     else:
         srcs, segdefs = stride2_sources(y, 3)
         y, _ = conv_op(tape, srcs, blk.conv2.weight, None, blk.bn2, "relu", segdefs=segdefs,
-                       out_hw=(srcs[0].t.shape[1], srcs[0].t.shape[2]), tag=tag + ".conv2")
+                       out_hw=(srcs[0].t.shape[1], srcs[0].t.shape[2]), tag=tag + ".conv2", stride2_of=y)
     idt = x
     if blk.downsample is not None:
         if stride == 1:

@@ -402,19 +402,40 @@ def run_train_leg(args, rank, world, dev):
             _train.DROPOUT_STEP = None
             torch.cuda.synchronize()
 
+    # Uploads are pipelined: micro-batch m+1 (of this or of the next step) travels host -> staging buffer on a copy stream while
+    # micro-batch m computes; a device-to-device copy (0.4 ms for 617 MB) moves it into the graph's static inputs. Every step
+    # still issues exactly n_micro uploads inside the timed region, and the region ends only after the last one has landed.
+    copy_stream = torch.cuda.Stream(device=dev) if graph is not None else None
+    stage = {k: torch.empty_like(v) for k, v in static.items()} if graph is not None else None
+    ev_ready, ev_free = torch.cuda.Event(), torch.cuda.Event()
+
+    def prefetch(m):
+        sl = slice(m * micro, (m + 1) * micro)
+        copy_stream.wait_event(ev_free)  # the previous contents have been copied out of the staging buffers
+        with torch.cuda.stream(copy_stream):
+            for k, v in host.items():
+                stage[k].copy_(v[sl], non_blocking=True)  # H2D of a micro-batch: inside the timed region
+            ev_ready.record(copy_stream)
+
     def graph_step():
+        cur = torch.cuda.current_stream()
         torch._foreach_zero_([p.grad for p in model.parameters() if p.grad is not None])
         total = None
         for m in range(n_micro):
-            sl = slice(m * micro, (m + 1) * micro)
-            for k, v in host.items():
-                static[k].copy_(v[sl], non_blocking=True)  # H2D of this micro-batch: inside the timed region
+            cur.wait_event(ev_ready)
+            for k in static:
+                static[k].copy_(stage[k], non_blocking=True)
+            ev_free.record(cur)
+            prefetch((m + 1) % n_micro)
             _train.DROPOUT_STEP.add_(1)
             graph.replay()
             total = static_loss.detach().clone() if total is None else total + static_loss.detach()
         opt.step(max_grad_norm=1.0)
         return total
 
+    if graph is not None:
+        ev_free.record(torch.cuda.current_stream())
+        prefetch(0)
     step = graph_step if graph is not None else eager_step
 
     def barrier():
@@ -432,6 +453,8 @@ def run_train_leg(args, rank, world, dev):
     for _ in range(steps):
         loss = step()
     lv = float(loss.item())  # D2H read of the step's loss
+    if copy_stream is not None:
+        torch.cuda.current_stream().wait_stream(copy_stream)  # the upload issued by the last step lands inside the timed region
     e1.record()
     barrier()
     launches = profiler.launch_count()

@@ -67,8 +67,50 @@ def full(src, dst, want=""):
                 print("   %-90s %s %s" % (k, rec[k]["value"], rec[k]["unit"]))
 
 
+def perkernel(src, dst):
+    """One record per kernel instantiation of a --set full capture: its LONGEST launch (the representative big tensor),
+    with duration, DRAM bytes / throughput, tensor-pipe and issue utilisation, registers, grid."""
+    if src.endswith(".csv"):  # `ncu -i x.ncu-rep --page raw --csv > x.csv` made on the GPU box (reports can exceed the 64 MiB pull limit)
+        raw = open(src).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = [r for r in csv.reader(raw.splitlines()) if r]
+    while rows and rows[0][0] != "ID":
+        rows.pop(0)
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    best, count = {}, collections.Counter()
+
+    def num(r, k):
+        try:
+            return float(r[idx[k]].replace(",", ""))
+        except Exception:
+            return 0.0
+    for r in rows[2:]:
+        name = re.sub(r"\(.*", "", r[idx["Kernel Name"]]).replace("void ", "")
+        count[name] += 1
+        if name not in best or num(r, "gpu__time_duration.sum") > num(best[name], "gpu__time_duration.sum"):
+            best[name] = r
+    out = {"source": src, "note": "ncu --set full --clock-control none; per kernel instantiation the longest captured launch",
+           "kernels": []}
+    for name, r in sorted(best.items(), key=lambda kv: -num(kv[1], "gpu__time_duration.sum")):
+        rec = {"kernel": name, "captured_launches": count[name]}
+        for k in KEYS:
+            if k in idx:
+                rec[k] = {"value": r[idx[k]], "unit": units[idx[k]]}
+        out["kernels"].append(rec)
+        print("%-60s %9s %s  dram %5s%%  tensor %5s%%  sm %5s%%" % (
+            name[:60], r[idx["gpu__time_duration.sum"]], units[idx["gpu__time_duration.sum"]],
+            r[idx["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]] if "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed" in idx else "?",
+            r[idx[KEYS[4]]] if KEYS[4] in idx else "?",
+            r[idx["sm__throughput.avg.pct_of_peak_sustained_elapsed"]] if "sm__throughput.avg.pct_of_peak_sustained_elapsed" in idx else "?"))
+    json.dump(out, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif sys.argv[1] == "perkernel":
+        perkernel(sys.argv[2], sys.argv[3])
     else:
         full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")

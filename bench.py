@@ -340,12 +340,13 @@ def run_train_leg(args, rank, world, dev):
     if per % micro:
         return {"skipped": "per-rank batch %d not a multiple of the micro-batch %d" % (per, micro)}
     torch.manual_seed(0)
-    cfg = conf.stage2_model_cfg("moe", K)
+    frames, hw = args.train_frames, args.train_hw  # conf default 4 x 224^2; BASELINE configs[4] = 12 frames (3 cameras) x 448^2
+    cfg = conf.stage2_model_cfg("moe", K, n_frames=frames)
     model = get_model(cfg).to(dev).train()
     wrapped = dp.DataParallel(model) if world > 1 else model
     opt = optim.FusedAdam([p for p in model.parameters() if p.requires_grad], lr=2e-4, betas=(0.9, 0.999), eps=1e-8, amsgrad=True)
     g = torch.Generator().manual_seed(4321 + rank)
-    host = {"images": torch.rand(per, 4, 3, 224, 224, generator=g).pin_memory(),
+    host = {"images": torch.rand(per, frames, 3, hw, hw, generator=g).pin_memory(),
             "speed": (torch.rand(per, 1, generator=g) * 1.2).pin_memory(),
             "command": torch.nn.functional.one_hot(torch.randint(0, 6, (per,), generator=g), 6).float().pin_memory(),
             "control": (torch.rand(per, 2, generator=g) * 2 - 1).pin_memory(),
@@ -464,9 +465,14 @@ def run_train_leg(args, rank, world, dev):
     if world > 1:
         torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
     ms_step = ms.item() / steps
-    gf = K * (3 * MOE_FWD_GF - MOE_STEM_DGRAD_GF)  # fwd + dgrad + wgrad per sample
+    # fwd + dgrad + wgrad per sample (17.963 / 0.694 GF at the conf shape; 77.38 / 8.32 GF for configs[4]); other
+    # geometries scale the conf figure by the pixel count (the stem's share moves with the frame count: approximate)
+    if (frames, hw) == (12, 448):
+        gf = K * (3 * 77.38 - 8.32)
+    else:
+        gf = K * (3 * MOE_FWD_GF - MOE_STEM_DGRAD_GF) * (hw * hw) / (224.0 * 224.0)
     out = {"metric": "train_samples_per_sec", "value": Bg / (ms_step / 1e3), "unit": "samples/s", "ms_per_step": ms_step,
-           "scaling": "strong", "workload": "moe K=%d ResNet18-ECA experts, fwd+moe_loss+bwd+allreduce+clip+Adam(amsgrad), bf16" % K,
+           "scaling": "strong", "workload": "moe K=%d ResNet18-ECA experts, %d frames x %dx%d, fwd+moe_loss+bwd+allreduce+clip+Adam(amsgrad), bf16" % (K, frames, hw, hw),
            "global_batch": Bg, "batch_per_gpu": per, "micro_batch": micro, "steps": steps, "loss": lv, "launch_mode": mode,
            "h2d_bytes_per_step": sum(v.numel() * 4 for v in host.values()), "gpu_launches": launches,
            "tflops_per_gpu": gf * per / ms_step / 1e3, "params": sum(p.numel() for p in model.parameters())}
@@ -492,6 +498,8 @@ def main():
     ap.add_argument("--train-batch", type=int, default=512, help="GLOBAL training batch, sharded over the ranks")
     ap.add_argument("--train-experts", type=int, default=6)
     ap.add_argument("--train-micro", type=int, default=256, help="largest micro-batch one rank runs at once")
+    ap.add_argument("--train-frames", type=int, default=4, help="frames stacked per sample (12 = 3 cameras x 4: BASELINE configs[4])")
+    ap.add_argument("--train-hw", type=int, default=224, help="frame height = width (448: BASELINE configs[4])")
     ap.add_argument("--no-graph", action="store_true", help="training leg: issue every launch from Python instead of one CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

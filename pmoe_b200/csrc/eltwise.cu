@@ -85,6 +85,31 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, long long sn,
   }
 }
 
+// Narrow destinations (<= 32 stored channels: the 3- and 12-channel image inputs): one thread per PIXEL writes all of its
+// channel groups, so that a warp's stores are 32 consecutive 32/64-byte pixel rows (fully written sectors) instead of 16-byte
+// halves of sectors completed by another warp much later; loads stay coalesced along w within each channel plane.
+template <typename T, int CG>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_pix_kernel(const float* __restrict__ src, long long sn, long long sc, long long sh,
+                                                               long long sw, int c, V4 dst) {
+  const long long total = (long long)dst.n * dst.h * dst.w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long pix = i;
+    const int w = (int)(pix % dst.w);
+    pix /= dst.w;
+    const int h = (int)(pix % dst.h);
+    const int n = (int)(pix / dst.h);
+    const float* sp = src + n * sn + h * sh + w * sw;
+    float v[CG][8];
+#pragma unroll
+    for (int g = 0; g < CG; ++g)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[g][k] = (g * 8 + k < c) ? __ldg(sp + (g * 8 + k) * sc) : 0.f;
+    T* dp = static_cast<T*>(dst.ptr) + n * dst.sn + h * dst.sh + w * dst.sw;
+#pragma unroll
+    for (int g = 0; g < CG; ++g) store8(dp + g * 8, v[g]);
+  }
+}
+
 // ---------------------------------------------------------------- NHWC -> NCHW fp32 (first c channels)
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(V4 src, int c, float* __restrict__ dst, long long dn, long long dc, long long dh,
@@ -528,6 +553,41 @@ __global__ void __launch_bounds__(kRedThreads) act_reduce_fast_kernel(const uint
   }
 }
 
+// y = x * gate[n, c] on dense bf16: grid (x, n), the gate of the thread's channel group in registers, four loads in flight
+__global__ void __launch_bounds__(256) scale_channels_fast_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long per_img,
+                                                                  int cg, const float* __restrict__ gate, long long gate_stride) {
+  const int n = blockIdx.y;
+  const long long stride = (long long)gridDim.x * blockDim.x;  // a multiple of cg
+  const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int g = (int)(first % cg);
+  float gt[8];
+  load8(gate + n * gate_stride + g * 8, gt);
+  const uint4* src = x + (size_t)n * per_img;
+  uint4* dst = y + (size_t)n * per_img;
+  for (long long i = first; i < per_img; i += 4 * stride) {
+    uint4 r[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long ii = i + (long long)u * stride;
+      ok[u] = ii < per_img;
+      r[u] = __ldg(src + (ok[u] ? ii : i));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      float v[8];
+      pool_bf16x8(r[u], v);
+      uint4 o;
+      o.x = pack_bf16x2(v[0] * gt[0], v[1] * gt[1]);
+      o.y = pack_bf16x2(v[2] * gt[2], v[3] * gt[3]);
+      o.z = pack_bf16x2(v[4] * gt[4], v[5] * gt[5]);
+      o.w = pack_bf16x2(v[6] * gt[6], v[7] * gt[7]);
+      dst[i + (long long)u * stride] = o;
+    }
+  }
+}
+
 static bool dense_view(const PmoeView4* v) {
   return v && v->ptr && v->sw == v->c && v->sh == (int64_t)v->w * v->c && v->sn == (int64_t)v->h * v->w * v->c;
 }
@@ -569,6 +629,15 @@ int pmoe_nchw_to_nhwc(const float* src, int64_t sn, int64_t sc, int64_t sh, int6
     return PMOE_ERR_ARG;
   }
   const long long items = (long long)dst->n * dst->h * dst->w * (dst->c / 8);
+  const long long pixels = (long long)dst->n * dst->h * dst->w;
+  if (dst->c == 16) {
+    DISPATCH_DTYPE(dst_dtype, (nchw_to_nhwc_pix_kernel<T, 2><<<grid_for(pixels, 256), 256, 0, stream>>>(src, sn, sc, sh, sw, c, to_v4(*dst))));
+    return check_launch("nchw_to_nhwc");
+  }
+  if (dst->c == 32) {
+    DISPATCH_DTYPE(dst_dtype, (nchw_to_nhwc_pix_kernel<T, 4><<<grid_for(pixels, 256), 256, 0, stream>>>(src, sn, sc, sh, sw, c, to_v4(*dst))));
+    return check_launch("nchw_to_nhwc");
+  }
   DISPATCH_DTYPE(dst_dtype, (nchw_to_nhwc_kernel<T><<<grid_for(items, 256), 256, 0, stream>>>(src, sn, sc, sh, sw, c, to_v4(*dst))));
   return check_launch("nchw_to_nhwc");
 }
@@ -676,6 +745,18 @@ int pmoe_scale_channels(const PmoeView4* src, const PmoeView4* dst, int32_t dtyp
     return PMOE_ERR_ARG;
   }
   const long long items = (long long)dst->n * dst->h * dst->w * (dst->c / 8);
+  if (dtype == PMOE_BF16 && dense_view(src) && dense_view(dst) && src->c == dst->c && dst->n <= 65535) {
+    const int cg = dst->c / 8;
+    const long long per_img = (long long)dst->h * dst->w * cg;
+    long long bx = (per_img + 4 * 256 - 1) / (4 * 256);
+    const long long cap = ((long long)num_sms() * 16 + dst->n - 1) / dst->n;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    if (256 % cg != 0) bx = (bx + cg - 1) / cg * cg;
+    scale_channels_fast_kernel<<<dim3((unsigned)bx, (unsigned)dst->n), 256, 0, stream>>>(
+        static_cast<const uint4*>(src->ptr), static_cast<uint4*>(dst->ptr), per_img, cg, gate, gate_stride);
+    return check_launch("scale_channels");
+  }
   DISPATCH_DTYPE(dtype, (scale_channels_kernel<T><<<grid_for(items, 256), 256, 0, stream>>>(to_v4(*src), to_v4(*dst), gate, gate_stride)));
   return check_launch("scale_channels");
 }

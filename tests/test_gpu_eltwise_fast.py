@@ -91,3 +91,32 @@ def test_eca_bwd_apply_fast_vs_generic(accumulate, n, h, w, c):
         outs.append(dx.float().clone())
         assert ((dx.float() - ref).abs() <= ref.abs().clamp_min(1e-2) * 2.0 ** -7).all()
     assert _rel(outs[0], outs[1]) < 4e-3
+
+
+@pytest.mark.parametrize("n,h,w,c", [(3, 20, 28, 64), (2, 7, 9, 48), (2, 14, 14, 16)])
+def test_scale_channels_fast_vs_generic(n, h, w, c):
+    from pmoe_b200 import nhwc
+    g = torch.Generator().manual_seed(11 * n + c)
+    x = torch.randn(n, h, w, c, generator=g).to(dev).to(torch.bfloat16)
+    gate = torch.rand(n, c, generator=g).to(dev)
+    ref = (x.float() * gate[:, None, None, :]).to(torch.bfloat16)
+    assert torch.equal(nhwc.scale_channels(x, gate), ref)
+    wide = torch.zeros(n, h, w, 2 * c, dtype=torch.bfloat16, device=dev)
+    wide[..., :c] = x
+    assert torch.equal(nhwc.scale_channels(wide[..., :c], gate), ref)   # strided source: generic kernel
+
+
+@pytest.mark.parametrize("c", [3, 12, 16, 23, 36])
+def test_nchw_to_nhwc_narrow_and_wide(c):
+    from pmoe_b200 import nhwc
+    g = torch.Generator().manual_seed(c)
+    x = torch.rand(3, c, 18, 22, generator=g).to(dev)
+    for dtype in (torch.bfloat16, torch.float32):
+        a = nhwc.from_nchw(x, dtype=dtype)
+        cp = a.t.shape[3]
+        assert cp % 16 == 0 and a.c == c
+        assert torch.equal(a.t[..., :c], x.permute(0, 2, 3, 1).to(dtype))
+        assert a.t[..., c:].abs().sum().item() == 0
+    xs = torch.rand(3, 2 * c, 18, 22, generator=g).to(dev)[:, ::2]      # strided source planes
+    a = nhwc.from_nchw(xs, dtype=torch.bfloat16)
+    assert torch.equal(a.t[..., :c], xs.permute(0, 2, 3, 1).to(torch.bfloat16))

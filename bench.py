@@ -145,7 +145,10 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_sample(batch=2, iters=1):
+def cpu_baseline_sample(batch=2, iters=None, budget_s=12.0):
+    """The oracle port (the same ATen CPU operators the reference modules dispatch to) on every host core, on a bounded sample of
+    the bench workload: batches of `batch` frames through the same PU-Net forward, repeated for ~budget_s seconds of CPU work
+    (at least 3 iterations) unless `iters` fixes the count."""
     from oracle import functional as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -153,12 +156,15 @@ def cpu_baseline_sample(batch=2, iters=1):
     x = synth_images(batch)
     with torch.no_grad():
         O.punet(x, sd, "", False, 4, 6)  # warm-up
-        t0 = time.perf_counter()
-        for _ in range(iters):
+        n, t0 = 0, time.perf_counter()
+        while True:
             O.punet(x, sd, "", False, 4, 6)
-        dt = time.perf_counter() - t0
-    return {"value": batch * iters / dt, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": "batch %d x %d iterations of the same PU-Net forward (fp32, %d threads)" % (batch, iters, cores)}
+            n += 1
+            dt = time.perf_counter() - t0
+            if (iters is not None and n >= iters) or (iters is None and n >= 3 and dt >= budget_s) or dt > 60.0:
+                break
+    return {"value": batch * n / dt, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": "%d iterations x batch %d of the same PU-Net forward = %.1f s of CPU work (fp32 ATen/oneDNN, %d threads)" % (n, batch, dt, cores)}
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
@@ -315,7 +321,7 @@ def run_cuda(args, rank, world, local_rank):
     if train is not None:
         line["train"] = train
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_sample(args.cpu_batch, 1)
+        line["cpu_baseline"] = cpu_baseline_sample(args.cpu_batch)
     print(json.dumps(line), flush=True)
 
 

@@ -173,6 +173,16 @@ int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* 
                       const double* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
                       const PmoeView4* dres, int32_t accumulate_dres, const float* fwd_scale, const float* fwd_shift,
                       pmoe_stream_t stream);
+/* The same batch-statistics apply when x is itself the ReLU output of an UPSTREAM BatchNorm and dx is that layer's complete
+ * gradient (torchvision's bn1 directly after the stem block, backbone.py:57-61): also accumulates next_sum_dx[c] += sum
+ * dx*[x>0] and next_sum_dx_x[c] += sum dx*x (zero-initialised fp64), from which the upstream layer's two backward
+ * reductions follow without a pass of its own: sum dy*m = next_sum_dx, sum dy*m*raw = (next_sum_dx_x - shift*next_sum_dx)
+ * / scale with the upstream forward's (scale, shift). Dense bf16, ReLU, channel-group count dividing 256; otherwise
+ * PMOE_ERR_UNSUPPORTED (nothing launched). */
+int pmoe_bn_bwd_apply_sums(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
+                           const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
+                           const double* sum_dy_xhat, float inv_n, const PmoeView4* dx, const float* fwd_scale,
+                           const float* fwd_shift, double* next_sum_dx, double* next_sum_dx_x, pmoe_stream_t stream);
 int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* dx, int32_t dtype, int32_t k, int32_t stride,
                      int32_t pad, int32_t accumulate, pmoe_stream_t stream);
 int pmoe_maxpool_bwd_idx(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* dx, int32_t dtype, int32_t k,

@@ -735,14 +735,21 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_fast_kernel(const u
   }
 }
 
-template <int ACT, bool BATCH>
+// NEXT: x is itself the ReLU output of an upstream BatchNorm (torchvision's bn1 directly after the stem block's conv+BN+ReLU),
+// and dx is that layer's complete upstream gradient: its backward reductions  sum dx*[x>0]  and  sum dx*x  (x = 0 exactly
+// where its mask is 0) are accumulated here from the registers, so the upstream layer needs no reduce pass of its own
+// (block layout threadIdx.x = lane*cg + g: requires 256 % cg == 0).
+template <int ACT, bool BATCH, bool NEXT>
 __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ z,
                                                                 const uint4* __restrict__ x, uint4* __restrict__ dx, uint4* dres,
                                                                 int accumulate_dres, long long total, int cg,
                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                 const float* __restrict__ gamma, const double* __restrict__ sum_dy,
                                                                 const double* __restrict__ sum_dy_xhat, float inv_n,
-                                                                const float* __restrict__ fwd_scale, const float* __restrict__ fwd_shift) {
+                                                                const float* __restrict__ fwd_scale, const float* __restrict__ fwd_shift,
+                                                                double* __restrict__ next_s1, double* __restrict__ next_s2) {
+  __shared__ float sm_next[NEXT ? kRedThreads * 8 : 8];
+  float na[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long stride = (long long)gridDim.x * blockDim.x;  // a multiple of cg: one channel group per thread
   const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const int g = (int)(first % cg);
@@ -822,7 +829,30 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(const uint4* __r
 #pragma unroll
           for (int q = 0; q < 8; ++q) o[q] = A[q] * d[q];
         }
-        dx[ii] = f32_to_bf16x8(o);
+        const uint4 pk = f32_to_bf16x8(o);
+        dx[ii] = pk;
+        if (NEXT) {  // sums of what a separate reduce pass would read back: the bf16-rounded dx
+          float ov[8];
+          bf16x8_to_f32(pk, ov);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            na[q] += xv[q] > 0.f ? ov[q] : 0.f;
+            nb[q] = fmaf(ov[q], xv[q], nb[q]);
+          }
+        }
+      }
+    }
+  }
+  if (NEXT) {
+    float ta[kRedMaxIter], tb[kRedMaxIter];
+    block_channel_sum(na, sm_next, cg, blockDim.x / cg, ta);
+    block_channel_sum(nb, sm_next, cg, blockDim.x / cg, tb);
+#pragma unroll
+    for (int j = 0; j < kRedMaxIter; ++j) {
+      const int c = threadIdx.x + j * kRedThreads;
+      if (c < cg * 8) {
+        atomicAdd(next_s1 + c, (double)ta[j]);
+        atomicAdd(next_s2 + c, (double)tb[j]);
       }
     }
   }
@@ -924,11 +954,11 @@ int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4*
   return check_launch("bn_bwd_reduce");
 }
 
-int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
-                      const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
-                      const double* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
-                      const PmoeView4* dres, int32_t accumulate_dres, const float* fwd_scale, const float* fwd_shift,
-                      pmoe_stream_t stream_) {
+static int bn_bwd_apply_impl(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
+                             const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
+                             const double* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
+                             const PmoeView4* dres, int32_t accumulate_dres, const float* fwd_scale, const float* fwd_shift,
+                             double* next_s1, double* next_s2, pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc;
   const bool mask_x = act == PMOE_ACT_RELU && (!z || !z->ptr) && x && x->ptr && fwd_scale && fwd_shift;
@@ -953,8 +983,17 @@ int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* 
     const int cg = dz->c / 8;
     int g4 = (grid + 3) / 4;  // four items per thread and iteration
     if (256 % cg != 0) g4 = (g4 + cg - 1) / cg * cg;
-#define PMOE_APPLY_FAST(A, B) bn_bwd_apply_fast_kernel<A, B><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, fwd_scale, fwd_shift)
-    if (mask_x && batch_stats) PMOE_APPLY_FAST(2, true);
+#define PMOE_APPLY_FAST(A, B) bn_bwd_apply_fast_kernel<A, B, false><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, fwd_scale, fwd_shift, nullptr, nullptr)
+    if (next_s1) {
+      if (!next_s2 || !batch_stats || !pdx || 256 % cg != 0 || !(mask_x || act == PMOE_ACT_RELU)) {
+        set_error("bn_bwd_apply_sums: needs batch statistics, a dx output, ReLU and a channel-group count that divides 256");
+        return PMOE_ERR_UNSUPPORTED;
+      }
+      if (mask_x)
+        bn_bwd_apply_fast_kernel<2, true, true><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, fwd_scale, fwd_shift, next_s1, next_s2);
+      else
+        bn_bwd_apply_fast_kernel<1, true, true><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, fwd_scale, fwd_shift, next_s1, next_s2);
+    } else if (mask_x && batch_stats) PMOE_APPLY_FAST(2, true);
     else if (mask_x) PMOE_APPLY_FAST(2, false);
     else if (act && batch_stats) PMOE_APPLY_FAST(1, true);
     else if (act) PMOE_APPLY_FAST(1, false);
@@ -963,8 +1002,8 @@ int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* 
 #undef PMOE_APPLY_FAST
     return check_launch("bn_bwd_apply");
   }
-  if (mask_x) {
-    set_error("bn_bwd_apply: the mask-from-x form needs contiguous bf16 tensors");
+  if (mask_x || next_s1) {
+    set_error("bn_bwd_apply: the mask-from-x and fused-sums forms need contiguous bf16 tensors");
     return PMOE_ERR_UNSUPPORTED;
   }
   if (flat_all) {
@@ -973,6 +1012,27 @@ int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* 
     BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T, false><<<grid, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres)));
   }
   return check_launch("bn_bwd_apply");
+}
+
+int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
+                      const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
+                      const double* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
+                      const PmoeView4* dres, int32_t accumulate_dres, const float* fwd_scale, const float* fwd_shift,
+                      pmoe_stream_t stream_) {
+  return bn_bwd_apply_impl(dz, z, x, dtype, act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, dx, dres, accumulate_dres,
+                           fwd_scale, fwd_shift, nullptr, nullptr, stream_);
+}
+
+int pmoe_bn_bwd_apply_sums(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
+                           const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
+                           const double* sum_dy_xhat, float inv_n, const PmoeView4* dx, const float* fwd_scale,
+                           const float* fwd_shift, double* next_sum_dx, double* next_sum_dx_x, pmoe_stream_t stream_) {
+  if (!next_sum_dx || !next_sum_dx_x) {
+    set_error("bn_bwd_apply_sums: both output sums are required");
+    return PMOE_ERR_ARG;
+  }
+  return bn_bwd_apply_impl(dz, z, x, dtype, act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, 1, dx, nullptr, 0, fwd_scale, fwd_shift,
+                           next_sum_dx, next_sum_dx_x, stream_);
 }
 
 int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* dx, int32_t dtype, int32_t k, int32_t stride,

@@ -31,6 +31,7 @@ class Tape:
         self.pending = {}           # id(param) -> gradient contributions still to come (data-parallel overlap)
         self.reported = set()
         self.bucketer = None        # pmoe_b200.dp.GradBucketer during a data-parallel backward
+        self.presums = {}           # id(Act) -> (sum dy*[y>0], sum dy*y) reduced by the kernel that wrote the Act's gradient
 
     def expect(self, *params):
         """Forward-time announcement that a recorded backward closure will add_pgrad() to these parameters."""
@@ -119,6 +120,30 @@ def _bn_bwd_reduce(dz, z, x, act, mean, rstd, cpad, fwd=None):
     return s1, s2
 
 
+FUSE_BN_CHAIN_SUMS = True  # tests switch it off to compare against the separate reduce pass
+
+
+def _bn_bwd_apply_sums(dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, dx, fwd):
+    """bn_bwd_apply (batch statistics, ReLU) that also reduces sum dx*[x>0] and sum dx*x for the upstream BatchNorm whose ReLU
+    output x is. Returns the two fp64 sums, or None (nothing launched) when the tensors do not qualify."""
+    cp = dz.shape[3]
+    if not (FUSE_BN_CHAIN_SUMS and dz.dtype == torch.bfloat16 and act == "relu" and dz.is_contiguous() and x.is_contiguous()
+            and dx.is_contiguous() and (z is None or z.is_contiguous()) and 256 % (cp // 8) == 0):
+        return None
+    mx = _mask_from_x(dz, x, act, fwd)
+    if z is None and not mx:
+        return None
+    n1 = torch.zeros(cp, dtype=torch.float64, device=dz.device)
+    n2 = torch.zeros(cp, dtype=torch.float64, device=dz.device)
+    vdz, vx, vdx = view4(dz), view4(x), view4(dx)
+    vz = view4(z) if (z is not None and not mx) else _lib.null_view()
+    check(profiler.launch("bn_bwd_apply", lambda: lib().pmoe_bn_bwd_apply_sums(
+        C.byref(vdz), C.byref(vz), C.byref(vx), dtype_code(dz), ACT[act], _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma),
+        _lib.ptr(s1), _lib.ptr(s2), float(inv_n), C.byref(vdx), _lib.ptr(fwd[0] if mx else None), _lib.ptr(fwd[1] if mx else None),
+        n1.data_ptr(), n2.data_ptr(), stream_ptr()), io=(dz, None if mx else z, x, dx)), "bn_bwd_apply_sums")
+    return n1, n2
+
+
 def _bn_bwd_apply(dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, batch_stats, dx, dres, acc_dres, fwd=None):
     mx = _mask_from_x(dz, x, act, fwd) and (dx is None or dx.is_contiguous()) and (dres is None or dres.is_contiguous())
     vdz = view4(dz)
@@ -144,6 +169,7 @@ def _axpy(src, dst, alpha=1.0, bcast=None, accumulate=False):
 def _accumulate(tape, act, g):
     """grads[act] += g (g already shaped like act.t)."""
     k = id(act)
+    tape.presums.pop(k, None)  # sums reduced from an earlier, now incomplete gradient
     if k in tape.grads:
         _axpy(g, tape.grads[k], 1.0, None, True)
     else:
@@ -154,6 +180,7 @@ def _grad_buffer(tape, act):
     """Existing gradient buffer of `act` (to be accumulated into) or a fresh one; returns (tensor, existed)."""
     k = id(act)
     if k in tape.grads:
+        tape.presums.pop(k, None)
         return tape.grads[k], True
     g = torch.empty(act.t.shape, dtype=act.t.dtype, device=act.t.device)
     tape.grads[k] = g
@@ -424,6 +451,7 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
                  residual=None if residual is None else residual.t, pool_sum=pool, pool_stride=pool_stride, flops=flops, tag=tag)
     z = _new_act(tape, z_t, cout, rg_in)
     z.stats = out_stats
+    z.bn_relu = bool(bn_train and act == "relu" and residual is None and fwd_aff is not None)  # z = relu(BN(raw)), nothing added
     if not (tape.save and rg_in):
         return z, pool
 
@@ -437,7 +465,16 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
             dres, acc_dres = _grad_buffer(tape, residual)
         dy = torch.empty(n, h, w, cstore, dtype=dt, device=dev)  # gradient w.r.t. the raw conv output
         if bn_train:
-            s1, s2 = _bn_bwd_reduce(dz, z_saved, raw, act, mean, rstd, cstore, fwd=fwd_aff)
+            pres = tape.presums.pop(id(z), None)
+            if pres is not None and fwd_aff is not None and act == "relu":
+                # the kernel that wrote dz also reduced sum dz*[z>0] and sum dz*z; with z = relu(scale*raw + shift):
+                # sum dz*m*raw = (sum dz*z - shift * sum dz*m) / scale, and the kernels' second sum is rstd*(that - mean*first)
+                sc, sh = fwd_aff[0][:cstore].double(), fwd_aff[1][:cstore].double()
+                s1 = pres[0]
+                sraw = torch.where(sc != 0, (pres[1] - sh * s1) / torch.where(sc != 0, sc, torch.ones_like(sc)), torch.zeros_like(sc))
+                s2 = rstd[:cstore].double() * (sraw - mean[:cstore].double() * s1)
+            else:
+                s1, s2 = _bn_bwd_reduce(dz, z_saved, raw, act, mean, rstd, cstore, fwd=fwd_aff)
             tape.add_pgrad(bn.weight, s2[:cout])
             tape.add_pgrad(bn.bias, s1[:cout])
             _bn_bwd_apply(dz, z_saved, raw, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, dy, dres, acc_dres, fwd=fwd_aff)
@@ -755,7 +792,15 @@ def bn_act_op(tape, bn, x, act="relu", tag=""):
                 s1, s2 = _bn_bwd_reduce(dz, zs, x.t, act, mean, rstd, cp, fwd=fwd_aff)
                 tape.add_pgrad(bn.weight, s2[:c])
                 tape.add_pgrad(bn.bias, s1[:c])
-                _bn_bwd_apply(dz, zs, x.t, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, tmp, None, False, fwd=fwd_aff)
+                nxt = None
+                if getattr(x, "bn_relu", False) and not existed:
+                    # x = relu(BN(raw)) of the conv just upstream and this is its only gradient so far: reduce that layer's
+                    # backward sums while dx is in registers (invalidated if anything is accumulated into dx later)
+                    nxt = _bn_bwd_apply_sums(dz, zs, x.t, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), tmp, fwd_aff)
+                if nxt is not None:
+                    tape.presums[id(x)] = nxt
+                else:
+                    _bn_bwd_apply(dz, zs, x.t, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, tmp, None, False, fwd=fwd_aff)
             else:
                 if _any_rg([bn.weight, bn.bias]):
                     raise NotImplementedError("pmoe_b200: gradients of BatchNorm affine parameters in eval mode are not supported")
@@ -1411,6 +1456,7 @@ def punet_module_forward(net, images):
 def _accumulate_copy(tape, act, gview):
     """grads[act] += gview where gview is a strided view with act's geometry."""
     k = id(act)
+    tape.presums.pop(k, None)
     if k in tape.grads:
         _axpy(gview, tape.grads[k], 1.0, None, True)
     else:

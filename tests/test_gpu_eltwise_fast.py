@@ -120,3 +120,67 @@ def test_nchw_to_nhwc_narrow_and_wide(c):
     xs = torch.rand(3, 2 * c, 18, 22, generator=g).to(dev)[:, ::2]      # strided source planes
     a = nhwc.from_nchw(xs, dtype=torch.bfloat16)
     assert torch.equal(a.t[..., :c], xs.permute(0, 2, 3, 1).to(torch.bfloat16))
+
+
+def test_bn_chain_sums_fused_into_apply_matches_reduce_pass():
+    """torchvision's bn1 follows the stem block's conv+BN+ReLU directly: bn1's backward-apply kernel also reduces the two
+    backward sums of the UPSTREAM BatchNorm (sum dx*[x>0], sum dx*x -> sum dy*m and sum dy*m*raw through the forward affine),
+    which then needs no reduce pass. Every gradient of the stem must agree with the separate-reduce form to bf16 noise, and
+    both with the fp32 CUDA-core path."""
+    import torch.nn as nn
+    from pmoe_b200 import config, train
+    from pmoe_b200.model.blocks.basics import EfficientConvBlock
+
+    class Stem(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = EfficientConvBlock(12, 64)
+            self.bn1 = nn.BatchNorm2d(64)
+
+        def forward(self, x):
+            def body(tape, a):
+                y = train.eca_conv_block(tape, self.conv1, a, tag="stem.conv1", want_out_stats=True)
+                y = train.bn_act_op(tape, self.bn1, y, "relu", tag="stem.bn1")
+                return train.maxpool_op(tape, y, 3, 2, 1)
+            return train.nhwc_module_forward(self, x, body)
+
+    torch.manual_seed(5)
+    ref_mod = Stem()
+    with torch.no_grad():
+        for m_ in ref_mod.modules():
+            if isinstance(m_, nn.BatchNorm2d):
+                m_.weight.uniform_(0.5, 1.5)
+                m_.bias.normal_(0, 0.2)
+    sd = ref_mod.state_dict()
+    x = torch.rand(8, 12, 64, 64, device=dev)
+    cot = torch.randn(8, 64, 32, 32, device=dev) * 1e-2
+
+    def run(prec, fuse):
+        old = train.FUSE_BN_CHAIN_SUMS
+        train.FUSE_BN_CHAIN_SUMS = fuse
+        try:
+            with config.use_precision(prec):
+                m = Stem()
+                m.load_state_dict(sd)
+                m = m.cuda().train()
+                out = m(x)
+                (out * cot).sum().backward()
+                return out.detach().float(), {n: p.grad.detach().double().clone() for n, p in m.named_parameters()}
+        finally:
+            train.FUSE_BN_CHAIN_SUMS = old
+
+    (of, gf), (os_, gs), (o32, g32) = run("bf16", True), run("bf16", False), run("fp32", False)
+    assert torch.equal(of, os_)                                   # the forward is untouched
+    names = [n for n in gf if "eca" not in n]                     # ECA kernel gradients: cancelling sums, not a yardstick
+    rows = []
+    for n in names:
+        d = (gf[n] - gs[n]).norm().item() / max(gs[n].norm().item(), 1e-30)
+        ef = (gf[n] - g32[n]).norm().item() / max(g32[n].norm().item(), 1e-30)
+        es = (gs[n] - g32[n]).norm().item() / max(g32[n].norm().item(), 1e-30)
+        rows.append((n, d, ef, es))
+    print("\n" + "\n".join("%-34s fused-vs-split %.2e | fused-vs-fp32 %.2e | split-vs-fp32 %.2e" % r for r in rows))
+    for n, d, ef, es in rows:
+        # the fused sums see the upstream raw output through its bf16-rounded ReLU output (one more rounding than the separate
+        # pass): the two forms may differ by bf16 noise, and the fused one must be as close to the fp32 path as the split one
+        assert d < 3e-2, (n, d)
+        assert ef < max(3e-2, 1.5 * es), (n, ef, es)

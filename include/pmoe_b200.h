@@ -195,6 +195,12 @@ int pmoe_eca_gate_bwd(const double* dgate, int64_t dgate_stride, const float* ga
                       pmoe_stream_t stream);
 int pmoe_eca_bwd_apply(const PmoeView4* dout, int32_t dtype, const float* gate, int64_t gate_stride, const float* dmean,
                        int64_t dmean_stride, const PmoeView4* dx, int32_t accumulate, pmoe_stream_t stream);
+/* The same pass when the ECA block's forward input x_fwd is the ReLU output of an upstream BatchNorm and dx its complete
+ * gradient (EfficientConvBlock's second gate, basics.py:118-121): also accumulates that layer's backward sums, as
+ * pmoe_bn_bwd_apply_sums does. Dense bf16, fresh dx, channel-group count dividing 256; otherwise PMOE_ERR_UNSUPPORTED. */
+int pmoe_eca_bwd_apply_sums(const PmoeView4* dout, int32_t dtype, const float* gate, int64_t gate_stride, const float* dmean,
+                            int64_t dmean_stride, const PmoeView4* dx, const PmoeView4* x_fwd, double* next_sum_dx,
+                            double* next_sum_dx_x, pmoe_stream_t stream);
 /* dst (+)= alpha*src + bcast[n][c]: gradient accumulation and global-avg-pool backward. */
 int pmoe_axpy(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, float alpha, const float* bcast, int64_t bcast_stride,
               int32_t accumulate, pmoe_stream_t stream);

@@ -623,11 +623,16 @@ __global__ void __launch_bounds__(256) maxpool3s2_bwd_pair_kernel(const uint4* _
 
 // dx (+)= dout * gate[n, c] + dmean[n, c] on dense bf16: grid (x, n), one channel group per thread, gate / dmean in
 // registers, four 16-byte loads in flight (the generic kernel: one load behind a div/mod chain, 61 % of HBM).
-template <bool ACC>
+// NEXT: xf is the forward input of the ECA block and at the same time the ReLU output of an upstream BatchNorm whose complete
+// gradient dx is: that layer's backward sums (sum dx*[xf>0], sum dx*xf; see bn_bwd_apply_fast_kernel) are reduced here.
+template <bool ACC, bool NEXT>
 __global__ void __launch_bounds__(256) eca_bwd_apply_fast_kernel(const uint4* __restrict__ dout, uint4* __restrict__ dx,
                                                                  long long per_img, int cg, const float* __restrict__ gate,
                                                                  long long gate_stride, const float* __restrict__ dmean,
-                                                                 long long dmean_stride) {
+                                                                 long long dmean_stride, const uint4* __restrict__ xf,
+                                                                 double* __restrict__ next_s1, double* __restrict__ next_s2) {
+  __shared__ float sm_next[NEXT ? kRedThreads * 8 : 8];
+  float na[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int n = blockIdx.y;
   const long long stride = (long long)gridDim.x * blockDim.x;  // a multiple of cg
   const long long first = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -638,7 +643,7 @@ __global__ void __launch_bounds__(256) eca_bwd_apply_fast_kernel(const uint4* __
   const uint4* src = dout + (size_t)n * per_img;
   uint4* dst = dx + (size_t)n * per_img;
   for (long long i = first; i < per_img; i += 4 * stride) {
-    uint4 r[4], ro[4];
+    uint4 r[4], ro[4], rx[4];
     bool ok[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -647,6 +652,7 @@ __global__ void __launch_bounds__(256) eca_bwd_apply_fast_kernel(const uint4* __
       const long long off = ok[u] ? ii : i;
       r[u] = __ldg(src + off);
       if (ACC) ro[u] = dst[off];
+      if (NEXT) rx[u] = __ldg(xf + (size_t)n * per_img + off);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -656,7 +662,31 @@ __global__ void __launch_bounds__(256) eca_bwd_apply_fast_kernel(const uint4* __
       if (ACC) bf16x8_to_f32(ro[u], o);
 #pragma unroll
       for (int q = 0; q < 8; ++q) o[q] = fmaf(d[q], gt[q], dm[q]) + (ACC ? o[q] : 0.f);
-      dst[i + (long long)u * stride] = f32_to_bf16x8(o);
+      const uint4 pk = f32_to_bf16x8(o);
+      dst[i + (long long)u * stride] = pk;
+      if (NEXT) {
+        float ov[8], xv[8];
+        bf16x8_to_f32(pk, ov);
+        bf16x8_to_f32(rx[u], xv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          na[q] += xv[q] > 0.f ? ov[q] : 0.f;
+          nb[q] = fmaf(ov[q], xv[q], nb[q]);
+        }
+      }
+    }
+  }
+  if (NEXT) {
+    float ta[kRedMaxIter], tb[kRedMaxIter];
+    block_channel_sum(na, sm_next, cg, blockDim.x / cg, ta);
+    block_channel_sum(nb, sm_next, cg, blockDim.x / cg, tb);
+#pragma unroll
+    for (int j = 0; j < kRedMaxIter; ++j) {
+      const int c = threadIdx.x + j * kRedThreads;
+      if (c < cg * 8) {
+        atomicAdd(next_s1 + c, (double)ta[j]);
+        atomicAdd(next_s2 + c, (double)tb[j]);
+      }
     }
   }
 }
@@ -1120,8 +1150,9 @@ int pmoe_eca_gate_bwd(const double* dgate, int64_t dgate_stride, const float* ga
   return check_launch("eca_gate_bwd");
 }
 
-int pmoe_eca_bwd_apply(const PmoeView4* dout, int32_t dtype, const float* gate, int64_t gate_stride, const float* dmean,
-                       int64_t dmean_stride, const PmoeView4* dx, int32_t accumulate, pmoe_stream_t stream_) {
+static int eca_bwd_apply_impl(const PmoeView4* dout, int32_t dtype, const float* gate, int64_t gate_stride, const float* dmean,
+                              int64_t dmean_stride, const PmoeView4* dx, int32_t accumulate, const PmoeView4* xf, double* next_s1,
+                              double* next_s2, pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc;
   if ((rc = chk(dout, dtype, "eca_bwd_apply dout"))) return rc;
@@ -1142,12 +1173,41 @@ int pmoe_eca_bwd_apply(const PmoeView4* dout, int32_t dtype, const float* gate, 
     dim3 grid((unsigned)bx, (unsigned)dx->n);
     const uint4* pd = static_cast<const uint4*>(dout->ptr);
     uint4* px = static_cast<uint4*>(dx->ptr);
-    if (accumulate) eca_bwd_apply_fast_kernel<true><<<grid, 256, 0, stream>>>(pd, px, per_img, cg, gate, gate_stride, dmean, dmean_stride);
-    else eca_bwd_apply_fast_kernel<false><<<grid, 256, 0, stream>>>(pd, px, per_img, cg, gate, gate_stride, dmean, dmean_stride);
+    if (next_s1) {
+      if (accumulate || 256 % cg != 0 || !xf || !xf->ptr || !all_flat(dx, {xf})) {
+        set_error("eca_bwd_apply_sums: needs a fresh dx, a dense forward input of dx's shape and a channel-group count dividing 256");
+        return PMOE_ERR_UNSUPPORTED;
+      }
+      eca_bwd_apply_fast_kernel<false, true><<<grid, 256, 0, stream>>>(pd, px, per_img, cg, gate, gate_stride, dmean, dmean_stride,
+                                                                        static_cast<const uint4*>(xf->ptr), next_s1, next_s2);
+    } else if (accumulate) {
+      eca_bwd_apply_fast_kernel<true, false><<<grid, 256, 0, stream>>>(pd, px, per_img, cg, gate, gate_stride, dmean, dmean_stride, nullptr, nullptr, nullptr);
+    } else {
+      eca_bwd_apply_fast_kernel<false, false><<<grid, 256, 0, stream>>>(pd, px, per_img, cg, gate, gate_stride, dmean, dmean_stride, nullptr, nullptr, nullptr);
+    }
     return check_launch("eca_bwd_apply");
+  }
+  if (next_s1) {
+    set_error("eca_bwd_apply_sums: dense bf16 tensors only");
+    return PMOE_ERR_UNSUPPORTED;
   }
   BW_DISPATCH(dtype, (eca_bwd_apply_kernel<T><<<bgrid(items, 256), 256, 0, stream>>>(bv4(dout), gate, gate_stride, dmean, dmean_stride, bv4(dx), accumulate)));
   return check_launch("eca_bwd_apply");
+}
+
+int pmoe_eca_bwd_apply(const PmoeView4* dout, int32_t dtype, const float* gate, int64_t gate_stride, const float* dmean,
+                       int64_t dmean_stride, const PmoeView4* dx, int32_t accumulate, pmoe_stream_t stream_) {
+  return eca_bwd_apply_impl(dout, dtype, gate, gate_stride, dmean, dmean_stride, dx, accumulate, nullptr, nullptr, nullptr, stream_);
+}
+
+int pmoe_eca_bwd_apply_sums(const PmoeView4* dout, int32_t dtype, const float* gate, int64_t gate_stride, const float* dmean,
+                            int64_t dmean_stride, const PmoeView4* dx, const PmoeView4* x_fwd, double* next_sum_dx,
+                            double* next_sum_dx_x, pmoe_stream_t stream_) {
+  if (!next_sum_dx || !next_sum_dx_x) {
+    set_error("eca_bwd_apply_sums: both output sums are required");
+    return PMOE_ERR_ARG;
+  }
+  return eca_bwd_apply_impl(dout, dtype, gate, gate_stride, dmean, dmean_stride, dx, 0, x_fwd, next_sum_dx, next_sum_dx_x, stream_);
 }
 
 int pmoe_axpy(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, float alpha, const float* bcast, int64_t bcast_stride,

@@ -641,6 +641,17 @@ def eca_op(tape, eca_mod, x, layout=None, pool_in=None):
             if _rg(x):
                 g, existed = _grad_buffer(tape, x)
                 vd, vg = view4(dy), view4(g)
+                if (FUSE_BN_CHAIN_SUMS and getattr(x, "bn_relu", False) and not existed and dy.dtype == torch.bfloat16
+                        and dy.is_contiguous() and x.t.is_contiguous() and 256 % (cp // 8) == 0):
+                    # x = relu(BN(raw)) of the conv upstream and this is its whole gradient: that layer's backward sums ride along
+                    n1 = torch.zeros(cp, dtype=torch.float64, device=dy.device)
+                    n2 = torch.zeros(cp, dtype=torch.float64, device=dy.device)
+                    vx = view4(x.t)
+                    check(profiler.launch("eca_bwd_apply", lambda: lib().pmoe_eca_bwd_apply_sums(
+                        C.byref(vd), dtype_code(dy), gate.data_ptr(), gate.stride(0), dmean.data_ptr(), dmean.stride(0), C.byref(vg),
+                        C.byref(vx), n1.data_ptr(), n2.data_ptr(), stream_ptr()), io=(dy, g, x.t)), "eca_bwd_apply_sums")
+                    tape.presums[id(x)] = (n1, n2)
+                    return
                 check(profiler.launch("eca_bwd_apply", lambda: lib().pmoe_eca_bwd_apply(
                     C.byref(vd), dtype_code(dy), gate.data_ptr(), gate.stride(0), dmean.data_ptr(), dmean.stride(0), C.byref(vg),
                     int(existed), stream_ptr()), io=(dy, g, g if existed else None)), "eca_bwd_apply")

@@ -356,6 +356,7 @@ def _stride2_dgrad_fused(tape, x, weight, dy, co_pad, ck_d, n, oh, ow, flops, ta
     wd4 = _cached_pack(weight, "s2d4|%d|%d|%s" % (cs, co_pad, dy.dtype), build)
     g = torch.empty(x.t.shape, dtype=dy.dtype, device=dy.device)   # every pixel of every parity is written
     tape.grads[id(x)] = g
+    tape.presums.pop(id(x), None)
     dsegs = [(0, dh, dw, 0, co_pad // ck_d) for (dh, dw) in shifts]
     rows = g.view(n, oh, 2, ow, 2 * cs)
     ops.conv([dy], wd4, dsegs, ck_d, rows[:, :, 0], out_extra=[rows[:, :, 1]], out_cols=2 * cs, flops=flops, tag="dgrad " + tag)
@@ -508,6 +509,7 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
             wd = _pack_dgrad(weight, src, segs_i, cstore, dt)
             dsegs = [(0, -dh, -dw, 0, cstore // ck_d) for (_, dh, dw, _, _) in segs_i]
             k = id(src.act)
+            tape.presums.pop(k, None)  # this launch changes (or creates) the gradient: sums reduced earlier no longer describe it
             if k not in tape.grads:
                 g = torch.empty(src.act.t.shape, dtype=dt, device=dev)
                 if src.t.shape != src.act.t.shape:

@@ -221,7 +221,16 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 // FEAT < 0: every optional feature is a run-time flag (generic). FEAT >= 0: the feature set is fixed at compile time
 // (kFeatShift | kFeatRelu | kFeatStats | kFeatPool2 | kFeatPoolSum | kFeatNchw | kFeatRes; no scale / other activations), which turns the per-element path into straight-line code (~3 instead of ~11 instructions per element: the
 // epilogue, not the tensor core, was the limit of the 64-channel layers).
-constexpr int kFeatShift = 1, kFeatRelu = 2, kFeatStats = 4, kFeatPool2 = 8, kFeatPoolSum = 16, kFeatNchw = 32, kFeatRes = 64;
+constexpr int kFeatShift = 1, kFeatRelu = 2, kFeatStats = 4, kFeatPool2 = 8, kFeatPoolSum = 16, kFeatNchw = 32, kFeatRes = 64,
+              kFeatElu = 128;
+// ELU for the compile-time epilogue of the expert heads (make_mlp act='elu', conf/stage_2.yaml:83-90): expm1f is a ~25-instruction
+// libdevice routine and made the 512-wide ELU layers 2-4x slower than their ReLU twins at 64k rows. exp(x) - 1 through the SFU, with a
+// cubic series near zero where that difference cancels (|error| < 1e-5 relative, far inside the bf16 rounding of the stored value).
+__device__ __forceinline__ float elu_fast(float x) {
+  const float series = x * fmaf(x, fmaf(x, 0.16666667f, 0.5f), 1.f);
+  const float ex = __expf(x) - 1.f;
+  return x > 0.f ? x : (x > -0.0625f ? series : ex);
+}
 template <int BN, int OCW, int SUB, int OUT_BYTES, int FEAT, class Iter>
 __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& it, uint8_t* out_stage, float* s_scale, float* s_shift,
                                              float* s_pool, float* s_sum, float* s_sq, uint64_t* tfull_bar, uint64_t* tempty_bar,
@@ -241,7 +250,7 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
   constexpr int NSB = OCW / SUB;          // 32-column blocks per chunk: 2 (one per warp of the pair) or 1
   const bool worker = half < NSB;         // with a single block per chunk the second warp only keeps the barriers
   constexpr bool kGen = FEAT < 0;
-  const int act = kGen ? p.act : ((FEAT & kFeatRelu) ? PMOE_ACT_RELU : PMOE_ACT_NONE);
+  const int act = kGen ? p.act : ((FEAT & kFeatRelu) ? PMOE_ACT_RELU : ((FEAT & kFeatElu) ? PMOE_ACT_ELU : PMOE_ACT_NONE));
   const bool has_scale = kGen && p.scale != nullptr;
   const bool has_shift = kGen ? (p.shift != nullptr) : (FEAT & kFeatShift) != 0;
   const bool has_stats = kGen ? (p.stat_sum != nullptr) : (FEAT & kFeatStats) != 0;
@@ -397,6 +406,9 @@ __device__ __forceinline__ void run_epilogue(const ConvTcParams& p, const Iter& 
         if (act == PMOE_ACT_RELU) {  // the branch is uniform and hoisted out of the element loop
 #pragma unroll
           for (int k = 0; k < SUB; ++k) y[k] = fmaxf(y[k], 0.f);
+        } else if (!kGen && act == PMOE_ACT_ELU) {
+#pragma unroll
+          for (int k = 0; k < SUB; ++k) y[k] = elu_fast(y[k]);
         } else if (act != PMOE_ACT_NONE) {
 #pragma unroll
           for (int k = 0; k < SUB; ++k) y[k] = apply_act(y[k], act);
@@ -1058,6 +1070,7 @@ static int launch_tc(const ConvTcParams& p, cudaStream_t stream) {
       case kFeatShift | kFeatRelu: return launch_tc_feat<BN, CK, kFeatShift | kFeatRelu>(p, stream);
       case kFeatShift | kFeatRelu | kFeatPool2: return launch_tc_feat<BN, CK, kFeatShift | kFeatRelu | kFeatPool2>(p, stream);
       case kFeatStats: return launch_tc_feat<BN, CK, kFeatStats>(p, stream);
+      case kFeatShift | kFeatElu: return launch_tc_feat<BN, CK, kFeatShift | kFeatElu>(p, stream);  // expert-head ELU layers
       case kFeatRes: return launch_tc_feat<BN, CK, kFeatRes>(p, stream);  // data gradient accumulated into an existing buffer
       case kFeatShift | kFeatRelu | kFeatRes: return launch_tc_feat<BN, CK, kFeatShift | kFeatRelu | kFeatRes>(p, stream);
       default: break;
@@ -1349,8 +1362,8 @@ extern "C" int pmoe_conv_tc(const PmoeConvTc* d, pmoe_stream_t stream_) {
   p.cout_pad = d->cout_pad;
   p.pool_stride = d->pool_stride > 0 ? d->pool_stride : d->cout_pad;
   p.feat = -1;
-  if (!d->scale && (d->act == PMOE_ACT_NONE || d->act == PMOE_ACT_RELU))
-    p.feat = (d->shift ? kFeatShift : 0) | (d->act == PMOE_ACT_RELU ? kFeatRelu : 0) | (d->stat_sum ? kFeatStats : 0) |
+  if (!d->scale && (d->act == PMOE_ACT_NONE || d->act == PMOE_ACT_RELU || d->act == PMOE_ACT_ELU))
+    p.feat = (d->shift ? kFeatShift : 0) | (d->act == PMOE_ACT_RELU ? kFeatRelu : 0) | (d->act == PMOE_ACT_ELU ? kFeatElu : 0) | (d->stat_sum ? kFeatStats : 0) |
              (d->pool2_out.ptr ? kFeatPool2 : 0) | (d->pool_sum ? kFeatPoolSum : 0) | (d->nchw_out ? kFeatNchw : 0) |
              (d->residual.ptr ? kFeatRes : 0);
   if (halo_bn) {

@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_fast_kernel(const u
         const bool ok = pp < p1;
         const long long off = ok ? pp * cg + g : p * cg + g;
         rd[u] = ok ? __ldg(dz + off) : make_uint4(0u, 0u, 0u, 0u);
-        if (ACT == 1) rz[u] = __ldg(z + off);
+        if (ACT == 1 || ACT == 3) rz[u] = __ldg(z + off);
         if (HAS_X || ACT == 2) rx[u] = __ldg(x + off);
       }
 #pragma unroll
@@ -737,6 +737,12 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_fast_kernel(const u
           bf16x8_to_f32(rz[u], zv);
 #pragma unroll
           for (int q = 0; q < 8; ++q) d[q] = zv[q] > 0.f ? d[q] : 0.f;
+        }
+        if (ACT == 3) {  // ELU from the saved output: d/dx = z + 1 for z <= 0
+          float zv[8];
+          bf16x8_to_f32(rz[u], zv);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) d[q] = zv[q] > 0.f ? d[q] : d[q] * (zv[q] + 1.f);
         }
         if (ACT == 2) {
 #pragma unroll
@@ -817,7 +823,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(const uint4* __r
       ok[u] = ii < total;
       const long long off = ok[u] ? ii : i;
       rd[u] = __ldg(dz + off);
-      if (ACT == 1) rz[u] = __ldg(z + off);
+      if (ACT == 1 || ACT == 3) rz[u] = __ldg(z + off);
       if (BATCH || ACT == 2) rx[u] = __ldg(x + off);
       if (dres != nullptr && accumulate_dres) ro[u] = dres[off];
     }
@@ -833,6 +839,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(const uint4* __r
         bf16x8_to_f32(rz[u], zv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) d[q] = zv[q] > 0.f ? d[q] : 0.f;
+      }
+      if (ACT == 3) {  // ELU from the saved output
+        float zv[8];
+        bf16x8_to_f32(rz[u], zv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) d[q] = zv[q] > 0.f ? d[q] : d[q] * (zv[q] + 1.f);
       }
       if (ACT == 2) {
 #pragma unroll
@@ -957,7 +969,7 @@ int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4*
   if (ppb < 64) ppb = 64;
   blocks = (npix + ppb - 1) / ppb;
   const bool flat = all_flat(dz, {dz, z, x});
-  if (flat && dtype == PMOE_BF16 && (act == PMOE_ACT_NONE || act == PMOE_ACT_RELU) && (!sum_dy_xhat || (x && x->ptr && mean && rstd))) {
+  if (flat && dtype == PMOE_BF16 && (act == PMOE_ACT_NONE || act == PMOE_ACT_RELU || act == PMOE_ACT_ELU) && (!sum_dy_xhat || (x && x->ptr && mean && rstd))) {
     const uint4* pdz = static_cast<const uint4*>(dz->ptr);
     const uint4* pz = (act && !mask_x) ? static_cast<const uint4*>(z->ptr) : nullptr;
     const bool has_x = sum_dy_xhat != nullptr;
@@ -965,6 +977,8 @@ int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4*
 #define PMOE_RED_FAST(A, X) bn_bwd_reduce_fast_kernel<A, X><<<(unsigned)blocks, 256, 0, stream>>>(pdz, pz, px, npix, cg, mean, rstd, sum_dy, sum_dy_xhat, ppb, fwd_scale, fwd_shift)
     if (mask_x && has_x) PMOE_RED_FAST(2, true);
     else if (mask_x) PMOE_RED_FAST(2, false);
+    else if (act == PMOE_ACT_ELU && has_x) PMOE_RED_FAST(3, true);
+    else if (act == PMOE_ACT_ELU) PMOE_RED_FAST(3, false);
     else if (act && has_x) PMOE_RED_FAST(1, true);
     else if (act) PMOE_RED_FAST(1, false);
     else if (has_x) PMOE_RED_FAST(0, true);
@@ -1004,7 +1018,7 @@ static int bn_bwd_apply_impl(const PmoeView4* dz, const PmoeView4* z, const Pmoe
   const long long items = (long long)dz->n * dz->h * dz->w * (dz->c / 8);
   const int grid = grid_cg(items, dz->c / 8);
   const bool flat_all = all_flat(dz, {dz, z, x, dx, dres});
-  if (flat_all && dtype == PMOE_BF16 && (act == PMOE_ACT_NONE || act == PMOE_ACT_RELU)) {
+  if (flat_all && dtype == PMOE_BF16 && (act == PMOE_ACT_NONE || act == PMOE_ACT_RELU || (act == PMOE_ACT_ELU && !next_s1))) {
     const uint4* pdz = static_cast<const uint4*>(dz->ptr);
     const uint4* pz = (act && !mask_x) ? static_cast<const uint4*>(z->ptr) : nullptr;
     const uint4* px = (batch_stats || mask_x) ? static_cast<const uint4*>(x->ptr) : nullptr;
@@ -1025,6 +1039,8 @@ static int bn_bwd_apply_impl(const PmoeView4* dz, const PmoeView4* z, const Pmoe
         bn_bwd_apply_fast_kernel<1, true, true><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, fwd_scale, fwd_shift, next_s1, next_s2);
     } else if (mask_x && batch_stats) PMOE_APPLY_FAST(2, true);
     else if (mask_x) PMOE_APPLY_FAST(2, false);
+    else if (act == PMOE_ACT_ELU && batch_stats) PMOE_APPLY_FAST(3, true);
+    else if (act == PMOE_ACT_ELU) PMOE_APPLY_FAST(3, false);
     else if (act && batch_stats) PMOE_APPLY_FAST(1, true);
     else if (act) PMOE_APPLY_FAST(1, false);
     else if (batch_stats) PMOE_APPLY_FAST(0, true);

@@ -28,3 +28,29 @@ def test_wgrad_tc_matches_simt_and_torch():
         assert r["rel_vs_simt"] < 1e-4, r
         if r.get("rel_vs_torch") is not None:
             assert r["rel_vs_torch"] < 1e-4, r
+
+
+@pytest.mark.parametrize("cout", [1, 4])
+def test_skinny_linear_wgrad_uses_padded_tensor_core_path(cout):
+    """The 512->1 / 512->4 expert-head Linears (model/moe.py:71-72) over many rows: the weight gradient of a layer with fewer than
+    64 output channels runs on the tensor-core kernel through a zero-padded dy (ops.conv_wgrad) and must equal torch's dy^T x on
+    the same bf16 operands (fp32 accumulation: 1e-4), also when accumulated into a non-zero dwpack."""
+    import torch
+    from pmoe_b200 import ops, profiler
+    rows, cin = 16384, 512
+    g = torch.Generator().manual_seed(cout)
+    x = torch.randn(1, 1, rows, cin, generator=g).cuda().to(torch.bfloat16)
+    dy = torch.zeros(1, 1, rows, 16, dtype=torch.bfloat16, device="cuda")
+    dy[..., :cout] = torch.randn(1, 1, rows, cout, generator=g).cuda().to(torch.bfloat16)
+    segs = ops.conv_segments([(0, 0)], [cin], 64)
+    base = torch.randn(16, cin, generator=g).cuda()
+    dwp = base.clone()
+    profiler.reset()
+    profiler.enable_events(True)
+    ops.conv_wgrad([x], segs, 64, dy, dwp, tag="skinny")
+    kinds = [r[0] for r in profiler.records()]
+    profiler.enable_events(False)
+    assert "conv_wgrad_tc" in kinds and "conv_wgrad" not in kinds, kinds
+    ref = dy[0, 0].float().t() @ x[0, 0].float() + base
+    assert ((dwp - ref).norm() / ref.norm()).item() < 1e-4
+    assert (dwp[cout:] - base[cout:]).abs().max().item() == 0

@@ -1076,6 +1076,13 @@ static int launch_tc(const ConvTcParams& p, cudaStream_t stream) {
       default: break;
     }
   }
+  if constexpr (CK == 16 && BN >= 64) {  // K = 16: data gradients of the 512->1 / 512->4 head Linears (one MMA per tile: pure epilogue)
+    switch (p.feat) {
+      case 0: return launch_tc_feat<BN, CK, 0>(p, stream);
+      case kFeatRes: return launch_tc_feat<BN, CK, kFeatRes>(p, stream);
+      default: break;
+    }
+  }
   return launch_tc_feat<BN, CK, -1>(p, stream);
 }
 

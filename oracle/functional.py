@@ -182,6 +182,62 @@ def resnet18_eca(x, sd, p, train):
     return resnet_eca(x, sd, p, train, "resnet18")
 
 
+# ------------------------------------------------------------------ MobileNetV2 + ECA stem (backbone.py:75-104)
+# torchvision MobileNetV2 (pinned 0.9.1, unchanged arithmetic in 0.26): features[0] = (Conv3x3 s2 -> replaced by the reference with
+# a STRIDE-1 EfficientConvBlock(n_frames*3 -> 32), BN, ReLU6); 17 InvertedResidual blocks (t, c, n, s below: 1x1 expand + BN +
+# ReLU6 unless t == 1, depthwise 3x3 stride s + BN + ReLU6, 1x1 project + BN, identity add when s == 1 and cin == cout);
+# features[18] = 1x1 conv 320 -> 1280 + BN + ReLU6; global average pool; classifier := Linear(1280, 512) (backbone.py:98-99).
+# Oracle groundwork for SURVEY §8 row a8 — the product does not build this family yet (get_backbone raises for it).
+MOBILENET_V2_CFG = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1))
+
+
+def _mbv2_blocks(cin=32):
+    out, idx = [], 1
+    for t, c, n, s in MOBILENET_V2_CFG:
+        for i in range(n):
+            out.append((idx, cin, c, s if i == 0 else 1, t))
+            cin, idx = c, idx + 1
+    return out
+
+
+def mobilenet_v2_eca(x, sd, p, train):
+    x = eca_conv_block(x, sd, p + "features.0.0.", train)
+    x = F.relu6(batchnorm(x, sd, p + "features.0.1.", train))
+    for idx, cin, cout, stride, t in _mbv2_blocks():
+        q = p + "features.%d.conv." % idx
+        y, j = x, 0
+        if t != 1:
+            y = F.relu6(batchnorm(F.conv2d(y, sd[q + "0.0.weight"]), sd, q + "0.1.", train))
+            j = 1
+        hid = y.shape[1]
+        y = F.relu6(batchnorm(F.conv2d(y, sd[q + "%d.0.weight" % j], None, stride, 1, 1, hid), sd, q + "%d.1." % j, train))
+        y = batchnorm(F.conv2d(y, sd[q + "%d.weight" % (j + 1)]), sd, q + "%d." % (j + 2), train)
+        x = x + y if (stride == 1 and cin == cout) else y
+    x = F.relu6(batchnorm(F.conv2d(x, sd[p + "features.18.0.weight"]), sd, p + "features.18.1.", train))
+    x = x.mean(dim=(2, 3))
+    return F.linear(x, sd[p + "classifier.weight"], sd[p + "classifier.bias"])
+
+
+def mobilenet_v2_spec(spec, p, cin, gamma=2, b=1):
+    eca_block_spec(spec, p + "features.0.0.", cin, 32, gamma, b)
+    _bn(spec, p + "features.0.1.", 32)
+    for idx, ci, co, stride, t in _mbv2_blocks():
+        q = p + "features.%d.conv." % idx
+        hid, j = ci * t, 0
+        if t != 1:
+            spec[q + "0.0.weight"] = (hid, ci, 1, 1)
+            _bn(spec, q + "0.1.", hid)
+            j = 1
+        spec[q + "%d.0.weight" % j] = (hid, 1, 3, 3)
+        _bn(spec, q + "%d.1." % j, hid)
+        spec[q + "%d.weight" % (j + 1)] = (co, hid, 1, 1)
+        _bn(spec, q + "%d." % (j + 2), co)
+    spec[p + "features.18.0.weight"] = (1280, 320, 1, 1)
+    _bn(spec, p + "features.18.1.", 1280)
+    spec[p + "classifier.weight"] = (512, 1280)
+    spec[p + "classifier.bias"] = (512,)
+
+
 # ------------------------------------------------------------------ PU-Net (model/punet.py:75-120)
 def punet(imgs, sd, p, train, past_frames=4, future_frames=6, inter_repr=False, unet_inter_repr=False):
     assert imgs.shape[-4] == past_frames

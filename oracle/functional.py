@@ -21,12 +21,13 @@ BN_MOMENTUM = 0.1
 
 
 # ------------------------------------------------------------------ blocks (model/blocks/basics.py)
-def batchnorm(x, sd, p, train):
-    """nn.BatchNorm{1,2}d defaults as instantiated at basics.py:34,52,55,103,124."""
+def batchnorm(x, sd, p, train, eps=BN_EPS, momentum=BN_MOMENTUM):
+    """nn.BatchNorm{1,2}d defaults as instantiated at basics.py:34,52,55,103,124 (torchvision's MobileNetV3 passes its own
+    eps / momentum)."""
     if train and p + "num_batches_tracked" in sd:
         sd[p + "num_batches_tracked"] += 1
     return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
-                        train, BN_MOMENTUM, BN_EPS)
+                        train, momentum, eps)
 
 
 def conv3_block(x, sd, p, train, stride=1):
@@ -216,6 +217,74 @@ def mobilenet_v2_eca(x, sd, p, train):
     x = F.relu6(batchnorm(F.conv2d(x, sd[p + "features.18.0.weight"]), sd, p + "features.18.1.", train))
     x = x.mean(dim=(2, 3))
     return F.linear(x, sd[p + "classifier.weight"], sd[p + "classifier.bias"])
+
+
+# torchvision MobileNetV3-Small (the arch `_get_mobilenet` falls back to, backbone.py:86-90): (cin, kernel, expanded, cout, SE, act, stride)
+MOBILENET_V3_SMALL_CFG = ((16, 3, 16, 16, True, "RE", 2), (16, 3, 72, 24, False, "RE", 2), (24, 3, 88, 24, False, "RE", 1),
+                          (24, 5, 96, 40, True, "HS", 2), (40, 5, 240, 40, True, "HS", 1), (40, 5, 240, 40, True, "HS", 1),
+                          (40, 5, 120, 48, True, "HS", 1), (48, 5, 144, 48, True, "HS", 1), (48, 5, 288, 96, True, "HS", 2),
+                          (96, 5, 576, 96, True, "HS", 1), (96, 5, 576, 96, True, "HS", 1))
+MBV3_BN = dict(eps=0.001, momentum=0.01)   # norm_layer = partial(BatchNorm2d, eps=0.001, momentum=0.01)
+
+
+def _make_divisible(v, divisor=8):
+    new_v = max(divisor, int(v + divisor / 2) // divisor * divisor)
+    return new_v + divisor if new_v < 0.9 * v else new_v
+
+
+def mobilenet_v3_small_eca(x, sd, p, train):
+    """Stride-1 ECA stem (16 channels) + BN + Hardswish; 11 inverted-residual blocks (1x1 expand unless expanded == cin, depthwise
+    k x k, optional squeeze-excite with ReLU / Hardsigmoid, 1x1 project, identity add when stride 1 and cin == cout); 1x1 conv to 576
+    + BN + Hardswish; global average pool; Linear(576, 1024) + Hardswish (+ Dropout, identity here) + Linear(1024, 512)."""
+    x = eca_conv_block(x, sd, p + "features.0.0.", train)
+    x = F.hardswish(batchnorm(x, sd, p + "features.0.1.", train, **MBV3_BN))
+    for i, (cin, k, exp, cout, se, act, stride) in enumerate(MOBILENET_V3_SMALL_CFG, start=1):
+        fn = F.hardswish if act == "HS" else F.relu
+        q = p + "features.%d.block." % i
+        y, j = x, 0
+        if exp != cin:
+            y = fn(batchnorm(F.conv2d(y, sd[q + "0.0.weight"]), sd, q + "0.1.", train, **MBV3_BN))
+            j = 1
+        y = fn(batchnorm(F.conv2d(y, sd[q + "%d.0.weight" % j], None, stride, (k - 1) // 2, 1, exp), sd, q + "%d.1." % j, train, **MBV3_BN))
+        j += 1
+        if se:
+            z = y.mean(dim=(2, 3), keepdim=True)
+            z = F.relu(F.conv2d(z, sd[q + "%d.fc1.weight" % j], sd[q + "%d.fc1.bias" % j]))
+            z = F.hardsigmoid(F.conv2d(z, sd[q + "%d.fc2.weight" % j], sd[q + "%d.fc2.bias" % j]))
+            y = y * z
+            j += 1
+        y = batchnorm(F.conv2d(y, sd[q + "%d.0.weight" % j]), sd, q + "%d.1." % j, train, **MBV3_BN)
+        x = x + y if (stride == 1 and cin == cout) else y
+    x = F.hardswish(batchnorm(F.conv2d(x, sd[p + "features.12.0.weight"]), sd, p + "features.12.1.", train, **MBV3_BN))
+    x = x.mean(dim=(2, 3))
+    x = F.hardswish(F.linear(x, sd[p + "classifier.0.weight"], sd[p + "classifier.0.bias"]))
+    return F.linear(x, sd[p + "classifier.3.weight"], sd[p + "classifier.3.bias"])
+
+
+def mobilenet_v3_small_spec(spec, p, cin, gamma=2, b=1):
+    eca_block_spec(spec, p + "features.0.0.", cin, 16, gamma, b)
+    _bn(spec, p + "features.0.1.", 16)
+    for i, (ci, k, exp, co, se, act, stride) in enumerate(MOBILENET_V3_SMALL_CFG, start=1):
+        q = p + "features.%d.block." % i
+        j = 0
+        if exp != ci:
+            spec[q + "0.0.weight"] = (exp, ci, 1, 1)
+            _bn(spec, q + "0.1.", exp)
+            j = 1
+        spec[q + "%d.0.weight" % j] = (exp, 1, k, k)
+        _bn(spec, q + "%d.1." % j, exp)
+        j += 1
+        if se:
+            sq = _make_divisible(exp // 4, 8)
+            spec[q + "%d.fc1.weight" % j], spec[q + "%d.fc1.bias" % j] = (sq, exp, 1, 1), (sq,)
+            spec[q + "%d.fc2.weight" % j], spec[q + "%d.fc2.bias" % j] = (exp, sq, 1, 1), (exp,)
+            j += 1
+        spec[q + "%d.0.weight" % j] = (co, exp, 1, 1)
+        _bn(spec, q + "%d.1." % j, co)
+    spec[p + "features.12.0.weight"] = (576, 96, 1, 1)
+    _bn(spec, p + "features.12.1.", 576)
+    spec[p + "classifier.0.weight"], spec[p + "classifier.0.bias"] = (1024, 576), (1024,)
+    spec[p + "classifier.3.weight"], spec[p + "classifier.3.bias"] = (512, 1024), (512,)
 
 
 def mobilenet_v2_spec(spec, p, cin, gamma=2, b=1):

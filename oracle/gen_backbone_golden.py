@@ -39,30 +39,34 @@ def main():
 
 
 def main_mobilenet():
-    """backbone.py:75-104 with arch='mobilenet_v2' (oracle groundwork for SURVEY §8 row a8; the product does not build the
+    """backbone.py:75-104 with arch='mobilenet_v2' / 'mobilenet_v3_small' (oracle groundwork for SURVEY §8 row a8; the product does not build the
     family yet): eval features, train features + gradients of the live reference -> tests/golden/backbone_mobilenet_v2.pt."""
     import warnings
     warnings.filterwarnings("ignore")
     import_reference()
     from model.blocks.backbone import get_backbone
-    spec = O.make_spec(O.mobilenet_v2_spec, 12, 2, 1)
-    sd = O.seeded_state_dict(spec, 33)
-    net = get_backbone(arch="mobilenet_v2", n_frames=4, pretrained=False, gamma=2, b=1, n_channels=3)
-    net.load_state_dict(sd, strict=True)
-    g = torch.Generator().manual_seed(133)
-    x = torch.rand(2, 12, 64, 64, generator=g)
-    cot = torch.randn(2, 512, generator=g) * 1e-2
-    net.eval()
-    with torch.no_grad():
-        f_eval = net(x)
-    net.train()
-    f_train = net(x)
-    (f_train * cot).sum().backward()
-    out = {"arch": "mobilenet_v2", "seed": 33, "x": x, "cot": cot, "feat_eval": f_eval, "feat_train": f_train.detach(),
-           "grads": grad_summary(net.named_parameters()), "bn": bn_summary(net.state_dict()),
-           "keys": {k: list(v.shape) for k, v in net.state_dict().items()}}
-    torch.save(out, os.path.join(ROOT, "tests", "golden", "backbone_mobilenet_v2.pt"))
-    print("mobilenet_v2 features", tuple(f_eval.shape), "params", sum(p.numel() for p in net.parameters()))
+    for arch, spec_fn, seed in (("mobilenet_v2", O.mobilenet_v2_spec, 33), ("mobilenet_v3_small", O.mobilenet_v3_small_spec, 34)):
+        spec = O.make_spec(spec_fn, 12, 2, 1)
+        sd = O.seeded_state_dict(spec, seed)
+        net = get_backbone(arch=arch, n_frames=4, pretrained=False, gamma=2, b=1, n_channels=3)
+        net.load_state_dict(sd, strict=True)
+        for m in net.modules():  # v3's classifier Dropout(p=0.2): switched off so that the train-mode golden is deterministic
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        g = torch.Generator().manual_seed(100 + seed)
+        x = torch.rand(2, 12, 64, 64, generator=g)
+        cot = torch.randn(2, 512, generator=g) * 1e-2
+        net.eval()
+        with torch.no_grad():
+            f_eval = net(x)
+        net.train()
+        f_train = net(x)
+        (f_train * cot).sum().backward()
+        out = {"arch": arch, "seed": seed, "x": x, "cot": cot, "feat_eval": f_eval, "feat_train": f_train.detach(),
+               "grads": grad_summary(net.named_parameters()), "bn": bn_summary(net.state_dict()),
+               "keys": {k: list(v.shape) for k, v in net.state_dict().items()}}
+        torch.save(out, os.path.join(ROOT, "tests", "golden", "backbone_%s.pt" % arch))
+        print(arch, "features", tuple(f_eval.shape), "params", sum(p.numel() for p in net.parameters()))
 
 
 if __name__ == "__main__":

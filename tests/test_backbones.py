@@ -127,21 +127,25 @@ def test_gpu_get_unet_segmentation_backbone(tmp_path, inter):
         assert _rel(got.cpu(), ref) < 1e-4
 
 
-def test_oracle_mobilenet_v2_vs_live_reference():
-    """Oracle groundwork for SURVEY §8 row a8 (`_get_mobilenet`, backbone.py:75-104, arch='mobilenet_v2'): the functional
-    restatement (stride-1 ECA stem, 17 inverted-residual blocks with depthwise 3x3 convs and ReLU6, 1280-wide head, Linear(1280,
-    512) classifier) against the live reference — state_dict keys/shapes, eval and train features, every gradient norm, BatchNorm
-    running statistics. The PRODUCT does not build this family yet: `get_backbone('mobilenet_v2')` must keep failing loudly
+@pytest.mark.parametrize("arch", ["mobilenet_v2", "mobilenet_v3_small"])
+def test_oracle_mobilenets_vs_live_reference(arch):
+    """Oracle groundwork for SURVEY §8 row a8 (`_get_mobilenet`, backbone.py:75-104): the functional restatements — MobileNetV2
+    (17 inverted-residual blocks, depthwise 3x3, ReLU6, Linear(1280, 512)) and MobileNetV3-Small (the arch the factory falls back
+    to: depthwise 3x3/5x5, squeeze-excite, Hardswish / Hardsigmoid, BN eps 1e-3 / momentum 0.01, Linear(576,1024)+Linear(1024,512)),
+    both with the stride-1 ECA stem — against the live reference: state_dict keys/shapes, eval and train features, every gradient
+    norm, BatchNorm running statistics. The PRODUCT does not build this family yet: `get_backbone` must keep failing loudly
     rather than fall back to anything."""
-    g = _load("mobilenet_v2")
-    spec = O.make_spec(O.mobilenet_v2_spec, 12, 2, 1)
+    g = _load(arch)
+    spec_fn, fwd = {"mobilenet_v2": (O.mobilenet_v2_spec, O.mobilenet_v2_eca),
+                    "mobilenet_v3_small": (O.mobilenet_v3_small_spec, O.mobilenet_v3_small_eca)}[arch]
+    spec = O.make_spec(spec_fn, 12, 2, 1)
     assert list(spec) == list(g["keys"]) and all(tuple(spec[k]) == tuple(g["keys"][k]) for k in spec)
     sd = O.seeded_state_dict(spec, g["seed"])
     with torch.no_grad():
-        fe = O.mobilenet_v2_eca(g["x"], {k: v.clone() for k, v in sd.items()}, "", False)
+        fe = fwd(g["x"], {k: v.clone() for k, v in sd.items()}, "", False)
     assert _rel(fe, g["feat_eval"]) < 1e-5
     leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
-    ft = O.mobilenet_v2_eca(g["x"], leaf, "", True)
+    ft = fwd(g["x"], leaf, "", True)
     assert _rel(ft.detach(), g["feat_train"]) < 1e-5
     (ft * g["cot"]).sum().backward()
     assert set(g["grads"]) == {k for k, v in leaf.items() if v.requires_grad}
@@ -151,4 +155,4 @@ def test_oracle_mobilenet_v2_vs_live_reference():
         assert _rel(leaf[k].float(), v.float()) < 1e-5
     from pmoe_b200.model.blocks.backbone import get_backbone
     with pytest.raises(NotImplementedError):
-        get_backbone(arch="mobilenet_v2", n_frames=4)
+        get_backbone(arch=arch, n_frames=4)

@@ -224,6 +224,12 @@ MOBILENET_V3_SMALL_CFG = ((16, 3, 16, 16, True, "RE", 2), (16, 3, 72, 24, False,
                           (24, 5, 96, 40, True, "HS", 2), (40, 5, 240, 40, True, "HS", 1), (40, 5, 240, 40, True, "HS", 1),
                           (40, 5, 120, 48, True, "HS", 1), (48, 5, 144, 48, True, "HS", 1), (48, 5, 288, 96, True, "HS", 2),
                           (96, 5, 576, 96, True, "HS", 1), (96, 5, 576, 96, True, "HS", 1))
+MOBILENET_V3_LARGE_CFG = ((16, 3, 16, 16, False, "RE", 1), (16, 3, 64, 24, False, "RE", 2), (24, 3, 72, 24, False, "RE", 1),
+                          (24, 5, 72, 40, True, "RE", 2), (40, 5, 120, 40, True, "RE", 1), (40, 5, 120, 40, True, "RE", 1),
+                          (40, 3, 240, 80, False, "HS", 2), (80, 3, 200, 80, False, "HS", 1), (80, 3, 184, 80, False, "HS", 1),
+                          (80, 3, 184, 80, False, "HS", 1), (80, 3, 480, 112, True, "HS", 1), (112, 3, 672, 112, True, "HS", 1),
+                          (112, 5, 672, 160, True, "HS", 2), (160, 5, 960, 160, True, "HS", 1), (160, 5, 960, 160, True, "HS", 1))
+MOBILENET_V3 = {"mobilenet_v3_small": (MOBILENET_V3_SMALL_CFG, 1024), "mobilenet_v3_large": (MOBILENET_V3_LARGE_CFG, 1280)}
 MBV3_BN = dict(eps=0.001, momentum=0.01)   # norm_layer = partial(BatchNorm2d, eps=0.001, momentum=0.01)
 
 
@@ -233,12 +239,22 @@ def _make_divisible(v, divisor=8):
 
 
 def mobilenet_v3_small_eca(x, sd, p, train):
+    return mobilenet_v3_eca(x, sd, p, train, "mobilenet_v3_small")
+
+
+def mobilenet_v3_large_eca(x, sd, p, train):
+    return mobilenet_v3_eca(x, sd, p, train, "mobilenet_v3_large")
+
+
+def mobilenet_v3_eca(x, sd, p, train, arch="mobilenet_v3_small"):
     """Stride-1 ECA stem (16 channels) + BN + Hardswish; 11 inverted-residual blocks (1x1 expand unless expanded == cin, depthwise
     k x k, optional squeeze-excite with ReLU / Hardsigmoid, 1x1 project, identity add when stride 1 and cin == cout); 1x1 conv to 576
     + BN + Hardswish; global average pool; Linear(576, 1024) + Hardswish (+ Dropout, identity here) + Linear(1024, 512)."""
     x = eca_conv_block(x, sd, p + "features.0.0.", train)
     x = F.hardswish(batchnorm(x, sd, p + "features.0.1.", train, **MBV3_BN))
-    for i, (cin, k, exp, cout, se, act, stride) in enumerate(MOBILENET_V3_SMALL_CFG, start=1):
+    cfg, _ = MOBILENET_V3[arch]
+    last = len(cfg) + 1
+    for i, (cin, k, exp, cout, se, act, stride) in enumerate(cfg, start=1):
         fn = F.hardswish if act == "HS" else F.relu
         q = p + "features.%d.block." % i
         y, j = x, 0
@@ -255,16 +271,26 @@ def mobilenet_v3_small_eca(x, sd, p, train):
             j += 1
         y = batchnorm(F.conv2d(y, sd[q + "%d.0.weight" % j]), sd, q + "%d.1." % j, train, **MBV3_BN)
         x = x + y if (stride == 1 and cin == cout) else y
-    x = F.hardswish(batchnorm(F.conv2d(x, sd[p + "features.12.0.weight"]), sd, p + "features.12.1.", train, **MBV3_BN))
+    x = F.hardswish(batchnorm(F.conv2d(x, sd[p + "features.%d.0.weight" % last]), sd, p + "features.%d.1." % last, train, **MBV3_BN))
     x = x.mean(dim=(2, 3))
     x = F.hardswish(F.linear(x, sd[p + "classifier.0.weight"], sd[p + "classifier.0.bias"]))
     return F.linear(x, sd[p + "classifier.3.weight"], sd[p + "classifier.3.bias"])
 
 
 def mobilenet_v3_small_spec(spec, p, cin, gamma=2, b=1):
+    mobilenet_v3_spec(spec, p, cin, gamma, b, "mobilenet_v3_small")
+
+
+def mobilenet_v3_large_spec(spec, p, cin, gamma=2, b=1):
+    mobilenet_v3_spec(spec, p, cin, gamma, b, "mobilenet_v3_large")
+
+
+def mobilenet_v3_spec(spec, p, cin, gamma=2, b=1, arch="mobilenet_v3_small"):
+    cfg, hidden = MOBILENET_V3[arch]
+    last, c_last = len(cfg) + 1, cfg[-1][3]
     eca_block_spec(spec, p + "features.0.0.", cin, 16, gamma, b)
     _bn(spec, p + "features.0.1.", 16)
-    for i, (ci, k, exp, co, se, act, stride) in enumerate(MOBILENET_V3_SMALL_CFG, start=1):
+    for i, (ci, k, exp, co, se, act, stride) in enumerate(cfg, start=1):
         q = p + "features.%d.block." % i
         j = 0
         if exp != ci:
@@ -281,10 +307,10 @@ def mobilenet_v3_small_spec(spec, p, cin, gamma=2, b=1):
             j += 1
         spec[q + "%d.0.weight" % j] = (co, exp, 1, 1)
         _bn(spec, q + "%d.1." % j, co)
-    spec[p + "features.12.0.weight"] = (576, 96, 1, 1)
-    _bn(spec, p + "features.12.1.", 576)
-    spec[p + "classifier.0.weight"], spec[p + "classifier.0.bias"] = (1024, 576), (1024,)
-    spec[p + "classifier.3.weight"], spec[p + "classifier.3.bias"] = (512, 1024), (512,)
+    spec[p + "features.%d.0.weight" % last] = (6 * c_last, c_last, 1, 1)
+    _bn(spec, p + "features.%d.1." % last, 6 * c_last)
+    spec[p + "classifier.0.weight"], spec[p + "classifier.0.bias"] = (hidden, 6 * c_last), (hidden,)
+    spec[p + "classifier.3.weight"], spec[p + "classifier.3.bias"] = (512, hidden), (512,)
 
 
 def mobilenet_v2_spec(spec, p, cin, gamma=2, b=1):

@@ -39,13 +39,14 @@ def main():
 
 
 def main_mobilenet():
-    """backbone.py:75-104 with arch='mobilenet_v2' / 'mobilenet_v3_small' (oracle groundwork for SURVEY §8 row a8; the product does not build the
+    """backbone.py:75-104 with arch='mobilenet_v2' / 'mobilenet_v3_small' / 'mobilenet_v3_large' (oracle groundwork for SURVEY §8 row a8; the product does not build the
     family yet): eval features, train features + gradients of the live reference -> tests/golden/backbone_mobilenet_v2.pt."""
     import warnings
     warnings.filterwarnings("ignore")
     import_reference()
     from model.blocks.backbone import get_backbone
-    for arch, spec_fn, seed in (("mobilenet_v2", O.mobilenet_v2_spec, 33), ("mobilenet_v3_small", O.mobilenet_v3_small_spec, 34)):
+    for arch, spec_fn, seed in (("mobilenet_v2", O.mobilenet_v2_spec, 33), ("mobilenet_v3_small", O.mobilenet_v3_small_spec, 34),
+                                ("mobilenet_v3_large", O.mobilenet_v3_large_spec, 35)):
         spec = O.make_spec(spec_fn, 12, 2, 1)
         sd = O.seeded_state_dict(spec, seed)
         net = get_backbone(arch=arch, n_frames=4, pretrained=False, gamma=2, b=1, n_channels=3)

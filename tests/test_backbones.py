@@ -127,17 +127,18 @@ def test_gpu_get_unet_segmentation_backbone(tmp_path, inter):
         assert _rel(got.cpu(), ref) < 1e-4
 
 
-@pytest.mark.parametrize("arch", ["mobilenet_v2", "mobilenet_v3_small"])
+@pytest.mark.parametrize("arch", ["mobilenet_v2", "mobilenet_v3_small", "mobilenet_v3_large"])
 def test_oracle_mobilenets_vs_live_reference(arch):
     """Oracle groundwork for SURVEY §8 row a8 (`_get_mobilenet`, backbone.py:75-104): the functional restatements — MobileNetV2
-    (17 inverted-residual blocks, depthwise 3x3, ReLU6, Linear(1280, 512)) and MobileNetV3-Small (the arch the factory falls back
+    (17 inverted-residual blocks, depthwise 3x3, ReLU6, Linear(1280, 512)) and MobileNetV3-Small / -Large (Small is the arch the factory falls back
     to: depthwise 3x3/5x5, squeeze-excite, Hardswish / Hardsigmoid, BN eps 1e-3 / momentum 0.01, Linear(576,1024)+Linear(1024,512)),
     both with the stride-1 ECA stem — against the live reference: state_dict keys/shapes, eval and train features, every gradient
     norm, BatchNorm running statistics. The PRODUCT does not build this family yet: `get_backbone` must keep failing loudly
     rather than fall back to anything."""
     g = _load(arch)
     spec_fn, fwd = {"mobilenet_v2": (O.mobilenet_v2_spec, O.mobilenet_v2_eca),
-                    "mobilenet_v3_small": (O.mobilenet_v3_small_spec, O.mobilenet_v3_small_eca)}[arch]
+                    "mobilenet_v3_small": (O.mobilenet_v3_small_spec, O.mobilenet_v3_small_eca),
+                    "mobilenet_v3_large": (O.mobilenet_v3_large_spec, O.mobilenet_v3_large_eca)}[arch]
     spec = O.make_spec(spec_fn, 12, 2, 1)
     assert list(spec) == list(g["keys"]) and all(tuple(spec[k]) == tuple(g["keys"][k]) for k in spec)
     sd = O.seeded_state_dict(spec, g["seed"])

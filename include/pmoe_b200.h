@@ -279,6 +279,30 @@ int pmoe_mt_rmsprop(const PmoeMtChunk* chunks_dev, int32_t n_chunks, double lr, 
  * chunk.p (averaged) += (chunk.g (current model parameter) - chunk.p) / (n_averaged + 1). */
 int pmoe_mt_swa_update(const PmoeMtChunk* chunks_dev, int32_t n_chunks, int64_t n_averaged, pmoe_stream_t stream);
 
+/* ---- weight layout (pack.cu) ------------------------------------------------------------------------------------------
+ * The conv / linear kernels read weights in a packed [cout_pad][K] operand layout; the nn.Parameter stays fp32 in the
+ * reference's (out, in, kh, kw) layout (model/blocks/basics.py:51,54). `idx` is a static int32 map of the
+ * packed layout: packed element i = parameter element idx[i], -1 = zero padding. */
+/* out[i] = idx[i] >= 0 ? w[idx[i]] : 0, stored as out_dtype (PMOE_F32 | PMOE_BF16). Runs after every optimizer step. */
+int pmoe_pack_gather(const float* w, const int32_t* idx, void* out, int32_t out_dtype, int64_t n, pmoe_stream_t stream);
+typedef struct PmoePackJob {
+  const float* w;
+  const int32_t* idx;
+  void* out;
+  int64_t n;
+  int32_t dtype;
+  int32_t chunk0; /* first chunk (of pmoe_pack_chunk_elems() elements) of this job; jobs sorted by chunk0 */
+} PmoePackJob;
+/* The same for a device table of jobs in ONE launch (all packed operands of a model). */
+int pmoe_pack_gather_mt(const PmoePackJob* jobs_dev, int32_t n_jobs, int32_t total_chunks, pmoe_stream_t stream);
+int pmoe_pack_chunk_elems(void);
+/* Weight gradient back to the parameter layout (aten::convolution_backward's grad_weight): dst[idx[i]] = alpha * packed[i]
+ * (+ dst[idx[i]] when accumulate) for idx[i] >= 0; dst may be a slot of a flat all-reduce bucket. */
+int pmoe_unpack_scatter(const float* packed, const int32_t* idx, float* dst, int64_t n, float alpha, int32_t accumulate,
+                        pmoe_stream_t stream);
+/* dst[i] (+)= (float) src[i]: fp64 per-channel sums (BatchNorm weight/bias gradients, Linear bias gradients) into fp32 slots. */
+int pmoe_cvt_f64_f32(const double* src, float* dst, int32_t n, int32_t accumulate, pmoe_stream_t stream);
+
 /* ---- input pipeline (preproc.cu) — SURVEY.md §8f rank 1 ------------------------------------------------------- */
 /* The reference dataset's eval-mode transform for every decoded frame, on the device and bit for bit:
  * Crop rows [crop_top, hs - crop_bottom) (augmenter.py:43-49) -> torchvision Resize((out_h, out_w)) on a PIL image = Pillow's

@@ -80,13 +80,20 @@ class GradBucketer:
             self.flat[b] = torch.zeros(self.sizes[b], dtype=torch.float32, device=self.device)
         return self.flat[b]
 
-    def ready(self, p, grad):
-        """Gradient of `p` is final: copy it into its slot; launch every bucket that became complete (in order)."""
+    def slot(self, p):
+        """p's slice of its flat bucket: the tape's kernels write the gradient straight into it (no staging copy)."""
+        b, off, n = self.slots[id(p)]
+        return self._buffer(b)[off:off + n]
+
+    def ready(self, p, grad=None):
+        """Gradient of `p` is final (already in its slot when `grad` is None, copied there otherwise); launch every bucket
+        that became complete (in order)."""
         b, off, n = self.slots[id(p)]
         if id(p) in self.have:
             raise RuntimeError("pmoe_b200.dp: gradient reported twice for one parameter")
         self.have.add(id(p))
-        self._buffer(b)[off:off + n].copy_(grad.reshape(-1))
+        if grad is not None:
+            self._buffer(b)[off:off + n].copy_(grad.reshape(-1))
         self.filled[b] += 1
         self._launch_complete()
 

@@ -86,10 +86,28 @@ def get_backbone(arch: str = "resnet18", n_frames: int = 4, pretrained: bool = F
                  n_channels: int = 3):
     if arch.lower() not in _ARCH:
         raise NotImplementedError("pmoe_b200 get_backbone: resnet18 / resnet34 / resnet50 run on the B200 kernels; got %r" % arch)
+    net = ResNet18ECA(n_frames * n_channels, gamma, b, arch.lower())
     if pretrained:
-        raise RuntimeError("pmoe_b200 get_backbone: pretrained=True needs the ImageNet download (no network here); load a "
-                           "checkpoint with load_state_dict instead and pass pretrained=False")
-    return ResNet18ECA(n_frames * n_channels, gamma, b, arch.lower())
+        _load_imagenet_weights(net, arch.lower())
+    return net
+
+
+def _load_imagenet_weights(net, arch):
+    """`models.resnetXX(pretrained=True)` of the reference (backbone.py:57-61): torchvision's ImageNet weights for every layer
+    the factory keeps — everything except `conv1` (replaced by the EfficientConvBlock) and `fc` (Identity / a fresh Linear).
+    torchvision fetches the file into the torch hub cache on first use; without it (and without a network) this raises."""
+    import torchvision
+    try:
+        ref = getattr(torchvision.models, arch)(weights="IMAGENET1K_V1")   # what the legacy `pretrained=True` selects
+    except Exception as ex:  # no cached weights and no network
+        raise RuntimeError("pmoe_b200 get_backbone(pretrained=True): torchvision could not provide the ImageNet weights of %s (%s: %s); "
+                           "place the torchvision checkpoint in the torch hub cache or pass pretrained=False and load a checkpoint"
+                           % (arch, type(ex).__name__, str(ex).splitlines()[0][:200])) from ex
+    sd = {k: v for k, v in ref.state_dict().items() if not (k.startswith("conv1.") or k.startswith("fc."))}
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    bad = [k for k in missing if not (k.startswith("conv1.") or k.startswith("fc."))]
+    if bad or unexpected:
+        raise RuntimeError("pmoe_b200 get_backbone(pretrained=True): key mismatch with torchvision's %s: %r %r" % (arch, bad, unexpected))
 
 
 def get_unet(model_dir: str, inter_repr: bool = True, n_frames: int = 4, gamma: int = 2, b: int = 1, n_channels: int = 3):

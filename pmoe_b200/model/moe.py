@@ -48,6 +48,17 @@ def _mixture(probs, mean, std):
 
 
 @torch.no_grad()
+def draw(probs, mean, std):
+    """`MixtureSameFamily(...).sample()` exactly as the reference calls it (moe.py:160-177, 352): the same torch.distributions
+    objects on the same device, so the generator is consumed identically (Categorical.sample(), then Normal.sample()). While a CUDA
+    graph is being captured (the B = 1 agent tick) torch.distributions cannot run — its argument checks synchronise — and the
+    graph-safe `sample_mixture` draws from the same distribution instead."""
+    if probs.is_cuda and torch.cuda.is_current_stream_capturing():
+        return sample_mixture(probs, mean, std)
+    return _mixture(probs, mean, std).sample()
+
+
+@torch.no_grad()
 def sample_mixture(probs, mean, std):
     """One draw per row from MixtureSameFamily(Categorical(probs), Independent(Normal(mean, std), 1)) — what the reference's
     `sample()` returns (moe.py:127-133) — written without torch.distributions: component k by inverse CDF of one uniform,
@@ -153,7 +164,7 @@ class MixtureOfExperts(nn.Module):
 
     def sample(self, images, speed, command) -> torch.Tensor:
         probs, mean, std, _, _ = self.components(images, speed, command)
-        return sample_mixture(probs, mean, std)
+        return draw(probs, mean, std)
 
 
 class MixtureOfExpertsShared(nn.Module):
@@ -201,7 +212,7 @@ class MixtureOfExpertsShared(nn.Module):
 
     def sample(self, images, speed, command) -> torch.Tensor:
         probs, mean, std, _, _ = self.components(images, speed, command)
-        return sample_mixture(probs, mean, std)
+        return draw(probs, mean, std)
 
 
 class PUNetExpert(nn.Module):
@@ -275,7 +286,7 @@ class PMoE(nn.Module):
     def forward(self, images, speed, command):
         punet_actions, _ = self.punet(images.clone(), speed.clone(), command.clone())
         probs, mean, std, _, _ = self.moe.components(images, speed, command)
-        moe_actions = sample_mixture(probs, mean, std)  # dists.sample() of the reference: no gradient into the mixture
+        moe_actions = draw(probs, mean, std)  # dists.sample() of the reference: no gradient into the mixture
         # the 2->1 combiners are 8 FLOPs per sample: left to ATen on the GPU
         lat = self.lat_weights(torch.cat([moe_actions[:, 0:1], punet_actions[:, 0:1]], dim=-1))
         lon = self.long_weights(torch.cat([moe_actions[:, 1:], punet_actions[:, 1:]], dim=-1))

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import _lib, profiler
+from . import _lib, packs, profiler
 from ._lib import check, lib, stream_ptr
 
 _CHUNK = 1 << 16  # elements per chunk: 83 M parameters -> ~1.5 k chunks, > 8 per SM
@@ -107,7 +107,7 @@ class FusedAdam(torch.optim.Optimizer):
         if max_grad_norm is not None:
             sq, _, _ = grad_sqnorm([p for g in self.param_groups for p in g["params"]])
         for gi, group in enumerate(self.param_groups):
-            rows, step_no = [], None
+            by_step = {}   # torch.optim.Adam keeps one step counter per parameter: one launch per distinct value
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -120,17 +120,18 @@ class FusedAdam(torch.optim.Optimizer):
                     if group["amsgrad"]:
                         st["max_exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
-                step_no = int(st["step"].item()) if step_no is None else step_no
-                rows.append((p, _flat_f32(p.grad, "gradient"), st["exp_avg"], st["exp_avg_sq"], st.get("max_exp_avg_sq")))
-            if not rows:
-                continue
-            dev = rows[0][0].device
-            tdev, n = self._tables.setdefault((gi, dev), ChunkTable()).get(rows, dev)
+                step_no = int(st["step"].item())   # host tensor: no device sync
+                by_step.setdefault(step_no, []).append((p, _flat_f32(p.grad, "gradient"), st["exp_avg"], st["exp_avg_sq"],
+                                                        st.get("max_exp_avg_sq")))
             b1, b2 = group["betas"]
-            check(profiler.launch("mt_adam", lambda: lib().pmoe_mt_adam(
-                tdev.data_ptr(), n, float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
-                step_no, int(group["amsgrad"]), None if sq is None else sq.data_ptr(), float(max_grad_norm or 0.0), stream_ptr())),
-                "mt_adam")
+            for step_no, rows in by_step.items():
+                dev = rows[0][0].device
+                tdev, n = self._tables.setdefault((gi, dev, step_no if len(by_step) > 1 else -1), ChunkTable()).get(rows, dev)
+                check(profiler.launch("mt_adam", lambda: lib().pmoe_mt_adam(
+                    tdev.data_ptr(), n, float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
+                    step_no, int(group["amsgrad"]), None if sq is None else sq.data_ptr(), float(max_grad_norm or 0.0), stream_ptr())),
+                    "mt_adam")
+                packs.bump([r[0] for r in rows])   # the kernel wrote the parameters through raw pointers
         return loss
 
 
@@ -177,6 +178,7 @@ class FusedRMSprop(torch.optim.Optimizer):
                 tdev.data_ptr(), n, float(group["lr"]), float(group["alpha"]), float(group["eps"]), float(group["weight_decay"]),
                 float(group["momentum"]), None if sq is None else sq.data_ptr(), float(max_grad_norm or 0.0), stream_ptr())),
                 "mt_rmsprop")
+            packs.bump([r[0] for r in rows])   # the kernel wrote the parameters through raw pointers
         return loss
 
 
@@ -205,4 +207,10 @@ class AveragedModel(torch.optim.swa_utils.AveragedModel):
             tdev, n = self._table.get([(a, b.detach(), None, None, None) for a, b in zip(mine, theirs)], dev)
             check(profiler.launch("mt_swa_update", lambda: lib().pmoe_mt_swa_update(tdev.data_ptr(), n, n_avg, stream_ptr())),
                   "mt_swa_update")
+            packs.bump(mine)
+        # use_buffers=False: torch keeps the averaged module's buffers (BatchNorm running statistics,
+        # num_batches_tracked) in sync with the model's on every update (swa_utils.py: `b_swa.copy_(b_model)`)
+        b_mine, b_theirs = list(self.module.buffers()), list(model.buffers())
+        if b_mine:
+            torch._foreach_copy_(b_mine, [b.detach().to(a.device) for a, b in zip(b_mine, b_theirs)])
         self.n_averaged += 1

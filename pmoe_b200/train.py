@@ -12,7 +12,7 @@ import ctypes as C
 
 import torch
 
-from . import _lib, config, dp, nhwc, ops, profiler
+from . import _lib, config, dp, nhwc, ops, packs, profiler
 from ._lib import ACT, check, lib, stream_ptr, view4
 from .nhwc import Act, dtype_code
 from .ops import TAPS3, pad_ch
@@ -32,6 +32,26 @@ class Tape:
         self.reported = set()
         self.bucketer = None        # pmoe_b200.dp.GradBucketer during a data-parallel backward
         self.presums = {}           # id(Act) -> (sum dy*[y>0], sum dy*y) reduced by the kernel that wrote the Act's gradient
+        self.arena = {}             # dtype -> [zeroed chunk, elements handed out]
+        self.nbt = []               # BatchNorm num_batches_tracked buffers to bump at the end of the pass
+        self.touched = []           # buffers written through raw pointers (running statistics): versions bumped at the end
+
+    # one memset per chunk instead of one per accumulator: the statistics / weight-gradient accumulators of a pass are
+    # slices of a few zero-filled chunks (every slice is handed out once, so it is still zero when its kernel runs)
+    _ARENA_ELEMS = {torch.float64: 1 << 16, torch.float32: 1 << 24}
+
+    def zeros(self, shape, dtype, device):
+        n = 1
+        for d in (shape if isinstance(shape, (tuple, list)) else (shape,)):
+            n *= int(d)
+        n_al = (n + 63) // 64 * 64  # 256-byte aligned slices
+        ent = self.arena.get((dtype, device))
+        if ent is None or ent[1] + n_al > ent[0].numel():
+            ent = [torch.zeros(max(self._ARENA_ELEMS.get(dtype, 1 << 16), n_al), dtype=dtype, device=device), 0]
+            self.arena[(dtype, device)] = ent
+        out = ent[0][ent[1]:ent[1] + n].view(shape)
+        ent[1] += n_al
+        return out
 
     def expect(self, *params):
         """Forward-time announcement that a recorded backward closure will add_pgrad() to these parameters."""
@@ -53,22 +73,43 @@ class Tape:
     def grad_of(self, act):
         return self.grads.pop(id(act), None)
 
-    def add_pgrad(self, p, g):
-        if not p.requires_grad:
-            return
+    def pgrad_slot(self, p):
+        """(flat fp32 buffer of p's gradient, whether it already holds a contribution). Under data parallelism the buffer
+        is p's slot of the flat all-reduce bucket, so kernels write gradients where NCCL reads them."""
         k = id(p)
-        self.params[k] = p
-        g = g.reshape(p.shape).to(torch.float32)
         if k in self.pgrads:
-            self.pgrads[k] = self.pgrads[k] + g
+            return self.pgrads[k].view(-1), True
+        if self.bucketer is not None:
+            buf = self.bucketer.slot(p)
         else:
-            self.pgrads[k] = g
+            buf = torch.empty(p.numel(), dtype=torch.float32, device=p.device)
+        self.params[k] = p
+        self.pgrads[k] = buf.view(p.shape)
+        return buf, False
+
+    def pgrad_done(self, p):
+        """One announced contribution to p's gradient has been written."""
+        k = id(p)
         left = self.pending.get(k, 0) - 1
         self.pending[k] = left
         if left == 0 and self.bucketer is not None:
-            # last contribution: hand the gradient to its all-reduce bucket while the tape keeps running
+            # last contribution: the bucket may leave for its all-reduce while the tape keeps running
             self.reported.add(k)
-            self.bucketer.ready(p, self.pgrads[k])
+            self.bucketer.ready(p, None)
+
+    def add_pgrad(self, p, g):
+        if not p.requires_grad:
+            return
+        slot, existed = self.pgrad_slot(p)
+        g = g.reshape(-1)
+        if g.dtype == torch.float64 and g.is_contiguous() and g.is_cuda:
+            check(profiler.launch("cvt_f64_f32", lambda: lib().pmoe_cvt_f64_f32(g.data_ptr(), slot.data_ptr(), g.numel(), int(existed),
+                                                                               stream_ptr())), "cvt_f64_f32")
+        elif existed:
+            slot.add_(g)
+        else:
+            slot.copy_(g)
+        self.pgrad_done(p)
 
     def backward(self):
         for fn in reversed(self.ops):
@@ -77,10 +118,19 @@ class Tape:
         self.alive = []
         self.grads = {}
         if self.bucketer is not None:  # gradients whose announced contributions did not all arrive
-            for k, g in self.pgrads.items():
+            for k in self.pgrads:
                 if k not in self.reported:
                     self.reported.add(k)
-                    self.bucketer.ready(self.params[k], g)
+                    self.bucketer.ready(self.params[k], None)
+
+    def finish_forward(self):
+        """End of the forward pass: the bookkeeping the kernels' raw-pointer writes owe to torch."""
+        if self.nbt:
+            torch._foreach_add_(self.nbt, 1)
+            self.nbt = []
+        if self.touched:
+            packs.bump(self.touched)
+            self.touched = []
 
 
 def _new_act(tape, t, c, rg):
@@ -106,9 +156,9 @@ def _mask_from_x(dz, x, act, fwd):
             and x.is_contiguous() and x.shape == dz.shape)
 
 
-def _bn_bwd_reduce(dz, z, x, act, mean, rstd, cpad, fwd=None):
-    s1 = torch.zeros(cpad, dtype=torch.float64, device=dz.device)
-    s2 = torch.zeros(cpad, dtype=torch.float64, device=dz.device) if x is not None else None
+def _bn_bwd_reduce(tape, dz, z, x, act, mean, rstd, cpad, fwd=None):
+    s1 = tape.zeros(cpad, torch.float64, dz.device)
+    s2 = tape.zeros(cpad, torch.float64, dz.device) if x is not None else None
     mx = _mask_from_x(dz, x, act, fwd)
     vdz = view4(dz)
     vz = view4(z) if (z is not None and not mx) else _lib.null_view()
@@ -123,7 +173,7 @@ def _bn_bwd_reduce(dz, z, x, act, mean, rstd, cpad, fwd=None):
 FUSE_BN_CHAIN_SUMS = True  # tests switch it off to compare against the separate reduce pass
 
 
-def _bn_bwd_apply_sums(dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, dx, fwd):
+def _bn_bwd_apply_sums(tape, dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, dx, fwd):
     """bn_bwd_apply (batch statistics, ReLU) that also reduces sum dx*[x>0] and sum dx*x for the upstream BatchNorm whose ReLU
     output x is. Returns the two fp64 sums, or None (nothing launched) when the tensors do not qualify."""
     cp = dz.shape[3]
@@ -133,8 +183,8 @@ def _bn_bwd_apply_sums(dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, dx, fwd)
     mx = _mask_from_x(dz, x, act, fwd)
     if z is None and not mx:
         return None
-    n1 = torch.zeros(cp, dtype=torch.float64, device=dz.device)
-    n2 = torch.zeros(cp, dtype=torch.float64, device=dz.device)
+    n1 = tape.zeros(cp, torch.float64, dz.device)
+    n2 = tape.zeros(cp, torch.float64, dz.device)
     vdz, vx, vdx = view4(dz), view4(x), view4(dx)
     vz = view4(z) if (z is not None and not mx) else _lib.null_view()
     check(profiler.launch("bn_bwd_apply", lambda: lib().pmoe_bn_bwd_apply_sums(
@@ -261,56 +311,34 @@ def _pack_cols(wf, src, r, s):
 
 
 def _pack_fwd(weight, srcs, segdefs, cop, dtype):
-    def build():
-        wf = weight.detach().float()
+    """-> (packed [cop][K] operand, its packs.Pack): K enumerates (segment, padded channel of the segment's source)."""
+    def build(wf):
         cols = []
         for (i, _, _, r, s) in segdefs:
             cols += _pack_cols(wf, srcs[i], r, s)
         wp = torch.cat(cols, dim=1)
         if cop > wp.shape[0]:
             wp = torch.nn.functional.pad(wp, (0, 0, 0, cop - wp.shape[0]))
-        return wp.to(dtype).contiguous()
+        return wp
     key = "f|%s|%s|%d|%s" % (";".join("%d:%s" % (x.cin0, x.lay) for x in srcs), segdefs, cop, dtype)
-    return _cached_pack(weight, key, build)
+    return packs.packed(_owner(weight), key, weight.shape, build, dtype)
 
 
 def _owner(weight):
     return getattr(weight, "owner", weight)
 
 
-def _cached_pack(weight, key, build):
-    weight = _owner(weight)
-    cache = weight.__dict__.setdefault("_pmoe_pack", {})
-    ver = (weight.data_ptr(), weight._version)
-    hit = cache.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
-    val = build()
-    if len(cache) > 8:
-        cache.clear()
-    cache[key] = (ver, val)
-    return val
-
-
-def _unpack_wgrad(dwp, weight, srcs, segdefs):
-    cout = weight.shape[0]
-    gw = torch.zeros(weight.shape, dtype=torch.float32, device=dwp.device)
-    off = 0
-    for (i, _, _, r, s) in segdefs:
-        src = srcs[i]
-        ci, o = src.cin0, off
-        for (gl, gp) in src.lay:
-            gw[:, ci:ci + gl, r, s] += dwp[:cout, o:o + gl]
-            ci += gl
-            o += gp
-        off += src.cpad
-    return gw
+def _wgrad_to_param(tape, dwp, pack, weight):
+    """Packed fp32 weight gradient -> the parameter's (out, in, kh, kw) gradient slot (one scatter launch)."""
+    p = _owner(weight)
+    slot, existed = tape.pgrad_slot(p)
+    packs.scatter_grad(dwp, pack.idx, slot, existed)
+    tape.pgrad_done(p)
 
 
 def _pack_dgrad(weight, src, segs_i, co_pad, dtype):
     """rows = physical channels of `src`, K = (segment of this source, padded cout)."""
-    def build():
-        wf = weight.detach().float()
+    def build(wf):
         cout = wf.shape[0]
         blocks = []
         for (_, _, _, r, s) in segs_i:
@@ -322,9 +350,9 @@ def _pack_dgrad(weight, src, segs_i, co_pad, dtype):
         rows_pad = ops.cout_padded(wd.shape[0])
         if rows_pad > wd.shape[0]:
             wd = torch.nn.functional.pad(wd, (0, 0, 0, rows_pad - wd.shape[0]))
-        return wd.to(dtype).contiguous()
+        return wd
     key = "d|%d:%s|%s|%d|%s" % (src.cin0, src.lay, segs_i, co_pad, dtype)
-    return _cached_pack(weight, key, build)
+    return packs.packed(_owner(weight), key, weight.shape, build, dtype)[0]
 
 
 FUSE_STRIDE2_DGRAD = True  # tests switch it off to compare against the one-launch-per-parity-view form
@@ -339,8 +367,7 @@ def _stride2_dgrad_fused(tape, x, weight, dy, co_pad, ck_d, n, oh, ow, flops, ta
     cs = x.cpad
     shifts = ((0, 0), (0, 1), (1, 0), (1, 1))
 
-    def build():
-        wf = weight.detach().float()
+    def build(wf):
         cout, cin = wf.shape[0], wf.shape[1]
         rows = []
         for a in range(2):
@@ -352,8 +379,8 @@ def _stride2_dgrad_fused(tape, x, weight, dy, co_pad, ck_d, n, oh, ow, flops, ta
                         blk[:cin, :cout] = wf[:, :, _S2_TAP[(a, dh)], _S2_TAP[(b, dw)]].t()
                     cols.append(blk)
                 rows.append(torch.cat(cols, 1))
-        return torch.cat(rows, 0).to(dy.dtype).contiguous()  # (4*cs, 4*co_pad)
-    wd4 = _cached_pack(weight, "s2d4|%d|%d|%s" % (cs, co_pad, dy.dtype), build)
+        return torch.cat(rows, 0)  # (4*cs, 4*co_pad)
+    wd4 = packs.packed(_owner(weight), "s2d4|%d|%d|%s" % (cs, co_pad, dy.dtype), weight.shape, build, dy.dtype)[0]
     g = torch.empty(x.t.shape, dtype=dy.dtype, device=dy.device)   # every pixel of every parity is written
     tape.grads[id(x)] = g
     tape.presums.pop(id(x), None)
@@ -367,8 +394,10 @@ def _bn_tail_forward(tape, bn, raw, ssum, ssq, count, cout, cstore, act, residua
     mom = 0.1 if bn.momentum is None else bn.momentum
     mean, rstd, scale, shift = nhwc.bn_finalize(ssum, ssq, count, cout, bn.weight.detach(), bn.bias.detach(), bn.eps, mom,
                                                 bn.running_mean if track else None, bn.running_var if track else None)
-    if track and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+    if track:
+        tape.touched += [bn.running_mean, bn.running_var]
+        if bn.num_batches_tracked is not None:
+            tape.nbt.append(bn.num_batches_tracked)
     z_t = out if out is not None else torch.empty(raw.shape, dtype=raw.dtype, device=raw.device)
     fused = False
     if (pool is not None or out_stats is not None) and residual is None:
@@ -385,6 +414,14 @@ def _bn_tail_forward(tape, bn, raw, ssum, ssq, count, cout, cstore, act, residua
                 C.byref(v), dtype_code(z_t), out_stats[0].data_ptr(), out_stats[1].data_ptr(), stream_ptr()), io=(z_t,)), "channel_stats")
     # (scale, shift) let the backward recompute the ReLU mask from `raw` instead of reading z (not with a residual add)
     return z_t, mean, rstd, ((scale, shift) if residual is None else None)
+
+
+def _padded_gamma(bn, cstore):
+    """BatchNorm weight as a [cstore] fp32 vector: the parameter itself when no channel padding is needed."""
+    g = bn.weight.detach()
+    if g.numel() == cstore and g.dtype == torch.float32 and g.is_contiguous():
+        return g
+    return ops.pad_vec(g, cstore, 0.0)
 
 
 def _eval_affine(bn, bias, cout, cop):
@@ -416,7 +453,8 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
     phys = [x.cpad for x in srcs]
     ck = ops.choose_ck(phys)
     segs = [(i, dh, dw, 0, phys[i] // ck) for (i, dh, dw, _, _) in segdefs]
-    wp = _pack_fwd(weight, srcs, segdefs, cop, dt)
+    wp, wpk = _pack_fwd(weight, srcs, segdefs, cop, dt)
+    assert bias is None or bn is None, "conv_op: a conv followed by BatchNorm carries no bias in the reference (basics.py:51-55)"
     n, h, w, _ = srcs[0].t.shape
     if out_hw is not None:
         h, w = out_hw
@@ -431,8 +469,8 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
     src_ts = [x.t for x in srcs]
     if bn_train:
         raw = torch.empty(n, h, w, cstore, dtype=dt, device=dev)
-        ssum = torch.zeros(cop, dtype=torch.float64, device=dev)
-        ssq = torch.zeros(cop, dtype=torch.float64, device=dev)
+        ssum = tape.zeros(cop, torch.float64, dev)
+        ssq = tape.zeros(cop, torch.float64, dev)
         if cop <= 512:
             ops.conv(src_ts, wp, segs, ck, raw, stat_sum=ssum, stat_sqsum=ssq, flops=flops, tag=tag)
         else:  # the epilogue keeps its per-channel partial sums in shared memory for at most 512 channels (resnet50: 1024/2048)
@@ -441,10 +479,10 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
             check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(vr), dtype_code(raw), ssum.data_ptr(),
                                                                                     ssq.data_ptr(), stream_ptr()), io=(raw,)), "channel_stats")
         if want_out_stats:
-            out_stats = (torch.zeros(cstore, dtype=torch.float64, device=dev), torch.zeros(cstore, dtype=torch.float64, device=dev))
+            out_stats = (tape.zeros(cstore, torch.float64, dev), tape.zeros(cstore, torch.float64, dev))
         z_t, mean, rstd, fwd_aff = _bn_tail_forward(tape, bn, raw, ssum, ssq, n * h * w, cout, cstore, act, residual, out,
                                                     pool=pool if want_pool else None, out_stats=out_stats)
-        gamma_p = ops.pad_vec(bn.weight.detach(), cstore, 0.0)
+        gamma_p = _padded_gamma(bn, cstore)
     else:
         scale, shift = _eval_affine(bn, bias, cout, cop)
         z_t = out if out is not None else torch.empty(n, h, w, cstore, dtype=dt, device=dev)
@@ -475,7 +513,7 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
                 sraw = torch.where(sc != 0, (pres[1] - sh * s1) / torch.where(sc != 0, sc, torch.ones_like(sc)), torch.zeros_like(sc))
                 s2 = rstd[:cstore].double() * (sraw - mean[:cstore].double() * s1)
             else:
-                s1, s2 = _bn_bwd_reduce(dz, z_saved, raw, act, mean, rstd, cstore, fwd=fwd_aff)
+                s1, s2 = _bn_bwd_reduce(tape, dz, z_saved, raw, act, mean, rstd, cstore, fwd=fwd_aff)
             tape.add_pgrad(bn.weight, s2[:cout])
             tape.add_pgrad(bn.bias, s1[:cout])
             _bn_bwd_apply(dz, z_saved, raw, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, dy, dres, acc_dres, fwd=fwd_aff)
@@ -483,14 +521,14 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
             if bn is not None and _any_rg([bn.weight, bn.bias]):
                 raise NotImplementedError("pmoe_b200: gradients of BatchNorm affine parameters in eval mode are not supported")
             if bias is not None and bias.requires_grad:
-                s1, _ = _bn_bwd_reduce(dz, z_saved, None, act, None, None, cstore)
+                s1, _ = _bn_bwd_reduce(tape, dz, z_saved, None, act, None, None, cstore)
                 tape.add_pgrad(bias, s1[:cout])
             _bn_bwd_apply(dz, z_saved, None, act, None, None, None if scale is None else scale[:cstore].contiguous(), None, None,
                           0.0, 0, dy, dres, acc_dres)
         if weight.requires_grad:
-            dwp = torch.zeros(cop, wp.shape[1], dtype=torch.float32, device=dev)
+            dwp = tape.zeros((cop, wp.shape[1]), torch.float32, dev)
             ops.conv_wgrad(src_ts, segs, ck, dy, dwp, flops=flops, tag="wgrad " + tag)
-            tape.add_pgrad(_owner(weight), _unpack_wgrad(dwp, weight, srcs, segdefs))
+            _wgrad_to_param(tape, dwp, wpk, weight)
         # data gradients: one launch per physical source whose owner needs them
         ck_d = ops.choose_ck([cstore])
         pre = {id(x.act): (id(x.act) in tape.grads) for x in srcs}
@@ -565,7 +603,12 @@ def conv_transpose_op(tape, up, x, tag=""):
     views = [out[:, a::2, b::2, :] for a in range(2) for b in range(2)]
     if cstore % 64 == 0 and dt == torch.bfloat16 and not config.FORCE_SIMT:
         # one GEMM with N = 4*Cout; column blocks (2a, 2a+1) land in the (n, h, w, 2*C) view of output rows 2h+a
-        wp4 = _cached_pack(weight, "T4|%d|%d|%s" % (cp, cstore, dt), lambda: ops.pack_convT_weight(up, cp, cstore, dt)[0])
+        def build4(wf):
+            w4 = torch.zeros(4 * cstore, cp, dtype=torch.float32, device=wf.device)
+            for q, (a, b) in enumerate(((0, 0), (0, 1), (1, 0), (1, 1))):
+                w4[q * cstore:q * cstore + cout, :cin] = wf[:, :, a, b].t()
+            return w4
+        wp4 = packs.packed(weight, "T4|%d|%d|%s" % (cp, cstore, dt), weight.shape, build4, dt)[0]
         shift4 = ops.pad_vec(bias.detach(), cstore, 0.0).repeat(4)
         rows = out.view(n, h, 2, w, 2 * cstore)
         ops.conv([x.t], wp4, segs, ck, rows[:, :, 0], shift=shift4, out_extra=[rows[:, :, 1]], out_cols=2 * cstore, flops=4 * flops,
@@ -583,13 +626,13 @@ def conv_transpose_op(tape, up, x, tag=""):
             if dy is None:
                 return
             if bias.requires_grad:
-                s1, _ = _bn_bwd_reduce(dy, None, None, None, None, None, cstore)
+                s1, _ = _bn_bwd_reduce(tape, dy, None, None, None, None, None, cstore)
                 tape.add_pgrad(bias, s1[:cout])
             if weight.requires_grad:
                 gw = torch.empty(cin, cout, 2, 2, dtype=torch.float32, device=dev)
                 for a in range(2):
                     for b in range(2):
-                        dwp = torch.zeros(cop, cp, dtype=torch.float32, device=dev)
+                        dwp = tape.zeros((cop, cp), torch.float32, dev)
                         ops.conv_wgrad([x.t], segs, ck, dy[:, a::2, b::2, :], dwp, flops=flops, tag="wgrad convT " + tag)
                         gw[:, :, a, b] = dwp[:cout, :cin].t()
                 tape.add_pgrad(weight, gw)
@@ -628,12 +671,12 @@ def eca_op(tape, eca_mod, x, layout=None, pool_in=None):
             dy = tape.grad_of(ya)
             if dy is None:
                 return
-            dgate = torch.zeros(n, cp, dtype=torch.float64, device=dy.device)  # cancelling sums: kept in fp64
+            dgate = tape.zeros((n, cp), torch.float64, dy.device)  # cancelling sums: kept in fp64
             va, vb = view4(dy), view4(x.t)
             check(profiler.launch("prod_channel_sums", lambda: lib().pmoe_prod_channel_sums(
                 C.byref(va), C.byref(vb), dtype_code(dy), dgate.data_ptr(), dgate.stride(0), stream_ptr()), io=(dy, x.t)), "prod_channel_sums")
             dmean = torch.empty(n, cp, dtype=torch.float32, device=dy.device)
-            dw = torch.zeros(w.numel(), dtype=torch.float64, device=dy.device)
+            dw = tape.zeros(w.numel(), torch.float64, dy.device)
             wf = w.detach().reshape(-1)
             check(profiler.launch("eca_gate_bwd", lambda: lib().pmoe_eca_gate_bwd(
                 dgate.data_ptr(), dgate.stride(0), gate.data_ptr(), gate.stride(0), sums.data_ptr(), sums.stride(0), n,
@@ -646,8 +689,8 @@ def eca_op(tape, eca_mod, x, layout=None, pool_in=None):
                 if (FUSE_BN_CHAIN_SUMS and getattr(x, "bn_relu", False) and not existed and dy.dtype == torch.bfloat16
                         and dy.is_contiguous() and x.t.is_contiguous() and 256 % (cp // 8) == 0):
                     # x = relu(BN(raw)) of the conv upstream and this is its whole gradient: that layer's backward sums ride along
-                    n1 = torch.zeros(cp, dtype=torch.float64, device=dy.device)
-                    n2 = torch.zeros(cp, dtype=torch.float64, device=dy.device)
+                    n1 = tape.zeros(cp, torch.float64, dy.device)
+                    n2 = tape.zeros(cp, torch.float64, dy.device)
                     vx = view4(x.t)
                     check(profiler.launch("eca_bwd_apply", lambda: lib().pmoe_eca_bwd_apply_sums(
                         C.byref(vd), dtype_code(dy), gate.data_ptr(), gate.stride(0), dmean.data_ptr(), dmean.stride(0), C.byref(vg),
@@ -782,13 +825,13 @@ def bn_act_op(tape, bn, x, act="relu", tag=""):
         if x.stats is not None and x.stats[0].numel() == cp:
             ssum, ssq = x.stats    # reduced by the kernel that wrote x (conv_op(want_out_stats=True))
         else:
-            ssum = torch.zeros(cp, dtype=torch.float64, device=dev)
-            ssq = torch.zeros(cp, dtype=torch.float64, device=dev)
+            ssum = tape.zeros(cp, torch.float64, dev)
+            ssq = tape.zeros(cp, torch.float64, dev)
             v = view4(x.t)
             check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(v), dtype_code(x.t), ssum.data_ptr(),
                                                                                     ssq.data_ptr(), stream_ptr()), io=(x.t,)), "channel_stats")
         z_t, mean, rstd, fwd_aff = _bn_tail_forward(tape, bn, x.t, ssum, ssq, n * h * w, c, cp, act, None, None)
-        gamma_p = ops.pad_vec(bn.weight.detach(), cp, 0.0)
+        gamma_p = _padded_gamma(bn, cp)
     else:
         scale, shift = _eval_affine(bn, None, c, cp)
         z_t = nhwc.affine_act(x.t, scale, shift, act)
@@ -802,14 +845,14 @@ def bn_act_op(tape, bn, x, act="relu", tag=""):
             g, existed = _grad_buffer(tape, x)
             tmp = g if not existed else torch.empty_like(g)
             if bn_train:
-                s1, s2 = _bn_bwd_reduce(dz, zs, x.t, act, mean, rstd, cp, fwd=fwd_aff)
+                s1, s2 = _bn_bwd_reduce(tape, dz, zs, x.t, act, mean, rstd, cp, fwd=fwd_aff)
                 tape.add_pgrad(bn.weight, s2[:c])
                 tape.add_pgrad(bn.bias, s1[:c])
                 nxt = None
                 if getattr(x, "bn_relu", False) and not existed:
                     # x = relu(BN(raw)) of the conv just upstream and this is its only gradient so far: reduce that layer's
                     # backward sums while dx is in registers (invalidated if anything is accumulated into dx later)
-                    nxt = _bn_bwd_apply_sums(dz, zs, x.t, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), tmp, fwd_aff)
+                    nxt = _bn_bwd_apply_sums(tape, dz, zs, x.t, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), tmp, fwd_aff)
                 if nxt is not None:
                     tape.presums[id(x)] = nxt
                 else:
@@ -1086,17 +1129,10 @@ def mlp_last_out(tape, seq, srcs, out, tag):
 # weights and bias for the tiles of image e (PmoeConvTc.wpack_img_stride / shift_img_stride). Forward and data gradient
 # are grouped; the weight gradient runs per expert on the views of the stacked tensors.
 def _grouped_pack(lins, srcs, cop, dt, kind):
-    """Stack the per-expert packed weights; cached on the first expert's weight, keyed on every expert's version."""
+    """Stacked (K, rows, cols) packed weights of the K experts' Linears + their packs.Pack list (shared index map)."""
     w0 = lins[0].weight
-    vers = tuple((l.weight.data_ptr(), l.weight._version) for l in lins)
-    cache = w0.__dict__.setdefault("_pmoe_gpack", {})
-    key = (kind, tuple((x.cin0, tuple(x.lay)) for x in srcs), cop, str(dt))
-    hit = cache.get(key)
-    if hit is not None and hit[0] == vers:
-        return hit[1]
-    packs = []
-    for l in lins:
-        w4 = l.weight.detach().float().view(l.weight.shape[0], l.weight.shape[1], 1, 1)
+
+    def build(w4):
         if kind == "f":
             cols = []
             for x in srcs:
@@ -1104,17 +1140,14 @@ def _grouped_pack(lins, srcs, cop, dt, kind):
             wp = torch.cat(cols, dim=1)
             if cop > wp.shape[0]:
                 wp = torch.nn.functional.pad(wp, (0, 0, 0, cop - wp.shape[0]))
-        else:  # data gradient of source `srcs[0]`: rows = its physical channels, K = padded cout
-            blk = torch.cat(_pack_cols(w4, srcs[0], 0, 0), dim=1).t()
-            blk = torch.nn.functional.pad(blk, (0, cop - blk.shape[1]))
-            rows = ops.cout_padded(blk.shape[0])
-            wp = torch.nn.functional.pad(blk, (0, 0, 0, rows - blk.shape[0]))
-        packs.append(wp.to(dt))
-    val = torch.stack(packs).contiguous()
-    if len(cache) > 8:
-        cache.clear()
-    cache[key] = (vers, val)
-    return val
+            return wp
+        # data gradient of source `srcs[0]`: rows = its physical channels, K = padded cout
+        blk = torch.cat(_pack_cols(w4, srcs[0], 0, 0), dim=1).t()
+        blk = torch.nn.functional.pad(blk, (0, cop - blk.shape[1]))
+        rows = ops.cout_padded(blk.shape[0])
+        return torch.nn.functional.pad(blk, (0, 0, 0, rows - blk.shape[0]))
+    key = (kind, tuple((x.cin0, tuple(x.lay)) for x in srcs), cop, str(dt))
+    return packs.packed_group([l.weight for l in lins], key, (w0.shape[0], w0.shape[1], 1, 1), build, dt)
 
 
 def grouped_linear_op(tape, srcs, lins, act=None, tag=""):
@@ -1128,7 +1161,7 @@ def grouped_linear_op(tape, srcs, lins, act=None, tag=""):
     phys = [x.cpad for x in srcs]
     ck = ops.choose_ck(phys)
     segs = [(i, 0, 0, 0, phys[i] // ck) for i in range(len(srcs))]
-    wp = _grouped_pack(lins, srcs, cop, dt, "f")
+    wp, wpks = _grouped_pack(lins, srcs, cop, dt, "f")
     B = srcs[0].t.shape[2]
     has_bias = lins[0].bias is not None
     shift = None
@@ -1153,26 +1186,17 @@ def grouped_linear_op(tape, srcs, lins, act=None, tag=""):
         _bn_bwd_apply(dz, z_saved, None, act, None, None, None, None, None, 0.0, 0, dy, None, False)
         for e, lin in enumerate(lins):
             if lin.bias is not None and lin.bias.requires_grad:
-                s1, _ = _bn_bwd_reduce(dy[e:e + 1], None, None, None, None, None, cstore)
+                s1, _ = _bn_bwd_reduce(tape, dy[e:e + 1], None, None, None, None, None, cstore)
                 tape.add_pgrad(lin.bias, s1[:cout])
             if lin.weight.requires_grad:
-                dwp = torch.zeros(cop, wp.shape[2], dtype=torch.float32, device=dev)
+                dwp = tape.zeros((cop, wp.shape[2]), torch.float32, dev)
                 ops.conv_wgrad([x.t[e:e + 1] for x in srcs], segs, ck, dy[e:e + 1], dwp, flops=flops / K, tag="wgrad grouped " + tag)
-                gw = torch.empty(lin.weight.shape, dtype=torch.float32, device=dev)
-                off = 0
-                for x in srcs:
-                    ci, o = x.cin0, off
-                    for (gl, gp) in x.lay:
-                        gw[:, ci:ci + gl] = dwp[:cout, o:o + gl]
-                        ci += gl
-                        o += gp
-                    off += x.cpad
-                tape.add_pgrad(lin.weight, gw)
+                _wgrad_to_param(tape, dwp, wpks[e], lin.weight)
         ck_d = ops.choose_ck([cstore])
         for x in srcs:
             if not _rg(x.act):
                 continue
-            wd = _grouped_pack(lins, [x], cstore, dt, "d")
+            wd = _grouped_pack(lins, [x], cstore, dt, "d")[0]
             g, existed = _grad_buffer(tape, x.act)
             ops.conv([dy], wd, [(0, 0, 0, 0, cstore // ck_d)], ck_d, g, residual=g if existed else None,
                      flops=2.0 * K * B * cout * x.nlog, tag="dgrad grouped " + tag)
@@ -1316,6 +1340,7 @@ class TapeFunction(torch.autograd.Function):
     def forward(ctx, runner, *params):
         tape = Tape(config.act_dtype(), save=any(p.requires_grad for p in params))
         outs, seed = runner(tape)
+        tape.finish_forward()
         ctx.tape, ctx.seed, ctx.plist = tape, seed, params
         ctx.dp = dp.current()  # a pmoe_b200.dp.DataParallel wrapper when the model runs under one
         ctx.mark_non_differentiable(*[o for o in outs if not o.is_floating_point()])
@@ -1352,11 +1377,16 @@ class TapeFunction(torch.autograd.Function):
 def run(module, runner):
     """Execute `runner(tape)` for `module`: through autograd when gradients are wanted, directly otherwise."""
     params = [p for p in module.parameters()]
-    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
-        outs = TapeFunction.apply(runner, *params)
-    else:
-        tape = Tape(config.act_dtype(), save=False)
-        outs, _ = runner(tape)
+    packs.begin_pass(module)
+    try:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            outs = TapeFunction.apply(runner, *params)
+        else:
+            tape = Tape(config.act_dtype(), save=False)
+            outs, _ = runner(tape)
+            tape.finish_forward()
+    finally:
+        packs.end_pass()
     return outs
 
 

@@ -24,7 +24,9 @@ def load_checkpoint(save: str, device: str):
     """torch.load(save, map_location=device) (io.py:36-47); a missing file is an error, as in the reference."""
     if not os.path.exists(save):
         raise FileNotFoundError("File doesn't exist {}".format(save))
-    return torch.load(save, map_location=device)
+    # the trainers' checkpoints carry numpy scalars next to the state dicts (`best`, `e_loss` = np.mean(...): train_2.py:346-370),
+    # which torch >= 2.6 refuses under its weights_only default; these files are the user's own training output
+    return torch.load(save, map_location=device, weights_only=False)
 
 
 def worker_init_fn(worker_id):

@@ -26,6 +26,9 @@ def freeze(model: nn.Module, exclude: List = [], verbose: bool = False) -> nn.Mo
 
 def check_grad_norm(net: nn.Module) -> float:
     """Global L2 norm of all gradients (utils/nn.py:10-19) with ONE host sync instead of one per parameter."""
+    from ..optim import check_grad_norm as _fused
+    if any(p.grad is not None and p.grad.is_cuda for p in net.parameters()):
+        return _fused(net)   # one multi-tensor launch (pmoe_mt_sqnorm)
     grads = [p.grad for p in net.parameters() if p.grad is not None]
     if not grads:
         return 0.0

@@ -168,11 +168,20 @@ int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4*
                        const float* fwd_shift, pmoe_stream_t stream);
 /* dx = gamma*rstd*(dy - sum_dy/N - xhat*sum_dy_xhat/N) (batch_stats) or dy*gamma (eval BN / plain);
  * dres (optional) receives the masked dy for a residual branch. fwd_scale/fwd_shift: as in pmoe_bn_bwd_reduce. */
+/* param_grads (optional, batch-statistics mode): the two reductions ARE the BatchNorm affine gradients (d bias = sum_dy,
+ * d weight = sum_dy_xhat); the kernel also stores them as fp32 into the parameters' gradient slots (first n channels;
+ * accumulate: add to what is there), which saves a conversion launch per parameter. */
+typedef struct PmoeBnParamGrads {
+  float* dgamma;
+  float* dbeta;
+  int32_t n;
+  int32_t accumulate;
+} PmoeBnParamGrads;
 int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
                       const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
                       const double* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
                       const PmoeView4* dres, int32_t accumulate_dres, const float* fwd_scale, const float* fwd_shift,
-                      pmoe_stream_t stream);
+                      const PmoeBnParamGrads* param_grads, pmoe_stream_t stream);
 /* The same batch-statistics apply when x is itself the ReLU output of an UPSTREAM BatchNorm and dx is that layer's complete
  * gradient (torchvision's bn1 directly after the stem block, backbone.py:57-61): also accumulates next_sum_dx[c] += sum
  * dx*[x>0] and next_sum_dx_x[c] += sum dx*x (zero-initialised fp64), from which the upstream layer's two backward
@@ -182,7 +191,8 @@ int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* 
 int pmoe_bn_bwd_apply_sums(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
                            const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
                            const double* sum_dy_xhat, float inv_n, const PmoeView4* dx, const float* fwd_scale,
-                           const float* fwd_shift, double* next_sum_dx, double* next_sum_dx_x, pmoe_stream_t stream);
+                           const float* fwd_shift, double* next_sum_dx, double* next_sum_dx_x, const PmoeBnParamGrads* param_grads,
+                           pmoe_stream_t stream);
 int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* dx, int32_t dtype, int32_t k, int32_t stride,
                      int32_t pad, int32_t accumulate, pmoe_stream_t stream);
 int pmoe_maxpool_bwd_idx(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* dx, int32_t dtype, int32_t k,

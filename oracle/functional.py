@@ -19,6 +19,42 @@ import torch.nn.functional as F
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 
+# ------------------------------------------------------------------ optional storage-precision emulation
+# The product stores every activation AND every activation gradient in bf16 (fp32 accumulation inside the kernels). A ReLU
+# network's gradient is a discontinuous function of its pre-activations, so comparing a bf16-storage step with the fp32
+# restatement measures how many ReLU masks the storage rounding flips, not whether the kernels are right. With
+# `storage("bf16")` active the SAME restatement rounds each stored tensor (forward value and, on the way back, its gradient)
+# to bf16 at the points where the product stores one: conv / linear outputs, BatchNorm+activation(+residual) outputs, ECA
+# scaled outputs, pooled features. Arithmetic stays fp32. Default (None): the plain fp32 restatement the goldens pin.
+import contextlib
+
+STORE = None
+
+
+class _RoundBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+@contextlib.contextmanager
+def storage(kind):
+    global STORE
+    old = STORE
+    STORE = {"bf16": _RoundBf16.apply, None: None, "fp32": None}[kind]
+    try:
+        yield
+    finally:
+        STORE = old
+
+
+def _st(x):
+    return x if STORE is None else STORE(x)
+
 
 # ------------------------------------------------------------------ blocks (model/blocks/basics.py)
 def batchnorm(x, sd, p, train, eps=BN_EPS, momentum=BN_MOMENTUM):
@@ -33,8 +69,8 @@ def batchnorm(x, sd, p, train, eps=BN_EPS, momentum=BN_MOMENTUM):
 def conv3_block(x, sd, p, train, stride=1):
     """basics.py:48-59 — (conv3x3 no-bias, BN, ReLU) twice."""
     for a, b in (("0", "1"), ("3", "4")):
-        x = F.conv2d(x, sd[p + a + ".weight"], None, stride, 1)
-        x = torch.relu(batchnorm(x, sd, p + b + ".", train))
+        x = _st(F.conv2d(x, sd[p + a + ".weight"], None, stride, 1))
+        x = _st(torch.relu(batchnorm(x, sd, p + b + ".", train)))
     return x
 
 
@@ -49,17 +85,17 @@ def eca(x, w):
     k = w.shape[-1]
     y = x.mean(dim=(2, 3))
     y = F.conv1d(y.unsqueeze(1), w, None, 1, k // 2).squeeze(1)
-    return x * torch.sigmoid(y)[:, :, None, None]
+    return _st(x * torch.sigmoid(y)[:, :, None, None])
 
 
 def eca_conv_block(x, sd, p, train, stride=1):
     """basics.py:80-135 — EfficientConvBlock."""
     x = eca(x, sd[p + "layer1.eca1.conv.weight"])
-    x = F.conv2d(x, sd[p + "layer1.conv1.0.weight"], None, stride, 1)
-    x = torch.relu(batchnorm(x, sd, p + "layer1.conv1.1.", train))
+    x = _st(F.conv2d(x, sd[p + "layer1.conv1.0.weight"], None, stride, 1))
+    x = _st(torch.relu(batchnorm(x, sd, p + "layer1.conv1.1.", train)))
     x = eca(x, sd[p + "layer2.eca2.conv.weight"])
-    x = F.conv2d(x, sd[p + "layer2.conv2.0.weight"], None, stride, 1)
-    return torch.relu(batchnorm(x, sd, p + "layer2.conv2.1.", train))
+    x = _st(F.conv2d(x, sd[p + "layer2.conv2.0.weight"], None, stride, 1))
+    return _st(torch.relu(batchnorm(x, sd, p + "layer2.conv2.1.", train)))
 
 
 def mlp_layout(dims, act, l_act=False, bn=True, dropout=0.0):
@@ -88,13 +124,17 @@ _ACTS = {"relu": torch.relu, "tanh": torch.tanh, "sigmoid": torch.sigmoid, "elu"
 
 def mlp(x, sd, p, cfg, train):
     """basics.py:11-45 forward of the Sequential built by make_mlp(**cfg)."""
-    for op in mlp_layout(cfg["dims"], cfg["act"], cfg.get("l_act", False), cfg.get("bn", True), cfg.get("dropout", 0.0)):
+    ops = mlp_layout(cfg["dims"], cfg["act"], cfg.get("l_act", False), cfg.get("bn", True), cfg.get("dropout", 0.0))
+    for i, op in enumerate(ops):
+        fused_act = i + 1 < len(ops) and ops[i + 1][0] == "act"  # the product applies bias + activation in the GEMM epilogue, then stores
         if op[0] == "linear":
             x = F.linear(x, sd[p + "%d.weight" % op[1]], sd.get(p + "%d.bias" % op[1]))
+            if not fused_act:
+                x = _st(x)
         elif op[0] == "bn":
             x = batchnorm(x, sd, p + "%d." % op[1], train)
         elif op[0] == "act":
-            x = _ACTS[op[2]](x)
+            x = _st(_ACTS[op[2]](x))
         elif op[0] == "dropout":
             x = F.dropout(x, op[2], train)
     return x
@@ -109,14 +149,14 @@ def unet(x, sd, p, train, inter_repr=False):
     x5 = conv3_block(F.max_pool2d(x4, 2, 2), sd, p + "dwn_5.", train)
     y = x5
     for i, skip in ((1, x4), (2, x3), (3, x2), (4, x1)):
-        up = F.conv_transpose2d(y, sd[p + "up_%d.weight" % i], sd[p + "up_%d.bias" % i], stride=2)
+        up = _st(F.conv_transpose2d(y, sd[p + "up_%d.weight" % i], sd[p + "up_%d.bias" % i], stride=2))
         # unet.py:72 output_size=skip.size(): pads bottom/right when the skip is odd-sized
         dh, dw = skip.shape[-2] - up.shape[-2], skip.shape[-1] - up.shape[-1]
         if dh or dw:
             up = F.conv_transpose2d(y, sd[p + "up_%d.weight" % i], sd[p + "up_%d.bias" % i], stride=2,
                                     output_padding=(dh, dw))
         y = conv3_block(torch.cat([skip, up], 1), sd, p + "up_forw_%d." % i, train)  # skip first (unet.py:73)
-    out = F.conv2d(y, sd[p + "out.weight"], sd[p + "out.bias"])
+    out = _st(F.conv2d(y, sd[p + "out.weight"], sd[p + "out.bias"]))
     if inter_repr:
         return x5.mean(dim=(2, 3)), out
     return out
@@ -153,7 +193,7 @@ def resnet_eca(x, sd, p, train, arch="resnet18"):
     Linear(fc.in_features, 512) (backbone.py:48-72: resnet18/34 BasicBlock, resnet50 Bottleneck with the stride on the 3x3)."""
     kind, blocks = RESNET_BLOCKS[arch]
     x = eca_conv_block(x, sd, p + "conv1.", train)
-    x = torch.relu(batchnorm(x, sd, p + "bn1.", train))
+    x = _st(torch.relu(batchnorm(x, sd, p + "bn1.", train)))
     x = F.max_pool2d(x, 3, 2, 1)
     for li, ((_, stride), nb) in enumerate(zip(RESNET18_LAYERS, blocks), start=1):
         for bi in range(nb):
@@ -161,21 +201,21 @@ def resnet_eca(x, sd, p, train, arch="resnet18"):
             s = stride if bi == 0 else 1
             idt = x
             if kind == "basic":
-                y = F.conv2d(x, sd[q + "conv1.weight"], None, s, 1)
-                y = torch.relu(batchnorm(y, sd, q + "bn1.", train))
-                y = F.conv2d(y, sd[q + "conv2.weight"], None, 1, 1)
-                y = batchnorm(y, sd, q + "bn2.", train)
+                y = _st(F.conv2d(x, sd[q + "conv1.weight"], None, s, 1))
+                y = _st(torch.relu(batchnorm(y, sd, q + "bn1.", train)))
+                y = _st(F.conv2d(y, sd[q + "conv2.weight"], None, 1, 1))
+                y = batchnorm(y, sd, q + "bn2.", train)   # the residual add + ReLU ride the same pass: one stored tensor
             else:
-                y = torch.relu(batchnorm(F.conv2d(x, sd[q + "conv1.weight"]), sd, q + "bn1.", train))
-                y = torch.relu(batchnorm(F.conv2d(y, sd[q + "conv2.weight"], None, s, 1), sd, q + "bn2.", train))
-                y = batchnorm(F.conv2d(y, sd[q + "conv3.weight"]), sd, q + "bn3.", train)
+                y = _st(torch.relu(batchnorm(_st(F.conv2d(x, sd[q + "conv1.weight"])), sd, q + "bn1.", train)))
+                y = _st(torch.relu(batchnorm(_st(F.conv2d(y, sd[q + "conv2.weight"], None, s, 1)), sd, q + "bn2.", train)))
+                y = batchnorm(_st(F.conv2d(y, sd[q + "conv3.weight"])), sd, q + "bn3.", train)
             if q + "downsample.0.weight" in sd:
-                idt = F.conv2d(x, sd[q + "downsample.0.weight"], None, s, 0)
-                idt = batchnorm(idt, sd, q + "downsample.1.", train)
-            x = torch.relu(y + idt)
-    x = x.mean(dim=(2, 3))
+                idt = _st(F.conv2d(x, sd[q + "downsample.0.weight"], None, s, 0))
+                idt = _st(batchnorm(idt, sd, q + "downsample.1.", train))
+            x = _st(torch.relu(y + idt))
+    x = _st(x.mean(dim=(2, 3)))
     if p + "fc.weight" in sd:
-        x = F.linear(x, sd[p + "fc.weight"], sd[p + "fc.bias"])
+        x = _st(F.linear(x, sd[p + "fc.weight"], sd[p + "fc.bias"]))
     return x
 
 
@@ -361,13 +401,13 @@ def expert(images, speed, command, sd, p, cfg, train, alt=False):
     feats = torch.cat([img, s, c], dim=-1)
     pred_speed = mlp(feats, sd, p + "speed_pred.", cfg["speed_prediction"], train)
     af = mlp(feats, sd, p + "action_features.", cfg["action_head"], train)
-    mean, std = F.linear(af, sd[p + "action_pred.weight"], sd[p + "action_pred.bias"]).split(2, dim=-1)
+    mean, std = _st(F.linear(af, sd[p + "action_pred.weight"], sd[p + "action_pred.bias"])).split(2, dim=-1)
     std = F.elu(std) + 1
     if alt:
         a = F.linear(feats, sd[p + "alpha.0.weight"], sd[p + "alpha.0.bias"])
-        alpha = F.linear(torch.relu(a), sd[p + "alpha.2.weight"], sd[p + "alpha.2.bias"])
+        alpha = _st(F.linear(_st(torch.relu(a)), sd[p + "alpha.2.weight"], sd[p + "alpha.2.bias"]))
     else:
-        alpha = torch.relu(F.linear(af, sd[p + "alpha.weight"], sd[p + "alpha.bias"]))
+        alpha = torch.relu(_st(F.linear(af, sd[p + "alpha.weight"], sd[p + "alpha.bias"])))  # the gating kernel applies the ReLU
     return alpha, mean, std, pred_speed
 
 

@@ -147,6 +147,24 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(BV4 dz, BV4 
 // ---------------------------------------------------------------- pass 2: dx (and the masked dy for a residual branch)
 // batch-stat BN : dx = gamma*rstd * (dy - sum_dy/N - xhat*sum_dy_xhat/N)
 // eval BN / bias: dx = dy * scale (scale may be NULL = 1)
+// Optional side output of the apply pass: the BatchNorm affine gradients are the two reductions themselves
+// (d beta = sum dy*m, d gamma = sum dy*m*xhat), so block 0 writes them as fp32 into the parameters' gradient slots
+// (a separate fp64 -> fp32 conversion launch per parameter otherwise: 2 x 20 BatchNorms x K experts per step).
+struct ParamGrads {
+  float* dgamma;
+  float* dbeta;
+  int n;
+  int accumulate;
+};
+__device__ __forceinline__ void write_param_grads(const ParamGrads& pg, const double* __restrict__ sum_dy,
+                                                  const double* __restrict__ sum_dy_xhat) {
+  if (blockIdx.x != 0 || pg.n <= 0) return;
+  for (int c = threadIdx.x; c < pg.n; c += blockDim.x) {
+    if (pg.dbeta) pg.dbeta[c] = (pg.accumulate ? pg.dbeta[c] : 0.f) + (float)sum_dy[c];
+    if (pg.dgamma && sum_dy_xhat) pg.dgamma[c] = (pg.accumulate ? pg.dgamma[c] : 0.f) + (float)sum_dy_xhat[c];
+  }
+}
+
 // FLAT: every view is a dense (n,h,w,c) tensor of the same shape -> item i lives at element offset 8*i in all of
 // them (no index arithmetic). The grid stride is a multiple of the channel-group count, so a thread keeps ONE channel
 // group for its whole loop and the per-channel constants are loaded once.
@@ -154,7 +172,8 @@ template <typename T, bool FLAT>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* __restrict__ mean,
                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
                                     const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat, float inv_n,
-                                    int batch_stats, BV4 dx, BV4 dres, int accumulate_dres) {
+                                    int batch_stats, BV4 dx, BV4 dres, int accumulate_dres, ParamGrads pg) {
+  if (batch_stats) write_param_grads(pg, sum_dy, sum_dy_xhat);
   const int cg = dz.c / 8;
   const long long total = (long long)dz.n * dz.h * dz.w * cg;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -783,7 +802,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_fast_kernel(const uint4* __r
                                                                 const float* __restrict__ gamma, const double* __restrict__ sum_dy,
                                                                 const double* __restrict__ sum_dy_xhat, float inv_n,
                                                                 const float* __restrict__ fwd_scale, const float* __restrict__ fwd_shift,
-                                                                double* __restrict__ next_s1, double* __restrict__ next_s2) {
+                                                                double* __restrict__ next_s1, double* __restrict__ next_s2, ParamGrads pg) {
+  if (BATCH) write_param_grads(pg, sum_dy, sum_dy_xhat);
   __shared__ float sm_next[NEXT ? kRedThreads * 8 : 8];
   float na[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long stride = (long long)gridDim.x * blockDim.x;  // a multiple of cg: one channel group per thread
@@ -1002,9 +1022,20 @@ static int bn_bwd_apply_impl(const PmoeView4* dz, const PmoeView4* z, const Pmoe
                              const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
                              const double* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
                              const PmoeView4* dres, int32_t accumulate_dres, const float* fwd_scale, const float* fwd_shift,
-                             double* next_s1, double* next_s2, pmoe_stream_t stream_) {
+                             double* next_s1, double* next_s2, const PmoeBnParamGrads* pgrads, pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc;
+  ParamGrads pg = {nullptr, nullptr, 0, 0};
+  if (pgrads && batch_stats) {
+    if (pgrads->n < 0 || pgrads->n > dz->c) {
+      set_error("bn_bwd_apply: parameter-gradient channel count out of range");
+      return PMOE_ERR_ARG;
+    }
+    pg.dgamma = pgrads->dgamma;
+    pg.dbeta = pgrads->dbeta;
+    pg.n = pgrads->n;
+    pg.accumulate = pgrads->accumulate;
+  }
   const bool mask_x = act == PMOE_ACT_RELU && (!z || !z->ptr) && x && x->ptr && fwd_scale && fwd_shift;
   if ((rc = chk(dz, dtype, "bn_bwd_apply dz"))) return rc;
   if ((rc = chk(z, dtype, "bn_bwd_apply z", act == PMOE_ACT_NONE || mask_x))) return rc;
@@ -1027,16 +1058,16 @@ static int bn_bwd_apply_impl(const PmoeView4* dz, const PmoeView4* z, const Pmoe
     const int cg = dz->c / 8;
     int g4 = (grid + 3) / 4;  // four items per thread and iteration
     if (256 % cg != 0) g4 = (g4 + cg - 1) / cg * cg;
-#define PMOE_APPLY_FAST(A, B) bn_bwd_apply_fast_kernel<A, B, false><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, fwd_scale, fwd_shift, nullptr, nullptr)
+#define PMOE_APPLY_FAST(A, B) bn_bwd_apply_fast_kernel<A, B, false><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, fwd_scale, fwd_shift, nullptr, nullptr, pg)
     if (next_s1) {
       if (!next_s2 || !batch_stats || !pdx || 256 % cg != 0 || !(mask_x || act == PMOE_ACT_RELU)) {
         set_error("bn_bwd_apply_sums: needs batch statistics, a dx output, ReLU and a channel-group count that divides 256");
         return PMOE_ERR_UNSUPPORTED;
       }
       if (mask_x)
-        bn_bwd_apply_fast_kernel<2, true, true><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, fwd_scale, fwd_shift, next_s1, next_s2);
+        bn_bwd_apply_fast_kernel<2, true, true><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, fwd_scale, fwd_shift, next_s1, next_s2, pg);
       else
-        bn_bwd_apply_fast_kernel<1, true, true><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, fwd_scale, fwd_shift, next_s1, next_s2);
+        bn_bwd_apply_fast_kernel<1, true, true><<<g4, 256, 0, stream>>>(pdz, pz, px, pdx, pdr, accumulate_dres, items, cg, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, fwd_scale, fwd_shift, next_s1, next_s2, pg);
     } else if (mask_x && batch_stats) PMOE_APPLY_FAST(2, true);
     else if (mask_x) PMOE_APPLY_FAST(2, false);
     else if (act == PMOE_ACT_ELU && batch_stats) PMOE_APPLY_FAST(3, true);
@@ -1053,9 +1084,9 @@ static int bn_bwd_apply_impl(const PmoeView4* dz, const PmoeView4* z, const Pmoe
     return PMOE_ERR_UNSUPPORTED;
   }
   if (flat_all) {
-    BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T, true><<<grid, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres)));
+    BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T, true><<<grid, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres, pg)));
   } else {
-    BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T, false><<<grid, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres)));
+    BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T, false><<<grid, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres, pg)));
   }
   return check_launch("bn_bwd_apply");
 }
@@ -1064,21 +1095,22 @@ int pmoe_bn_bwd_apply(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* 
                       const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
                       const double* sum_dy_xhat, float inv_n, int32_t batch_stats, const PmoeView4* dx,
                       const PmoeView4* dres, int32_t accumulate_dres, const float* fwd_scale, const float* fwd_shift,
-                      pmoe_stream_t stream_) {
+                      const PmoeBnParamGrads* param_grads, pmoe_stream_t stream_) {
   return bn_bwd_apply_impl(dz, z, x, dtype, act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, dx, dres, accumulate_dres,
-                           fwd_scale, fwd_shift, nullptr, nullptr, stream_);
+                           fwd_scale, fwd_shift, nullptr, nullptr, param_grads, stream_);
 }
 
 int pmoe_bn_bwd_apply_sums(const PmoeView4* dz, const PmoeView4* z, const PmoeView4* x, int32_t dtype, int32_t act,
                            const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
                            const double* sum_dy_xhat, float inv_n, const PmoeView4* dx, const float* fwd_scale,
-                           const float* fwd_shift, double* next_sum_dx, double* next_sum_dx_x, pmoe_stream_t stream_) {
+                           const float* fwd_shift, double* next_sum_dx, double* next_sum_dx_x, const PmoeBnParamGrads* param_grads,
+                           pmoe_stream_t stream_) {
   if (!next_sum_dx || !next_sum_dx_x) {
     set_error("bn_bwd_apply_sums: both output sums are required");
     return PMOE_ERR_ARG;
   }
   return bn_bwd_apply_impl(dz, z, x, dtype, act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, 1, dx, nullptr, 0, fwd_scale, fwd_shift,
-                           next_sum_dx, next_sum_dx_x, stream_);
+                           next_sum_dx, next_sum_dx_x, param_grads, stream_);
 }
 
 int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* dx, int32_t dtype, int32_t k, int32_t stride,

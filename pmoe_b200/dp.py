@@ -42,8 +42,10 @@ class GradBucketer:
     """Flat fp32 buckets over a fixed parameter list; all-reduce(avg) per bucket, launched in bucket order as buckets
     fill up (every rank fills them in the same order because every rank replays the same tape)."""
 
-    def __init__(self, params, group=None, bucket_bytes=32 << 20, device=None):
+    def __init__(self, params, group=None, bucket_bytes=32 << 20, device=None, persistent=False):
         self.group = group
+        self.persistent = persistent   # keep the flat buffers across backward passes (gradient_as_bucket_view)
+        self._keep = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
         self.device = device if device is not None else (self.params[0].device if self.params else torch.device("cpu"))
@@ -68,7 +70,15 @@ class GradBucketer:
 
     # ---- one backward pass
     def reset(self):
-        self.flat = [None] * len(self.sizes)
+        if self.persistent:
+            if self._keep is None:
+                self._keep = [torch.zeros(n, dtype=torch.float32, device=self.device) for n in self.sizes]
+            else:
+                for buf in self._keep:   # parameters that receive no gradient in this pass must read zero
+                    buf.zero_()
+            self.flat = list(self._keep)
+        else:
+            self.flat = [None] * len(self.sizes)
         self.filled = [0] * len(self.sizes)
         self.have = set()
         self.handles = []
@@ -129,9 +139,10 @@ class GradBucketer:
         out = {}
         for p in self.params:
             b, off, n = self.slots[id(p)]
-            out[id(p)] = self.flat[b][off:off + n].view(p.shape) if id(p) in self.have else None
+            out[id(p)] = self.flat[b][off:off + n].view(p.shape) if (id(p) in self.have or self.persistent) else None
         stats = {"buckets": len(self.sizes), "launched": self.launched, "bytes": 4 * sum(self.sizes)}
-        self.reset()
+        if not self.persistent:
+            self.reset()
         return out, stats
 
 
@@ -140,9 +151,14 @@ class DataParallel(torch.nn.Module):
     executor picks this wrapper up (dp.current()) and routes its parameter gradients through a GradBucketer.
     Parameters and buffers are broadcast from rank 0 at construction (replicas start identical)."""
 
-    def __init__(self, module, process_group=None, bucket_mb=32, broadcast=True):
+    def __init__(self, module, process_group=None, bucket_mb=32, broadcast=True, gradient_as_bucket_view=False):
+        """gradient_as_bucket_view: every parameter's .grad IS its slice of the flat all-reduce buckets — the backward kernels
+        write there, NCCL reduces in place, the optimizer reads the result: no copy or add between them. Each backward
+        OVERWRITES the gradients (no accumulation across backward calls): use it when every optimizer step follows exactly
+        one backward pass."""
         super().__init__()
         self.module = module
+        self.as_bucket_view = bool(gradient_as_bucket_view)
         self.group = process_group
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self.last_stats = None
@@ -169,7 +185,7 @@ class DataParallel(torch.nn.Module):
         key = tuple(id(p) for p in params if p.requires_grad)
         b = self._bucketers.get(key)
         if b is None:
-            b = self._bucketers[key] = GradBucketer(params, self.group, self.bucket_bytes)
+            b = self._bucketers[key] = GradBucketer(params, self.group, self.bucket_bytes, persistent=self.as_bucket_view)
         b.reset()
         return b
 

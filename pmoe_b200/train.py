@@ -19,6 +19,34 @@ from .ops import TAPS3, pad_ch
 
 
 # ------------------------------------------------------------------------------------------------ tape
+ACCUMULATE_IN_PLACE = True  # gradients of parameters that already have a .grad are added into it by the kernels themselves
+
+
+class BnParamGrads(C.Structure):  # PmoeBnParamGrads
+    _fields_ = [("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("n", C.c_int32), ("accumulate", C.c_int32)]
+
+
+def _bn_pgrads(tape, bn, c):
+    """Gradient slots of a BatchNorm's weight / bias for the apply kernel's side output -> (struct or None, params to mark done)."""
+    pg, done, acc = BnParamGrads(), [], None
+    for prm, field in ((bn.weight, "dgamma"), (bn.bias, "dbeta")):
+        if prm is None or not prm.requires_grad:
+            continue
+        slot, existed = tape.pgrad_slot(prm)
+        if acc is None:
+            acc = existed
+        elif acc != existed:      # one slot fresh, one not: make both accumulate
+            if not existed:
+                slot.zero_()
+            acc = True
+        setattr(pg, field, slot.data_ptr())
+        done.append(prm)
+    if not done:
+        return None, done
+    pg.n, pg.accumulate = int(c), int(bool(acc))
+    return pg, done
+
+
 class Tape:
     def __init__(self, dtype, save):
         self.dtype = dtype
@@ -33,6 +61,7 @@ class Tape:
         self.bucketer = None        # pmoe_b200.dp.GradBucketer during a data-parallel backward
         self.presums = {}           # id(Act) -> (sum dy*[y>0], sum dy*y) reduced by the kernel that wrote the Act's gradient
         self.arena = {}             # dtype -> [zeroed chunk, elements handed out]
+        self.direct = set()         # id(param) whose gradient was accumulated straight into param.grad
         self.nbt = []               # BatchNorm num_batches_tracked buffers to bump at the end of the pass
         self.touched = []           # buffers written through raw pointers (running statistics): versions bumped at the end
 
@@ -79,13 +108,21 @@ class Tape:
         k = id(p)
         if k in self.pgrads:
             return self.pgrads[k].view(-1), True
+        self.params[k] = p
         if self.bucketer is not None:
             buf = self.bucketer.slot(p)
-        else:
-            buf = torch.empty(p.numel(), dtype=torch.float32, device=p.device)
-        self.params[k] = p
-        self.pgrads[k] = buf.view(p.shape)
-        return buf, False
+            self.pgrads[k] = buf.view(p.shape)
+            return buf, False
+        g = p.grad
+        if ACCUMULATE_IN_PLACE and g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.device == p.device:
+            # the parameter already carries a gradient (micro-batch accumulation, captured graphs with static .grad): the kernels
+            # add into it directly instead of handing autograd a second tensor to add (one read-modify-write of every gradient less)
+            self.pgrads[k] = g
+            self.direct.add(k)
+            return g.view(-1), True
+        full = torch.empty(p.shape, dtype=torch.float32, device=p.device)  # owns its storage: AccumulateGrad can take it without a copy
+        self.pgrads[k] = full
+        return full.view(-1), False
 
     def pgrad_done(self, p):
         """One announced contribution to p's gradient has been written."""
@@ -173,7 +210,7 @@ def _bn_bwd_reduce(tape, dz, z, x, act, mean, rstd, cpad, fwd=None):
 FUSE_BN_CHAIN_SUMS = True  # tests switch it off to compare against the separate reduce pass
 
 
-def _bn_bwd_apply_sums(tape, dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, dx, fwd):
+def _bn_bwd_apply_sums(tape, dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, dx, fwd, pgrads=None):
     """bn_bwd_apply (batch statistics, ReLU) that also reduces sum dx*[x>0] and sum dx*x for the upstream BatchNorm whose ReLU
     output x is. Returns the two fp64 sums, or None (nothing launched) when the tensors do not qualify."""
     cp = dz.shape[3]
@@ -190,11 +227,12 @@ def _bn_bwd_apply_sums(tape, dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, dx
     check(profiler.launch("bn_bwd_apply", lambda: lib().pmoe_bn_bwd_apply_sums(
         C.byref(vdz), C.byref(vz), C.byref(vx), dtype_code(dz), ACT[act], _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma),
         _lib.ptr(s1), _lib.ptr(s2), float(inv_n), C.byref(vdx), _lib.ptr(fwd[0] if mx else None), _lib.ptr(fwd[1] if mx else None),
-        n1.data_ptr(), n2.data_ptr(), stream_ptr()), io=(dz, None if mx else z, x, dx)), "bn_bwd_apply_sums")
+        n1.data_ptr(), n2.data_ptr(), None if pgrads is None else C.byref(pgrads), stream_ptr()), io=(dz, None if mx else z, x, dx)),
+        "bn_bwd_apply_sums")
     return n1, n2
 
 
-def _bn_bwd_apply(dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, batch_stats, dx, dres, acc_dres, fwd=None):
+def _bn_bwd_apply(dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, batch_stats, dx, dres, acc_dres, fwd=None, pgrads=None):
     mx = _mask_from_x(dz, x, act, fwd) and (dx is None or dx.is_contiguous()) and (dres is None or dres.is_contiguous())
     vdz = view4(dz)
     vz = view4(z) if (z is not None and not mx) else _lib.null_view()
@@ -204,7 +242,7 @@ def _bn_bwd_apply(dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, batch_stats, 
     check(profiler.launch("bn_bwd_apply", lambda: lib().pmoe_bn_bwd_apply(
         C.byref(vdz), C.byref(vz), C.byref(vx), dtype_code(dz), ACT[act], _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(gamma),
         _lib.ptr(s1), _lib.ptr(s2), float(inv_n), int(batch_stats), C.byref(vdx), C.byref(vdr), int(acc_dres),
-        _lib.ptr(fwd[0] if mx else None), _lib.ptr(fwd[1] if mx else None), stream_ptr()),
+        _lib.ptr(fwd[0] if mx else None), _lib.ptr(fwd[1] if mx else None), None if pgrads is None else C.byref(pgrads), stream_ptr()),
         io=(dz, None if (z is None or mx) else z, x, dx, dres, dres if (acc_dres and dres is not None) else None)), "bn_bwd_apply")
 
 
@@ -433,8 +471,19 @@ def _eval_affine(bn, bias, cout, cop):
         from .infer import cached
         return cached(bn, "evalaff%d" % cop, [bn.weight, bn.bias, bn.running_mean, bn.running_var], build)
     if bias is not None:
-        return None, ops.pad_vec(bias.detach(), cop, 0.0)
+        return None, _padded_bias(bias, cop)
     return None, None
+
+
+def _padded_bias(bias, cop, repeat=1):
+    """Bias as the [cop] (x repeat) fp32 shift vector of the GEMM epilogue: the parameter itself when nothing needs padding,
+    otherwise a packed operand refreshed with the weights (no per-call fill + copy launches)."""
+    b = bias.detach()
+    if repeat == 1 and b.numel() == cop and b.dtype == torch.float32 and b.is_contiguous():
+        return b
+    n = b.numel()
+    return packs.packed(bias, "bias|%d|%d" % (cop, repeat), bias.shape,
+                        lambda v: torch.nn.functional.pad(v, (0, cop - n)).repeat(repeat), torch.float32)[0]
 
 
 def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, want_pool=False, ksize=3, layouts=None,
@@ -514,9 +563,11 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
                 s2 = rstd[:cstore].double() * (sraw - mean[:cstore].double() * s1)
             else:
                 s1, s2 = _bn_bwd_reduce(tape, dz, z_saved, raw, act, mean, rstd, cstore, fwd=fwd_aff)
-            tape.add_pgrad(bn.weight, s2[:cout])
-            tape.add_pgrad(bn.bias, s1[:cout])
-            _bn_bwd_apply(dz, z_saved, raw, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, dy, dres, acc_dres, fwd=fwd_aff)
+            pg, pdone = _bn_pgrads(tape, bn, cout)   # d weight = s2, d bias = s1: written by the apply kernel
+            _bn_bwd_apply(dz, z_saved, raw, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, dy, dres, acc_dres, fwd=fwd_aff,
+                          pgrads=pg)
+            for prm in pdone:
+                tape.pgrad_done(prm)
         else:
             if bn is not None and _any_rg([bn.weight, bn.bias]):
                 raise NotImplementedError("pmoe_b200: gradients of BatchNorm affine parameters in eval mode are not supported")
@@ -609,7 +660,7 @@ def conv_transpose_op(tape, up, x, tag=""):
                 w4[q * cstore:q * cstore + cout, :cin] = wf[:, :, a, b].t()
             return w4
         wp4 = packs.packed(weight, "T4|%d|%d|%s" % (cp, cstore, dt), weight.shape, build4, dt)[0]
-        shift4 = ops.pad_vec(bias.detach(), cstore, 0.0).repeat(4)
+        shift4 = _padded_bias(bias, cstore, repeat=4)
         rows = out.view(n, h, 2, w, 2 * cstore)
         ops.conv([x.t], wp4, segs, ck, rows[:, :, 0], shift=shift4, out_extra=[rows[:, :, 1]], out_cols=2 * cstore, flops=4 * flops,
                  tag="convT " + tag)
@@ -846,17 +897,19 @@ def bn_act_op(tape, bn, x, act="relu", tag=""):
             tmp = g if not existed else torch.empty_like(g)
             if bn_train:
                 s1, s2 = _bn_bwd_reduce(tape, dz, zs, x.t, act, mean, rstd, cp, fwd=fwd_aff)
-                tape.add_pgrad(bn.weight, s2[:c])
-                tape.add_pgrad(bn.bias, s1[:c])
+                pg, pdone = _bn_pgrads(tape, bn, c)
                 nxt = None
                 if getattr(x, "bn_relu", False) and not existed:
                     # x = relu(BN(raw)) of the conv just upstream and this is its only gradient so far: reduce that layer's
                     # backward sums while dx is in registers (invalidated if anything is accumulated into dx later)
-                    nxt = _bn_bwd_apply_sums(tape, dz, zs, x.t, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), tmp, fwd_aff)
+                    nxt = _bn_bwd_apply_sums(tape, dz, zs, x.t, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), tmp, fwd_aff, pgrads=pg)
                 if nxt is not None:
                     tape.presums[id(x)] = nxt
                 else:
-                    _bn_bwd_apply(dz, zs, x.t, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, tmp, None, False, fwd=fwd_aff)
+                    _bn_bwd_apply(dz, zs, x.t, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, tmp, None, False, fwd=fwd_aff,
+                                  pgrads=pg)
+                for prm in pdone:
+                    tape.pgrad_done(prm)
             else:
                 if _any_rg([bn.weight, bn.bias]):
                     raise NotImplementedError("pmoe_b200: gradients of BatchNorm affine parameters in eval mode are not supported")
@@ -1165,9 +1218,9 @@ def grouped_linear_op(tape, srcs, lins, act=None, tag=""):
     B = srcs[0].t.shape[2]
     has_bias = lins[0].bias is not None
     shift = None
-    if has_bias:
-        shift = torch.zeros(K, cop, dtype=torch.float32, device=dev)
-        shift[:, :cout] = torch.stack([l.bias.detach().float() for l in lins])
+    if has_bias:   # (K, cop) stacked biases, refreshed with the weights
+        shift = packs.packed_group([l.bias for l in lins], ("bias", cop), lins[0].bias.shape,
+                                   lambda v: torch.nn.functional.pad(v, (0, cop - cout)), torch.float32)[0]
     z_t = torch.empty(K, 1, B, cstore, dtype=dt, device=dev)
     flops = 2.0 * K * B * cout * sum(x.nlog for x in srcs)
     ops.conv([x.t for x in srcs], wp, segs, ck, z_t, shift=shift, act=act, flops=flops, tag="grouped " + tag)
@@ -1356,9 +1409,20 @@ class TapeFunction(torch.autograd.Function):
         if tape.bucketer is not None:
             reduced, stats = tape.bucketer.finish()
             ctx.dp.note_reduced([p for p in ctx.plist if p.requires_grad], stats)
-            grads = tuple(reduced.get(id(p)) if p.requires_grad else None for p in ctx.plist)
+            if ctx.dp.as_bucket_view:
+                # .grad aliases the reduced bucket slices: nothing is handed to AccumulateGrad
+                for p in ctx.plist:
+                    v = reduced.get(id(p)) if p.requires_grad else None
+                    if v is not None and (p.grad is None or p.grad.data_ptr() != v.data_ptr()):
+                        p.grad = v
+                packs.bump([p.grad for p in ctx.plist if p.requires_grad and p.grad is not None])
+                grads = tuple(None for _ in ctx.plist)
+            else:
+                grads = tuple(reduced.get(id(p)) if p.requires_grad else None for p in ctx.plist)
         else:
-            grads = tuple(tape.pgrads.get(id(p)) if p.requires_grad else None for p in ctx.plist)
+            grads = tuple((tape.pgrads.get(id(p)) if (p.requires_grad and id(p) not in tape.direct) else None) for p in ctx.plist)
+            if tape.direct:
+                packs.bump([p.grad for p in ctx.plist if id(p) in tape.direct])
         ctx.tape = None
         if DIRECT_GRADS and ctx.dp is None:
             # hand the gradients to .grad ourselves: the engine would clone each of the ~500 tensors it cannot steal

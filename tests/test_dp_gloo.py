@@ -95,3 +95,33 @@ def test_bucketer_single_process_no_group():
     with pytest.raises(RuntimeError):
         b.ready(params[0], torch.zeros(10))
         b.ready(params[0], torch.zeros(10))
+
+
+def test_bucketer_slots_are_written_in_place_and_persistent_buckets_alias():
+    """slot(): the backward kernels write a gradient straight into its bucket slice (no staging copy); persistent buckets
+    (gradient_as_bucket_view) hand back the SAME storage every pass, zeroed, so .grad can alias it."""
+    from pmoe_b200 import dp
+    params = [torch.nn.Parameter(torch.zeros(10)), torch.nn.Parameter(torch.zeros(3, 3)), torch.nn.Parameter(torch.zeros(5))]
+    b = dp.GradBucketer(params, bucket_bytes=1 << 20, persistent=True)
+    s1 = b.slot(params[1])
+    s1.copy_(torch.arange(9.0))
+    b.ready(params[1])
+    b.slot(params[0]).fill_(2.0)
+    b.ready(params[0])
+    red, _ = b.finish()
+    assert torch.equal(red[id(params[1])], torch.arange(9.0).view(3, 3)) and torch.equal(red[id(params[0])], torch.full((10,), 2.0))
+    assert torch.equal(red[id(params[2])], torch.zeros(5))       # no gradient this pass: reads zero
+    ptr = red[id(params[1])].data_ptr()
+    b.reset()
+    assert b.slot(params[1]).data_ptr() == ptr and float(b.slot(params[1]).abs().sum()) == 0.0
+
+
+def test_checkpoint_with_numpy_scalars_loads(tmp_path):
+    """The reference trainers store np.mean(...) entries next to the state dicts (train_2.py:346-370); torch >= 2.6 refuses
+    them under weights_only=True."""
+    import numpy as np
+    from pmoe_b200.utils import io
+    path = io.save_checkpoint({"epoch": 3, "best": np.float64(0.25), "e_loss": [np.mean([1.0, 2.0])], "model": {"w": torch.ones(2)}},
+                              False, str(tmp_path), "model-3")
+    ck = io.load_checkpoint(path, "cpu")
+    assert float(ck["best"]) == 0.25 and torch.equal(ck["model"]["w"], torch.ones(2))

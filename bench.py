@@ -413,10 +413,17 @@ def run_train_leg(args, rank, world, dev, peaks, local_rank):
                 static_loss.backward()
             launches_per_micro = profiler.launch_count()
             mode = "cuda_graph"
-        except Exception as ex:  # capture is an optimisation: fall back to the eager tape
+        except Exception as ex:  # capture is an optimisation: fall back to the eager tape, loudly
+            import traceback
+            print("bench: CUDA-graph capture of the training micro-step failed, running the eager tape instead:\n" + traceback.format_exc(),
+                  file=sys.stderr, flush=True)
             graph, mode = None, "eager (graph capture failed: %s)" % str(ex).splitlines()[0][:160]
+            static_loss = None
             _train.DROPOUT_STEP = None
             torch.cuda.synchronize()
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
 
     copy_stream = torch.cuda.Stream(device=dev)
     stage = {k: torch.empty_like(v) for k, v in static.items()}

@@ -1402,9 +1402,15 @@ class TapeFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *gouts):
         tape = ctx.tape
+        if tape is None:
+            raise RuntimeError("pmoe_b200: backward through the same forward pass twice (the tape frees its buffers as it replays; "
+                               "run forward again)")
         if ctx.dp is not None:
             tape.bucketer = ctx.dp.make_bucketer(ctx.plist)
         ctx.seed(tape, gouts)
+        # the seed closure holds the forward's output tensors, whose grad_fn is this node: drop it so that the finished graph (and the
+        # AccumulateGrad nodes it keeps alive, with the stream they were created on) can be freed
+        ctx.seed = None
         tape.backward()
         if tape.bucketer is not None:
             reduced, stats = tape.bucketer.finish()

@@ -46,6 +46,9 @@ class GradBucketer:
         self.group = group
         self.persistent = persistent   # keep the flat buffers across backward passes (gradient_as_bucket_view)
         self._keep = None
+        self.eager_alloc = False       # set while a multi-stream tape is the producer (pmoe_b200.train.Tape.branch)
+        self.producer_streams = None   # callable -> CUDA streams that may hold un-finished writes into the buckets
+        self._comm_stream = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params = [p for p in params if p.requires_grad]
         self.device = device if device is not None else (self.params[0].device if self.params else torch.device("cpu"))
@@ -78,7 +81,9 @@ class GradBucketer:
                     buf.zero_()
             self.flat = list(self._keep)
         else:
-            self.flat = [None] * len(self.sizes)
+            # allocated (and zero-filled) up front on the caller's stream: gradient kernels may write the slots from side streams
+            self.flat = [torch.zeros(n, dtype=torch.float32, device=self.device) for n in self.sizes] if self.eager_alloc else \
+                [None] * len(self.sizes)
         self.filled = [0] * len(self.sizes)
         self.have = set()
         self.handles = []
@@ -119,6 +124,20 @@ class GradBucketer:
             return
         backend = dist.get_backend(self.group)
         if backend == "nccl":
+            streams = self.producer_streams() if self.producer_streams is not None else []
+            if streams:
+                # the bucket was filled from several streams: launch the reduction from a stream that waits for all of them,
+                # without stalling any of the producers
+                if self._comm_stream is None:
+                    self._comm_stream = torch.cuda.Stream(device=self.device)
+                comm = self._comm_stream
+                comm.wait_stream(torch.cuda.current_stream())
+                for st in streams:
+                    comm.wait_stream(st)
+                with torch.cuda.stream(comm):
+                    self.handles.append(dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+                self._used_comm = True
+                return
             self.handles.append(dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
         else:  # gloo (CPU tests): sum, then scale
             h = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -136,6 +155,9 @@ class GradBucketer:
                 h[1].div_(self.world)
             else:
                 h.wait()  # makes the current stream wait for the NCCL stream
+        if getattr(self, "_used_comm", False):
+            torch.cuda.current_stream().wait_stream(self._comm_stream)   # rejoin (also ends the branch inside a graph capture)
+            self._used_comm = False
         out = {}
         for p in self.params:
             b, off, n = self.slots[id(p)]
@@ -181,11 +203,13 @@ class DataParallel(torch.nn.Module):
         dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.group)
         p.grad.div_(world)
 
-    def make_bucketer(self, params):
+    def make_bucketer(self, params, eager_alloc=False):
         key = tuple(id(p) for p in params if p.requires_grad)
         b = self._bucketers.get(key)
         if b is None:
             b = self._bucketers[key] = GradBucketer(params, self.group, self.bucket_bytes, persistent=self.as_bucket_view)
+        b.eager_alloc = eager_alloc
+        b.producer_streams = None
         b.reset()
         return b
 

@@ -114,7 +114,12 @@ def _run_experts(owner, experts, images, speed, command, alt, softmax=True):
         sp_buf = torch.zeros(1, 1, B, K * 16, dtype=tape.dtype, device=dev)
         if train.grouped_supported(experts, alt):
             # encoders per expert, then ALL experts' heads with one launch per layer (grouped GEMM over the expert axis)
-            feats = [train.backbone_features(tape, ex.backbone, x, tag="moe.%d.backbone" % k) for k, ex in enumerate(experts)]
+            feats = []
+            small = B * images.shape[-2] * images.shape[-1] <= train.MULTI_STREAM_MAX_PIXELS
+            for k, ex in enumerate(experts):   # the encoders share only the input: each on its own stream (train.Tape.branch)
+                with tape.branch(k, enable=small and K > 1):
+                    feats.append(train.backbone_features(tape, ex.backbone, x, tag="moe.%d.backbone" % k))
+            tape.join()
             al, ap, sp = train.expert_heads_grouped(tape, experts, feats, speed_a, cmd_a, alt)
             gm = train.GateMixture(tape, [al], [ap], al.t, ap.t, B, K, relu_alpha=not alt, a_sk=B * 16, p_sk=B * 16)
             speeds = sp.t.view(K, B, 16)[:, :, :1].permute(1, 0, 2).float().contiguous()

@@ -19,6 +19,22 @@ from .ops import TAPS3, pad_ch
 
 
 # ------------------------------------------------------------------------------------------------ tape
+import contextlib
+import os as _os0
+
+MULTI_STREAM = _os0.environ.get("PMOE_MULTI_STREAM", "1") == "1"   # independent sub-networks (expert encoders) on side streams
+MULTI_STREAM_MAX_PIXELS = 160 * 224 * 224   # ... when one sub-network's batch is small enough to leave SMs idle (B <= 160 at 224^2)
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device, index):
+    key = (device.index if device.index is not None else torch.cuda.current_device(), index)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
+
+
 ACCUMULATE_IN_PLACE = True  # gradients of parameters that already have a .grad are added into it by the kernels themselves
 
 
@@ -62,6 +78,8 @@ class Tape:
         self.presums = {}           # id(Act) -> (sum dy*[y>0], sum dy*y) reduced by the kernel that wrote the Act's gradient
         self.arena = {}             # dtype -> [zeroed chunk, elements handed out]
         self.direct = set()         # id(param) whose gradient was accumulated straight into param.grad
+        self.branch_stream = None   # side stream of the branch being recorded / replayed (None: the caller's stream)
+        self.side_streams = []      # side streams this pass has forked work onto
         self.nbt = []               # BatchNorm num_batches_tracked buffers to bump at the end of the pass
         self.touched = []           # buffers written through raw pointers (running statistics): versions bumped at the end
 
@@ -74,10 +92,11 @@ class Tape:
         for d in (shape if isinstance(shape, (tuple, list)) else (shape,)):
             n *= int(d)
         n_al = (n + 63) // 64 * 64  # 256-byte aligned slices
-        ent = self.arena.get((dtype, device))
+        key = (dtype, device, id(self.branch_stream))   # one arena per stream: a chunk is zero-filled on the stream that uses it
+        ent = self.arena.get(key)
         if ent is None or ent[1] + n_al > ent[0].numel():
             ent = [torch.zeros(max(self._ARENA_ELEMS.get(dtype, 1 << 16), n_al), dtype=dtype, device=device), 0]
-            self.arena[(dtype, device)] = ent
+            self.arena[key] = ent
         out = ent[0][ent[1]:ent[1] + n].view(shape)
         ent[1] += n_al
         return out
@@ -92,7 +111,35 @@ class Tape:
 
     def record(self, fn):
         if self.save:
-            self.ops.append(fn)
+            self.ops.append((fn, self.branch_stream))
+
+    @contextlib.contextmanager
+    def branch(self, index, enable=True):
+        """Run (and later replay the backward of) an independent sub-network on its own CUDA stream: the K expert encoders of a
+        mixture share nothing but the input, and at small per-GPU batches their late stages are too small to fill 148 SMs one
+        kernel at a time. Forward: the side stream waits for the caller's stream at entry; `join()` makes the caller's stream wait
+        for every side stream. Backward: a closure recorded inside a branch replays on the same side stream, after the caller's
+        stream has produced the gradients it consumes. Inside CUDA-graph capture the branches become parallel graph branches."""
+        if not (MULTI_STREAM and enable):
+            yield
+            return
+        main = torch.cuda.current_stream()
+        side = _side_stream(main.device, index)
+        side.wait_stream(main)
+        if side not in self.side_streams:
+            self.side_streams.append(side)
+        prev, self.branch_stream = self.branch_stream, side
+        try:
+            with torch.cuda.stream(side):
+                yield
+        finally:
+            self.branch_stream = prev
+
+    def join(self):
+        """The caller's stream waits for all side streams (end of the forked section of the forward pass)."""
+        main = torch.cuda.current_stream()
+        for s_ in self.side_streams:
+            main.wait_stream(s_)
 
     def track(self, act):
         if self.save:
@@ -100,7 +147,10 @@ class Tape:
         return act
 
     def grad_of(self, act):
-        return self.grads.pop(id(act), None)
+        g = self.grads.pop(id(act), None)
+        if g is not None and self.branch_stream is not None:
+            g.record_stream(self.branch_stream)   # may have been produced (allocated) on another stream: keep it until this one is done
+        return g
 
     def pgrad_slot(self, p):
         """(flat fp32 buffer of p's gradient, whether it already holds a contribution). Under data parallelism the buffer
@@ -149,8 +199,26 @@ class Tape:
         self.pgrad_done(p)
 
     def backward(self):
-        for fn in reversed(self.ops):
-            fn()
+        main = torch.cuda.current_stream()
+        forked = []
+        for fn, side in reversed(self.ops):
+            if side is None:
+                if forked:       # back on the caller's stream: everything the side streams produced is needed (or about to be freed)
+                    for s_ in forked:
+                        main.wait_stream(s_)
+                    forked = []
+                self.branch_stream = None
+                fn()
+            else:
+                if side not in forked:
+                    side.wait_stream(main)   # the gradients this branch consumes were produced on the caller's stream
+                    forked.append(side)
+                self.branch_stream = side
+                with torch.cuda.stream(side):
+                    fn()
+        self.branch_stream = None
+        for s_ in forked:
+            main.wait_stream(s_)
         self.ops = []
         self.alive = []
         self.grads = {}
@@ -1406,7 +1474,9 @@ class TapeFunction(torch.autograd.Function):
             raise RuntimeError("pmoe_b200: backward through the same forward pass twice (the tape frees its buffers as it replays; "
                                "run forward again)")
         if ctx.dp is not None:
-            tape.bucketer = ctx.dp.make_bucketer(ctx.plist)
+            tape.bucketer = ctx.dp.make_bucketer(ctx.plist, eager_alloc=bool(tape.side_streams))
+            if tape.side_streams:
+                tape.bucketer.producer_streams = lambda: list(tape.side_streams)
         ctx.seed(tape, gouts)
         # the seed closure holds the forward's output tensors, whose grad_fn is this node: drop it so that the finished graph (and the
         # AccumulateGrad nodes it keeps alive, with the stream they were created on) can be freed

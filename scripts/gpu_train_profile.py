@@ -82,4 +82,4 @@ top = sorted(recs, key=lambda r: -r[1])[:25]
 for kind, t, f, b, tag in top:
     print("  %-16s %-44s %7.3f ms %8.1f TF %8.0f GB/s" % (kind, tag, t, f / max(t, 1e-9) / 1e9, b / max(t, 1e-9) / 1e6))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump({"ms_per_step": ms, "batch": B, "k": args.k, "hbm_peak_gbs": HBM_PEAK, "rows": rows, "top": top, "all": recs}, open("gpurun_out/train_profile.json", "w"), indent=1)
+json.dump({"ms_per_step": ms, "batch": B, "k": args.k, "hbm_peak_gbs": HBM_PEAK, "rows": rows, "top": top, "all": recs}, open("gpurun_out/train_profile_k%d_b%d.json" % (args.k, B), "w"), indent=1)

@@ -27,7 +27,8 @@ typedef void* pmoe_stream_t; /* cudaStream_t */
 
 enum { PMOE_OK = 0, PMOE_ERR_ARG = -1, PMOE_ERR_UNSUPPORTED = -2, PMOE_ERR_LAUNCH = -3, PMOE_ERR_DRIVER = -4 };
 enum { PMOE_F32 = 0, PMOE_BF16 = 1 };
-enum { PMOE_ACT_NONE = 0, PMOE_ACT_RELU = 1, PMOE_ACT_ELU = 2, PMOE_ACT_TANH = 3, PMOE_ACT_SIGMOID = 4 };
+enum { PMOE_ACT_NONE = 0, PMOE_ACT_RELU = 1, PMOE_ACT_ELU = 2, PMOE_ACT_TANH = 3, PMOE_ACT_SIGMOID = 4,
+       PMOE_ACT_RELU6 = 5, PMOE_ACT_HSWISH = 6, PMOE_ACT_HSIGMOID = 7 }; /* 5-7: torchvision MobileNetV2/V3 (backbone.py:75-104) */
 
 /* Strided NHWC view; strides in ELEMENTS, channel stride is 1. */
 typedef struct PmoeView4 {
@@ -288,6 +289,19 @@ int pmoe_mt_rmsprop(const PmoeMtChunk* chunks_dev, int32_t n_chunks, double lr, 
 /* torch.optim.swa_utils.AveragedModel.update_parameters, default avg_fn (train_2.py:119-121,179-187):
  * chunk.p (averaged) += (chunk.g (current model parameter) - chunk.p) / (n_averaged + 1). */
 int pmoe_mt_swa_update(const PmoeMtChunk* chunks_dev, int32_t n_chunks, int64_t n_averaged, pmoe_stream_t stream);
+
+/* ---- depthwise convolutions (depthwise.cu): torchvision MobileNetV2 / V3 inverted-residual blocks, the alternative backbones
+ * of the reference's factory (model/blocks/backbone.py:75-104 -> nn.Conv2d(c, c, k, stride, (k-1)/2, groups=c, bias=False)).
+ * Views are NHWC (dtype PMOE_F32 | PMOE_BF16, channels a multiple of 8); w_packed is [k*k][w_cpad] fp32, tap-major
+ * (w_packed[(r*k+s)*w_cpad + c] = weight[c, 0, r, s]), produced by pmoe_pack_gather. */
+int pmoe_dwconv_fwd(const PmoeView4* x, const float* w_packed, int32_t w_cpad, const PmoeView4* y, int32_t dtype, int32_t k,
+                    int32_t stride, int32_t pad, pmoe_stream_t stream);
+/* dx (+)= conv_transpose of dy with the same weights (aten::convolution_backward, input half). */
+int pmoe_dwconv_dgrad(const PmoeView4* dy, const float* w_packed, int32_t w_cpad, const PmoeView4* dx, int32_t dtype, int32_t k,
+                      int32_t stride, int32_t pad, int32_t accumulate, pmoe_stream_t stream);
+/* dw_packed[k*k][w_cpad] (fp32, ACCUMULATED into) += sum over pixels of dy * shifted x (weight half). */
+int pmoe_dwconv_wgrad(const PmoeView4* x, const PmoeView4* dy, float* dw_packed, int32_t w_cpad, int32_t dtype, int32_t k,
+                      int32_t stride, int32_t pad, pmoe_stream_t stream);
 
 /* ---- weight layout (pack.cu) ------------------------------------------------------------------------------------------
  * The conv / linear kernels read weights in a packed [cout_pad][K] operand layout; the nn.Parameter stays fp32 in the

@@ -16,7 +16,7 @@ _lib = None
 
 MAX_SRC = 6
 MAX_SEG = 64
-ACT = {None: 0, "none": 0, "relu": 1, "elu": 2, "tanh": 3, "sigmoid": 4}
+ACT = {None: 0, "none": 0, "relu": 1, "elu": 2, "tanh": 3, "sigmoid": 4, "relu6": 5, "hswish": 6, "hsigmoid": 7}
 F32, BF16 = 0, 1
 
 

@@ -6,6 +6,7 @@
 //                        k enumerating (segment, chunk, channel) exactly as the forward's wpack.
 // Tiles: 64 pixels x 64 output channels x 16 K per step, 256 threads, 4x4 register block each.
 #include "host_util.h"
+#include "act.cuh"
 #include "ptx.cuh"
 
 #include <string.h>
@@ -79,7 +80,7 @@ __device__ __forceinline__ float simt_act(float x, int act) {
     case PMOE_ACT_ELU: return x > 0.f ? x : expm1f(x);
     case PMOE_ACT_TANH: return tanhf(x);
     case PMOE_ACT_SIGMOID: return 1.f / (1.f + expf(-x));
-    default: return x;
+    default: return act_piecewise(x, act);
   }
 }
 

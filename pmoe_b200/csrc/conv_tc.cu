@@ -13,6 +13,7 @@
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 #include "host_util.h"
+#include "act.cuh"
 #include "ptx.cuh"
 
 #include <initializer_list>
@@ -127,7 +128,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     case PMOE_ACT_ELU: return x > 0.f ? x : expm1f(x);
     case PMOE_ACT_TANH: return tanhf(x);
     case PMOE_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
-    default: return x;
+    default: return act_piecewise(x, act);
   }
 }
 

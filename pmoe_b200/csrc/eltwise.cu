@@ -3,6 +3,7 @@
 // strided NHWC views, 8 channels (16 B of bf16 / 32 B of fp32) per thread, grid-stride loops sized
 // to a multiple of the SM count.
 #include "host_util.h"
+#include "act.cuh"
 #include "ptx.cuh"
 #include "reduce.cuh"
 
@@ -466,6 +467,9 @@ __global__ void __launch_bounds__(256) affine_act_kernel(V4 src, V4 dst, const f
     if (act == PMOE_ACT_RELU) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+    } else if (act != PMOE_ACT_NONE) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = act_piecewise(v[q], act);
     }
     store8(static_cast<T*>(dst.ptr) + o_d, v);
   }

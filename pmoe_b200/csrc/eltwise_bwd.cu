@@ -2,6 +2,7 @@
 // reductions, then the elementwise apply), max-pool backward (first-max tie rule of ATen), ECA backward,
 // gradient accumulation. Same conventions as eltwise.cu: strided NHWC views, 8 channels per thread.
 #include "host_util.h"
+#include "act.cuh"
 #include "ptx.cuh"
 #include "reduce.cuh"
 
@@ -61,7 +62,9 @@ __device__ __forceinline__ float act_grad(float z, int act) {
     case PMOE_ACT_ELU: return z > 0.f ? 1.f : z + 1.f;  // z = exp(x)-1 for x<=0  ->  dz/dx = z+1
     case PMOE_ACT_TANH: return 1.f - z * z;
     case PMOE_ACT_SIGMOID: return z * (1.f - z);
-    default: return 1.f;
+    case PMOE_ACT_RELU6: return (z > 0.f && z < 6.f) ? 1.f : 0.f;
+    case PMOE_ACT_HSIGMOID: return (z > 0.f && z < 1.f) ? (1.f / 6.f) : 0.f;
+    default: return 1.f;  // Hardswish is not a function of its output: callers pass the forward affine (pre-activation from x)
   }
 }
 
@@ -79,7 +82,10 @@ static inline int bgrid(long long items, int threads) {
 template <typename T, bool FLAT>
 __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* __restrict__ mean,
                                      const float* __restrict__ rstd, double* __restrict__ sum_dy,
-                                     double* __restrict__ sum_dy_xhat, long long pix_per_block) {
+                                     double* __restrict__ sum_dy_xhat, long long pix_per_block,
+                                     const float* __restrict__ fwd_scale, const float* __restrict__ fwd_shift) {
+  // fwd_scale / fwd_shift (optional): the activation's derivative is taken at the PRE-activation u = fwd_scale*x + fwd_shift,
+  // recomputed from the layer input x (needed for Hardswish, whose output does not determine it; z is then not read)
   __shared__ float sm[kRedThreads * 8];
   const int cg = dz.c / 8;
   const int lanes = blockDim.x / cg;
@@ -90,11 +96,13 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(BV4 dz, BV4 
   if (p1 > npix) p1 = npix;
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (lane < lanes) {
-    float m[8], r[8];
+    float m[8], r[8], fsc[8], fsh[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       m[q] = mean ? __ldg(mean + g * 8 + q) : 0.f;
       r[q] = rstd ? __ldg(rstd + g * 8 + q) : 1.f;
+      fsc[q] = fwd_scale ? __ldg(fwd_scale + g * 8 + q) : 1.f;
+      fsh[q] = fwd_scale ? __ldg(fwd_shift + g * 8 + q) : 0.f;
     }
 #pragma unroll 4
     for (long long p = p0 + lane; p < p1; p += lanes) {
@@ -111,7 +119,11 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(BV4 dz, BV4 
       }
       float d[8], xv[8];
       bload8(static_cast<const T*>(dz.ptr) + o_dz, d);
-      if (act != PMOE_ACT_NONE) {
+      if (fwd_scale) {
+        bload8(static_cast<const T*>(x.ptr) + o_x, xv);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) d[q] *= act_grad_pre(fmaf(xv[q], fsc[q], fsh[q]), act);
+      } else if (act != PMOE_ACT_NONE) {
         float zv[8];
         bload8(static_cast<const T*>(z.ptr) + o_z, zv);
         if (act == PMOE_ACT_RELU) {  // uniform branch hoisted out of the element loop (a per-element switch is ~10x the code)
@@ -124,8 +136,8 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(BV4 dz, BV4 
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) a[q] += d[q];
-      if (x.ptr) {
-        bload8(static_cast<const T*>(x.ptr) + o_x, xv);
+      if (x.ptr && sum_dy_xhat) {
+        if (!fwd_scale) bload8(static_cast<const T*>(x.ptr) + o_x, xv);
 #pragma unroll
         for (int q = 0; q < 8; ++q) b[q] += d[q] * (xv[q] - m[q]) * r[q];
       }
@@ -172,7 +184,8 @@ template <typename T, bool FLAT>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BV4 dz, BV4 z, BV4 x, int act, const float* __restrict__ mean,
                                     const float* __restrict__ rstd, const float* __restrict__ gamma,
                                     const double* __restrict__ sum_dy, const double* __restrict__ sum_dy_xhat, float inv_n,
-                                    int batch_stats, BV4 dx, BV4 dres, int accumulate_dres, ParamGrads pg) {
+                                    int batch_stats, BV4 dx, BV4 dres, int accumulate_dres, ParamGrads pg,
+                                    const float* __restrict__ fwd_scale, const float* __restrict__ fwd_shift) {
   if (batch_stats) write_param_grads(pg, sum_dy, sum_dy_xhat);
   const int cg = dz.c / 8;
   const long long total = (long long)dz.n * dz.h * dz.w * cg;
@@ -214,7 +227,13 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BV4 dz, BV4 z, BV4 x,
     }
     float d[8];
     bload8(static_cast<const T*>(dz.ptr) + o_dz, d);
-    if (act != PMOE_ACT_NONE) {
+    if (fwd_scale) {  // derivative at the pre-activation recomputed from x (see bn_bwd_reduce_kernel)
+      float xp[8];
+      bload8(static_cast<const T*>(x.ptr) + o_x, xp);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        d[q] *= act_grad_pre(fmaf(xp[q], __ldg(fwd_scale + g * 8 + q), __ldg(fwd_shift + g * 8 + q)), act);
+    } else if (act != PMOE_ACT_NONE) {
       float zv[8];
       bload8(static_cast<const T*>(z.ptr) + o_z, zv);
       if (act == PMOE_ACT_RELU) {
@@ -954,6 +973,10 @@ static int chk(const PmoeView4* v, int dtype, const char* what, bool optional = 
 
 using namespace pmoe;
 
+static inline bool host_piecewise(int act) {
+  return act == PMOE_ACT_RELU || act == PMOE_ACT_RELU6 || act == PMOE_ACT_HSWISH || act == PMOE_ACT_HSIGMOID;
+}
+
 #define BW_DISPATCH(dtype, ...)                      \
   if ((dtype) == PMOE_BF16) {                        \
     using T = __nv_bfloat16;                         \
@@ -973,13 +996,15 @@ int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4*
                        const float* fwd_shift, pmoe_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   int rc;
-  // mask_x: no saved output given; the ReLU mask is recomputed from x with the forward's scale/shift
-  const bool mask_x = act == PMOE_ACT_RELU && (!z || !z->ptr) && x && x->ptr && fwd_scale && fwd_shift;
+  // pre_x: no saved output given; the activation's derivative is taken at the pre-activation recomputed from x with the forward's
+  // scale/shift (ReLU / ReLU6 / Hardswish / Hardsigmoid). mask_x: its dense-bf16 ReLU form (fast kernels)
+  const bool pre_x = host_piecewise(act) && (!z || !z->ptr) && x && x->ptr && fwd_scale && fwd_shift;
+  const bool mask_x = pre_x && act == PMOE_ACT_RELU;
   if ((rc = chk(dz, dtype, "bn_bwd_reduce dz"))) return rc;
-  if ((rc = chk(z, dtype, "bn_bwd_reduce z", act == PMOE_ACT_NONE || mask_x))) return rc;
+  if ((rc = chk(z, dtype, "bn_bwd_reduce z", act == PMOE_ACT_NONE || pre_x))) return rc;
   if ((rc = chk(x, dtype, "bn_bwd_reduce x", true))) return rc;
   const int cg = dz->c / 8;
-  if (!sum_dy || cg > 256 || (act != PMOE_ACT_NONE && !mask_x && (!z || !z->ptr))) {
+  if (!sum_dy || cg > 256 || (act != PMOE_ACT_NONE && !pre_x && (!z || !z->ptr)) || (act == PMOE_ACT_HSWISH && !pre_x)) {
     set_error("bn_bwd_reduce: bad arguments");
     return PMOE_ERR_ARG;
   }
@@ -1006,14 +1031,12 @@ int pmoe_bn_bwd_reduce(const PmoeView4* dz, const PmoeView4* z, const PmoeView4*
 #undef PMOE_RED_FAST
     return check_launch("bn_bwd_reduce");
   }
-  if (mask_x) {
-    set_error("bn_bwd_reduce: the mask-from-x form needs contiguous bf16 tensors");
-    return PMOE_ERR_UNSUPPORTED;
-  }
+  const float* gsc = pre_x ? fwd_scale : nullptr;
+  const float* gsh = pre_x ? fwd_shift : nullptr;
   if (flat) {
-    BW_DISPATCH(dtype, (bn_bwd_reduce_kernel<T, true><<<(unsigned)blocks, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, sum_dy, sum_dy_xhat, ppb)));
+    BW_DISPATCH(dtype, (bn_bwd_reduce_kernel<T, true><<<(unsigned)blocks, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, sum_dy, sum_dy_xhat, ppb, gsc, gsh)));
   } else {
-    BW_DISPATCH(dtype, (bn_bwd_reduce_kernel<T, false><<<(unsigned)blocks, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, sum_dy, sum_dy_xhat, ppb)));
+    BW_DISPATCH(dtype, (bn_bwd_reduce_kernel<T, false><<<(unsigned)blocks, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, sum_dy, sum_dy_xhat, ppb, gsc, gsh)));
   }
   return check_launch("bn_bwd_reduce");
 }
@@ -1036,9 +1059,14 @@ static int bn_bwd_apply_impl(const PmoeView4* dz, const PmoeView4* z, const Pmoe
     pg.n = pgrads->n;
     pg.accumulate = pgrads->accumulate;
   }
-  const bool mask_x = act == PMOE_ACT_RELU && (!z || !z->ptr) && x && x->ptr && fwd_scale && fwd_shift;
+  const bool pre_x = host_piecewise(act) && (!z || !z->ptr) && x && x->ptr && fwd_scale && fwd_shift;
+  const bool mask_x = pre_x && act == PMOE_ACT_RELU;
   if ((rc = chk(dz, dtype, "bn_bwd_apply dz"))) return rc;
-  if ((rc = chk(z, dtype, "bn_bwd_apply z", act == PMOE_ACT_NONE || mask_x))) return rc;
+  if ((rc = chk(z, dtype, "bn_bwd_apply z", act == PMOE_ACT_NONE || pre_x))) return rc;
+  if (act == PMOE_ACT_HSWISH && !pre_x) {
+    set_error("bn_bwd_apply: Hardswish needs the layer input x and the forward affine (its output does not determine the pre-activation)");
+    return PMOE_ERR_ARG;
+  }
   if ((rc = chk(x, dtype, "bn_bwd_apply x", !batch_stats))) return rc;
   if ((rc = chk(dx, dtype, "bn_bwd_apply dx", true))) return rc;
   if ((rc = chk(dres, dtype, "bn_bwd_apply dres", true))) return rc;
@@ -1079,14 +1107,16 @@ static int bn_bwd_apply_impl(const PmoeView4* dz, const PmoeView4* z, const Pmoe
 #undef PMOE_APPLY_FAST
     return check_launch("bn_bwd_apply");
   }
-  if (mask_x || next_s1) {
-    set_error("bn_bwd_apply: the mask-from-x and fused-sums forms need contiguous bf16 tensors");
+  if (next_s1) {
+    set_error("bn_bwd_apply: the fused-sums form needs contiguous bf16 tensors");
     return PMOE_ERR_UNSUPPORTED;
   }
+  const float* gsc = pre_x ? fwd_scale : nullptr;
+  const float* gsh = pre_x ? fwd_shift : nullptr;
   if (flat_all) {
-    BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T, true><<<grid, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres, pg)));
+    BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T, true><<<grid, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres, pg, gsc, gsh)));
   } else {
-    BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T, false><<<grid, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres, pg)));
+    BW_DISPATCH(dtype, (bn_bwd_apply_kernel<T, false><<<grid, 256, 0, stream>>>(bv4(dz), bv4(z), bv4(x), act, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, batch_stats, bv4(dx), bv4(dres), accumulate_dres, pg, gsc, gsh)));
   }
   return check_launch("bn_bwd_apply");
 }

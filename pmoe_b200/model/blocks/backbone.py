@@ -3,8 +3,8 @@
 `resnet18` is the conf default (conf/stage_2.yaml:111); `resnet34` (BasicBlock, [3,4,6,3]) and `resnet50` (Bottleneck,
 [3,4,6,3], fc := Linear(2048, 512)) are the other ResNets `_get_resnet` accepts. The modules reproduce torchvision's
 state_dict keys with `conv1` replaced by an EfficientConvBlock and `fc` by Identity / Linear, so reference checkpoints load
-with strict=True. `get_unet` builds the 'segmentation' backbone (entry block + U-Net). The mobilenet family (depthwise convolutions,
-hard-swish, squeeze-excite) is not built yet: `get_backbone` raises for it.
+with strict=True. `get_unet` builds the 'segmentation' backbone (entry block + U-Net). The mobilenet family (`_get_mobilenet`,
+backbone.py:75-104: depthwise convolutions, ReLU6 / Hardswish / Hardsigmoid, squeeze-excite) lives in `mobilenet.py`.
 """
 import torch
 import torch.nn as nn
@@ -84,8 +84,14 @@ class ResNet18ECA(nn.Module):
 
 def get_backbone(arch: str = "resnet18", n_frames: int = 4, pretrained: bool = False, gamma: int = 2, b: int = 1,
                  n_channels: int = 3):
-    if arch.lower() not in _ARCH:
-        raise NotImplementedError("pmoe_b200 get_backbone: resnet18 / resnet34 / resnet50 run on the B200 kernels; got %r" % arch)
+    if "resnet" in arch:           # backbone.py:21-25
+        key = arch.lower() if arch.lower() in _ARCH else "resnet18"   # backbone.py:57-61: unknown ResNet names fall back to resnet18
+    elif "mobilenet" in arch:
+        from .mobilenet import MobileNetECA
+        return MobileNetECA(arch.lower(), n_frames * n_channels, gamma, b, pretrained)
+    else:
+        return None                # the reference's factory falls through (and its callers then fail on None)
+    arch = key
     net = ResNet18ECA(n_frames * n_channels, gamma, b, arch.lower())
     if pretrained:
         _load_imagenet_weights(net, arch.lower())

@@ -130,14 +130,17 @@ def _run_experts(owner, experts, images, speed, command, alt, softmax=True):
                     train.seed_stacked(tp, sp, g[3])
             return [gm.probs, gm.mean, gm.std, speeds, gm.route], seed
         als, aps, sps = [], [], []
+        small = B * images.shape[-2] * images.shape[-1] <= train.MULTI_STREAM_MAX_PIXELS
         for k, ex in enumerate(experts):
-            fa = train.backbone_features(tape, ex.backbone, x, tag="moe.%d.backbone" % k)
-            sl = slice(k * 16, (k + 1) * 16)
-            al, ap, sp = train.expert_heads(tape, ex, fa, speed_a, cmd_a, alt, alpha_buf[..., sl], ap_buf[..., sl], sp_buf[..., sl],
-                                            tag="moe.%d" % k)
+            with tape.branch(k, enable=small and K > 1):   # encoder + heads of one expert: independent of the others up to the gating
+                fa = train.backbone_features(tape, ex.backbone, x, tag="moe.%d.backbone" % k)
+                sl = slice(k * 16, (k + 1) * 16)
+                al, ap, sp = train.expert_heads(tape, ex, fa, speed_a, cmd_a, alt, alpha_buf[..., sl], ap_buf[..., sl], sp_buf[..., sl],
+                                                tag="moe.%d" % k)
             als.append(al)
             aps.append(ap)
             sps.append(sp)
+        tape.join()
         gm = train.GateMixture(tape, als, aps, alpha_buf, ap_buf, B, K, relu_alpha=not alt, a_sk=16, p_sk=16)
         speeds = sp_buf.view(B, K, 16)[:, :, :1].float()
 
@@ -251,9 +254,12 @@ class PUNetExpert(nn.Module):
             else:
                 P, Fu, slot, ncls = r["P"], r["F"], r["slot"], r["ncls"]
                 fut = train.ring_window(tape, r["ring"], r["futures"], P * slot, slot, ncls)
-                stem = train.eca_conv_block(tape, self.backbone.conv1, fut, (Fu, ncls, slot), r["pools"][:, P * slot:(P + Fu) * slot],
-                                            tag="backbone.conv1")
-                img = train.backbone_head(tape, self.backbone, train.resnet18_after_stem(tape, self.backbone, stem))
+                if hasattr(self.backbone, "tape_features"):   # MobileNet family
+                    img = self.backbone.tape_features(tape, fut, "backbone", (Fu, ncls, slot), r["pools"][:, P * slot:(P + Fu) * slot])
+                else:
+                    stem = train.eca_conv_block(tape, self.backbone.conv1, fut, (Fu, ncls, slot), r["pools"][:, P * slot:(P + Fu) * slot],
+                                                tag="backbone.conv1", want_out_stats=self.backbone.bn1.training)
+                    img = train.backbone_head(tape, self.backbone, train.resnet18_after_stem(tape, self.backbone, stem))
             feats = [img, s, c]
             af = train.mlp(tape, self.action_pred[0], feats, "action_pred.0")
             act = train.linear_op(tape, [af], self.action_pred[1], "tanh", tag="action_pred.1")

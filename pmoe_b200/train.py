@@ -261,10 +261,20 @@ def _mask_from_x(dz, x, act, fwd):
             and x.is_contiguous() and x.shape == dz.shape)
 
 
+PRE_ACTS = ("hswish",)                       # activations whose derivative is not a function of their output
+_PIECEWISE = ("relu6", "hswish", "hsigmoid")  # ... and those whose derivative the kernels can take at the recomputed pre-activation
+
+
+def _pre_from_x(x, act, fwd):
+    """MobileNet activations: derivative at the pre-activation fwd_scale*x + fwd_shift recomputed from the layer input (generic
+    kernels, any dtype / strides); the saved output is then not read."""
+    return fwd is not None and x is not None and act in _PIECEWISE
+
+
 def _bn_bwd_reduce(tape, dz, z, x, act, mean, rstd, cpad, fwd=None):
     s1 = tape.zeros(cpad, torch.float64, dz.device)
     s2 = tape.zeros(cpad, torch.float64, dz.device) if x is not None else None
-    mx = _mask_from_x(dz, x, act, fwd)
+    mx = _mask_from_x(dz, x, act, fwd) or _pre_from_x(x, act, fwd)
     vdz = view4(dz)
     vz = view4(z) if (z is not None and not mx) else _lib.null_view()
     vx = view4(x) if x is not None else _lib.null_view()
@@ -301,7 +311,8 @@ def _bn_bwd_apply_sums(tape, dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, dx
 
 
 def _bn_bwd_apply(dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, batch_stats, dx, dres, acc_dres, fwd=None, pgrads=None):
-    mx = _mask_from_x(dz, x, act, fwd) and (dx is None or dx.is_contiguous()) and (dres is None or dres.is_contiguous())
+    mx = (_mask_from_x(dz, x, act, fwd) and (dx is None or dx.is_contiguous()) and (dres is None or dres.is_contiguous())) \
+        or _pre_from_x(x, act, fwd)
     vdz = view4(dz)
     vz = view4(z) if (z is not None and not mx) else _lib.null_view()
     vx = view4(x) if x is not None else _lib.null_view()
@@ -560,6 +571,13 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
     (batch statistics when bn.training, folded running statistics otherwise), optional residual add and activation.
     Returns (Act z, pool_sum or None)."""
     dt = tape.dtype
+    if act in PRE_ACTS and tape.save and not (bn is not None and bn.training):
+        y, _ = conv_op(tape, srcs, weight, bias, bn, None, residual, False, ksize, layouts, segdefs, None, None, 0, out_hw, tag, False, stride2_of)
+        z = act_op(tape, y, act, tag)
+        pool = None
+        if want_pool:
+            pool = nhwc.channel_sums(z.t, out=pool_out) if pool_out is not None else nhwc.channel_sums(z.t)
+        return z, pool
     if not isinstance(srcs[0], Src):
         srcs = concat_sources(srcs, layouts)
     dev = srcs[0].t.device
@@ -684,6 +702,143 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
     tape.expect(_owner(weight))
     tape.record(backward)
     return z, pool
+
+
+def act_op(tape, x, act, tag=""):
+    """Stand-alone activation (Hardswish after a Linear / an eval-mode conv): y = act(x); backward at the pre-activation x."""
+    dev = x.t.device
+    cp = x.cpad
+    ones = torch.ones(cp, dtype=torch.float32, device=dev)
+    zeros = torch.zeros(cp, dtype=torch.float32, device=dev)
+    y = nhwc.affine_act(x.t, ones, zeros, act)
+    ya = _new_act(tape, y, x.c, _rg(x))
+    if tape.save and _rg(x):
+        def backward():
+            dz = tape.grad_of(ya)
+            if dz is None:
+                return
+            g, existed = _grad_buffer(tape, x)
+            tmp = g if not existed else torch.empty_like(g)
+            _bn_bwd_apply(dz, None if act in _PIECEWISE else y, x.t, act, None, None, None, None, None, 0.0, 0, tmp, None, False,
+                          fwd=(ones, zeros))
+            if existed:
+                _axpy(tmp, g, 1.0, None, True)
+        tape.record(backward)
+    return ya
+
+
+def dwconv_op(tape, x, conv, bn, act, tag=""):
+    """Depthwise nn.Conv2d(c, c, k, stride, (k-1)//2, groups=c, bias=False) + BatchNorm2d + activation: the middle layer of
+    torchvision's MobileNetV2 / V3 InvertedResidual (backbone.py:75-104). Returns the Act."""
+    dt, dev = tape.dtype, x.t.device
+    k, stride, pad = int(conv.kernel_size[0]), int(conv.stride[0]), int(conv.padding[0])
+    if conv.groups != conv.in_channels or conv.in_channels != conv.out_channels or conv.bias is not None or conv.dilation[0] != 1:
+        raise RuntimeError("pmoe_b200 dwconv_op: depthwise, bias-free, undilated convolutions only (got %r)" % (conv,))
+    c, cp = x.c, x.cpad
+    n, h, w, _ = x.t.shape
+    oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    weight = conv.weight
+
+    def build(wf):   # (c, 1, k, k) -> [k*k][cp], tap-major
+        return torch.nn.functional.pad(wf[:, 0].permute(1, 2, 0).reshape(k * k, c), (0, cp - c))
+    wpk, went = packs.packed(weight, "dw|%d|%d" % (k, cp), weight.shape, build, torch.float32)
+    raw = torch.empty(n, oh, ow, cp, dtype=dt, device=dev)
+    vx, vr = view4(x.t), view4(raw)
+    io_b = (x.t, raw)
+    check(profiler.launch("dwconv", lambda: lib().pmoe_dwconv_fwd(C.byref(vx), wpk.data_ptr(), cp, C.byref(vr), dtype_code(raw), k, stride, pad,
+                                                                   stream_ptr()), io=io_b), "dwconv_fwd")
+    bn_train = bn is not None and bn.training
+    rg = _rg(x) or weight.requires_grad or (bn is not None and _any_rg([bn.weight, bn.bias]))
+    mean = rstd = gamma_p = fwd_aff = scale = shift = None
+    if bn_train:
+        ssum, ssq = tape.zeros(cp, torch.float64, dev), tape.zeros(cp, torch.float64, dev)
+        check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(vr), dtype_code(raw), ssum.data_ptr(), ssq.data_ptr(),
+                                                                                stream_ptr()), io=(raw,)), "channel_stats")
+        z_t, mean, rstd, fwd_aff = _bn_tail_forward(tape, bn, raw, ssum, ssq, n * oh * ow, c, cp, act, None, None)
+        gamma_p = _padded_gamma(bn, cp)
+    else:
+        scale, shift = _eval_affine(bn, None, c, cp)
+        if scale is None:
+            scale = torch.ones(cp, dtype=torch.float32, device=dev)
+            shift = torch.zeros(cp, dtype=torch.float32, device=dev)
+        z_t = nhwc.affine_act(raw, scale, shift, act)
+    z = _new_act(tape, z_t, c, rg)
+    if not (tape.save and rg):
+        return z
+
+    def backward():
+        dz = tape.grad_of(z)
+        if dz is None:
+            return
+        z_saved = z_t if act not in (None, "none") else None
+        dy = torch.empty(n, oh, ow, cp, dtype=dt, device=dev)
+        if bn_train:
+            s1, s2 = _bn_bwd_reduce(tape, dz, z_saved, raw, act, mean, rstd, cp, fwd=fwd_aff)
+            pg, pdone = _bn_pgrads(tape, bn, c)
+            _bn_bwd_apply(dz, z_saved, raw, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * oh * ow), 1, dy, None, False, fwd=fwd_aff, pgrads=pg)
+            for prm in pdone:
+                tape.pgrad_done(prm)
+        else:
+            if bn is not None and _any_rg([bn.weight, bn.bias]):
+                raise NotImplementedError("pmoe_b200: gradients of BatchNorm affine parameters in eval mode are not supported")
+            pre = act in _PIECEWISE
+            _bn_bwd_apply(dz, None if pre else z_saved, raw if pre else None, act, None, None, scale[:cp].contiguous(), None, None, 0.0, 0,
+                          dy, None, False, fwd=(scale, shift) if pre else None)
+        vdy = view4(dy)
+        if weight.requires_grad:
+            dwp = tape.zeros((k * k, cp), torch.float32, dev)
+            check(profiler.launch("dwconv_wgrad", lambda: lib().pmoe_dwconv_wgrad(C.byref(vx), C.byref(vdy), dwp.data_ptr(), cp, dtype_code(dy), k,
+                                                                                 stride, pad, stream_ptr()), io=(x.t, dy)), "dwconv_wgrad")
+            _wgrad_to_param(tape, dwp, went, weight)
+        if _rg(x):
+            g, existed = _grad_buffer(tape, x)
+            vg = view4(g)
+            check(profiler.launch("dwconv_dgrad", lambda: lib().pmoe_dwconv_dgrad(C.byref(vdy), wpk.data_ptr(), cp, C.byref(vg), dtype_code(g), k,
+                                                                                 stride, pad, int(existed), stream_ptr()),
+                                  io=(dy, g, g if existed else None)), "dwconv_dgrad")
+
+    if bn_train:
+        tape.expect(bn.weight, bn.bias)
+    tape.expect(weight)
+    tape.record(backward)
+    return z
+
+
+def se_op(tape, se, x, tag=""):
+    """torchvision SqueezeExcitation (MobileNetV3): x * hardsigmoid(fc2(relu(fc1(avgpool(x))))), fc1 / fc2 = 1x1 Conv2d with bias.
+    The two small linears run on the tape as 1x1 convs over the pooled (1,1,N,C) vector; the gate scales x per (n, c)."""
+    n, h, w, cp = x.t.shape
+    sums = nhwc.channel_sums(x.t)
+    inter = InterRepr(tape, x, sums)
+    a = feature_act(tape, inter)
+    hid, _ = conv_op(tape, [a], se.fc1.weight, se.fc1.bias, None, "relu", ksize=1, tag=tag + ".fc1")
+    gact, _ = conv_op(tape, [hid], se.fc2.weight, se.fc2.bias, None, "hsigmoid", ksize=1, tag=tag + ".fc2")
+    gate = gact.t.view(n, gact.cpad).float()
+    if gact.cpad != cp:
+        raise RuntimeError("pmoe_b200 se_op: gate / activation channel padding mismatch (%d vs %d)" % (gact.cpad, cp))
+    y = nhwc.scale_channels(x.t, gate)
+    rg = _rg(x) or _rg(gact)
+    ya = _new_act(tape, y, x.c, rg)
+    if tape.save and rg:
+        def backward():
+            dy = tape.grad_of(ya)
+            if dy is None:
+                return
+            if _rg(gact):   # d gate[n, c] = sum over pixels of dy * x
+                dgate = tape.zeros((n, cp), torch.float64, dy.device)
+                va, vb = view4(dy), view4(x.t)
+                check(profiler.launch("prod_channel_sums", lambda: lib().pmoe_prod_channel_sums(
+                    C.byref(va), C.byref(vb), dtype_code(dy), dgate.data_ptr(), dgate.stride(0), stream_ptr()), io=(dy, x.t)), "prod_channel_sums")
+                seed_vec(tape, gact, dgate[:, :gact.c].float())
+            if _rg(x):
+                g, existed = _grad_buffer(tape, x)
+                if existed:
+                    tmp = nhwc.scale_channels(dy, gate)
+                    _axpy(tmp, g, 1.0, None, True)
+                else:
+                    nhwc.scale_channels(dy, gate, out=g)
+        tape.record(backward)
+    return ya
 
 
 def maxpool_op(tape, x, k, stride, pad):
@@ -1066,6 +1221,8 @@ def backbone_head(tape, net, inter, tag="backbone"):
 
 
 def backbone_features(tape, net, x, tag="backbone"):
+    if hasattr(net, "tape_features"):   # MobileNetECA walks its own (torchvision) module tree
+        return net.tape_features(tape, x, tag)
     return backbone_head(tape, net, resnet18_eca(tape, net, x, tag), tag)
 
 

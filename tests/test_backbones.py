@@ -133,8 +133,8 @@ def test_oracle_mobilenets_vs_live_reference(arch):
     (17 inverted-residual blocks, depthwise 3x3, ReLU6, Linear(1280, 512)) and MobileNetV3-Small / -Large (Small is the arch the factory falls back
     to: depthwise 3x3/5x5, squeeze-excite, Hardswish / Hardsigmoid, BN eps 1e-3 / momentum 0.01, Linear(576,1024)+Linear(1024,512)),
     both with the stride-1 ECA stem — against the live reference: state_dict keys/shapes, eval and train features, every gradient
-    norm, BatchNorm running statistics. The PRODUCT does not build this family yet: `get_backbone` must keep failing loudly
-    rather than fall back to anything."""
+    norm, BatchNorm running statistics; and the product's `get_backbone` builds a module with the same state_dict (its forward /
+    backward on the GPU kernels: tests/test_gpu_mobilenet.py)."""
     g = _load(arch)
     spec_fn, fwd = {"mobilenet_v2": (O.mobilenet_v2_spec, O.mobilenet_v2_eca),
                     "mobilenet_v3_small": (O.mobilenet_v3_small_spec, O.mobilenet_v3_small_eca),
@@ -154,6 +154,9 @@ def test_oracle_mobilenets_vs_live_reference(arch):
     assert worst < 2e-3, worst
     for k, v in g["bn"].items():
         assert _rel(leaf[k].float(), v.float()) < 1e-5
+    # the product's module tree (torchvision's, with the ECA stem and the 512-wide head) carries exactly the reference's state_dict
     from pmoe_b200.model.blocks.backbone import get_backbone
-    with pytest.raises(NotImplementedError):
-        get_backbone(arch=arch, n_frames=4)
+    net = get_backbone(arch=arch, n_frames=4)
+    mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert list(mine) == list(g["keys"]) and all(mine[k] == tuple(g["keys"][k]) for k in mine)
+    net.load_state_dict(sd, strict=True)

@@ -36,35 +36,62 @@ def _step(model, cfg, d):
         {k: v.clone() for k, v in model.state_dict().items() if "running" in k}
 
 
-def test_multi_stream_experts_match_single_stream():
-    from pmoe_b200 import train
-    cfg, model0, d = _case()
+def _runs(prec, HW):
+    from pmoe_b200 import config, train
+    cfg, model0, d = _case(HW=HW)
     runs = {}
-    for tag, ms in (("single", False), ("multi", True), ("multi2", True), ("multi3", True)):
-        old = train.MULTI_STREAM
-        train.MULTI_STREAM = ms
-        try:
-            runs[tag] = _step(copy.deepcopy(model0).to(dev).train(), cfg, d)
-        finally:
-            train.MULTI_STREAM = old
+    with config.use_precision(prec):
+        for tag, ms in (("single", False), ("single2", False), ("multi", True), ("multi2", True), ("multi3", True)):
+            old = train.MULTI_STREAM
+            train.MULTI_STREAM = ms
+            try:
+                runs[tag] = _step(copy.deepcopy(model0).to(dev).train(), cfg, d)
+            finally:
+                train.MULTI_STREAM = old
+    return runs
+
+
+def _median_worst(ga, gb):
+    errs = sorted(rel_err(ga[n], gb[n]) for n in gb)
+    return errs[len(errs) // 2], errs[-1]
+
+
+def test_multi_stream_experts_match_single_stream_fp32():
+    """fp32 parity mode (CUDA-core kernels, per-expert heads): the step is reproducible to ~1e-6, so a missing cross-stream
+    dependency cannot hide behind rounding noise — every gradient of the multi-stream tape equals the single-stream one."""
+    runs = _runs("fp32", 64)
     l0, g0, bn0 = runs["single"]
+    base = _median_worst(runs["single2"][1], g0)
     for tag in ("multi", "multi2", "multi3"):
         l1, g1, bn1 = runs[tag]
-        worst = max(rel_err(g1[n], g0[n]) for n in g0)
+        med, worst = _median_worst(g1, g0)
         bn = max(rel_err(bn1[k].float(), bn0[k].float()) for k in bn0)
-        print("\n[%s vs single stream] loss %.6f vs %.6f | worst gradient rel %.3e | BN statistics rel %.3e" % (tag, l1, l0, worst, bn))
+        print("\n[fp32 %s vs single stream] loss %.7f vs %.7f | gradients median %.2e worst %.2e (single vs single: %.2e / %.2e) | BN statistics %.2e"
+              % (tag, l1, l0, med, worst, base[0], base[1], bn))
+        assert abs(l1 - l0) < 1e-5 * max(1.0, abs(l0)) and bn < 1e-5
+        assert med < max(1e-4, 10 * base[0]) and worst < max(5e-2, 10 * base[1])   # worst: a ReLU mask flipped by summation order (see test_gpu_moe.py)
+
+
+def test_multi_stream_experts_match_single_stream_bf16():
+    """bf16 tensor-core path (grouped heads): compared at the run-to-run noise of the single-stream tape itself (the order of the
+    fp32 atomics of the ECA pool sums moves single bf16 ulps, which train-mode BatchNorm at random init amplifies)."""
+    runs = _runs("bf16", 128)
+    l0, g0, bn0 = runs["single"]
+    base = _median_worst(runs["single2"][1], g0)
+    for tag in ("multi", "multi2", "multi3"):
+        l1, g1, bn1 = runs[tag]
+        med, worst = _median_worst(g1, g0)
+        print("\n[bf16 %s vs single stream] loss %.6f vs %.6f | gradients median %.2e worst %.2e (single vs single: %.2e / %.2e)"
+              % (tag, l1, l0, med, worst, base[0], base[1]))
         assert all(torch.isfinite(v).all() for v in g1.values())
         assert abs(l1 - l0) < 1e-3 * max(1.0, abs(l0))
-        assert bn < 1e-4            # forward statistics: identical up to atomic order
-        assert worst < 1e-1         # bf16 gradients move by a few 1e-2 with the order of the fp32 atomics alone (B = 8 at random init)
-    # run-to-run agreement of the multi-stream tape is as good as single-vs-multi (no race)
-    assert max(rel_err(runs["multi2"][1][n], runs["multi"][1][n]) for n in g0) < 1e-1
+        assert med < max(2e-2, 3 * base[0])
 
 
 def test_multi_stream_branches_inside_a_captured_graph():
     from pmoe_b200 import loss as L, train
     assert train.MULTI_STREAM
-    cfg, model0, d = _case()
+    cfg, model0, d = _case(HW=128)
     torch.distributions.Distribution.set_default_validate_args(False)
     try:
         model = copy.deepcopy(model0).to(dev).train()
@@ -94,8 +121,8 @@ def test_multi_stream_branches_inside_a_captured_graph():
             torch._foreach_zero_([p.grad for p in model.parameters()])
             graph.replay()
             torch.cuda.synchronize()
-            worst = max(rel_err(p.grad, g_eager[n]) for n, p in model.named_parameters())
-            print("\n[graph replay %d, multi-stream] loss %.6f vs eager %.6f | worst gradient rel %.3e" % (rep, static_loss.item(), l_eager, worst))
-            assert abs(static_loss.item() - l_eager) < 1e-3 * max(1.0, abs(l_eager)) and worst < 1e-1
+            med, worst = _median_worst({n: p.grad for n, p in model.named_parameters()}, g_eager)
+            print("\n[graph replay %d, multi-stream] loss %.6f vs eager %.6f | gradients median %.2e worst %.2e" % (rep, static_loss.item(), l_eager, med, worst))
+            assert abs(static_loss.item() - l_eager) < 1e-3 * max(1.0, abs(l_eager)) and med < 5e-2
     finally:
         torch.distributions.Distribution.set_default_validate_args(True)

@@ -56,12 +56,59 @@ def _st(x):
     return x if STORE is None else STORE(x)
 
 
+class _BnStored(torch.autograd.Function):
+    """conv output -> train-mode BatchNorm under bf16 storage, forward and backward as the product's kernels compute them: batch
+    statistics of the UNROUNDED fp32 accumulators (conv epilogue), normalisation of the STORED (rounded) tensor r with them;
+    backward by the standard formula on xhat = (r - mean) * rstd, the resulting gradient of the conv output stored in bf16."""
+
+    @staticmethod
+    def forward(ctx, src, weight, bias, eps):
+        dims = [d for d in range(src.dim()) if d != 1]
+        shape = [1, -1] + [1] * (src.dim() - 2)
+        mean, var = src.mean(dim=dims), src.var(dim=dims, unbiased=False)
+        rstd = torch.rsqrt(var + eps)
+        r = src.to(torch.bfloat16).to(src.dtype)
+        xhat = (r - mean.view(shape)) * rstd.view(shape)
+        ctx.save_for_backward(xhat, weight, rstd)
+        ctx.dims, ctx.shape = dims, shape
+        return xhat * weight.view(shape) + bias.view(shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        xhat, weight, rstd = ctx.saved_tensors
+        dims, shape = ctx.dims, ctx.shape
+        s1, s2 = g.sum(dim=dims), (g * xhat).sum(dim=dims)
+        n = g.numel() / g.shape[1]
+        dx = (weight * rstd).view(shape) * (g - (s1 / n).view(shape) - xhat * (s2 / n).view(shape))
+        return dx.to(torch.bfloat16).to(g.dtype), s2, s1, None
+
+
+def _stc(x):
+    """A stored convolution output. The product takes the train-mode BatchNorm statistics of a conv output from the fp32
+    accumulators (conv epilogue) and normalises the STORED, rounded tensor with them; the rounded tensor therefore carries its
+    unrounded source along for `batchnorm` (a 1.5e-3 difference in the normalised output otherwise)."""
+    if STORE is None:
+        return x
+    y = STORE(x)
+    y._pmoe_unrounded = x
+    return y
+
+
 # ------------------------------------------------------------------ blocks (model/blocks/basics.py)
 def batchnorm(x, sd, p, train, eps=BN_EPS, momentum=BN_MOMENTUM):
     """nn.BatchNorm{1,2}d defaults as instantiated at basics.py:34,52,55,103,124 (torchvision's MobileNetV3 passes its own
     eps / momentum)."""
     if train and p + "num_batches_tracked" in sd:
         sd[p + "num_batches_tracked"] += 1
+    src = getattr(x, "_pmoe_unrounded", None)
+    if train and STORE is not None and src is not None:
+        # storage emulation of conv -> train-mode BatchNorm exactly as the product computes it (see _BnStored)
+        with torch.no_grad():
+            dims = [d for d in range(src.dim()) if d != 1]
+            n = src.numel() / src.shape[1]
+            sd[p + "running_mean"].mul_(1 - momentum).add_(momentum * src.mean(dim=dims))
+            sd[p + "running_var"].mul_(1 - momentum).add_(momentum * src.var(dim=dims, unbiased=False) * n / max(n - 1, 1))
+        return _BnStored.apply(src, sd[p + "weight"], sd[p + "bias"], eps)
     return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
                         train, momentum, eps)
 
@@ -69,7 +116,7 @@ def batchnorm(x, sd, p, train, eps=BN_EPS, momentum=BN_MOMENTUM):
 def conv3_block(x, sd, p, train, stride=1):
     """basics.py:48-59 — (conv3x3 no-bias, BN, ReLU) twice."""
     for a, b in (("0", "1"), ("3", "4")):
-        x = _st(F.conv2d(x, sd[p + a + ".weight"], None, stride, 1))
+        x = _stc(F.conv2d(x, sd[p + a + ".weight"], None, stride, 1))
         x = _st(torch.relu(batchnorm(x, sd, p + b + ".", train)))
     return x
 
@@ -91,10 +138,10 @@ def eca(x, w):
 def eca_conv_block(x, sd, p, train, stride=1):
     """basics.py:80-135 — EfficientConvBlock."""
     x = eca(x, sd[p + "layer1.eca1.conv.weight"])
-    x = _st(F.conv2d(x, sd[p + "layer1.conv1.0.weight"], None, stride, 1))
+    x = _stc(F.conv2d(x, sd[p + "layer1.conv1.0.weight"], None, stride, 1))
     x = _st(torch.relu(batchnorm(x, sd, p + "layer1.conv1.1.", train)))
     x = eca(x, sd[p + "layer2.eca2.conv.weight"])
-    x = _st(F.conv2d(x, sd[p + "layer2.conv2.0.weight"], None, stride, 1))
+    x = _stc(F.conv2d(x, sd[p + "layer2.conv2.0.weight"], None, stride, 1))
     return _st(torch.relu(batchnorm(x, sd, p + "layer2.conv2.1.", train)))
 
 
@@ -156,7 +203,7 @@ def unet(x, sd, p, train, inter_repr=False):
             up = F.conv_transpose2d(y, sd[p + "up_%d.weight" % i], sd[p + "up_%d.bias" % i], stride=2,
                                     output_padding=(dh, dw))
         y = conv3_block(torch.cat([skip, up], 1), sd, p + "up_forw_%d." % i, train)  # skip first (unet.py:73)
-    out = _st(F.conv2d(y, sd[p + "out.weight"], sd[p + "out.bias"]))
+    out = _stc(F.conv2d(y, sd[p + "out.weight"], sd[p + "out.bias"]))
     if inter_repr:
         return x5.mean(dim=(2, 3)), out
     return out
@@ -201,16 +248,16 @@ def resnet_eca(x, sd, p, train, arch="resnet18"):
             s = stride if bi == 0 else 1
             idt = x
             if kind == "basic":
-                y = _st(F.conv2d(x, sd[q + "conv1.weight"], None, s, 1))
+                y = _stc(F.conv2d(x, sd[q + "conv1.weight"], None, s, 1))
                 y = _st(torch.relu(batchnorm(y, sd, q + "bn1.", train)))
-                y = _st(F.conv2d(y, sd[q + "conv2.weight"], None, 1, 1))
+                y = _stc(F.conv2d(y, sd[q + "conv2.weight"], None, 1, 1))
                 y = batchnorm(y, sd, q + "bn2.", train)   # the residual add + ReLU ride the same pass: one stored tensor
             else:
-                y = _st(torch.relu(batchnorm(_st(F.conv2d(x, sd[q + "conv1.weight"])), sd, q + "bn1.", train)))
-                y = _st(torch.relu(batchnorm(_st(F.conv2d(y, sd[q + "conv2.weight"], None, s, 1)), sd, q + "bn2.", train)))
-                y = batchnorm(_st(F.conv2d(y, sd[q + "conv3.weight"])), sd, q + "bn3.", train)
+                y = _st(torch.relu(batchnorm(_stc(F.conv2d(x, sd[q + "conv1.weight"])), sd, q + "bn1.", train)))
+                y = _st(torch.relu(batchnorm(_stc(F.conv2d(y, sd[q + "conv2.weight"], None, s, 1)), sd, q + "bn2.", train)))
+                y = batchnorm(_stc(F.conv2d(y, sd[q + "conv3.weight"])), sd, q + "bn3.", train)
             if q + "downsample.0.weight" in sd:
-                idt = _st(F.conv2d(x, sd[q + "downsample.0.weight"], None, s, 0))
+                idt = _stc(F.conv2d(x, sd[q + "downsample.0.weight"], None, s, 0))
                 idt = _st(batchnorm(idt, sd, q + "downsample.1.", train))
             x = _st(torch.relu(y + idt))
     x = _st(x.mean(dim=(2, 3)))

@@ -29,7 +29,7 @@ __device__ __forceinline__ float act_grad_pre(float u, int act) {
   switch (act) {
     case PMOE_ACT_RELU: return u > 0.f ? 1.f : 0.f;
     case PMOE_ACT_RELU6: return (u > 0.f && u < 6.f) ? 1.f : 0.f;
-    case PMOE_ACT_HSWISH: return u < -3.f ? 0.f : (u <= 3.f ? (2.f * u + 3.f) * (1.f / 6.f) : 1.f);
+    case PMOE_ACT_HSWISH: return u <= -3.f ? 0.f : (u < 3.f ? (2.f * u + 3.f) * (1.f / 6.f) : 1.f);  // open interval, as ATen's CUDA kernel
     case PMOE_ACT_HSIGMOID: return (u > -3.f && u < 3.f) ? (1.f / 6.f) : 0.f;
     default: return 1.f;
   }

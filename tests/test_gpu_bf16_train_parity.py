@@ -190,14 +190,14 @@ def _coherent_loss(y, target):
 def _basic_block_oracle(x, sd, p, train, stride):
     """torchvision BasicBlock (backbone.py:57-61 instantiates torchvision's ResNet): the lines of O.resnet_eca for one block."""
     import torch.nn.functional as F
-    st = O._st   # storage rounding points of the product (identity unless O.storage("bf16") is active)
-    y = st(F.conv2d(x, sd[p + "conv1.weight"], None, stride, 1))
+    st, stc = O._st, O._stc   # storage rounding points of the product (identity unless O.storage("bf16") is active)
+    y = stc(F.conv2d(x, sd[p + "conv1.weight"], None, stride, 1))
     y = st(torch.relu(O.batchnorm(y, sd, p + "bn1.", train)))
-    y = st(F.conv2d(y, sd[p + "conv2.weight"], None, 1, 1))
+    y = stc(F.conv2d(y, sd[p + "conv2.weight"], None, 1, 1))
     y = O.batchnorm(y, sd, p + "bn2.", train)
     idt = x
     if p + "downsample.0.weight" in sd:
-        idt = st(O.batchnorm(st(F.conv2d(x, sd[p + "downsample.0.weight"], None, stride, 0)), sd, p + "downsample.1.", train))
+        idt = st(O.batchnorm(stc(F.conv2d(x, sd[p + "downsample.0.weight"], None, stride, 0)), sd, p + "downsample.1.", train))
     return st(torch.relu(y + idt))
 
 

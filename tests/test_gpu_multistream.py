@@ -89,40 +89,49 @@ def test_multi_stream_experts_match_single_stream_bf16():
 
 
 def test_multi_stream_branches_inside_a_captured_graph():
-    from pmoe_b200 import loss as L, train
+    """fp32 parity mode, so that the replayed graph can be held to the eager single-stream step tightly: the side streams become
+    parallel branches of the captured graph and must rejoin it (capture would fail otherwise)."""
+    from pmoe_b200 import config, loss as L, train
     assert train.MULTI_STREAM
-    cfg, model0, d = _case(HW=128)
+    cfg, model0, d = _case(HW=64)
     torch.distributions.Distribution.set_default_validate_args(False)
     try:
-        model = copy.deepcopy(model0).to(dev).train()
+        with config.use_precision("fp32"):
+            old = train.MULTI_STREAM
+            train.MULTI_STREAM = False
+            try:
+                l_eager, g_eager, _ = _step(copy.deepcopy(model0).to(dev).train(), cfg, d)
+            finally:
+                train.MULTI_STREAM = old
+            model = copy.deepcopy(model0).to(dev).train()
 
-        def fwd_bwd():
-            dist_, sp = model(d["images"], d["speed"], d["command"])
-            loss = L.moe_loss(dist_, sp, d["control"], d["target"].clone(), cfg.loss_coefs)
-            loss.backward()
-            return loss
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                for p in model.parameters():
-                    p.grad = None
-                fwd_bwd()
-        torch.cuda.current_stream().wait_stream(side)
-        l_eager, g_eager, _ = _step(copy.deepcopy(model0).to(dev).train(), cfg, d)
-        model.load_state_dict(copy.deepcopy(model0).state_dict())
-        for p in model.parameters():
-            p.grad.zero_()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            static_loss = fwd_bwd()
-        for rep in range(2):
+            def fwd_bwd():
+                dist_, sp = model(d["images"], d["speed"], d["command"])
+                loss = L.moe_loss(dist_, sp, d["control"], d["target"].clone(), cfg.loss_coefs)
+                loss.backward()
+                return loss
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    for p in model.parameters():
+                        p.grad = None
+                    fwd_bwd()
+            torch.cuda.current_stream().wait_stream(side)
             model.load_state_dict(copy.deepcopy(model0).state_dict())
-            torch._foreach_zero_([p.grad for p in model.parameters()])
-            graph.replay()
-            torch.cuda.synchronize()
-            med, worst = _median_worst({n: p.grad for n, p in model.named_parameters()}, g_eager)
-            print("\n[graph replay %d, multi-stream] loss %.6f vs eager %.6f | gradients median %.2e worst %.2e" % (rep, static_loss.item(), l_eager, med, worst))
-            assert abs(static_loss.item() - l_eager) < 1e-3 * max(1.0, abs(l_eager)) and med < 5e-2
+            for p in model.parameters():
+                p.grad.zero_()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = fwd_bwd()
+            for rep in range(2):
+                model.load_state_dict(copy.deepcopy(model0).state_dict())
+                torch._foreach_zero_([p.grad for p in model.parameters()])
+                graph.replay()
+                torch.cuda.synchronize()
+                med, worst = _median_worst({n: p.grad for n, p in model.named_parameters()}, g_eager)
+                print("\n[fp32 graph replay %d, multi-stream] loss %.7f vs eager single-stream %.7f | gradients median %.2e worst %.2e"
+                      % (rep, static_loss.item(), l_eager, med, worst))
+                assert abs(static_loss.item() - l_eager) < 1e-5 * max(1.0, abs(l_eager)) and med < 1e-3 and worst < 1e-1   # the fp32 step has two ReLU-mask modes (scripts/gpu_determinism.py): a replay may land in the other
     finally:
         torch.distributions.Distribution.set_default_validate_args(True)

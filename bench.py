@@ -533,14 +533,14 @@ def run_train_leg(args, rank, world, dev, peaks, local_rank):
     import gc
     gc.collect()
     torch.cuda.empty_cache()
-    if rank == 0:
-        _train.DROPOUT_STEP = None
-        zero_grads()
-        profiler.enable_events(True)
-        loss_of(static).backward()
-        torch.cuda.synchronize()
-        prof = profiler.summary()
-        profiler.enable_events(False)
+    # (every rank runs it: under data parallelism the pass contains the bucket all-reduces, which all ranks must enter)
+    _train.DROPOUT_STEP = None
+    zero_grads()
+    profiler.enable_events(True)
+    loss_of(static).backward()
+    torch.cuda.synchronize()
+    prof = profiler.summary()
+    profiler.enable_events(False)
 
     t = torch.tensor([ms_value, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
@@ -655,7 +655,8 @@ def main():
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     try:
         run_cuda(args, rank, world, local_rank)
     finally:

@@ -23,7 +23,7 @@ import contextlib
 import os as _os0
 
 MULTI_STREAM = _os0.environ.get("PMOE_MULTI_STREAM", "1") == "1"   # independent sub-networks (expert encoders) on side streams
-MULTI_STREAM_MAX_PIXELS = 160 * 224 * 224   # ... when one sub-network's batch is small enough to leave SMs idle (B <= 160 at 224^2)
+MULTI_STREAM_MAX_PIXELS = int(_os0.environ.get("PMOE_MULTI_STREAM_MAX_BATCH", "160")) * 224 * 224   # ... when one sub-network's batch is small enough to leave SMs idle (B <= 160 at 224^2)
 _SIDE_STREAMS = {}
 
 

@@ -113,6 +113,8 @@ int pmoe_conv_wgrad_simt(const PmoeConvTc* desc, int32_t dtype, float* dwpack, p
 /* Tensor-core weight gradient (bf16 dy / activations, fp32 accumulation in TMEM, fp32 atomics into dwpack). Same contract
  * as pmoe_conv_wgrad_simt with dtype = PMOE_BF16. Returns PMOE_ERR_UNSUPPORTED, launching nothing, when the descriptor is
  * outside what the tensor-core kernels cover (the caller then uses pmoe_conv_wgrad_simt). */
+/* Grouped form: desc->wpack_img_stride > 0 makes every image of the dy / source views one GROUP whose gradient goes to
+ * dwpack + image * wpack_img_stride (floats): the K experts' equally shaped Linear layers (model/moe.py:53-72) in ONE launch. */
 int pmoe_conv_wgrad_tc(const PmoeConvTc* desc, float* dwpack, pmoe_stream_t stream);
 
 /* ---- memory-bound kernels (eltwise.cu); dtype = PMOE_F32 | PMOE_BF16 of the NHWC views ------------- */
@@ -324,6 +326,10 @@ int pmoe_pack_chunk_elems(void);
  * (+ dst[idx[i]] when accumulate) for idx[i] >= 0; dst may be a slot of a flat all-reduce bucket. */
 int pmoe_unpack_scatter(const float* packed, const int32_t* idx, float* dst, int64_t n, float alpha, int32_t accumulate,
                         pmoe_stream_t stream);
+/* The same for up to 16 equally shaped parameters at once: packed is [n_groups][n] (the K experts' stacked gradients of one
+ * layer), `dst` / `accumulate` are HOST arrays of n_groups device pointers / flags (a NULL pointer skips its group). */
+int pmoe_unpack_scatter_group(const float* packed, const int32_t* idx, float* const* dst, const int32_t* accumulate,
+                              int32_t n_groups, int64_t n, float alpha, pmoe_stream_t stream);
 /* dst[i] (+)= (float) src[i]: fp64 per-channel sums (BatchNorm weight/bias gradients, Linear bias gradients) into fp32 slots. */
 int pmoe_cvt_f64_f32(const double* src, float* dst, int32_t n, int32_t accumulate, pmoe_stream_t stream);
 

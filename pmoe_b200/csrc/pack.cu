@@ -110,6 +110,25 @@ __global__ void __launch_bounds__(256) unpack_scatter_kernel(const float* __rest
   }
 }
 
+// The same for a GROUP of up to 16 equally shaped parameters in one launch: packed is [K][n] (the K experts' stacked gradients of
+// one layer), group g scatters into dst[g]. grid.y = group.
+struct ScatterGroup {
+  float* dst[16];
+  int accumulate[16];
+};
+__global__ void __launch_bounds__(256) unpack_scatter_group_kernel(const float* __restrict__ packed, const int32_t* __restrict__ idx,
+                                                                   ScatterGroup grp, int64_t n, float alpha) {
+  const int g = blockIdx.y;
+  float* __restrict__ dst = grp.dst[g];
+  if (dst == nullptr) return;
+  const int acc = grp.accumulate[g];
+  const float* __restrict__ src = packed + (int64_t)g * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t id = __ldg(idx + i);
+    if (id >= 0) dst[id] = acc ? dst[id] + alpha * src[i] : alpha * src[i];
+  }
+}
+
 // dst[i] (+)= (float) src[i]: fp64 per-channel reductions (BatchNorm / bias gradients) into fp32 gradient slots.
 __global__ void __launch_bounds__(256) cvt_f64_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int n, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -169,4 +188,24 @@ extern "C" int pmoe_cvt_f64_f32(const double* src, float* dst, int32_t n, int32_
   }
   cvt_f64_f32_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_)>>>(src, dst, n, accumulate);
   return check_launch("cvt_f64_f32");
+}
+
+extern "C" int pmoe_unpack_scatter_group(const float* packed, const int32_t* idx, float* const* dst, const int32_t* accumulate,
+                                         int32_t n_groups, int64_t n, float alpha, pmoe_stream_t stream_) {
+  if (n <= 0 || n_groups <= 0) return PMOE_OK;
+  if (!packed || !idx || !dst || !accumulate || n_groups > 16) {
+    set_error("unpack_scatter_group: null pointer or more than 16 groups");
+    return PMOE_ERR_ARG;
+  }
+  ScatterGroup grp;
+  for (int g = 0; g < 16; ++g) {
+    grp.dst[g] = g < n_groups ? dst[g] : nullptr;      // host arrays: copied into the launch parameters
+    grp.accumulate[g] = g < n_groups ? accumulate[g] : 0;
+  }
+  const int64_t blocks = (n + 1023) / 1024;
+  int gx = grid_for(blocks);
+  if (gx > 64) gx = 64;
+  dim3 grid((unsigned)gx, (unsigned)n_groups);
+  unpack_scatter_group_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(packed, idx, grp, n, alpha);
+  return check_launch("unpack_scatter_group");
 }

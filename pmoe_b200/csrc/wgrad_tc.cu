@@ -234,6 +234,10 @@ struct alignas(64) WgStreamParams {
   int splits, a_stages;
   float* dw;
   int ktot, cout_pad;
+  // grouped mode (dw_img_stride > 0): every image is one GROUP with its own weight gradient, dw_img_stride floats apart — the K
+  // experts' equally shaped Linear layers as one launch (expert = image axis of the stacked activations, model/moe.py:53-72);
+  // a CTA's pixel range then lies inside one image
+  long long dw_img_stride;
 };
 constexpr int kWgMaxUnits = PMOE_MAX_SEG * 4;
 constexpr int kWgAStage = 32 * 1024;  // 128 pixel rows x 128 input channels (bf16)
@@ -296,12 +300,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_stream_kernel(con
   const int split = u % p.splits;
   u /= p.splits;
   const int grp = u % p.n_groups;
-  const int nt = u / p.n_groups;
+  u /= p.n_groups;
+  const int nt = u % p.n_tiles;
+  const int gimg = u / p.n_tiles;  // 0 unless grouped
   // 32-bit tile arithmetic below: a 64-bit division is a subroutine call, and a call inside the lane-0 producer branch
   // makes ptxas give up on proving the MMA warp converged
-  const int t_begin = (int)((p.m_tiles * split) / p.splits);
-  const int t_end = (int)((p.m_tiles * (split + 1)) / p.splits);
   const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const bool grouped = p.dw_img_stride > 0;
+  const int t_base = grouped ? gimg * tiles_per_img : 0;
+  const int t_count = grouped ? tiles_per_img : (int)p.m_tiles;
+  const int t_begin = t_base + (int)(((long long)t_count * split) / p.splits);
+  const int t_end = t_base + (int)(((long long)t_count * (split + 1)) / p.splits);
   const int unit0 = grp * p.n_acc * UPM;
   int n_acc = (p.n_units - unit0 + UPM - 1) / UPM;  // accumulators with at least one live unit
   if (n_acc > p.n_acc) n_acc = p.n_acc;
@@ -383,7 +392,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) conv_wgrad_tc_stream_kernel(con
       for (int a = 0; a < n_acc; ++a) {
         const int un = unit0 + a * UPM + uq;
         const bool live = un < p.n_units;
-        float* dst = p.dw + (long long)(live ? un : 0) * CK + ch;
+        float* dst = p.dw + (long long)gimg * p.dw_img_stride + (long long)(live ? un : 0) * CK + ch;
         for (int cb = 0; cb < p.N; cb += 32) {
           uint32_t raw[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * p.N + cb), raw);
@@ -494,9 +503,12 @@ static int wgrad_stream(const PmoeConvTc* d, float* dwpack, cudaStream_t stream)
   p.tiles_h = (o.h + p.bh - 1) / p.bh;
   p.n_img = o.n;
   p.m_tiles = (long long)p.tiles_w * p.tiles_h * p.n_img;
-  const long long units = (long long)p.n_tiles * p.n_groups;
+  p.dw_img_stride = d->wpack_img_stride > 0 ? d->wpack_img_stride : 0;
+  const long long n_grp_img = p.dw_img_stride > 0 ? p.n_img : 1;
+  const long long units = (long long)p.n_tiles * p.n_groups * n_grp_img;
+  const long long tiles_each = p.dw_img_stride > 0 ? (long long)p.tiles_w * p.tiles_h : p.m_tiles;
   long long splits = (long long)num_sms() / units;
-  if (splits > p.m_tiles) splits = p.m_tiles;
+  if (splits > tiles_each) splits = tiles_each;
   if (splits < 1) splits = 1;
   p.splits = (int)splits;
   const int dy_stage = (p.N / 64) * kWgDyBlock;
@@ -546,7 +558,8 @@ extern "C" int pmoe_conv_wgrad_tc(const PmoeConvTc* d, float* dwpack, pmoe_strea
   int total_chunks = 0;
   for (int i = 0; i < d->n_src; ++i) total_chunks += d->src[i].c / 64;
   static const bool halo_off = getenv("PMOE_NO_HALO") != nullptr;
-  if (halo_off || !ok || total_chunks > PMOE_MAX_SEG || 9 * total_chunks * 64 != d->ktot) return wgrad_stream(d, dwpack, stream);
+  if (halo_off || !ok || total_chunks > PMOE_MAX_SEG || 9 * total_chunks * 64 != d->ktot || d->wpack_img_stride > 0)
+    return wgrad_stream(d, dwpack, stream);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   int g = 0;

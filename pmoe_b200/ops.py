@@ -200,8 +200,8 @@ def conv_wgrad(srcs, segs, ck, dy, dwpack, flops=0.0, tag=""):
     """dwpack[cout_pad, ktot] (fp32) += sum_pixels dy[p, co] * x_k[p] in the packed K order of the forward."""
     dt = dy.dtype
     from . import config
-    if (dt == torch.bfloat16 and not config.FORCE_SIMT and dy.shape[3] < 64 and dy.shape[0] * dy.shape[1] * dy.shape[2] >= 8192
-            and dwpack.shape[0] <= 64):
+    if (dt == torch.bfloat16 and not config.FORCE_SIMT and dy.shape[3] < 64 and (dy.shape[0] * dy.shape[1] * dy.shape[2] >= 8192 or dwpack.dim() == 3)
+            and dwpack.shape[-2] <= 64):
         # Skinny outputs (the 512->1 / 512->4 expert-head Linears over 64k rows): the tensor-core kernel wants >= 64 gradient
         # channels, and the CUDA-core fallback took 183 us per expert and layer for a 67 MB read. Zero-pad dy to 64 channels
         # (8 MB at 64k rows) and run the tensor-core kernel; only the first rows of its result are real.
@@ -210,17 +210,20 @@ def conv_wgrad(srcs, segs, ck, dy, dwpack, flops=0.0, tag=""):
         vs, vd = _lib.view4(dy), _lib.view4(dyp[..., :c])
         _lib.check(profiler.launch("axpy", lambda: _lib.lib().pmoe_axpy(C.byref(vs), C.byref(vd), _lib.BF16, 1.0, None, 0, 0,
                                                                         _lib.stream_ptr()), io=(dy, dy)), "axpy")
-        wide = torch.zeros(64, dwpack.shape[1], dtype=torch.float32, device=dy.device)
+        grouped = dwpack.dim() == 3   # (K, cout_pad, ktot): one gradient per image / expert
+        wide = torch.zeros(((dwpack.shape[0],) if grouped else ()) + (64, dwpack.shape[-1]), dtype=torch.float32, device=dy.device)
         dw = _fill_desc(srcs, wide, segs, ck, dyp, None, None, None, None, None, None, None, None, 0, dt)
         tc = _lib.lib().pmoe_conv_wgrad_tc
         sp = _lib.stream_ptr()
         rc = profiler.launch("conv_wgrad_tc", lambda: tc(C.byref(dw), wide.data_ptr(), sp), flops, 0.0, tag)
         if rc == 0:
-            dwpack += wide[:dwpack.shape[0]]
+            dwpack += wide[..., :dwpack.shape[-2], :]
             return dwpack
         if rc != -2:
             _lib.check(rc, "conv_wgrad_tc")
         profiler.uncount()
+    if dwpack.dim() == 3 and (dt != torch.bfloat16 or config.FORCE_SIMT):
+        raise RuntimeError("pmoe_b200 conv_wgrad: the grouped (per-image) weight gradient is a tensor-core kernel feature")
     d = _fill_desc(srcs, dwpack, segs, ck, dy, None, None, None, None, None, None, None, None, 0, dt)
     assert dwpack.dtype == torch.float32
     sp = _lib.stream_ptr()
@@ -230,7 +233,7 @@ def conv_wgrad(srcs, segs, ck, dy, dwpack, flops=0.0, tag=""):
         rc = profiler.launch("conv_wgrad_tc", lambda: tc(C.byref(d), dwpack.data_ptr(), sp), flops, 0.0, tag)
         if rc == 0:
             return dwpack
-        if rc != -2:
+        if rc != -2 or dwpack.dim() == 3:
             _lib.check(rc, "conv_wgrad_tc")
         profiler.uncount()
     fn = _lib.lib().pmoe_conv_wgrad_simt

@@ -14,7 +14,7 @@ import torch
 from . import _lib, packs, profiler
 from ._lib import check, lib, stream_ptr
 
-_CHUNK = 1 << 16  # elements per chunk: 83 M parameters -> ~1.5 k chunks, > 8 per SM
+_CHUNK = 1 << 14  # elements per chunk: 83 M parameters -> ~5 k chunks; one expert (13.8 M) still gives every SM several CTAs
 _DT = np.dtype([("p", "<u8"), ("g", "<u8"), ("m", "<u8"), ("v", "<u8"), ("vmax", "<u8"), ("n", "<i4"), ("pad", "<i4")])
 assert _DT.itemsize == 48
 

@@ -188,6 +188,20 @@ def scatter_grad(packed_grad, idx, dst_flat, accumulate, alpha=1.0):
         "unpack_scatter")
 
 
+def scatter_grad_group(packed_grad, idx, dst_flats, accumulates, alpha=1.0):
+    """packed_grad (K, ...) stacked packed gradients of K equally shaped parameters -> their K gradient slots, one launch per 16."""
+    K = packed_grad.shape[0]
+    n = idx.numel()
+    assert packed_grad.dtype == torch.float32 and packed_grad.is_contiguous() and packed_grad.numel() == K * n
+    for g0 in range(0, K, 16):
+        g1 = min(K, g0 + 16)
+        ptrs = (C.c_void_p * (g1 - g0))(*[None if d is None else d.data_ptr() for d in dst_flats[g0:g1]])
+        accs = (C.c_int32 * (g1 - g0))(*[int(bool(a)) for a in accumulates[g0:g1]])
+        base = packed_grad.data_ptr() + g0 * n * 4
+        check(profiler.launch("unpack_scatter", lambda: lib().pmoe_unpack_scatter_group(
+            base, idx.data_ptr(), ptrs, accs, g1 - g0, n, float(alpha), stream_ptr())), "unpack_scatter_group")
+
+
 def bump(tensors):
     """Tell torch that kernels wrote these tensors through raw pointers (derived caches key on `_version`)."""
     ts = [t for t in tensors if t is not None]

@@ -453,6 +453,23 @@ def _wgrad_to_param(tape, dwp, pack, weight):
     tape.pgrad_done(p)
 
 
+def _group_to_params(tape, stacked, pack_list, params):
+    """Stacked (K, ...) packed gradients of K equally shaped parameters -> their gradient slots in one scatter launch."""
+    slots, accs, done = [], [], []
+    for prm in params:
+        if prm is None or not prm.requires_grad:
+            slots.append(None)
+            accs.append(False)
+            continue
+        slot, existed = tape.pgrad_slot(prm)
+        slots.append(slot)
+        accs.append(existed)
+        done.append(prm)
+    packs.scatter_grad_group(stacked.contiguous(), pack_list[0].idx, slots, accs)
+    for prm in done:
+        tape.pgrad_done(prm)
+
+
 def _pack_dgrad(weight, src, segs_i, co_pad, dtype):
     """rows = physical channels of `src`, K = (segment of this source, padded cout)."""
     def build(wf):
@@ -1444,8 +1461,8 @@ def grouped_linear_op(tape, srcs, lins, act=None, tag=""):
     has_bias = lins[0].bias is not None
     shift = None
     if has_bias:   # (K, cop) stacked biases, refreshed with the weights
-        shift = packs.packed_group([l.bias for l in lins], ("bias", cop), lins[0].bias.shape,
-                                   lambda v: torch.nn.functional.pad(v, (0, cop - cout)), torch.float32)[0]
+        shift, bias_packs = packs.packed_group([l.bias for l in lins], ("bias", cop), lins[0].bias.shape,
+                                               lambda v: torch.nn.functional.pad(v, (0, cop - cout)), torch.float32)
     z_t = torch.empty(K, 1, B, cstore, dtype=dt, device=dev)
     flops = 2.0 * K * B * cout * sum(x.nlog for x in srcs)
     ops.conv([x.t for x in srcs], wp, segs, ck, z_t, shift=shift, act=act, flops=flops, tag="grouped " + tag)
@@ -1462,14 +1479,15 @@ def grouped_linear_op(tape, srcs, lins, act=None, tag=""):
         z_saved = z_t if act not in (None, "none") else None
         dy = torch.empty(K, 1, B, cstore, dtype=dt, device=dev)
         _bn_bwd_apply(dz, z_saved, None, act, None, None, None, None, None, 0.0, 0, dy, None, False)
-        for e, lin in enumerate(lins):
-            if lin.bias is not None and lin.bias.requires_grad:
-                s1, _ = _bn_bwd_reduce(tape, dy[e:e + 1], None, None, None, None, None, cstore)
-                tape.add_pgrad(lin.bias, s1[:cout])
-            if lin.weight.requires_grad:
-                dwp = tape.zeros((cop, wp.shape[2]), torch.float32, dev)
-                ops.conv_wgrad([x.t[e:e + 1] for x in srcs], segs, ck, dy[e:e + 1], dwp, flops=flops / K, tag="wgrad grouped " + tag)
-                _wgrad_to_param(tape, dwp, wpks[e], lin.weight)
+        if has_bias and any(l.bias.requires_grad for l in lins):
+            bsum = nhwc.channel_sums(dy)                      # (K, cstore): per-expert bias gradients in one launch
+            _group_to_params(tape, bsum if cstore == cop else torch.nn.functional.pad(bsum, (0, cop - cstore)), bias_packs,
+                             [l.bias for l in lins])
+        if any(l.weight.requires_grad for l in lins):
+            # ONE launch for the K experts' weight gradients: the expert is the image axis, each image accumulates into its own slice
+            dwp = tape.zeros((K, cop, wp.shape[2]), torch.float32, dev)
+            ops.conv_wgrad([x.t for x in srcs], segs, ck, dy, dwp, flops=flops, tag="wgrad grouped " + tag)
+            _group_to_params(tape, dwp, wpks, [l.weight for l in lins])
         ck_d = ops.choose_ck([cstore])
         for x in srcs:
             if not _rg(x.act):

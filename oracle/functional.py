@@ -109,6 +109,10 @@ def batchnorm(x, sd, p, train, eps=BN_EPS, momentum=BN_MOMENTUM):
             sd[p + "running_mean"].mul_(1 - momentum).add_(momentum * src.mean(dim=dims))
             sd[p + "running_var"].mul_(1 - momentum).add_(momentum * src.var(dim=dims, unbiased=False) * n / max(n - 1, 1))
         return _BnStored.apply(src, sd[p + "weight"], sd[p + "bias"], eps)
+    if (not train) and STORE is not None and src is not None:
+        # eval mode: the product folds the BatchNorm into the conv epilogue — the conv output is never stored on its own, the
+        # first rounding happens after BatchNorm + activation (the caller's _st)
+        x = src
     return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
                         train, momentum, eps)
 

@@ -21,3 +21,19 @@ def rel_err(a, b):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+def bf16_eval_errors(out, ref_fp32, ref_bf16_storage):
+    """(distance to the fp32 oracle, distance to the oracle run with bf16 storage, that oracle's own distance to fp32)."""
+    return rel_err(out, ref_fp32), rel_err(out, ref_bf16_storage), rel_err(ref_bf16_storage, ref_fp32)
+
+
+def assert_bf16_eval(out, ref_fp32, ref_bf16_storage, what=""):
+    """north_star bf16 bound for outputs: within 1e-2 of the reference in bf16 (the oracle evaluated with the product's storage
+    points rounded to bf16) and, against the fp32 reference, never further than 1e-2 or 1.25 x what that bf16 evaluation itself
+    costs (small random-init geometries put ~1e-2 of storage noise on a 23-layer U-Net, chains of U-Nets more)."""
+    e32, eemu, eself = bf16_eval_errors(out, ref_fp32, ref_bf16_storage)
+    print("[bf16 eval %s] vs fp32 oracle %.3e | vs bf16-storage oracle %.3e | bf16-storage oracle vs fp32 %.3e" % (what, e32, eemu, eself))
+    assert eemu < 1e-2, (what, eemu)
+    assert e32 < max(1e-2, 1.25 * eself), (what, e32, eself)
+    return e32, eemu, eself

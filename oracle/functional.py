@@ -83,6 +83,21 @@ class _BnStored(torch.autograd.Function):
         return dx.to(torch.bfloat16).to(g.dtype), s2, s1, None
 
 
+def _wq(w):
+    """A conv / linear weight as the product's kernels read it under bf16 storage: rounded to bf16 (the packed operand)."""
+    return w if STORE is None else w.to(torch.bfloat16).to(w.dtype)
+
+
+def _conv(x, w, bias, stride, pad):
+    """Dense convolution whose output the product stores: weights as stored (bf16 under storage emulation), output through
+    `_stc`; the arguments ride along for the eval-mode BatchNorm fold (see `batchnorm`)."""
+    if STORE is None:
+        return F.conv2d(x, w, bias, stride, pad)
+    y = _stc(F.conv2d(x, _wq(w), bias, stride, pad))
+    y._pmoe_conv = (x, w, bias, stride, pad)
+    return y
+
+
 def _stc(x):
     """A stored convolution output. The product takes the train-mode BatchNorm statistics of a conv output from the fp32
     accumulators (conv epilogue) and normalises the STORED, rounded tensor with them; the rounded tensor therefore carries its
@@ -110,8 +125,14 @@ def batchnorm(x, sd, p, train, eps=BN_EPS, momentum=BN_MOMENTUM):
             sd[p + "running_var"].mul_(1 - momentum).add_(momentum * src.var(dim=dims, unbiased=False) * n / max(n - 1, 1))
         return _BnStored.apply(src, sd[p + "weight"], sd[p + "bias"], eps)
     if (not train) and STORE is not None and src is not None:
-        # eval mode: the product folds the BatchNorm into the conv epilogue — the conv output is never stored on its own, the
-        # first rounding happens after BatchNorm + activation (the caller's _st)
+        # eval mode: the product folds the BatchNorm into the conv — scale into the packed bf16 weights, shift into the epilogue —
+        # so the conv output is never stored on its own; the first rounding happens after BatchNorm + activation (the caller's _st)
+        conv_args = getattr(x, "_pmoe_conv", None)
+        if conv_args is not None and conv_args[2] is None:
+            xin, w, _, stride, pad = conv_args
+            scale = sd[p + "weight"] * torch.rsqrt(sd[p + "running_var"] + eps)
+            shift = sd[p + "bias"] - sd[p + "running_mean"] * scale
+            return F.conv2d(xin, _wq(w * scale.view(-1, 1, 1, 1)), None, stride, pad) + shift.view(1, -1, 1, 1)
         x = src
     return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
                         train, momentum, eps)
@@ -119,8 +140,9 @@ def batchnorm(x, sd, p, train, eps=BN_EPS, momentum=BN_MOMENTUM):
 
 def conv3_block(x, sd, p, train, stride=1):
     """basics.py:48-59 — (conv3x3 no-bias, BN, ReLU) twice."""
+    x = _st(x)   # a block's input is a stored tensor (the network input is converted to the storage dtype at the module boundary)
     for a, b in (("0", "1"), ("3", "4")):
-        x = _stc(F.conv2d(x, sd[p + a + ".weight"], None, stride, 1))
+        x = _conv(x, sd[p + a + ".weight"], None, stride, 1)
         x = _st(torch.relu(batchnorm(x, sd, p + b + ".", train)))
     return x
 
@@ -141,11 +163,11 @@ def eca(x, w):
 
 def eca_conv_block(x, sd, p, train, stride=1):
     """basics.py:80-135 — EfficientConvBlock."""
-    x = eca(x, sd[p + "layer1.eca1.conv.weight"])
-    x = _stc(F.conv2d(x, sd[p + "layer1.conv1.0.weight"], None, stride, 1))
+    x = eca(_st(x), sd[p + "layer1.eca1.conv.weight"])
+    x = _conv(x, sd[p + "layer1.conv1.0.weight"], None, stride, 1)
     x = _st(torch.relu(batchnorm(x, sd, p + "layer1.conv1.1.", train)))
     x = eca(x, sd[p + "layer2.eca2.conv.weight"])
-    x = _stc(F.conv2d(x, sd[p + "layer2.conv2.0.weight"], None, stride, 1))
+    x = _conv(x, sd[p + "layer2.conv2.0.weight"], None, stride, 1)
     return _st(torch.relu(batchnorm(x, sd, p + "layer2.conv2.1.", train)))
 
 
@@ -179,7 +201,7 @@ def mlp(x, sd, p, cfg, train):
     for i, op in enumerate(ops):
         fused_act = i + 1 < len(ops) and ops[i + 1][0] == "act"  # the product applies bias + activation in the GEMM epilogue, then stores
         if op[0] == "linear":
-            x = F.linear(x, sd[p + "%d.weight" % op[1]], sd.get(p + "%d.bias" % op[1]))
+            x = F.linear(x, _wq(sd[p + "%d.weight" % op[1]]), sd.get(p + "%d.bias" % op[1]))
             if not fused_act:
                 x = _st(x)
         elif op[0] == "bn":
@@ -200,14 +222,14 @@ def unet(x, sd, p, train, inter_repr=False):
     x5 = conv3_block(F.max_pool2d(x4, 2, 2), sd, p + "dwn_5.", train)
     y = x5
     for i, skip in ((1, x4), (2, x3), (3, x2), (4, x1)):
-        up = _st(F.conv_transpose2d(y, sd[p + "up_%d.weight" % i], sd[p + "up_%d.bias" % i], stride=2))
+        up = _st(F.conv_transpose2d(y, _wq(sd[p + "up_%d.weight" % i]), sd[p + "up_%d.bias" % i], stride=2))
         # unet.py:72 output_size=skip.size(): pads bottom/right when the skip is odd-sized
         dh, dw = skip.shape[-2] - up.shape[-2], skip.shape[-1] - up.shape[-1]
         if dh or dw:
             up = F.conv_transpose2d(y, sd[p + "up_%d.weight" % i], sd[p + "up_%d.bias" % i], stride=2,
                                     output_padding=(dh, dw))
         y = conv3_block(torch.cat([skip, up], 1), sd, p + "up_forw_%d." % i, train)  # skip first (unet.py:73)
-    out = _stc(F.conv2d(y, sd[p + "out.weight"], sd[p + "out.bias"]))
+    out = _conv(y, sd[p + "out.weight"], sd[p + "out.bias"], 1, 0)
     if inter_repr:
         return x5.mean(dim=(2, 3)), out
     return out
@@ -252,21 +274,21 @@ def resnet_eca(x, sd, p, train, arch="resnet18"):
             s = stride if bi == 0 else 1
             idt = x
             if kind == "basic":
-                y = _stc(F.conv2d(x, sd[q + "conv1.weight"], None, s, 1))
+                y = _conv(x, sd[q + "conv1.weight"], None, s, 1)
                 y = _st(torch.relu(batchnorm(y, sd, q + "bn1.", train)))
-                y = _stc(F.conv2d(y, sd[q + "conv2.weight"], None, 1, 1))
+                y = _conv(y, sd[q + "conv2.weight"], None, 1, 1)
                 y = batchnorm(y, sd, q + "bn2.", train)   # the residual add + ReLU ride the same pass: one stored tensor
             else:
-                y = _st(torch.relu(batchnorm(_stc(F.conv2d(x, sd[q + "conv1.weight"])), sd, q + "bn1.", train)))
-                y = _st(torch.relu(batchnorm(_stc(F.conv2d(y, sd[q + "conv2.weight"], None, s, 1)), sd, q + "bn2.", train)))
-                y = batchnorm(_stc(F.conv2d(y, sd[q + "conv3.weight"])), sd, q + "bn3.", train)
+                y = _st(torch.relu(batchnorm(_conv(x, sd[q + "conv1.weight"], None, 1, 0), sd, q + "bn1.", train)))
+                y = _st(torch.relu(batchnorm(_conv(y, sd[q + "conv2.weight"], None, s, 1), sd, q + "bn2.", train)))
+                y = batchnorm(_conv(y, sd[q + "conv3.weight"], None, 1, 0), sd, q + "bn3.", train)
             if q + "downsample.0.weight" in sd:
-                idt = _stc(F.conv2d(x, sd[q + "downsample.0.weight"], None, s, 0))
+                idt = _conv(x, sd[q + "downsample.0.weight"], None, s, 0)
                 idt = _st(batchnorm(idt, sd, q + "downsample.1.", train))
             x = _st(torch.relu(y + idt))
     x = _st(x.mean(dim=(2, 3)))
     if p + "fc.weight" in sd:
-        x = _st(F.linear(x, sd[p + "fc.weight"], sd[p + "fc.bias"]))
+        x = _st(F.linear(x, _wq(sd[p + "fc.weight"]), sd[p + "fc.bias"]))
     return x
 
 
@@ -452,13 +474,13 @@ def expert(images, speed, command, sd, p, cfg, train, alt=False):
     feats = torch.cat([img, s, c], dim=-1)
     pred_speed = mlp(feats, sd, p + "speed_pred.", cfg["speed_prediction"], train)
     af = mlp(feats, sd, p + "action_features.", cfg["action_head"], train)
-    mean, std = _st(F.linear(af, sd[p + "action_pred.weight"], sd[p + "action_pred.bias"])).split(2, dim=-1)
+    mean, std = _st(F.linear(af, _wq(sd[p + "action_pred.weight"]), sd[p + "action_pred.bias"])).split(2, dim=-1)
     std = F.elu(std) + 1
     if alt:
-        a = F.linear(feats, sd[p + "alpha.0.weight"], sd[p + "alpha.0.bias"])
-        alpha = _st(F.linear(_st(torch.relu(a)), sd[p + "alpha.2.weight"], sd[p + "alpha.2.bias"]))
+        a = F.linear(feats, _wq(sd[p + "alpha.0.weight"]), sd[p + "alpha.0.bias"])
+        alpha = _st(F.linear(_st(torch.relu(a)), _wq(sd[p + "alpha.2.weight"]), sd[p + "alpha.2.bias"]))
     else:
-        alpha = torch.relu(_st(F.linear(af, sd[p + "alpha.weight"], sd[p + "alpha.bias"])))  # the gating kernel applies the ReLU
+        alpha = torch.relu(_st(F.linear(af, _wq(sd[p + "alpha.weight"]), sd[p + "alpha.bias"])))  # the gating kernel applies the ReLU
     return alpha, mean, std, pred_speed
 
 

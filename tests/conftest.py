@@ -34,6 +34,8 @@ def assert_bf16_eval(out, ref_fp32, ref_bf16_storage, what=""):
     costs (small random-init geometries put ~1e-2 of storage noise on a 23-layer U-Net, chains of U-Nets more)."""
     e32, eemu, eself = bf16_eval_errors(out, ref_fp32, ref_bf16_storage)
     print("[bf16 eval %s] vs fp32 oracle %.3e | vs bf16-storage oracle %.3e | bf16-storage oracle vs fp32 %.3e" % (what, e32, eemu, eself))
-    assert eemu < 1e-2, (what, eemu)
+    # two bf16-storage evaluations whose rounding noise is independent are sqrt(2) x that noise apart: where the evaluation itself
+    # loses more than 1e-2 against fp32 (chains of U-Nets), the distance to it is bounded by 1.5 x its own distance to fp32
+    assert eemu < max(1e-2, 1.5 * eself), (what, eemu, eself)
     assert e32 < max(1e-2, 1.25 * eself), (what, e32, eself)
     return e32, eemu, eself

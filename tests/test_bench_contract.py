@@ -42,3 +42,32 @@ def test_recorded_bench_line_has_the_contract_keys(path):
 
 def test_a_single_gpu_line_with_cpu_baseline_is_recorded():
     assert any("cpu_baseline" in json.load(open(p)) and json.load(open(p))["n_gpus"] == 1 for p in LINES)
+
+
+R02 = sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench_line_*.json")))
+
+
+@pytest.mark.parametrize("path", R02, ids=[os.path.basename(p) for p in R02])
+def test_recorded_round2_bench_line_has_the_contract_keys(path):
+    """Round 2: the training step (BASELINE configs[2]) is the primary metric, strong scaling over the ranks."""
+    d = json.load(open(path))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "roofline_hbm"):
+        assert k in d, k
+    assert d["metric"] == "train_samples_per_sec" and d["unit"] == "samples/s" and d["higher_is_better"] is True
+    assert d["scaling"] == "strong" and d["vs_baseline"] is None and d["dtype"] == "bf16" and d["data"] == "synthetic"
+    assert "workload" in d["config"] and "model" not in d["config"] and d["warmup"] >= 3
+    assert abs(d["value"] - d["config"]["global_batch"] / (d["ms_per_step"] / 1e3)) < 1e-6 * d["value"]
+    e = d["e2e"]
+    assert e["unit"] == d["unit"] and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.02
+    assert d["gpu_launches"] > 0 and d["config"]["launch_mode"] == "cuda_graph"
+    c = d["clocks"]
+    assert c["sm_mhz"] > 0 and not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"])
+    for r, bound, unit in ((d["roofline"], "tensor", "TFLOP/s"), (d["roofline_hbm"], "hbm", "GB/s")):
+        assert r["bound"] == bound and r["unit"] == unit and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] < 1
+        assert r["traffic"] is None or r["traffic"] > 0
+    if d["n_gpus"] == 1:
+        cb = d["cpu_baseline"]
+        assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and cb["unit"] == d["unit"] and cb["sample"]
+    if "infer" in d:
+        assert d["infer"]["metric"] == "infer_frames_per_sec" and d["infer"]["e2e"]["d2h_bytes_per_step"] > 0

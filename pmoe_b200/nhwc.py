@@ -18,10 +18,11 @@ def dtype_code(t):
 
 class Act:
     """An NHWC activation: tensor (N,H,W,Cpad) with `c` logical channels; channels [c, Cpad) are zero."""
-    __slots__ = ("t", "c", "rg", "stats", "bn_relu")
+    __slots__ = ("t", "c", "rg", "stats", "bn_relu", "gate_grad")
 
     def __init__(self, t, c, rg=False):
         self.t, self.c, self.rg = t, c, rg
+        self.gate_grad = None  # ECA of a network input: callback(d gate (N, Cpad) fp32) fed by the consuming conv's per-image wgrad
         self.bn_relu = False  # t = relu(BatchNorm(raw conv output)) with batch statistics and nothing added (set by train.conv_op)
         self.stats = None   # (sum, sum of squares) per channel, fp64, when the producing kernel already reduced them
 

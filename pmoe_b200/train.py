@@ -286,6 +286,7 @@ def _bn_bwd_reduce(tape, dz, z, x, act, mean, rstd, cpad, fwd=None):
 
 
 FUSE_BN_CHAIN_SUMS = True  # tests switch it off to compare against the separate reduce pass
+GATE_GRAD_FROM_WGRAD = True  # the stem's first ECA gate takes its gradient from the conv's per-image weight gradient (see eca_op)
 
 
 def _bn_bwd_apply_sums(tape, dz, z, x, act, mean, rstd, gamma, s1, s2, inv_n, dx, fwd, pgrads=None):
@@ -612,8 +613,8 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
         h, w = out_hw
     flops = 2.0 * n * h * w * cout * sum(srcs[i].nlog for (i, _, _, _, _) in segdefs)
     bn_train = bn is not None and bn.training
-    rg_in = any(_rg(x.act) for x in srcs) or _any_rg([_owner(weight), bias]) or (bn is not None and _any_rg([bn.weight, bn.bias])) \
-        or (residual is not None and _rg(residual))
+    rg_in = any(_rg(x.act) or getattr(x.act, "gate_grad", None) is not None for x in srcs) or _any_rg([_owner(weight), bias]) \
+        or (bn is not None and _any_rg([bn.weight, bn.bias])) or (residual is not None and _rg(residual))
     pool = None
     if want_pool:
         pool = pool_out if pool_out is not None else torch.zeros(n, cop, dtype=torch.float32, device=dev)
@@ -679,7 +680,20 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
                 tape.add_pgrad(bias, s1[:cout])
             _bn_bwd_apply(dz, z_saved, None, act, None, None, None if scale is None else scale[:cstore].contiguous(), None, None,
                           0.0, 0, dy, dres, acc_dres)
-        if weight.requires_grad:
+        gate_hooks = [x for x in srcs if getattr(x.act, "gate_grad", None) is not None]
+        if gate_hooks:
+            # per-image weight gradient (grouped mode of the tensor-core kernel): its sum over the images is dW, and contracted
+            # with W over (co, tap) it is the gradient of the ECA gate that scaled this conv's input
+            if len(srcs) != 1 or dt != torch.bfloat16:
+                raise RuntimeError("pmoe_b200 conv_op: a gate-gradient source must be the conv's only source on the tensor-core path")
+            dwn = tape.zeros((n, cop, wp.shape[1]), torch.float32, dev)
+            ops.conv_wgrad(src_ts, segs, ck, dy, dwn, flops=flops, tag="wgrad " + tag)
+            cpx = srcs[0].cpad
+            dg = (dwn.view(n, cop, -1, cpx) * wp.float().view(1, cop, -1, cpx)).sum(dim=(1, 2))
+            gate_hooks[0].act.gate_grad(dg)
+            if weight.requires_grad:
+                _wgrad_to_param(tape, dwn.sum(dim=0), wpk, weight)
+        elif weight.requires_grad:
             dwp = tape.zeros((cop, wp.shape[1]), torch.float32, dev)
             ops.conv_wgrad(src_ts, segs, ck, dy, dwp, flops=flops, tag="wgrad " + tag)
             _wgrad_to_param(tape, dwp, wpk, weight)
@@ -956,6 +970,28 @@ def eca_op(tape, eca_mod, x, layout=None, pool_in=None):
     gate = nhwc.eca_gate(sums, h * wd, w.detach(), groups, gl, gs)
     y = nhwc.scale_channels(x.t, gate)
     rg = _rg(x) or w.requires_grad
+    if (GATE_GRAD_FROM_WGRAD and tape.save and not _rg(x) and w.requires_grad and tape.dtype == torch.bfloat16 and not config.FORCE_SIMT
+            and groups == 1):
+        # ECA on a network INPUT (the stem's first gate): x needs no gradient, and the gate's gradient
+        #   d gate[n, c] = sum_p d(x*gate)[n, p, c] * x[n, p, c]
+        # equals sum over (co, tap) of W[co, c, tap] * dW_n[co, c, tap] / gate[n, c], with dW_n the consuming conv's PER-IMAGE weight
+        # gradient (it sees x * gate as its input). The conv computes dW_n anyway (grouped mode of the weight-gradient kernel),
+        # so the 64 -> 16-channel data-gradient launch and two passes over the input-sized tensors are not needed at all.
+        ya = _new_act(tape, y, x.c, False)
+
+        def gate_grad(dg_gated):   # (N, Cpad) fp32: sum over (co, tap) of W * dW_n
+            dgate = (dg_gated.double() / gate.double().clamp_min(1e-30)).contiguous()
+            dmean = torch.empty(n, cp, dtype=torch.float32, device=dgate.device)
+            dw = tape.zeros(w.numel(), torch.float64, dgate.device)
+            wf = w.detach().reshape(-1)
+            check(profiler.launch("eca_gate_bwd", lambda: lib().pmoe_eca_gate_bwd(
+                dgate.data_ptr(), dgate.stride(0), gate.data_ptr(), gate.stride(0), sums.data_ptr(), sums.stride(0), n,
+                1.0 / float(h * wd), wf.data_ptr(), wf.numel(), groups, gl, gs, dmean.data_ptr(), dmean.stride(0),
+                dw.data_ptr(), stream_ptr())), "eca_gate_bwd")
+            tape.add_pgrad(w, dw)
+        ya.gate_grad = gate_grad
+        tape.expect(w)
+        return ya
     ya = _new_act(tape, y, x.c, rg)
     if tape.save and rg:
         def backward():

@@ -192,18 +192,25 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const __grid_constant__ 
     }
   }
   if (p.stat_sum) {
+    // fixed summation order inside the block (the fp32 parity mode must not depend on the order shared-memory atomics land in:
+    // a 1e-7 difference in a batch statistic flips ReLU masks downstream); the operand tiles are free by now
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      atomicAdd(&s_red[0][tx * 4 + j], st_sum[j]);
-      atomicAdd(&s_red[1][tx * 4 + j], st_sq[j]);
+      As[ty][tx * 4 + j] = st_sum[j];
+      Bs[ty][tx * 4 + j] = st_sq[j];
     }
     __syncthreads();
     if (tid < 64 && n0 + tid < p.cout_pad) {
-      atomicAdd(p.stat_sum + n0 + tid, (double)s_red[0][tid]);
-      atomicAdd(p.stat_sq + n0 + tid, (double)s_red[1][tid]);
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        a += (double)As[r][tid];
+        b += (double)Bs[r][tid];
+      }
+      atomicAdd(p.stat_sum + n0 + tid, a);   // fp64 across blocks: order effects are 1e-16
+      atomicAdd(p.stat_sq + n0 + tid, b);
     }
-    __syncthreads();
-    if (tid < 64) s_red[0][tid] = 0.f;
     __syncthreads();
   }
   if (p.pool_sum) {

@@ -782,7 +782,11 @@ int pmoe_channel_sums(const PmoeView4* src, int32_t dtype, float* out, int64_t o
         static_cast<const uint4*>(src->ptr), nullptr, hw, cg, nullptr, nullptr, out, out_stride, nullptr, nullptr, ppb);
     return check_launch("channel_sums");
   }
-  int rows = 1024;
+  // fp32 (the parity mode): ONE block per image walks all its pixels, so the per-image sums do not depend on the order in which
+  // several blocks' fp32 atomics land (they feed the ECA gates: a 1e-7 difference flips ReLU masks downstream)
+  long long rows_ll = dtype == PMOE_F32 ? hw : 1024;
+  if (rows_ll > 0x7fffffffLL) rows_ll = 0x7fffffffLL;
+  const int rows = (int)rows_ll;
   dim3 grid((unsigned)((hw + rows - 1) / rows), (unsigned)src->n);
   DISPATCH_DTYPE(dtype, (channel_sums_kernel<T><<<grid, 256, 0, stream>>>(to_v4(*src), out, out_stride, rows)));
   return check_launch("channel_sums");

@@ -508,6 +508,19 @@ static int wgrad_stream(const PmoeConvTc* d, float* dwpack, cudaStream_t stream)
   const long long units = (long long)p.n_tiles * p.n_groups * n_grp_img;
   const long long tiles_each = p.dw_img_stride > 0 ? (long long)p.tiles_w * p.tiles_h : p.m_tiles;
   long long splits = (long long)num_sms() / units;
+  if (splits < 1) {
+    // more (N tile, unit group, image) work items than SMs: split each into a few pixel ranges so that the last wave is full
+    // (256 images on 148 SMs: 1 split = 2 waves of whole images, 4 splits = 7 waves of quarter images = 1.75)
+    double best = 1e30;
+    splits = 1;
+    for (long long sp = 1; sp <= 8 && sp <= tiles_each; ++sp) {
+      const double waves = (double)((units * sp + num_sms() - 1) / num_sms()) / (double)sp;
+      if (waves < best - 1e-9) {
+        best = waves;
+        splits = sp;
+      }
+    }
+  }
   if (splits > tiles_each) splits = tiles_each;
   if (splits < 1) splits = 1;
   p.splits = (int)splits;

@@ -169,12 +169,18 @@ def conv_simt(srcs, wpack, segs, ck, out, scale=None, shift=None, act=None, resi
             conv_simt(srcs, wpack[q * cols:(q + 1) * cols], segs, ck, view, None if scale is None else scale[q * cols:(q + 1) * cols],
                       None if shift is None else shift[q * cols:(q + 1) * cols], act, flops=flops / (len(out_extra) + 1), tag=tag)
         return out
-    d = _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum, stat_sqsum, pool_sum, src_channels,
-                   pool_stride, dt)
+    det_pool = pool_sum is not None and dt == torch.float32   # parity mode: per-image sums by the order-independent reduction kernel
+    d = _fill_desc(srcs, wpack, segs, ck, out, scale, shift, act, residual, stat_sum, stat_sqsum, None if det_pool else pool_sum,
+                   src_channels, pool_stride, dt)
     fn = _lib.lib().pmoe_conv_simt
     sp = _lib.stream_ptr()
     code = _lib.BF16 if dt == torch.bfloat16 else _lib.F32
     _lib.check(profiler.launch("conv_simt", lambda: fn(C.byref(d), code, sp), flops, 0.0, tag), "conv_simt")
+    if det_pool:
+        v = _lib.view4(out)
+        stride = int(pool_stride) if pool_stride else (pool_sum.stride(0) if pool_sum.dim() == 2 else out.shape[3])
+        _lib.check(profiler.launch("channel_sums", lambda: _lib.lib().pmoe_channel_sums(C.byref(v), code, pool_sum.data_ptr(), stride, sp)),
+                   "channel_sums")
     return out
 
 

@@ -62,10 +62,10 @@ def test_gpu_backbones_vs_live_reference(arch):
     ref_err = sorted(abs(g["grads"][n]["norm"] - n64[n]) / max(n64[n], 1e-12) for n in g["grads"])
     mp, wp = ref_err[len(ref_err) // 2], ref_err[-1]
     best = None
-    for attempt in range(16):
-        # A pre-activation within rounding distance of zero flips its ReLU mask and moves every gradient upstream of it by
-        # ~1e-3 (tests/test_gpu_train.py, scripts/gpu_determinism.py): every attempt must stay inside the loose bound that
-        # covers a flip; the step is repeated until one lands in the mode the reference (and fp64) sit in.
+    for attempt in range(1):
+        # The fp32 parity mode reduces its statistics in a fixed order, so the step is reproducible (round 1 repeated it up to 16
+        # times until it landed in the reference's ReLU-mask mode): one attempt, the typical tensor within 4x the reference's own
+        # distance to fp64, the worst one inside the bound that covers a flipped mask.
         with config.use_precision("fp32"):
             net = get_backbone(arch=arch, n_frames=4, pretrained=False, gamma=2, b=1, n_channels=3)
             net.load_state_dict(sd, strict=True)
@@ -86,8 +86,6 @@ def test_gpu_backbones_vs_live_reference(arch):
         assert len(our_err) > 100 and e_eval < 1e-4 and e_train < 1e-4 and bn_err < 1e-4
         assert mc < 5e-3 and wc < max(10 * wp + 1e-3, 1e-1)
         best = mc if best is None else min(best, mc)
-        if mc < max(4 * mp, 1e-4):
-            break
     assert best < max(4 * mp, 1e-4)
     with config.use_precision("bf16"):
         net = get_backbone(arch=arch, n_frames=4, pretrained=False, gamma=2, b=1, n_channels=3)

@@ -69,7 +69,9 @@ def test_multi_stream_experts_match_single_stream_fp32():
         print("\n[fp32 %s vs single stream] loss %.7f vs %.7f | gradients median %.2e worst %.2e (single vs single: %.2e / %.2e) | BN statistics %.2e"
               % (tag, l1, l0, med, worst, base[0], base[1], bn))
         assert abs(l1 - l0) < 1e-5 * max(1.0, abs(l0)) and bn < 1e-5
-        assert med < max(1e-4, 10 * base[0]) and worst < max(5e-2, 10 * base[1])   # worst: a ReLU mask flipped by summation order (see test_gpu_moe.py)
+        # a ReLU mask flipped by summation order (the fp32 step has two modes, scripts/gpu_determinism.py) moves the median to ~1e-3 and
+        # single tensors to ~5e-2; a missing cross-stream dependency gives O(1) garbage
+        assert med < 3e-3 and worst < max(1e-1, 2 * base[1])
 
 
 def test_multi_stream_experts_match_single_stream_bf16():

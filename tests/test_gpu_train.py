@@ -73,36 +73,33 @@ def test_unet_stage0_train_step_fp32_vs_reference_golden():
     g = load("unet_stage0.pt")
     sd = O.seeded_state_dict(O.make_spec(O.unet_spec, 3, 23), g["seed"])
     up = upstream_seg_grad(g["logits_train"], g["mask"])  # exactly what the reference back-propagated
-    # Typical gradient error is ~5e-6, but the step is not a continuous function of its rounding: the forward differs by
-    # ~2e-6 run to run (atomic summation order), a pre-activation within that distance of 0 flips its ReLU mask, and at this
-    # size (B=2, 32x32: 8 values per channel at the bottleneck) one flip moves a BatchNorm bias gradient (a cancelling sum)
-    # by ~1e-3 and shifts everything upstream of it — scripts/gpu_determinism.py shows the modes (about 3:1), and the CPU
-    # reference sits in one of them by the same chance.  So: EVERY attempt must stay inside the loose bound that covers a
-    # flip, and the step is repeated until one attempt lands in the reference's mode, where the tight median bound holds.
-    best = None
-    for attempt in range(24):
+    # The fp32 parity mode reduces its batch statistics and per-image pool sums in a fixed order (conv_simt.cu, channel_sums): the
+    # forward is bit-reproducible, so the ReLU masks — and with them every gradient — no longer depend on the order atomics land in,
+    # and ONE attempt is held to the bounds (round 1 repeated the step until it landed in the reference's mask mode).
+    outs = []
+    for attempt in range(2):
         with config.use_precision("fp32"):
             net = UNet(3, 23)
             net.load_state_dict(sd, strict=True)
             net = net.cuda().train()
             logits = net(g["img"].cuda())
             logits.backward(gradient=up.cuda())
-        e_out = rel_err(logits.detach().cpu(), g["logits_train"])
-        wn, wv, n = grad_report(net.named_parameters(), g["grads"])
-        bn_err = max(rel_err(net.state_dict()[k].float().cpu(), v.float()) for k, v in g["bn"].items() if v.is_floating_point())
-        errs = sorted(abs(p.grad.detach().double().norm().item() - g["grads"][nm]["norm"]) / max(g["grads"][nm]["norm"], 1e-8)
-                      for nm, p in net.named_parameters() if nm in g["grads"])
-        med = errs[len(errs) // 2]
-        print("\n[fp32] unet train #%d: logits rel %.3e | grad norm err %.3e (%s) | sample err %.3e (%s) | median %.3e | bn %.3e"
-              % (attempt, e_out, wn[0], wn[1], wv[0], wv[1], med, bn_err))
-        assert n > 40
-        assert e_out < 1e-4
-        assert bn_err < 1e-4
-        assert wn[0] < 5e-3 and wv[0] < 5e-3 and med < 5e-3
-        best = med if best is None else min(best, med)
-        if med < 1e-4:
-            break
-    assert best < 1e-4
+        outs.append(logits.detach().clone())
+    assert torch.equal(outs[0], outs[1])                       # reproducible forward
+    e_out = rel_err(logits.detach().cpu(), g["logits_train"])
+    wn, wv, n = grad_report(net.named_parameters(), g["grads"])
+    bn_err = max(rel_err(net.state_dict()[k].float().cpu(), v.float()) for k, v in g["bn"].items() if v.is_floating_point())
+    errs = sorted(abs(p.grad.detach().double().norm().item() - g["grads"][nm]["norm"]) / max(g["grads"][nm]["norm"], 1e-8)
+                  for nm, p in net.named_parameters() if nm in g["grads"])
+    med = errs[len(errs) // 2]
+    print("\n[fp32] unet train: logits rel %.3e | grad norm err %.3e (%s) | sample err %.3e (%s) | median %.3e | bn %.3e"
+          % (e_out, wn[0], wn[1], wv[0], wv[1], med, bn_err))
+    assert n > 40
+    assert e_out < 1e-4
+    assert bn_err < 1e-4
+    # a pre-activation within 1e-6 of zero can still sit on the other side of zero than in the CPU reference (different, but now
+    # fixed, summation order): the worst tensor keeps the bound that covers one such flip, the typical tensor north_star's 1e-4
+    assert wn[0] < 5e-3 and wv[0] < 5e-3 and med < 1e-4
     assert int(net.state_dict()["dwn_1.1.num_batches_tracked"]) == 1
 
 

@@ -17,12 +17,15 @@ from oracle.gen_golden import import_reference, grad_summary, bn_summary  # noqa
 def main():
     import_reference()
     from model.blocks.backbone import get_backbone
-    for arch, seed in (("resnet34", 31), ("resnet50", 32)):
+    # input seeds: resnet34's first choice (131) put one pre-activation within 1e-7 of zero — a 1e-7 input perturbation flipped
+    # its ReLU mask and moved the median gradient by 3.6e-4 on the CPU reference itself, so no implementation with another
+    # summation order could be held to 1e-4 on it; 531 has no such tie (perturbed run: median 3e-7, worst 4e-6)
+    for arch, seed, xseed in (("resnet34", 31, 531), ("resnet50", 32, 132)):
         spec = O.make_spec(O.resnet_spec, 12, 2, 1, arch)
         sd = O.seeded_state_dict(spec, seed)
         net = get_backbone(arch=arch, n_frames=4, pretrained=False, gamma=2, b=1, n_channels=3)
         net.load_state_dict(sd, strict=True)
-        g = torch.Generator().manual_seed(100 + seed)
+        g = torch.Generator().manual_seed(xseed)
         x = torch.rand(2, 12, 64, 64, generator=g)
         cot = torch.randn(2, 512, generator=g) * 1e-2
         net.eval()

@@ -98,6 +98,7 @@ def compare_grads(tag, g_cuda, g_fp32, g_emu, pick=None):
     m32, _, _ = quantiles(e_f32)
     ms, _, _ = quantiles(e_self)
     print("   yardsticks vs the fp32 oracle (ReLU-mask flips of bf16 storage): product median %.3e | bf16-storage oracle median %.3e" % (m32, ms))
+    compare_grads.last = (e_emu, e_f32, e_self)
     return med, p90, worst, m32, ms, len(names)
 
 
@@ -279,5 +280,10 @@ def test_block_gradients_bf16_vs_oracle(case):
     med, p90, worst, m32, ms, n = compare_grads(name + " bf16 grads", gc, res["fp32"][1], res["bf16"][1])
     assert n == len(gc)
     assert e_out < 1e-2
-    assert worst < max(1e-2, 2.5 * noise)    # every gradient tensor vs the reference in bf16: 1e-2, or the comparison's own noise floor
+    # every gradient tensor vs the reference in bf16: 1e-2, or the comparison's own noise floor — or, where the product computes a
+    # gradient in HIGHER precision than bf16 storage allows the emulation (the stem's first ECA gate takes its gradient from the fp32
+    # per-image weight gradient instead of a bf16 data gradient), at least as close to the fp32 oracle as the emulation is
+    e_emu, e_f32, e_self = compare_grads.last
+    for nm in e_emu:
+        assert e_emu[nm] < max(1e-2, 2.5 * noise) or e_f32[nm] <= 1.05 * e_self[nm], (nm, e_emu[nm], e_f32[nm], e_self[nm])
     assert m32 < 1.25 * ms + 1e-2

@@ -61,6 +61,16 @@ def test_gpu_backbones_vs_live_reference(arch):
     n64 = {n: leaf64[n].grad.norm().item() for n in g["grads"]}
     ref_err = sorted(abs(g["grads"][n]["norm"] - n64[n]) / max(n64[n], 1e-12) for n in g["grads"])
     mp, wp = ref_err[len(ref_err) // 2], ref_err[-1]
+    # conditioning of this step: the fp32 oracle with its input moved by 1e-6 relative (what another summation order does to the
+    # first layers' sums) against fp64 — with 8 values per channel in the last stage, ReLU masks flip under such a perturbation and
+    # the reference's OWN median gradient error goes from 5e-7 to 1e-4..1e-3. No second implementation can be held tighter than that.
+    sens = 0.0
+    for ps in (1, 2):
+        leaf32 = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone()) for k, v in sd.items()}
+        xp = g["x"] * (1 + 1e-6 * torch.randn(g["x"].shape, generator=torch.Generator().manual_seed(ps)))
+        (O.resnet_eca(xp, leaf32, "", True, arch) * g["cot"]).sum().backward()
+        pe = sorted(abs(leaf32[n].grad.double().norm().item() - n64[n]) / max(n64[n], 1e-12) for n in g["grads"])
+        sens = max(sens, pe[len(pe) // 2])
     best = None
     for attempt in range(1):
         # The fp32 parity mode reduces its statistics in a fixed order, so the step is reproducible (round 1 repeated it up to 16
@@ -86,7 +96,8 @@ def test_gpu_backbones_vs_live_reference(arch):
         assert len(our_err) > 100 and e_eval < 1e-4 and e_train < 1e-4 and bn_err < 1e-4
         assert mc < 5e-3 and wc < max(10 * wp + 1e-3, 1e-1)
         best = mc if best is None else min(best, mc)
-    assert best < max(4 * mp, 1e-4)
+    print("[%s] conditioning: reference fp32 with a 1e-6 input perturbation vs fp64: median %.2e" % (arch, sens))
+    assert best < max(4 * mp, 1e-4, 2 * sens)
     with config.use_precision("bf16"):
         net = get_backbone(arch=arch, n_frames=4, pretrained=False, gamma=2, b=1, n_channels=3)
         net.load_state_dict(sd, strict=True)

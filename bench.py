@@ -377,7 +377,7 @@ def run_train_leg(args, rank, world, dev, peaks, local_rank):
     n_micro = per // micro
     frames, hw = args.train_frames, args.train_hw
     torch.manual_seed(0)
-    cfg = conf.stage2_model_cfg("moe", K, n_frames=frames)
+    cfg = conf.stage2_model_cfg(args.train_type, K, n_frames=frames)
     model = get_model(cfg).to(dev).train()
     wrapped = dp.DataParallel(model, gradient_as_bucket_view=(n_micro == 1)) if world > 1 else model
     opt = optim.FusedAdam([p for p in model.parameters() if p.requires_grad], lr=2e-4, betas=(0.9, 0.999), eps=1e-8, amsgrad=True)
@@ -554,7 +554,7 @@ def run_train_leg(args, rank, world, dev, peaks, local_rank):
     if rank != 0:
         return None
     ms_step = ms_value / K_steps
-    gf = train_gf_per_sample(K, frames, hw)
+    gf = train_gf_per_sample(1 if args.train_type == "moe_shared" else K, frames, hw)   # moe_shared: ONE shared encoder
     tc_ms = sum(prof[k]["ms"] for k in TC_KINDS if k in prof)
     tc_fl = sum(prof[k]["flops"] for k in TC_KINDS if k in prof)
     tc_n = sum(prof[k]["launches"] for k in TC_KINDS if k in prof)
@@ -568,7 +568,7 @@ def run_train_leg(args, rank, world, dev, peaks, local_rank):
         "metric": "train_samples_per_sec", "value": Bg / (ms_step / 1e3), "unit": "samples/s", "n_gpus": world, "steps": K_steps,
         "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": TRAIN_WORKLOAD % (K, frames, hw, hw), "global_batch": Bg, "batch_per_gpu": per, "micro_batch": micro,
+        "config": {"workload": (TRAIN_WORKLOAD % (K, frames, hw, hw)).replace("type='moe'", "type='%s'" % args.train_type), "global_batch": Bg, "batch_per_gpu": per, "micro_batch": micro,
                    "parallelism": "dp%d (batch-sharded, bucketed NCCL all-reduce inside the captured graph)" % world if world > 1 else "1 GPU",
                    "launch_mode": mode, "params": params,
                    "l2": "activations of one micro-batch (%.0f GB) exceed the 126 MB L2 many times over" % (77e-3 * micro * K),
@@ -642,6 +642,8 @@ def main():
     ap.add_argument("--no-infer", action="store_true", help="skip the nested inference leg (BASELINE configs[1])")
     ap.add_argument("--train-batch", type=int, default=512, help="GLOBAL training batch, sharded over the ranks")
     ap.add_argument("--train-experts", type=int, default=6)
+    ap.add_argument("--train-type", default="moe", choices=["moe", "moe_alt", "moe_shared"],
+                    help="mixture flavour of the training leg (moe = BASELINE configs[2] / SURVEY 3a; moe_shared = 3b)")
     ap.add_argument("--train-micro", type=int, default=256, help="largest micro-batch one rank runs at once")
     ap.add_argument("--train-frames", type=int, default=4, help="frames stacked per sample (12 = 3 cameras x 4: BASELINE configs[4])")
     ap.add_argument("--train-hw", type=int, default=224, help="frame height = width (448: BASELINE configs[4])")

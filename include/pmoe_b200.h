@@ -330,6 +330,10 @@ int pmoe_unpack_scatter(const float* packed, const int32_t* idx, float* dst, int
  * layer), `dst` / `accumulate` are HOST arrays of n_groups device pointers / flags (a NULL pointer skips its group). */
 int pmoe_unpack_scatter_group(const float* packed, const int32_t* idx, float* const* dst, const int32_t* accumulate,
                               int32_t n_groups, int64_t n, float alpha, pmoe_stream_t stream);
+/* The same gradients through the INVERSE map (parameter element j = packed element inv[j], n_param entries): coalesced writes
+ * into the gradient slots, gathered reads of the packed gradient ([n_groups][n_packed]). The form the training path uses. */
+int pmoe_unpack_gather_group(const float* packed, const int32_t* inv, float* const* dst, const int32_t* accumulate,
+                             int32_t n_groups, int64_t n_param, int64_t n_packed, float alpha, pmoe_stream_t stream);
 /* dst[i] (+)= (float) src[i]: fp64 per-channel sums (BatchNorm weight/bias gradients, Linear bias gradients) into fp32 slots. */
 int pmoe_cvt_f64_f32(const double* src, float* dst, int32_t n, int32_t accumulate, pmoe_stream_t stream);
 

@@ -129,6 +129,22 @@ __global__ void __launch_bounds__(256) unpack_scatter_group_kernel(const float* 
   }
 }
 
+// The same result through the INVERSE map (parameter element j <- packed element inv[j]): the writes into the gradient slot are
+// coalesced and only the fp32 reads are gathered (the scatter form writes 4-byte words nine floats apart for a 3x3 weight: every
+// store a partial sector). grid.y = group (1 for a single parameter).
+__global__ void __launch_bounds__(256) unpack_gather_group_kernel(const float* __restrict__ packed, const int32_t* __restrict__ inv,
+                                                                  ScatterGroup grp, int64_t n_param, int64_t n_packed, float alpha) {
+  const int g = blockIdx.y;
+  float* __restrict__ dst = grp.dst[g];
+  if (dst == nullptr) return;
+  const int acc = grp.accumulate[g];
+  const float* __restrict__ src = packed + (int64_t)g * n_packed;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_param; j += (int64_t)gridDim.x * blockDim.x) {
+    const float v = alpha * __ldg(src + __ldg(inv + j));
+    dst[j] = acc ? dst[j] + v : v;
+  }
+}
+
 // dst[i] (+)= (float) src[i]: fp64 per-channel reductions (BatchNorm / bias gradients) into fp32 gradient slots.
 __global__ void __launch_bounds__(256) cvt_f64_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int n, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,4 +224,24 @@ extern "C" int pmoe_unpack_scatter_group(const float* packed, const int32_t* idx
   dim3 grid((unsigned)gx, (unsigned)n_groups);
   unpack_scatter_group_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(packed, idx, grp, n, alpha);
   return check_launch("unpack_scatter_group");
+}
+
+extern "C" int pmoe_unpack_gather_group(const float* packed, const int32_t* inv, float* const* dst, const int32_t* accumulate,
+                                        int32_t n_groups, int64_t n_param, int64_t n_packed, float alpha, pmoe_stream_t stream_) {
+  if (n_param <= 0 || n_groups <= 0) return PMOE_OK;
+  if (!packed || !inv || !dst || !accumulate || n_groups > 16) {
+    set_error("unpack_gather_group: null pointer or more than 16 groups");
+    return PMOE_ERR_ARG;
+  }
+  ScatterGroup grp;
+  for (int g = 0; g < 16; ++g) {
+    grp.dst[g] = g < n_groups ? dst[g] : nullptr;
+    grp.accumulate[g] = g < n_groups ? accumulate[g] : 0;
+  }
+  const int64_t blocks = (n_param + 1023) / 1024;
+  int gx = grid_for(blocks);
+  if (n_groups > 1 && gx > 128) gx = 128;
+  dim3 grid((unsigned)gx, (unsigned)n_groups);
+  unpack_gather_group_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(packed, inv, grp, n_param, n_packed, alpha);
+  return check_launch("unpack_gather_group");
 }

@@ -28,12 +28,26 @@ _current = None               # registry of the module whose pass is running
 
 class Pack:
     """One packed operand: `out` (static buffer) = gather(owner, idx)."""
-    __slots__ = ("owner", "idx", "out", "ver", "stamp", "code", "key")
+    __slots__ = ("owner", "idx", "out", "ver", "stamp", "code", "key", "_inv")
 
     def __init__(self, owner, idx, out, key):
         self.owner, self.idx, self.out, self.key = owner, idx, out, key
+        self._inv = None
         self.ver, self.stamp = None, -1
         self.code = _lib.BF16 if out.dtype == torch.bfloat16 else _lib.F32
+
+    def inverse(self):
+        """int32 map parameter element -> packed element (every parameter element appears exactly once in a forward packing)."""
+        if self._inv is None:
+            flat = self.idx.reshape(-1).long()
+            pos = torch.nonzero(flat >= 0).reshape(-1)
+            n = self.owner.numel()
+            inv = torch.full((n,), -1, dtype=torch.int64, device=flat.device)
+            inv[flat[pos]] = pos
+            if pos.numel() != n or bool((inv < 0).any()):
+                raise RuntimeError("pmoe_b200 packs: this packing is not a bijection onto the parameter (no inverse map)")
+            self._inv = inv.to(torch.int32).contiguous()
+        return self._inv
 
     def version(self):
         return (self.owner.data_ptr(), self.owner._version)
@@ -186,6 +200,23 @@ def scatter_grad(packed_grad, idx, dst_flat, accumulate, alpha=1.0):
     check(profiler.launch("unpack_scatter", lambda: lib().pmoe_unpack_scatter(
         packed_grad.data_ptr(), idx.data_ptr(), dst_flat.data_ptr(), idx.numel(), float(alpha), int(accumulate), stream_ptr())),
         "unpack_scatter")
+
+
+def unpack_grads(packed_grad, pack, dst_flats, accumulates, alpha=1.0):
+    """Packed fp32 weight gradient(s) -> gradient slot(s) in the parameter layout through the pack's inverse map (coalesced
+    writes). packed_grad: one packed gradient (shape of pack.idx) with one slot, or (K, ...) stacked gradients of K equally shaped
+    parameters with K slots (a None slot is skipped)."""
+    inv = pack.inverse()
+    n_packed = pack.idx.numel()
+    K = len(dst_flats)
+    assert packed_grad.dtype == torch.float32 and packed_grad.is_contiguous() and packed_grad.numel() == K * n_packed
+    for g0 in range(0, K, 16):
+        g1 = min(K, g0 + 16)
+        ptrs = (C.c_void_p * (g1 - g0))(*[None if d is None else d.data_ptr() for d in dst_flats[g0:g1]])
+        accs = (C.c_int32 * (g1 - g0))(*[int(bool(a)) for a in accumulates[g0:g1]])
+        base = packed_grad.data_ptr() + g0 * n_packed * 4
+        check(profiler.launch("unpack_scatter", lambda: lib().pmoe_unpack_gather_group(
+            base, inv.data_ptr(), ptrs, accs, g1 - g0, inv.numel(), n_packed, float(alpha), stream_ptr())), "unpack_gather_group")
 
 
 def scatter_grad_group(packed_grad, idx, dst_flats, accumulates, alpha=1.0):

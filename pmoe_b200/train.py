@@ -450,7 +450,7 @@ def _wgrad_to_param(tape, dwp, pack, weight):
     """Packed fp32 weight gradient -> the parameter's (out, in, kh, kw) gradient slot (one scatter launch)."""
     p = _owner(weight)
     slot, existed = tape.pgrad_slot(p)
-    packs.scatter_grad(dwp, pack.idx, slot, existed)
+    packs.unpack_grads(dwp if dwp.is_contiguous() else dwp.contiguous(), pack, [slot], [existed])
     tape.pgrad_done(p)
 
 
@@ -466,7 +466,7 @@ def _group_to_params(tape, stacked, pack_list, params):
         slots.append(slot)
         accs.append(existed)
         done.append(prm)
-    packs.scatter_grad_group(stacked.contiguous(), pack_list[0].idx, slots, accs)
+    packs.unpack_grads(stacked.contiguous(), pack_list[0], slots, accs)
     for prm in done:
         tape.pgrad_done(prm)
 

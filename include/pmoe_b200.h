@@ -196,6 +196,26 @@ int pmoe_bn_bwd_apply_sums(const PmoeView4* dz, const PmoeView4* z, const PmoeVi
                            const double* sum_dy_xhat, float inv_n, const PmoeView4* dx, const float* fwd_scale,
                            const float* fwd_shift, double* next_sum_dx, double* next_sum_dx_x, const PmoeBnParamGrads* param_grads,
                            pmoe_stream_t stream);
+/* The tail of the ResNet stem in training, torchvision's bn1 -> relu -> MaxPool2d(3, 2, 1) behind conv1 := EfficientConvBlock
+ * (reference PMoE/model/blocks/backbone.py:57-61; replaces pmoe_affine_act + pmoe_maxpool_idx | pmoe_maxpool_bwd_idx +
+ * pmoe_bn_bwd_reduce + pmoe_bn_bwd_apply_sums on that path). Dense bf16 NHWC, even H and W, channel-group count dividing 256;
+ * otherwise PMOE_ERR_UNSUPPORTED and the caller runs the separate entry points.
+ *   fwd:    y = maxpool(relu(scale*x + shift)) with (scale, shift) of pmoe_bn_finalize; idx: argmax codes r*3+c as pmoe_maxpool_idx
+ *           writes them, x_at_max: x at the argmax, dense bf16 (n, oh, ow, c) — the normalised tensor is never stored.
+ *   reduce: sum_dy / sum_dy_xhat of pmoe_bn_bwd_reduce for the gradient routed through pool and ReLU, from the POOLED grid
+ *           (both must be zeroed by the caller).
+ *   apply:  dx of pmoe_bn_bwd_apply for every input pixel (the routed gradient is gathered from the windows that hold the pixel,
+ *           never stored); next_sum_dx / next_sum_dx_x (optional, zeroed by the caller) and param_grads as in
+ *           pmoe_bn_bwd_apply_sums. inv_n = 1 / (n*h*w) of x. */
+int pmoe_bn_relu_maxpool_fwd(const PmoeView4* x, const float* scale, const float* shift, const PmoeView4* y, uint8_t* idx,
+                             void* x_at_max, pmoe_stream_t stream);
+int pmoe_bn_relu_maxpool_bwd_reduce(const PmoeView4* dy, const void* x_at_max, const float* fwd_scale, const float* fwd_shift,
+                                    const float* mean, const float* rstd, double* sum_dy, double* sum_dy_xhat, pmoe_stream_t stream);
+int pmoe_bn_relu_maxpool_bwd_apply(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* x, const float* fwd_scale,
+                                   const float* fwd_shift, const float* mean, const float* rstd, const float* gamma,
+                                   const double* sum_dy, const double* sum_dy_xhat, float inv_n, const PmoeView4* dx,
+                                   double* next_sum_dx, double* next_sum_dx_x, const PmoeBnParamGrads* param_grads,
+                                   pmoe_stream_t stream);
 int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* dx, int32_t dtype, int32_t k, int32_t stride,
                      int32_t pad, int32_t accumulate, pmoe_stream_t stream);
 int pmoe_maxpool_bwd_idx(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* dx, int32_t dtype, int32_t k,

@@ -1,0 +1,384 @@
+// The tail of the ResNet stem in training: torchvision's bn1 -> ReLU -> MaxPool2d(3, 2, 1) directly behind the stem block
+// (model/blocks/backbone.py:57-61 keeps torchvision's `bn1`, `relu`, `maxpool` after `conv1 := EfficientConvBlock`). At 224^2 x 64
+// channels these are the largest memory-bound tensors of an expert (1.6 GB at 256 samples), and as separate launches the chain
+// reads / writes them 5 + 6.4 times (apply, pool | pool backward, BatchNorm reduce, BatchNorm apply). Here:
+//
+//  forward   p = maxpool(relu(scale * x + shift)) WITHOUT materialising the normalised tensor: relu(scale*x + shift) is monotone in
+//            x, so the window maximum is taken on x itself (sign-flipped for channels with scale < 0) and the affine + ReLU is
+//            applied once per OUTPUT. Stores p, the argmax codes and x at the argmax (exact bf16 bits, 1/4 of a tensor).
+//  reduce    the two BatchNorm-backward sums need dz = route(dp) * mask only where dz != 0, i.e. at the argmax positions: a pass
+//            over the POOLED grid (dp and x-at-argmax: half a tensor instead of three).
+//  apply     dx = gamma * rstd * (dz*m - c1 - xhat * c2) for every input pixel with dz gathered from the (<= 4) windows that
+//            hold the pixel (the pair form of maxpool3s2_bwd_pair_kernel) — the pooled gradient is never scattered to a full
+//            tensor — plus the backward sums of the UPSTREAM BatchNorm (x is its ReLU output) and the affine gradients.
+//
+// Dense bf16 NHWC, even H and W, 256 % (C/8) == 0. Ties between equal inputs go to the first window element like ATen's; ties
+// between equal OUTPUTS of different inputs go to the larger input (the fp32 reference has no such ties; windows whose maximum is
+// <= 0 pass no gradient whichever position is recorded; a channel whose gamma is exactly 0 is constant, and only its own d gamma
+// depends on the position).
+#include <cuda_bf16.h>
+
+#include "host_util.h"
+#include "reduce.cuh"
+
+namespace pmoe {
+
+__device__ __forceinline__ void st_bf16x8_to_f32(const uint4& r, float (&v)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    v[2 * q] = __uint_as_float(w[q] << 16);
+    v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint32_t st_pack2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint4 st_f32_to_bf16x8(const float (&v)[8]) {
+  return make_uint4(st_pack2(v[0], v[1]), st_pack2(v[2], v[3]), st_pack2(v[4], v[5]), st_pack2(v[6], v[7]));
+}
+__device__ __forceinline__ void st_load8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// ---------------------------------------------------------------------------------------------------------------- forward
+__global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ idx,
+                                                                  uint4* __restrict__ xmax, int H, int W, int OH, int OW, int cg,
+                                                                  const float* __restrict__ scale, const float* __restrict__ shift) {
+  const int n = blockIdx.x / OH, oh = blockIdx.x - n * OH;
+  const int row_items = OW * cg;
+  const uint4* img = x + (size_t)n * H * W * cg;
+  const int g = threadIdx.x % cg;   // 256 % cg == 0 and the item stride is a multiple of 256: one channel group per thread
+  float sc[8], sh[8];
+  st_load8(scale + g * 8, sc);
+  st_load8(shift + g * 8, sh);
+  uint32_t flip[4];                  // sign-bit mask of the channels whose scale is negative (their window MINIMUM wins)
+#pragma unroll
+  for (int q = 0; q < 4; ++q) flip[q] = (sc[2 * q] < 0.f ? 0x00008000u : 0u) | (sc[2 * q + 1] < 0.f ? 0x80000000u : 0u);
+  for (int item = blockIdx.y * blockDim.x + threadIdx.x; item < row_items; item += gridDim.y * blockDim.x) {
+    const int ow = item / cg;
+    float m[8];
+    uint32_t arg[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      m[q] = -INFINITY;
+      arg[q] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int iw = ow * 2 - 1 + c;
+        if (iw < 0 || iw >= W) continue;
+        uint4 raw = __ldg(img + ((size_t)ih * W + iw) * cg + g);
+        raw.x ^= flip[0];
+        raw.y ^= flip[1];
+        raw.z ^= flip[2];
+        raw.w ^= flip[3];
+        float v[8];
+        st_bf16x8_to_f32(raw, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (v[q] > m[q]) {  // the first maximum in row-major window order wins
+            m[q] = v[q];
+            arg[q] = (uint32_t)(r * 3 + c);
+          }
+      }
+    }
+    uint4 xm = st_f32_to_bf16x8(m);   // exact: the values are bf16 already
+    xm.x ^= flip[0];
+    xm.y ^= flip[1];
+    xm.z ^= flip[2];
+    xm.w ^= flip[3];
+    float xv[8], o[8];
+    st_bf16x8_to_f32(xm, xv);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = fmaxf(fmaf(xv[q], sc[q], sh[q]), 0.f);
+    const size_t off = ((size_t)blockIdx.x * OW + ow) * cg + g;
+    y[off] = st_f32_to_bf16x8(o);
+    xmax[off] = xm;
+    uint2 pk;
+    pk.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+    pk.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+    idx[off] = pk;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- reduce
+__global__ void __launch_bounds__(kRedThreads) bn_relu_maxpool_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ xmax,
+                                                                                 long long npix, int cg, const float* __restrict__ fsc,
+                                                                                 const float* __restrict__ fsh, const float* __restrict__ mean,
+                                                                                 const float* __restrict__ rstd, double* __restrict__ sum_dy,
+                                                                                 double* __restrict__ sum_dy_xhat, long long pix_per_block) {
+  __shared__ float sm[kRedThreads * 8];
+  const int lanes = blockDim.x / cg;
+  const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
+  float sc[8], sh[8];
+  st_load8(fsc + g * 8, sc);
+  st_load8(fsh + g * 8, sh);
+  const long long p0 = (long long)blockIdx.x * pix_per_block;
+  long long p1 = p0 + pix_per_block;
+  if (p1 > npix) p1 = npix;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (lane < lanes) {
+    for (long long p = p0 + lane; p < p1; p += lanes) {
+      float d[8], xv[8];
+      st_bf16x8_to_f32(__ldg(dy + p * cg + g), d);
+      st_bf16x8_to_f32(__ldg(xmax + p * cg + g), xv);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float dm = fmaf(xv[q], sc[q], sh[q]) > 0.f ? d[q] : 0.f;
+        a[q] += dm;
+        b[q] = fmaf(dm, xv[q], b[q]);
+      }
+    }
+  }
+  float ta[kRedMaxIter], tb[kRedMaxIter];
+  block_channel_sum(a, sm, cg, lanes, ta);
+  block_channel_sum(b, sm, cg, lanes, tb);
+#pragma unroll
+  for (int j = 0; j < kRedMaxIter; ++j) {
+    const int c = threadIdx.x + j * kRedThreads;
+    if (c < cg * 8) {
+      atomicAdd(sum_dy + c, (double)ta[j]);
+      atomicAdd(sum_dy_xhat + c, (double)__ldg(rstd + c) * ((double)tb[j] - (double)__ldg(mean + c) * (double)ta[j]));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- apply
+struct StParamGrads {
+  float* dgamma;
+  float* dbeta;
+  int n;
+  int accumulate;
+};
+
+__device__ __forceinline__ void st_add_masked(float (&o)[8], const uint2& code, const uint4& grad, uint32_t want) {
+  const uint32_t w4 = want * 0x01010101u;
+  const uint32_t m0 = __vcmpeq4(code.x, w4), m1 = __vcmpeq4(code.y, w4);
+  const uint32_t gq[4] = {grad.x & __byte_perm(m0, 0u, 0x1100u), grad.y & __byte_perm(m0, 0u, 0x3322u),
+                          grad.z & __byte_perm(m1, 0u, 0x1100u), grad.w & __byte_perm(m1, 0u, 0x3322u)};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    o[2 * q] += __uint_as_float(gq[q] << 16);
+    o[2 * q + 1] += __uint_as_float(gq[q] & 0xffff0000u);
+  }
+}
+
+template <bool NEXT>
+__global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_apply_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
+                                                                        const uint4* __restrict__ x, uint4* __restrict__ dx, int rows, int H,
+                                                                        int W, int OH, int OW, int cg, const float* __restrict__ fsc,
+                                                                        const float* __restrict__ fsh, const float* __restrict__ mean,
+                                                                        const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                        const double* __restrict__ sum_dy,
+                                                                        const double* __restrict__ sum_dy_xhat, float inv_n,
+                                                                        double* __restrict__ next_s1, double* __restrict__ next_s2,
+                                                                        StParamGrads pg) {
+  __shared__ float sm_next[NEXT ? kRedThreads * 8 : 8];
+  if (blockIdx.x == 0 && pg.n > 0) {   // the BatchNorm affine gradients are the two reductions themselves
+    for (int c = threadIdx.x; c < pg.n; c += blockDim.x) {
+      if (pg.dbeta) pg.dbeta[c] = (pg.accumulate ? pg.dbeta[c] : 0.f) + (float)sum_dy[c];
+      if (pg.dgamma) pg.dgamma[c] = (pg.accumulate ? pg.dgamma[c] : 0.f) + (float)sum_dy_xhat[c];
+    }
+  }
+  const int items = (W >> 1) * cg;
+  const int g = threadIdx.x % cg;
+  float sc[8], sh[8], A[8], Bc[8], Cc[8];
+  st_load8(fsc + g * 8, sc);
+  st_load8(fsh + g * 8, sh);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {  // dx = gamma*rstd*(d - c1 - (x - mean)*rstd*c2) = A*d + B*x + C
+    const int c = g * 8 + q;
+    const double r = (double)__ldg(rstd + c), m = (double)__ldg(mean + c), gm = gamma ? (double)__ldg(gamma + c) : 1.0;
+    const double c1 = sum_dy[c] * (double)inv_n, c2 = sum_dy_xhat[c] * (double)inv_n;
+    A[q] = (float)(gm * r);
+    Bc[q] = (float)(-gm * r * r * c2);
+    Cc[q] = (float)(gm * r * (r * c2 * m - c1));
+  }
+  float na[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  // a block walks whole input rows (few blocks, so the upstream sums cost a handful of atomics per channel)
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+  const int n = row / H, ih = row - n * H;
+  const bool odd = (ih & 1) != 0;
+  const int oh0 = ih >> 1;                  // row-window that holds this row at r = 1 (even row) or r = 2 (odd row)
+  const uint32_t r0 = odd ? 6u : 3u;        // r * 3
+  const bool two = odd && (oh0 + 1 < OH);   // odd rows are also row 0 of the window below
+  for (int item = threadIdx.x; item < items; item += blockDim.x) {
+    const int j = item / cg;
+    const bool right = j + 1 < OW;
+    const size_t oa = (((size_t)n * OH + oh0) * OW + j) * cg + g;
+    const size_t oc = oa + (size_t)OW * cg;
+    const uint2 zc = make_uint2(0xffffffffu, 0xffffffffu);  // code 255 never matches
+    const uint4 zg = make_uint4(0u, 0u, 0u, 0u);
+    const uint2 cA = __ldg(idx + oa);
+    const uint4 gA = __ldg(dy + oa);
+    const uint2 cB = right ? __ldg(idx + oa + cg) : zc;
+    const uint4 gB = right ? __ldg(dy + oa + cg) : zg;
+    const uint2 cC = two ? __ldg(idx + oc) : zc;
+    const uint4 gC = two ? __ldg(dy + oc) : zg;
+    const uint2 cD = (two && right) ? __ldg(idx + oc + cg) : zc;
+    const uint4 gD = (two && right) ? __ldg(dy + oc + cg) : zg;
+    const size_t od = ((size_t)row * W + 2 * j) * cg + g;
+    const uint4 x0r = __ldg(x + od), x1r = __ldg(x + od + cg);
+    float o0[8], o1[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o0[q] = o1[q] = 0.f;
+    st_add_masked(o0, cA, gA, r0 + 1u);
+    st_add_masked(o1, cA, gA, r0 + 2u);
+    st_add_masked(o1, cB, gB, r0);
+    if (two) {
+      st_add_masked(o0, cC, gC, 1u);
+      st_add_masked(o1, cC, gC, 2u);
+      st_add_masked(o1, cD, gD, 0u);
+    }
+    float x0[8], x1[8];
+    st_bf16x8_to_f32(x0r, x0);
+    st_bf16x8_to_f32(x1r, x1);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float d0 = fmaf(x0[q], sc[q], sh[q]) > 0.f ? o0[q] : 0.f;   // ReLU mask of the fused layer, recomputed from x
+      const float d1 = fmaf(x1[q], sc[q], sh[q]) > 0.f ? o1[q] : 0.f;
+      o0[q] = fmaf(A[q], d0, fmaf(Bc[q], x0[q], Cc[q]));
+      o1[q] = fmaf(A[q], d1, fmaf(Bc[q], x1[q], Cc[q]));
+    }
+    const uint4 p0 = st_f32_to_bf16x8(o0), p1 = st_f32_to_bf16x8(o1);
+    dx[od] = p0;
+    dx[od + cg] = p1;
+    if (NEXT) {  // backward sums of the upstream BatchNorm whose ReLU output x is: what a reduce pass would read back (rounded dx)
+      float v0[8], v1[8];
+      st_bf16x8_to_f32(p0, v0);
+      st_bf16x8_to_f32(p1, v1);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        na[q] += (x0[q] > 0.f ? v0[q] : 0.f) + (x1[q] > 0.f ? v1[q] : 0.f);
+        nb[q] = fmaf(v0[q], x0[q], fmaf(v1[q], x1[q], nb[q]));
+      }
+    }
+  }
+  }
+  if (NEXT) {
+    float ta[kRedMaxIter], tb[kRedMaxIter];
+    block_channel_sum(na, sm_next, cg, blockDim.x / cg, ta);
+    block_channel_sum(nb, sm_next, cg, blockDim.x / cg, tb);
+#pragma unroll
+    for (int j = 0; j < kRedMaxIter; ++j) {
+      const int c = threadIdx.x + j * kRedThreads;
+      if (c < cg * 8) {
+        atomicAdd(next_s1 + c, (double)ta[j]);
+        atomicAdd(next_s2 + c, (double)tb[j]);
+      }
+    }
+  }
+}
+
+static bool st_dense(const PmoeView4* v) {
+  return v && v->ptr && v->c % 8 == 0 && ((uintptr_t)v->ptr % 16) == 0 && v->sw == v->c && v->sh == (int64_t)v->w * v->c &&
+         v->sn == (int64_t)v->h * v->w * v->c;
+}
+
+static int st_geometry(const PmoeView4* x, const PmoeView4* y, const char* what) {
+  if (!st_dense(x) || !st_dense(y)) {
+    set_error("%s: dense 16-byte aligned NHWC bf16 tensors with a multiple of 8 channels", what);
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  const int cg = x->c / 8;
+  if (x->h % 2 || x->w % 2 || y->h != x->h / 2 || y->w != x->w / 2 || y->n != x->n || y->c != x->c || cg > 256 || 256 % cg != 0) {
+    set_error("%s: MaxPool2d(3, 2, 1) of an even-sized input, channel-group count dividing 256", what);
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  if ((long long)x->n * x->h > 2147483647LL) {
+    set_error("%s: too many rows", what);
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  return PMOE_OK;
+}
+
+}  // namespace pmoe
+
+using namespace pmoe;
+
+extern "C" int pmoe_bn_relu_maxpool_fwd(const PmoeView4* x, const float* scale, const float* shift, const PmoeView4* y, uint8_t* idx,
+                                        void* x_at_max, pmoe_stream_t stream_) {
+  int rc = st_geometry(x, y, "bn_relu_maxpool_fwd");
+  if (rc) return rc;
+  if (!scale || !shift || !idx || !x_at_max || ((uintptr_t)scale % 16) || ((uintptr_t)shift % 16) || ((uintptr_t)idx % 8) || ((uintptr_t)x_at_max % 16)) {
+    set_error("bn_relu_maxpool_fwd: scale / shift (16-byte aligned), argmax codes and x-at-argmax buffers are required");
+    return PMOE_ERR_ARG;
+  }
+  const int cg = x->c / 8;
+  dim3 grid((unsigned)(y->n * y->h), (unsigned)((y->w * cg + 255) / 256));
+  bn_relu_maxpool_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const uint4*>(x->ptr), static_cast<uint4*>(y->ptr), reinterpret_cast<uint2*>(idx), static_cast<uint4*>(x_at_max), x->h, x->w,
+      y->h, y->w, cg, scale, shift);
+  return check_launch("bn_relu_maxpool_fwd");
+}
+
+extern "C" int pmoe_bn_relu_maxpool_bwd_reduce(const PmoeView4* dy, const void* x_at_max, const float* fwd_scale, const float* fwd_shift,
+                                               const float* mean, const float* rstd, double* sum_dy, double* sum_dy_xhat,
+                                               pmoe_stream_t stream_) {
+  if (!st_dense(dy) || !x_at_max || !fwd_scale || !fwd_shift || !mean || !rstd || !sum_dy || !sum_dy_xhat || ((uintptr_t)x_at_max % 16) ||
+      ((uintptr_t)fwd_scale % 16) || ((uintptr_t)fwd_shift % 16)) {
+    set_error("bn_relu_maxpool_bwd_reduce: dense bf16 pooled gradient and all statistics are required");
+    return PMOE_ERR_ARG;
+  }
+  const int cg = dy->c / 8;
+  if (cg > 256 || 256 % cg != 0) {
+    set_error("bn_relu_maxpool_bwd_reduce: channel-group count must divide 256");
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  const long long npix = (long long)dy->n * dy->h * dy->w;
+  long long blocks = (long long)num_sms() * 8;
+  long long ppb = (npix + blocks - 1) / blocks;
+  if (ppb < 64) ppb = 64;
+  blocks = (npix + ppb - 1) / ppb;
+  bn_relu_maxpool_bwd_reduce_kernel<<<(unsigned)blocks, kRedThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const uint4*>(dy->ptr), static_cast<const uint4*>(x_at_max), npix, cg, fwd_scale, fwd_shift, mean, rstd, sum_dy, sum_dy_xhat,
+      ppb);
+  return check_launch("bn_relu_maxpool_bwd_reduce");
+}
+
+extern "C" int pmoe_bn_relu_maxpool_bwd_apply(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* x, const float* fwd_scale,
+                                              const float* fwd_shift, const float* mean, const float* rstd, const float* gamma,
+                                              const double* sum_dy, const double* sum_dy_xhat, float inv_n, const PmoeView4* dx,
+                                              double* next_sum_dx, double* next_sum_dx_x, const PmoeBnParamGrads* param_grads,
+                                              pmoe_stream_t stream_) {
+  int rc = st_geometry(x, dy, "bn_relu_maxpool_bwd_apply");
+  if (rc) return rc;
+  if (!st_dense(dx) || dx->n != x->n || dx->h != x->h || dx->w != x->w || dx->c != x->c || !idx || ((uintptr_t)idx % 8) || !fwd_scale ||
+      !fwd_shift || !mean || !rstd || !sum_dy || !sum_dy_xhat || ((uintptr_t)fwd_scale % 16) || ((uintptr_t)fwd_shift % 16) ||
+      (next_sum_dx != nullptr) != (next_sum_dx_x != nullptr)) {
+    set_error("bn_relu_maxpool_bwd_apply: bad arguments");
+    return PMOE_ERR_ARG;
+  }
+  StParamGrads pg = {nullptr, nullptr, 0, 0};
+  if (param_grads) {
+    if (param_grads->n < 0 || param_grads->n > x->c) {
+      set_error("bn_relu_maxpool_bwd_apply: parameter-gradient channel count out of range");
+      return PMOE_ERR_ARG;
+    }
+    pg.dgamma = param_grads->dgamma;
+    pg.dbeta = param_grads->dbeta;
+    pg.n = param_grads->n;
+    pg.accumulate = param_grads->accumulate;
+  }
+  const int cg = x->c / 8;
+  const int rows = x->n * x->h;
+  int grid = num_sms() * 8;
+  if (grid > rows) grid = rows;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (next_sum_dx)
+    bn_relu_maxpool_bwd_apply_kernel<true><<<grid, 256, 0, stream>>>(
+        static_cast<const uint4*>(dy->ptr), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(x->ptr), static_cast<uint4*>(dx->ptr),
+        rows, x->h, x->w, dy->h, dy->w, cg, fwd_scale, fwd_shift, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, next_sum_dx, next_sum_dx_x, pg);
+  else
+    bn_relu_maxpool_bwd_apply_kernel<false><<<grid, 256, 0, stream>>>(
+        static_cast<const uint4*>(dy->ptr), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(x->ptr), static_cast<uint4*>(dx->ptr),
+        rows, x->h, x->w, dy->h, dy->w, cg, fwd_scale, fwd_shift, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, nullptr, nullptr, pg);
+  return check_launch("bn_relu_maxpool_bwd_apply");
+}

@@ -524,7 +524,8 @@ def _stride2_dgrad_fused(tape, x, weight, dy, co_pad, ck_d, n, oh, ow, flops, ta
     ops.conv([dy], wd4, dsegs, ck_d, rows[:, :, 0], out_extra=[rows[:, :, 1]], out_cols=2 * cs, flops=flops, tag="dgrad " + tag)
 
 
-def _bn_tail_forward(tape, bn, raw, ssum, ssq, count, cout, cstore, act, residual, out, pool=None, out_stats=None):
+def _bn_finalize(tape, bn, ssum, ssq, count, cout):
+    """Batch statistics -> (mean, rstd, scale, shift) and the running-statistics update of a training BatchNorm2d."""
     track = bn.track_running_stats and bn.running_mean is not None
     mom = 0.1 if bn.momentum is None else bn.momentum
     mean, rstd, scale, shift = nhwc.bn_finalize(ssum, ssq, count, cout, bn.weight.detach(), bn.bias.detach(), bn.eps, mom,
@@ -533,6 +534,11 @@ def _bn_tail_forward(tape, bn, raw, ssum, ssq, count, cout, cstore, act, residua
         tape.touched += [bn.running_mean, bn.running_var]
         if bn.num_batches_tracked is not None:
             tape.nbt.append(bn.num_batches_tracked)
+    return mean, rstd, scale, shift
+
+
+def _bn_tail_forward(tape, bn, raw, ssum, ssq, count, cout, cstore, act, residual, out, pool=None, out_stats=None):
+    mean, rstd, scale, shift = _bn_finalize(tape, bn, ssum, ssq, count, cout)
     z_t = out if out is not None else torch.empty(raw.shape, dtype=raw.dtype, device=raw.device)
     fused = False
     if (pool is not None or out_stats is not None) and residual is None:
@@ -1250,9 +1256,75 @@ def resnet18_eca(tape, net, x, tag="backbone"):
     return resnet18_after_stem(tape, net, stem, tag)
 
 
+FUSE_STEM_TAIL = _os0.environ.get("PMOE_FUSE_STEM_TAIL", "1") != "0"   # tests switch it off to compare with the separate launches
+
+
+def bn_relu_maxpool_op(tape, bn, x, tag=""):
+    """torchvision's bn1 -> relu -> MaxPool2d(3, 2, 1) behind the ResNet stem (backbone.py:57-61) as three launches of
+    csrc/stem_tail.cu instead of five: the normalised full-resolution tensor and its gradient are never stored. Falls back to
+    bn_act_op + maxpool_op for eval-mode statistics, fp32 tapes and geometries the kernels do not take."""
+    n, h, w, cp = x.t.shape
+    if not (FUSE_STEM_TAIL and bn.training and tape.dtype == torch.bfloat16 and x.t.dtype == torch.bfloat16 and x.t.is_contiguous()
+            and h % 2 == 0 and w % 2 == 0 and cp % 8 == 0 and 256 % (cp // 8) == 0):
+        return maxpool_op(tape, bn_act_op(tape, bn, x, "relu", tag=tag), 3, 2, 1)
+    dev, c = x.t.device, x.c
+    rg = _rg(x) or _any_rg([bn.weight, bn.bias])
+    if x.stats is not None and x.stats[0].numel() == cp:
+        ssum, ssq = x.stats
+    else:
+        ssum = tape.zeros(cp, torch.float64, dev)
+        ssq = tape.zeros(cp, torch.float64, dev)
+        v = view4(x.t)
+        check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(C.byref(v), dtype_code(x.t), ssum.data_ptr(),
+                                                                                ssq.data_ptr(), stream_ptr()), io=(x.t,)), "channel_stats")
+    mean, rstd, scale, shift = _bn_finalize(tape, bn, ssum, ssq, n * h * w, c)
+    scale, shift = scale[:cp], shift[:cp]
+    p_t = torch.empty(n, h // 2, w // 2, cp, dtype=x.t.dtype, device=dev)
+    x_at_max = torch.empty_like(p_t)
+    idx = torch.empty(p_t.shape, dtype=torch.uint8, device=dev)
+    vx, vp = view4(x.t), view4(p_t)
+    check(profiler.launch("bn_relu_maxpool", lambda: lib().pmoe_bn_relu_maxpool_fwd(
+        C.byref(vx), scale.data_ptr(), shift.data_ptr(), C.byref(vp), idx.data_ptr(), x_at_max.data_ptr(), stream_ptr()),
+        io=(x.t, p_t, idx, x_at_max)), "bn_relu_maxpool_fwd")
+    pa = _new_act(tape, p_t, c, rg)
+    if tape.save and rg:
+        gamma_p = _padded_gamma(bn, cp)
+
+        def backward():
+            dp = tape.grad_of(pa)
+            if dp is None:
+                return
+            if not dp.is_contiguous():
+                dp = dp.contiguous()
+            g, existed = _grad_buffer(tape, x)
+            tmp = g if (not existed and g.is_contiguous()) else torch.empty(x.t.shape, dtype=x.t.dtype, device=dev)
+            s1 = tape.zeros(cp, torch.float64, dev)
+            s2 = tape.zeros(cp, torch.float64, dev)
+            vdp, vxx, vdx = view4(dp), view4(x.t), view4(tmp)
+            check(profiler.launch("bn_relu_maxpool_bwd_reduce", lambda: lib().pmoe_bn_relu_maxpool_bwd_reduce(
+                C.byref(vdp), x_at_max.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                s1.data_ptr(), s2.data_ptr(), stream_ptr()), io=(dp, x_at_max)), "bn_relu_maxpool_bwd_reduce")
+            pg, pdone = _bn_pgrads(tape, bn, c)
+            chain = getattr(x, "bn_relu", False) and not existed and tmp is g and FUSE_BN_CHAIN_SUMS
+            n1 = tape.zeros(cp, torch.float64, dev) if chain else None
+            n2 = tape.zeros(cp, torch.float64, dev) if chain else None
+            check(profiler.launch("bn_relu_maxpool_bwd_apply", lambda: lib().pmoe_bn_relu_maxpool_bwd_apply(
+                C.byref(vdp), idx.data_ptr(), C.byref(vxx), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                gamma_p.data_ptr(), s1.data_ptr(), s2.data_ptr(), 1.0 / (n * h * w), C.byref(vdx), _lib.ptr(n1), _lib.ptr(n2),
+                None if pg is None else C.byref(pg), stream_ptr()), io=(dp, idx, x.t, tmp)), "bn_relu_maxpool_bwd_apply")
+            if chain:
+                tape.presums[id(x)] = (n1, n2)
+            for prm in pdone:
+                tape.pgrad_done(prm)
+            if tmp is not g:
+                _axpy(tmp, g, 1.0, None, existed)
+        tape.expect(bn.weight, bn.bias)
+        tape.record(backward)
+    return pa
+
+
 def resnet18_after_stem(tape, net, stem, tag="backbone"):
-    y = bn_act_op(tape, net.bn1, stem, "relu", tag=tag + ".bn1")
-    y = maxpool_op(tape, y, 3, 2, 1)
+    y = bn_relu_maxpool_op(tape, net.bn1, stem, tag=tag + ".bn1")
     pool = None
     layers = (net.layer1, net.layer2, net.layer3, net.layer4)
     for li, layer in enumerate(layers, start=1):

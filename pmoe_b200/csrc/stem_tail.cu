@@ -44,13 +44,20 @@ __device__ __forceinline__ void st_load8(const float* p, float (&v)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------- forward
+// Two bf16 channels per 32-bit lane all the way: `set.gt.bf16x2` gives a 0xffff / 0 mask per channel, and the running maximum
+// and its 16-bit argmax code are merged with one LOP3 each (3 instructions per tap and channel PAIR instead of ~10 on unpacked
+// fp32 values: the unpacked form was ALU-pipe bound at 3.0 TB/s, ncu 65 % alu / 37 % DRAM).
+__device__ __forceinline__ uint32_t st_gt2_mask(uint32_t a, uint32_t b) {
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+
 __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ idx,
                                                                   uint4* __restrict__ xmax, int H, int W, int OH, int OW, int cg,
-                                                                  const float* __restrict__ scale, const float* __restrict__ shift) {
+                                                                  int cg_shift, const float* __restrict__ scale, const float* __restrict__ shift) {
   const int n = blockIdx.x / OH, oh = blockIdx.x - n * OH;
   const int row_items = OW * cg;
   const uint4* img = x + (size_t)n * H * W * cg;
-  const int g = threadIdx.x % cg;   // 256 % cg == 0 and the item stride is a multiple of 256: one channel group per thread
+  const int g = threadIdx.x & (cg - 1);   // cg divides 256 (a power of two) and the item stride is a multiple of 256: one channel group per thread
   float sc[8], sh[8];
   st_load8(scale + g * 8, sc);
   st_load8(shift + g * 8, sh);
@@ -58,42 +65,29 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* _
 #pragma unroll
   for (int q = 0; q < 4; ++q) flip[q] = (sc[2 * q] < 0.f ? 0x00008000u : 0u) | (sc[2 * q + 1] < 0.f ? 0x80000000u : 0u);
   for (int item = blockIdx.y * blockDim.x + threadIdx.x; item < row_items; item += gridDim.y * blockDim.x) {
-    const int ow = item / cg;
-    float m[8];
-    uint32_t arg[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      m[q] = -INFINITY;
-      arg[q] = 0;
-    }
+    const int ow = item >> cg_shift;
+    // even H and W: only the top row (oh == 0, r == 0) and the left column (ow == 0, c == 0) of a window can fall outside
+    const uint4* base = img + ((long long)(oh * 2 - 1) * W + (ow * 2 - 1)) * cg + g;
+    uint32_t m[4] = {0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u};   // -inf
+    uint32_t arg[4] = {0u, 0u, 0u, 0u};                                      // 16-bit code per channel
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const int ih = oh * 2 - 1 + r;
-      if (ih < 0 || ih >= H) continue;
+      if (r == 0 && oh == 0) continue;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const int iw = ow * 2 - 1 + c;
-        if (iw < 0 || iw >= W) continue;
-        uint4 raw = __ldg(img + ((size_t)ih * W + iw) * cg + g);
-        raw.x ^= flip[0];
-        raw.y ^= flip[1];
-        raw.z ^= flip[2];
-        raw.w ^= flip[3];
-        float v[8];
-        st_bf16x8_to_f32(raw, v);
+        if (c == 0 && ow == 0) continue;
+        const uint4 raw = __ldg(base + ((long long)r * W + c) * cg);
+        const uint32_t v[4] = {raw.x ^ flip[0], raw.y ^ flip[1], raw.z ^ flip[2], raw.w ^ flip[3]};
+        const uint32_t code2 = (uint32_t)(r * 3 + c) * 0x00010001u;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (v[q] > m[q]) {  // the first maximum in row-major window order wins
-            m[q] = v[q];
-            arg[q] = (uint32_t)(r * 3 + c);
-          }
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t gt = st_gt2_mask(v[q], m[q]);   // strictly greater: the first maximum in row-major window order wins
+          m[q] = (v[q] & gt) | (m[q] & ~gt);
+          arg[q] = (code2 & gt) | (arg[q] & ~gt);
+        }
       }
     }
-    uint4 xm = st_f32_to_bf16x8(m);   // exact: the values are bf16 already
-    xm.x ^= flip[0];
-    xm.y ^= flip[1];
-    xm.z ^= flip[2];
-    xm.w ^= flip[3];
+    const uint4 xm = make_uint4(m[0] ^ flip[0], m[1] ^ flip[1], m[2] ^ flip[2], m[3] ^ flip[3]);   // exact input bits
     float xv[8], o[8];
     st_bf16x8_to_f32(xm, xv);
 #pragma unroll
@@ -101,10 +95,7 @@ __global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* _
     const size_t off = ((size_t)blockIdx.x * OW + ow) * cg + g;
     y[off] = st_f32_to_bf16x8(o);
     xmax[off] = xm;
-    uint2 pk;
-    pk.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
-    pk.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
-    idx[off] = pk;
+    idx[off] = make_uint2(__byte_perm(arg[0], arg[1], 0x6420u), __byte_perm(arg[2], arg[3], 0x6420u));
   }
 }
 
@@ -158,22 +149,40 @@ struct StParamGrads {
   int accumulate;
 };
 
-__device__ __forceinline__ void st_add_masked(float (&o)[8], const uint2& code, const uint4& grad, uint32_t want) {
+// volatile shared-memory read of 8 floats: the per-channel constants are re-read where they are used instead of being hoisted
+// out of the item loop into 40 registers.
+__device__ __forceinline__ void st_lds8(uint32_t addr, float (&v)[8]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(addr + 16u));
+}
+// prmt.b32 with the selector's sign-replicate bit (bit 3 of a nibble: the selected byte's msb fills the target byte);
+// __byte_perm() masks the selector to 3 bits per nibble, so the instruction is written out.
+__device__ __forceinline__ uint32_t st_prmt(uint32_t a, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(sel));
+  return d;
+}
+// Pooled gradient of the windows whose recorded argmax is `want`, two bf16 channels per lane. Codes are < 16, so per byte
+// 0x80 - (code ^ want) keeps bit 7 only where they are equal (no borrow crosses a byte); PRMT's sign-replicate mode widens
+// that bit to the 16-bit lane of the channel. The sum over the (<= 4) windows that hold a pixel is taken with bf16 adds: one or
+// two terms round exactly like the separate pool-backward launch (fp32 sum stored as bf16); three or four terms (a pixel that is
+// the maximum of every window around it) round once more.
+__device__ __forceinline__ void st_add_masked(uint32_t (&o)[4], const uint2& code, const uint4& grad, uint32_t want) {
   const uint32_t w4 = want * 0x01010101u;
-  const uint32_t m0 = __vcmpeq4(code.x, w4), m1 = __vcmpeq4(code.y, w4);
-  const uint32_t gq[4] = {grad.x & __byte_perm(m0, 0u, 0x1100u), grad.y & __byte_perm(m0, 0u, 0x3322u),
-                          grad.z & __byte_perm(m1, 0u, 0x1100u), grad.w & __byte_perm(m1, 0u, 0x3322u)};
+  const uint32_t f0 = 0x80808080u - (code.x ^ w4), f1 = 0x80808080u - (code.y ^ w4);
+  const uint32_t gq[4] = {grad.x & st_prmt(f0, 0x9988u), grad.y & st_prmt(f0, 0xbbaau),
+                          grad.z & st_prmt(f1, 0x9988u), grad.w & st_prmt(f1, 0xbbaau)};
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    o[2 * q] += __uint_as_float(gq[q] << 16);
-    o[2 * q + 1] += __uint_as_float(gq[q] & 0xffff0000u);
+    const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&o[q]), *reinterpret_cast<const __nv_bfloat162*>(&gq[q]));
+    o[q] = *reinterpret_cast<const uint32_t*>(&r);
   }
 }
 
 template <bool NEXT>
-__global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_apply_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
+__global__ void __launch_bounds__(256, NEXT ? 3 : 4) bn_relu_maxpool_bwd_apply_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
                                                                         const uint4* __restrict__ x, uint4* __restrict__ dx, int rows, int H,
-                                                                        int W, int OH, int OW, int cg, const float* __restrict__ fsc,
+                                                                        int W, int OH, int OW, int cg, int cg_shift, const float* __restrict__ fsc,
                                                                         const float* __restrict__ fsh, const float* __restrict__ mean,
                                                                         const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                                         const double* __restrict__ sum_dy,
@@ -181,26 +190,28 @@ __global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_apply_kernel(const
                                                                         double* __restrict__ next_s1, double* __restrict__ next_s2,
                                                                         StParamGrads pg) {
   __shared__ float sm_next[NEXT ? kRedThreads * 8 : 8];
+  extern __shared__ float st_cst[];   // [5][C]: forward scale, shift and dx = A*d + B*x + C, read back per use (40 registers less)
   if (blockIdx.x == 0 && pg.n > 0) {   // the BatchNorm affine gradients are the two reductions themselves
     for (int c = threadIdx.x; c < pg.n; c += blockDim.x) {
       if (pg.dbeta) pg.dbeta[c] = (pg.accumulate ? pg.dbeta[c] : 0.f) + (float)sum_dy[c];
       if (pg.dgamma) pg.dgamma[c] = (pg.accumulate ? pg.dgamma[c] : 0.f) + (float)sum_dy_xhat[c];
     }
   }
-  const int items = (W >> 1) * cg;
-  const int g = threadIdx.x % cg;
-  float sc[8], sh[8], A[8], Bc[8], Cc[8];
-  st_load8(fsc + g * 8, sc);
-  st_load8(fsh + g * 8, sh);
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {  // dx = gamma*rstd*(d - c1 - (x - mean)*rstd*c2) = A*d + B*x + C
-    const int c = g * 8 + q;
+  const int C8 = cg * 8;
+  for (int c = threadIdx.x; c < C8; c += blockDim.x) {  // dx = gamma*rstd*(d - c1 - (x - mean)*rstd*c2) = A*d + B*x + C
     const double r = (double)__ldg(rstd + c), m = (double)__ldg(mean + c), gm = gamma ? (double)__ldg(gamma + c) : 1.0;
     const double c1 = sum_dy[c] * (double)inv_n, c2 = sum_dy_xhat[c] * (double)inv_n;
-    A[q] = (float)(gm * r);
-    Bc[q] = (float)(-gm * r * r * c2);
-    Cc[q] = (float)(gm * r * (r * c2 * m - c1));
+    st_cst[c] = __ldg(fsc + c);
+    st_cst[C8 + c] = __ldg(fsh + c);
+    st_cst[2 * C8 + c] = (float)(gm * r);
+    st_cst[3 * C8 + c] = (float)(-gm * r * r * c2);
+    st_cst[4 * C8 + c] = (float)(gm * r * (r * c2 * m - c1));
   }
+  __syncthreads();
+  const int items = (W >> 1) * cg;
+  const int g = threadIdx.x & (cg - 1);
+  const uint32_t cst = (uint32_t)__cvta_generic_to_shared(st_cst) + (uint32_t)g * 32u;
+  const uint32_t cst_stride = (uint32_t)C8 * 4u;
   float na[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // a block walks whole input rows (few blocks, so the upstream sums cost a handful of atomics per channel)
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -210,7 +221,7 @@ __global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_apply_kernel(const
   const uint32_t r0 = odd ? 6u : 3u;        // r * 3
   const bool two = odd && (oh0 + 1 < OH);   // odd rows are also row 0 of the window below
   for (int item = threadIdx.x; item < items; item += blockDim.x) {
-    const int j = item / cg;
+    const int j = item >> cg_shift;
     const bool right = j + 1 < OW;
     const size_t oa = (((size_t)n * OH + oh0) * OW + j) * cg + g;
     const size_t oc = oa + (size_t)OW * cg;
@@ -226,26 +237,49 @@ __global__ void __launch_bounds__(256, 2) bn_relu_maxpool_bwd_apply_kernel(const
     const uint4 gD = (two && right) ? __ldg(dy + oc + cg) : zg;
     const size_t od = ((size_t)row * W + 2 * j) * cg + g;
     const uint4 x0r = __ldg(x + od), x1r = __ldg(x + od + cg);
-    float o0[8], o1[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) o0[q] = o1[q] = 0.f;
-    st_add_masked(o0, cA, gA, r0 + 1u);
-    st_add_masked(o1, cA, gA, r0 + 2u);
-    st_add_masked(o1, cB, gB, r0);
+    uint32_t q0[4] = {0u, 0u, 0u, 0u}, q1[4] = {0u, 0u, 0u, 0u};
+    st_add_masked(q0, cA, gA, r0 + 1u);
+    st_add_masked(q1, cA, gA, r0 + 2u);
+    st_add_masked(q1, cB, gB, r0);
     if (two) {
-      st_add_masked(o0, cC, gC, 1u);
-      st_add_masked(o1, cC, gC, 2u);
-      st_add_masked(o1, cD, gD, 0u);
+      st_add_masked(q0, cC, gC, 1u);
+      st_add_masked(q1, cC, gC, 2u);
+      st_add_masked(q1, cD, gD, 0u);
     }
+    float o0[8], o1[8];
+    st_bf16x8_to_f32(make_uint4(q0[0], q0[1], q0[2], q0[3]), o0);
+    st_bf16x8_to_f32(make_uint4(q1[0], q1[1], q1[2], q1[3]), o1);
     float x0[8], x1[8];
     st_bf16x8_to_f32(x0r, x0);
     st_bf16x8_to_f32(x1r, x1);
+    {
+      float sc[8], sh[8];
+      st_lds8(cst, sc);
+      st_lds8(cst + cst_stride, sh);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float d0 = fmaf(x0[q], sc[q], sh[q]) > 0.f ? o0[q] : 0.f;   // ReLU mask of the fused layer, recomputed from x
-      const float d1 = fmaf(x1[q], sc[q], sh[q]) > 0.f ? o1[q] : 0.f;
-      o0[q] = fmaf(A[q], d0, fmaf(Bc[q], x0[q], Cc[q]));
-      o1[q] = fmaf(A[q], d1, fmaf(Bc[q], x1[q], Cc[q]));
+      for (int q = 0; q < 8; ++q) {   // ReLU mask of the fused layer, recomputed from x
+        o0[q] = fmaf(x0[q], sc[q], sh[q]) > 0.f ? o0[q] : 0.f;
+        o1[q] = fmaf(x1[q], sc[q], sh[q]) > 0.f ? o1[q] : 0.f;
+      }
+    }
+    {
+      float A[8], Bc[8];
+      st_lds8(cst + 2u * cst_stride, A);
+      st_lds8(cst + 3u * cst_stride, Bc);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        o0[q] = fmaf(A[q], o0[q], Bc[q] * x0[q]);
+        o1[q] = fmaf(A[q], o1[q], Bc[q] * x1[q]);
+      }
+    }
+    {
+      float Cc[8];
+      st_lds8(cst + 4u * cst_stride, Cc);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        o0[q] += Cc[q];
+        o1[q] += Cc[q];
+      }
     }
     const uint4 p0 = st_f32_to_bf16x8(o0), p1 = st_f32_to_bf16x8(o1);
     dx[od] = p0;
@@ -315,7 +349,7 @@ extern "C" int pmoe_bn_relu_maxpool_fwd(const PmoeView4* x, const float* scale, 
   dim3 grid((unsigned)(y->n * y->h), (unsigned)((y->w * cg + 255) / 256));
   bn_relu_maxpool_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const uint4*>(x->ptr), static_cast<uint4*>(y->ptr), reinterpret_cast<uint2*>(idx), static_cast<uint4*>(x_at_max), x->h, x->w,
-      y->h, y->w, cg, scale, shift);
+      y->h, y->w, cg, __builtin_ctz((unsigned)cg), scale, shift);
   return check_launch("bn_relu_maxpool_fwd");
 }
 
@@ -372,13 +406,14 @@ extern "C" int pmoe_bn_relu_maxpool_bwd_apply(const PmoeView4* dy, const uint8_t
   int grid = num_sms() * 8;
   if (grid > rows) grid = rows;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t cst_bytes = (size_t)5 * x->c * sizeof(float);   // <= 40 KB (cg <= 256)
   if (next_sum_dx)
-    bn_relu_maxpool_bwd_apply_kernel<true><<<grid, 256, 0, stream>>>(
+    bn_relu_maxpool_bwd_apply_kernel<true><<<grid, 256, cst_bytes, stream>>>(
         static_cast<const uint4*>(dy->ptr), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(x->ptr), static_cast<uint4*>(dx->ptr),
-        rows, x->h, x->w, dy->h, dy->w, cg, fwd_scale, fwd_shift, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, next_sum_dx, next_sum_dx_x, pg);
+        rows, x->h, x->w, dy->h, dy->w, cg, __builtin_ctz((unsigned)cg), fwd_scale, fwd_shift, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, next_sum_dx, next_sum_dx_x, pg);
   else
-    bn_relu_maxpool_bwd_apply_kernel<false><<<grid, 256, 0, stream>>>(
+    bn_relu_maxpool_bwd_apply_kernel<false><<<grid, 256, cst_bytes, stream>>>(
         static_cast<const uint4*>(dy->ptr), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(x->ptr), static_cast<uint4*>(dx->ptr),
-        rows, x->h, x->w, dy->h, dy->w, cg, fwd_scale, fwd_shift, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, nullptr, nullptr, pg);
+        rows, x->h, x->w, dy->h, dy->w, cg, __builtin_ctz((unsigned)cg), fwd_scale, fwd_shift, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, nullptr, nullptr, pg);
   return check_launch("bn_relu_maxpool_bwd_apply");
 }

@@ -149,11 +149,30 @@ struct StParamGrads {
   int accumulate;
 };
 
-// volatile shared-memory read of 8 floats: the per-channel constants are re-read where they are used instead of being hoisted
-// out of the item loop into 40 registers.
+// volatile shared-memory read of 8 floats: per-channel constants are re-read where they are used instead of being hoisted out
+// of the item loop into registers.
 __device__ __forceinline__ void st_lds8(uint32_t addr, float (&v)[8]) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(addr + 16u));
+}
+// The ReLU mask of the fused layer, fmaf(x, scale, shift) > 0, as a compare of the bf16 input itself: with x' = x for scale > 0
+// and -x for scale < 0 the predicate fmaf(x', |scale|, shift) > 0 is monotone in x' (rounding is monotone), so it equals
+// x' > T for the largest bf16 T at which it is still false. T is found by bisection over the ordered bf16 bit patterns between
+// -inf and +inf (16 evaluations of the very expression the forward kernel used), once per channel and block: the mask is
+// bit-identical to the forward's, and the item loop needs neither scale / shift nor the 3 instructions per element.
+__device__ __forceinline__ float st_key_to_float(uint32_t k) {   // ordered key -> bf16 value (0x007f = -inf ... 0xff80 = +inf)
+  const uint32_t bits = (k & 0x8000u) ? (k ^ 0x8000u) : (~k & 0xffffu);
+  return __uint_as_float(bits << 16);
+}
+__device__ __forceinline__ uint32_t st_relu_threshold(float scale, float shift) {
+  if (scale == 0.f) return shift > 0.f ? 0xff80u : 0x7f80u;   // constant channel: every (finite) input passes / none does
+  const float s = fabsf(scale);
+  uint32_t lo = 0x007fu, hi = 0xff80u;                        // predicate false at -inf, true at +inf
+  while (hi - lo > 1u) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (fmaf(st_key_to_float(mid), s, shift) > 0.f) hi = mid; else lo = mid;
+  }
+  return (lo & 0x8000u) ? (lo ^ 0x8000u) : (~lo & 0xffffu);
 }
 // prmt.b32 with the selector's sign-replicate bit (bit 3 of a nibble: the selected byte's msb fills the target byte);
 // __byte_perm() masks the selector to 3 bits per nibble, so the instruction is written out.
@@ -190,28 +209,37 @@ __global__ void __launch_bounds__(256, NEXT ? 3 : 4) bn_relu_maxpool_bwd_apply_k
                                                                         double* __restrict__ next_s1, double* __restrict__ next_s2,
                                                                         StParamGrads pg) {
   __shared__ float sm_next[NEXT ? kRedThreads * 8 : 8];
-  extern __shared__ float st_cst[];   // [5][C]: forward scale, shift and dx = A*d + B*x + C, read back per use (40 registers less)
+  extern __shared__ float st_cst[];   // [3][C]: dx = A*d + B*x + C per channel, re-read per item (24 registers less: one more block per SM)
+  __shared__ uint32_t sm_thr[256 * 4], sm_flip[256 * 4];   // per channel PAIR: packed ReLU thresholds and sign flips (see st_relu_threshold)
   if (blockIdx.x == 0 && pg.n > 0) {   // the BatchNorm affine gradients are the two reductions themselves
     for (int c = threadIdx.x; c < pg.n; c += blockDim.x) {
       if (pg.dbeta) pg.dbeta[c] = (pg.accumulate ? pg.dbeta[c] : 0.f) + (float)sum_dy[c];
       if (pg.dgamma) pg.dgamma[c] = (pg.accumulate ? pg.dgamma[c] : 0.f) + (float)sum_dy_xhat[c];
     }
   }
-  const int C8 = cg * 8;
-  for (int c = threadIdx.x; c < C8; c += blockDim.x) {  // dx = gamma*rstd*(d - c1 - (x - mean)*rstd*c2) = A*d + B*x + C
+  for (int c = threadIdx.x; c < cg * 8; c += blockDim.x) {  // dx = gamma*rstd*(d - c1 - (x - mean)*rstd*c2) = A*d + B*x + C
     const double r = (double)__ldg(rstd + c), m = (double)__ldg(mean + c), gm = gamma ? (double)__ldg(gamma + c) : 1.0;
     const double c1 = sum_dy[c] * (double)inv_n, c2 = sum_dy_xhat[c] * (double)inv_n;
-    st_cst[c] = __ldg(fsc + c);
-    st_cst[C8 + c] = __ldg(fsh + c);
-    st_cst[2 * C8 + c] = (float)(gm * r);
-    st_cst[3 * C8 + c] = (float)(-gm * r * r * c2);
-    st_cst[4 * C8 + c] = (float)(gm * r * (r * c2 * m - c1));
+    st_cst[c] = (float)(gm * r);
+    st_cst[cg * 8 + c] = (float)(-gm * r * r * c2);
+    st_cst[cg * 16 + c] = (float)(gm * r * (r * c2 * m - c1));
+  }
+  for (int c2 = threadIdx.x; c2 < cg * 4; c2 += blockDim.x) {
+    const float s0 = __ldg(fsc + 2 * c2), s1 = __ldg(fsc + 2 * c2 + 1);
+    sm_thr[c2] = st_relu_threshold(s0, __ldg(fsh + 2 * c2)) | (st_relu_threshold(s1, __ldg(fsh + 2 * c2 + 1)) << 16);
+    sm_flip[c2] = (s0 < 0.f ? 0x00008000u : 0u) | (s1 < 0.f ? 0x80000000u : 0u);
   }
   __syncthreads();
   const int items = (W >> 1) * cg;
   const int g = threadIdx.x & (cg - 1);
+  uint32_t thr[4], flip[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    thr[q] = sm_thr[g * 4 + q];
+    flip[q] = sm_flip[g * 4 + q];
+  }
   const uint32_t cst = (uint32_t)__cvta_generic_to_shared(st_cst) + (uint32_t)g * 32u;
-  const uint32_t cst_stride = (uint32_t)C8 * 4u;
+  const uint32_t cst_stride = (uint32_t)cg * 32u;
   float na[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // a block walks whole input rows (few blocks, so the upstream sums cost a handful of atomics per channel)
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -246,26 +274,23 @@ __global__ void __launch_bounds__(256, NEXT ? 3 : 4) bn_relu_maxpool_bwd_apply_k
       st_add_masked(q1, cC, gC, 2u);
       st_add_masked(q1, cD, gD, 0u);
     }
-    float o0[8], o1[8];
+    {  // ReLU mask of the fused layer on the packed values: fmaf(x, scale, shift) > 0  <=>  (+-x) > threshold, exactly
+      const uint32_t xa[4] = {x0r.x, x0r.y, x0r.z, x0r.w}, xb[4] = {x1r.x, x1r.y, x1r.z, x1r.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        q0[q] &= st_gt2_mask(xa[q] ^ flip[q], thr[q]);
+        q1[q] &= st_gt2_mask(xb[q] ^ flip[q], thr[q]);
+      }
+    }
+    float o0[8], o1[8], x0[8], x1[8];
     st_bf16x8_to_f32(make_uint4(q0[0], q0[1], q0[2], q0[3]), o0);
     st_bf16x8_to_f32(make_uint4(q1[0], q1[1], q1[2], q1[3]), o1);
-    float x0[8], x1[8];
     st_bf16x8_to_f32(x0r, x0);
     st_bf16x8_to_f32(x1r, x1);
     {
-      float sc[8], sh[8];
-      st_lds8(cst, sc);
-      st_lds8(cst + cst_stride, sh);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {   // ReLU mask of the fused layer, recomputed from x
-        o0[q] = fmaf(x0[q], sc[q], sh[q]) > 0.f ? o0[q] : 0.f;
-        o1[q] = fmaf(x1[q], sc[q], sh[q]) > 0.f ? o1[q] : 0.f;
-      }
-    }
-    {
       float A[8], Bc[8];
-      st_lds8(cst + 2u * cst_stride, A);
-      st_lds8(cst + 3u * cst_stride, Bc);
+      st_lds8(cst, A);
+      st_lds8(cst + cst_stride, Bc);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         o0[q] = fmaf(A[q], o0[q], Bc[q] * x0[q]);
@@ -274,7 +299,7 @@ __global__ void __launch_bounds__(256, NEXT ? 3 : 4) bn_relu_maxpool_bwd_apply_k
     }
     {
       float Cc[8];
-      st_lds8(cst + 4u * cst_stride, Cc);
+      st_lds8(cst + 2u * cst_stride, Cc);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         o0[q] += Cc[q];
@@ -406,7 +431,7 @@ extern "C" int pmoe_bn_relu_maxpool_bwd_apply(const PmoeView4* dy, const uint8_t
   int grid = num_sms() * 8;
   if (grid > rows) grid = rows;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const size_t cst_bytes = (size_t)5 * x->c * sizeof(float);   // <= 40 KB (cg <= 256)
+  const size_t cst_bytes = (size_t)3 * x->c * sizeof(float);   // <= 24 KB (cg <= 256)
   if (next_sum_dx)
     bn_relu_maxpool_bwd_apply_kernel<true><<<grid, 256, cst_bytes, stream>>>(
         static_cast<const uint4*>(dy->ptr), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(x->ptr), static_cast<uint4*>(dx->ptr),

@@ -309,14 +309,12 @@ __global__ void __launch_bounds__(256, NEXT ? 3 : 4) bn_relu_maxpool_bwd_apply_k
     const uint4 p0 = st_f32_to_bf16x8(o0), p1 = st_f32_to_bf16x8(o1);
     dx[od] = p0;
     dx[od + cg] = p1;
-    if (NEXT) {  // backward sums of the upstream BatchNorm whose ReLU output x is: what a reduce pass would read back (rounded dx)
-      float v0[8], v1[8];
-      st_bf16x8_to_f32(p0, v0);
-      st_bf16x8_to_f32(p1, v1);
+    if (NEXT) {  // backward sums of the upstream BatchNorm whose ReLU output x is, from the fp32 values before dx is rounded for
+                 // storage (a reduce pass would read the rounded ones back: the difference is a zero-mean sum of rounding errors)
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        na[q] += (x0[q] > 0.f ? v0[q] : 0.f) + (x1[q] > 0.f ? v1[q] : 0.f);
-        nb[q] = fmaf(v0[q], x0[q], fmaf(v1[q], x1[q], nb[q]));
+        na[q] += (x0[q] > 0.f ? o0[q] : 0.f) + (x1[q] > 0.f ? o1[q] : 0.f);
+        nb[q] = fmaf(o0[q], x0[q], fmaf(o1[q], x1[q], nb[q]));
       }
     }
   }
@@ -428,10 +426,18 @@ extern "C" int pmoe_bn_relu_maxpool_bwd_apply(const PmoeView4* dy, const uint8_t
   }
   const int cg = x->c / 8;
   const int rows = x->n * x->h;
-  int grid = num_sms() * 8;
-  if (grid > rows) grid = rows;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const size_t cst_bytes = (size_t)3 * x->c * sizeof(float);   // <= 24 KB (cg <= 256)
+  // ONE resident wave: blocks walk rows round-robin, so every SM holds its full complement of blocks until the end (8 blocks per
+  // SM at 3 resident ran as 3 + 3 + 2), and the upstream sums cost one atomic per channel and resident block.
+  int per_sm = 0;
+  if (next_sum_dx)
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_relu_maxpool_bwd_apply_kernel<true>, 256, cst_bytes);
+  else
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_relu_maxpool_bwd_apply_kernel<false>, 256, cst_bytes);
+  if (per_sm < 1) per_sm = 1;
+  int grid = num_sms() * per_sm;
+  if (grid > rows) grid = rows;
   if (next_sum_dx)
     bn_relu_maxpool_bwd_apply_kernel<true><<<grid, 256, cst_bytes, stream>>>(
         static_cast<const uint4*>(dy->ptr), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(x->ptr), static_cast<uint4*>(dx->ptr),

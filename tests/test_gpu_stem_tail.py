@@ -108,11 +108,14 @@ def test_stem_tail_backward_vs_autograd(n, h, w, c, chain):
     assert _rel(dx.float(), xd.grad) < 4e-3                       # bf16 storage of dx
     off = 7.0 if chain else 0.0
     assert _rel(dgam.double() - off, gd.grad) < 1e-4 and _rel(dbet.double() - (-3.0 if chain else 0.0), bd.grad) < 1e-4
-    if chain:   # sums of the STORED dx: what a separate reduce pass of the upstream layer would read back
-        assert _rel(n1, (dx.double() * (x > 0)).sum(dim=(0, 1, 2))) < 1e-5 or \
-            (n1 - (dx.double() * (x > 0)).sum(dim=(0, 1, 2))).abs().max().item() < 1e-5 * dx.double().abs().sum(dim=(0, 1, 2)).max().item()
-        ref2 = (dx.double() * x.double()).sum(dim=(0, 1, 2))
-        assert (n2 - ref2).abs().max().item() < 1e-5 * (dx.double() * x.double()).abs().sum(dim=(0, 1, 2)).max().item()
+    if chain:   # the upstream BatchNorm's backward sums, taken from the fp32 dx before it is rounded for storage: they differ from
+        # the sums of the STORED dx (what a separate reduce pass reads back) by a zero-mean sum of bf16 rounding errors,
+        # |err_i| <= 2^-9 |dx_i|, i.e. a few 2^-9 * sqrt(sum dx^2) per channel
+        dxd = dx.double()
+        tol1 = 4 * 2.0 ** -9 * (dxd * (x > 0)).pow(2).sum(dim=(0, 1, 2)).sqrt() + 1e-6 * dxd.abs().sum(dim=(0, 1, 2))
+        assert bool(((n1 - (dxd * (x > 0)).sum(dim=(0, 1, 2))).abs() <= tol1).all())
+        tol2 = 4 * 2.0 ** -9 * (dxd * x.double()).pow(2).sum(dim=(0, 1, 2)).sqrt() + 1e-6 * (dxd * x.double()).abs().sum(dim=(0, 1, 2))
+        assert bool(((n2 - (dxd * x.double()).sum(dim=(0, 1, 2))).abs() <= tol2).all())
 
 
 def test_stem_tail_rejects_other_geometries():

@@ -234,6 +234,23 @@ int pmoe_eca_bwd_apply(const PmoeView4* dout, int32_t dtype, const float* gate, 
 int pmoe_eca_bwd_apply_sums(const PmoeView4* dout, int32_t dtype, const float* gate, int64_t gate_stride, const float* dmean,
                             int64_t dmean_stride, const PmoeView4* dx, const PmoeView4* x_fwd, double* next_sum_dx,
                             double* next_sum_dx_x, pmoe_stream_t stream);
+/* EfficientConvBlock's second gate in training (reference PMoE/model/blocks/basics.py:118-121: conv1 -> BN -> ReLU -> ECA gate ->
+ * conv2) without ever storing the gradient of the gated tensor's input: d c1 = dy * gate[n, c] + dmean[n, c] is affine in the data
+ * gradient dy of conv2 per (image, channel). Replaces pmoe_prod_channel_sums + pmoe_eca_bwd_apply_sums + pmoe_bn_bwd_apply (8 tensor
+ * passes) by 5. Dense bf16 NHWC; otherwise PMOE_ERR_UNSUPPORTED and the caller runs the separate entry points.
+ *   sums:  per (image, channel), accumulated into zeroed fp64 (n, out_stride) arrays: sum_dy_m = sum dy * [c1 > 0],
+ *          sum_dy_c1 = sum dy * c1 (the gate's gradient, input of pmoe_eca_gate_bwd), sum_m = sum [c1 > 0]. The BatchNorm's two
+ *          backward sums follow as sum_n gate*sum_dy_m + dmean*sum_m and sum_n gate*sum_dy_c1 + dmean*pool_sum (then through the
+ *          forward affine as for pmoe_bn_bwd_apply_sums' outputs).
+ *   apply: draw = gamma*rstd*(dz - sum_dy/N - xhat*sum_dy_xhat/N) with dz = [relu mask of raw] * (dy*gate + dmean), the ReLU mask
+ *          recomputed from raw with the forward's (fwd_scale, fwd_shift); param_grads as in pmoe_bn_bwd_apply_sums.
+ *          inv_n = 1 / (n*h*w). */
+int pmoe_eca_bn_bwd_sums(const PmoeView4* dy, const PmoeView4* c1, double* sum_dy_m, double* sum_dy_c1, double* sum_m,
+                         int64_t out_stride, pmoe_stream_t stream);
+int pmoe_eca_bn_bwd_apply(const PmoeView4* dy, const PmoeView4* raw, const float* gate, int64_t gate_stride, const float* dmean,
+                          int64_t dmean_stride, const float* fwd_scale, const float* fwd_shift, const float* mean, const float* rstd,
+                          const float* gamma, const double* sum_dy, const double* sum_dy_xhat, float inv_n, const PmoeView4* dx,
+                          const PmoeBnParamGrads* param_grads, pmoe_stream_t stream);
 /* dst (+)= alpha*src + bcast[n][c]: gradient accumulation and global-avg-pool backward. */
 int pmoe_axpy(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, float alpha, const float* bcast, int64_t bcast_stride,
               int32_t accumulate, pmoe_stream_t stream);

@@ -198,8 +198,29 @@ __device__ __forceinline__ void st_add_masked(uint32_t (&o)[4], const uint2& cod
   }
 }
 
-template <bool NEXT>
-__global__ void __launch_bounds__(256, NEXT ? 3 : 4) bn_relu_maxpool_bwd_apply_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
+// block_channel_sum (reduce.cuh) for a block of BT threads: thread t holds the totals of channels t, t + BT, ... in out[].
+template <int BT>
+__device__ __forceinline__ void st_block_channel_sum(const float (&v)[8], float* sm, int cg, float (&out)[2048 / BT]) {
+  float4* s4 = reinterpret_cast<float4*>(sm) + threadIdx.x * 2;
+  s4[0] = make_float4(v[0], v[1], v[2], v[3]);
+  s4[1] = make_float4(v[4], v[5], v[6], v[7]);
+  __syncthreads();
+  const int nch = cg * 8, lanes = BT / cg;
+#pragma unroll
+  for (int j = 0; j < 2048 / BT; ++j) {
+    const int c = threadIdx.x + j * BT;
+    float t = 0.f;
+    if (c < nch)
+      for (int l = 0; l < lanes; ++l) t += sm[l * nch + c];
+    out[j] = t;
+  }
+  __syncthreads();
+}
+
+// BT = 128 threads wherever the channel-group count allows: 112 pixel pairs x 8 groups of a 224-wide 64-channel row are exactly 7
+// rounds of 128 items (3.5 rounds of 256 left every eighth thread idle), and registers are allocated in finer steps.
+template <bool NEXT, int BT>
+__global__ void __launch_bounds__(BT, (NEXT ? 896 : 1024) / BT) bn_relu_maxpool_bwd_apply_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
                                                                         const uint4* __restrict__ x, uint4* __restrict__ dx, int rows, int H,
                                                                         int W, int OH, int OW, int cg, int cg_shift, const float* __restrict__ fsc,
                                                                         const float* __restrict__ fsh, const float* __restrict__ mean,
@@ -208,7 +229,7 @@ __global__ void __launch_bounds__(256, NEXT ? 3 : 4) bn_relu_maxpool_bwd_apply_k
                                                                         const double* __restrict__ sum_dy_xhat, float inv_n,
                                                                         double* __restrict__ next_s1, double* __restrict__ next_s2,
                                                                         StParamGrads pg) {
-  __shared__ float sm_next[NEXT ? kRedThreads * 8 : 8];
+  __shared__ float sm_next[NEXT ? BT * 8 : 8];
   extern __shared__ float st_cst[];   // [3][C]: dx = A*d + B*x + C per channel, re-read per item (24 registers less: one more block per SM)
   __shared__ uint32_t sm_thr[256 * 4], sm_flip[256 * 4];   // per channel PAIR: packed ReLU thresholds and sign flips (see st_relu_threshold)
   if (blockIdx.x == 0 && pg.n > 0) {   // the BatchNorm affine gradients are the two reductions themselves
@@ -320,16 +341,156 @@ __global__ void __launch_bounds__(256, NEXT ? 3 : 4) bn_relu_maxpool_bwd_apply_k
   }
   }
   if (NEXT) {
-    float ta[kRedMaxIter], tb[kRedMaxIter];
-    block_channel_sum(na, sm_next, cg, blockDim.x / cg, ta);
-    block_channel_sum(nb, sm_next, cg, blockDim.x / cg, tb);
+    float ta[2048 / BT], tb[2048 / BT];
+    st_block_channel_sum<BT>(na, sm_next, cg, ta);
+    st_block_channel_sum<BT>(nb, sm_next, cg, tb);
 #pragma unroll
-    for (int j = 0; j < kRedMaxIter; ++j) {
-      const int c = threadIdx.x + j * kRedThreads;
+    for (int j = 0; j < 2048 / BT; ++j) {
+      const int c = threadIdx.x + j * BT;
       if (c < cg * 8) {
         atomicAdd(next_s1 + c, (double)ta[j]);
         atomicAdd(next_s2 + c, (double)tb[j]);
       }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------- ECA + BatchNorm
+// EfficientConvBlock's second gate in training (basics.py:118-121): c1 = relu(BN(raw)) -> c1s = c1 * gate[n, c] -> conv2. The data
+// gradient of conv2 arrives as dy = d c1s. The separate launches spend three passes of 2 + 3 + 3 tensors on it (gate gradient
+// sum dy*c1; dc1 = dy*gate + dmean stored; BatchNorm apply reading dc1 and raw). dc1 is an affine function of dy per (image,
+// channel), so it never has to exist in memory:
+//   sums   per (image, channel): P1 = sum dy*[c1 > 0], P2 = sum dy*c1 (= d gate), M0 = sum [c1 > 0]. With the gate's own backward
+//          (dmean[n, c], a tiny kernel) the BatchNorm's two backward sums follow on the host side of the launch:
+//          sum dc1*m = sum_n gate*P1 + dmean*M0,  sum dc1*c1 = sum_n gate*P2 + dmean*sum c1 (the forward's pooled sums).
+//   apply  draw = A * m * (dy*gate[n, c] + dmean[n, c]) + B * raw + C with (A, B, C) as in bn_relu_maxpool_bwd_apply: 2 reads + 1 write.
+__global__ void __launch_bounds__(kRedThreads) eca_bn_bwd_sums_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ c1, int hw,
+                                                                      int cg, int pix_per_block, double* __restrict__ P1,
+                                                                      double* __restrict__ P2, double* __restrict__ M0,
+                                                                      long long out_stride) {
+  __shared__ float sm[kRedThreads * 8];
+  const int lanes = blockDim.x / cg;
+  const int g = threadIdx.x & (cg - 1), lane = threadIdx.x / cg;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, hw);
+  const uint4* dyi = dy + (size_t)n * hw * cg + g;
+  const uint4* xi = c1 + (size_t)n * hw * cg + g;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0}, m0[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = p0 + lane; p < p1; p += 2 * lanes) {   // two pixels per round: four 16-byte loads in flight per thread
+    const bool two = p + lanes < p1;
+    const uint4 d0 = __ldg(dyi + (size_t)p * cg), x0 = __ldg(xi + (size_t)p * cg);
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    const uint4 d1 = two ? __ldg(dyi + (size_t)(p + lanes) * cg) : zero, x1 = two ? __ldg(xi + (size_t)(p + lanes) * cg) : zero;
+    float dv0[8], xv0[8], dv1[8], xv1[8];
+    st_bf16x8_to_f32(d0, dv0);
+    st_bf16x8_to_f32(x0, xv0);
+    st_bf16x8_to_f32(d1, dv1);
+    st_bf16x8_to_f32(x1, xv1);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const bool k0 = xv0[q] > 0.f, k1 = xv1[q] > 0.f;
+      a[q] += (k0 ? dv0[q] : 0.f) + (k1 ? dv1[q] : 0.f);
+      b[q] = fmaf(dv0[q], xv0[q], fmaf(dv1[q], xv1[q], b[q]));
+      m0[q] += (k0 ? 1.f : 0.f) + (k1 ? 1.f : 0.f);
+    }
+  }
+  float ta[kRedMaxIter], tb[kRedMaxIter], tm[kRedMaxIter];
+  block_channel_sum(a, sm, cg, lanes, ta);
+  block_channel_sum(b, sm, cg, lanes, tb);
+  block_channel_sum(m0, sm, cg, lanes, tm);
+#pragma unroll
+  for (int j = 0; j < kRedMaxIter; ++j) {
+    const int c = threadIdx.x + j * kRedThreads;
+    if (c < cg * 8) {
+      atomicAdd(P1 + n * out_stride + c, (double)ta[j]);
+      atomicAdd(P2 + n * out_stride + c, (double)tb[j]);
+      atomicAdd(M0 + n * out_stride + c, (double)tm[j]);
+    }
+  }
+}
+
+template <int BT>
+__global__ void __launch_bounds__(BT, 1024 / BT) eca_bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ raw,
+                                                                         uint4* __restrict__ dx, int n_img, int hw, int cg, int cg_shift,
+                                                                         int blocks_per_img, const float* __restrict__ gate,
+                                                                         long long gate_stride, const float* __restrict__ dmean,
+                                                                         long long dmean_stride, const float* __restrict__ fsc,
+                                                                         const float* __restrict__ fsh, const float* __restrict__ mean,
+                                                                         const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                         const double* __restrict__ sum_dy,
+                                                                         const double* __restrict__ sum_dy_xhat, float inv_n,
+                                                                         StParamGrads pg) {
+  __shared__ uint32_t sm_thr[BT * 4], sm_flip[BT * 4];
+  __shared__ float sm_a[BT * 8], sm_b[BT * 8], sm_c[BT * 8];
+  if (blockIdx.x == 0 && pg.n > 0) {   // the BatchNorm affine gradients are the two reductions themselves
+    for (int c = threadIdx.x; c < pg.n; c += BT) {
+      if (pg.dbeta) pg.dbeta[c] = (pg.accumulate ? pg.dbeta[c] : 0.f) + (float)sum_dy[c];
+      if (pg.dgamma) pg.dgamma[c] = (pg.accumulate ? pg.dgamma[c] : 0.f) + (float)sum_dy_xhat[c];
+    }
+  }
+  for (int c = threadIdx.x; c < cg * 8; c += BT) {  // draw = gamma*rstd*(d - c1 - (raw - mean)*rstd*c2) = A*d + B*raw + C
+    const double r = (double)__ldg(rstd + c), m = (double)__ldg(mean + c), gm = gamma ? (double)__ldg(gamma + c) : 1.0;
+    const double c1 = sum_dy[c] * (double)inv_n, c2 = sum_dy_xhat[c] * (double)inv_n;
+    sm_a[c] = (float)(gm * r);
+    sm_b[c] = (float)(-gm * r * r * c2);
+    sm_c[c] = (float)(gm * r * (r * c2 * m - c1));
+  }
+  for (int c2 = threadIdx.x; c2 < cg * 4; c2 += BT) {
+    const float s0 = __ldg(fsc + 2 * c2), s1 = __ldg(fsc + 2 * c2 + 1);
+    sm_thr[c2] = st_relu_threshold(s0, __ldg(fsh + 2 * c2)) | (st_relu_threshold(s1, __ldg(fsh + 2 * c2 + 1)) << 16);
+    sm_flip[c2] = (s0 < 0.f ? 0x00008000u : 0u) | (s1 < 0.f ? 0x80000000u : 0u);
+  }
+  __syncthreads();
+  const int g = threadIdx.x & (cg - 1);
+  uint32_t thr[4], flip[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    thr[q] = sm_thr[g * 4 + q];
+    flip[q] = sm_flip[g * 4 + q];
+  }
+  float Bc[8], Cc[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    Bc[q] = sm_b[g * 8 + q];
+    Cc[q] = sm_c[g * 8 + q];
+  }
+  const int img_items = hw * cg;
+  // a block stays inside one image (its gate / dmean row folded with A once), walking that image's items with stride
+  for (int job = blockIdx.x; job < n_img * blocks_per_img; job += gridDim.x) {
+    const int n = job / blocks_per_img, part = job - n * blocks_per_img;
+    float Ag[8], Ad[8];
+    {
+      float gt[8], dm[8];
+      st_load8(gate + n * gate_stride + g * 8, gt);
+      st_load8(dmean + n * dmean_stride + g * 8, dm);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float A = sm_a[g * 8 + q];
+        Ag[q] = A * gt[q];
+        Ad[q] = A * dm[q];
+      }
+    }
+    const size_t base = (size_t)n * img_items;
+    for (int item = part * BT + threadIdx.x; item < img_items; item += blocks_per_img * BT) {
+      const uint4 dr = __ldg(dy + base + item), xr = __ldg(raw + base + item);
+      const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w};
+      uint32_t dw[4] = {dr.x, dr.y, dr.z, dr.w};
+      uint32_t mk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        mk[q] = st_gt2_mask(xw[q] ^ flip[q], thr[q]);   // ReLU mask of the forward, exactly (see st_relu_threshold)
+        dw[q] &= mk[q];
+      }
+      float d[8], x[8], o[8];
+      st_bf16x8_to_f32(make_uint4(dw[0], dw[1], dw[2], dw[3]), d);
+      st_bf16x8_to_f32(xr, x);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const bool on = (mk[q >> 1] >> ((q & 1) * 16)) & 1u;
+        o[q] = fmaf(Ag[q], d[q], fmaf(Bc[q], x[q], Cc[q] + (on ? Ad[q] : 0.f)));
+      }
+      dx[base + item] = st_f32_to_bf16x8(o);
     }
   }
 }
@@ -430,21 +591,99 @@ extern "C" int pmoe_bn_relu_maxpool_bwd_apply(const PmoeView4* dy, const uint8_t
   const size_t cst_bytes = (size_t)3 * x->c * sizeof(float);   // <= 24 KB (cg <= 256)
   // ONE resident wave: blocks walk rows round-robin, so every SM holds its full complement of blocks until the end (8 blocks per
   // SM at 3 resident ran as 3 + 3 + 2), and the upstream sums cost one atomic per channel and resident block.
-  int per_sm = 0;
-  if (next_sum_dx)
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_relu_maxpool_bwd_apply_kernel<true>, 256, cst_bytes);
-  else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_relu_maxpool_bwd_apply_kernel<false>, 256, cst_bytes);
-  if (per_sm < 1) per_sm = 1;
-  int grid = num_sms() * per_sm;
-  if (grid > rows) grid = rows;
-  if (next_sum_dx)
-    bn_relu_maxpool_bwd_apply_kernel<true><<<grid, 256, cst_bytes, stream>>>(
-        static_cast<const uint4*>(dy->ptr), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(x->ptr), static_cast<uint4*>(dx->ptr),
-        rows, x->h, x->w, dy->h, dy->w, cg, __builtin_ctz((unsigned)cg), fwd_scale, fwd_shift, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, next_sum_dx, next_sum_dx_x, pg);
-  else
-    bn_relu_maxpool_bwd_apply_kernel<false><<<grid, 256, cst_bytes, stream>>>(
-        static_cast<const uint4*>(dy->ptr), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(x->ptr), static_cast<uint4*>(dx->ptr),
-        rows, x->h, x->w, dy->h, dy->w, cg, __builtin_ctz((unsigned)cg), fwd_scale, fwd_shift, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, nullptr, nullptr, pg);
+  const uint4* dyp = static_cast<const uint4*>(dy->ptr);
+  const uint2* idp = reinterpret_cast<const uint2*>(idx);
+  const uint4* xp = static_cast<const uint4*>(x->ptr);
+  uint4* dxp = static_cast<uint4*>(dx->ptr);
+  const int sh_ = __builtin_ctz((unsigned)cg);
+#define ST_APPLY(NEXT_, BT_)                                                                                                       \
+  do {                                                                                                                             \
+    int per_sm = 0;                                                                                                                \
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_relu_maxpool_bwd_apply_kernel<NEXT_, BT_>, BT_, cst_bytes);          \
+    if (per_sm < 1) per_sm = 1;                                                                                                    \
+    int grid = num_sms() * per_sm;                                                                                                 \
+    if (grid > rows) grid = rows;                                                                                                  \
+    bn_relu_maxpool_bwd_apply_kernel<NEXT_, BT_><<<grid, BT_, cst_bytes, stream>>>(                                                \
+        dyp, idp, xp, dxp, rows, x->h, x->w, dy->h, dy->w, cg, sh_, fwd_scale, fwd_shift, mean, rstd, gamma, sum_dy, sum_dy_xhat,  \
+        inv_n, next_sum_dx, next_sum_dx_x, pg);                                                                                    \
+  } while (0)
+  if (cg <= 128) {
+    if (next_sum_dx) ST_APPLY(true, 128); else ST_APPLY(false, 128);
+  } else {
+    if (next_sum_dx) ST_APPLY(true, 256); else ST_APPLY(false, 256);
+  }
+#undef ST_APPLY
   return check_launch("bn_relu_maxpool_bwd_apply");
+}
+
+extern "C" int pmoe_eca_bn_bwd_sums(const PmoeView4* dy, const PmoeView4* c1, double* sum_dy_m, double* sum_dy_c1, double* sum_m,
+                                    int64_t out_stride, pmoe_stream_t stream_) {
+  if (!st_dense(dy) || !st_dense(c1) || dy->n != c1->n || dy->h != c1->h || dy->w != c1->w || dy->c != c1->c || !sum_dy_m || !sum_dy_c1 ||
+      !sum_m || out_stride < dy->c) {
+    set_error("eca_bn_bwd_sums: two dense bf16 NHWC tensors of one shape and three (n, >= c) fp64 outputs are required");
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  const int cg = dy->c / 8;
+  const long long hw = (long long)dy->h * dy->w;
+  if (cg > 256 || 256 % cg != 0 || hw * cg > 2147483647LL || dy->n > 65535) {
+    set_error("eca_bn_bwd_sums: channel-group count must divide 256, image size and count within the grid limits");
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  long long blocks = ((long long)num_sms() * 8 + dy->n - 1) / dy->n;   // per image
+  long long ppb = (hw + blocks - 1) / blocks;
+  if (ppb < 64) ppb = 64;
+  blocks = (hw + ppb - 1) / ppb;
+  dim3 grid((unsigned)blocks, (unsigned)dy->n);
+  eca_bn_bwd_sums_kernel<<<grid, kRedThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const uint4*>(dy->ptr), static_cast<const uint4*>(c1->ptr), (int)hw, cg, (int)ppb, sum_dy_m, sum_dy_c1, sum_m, out_stride);
+  return check_launch("eca_bn_bwd_sums");
+}
+
+extern "C" int pmoe_eca_bn_bwd_apply(const PmoeView4* dy, const PmoeView4* raw, const float* gate, int64_t gate_stride, const float* dmean,
+                                     int64_t dmean_stride, const float* fwd_scale, const float* fwd_shift, const float* mean,
+                                     const float* rstd, const float* gamma, const double* sum_dy, const double* sum_dy_xhat, float inv_n,
+                                     const PmoeView4* dx, const PmoeBnParamGrads* param_grads, pmoe_stream_t stream_) {
+  if (!st_dense(dy) || !st_dense(raw) || !st_dense(dx) || dy->n != raw->n || dy->h != raw->h || dy->w != raw->w || dy->c != raw->c ||
+      dx->n != raw->n || dx->h != raw->h || dx->w != raw->w || dx->c != raw->c) {
+    set_error("eca_bn_bwd_apply: three dense bf16 NHWC tensors of one shape are required");
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  if (!gate || !dmean || !fwd_scale || !fwd_shift || !mean || !rstd || !sum_dy || !sum_dy_xhat || gate_stride < dy->c || dmean_stride < dy->c ||
+      ((uintptr_t)gate % 16) || ((uintptr_t)dmean % 16) || gate_stride % 4 || dmean_stride % 4) {
+    set_error("eca_bn_bwd_apply: bad arguments (gate / dmean rows 16-byte aligned, all statistics required)");
+    return PMOE_ERR_ARG;
+  }
+  const int cg = dy->c / 8;
+  const long long hw = (long long)dy->h * dy->w;
+  if (cg > 128 || 128 % cg != 0 || hw * cg > 2147483647LL) {
+    set_error("eca_bn_bwd_apply: channel-group count must divide 128");
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  StParamGrads pg = {nullptr, nullptr, 0, 0};
+  if (param_grads) {
+    if (param_grads->n < 0 || param_grads->n > dy->c) {
+      set_error("eca_bn_bwd_apply: parameter-gradient channel count out of range");
+      return PMOE_ERR_ARG;
+    }
+    pg.dgamma = param_grads->dgamma;
+    pg.dbeta = param_grads->dbeta;
+    pg.n = param_grads->n;
+    pg.accumulate = param_grads->accumulate;
+  }
+  constexpr int BT = 128;
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eca_bn_bwd_apply_kernel<BT>, BT, 0);
+  if (per_sm < 1) per_sm = 1;
+  const long long resident = (long long)num_sms() * per_sm;
+  long long bpi = (resident + dy->n - 1) / dy->n;                 // blocks per image: about one resident wave in total
+  const long long max_bpi = (hw * cg + BT - 1) / BT;
+  if (bpi > max_bpi) bpi = max_bpi;
+  if (bpi < 1) bpi = 1;
+  long long grid = (long long)dy->n * bpi;
+  if (grid > resident) grid = resident;
+  eca_bn_bwd_apply_kernel<BT><<<(unsigned)grid, BT, 0, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const uint4*>(dy->ptr), static_cast<const uint4*>(raw->ptr), static_cast<uint4*>(dx->ptr), dy->n, (int)hw, cg,
+      __builtin_ctz((unsigned)cg), (int)bpi, gate, gate_stride, dmean, dmean_stride, fwd_scale, fwd_shift, mean, rstd, gamma, sum_dy, sum_dy_xhat,
+      inv_n, pg);
+  return check_launch("eca_bn_bwd_apply");
 }

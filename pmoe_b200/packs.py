@@ -132,6 +132,34 @@ def end_pass():
         reg.build_table()
 
 
+def current():
+    """The registry of the pass that is running (None outside a pass)."""
+    return _current
+
+
+class resumed:
+    """Backward of a pass: operands first built there (data-gradient packings) join the registry of the module whose forward
+    recorded the tape, so the next pass refreshes them with everything else in the one multi-tensor launch instead of one
+    gather launch each (one per layer and expert, inside a captured graph on every replay)."""
+
+    def __init__(self, reg):
+        self.reg = reg
+
+    def __enter__(self):
+        global _current
+        self.prev = _current
+        if self.reg is not None:
+            _current = self.reg
+        return self
+
+    def __exit__(self, *exc):
+        global _current
+        _current = self.prev
+        if self.reg is not None and self.reg.table is None and not _capturing():
+            self.reg.build_table()
+        return False
+
+
 def stand_in(shape, device):
     n = 1
     for s in shape:

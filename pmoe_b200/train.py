@@ -76,6 +76,7 @@ class Tape:
         self.reported = set()
         self.bucketer = None        # pmoe_b200.dp.GradBucketer during a data-parallel backward
         self.presums = {}           # id(Act) -> (sum dy*[y>0], sum dy*y) reduced by the kernel that wrote the Act's gradient
+        self.lazy = {}              # id(Act) -> (dy, gate, dmean): gradient dy*gate[n,c] + dmean[n,c] that is never stored (eca_op)
         self.arena = {}             # dtype -> [zeroed chunk, elements handed out]
         self.direct = set()         # id(param) whose gradient was accumulated straight into param.grad
         self.branch_stream = None   # side stream of the branch being recorded / replayed (None: the caller's stream)
@@ -222,6 +223,7 @@ class Tape:
         self.ops = []
         self.alive = []
         self.grads = {}
+        self.lazy = {}
         if self.bucketer is not None:  # gradients whose announced contributions did not all arrive
             for k in self.pgrads:
                 if k not in self.reported:
@@ -286,6 +288,7 @@ def _bn_bwd_reduce(tape, dz, z, x, act, mean, rstd, cpad, fwd=None):
 
 
 FUSE_BN_CHAIN_SUMS = True  # tests switch it off to compare against the separate reduce pass
+FUSE_ECA_BN_BWD = _os0.environ.get("PMOE_FUSE_ECA_BN_BWD", "1") != "0"   # ECA gate behind conv+BN+ReLU: its input gradient is never stored
 GATE_GRAD_FROM_WGRAD = True  # the stem's first ECA gate takes its gradient from the conv's per-image weight gradient (see eca_op)
 
 
@@ -654,8 +657,17 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
         return z, pool
 
     def backward():
-        dz = tape.grad_of(z)
-        if dz is None:
+        lazy = tape.lazy.pop(id(z), None)
+        if lazy is not None and (id(z) in tape.grads or not (bn_train and fwd_aff is not None and act == "relu" and id(z) in tape.presums)):
+            # something else contributed to (or invalidated the sums of) this gradient: store the lazy part after all
+            g, existed = _grad_buffer(tape, z)
+            vd, vg = view4(lazy[0]), view4(g)
+            check(profiler.launch("eca_bwd_apply", lambda: lib().pmoe_eca_bwd_apply(
+                C.byref(vd), dtype_code(lazy[0]), lazy[1].data_ptr(), lazy[1].stride(0), lazy[2].data_ptr(), lazy[2].stride(0), C.byref(vg),
+                int(existed), stream_ptr()), io=(lazy[0], g, g if existed else None)), "eca_bwd_apply")
+            lazy = None
+        dz = None if lazy is not None else tape.grad_of(z)
+        if dz is None and lazy is None:
             return
         z_saved = z_t if act not in (None, "none") else None
         dres, acc_dres = None, False
@@ -674,8 +686,17 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
             else:
                 s1, s2 = _bn_bwd_reduce(tape, dz, z_saved, raw, act, mean, rstd, cstore, fwd=fwd_aff)
             pg, pdone = _bn_pgrads(tape, bn, cout)   # d weight = s2, d bias = s1: written by the apply kernel
-            _bn_bwd_apply(dz, z_saved, raw, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, dy, dres, acc_dres, fwd=fwd_aff,
-                          pgrads=pg)
+            if lazy is not None:
+                vl, vr, vo = view4(lazy[0]), view4(raw), view4(dy)
+                s1c, s2c = s1.contiguous(), s2.contiguous()
+                check(profiler.launch("eca_bn_bwd_apply", lambda: lib().pmoe_eca_bn_bwd_apply(
+                    C.byref(vl), C.byref(vr), lazy[1].data_ptr(), lazy[1].stride(0), lazy[2].data_ptr(), lazy[2].stride(0),
+                    fwd_aff[0].data_ptr(), fwd_aff[1].data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma_p.data_ptr(), s1c.data_ptr(),
+                    s2c.data_ptr(), 1.0 / (n * h * w), C.byref(vo), None if pg is None else C.byref(pg), stream_ptr()),
+                    io=(lazy[0], raw, dy)), "eca_bn_bwd_apply")
+            else:
+                _bn_bwd_apply(dz, z_saved, raw, act, mean, rstd, gamma_p, s1, s2, 1.0 / (n * h * w), 1, dy, dres, acc_dres, fwd=fwd_aff,
+                              pgrads=pg)
             for prm in pdone:
                 tape.pgrad_done(prm)
         else:
@@ -1006,8 +1027,23 @@ def eca_op(tape, eca_mod, x, layout=None, pool_in=None):
                 return
             dgate = tape.zeros((n, cp), torch.float64, dy.device)  # cancelling sums: kept in fp64
             va, vb = view4(dy), view4(x.t)
-            check(profiler.launch("prod_channel_sums", lambda: lib().pmoe_prod_channel_sums(
-                C.byref(va), C.byref(vb), dtype_code(dy), dgate.data_ptr(), dgate.stride(0), stream_ptr()), io=(dy, x.t)), "prod_channel_sums")
+            lazy_ok = False
+            if (FUSE_ECA_BN_BWD and FUSE_BN_CHAIN_SUMS and _rg(x) and getattr(x, "bn_relu", False) and id(x) not in tape.grads
+                    and dy.dtype == torch.bfloat16 and dy.is_contiguous() and x.t.is_contiguous() and x.t.dtype == torch.bfloat16
+                    and 128 % (cp // 8) == 0 and groups == 1 and gate.stride(0) % 4 == 0):
+                p1 = tape.zeros((n, cp), torch.float64, dy.device)
+                m0 = tape.zeros((n, cp), torch.float64, dy.device)
+                rc = profiler.launch("eca_bn_bwd_sums", lambda: lib().pmoe_eca_bn_bwd_sums(
+                    C.byref(va), C.byref(vb), p1.data_ptr(), dgate.data_ptr(), m0.data_ptr(), dgate.stride(0), stream_ptr()), io=(dy, x.t))
+                if rc == 0:
+                    lazy_ok = True
+                elif rc != -2:
+                    check(rc, "eca_bn_bwd_sums")
+                else:
+                    profiler.uncount()
+            if not lazy_ok:
+                check(profiler.launch("prod_channel_sums", lambda: lib().pmoe_prod_channel_sums(
+                    C.byref(va), C.byref(vb), dtype_code(dy), dgate.data_ptr(), dgate.stride(0), stream_ptr()), io=(dy, x.t)), "prod_channel_sums")
             dmean = torch.empty(n, cp, dtype=torch.float32, device=dy.device)
             dw = tape.zeros(w.numel(), torch.float64, dy.device)
             wf = w.detach().reshape(-1)
@@ -1017,6 +1053,17 @@ def eca_op(tape, eca_mod, x, layout=None, pool_in=None):
                 dw.data_ptr(), stream_ptr())), "eca_gate_bwd")
             tape.add_pgrad(w, dw)
             if _rg(x):
+                if lazy_ok:
+                    # x = relu(BN(raw)) of the conv upstream, this is its whole gradient so far and it is affine in dy per (image,
+                    # channel): hand (dy, gate, dmean) and the BatchNorm's two backward sums to that layer instead of storing it
+                    sm = sums[:, :cp].double()
+                    gt = gate[:, :cp].double()
+                    dmd = dmean.double()                         # the per-pixel constant of the gradient (d mean / HW)
+                    n1 = (gt * p1 + dmd * m0).sum(dim=0)          # sum dc1 * [c1 > 0]
+                    n2 = (gt * dgate + dmd * sm).sum(dim=0)       # sum dc1 * c1
+                    tape.presums[id(x)] = (n1, n2)
+                    tape.lazy[id(x)] = (dy, gate, dmean)
+                    return
                 g, existed = _grad_buffer(tape, x)
                 vd, vg = view4(dy), view4(g)
                 if (FUSE_BN_CHAIN_SUMS and getattr(x, "bn_relu", False) and not existed and dy.dtype == torch.bfloat16
@@ -1745,6 +1792,7 @@ class TapeFunction(torch.autograd.Function):
         tape = Tape(config.act_dtype(), save=any(p.requires_grad for p in params))
         outs, seed = runner(tape)
         tape.finish_forward()
+        tape.registry = packs.current()
         ctx.tape, ctx.seed, ctx.plist = tape, seed, params
         ctx.dp = dp.current()  # a pmoe_b200.dp.DataParallel wrapper when the model runs under one
         ctx.mark_non_differentiable(*[o for o in outs if not o.is_floating_point()])
@@ -1760,11 +1808,12 @@ class TapeFunction(torch.autograd.Function):
             tape.bucketer = ctx.dp.make_bucketer(ctx.plist, eager_alloc=bool(tape.side_streams))
             if tape.side_streams:
                 tape.bucketer.producer_streams = lambda: list(tape.side_streams)
-        ctx.seed(tape, gouts)
-        # the seed closure holds the forward's output tensors, whose grad_fn is this node: drop it so that the finished graph (and the
-        # AccumulateGrad nodes it keeps alive, with the stream they were created on) can be freed
-        ctx.seed = None
-        tape.backward()
+        with packs.resumed(getattr(tape, "registry", None)):
+            ctx.seed(tape, gouts)
+            # the seed closure holds the forward's output tensors, whose grad_fn is this node: drop it so that the finished graph (and
+            # the AccumulateGrad nodes it keeps alive, with the stream they were created on) can be freed
+            ctx.seed = None
+            tape.backward()
         if tape.bucketer is not None:
             reduced, stats = tape.bucketer.finish()
             ctx.dp.note_reduced([p for p in ctx.plist if p.requires_grad], stats)

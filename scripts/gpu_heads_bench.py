@@ -180,6 +180,13 @@ def main():
             for ms_, k_, t_ in rows[:14]:
                 print("   %8.3f ms  %-16s %s" % (ms_, k_, t_))
             print("   sum of profiled launches %.2f ms over %d" % (sum(r[0] for r in rows), len(rows)))
+            import collections
+            cnt, tms = collections.Counter(), collections.Counter()
+            for ms_, k_, t_ in rows:
+                cnt[k_] += 1
+                tms[k_] += ms_
+            print("   launches by kernel: " + ", ".join("%s x%d (%.2f ms)" % (k_, n_, tms[k_]) for k_, n_ in cnt.most_common()))
+            rec["launches_by_kernel"] = {k_: [n_, tms[k_]] for k_, n_ in cnt.most_common()}
             profiler.enable_events(False)
         report.append(rec)
         del bank, feats

@@ -1,0 +1,131 @@
+"""EfficientConvBlock's second gate in training without a stored input gradient (csrc/stem_tail.cu: pmoe_eca_bn_bwd_sums /
+pmoe_eca_bn_bwd_apply; reference basics.py:118-121, conv1 -> BN -> ReLU -> ECA gate -> conv2) through the C-ABI:
+ - the per-(image, channel) sums against torch in fp64 on the same bf16 operands;
+ - the fused apply against the formula evaluated in fp64 (BatchNorm backward of dz = mask * (dy * gate + dmean)), negative gammas
+   and a dead channel included, bf16 storage of the result being the only difference;
+ - the stem block's training step with the fusion on and off: every parameter gradient of the two forms agrees to bf16 storage
+   precision, and both agree with the CPU oracle."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def _operands(n, h, w, c, seed):
+    g = torch.Generator().manual_seed(seed)
+    raw = (torch.randn(n, h, w, c, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    gamma = torch.randn(c, generator=g)
+    gamma[0] = 0.0
+    beta = torch.randn(c, generator=g) * 0.5
+    dy = torch.randn(n, h, w, c, generator=g).to(torch.bfloat16)
+    gate = torch.sigmoid(torch.randn(n, c, generator=g))
+    dmean = torch.randn(n, c, generator=g) * 0.05
+    rd = raw.double()
+    mean = rd.mean(dim=(0, 1, 2))
+    rstd = 1.0 / torch.sqrt(rd.var(dim=(0, 1, 2), unbiased=False) + 1e-5)
+    scale = (gamma.double() * rstd).float()
+    shift = (beta.double() - mean * gamma.double() * rstd).float()
+    c1 = torch.relu(torch.addcmul(shift, raw.float(), scale)).to(torch.bfloat16)   # what affine_act stores
+    return [t.to(dev) for t in (raw, gamma, beta, dy, gate, dmean, mean.float(), rstd.float(), scale, shift, c1)]
+
+
+@pytest.mark.parametrize("n,h,w,c", [(3, 20, 28, 64), (2, 7, 9, 16), (1, 1, 3, 8), (5, 16, 16, 128)])
+def test_eca_bn_bwd_sums(n, h, w, c):
+    from pmoe_b200._lib import lib, check, view4, stream_ptr
+    raw, gamma, beta, dy, gate, dmean, mean, rstd, scale, shift, c1 = _operands(n, h, w, c, 3 * n + c)
+    p1 = torch.zeros(n, c, dtype=torch.float64, device=dev)
+    p2 = torch.zeros(n, c, dtype=torch.float64, device=dev)
+    m0 = torch.zeros(n, c, dtype=torch.float64, device=dev)
+    vd, vc = view4(dy), view4(c1)
+    check(lib().pmoe_eca_bn_bwd_sums(C.byref(vd), C.byref(vc), p1.data_ptr(), p2.data_ptr(), m0.data_ptr(), c, stream_ptr()), "sums")
+    on = (c1 > 0).double()
+    assert torch.equal(m0, on.sum(dim=(1, 2)))
+    ref1 = (dy.double() * on).sum(dim=(1, 2))
+    ref2 = (dy.double() * c1.double()).sum(dim=(1, 2))
+    tol1 = 1e-5 * (dy.double() * on).abs().sum(dim=(1, 2)) + 1e-9     # fp32 partial sums per block, fp64 across blocks
+    tol2 = 1e-5 * (dy.double() * c1.double()).abs().sum(dim=(1, 2)) + 1e-9
+    assert bool(((p1 - ref1).abs() <= tol1).all()) and bool(((p2 - ref2).abs() <= tol2).all())
+
+
+@pytest.mark.parametrize("n,h,w,c", [(3, 20, 28, 64), (2, 7, 9, 16), (1, 1, 3, 8), (5, 16, 16, 128)])
+def test_eca_bn_bwd_apply_vs_fp64(n, h, w, c):
+    from pmoe_b200 import train
+    from pmoe_b200._lib import lib, check, view4, stream_ptr
+    raw, gamma, beta, dy, gate, dmean, mean, rstd, scale, shift, c1 = _operands(n, h, w, c, 7 * n + c)
+    # the mask exactly as the forward computed it: fp32 fma of the bf16 input with the fp32 affine
+    m = (torch.addcmul(shift, raw.float(), scale) > 0).double()
+    dz = m * (dy.double() * gate.double()[:, None, None, :] + dmean.double()[:, None, None, :])
+    xhat = (raw.double() - mean.double()) * rstd.double()
+    s1 = dz.sum(dim=(0, 1, 2))
+    s2 = (dz * xhat).sum(dim=(0, 1, 2))
+    N = n * h * w
+    ref = gamma.double() * rstd.double() * (dz - s1 / N - xhat * s2 / N)
+    dx = torch.empty_like(raw)
+    dgam = torch.full((c,), 7.0, device=dev)
+    dbet = torch.full((c,), -3.0, device=dev)
+    pg = train.BnParamGrads()
+    pg.dgamma, pg.dbeta, pg.n, pg.accumulate = dgam.data_ptr(), dbet.data_ptr(), c, 1
+    vd, vr, vx = view4(dy), view4(raw), view4(dx)
+    check(lib().pmoe_eca_bn_bwd_apply(C.byref(vd), C.byref(vr), gate.data_ptr(), gate.stride(0), dmean.data_ptr(), dmean.stride(0),
+                                      scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                      s1.data_ptr(), s2.data_ptr(), 1.0 / N, C.byref(vx), C.byref(pg), stream_ptr()), "apply")
+    assert _rel(dx.float(), ref) < 4e-3                       # bf16 storage of dx
+    assert _rel(dgam.double() - 7.0, s2) < 1e-5 and _rel(dbet.double() + 3.0, s1) < 1e-5
+
+
+def test_eca_bn_bwd_rejects_strided():
+    from pmoe_b200._lib import lib, view4, stream_ptr
+    a = torch.zeros(1, 4, 4, 32, dtype=torch.bfloat16, device=dev)[..., :16]      # channel slice: not dense
+    b = torch.zeros(1, 4, 4, 16, dtype=torch.bfloat16, device=dev)
+    z = torch.zeros(1, 16, dtype=torch.float64, device=dev)
+    va, vb = view4(a), view4(b)
+    assert lib().pmoe_eca_bn_bwd_sums(C.byref(va), C.byref(vb), z.data_ptr(), z.data_ptr(), z.data_ptr(), 16, stream_ptr()) == -2
+
+
+@pytest.mark.parametrize("cin,cout", [(12, 64), (24, 32)])
+def test_stem_block_step_with_and_without_lazy_gate_gradient(cin, cout):
+    from pmoe_b200 import config, train
+    from pmoe_b200.model.blocks.basics import EfficientConvBlock
+    from oracle import functional as O
+    torch.manual_seed(11)
+    x = torch.rand(4, cin, 32, 48, device=dev)
+    cot = torch.randn(4, cout, 32, 48, device=dev)
+    grads, outs = {}, {}
+    with config.use_precision("bf16"):
+        blk = EfficientConvBlock(cin, cout).cuda().train()
+        sd = {k: v.clone() for k, v in blk.state_dict().items()}
+        for fused in (True, False):
+            blk.load_state_dict(sd)
+            blk.zero_grad(set_to_none=True)
+            old = train.FUSE_ECA_BN_BWD
+            train.FUSE_ECA_BN_BWD = fused
+            try:
+                y = blk(x)
+                (y * cot).sum().backward()
+            finally:
+                train.FUSE_ECA_BN_BWD = old
+            outs[fused] = y.detach().clone()
+            grads[fused] = {k: p.grad.detach().clone() for k, p in blk.named_parameters()}
+    assert torch.equal(outs[True], outs[False]) or _rel(outs[True], outs[False]) < 1e-3   # the forward is the same code
+    for k, g in grads[False].items():
+        assert _rel(grads[True][k], g) < 1e-2, (k, _rel(grads[True][k], g))
+    # both against the fp32 CPU oracle on the same weights: the form that never rounds the gate's input gradient to bf16 is not
+    # further from it than the form that stores it (bf16 arithmetic of the product either way)
+    sdg = {k: (v.detach().cpu().clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))
+               else v.detach().cpu().clone()) for k, v in sd.items()}
+    ref = O.eca_conv_block(x.cpu(), sdg, "", True)
+    (ref * cot.cpu()).sum().backward()
+    err = {}
+    for fused in (True, False):
+        num = sum((grads[fused][k].cpu().double() - sdg[k].grad.double()).pow(2).sum() for k in grads[fused])
+        den = sum(sdg[k].grad.double().pow(2).sum() for k in grads[fused])
+        err[fused] = (num / den).sqrt().item()
+    print("\n   stem block gradients vs the fp32 oracle: lazy %.3e | stored %.3e" % (err[True], err[False]))
+    assert err[True] < 1.5 * err[False] + 2e-3, err

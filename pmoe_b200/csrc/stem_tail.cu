@@ -614,9 +614,13 @@ extern "C" int pmoe_bn_relu_maxpool_bwd_apply(const PmoeView4* dy, const uint8_t
   const int sh_ = __builtin_ctz((unsigned)cg);
 #define ST_APPLY(NEXT_, BT_)                                                                                                       \
   do {                                                                                                                             \
-    int per_sm = 0;                                                                                                                \
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_relu_maxpool_bwd_apply_kernel<NEXT_, BT_>, BT_, cst_bytes);          \
-    if (per_sm < 1) per_sm = 1;                                                                                                    \
+    static int per_sm_cached = 0; /* per instantiation; the 3 * C floats of dynamic shared memory never change the answer here */ \
+    if (per_sm_cached == 0) {                                                                                                      \
+      int q_ = 0;                                                                                                                  \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q_, bn_relu_maxpool_bwd_apply_kernel<NEXT_, BT_>, BT_, 24 * 1024);            \
+      per_sm_cached = q_ < 1 ? 1 : q_;                                                                                             \
+    }                                                                                                                              \
+    const int per_sm = per_sm_cached;                                                                                              \
     int grid = num_sms() * per_sm;                                                                                                 \
     if (grid > rows) grid = rows;                                                                                                  \
     bn_relu_maxpool_bwd_apply_kernel<NEXT_, BT_><<<grid, BT_, cst_bytes, stream>>>(                                                \
@@ -687,9 +691,12 @@ extern "C" int pmoe_eca_bn_bwd_apply(const PmoeView4* dy, const PmoeView4* raw, 
     pg.accumulate = param_grads->accumulate;
   }
   constexpr int BT = 128;
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eca_bn_bwd_apply_kernel<BT>, BT, 0);
-  if (per_sm < 1) per_sm = 1;
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int q = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, eca_bn_bwd_apply_kernel<BT>, BT, 0);
+    per_sm = q < 1 ? 1 : q;
+  }
   long long grid = (long long)num_sms() * per_sm;                 // one resident wave sweeping the tensor front to back
   const long long need = (hw * cg * dy->n + BT - 1) / BT;
   if (grid > need) grid = need;

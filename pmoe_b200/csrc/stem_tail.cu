@@ -18,6 +18,8 @@
 // depends on the position).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "host_util.h"
 #include "reduce.cuh"
 
@@ -51,7 +53,8 @@ __device__ __forceinline__ uint32_t st_gt2_mask(uint32_t a, uint32_t b) {
   return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
 }
 
-__global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ idx,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ idx,
                                                                   uint4* __restrict__ xmax, int H, int W, int OH, int OW, int cg,
                                                                   int cg_shift, const float* __restrict__ scale, const float* __restrict__ shift) {
   const int n = blockIdx.x / OH, oh = blockIdx.x - n * OH;
@@ -547,9 +550,9 @@ extern "C" int pmoe_bn_relu_maxpool_fwd(const PmoeView4* x, const float* scale, 
   }
   const int cg = x->c / 8;
   dim3 grid((unsigned)(y->n * y->h), (unsigned)((y->w * cg + 255) / 256));
-  bn_relu_maxpool_fwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+  bn_relu_maxpool_fwd_kernel<4><<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const uint4*>(x->ptr), static_cast<uint4*>(y->ptr), reinterpret_cast<uint2*>(idx), static_cast<uint4*>(x_at_max), x->h, x->w,
-      y->h, y->w, cg, __builtin_ctz((unsigned)cg), scale, shift);
+      y->h, y->w, cg, __builtin_ctz((unsigned)cg), scale, shift);   // (5 or 6 resident blocks per SM spill and measured 3-7 % slower)
   return check_launch("bn_relu_maxpool_fwd");
 }
 

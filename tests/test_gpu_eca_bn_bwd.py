@@ -134,3 +134,38 @@ def test_stem_block_step_with_and_without_lazy_gate_gradient(cin, cout):
         err[fused] = (num / den).sqrt().item()
     print("\n   stem block gradients vs the fp32 oracle: lazy %.3e | stored %.3e" % (err[True], err[False]))
     assert err[True] < 1.5 * err[False] + 2e-3, err
+
+
+def test_relu_threshold_is_exact_for_every_bf16_input():
+    """st_relu_threshold (bisection per channel): the packed compare x' > T must reproduce fmaf(x, scale, shift) > 0 for EVERY finite
+    bf16 x. With gamma = rstd = gate = 1, dmean = 0 and zero backward sums, pmoe_eca_bn_bwd_apply returns dx = mask * dy."""
+    from pmoe_b200._lib import lib, check, view4, stream_ptr
+    c = 64
+    bits = torch.arange(65536, dtype=torch.int32)
+    xall = bits.to(torch.int16).view(torch.bfloat16)                       # every bf16 pattern once
+    finite = torch.isfinite(xall.float())
+    x = xall.view(1, 256, 256, 1).expand(1, 256, 256, c).contiguous().to(dev)
+    g = torch.Generator().manual_seed(17)
+    scale = torch.randn(c, generator=g) * torch.tensor([10.0 ** ((i % 9) - 4) for i in range(c)])
+    shift = torch.randn(c, generator=g) * torch.tensor([10.0 ** (((i // 3) % 9) - 4) for i in range(c)])
+    scale[0], shift[0] = 0.0, 1.0
+    scale[1], shift[1] = 0.0, -1.0
+    scale[2], shift[2] = 1.0, 0.0
+    scale[3], shift[3] = -1.0, 0.0
+    scale[4], shift[4] = 3e-39, 1e-38                                      # denormal scale
+    scale, shift = scale.to(dev), shift.to(dev)
+    dy = torch.ones_like(x)
+    ones = torch.ones(1, c, device=dev)
+    zeros = torch.zeros(1, c, device=dev)
+    one_c, zero_c = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+    z64 = torch.zeros(c, dtype=torch.float64, device=dev)
+    dx = torch.empty_like(x)
+    vd, vr, vx = view4(dy), view4(x), view4(dx)
+    check(lib().pmoe_eca_bn_bwd_apply(C.byref(vd), C.byref(vr), ones.data_ptr(), ones.stride(0), zeros.data_ptr(), zeros.stride(0),
+                                      scale.data_ptr(), shift.data_ptr(), zero_c.data_ptr(), one_c.data_ptr(), one_c.data_ptr(),
+                                      z64.data_ptr(), z64.data_ptr(), 1.0 / 65536, C.byref(vx), None, stream_ptr()), "apply")
+    got = dx.view(65536, c).float() > 0.5
+    want = torch.addcmul(shift, x.view(65536, c).float(), scale) > 0          # one fused multiply-add in fp32, as the forward kernels do
+    fin = finite.to(dev)
+    bad = (got != want)[fin]
+    assert not bool(bad.any()), (int(bad.sum()), torch.nonzero(bad)[:8].tolist())

@@ -186,3 +186,88 @@ def test_resnet18_step_with_and_without_fused_stem_tail():
     # exactness of the kernels themselves is pinned by the tests above)
     assert ab_f < 2 * floor_f + 1e-2, (ab_f, floor_f)
     assert ab_g < 2 * floor_g + 0.35, (ab_g, floor_g)
+
+
+def test_stem_backward_kernels_at_bench_size_properties():
+    """BASELINE configs[2] geometry (one micro-batch of the 224^2 x 64-channel stem tensors; 128 images here to bound memory):
+    size-independent properties of a BatchNorm backward — its output is orthogonal to the constant and to x-hat per channel
+    (sum dx = 0, sum dx * xhat = 0 up to the bf16 storage of dx) — for the fused stem tail and for the fused ECA + BatchNorm apply,
+    and the fused forward equals the separate launches bit for bit."""
+    from pmoe_b200 import nhwc, train
+    from pmoe_b200._lib import lib, check, view4, stream_ptr
+    n, h, w, c = 128, 224, 224, 64
+    g = torch.Generator(device=dev).manual_seed(5)
+    x = (torch.randn(n, h, w, c, generator=g, device=dev) * 1.5 + 0.3).to(torch.bfloat16)
+    gamma = torch.rand(c, generator=g, device=dev) + 0.5
+    beta = torch.randn(c, generator=g, device=dev) * 0.3
+    s_ = torch.zeros(c, dtype=torch.float64, device=dev)
+    q_ = torch.zeros(c, dtype=torch.float64, device=dev)
+    vx = view4(x)
+    check(lib().pmoe_channel_stats(C.byref(vx), 1, s_.data_ptr(), q_.data_ptr(), stream_ptr()), "stats")
+    N = n * h * w
+    mean64 = s_ / N
+    rstd64 = 1.0 / torch.sqrt((q_ / N - mean64 * mean64).clamp_min(0) + 1e-5)
+    scale = (gamma.double() * rstd64).float()
+    shift = (beta.double() - mean64 * gamma.double() * rstd64).float()
+    mean, rstd = mean64.float(), rstd64.float()
+    # ---- stem tail
+    p, idx, xm = _fused_forward(x, scale, shift)
+    z = nhwc.affine_act(x, scale, shift, "relu")
+    assert torch.equal(p, nhwc.maxpool(nhwc.Act(z, c), 3, 2, 1).t)
+    del z
+    dp = (torch.randn(n, h // 2, w // 2, c, generator=g, device=dev) + 0.7).to(torch.bfloat16)   # non-zero mean: sum dz ~ sum |dz|
+    s1 = torch.zeros(c, dtype=torch.float64, device=dev)
+    s2 = torch.zeros(c, dtype=torch.float64, device=dev)
+    vdp = view4(dp)
+    check(lib().pmoe_bn_relu_maxpool_bwd_reduce(C.byref(vdp), xm.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                                                rstd.data_ptr(), s1.data_ptr(), s2.data_ptr(), stream_ptr()), "reduce")
+    dx = torch.empty_like(x)
+    vdx = view4(dx)
+    check(lib().pmoe_bn_relu_maxpool_bwd_apply(
+        C.byref(vdp), idx.data_ptr(), C.byref(vx), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+        s1.data_ptr(), s2.data_ptr(), 1.0 / N, C.byref(vdx), None, None, None, stream_ptr()), "apply")
+
+    def orthogonality(dx_):
+        a = torch.zeros(c, dtype=torch.float64, device=dev)
+        b = torch.zeros(c, dtype=torch.float64, device=dev)
+        ab = torch.zeros(c, dtype=torch.float64, device=dev)
+        for i in range(0, n, 16):   # chunks bound the fp64 temporaries
+            d = dx_[i:i + 16].double()
+            xh = (x[i:i + 16].double() - mean64) * rstd64
+            a += d.sum(dim=(0, 1, 2))
+            b += (d * xh).sum(dim=(0, 1, 2))
+            ab += d.abs().sum(dim=(0, 1, 2))
+        return (a.abs() / ab).max().item(), (b.abs() / ab).max().item()
+    o1, o2 = orthogonality(dx)
+    # Without the two subtracted means the sums would be ~0.5 of sum|dx| (the pooled gradient has mean 0.7). What is left is the bf16
+    # storage of dx, and it is NOT sqrt(N)-small: the routed values are A[c] * (a bf16 number), a few hundred distinct products per
+    # channel whose rounding errors repeat — rounding the exact fp64 result to bf16 leaves 1e-4 of sum|dx|
+    # (scripts/gpu_stem_tail_sumcheck.py: 0.9e-4 for the rounded exact result, 1.7e-4 for the kernel).
+    print("\n   stem tail at %dx%dx%dx%d: |sum dx| / sum|dx| = %.2e, |sum dx xhat| / sum|dx| = %.2e" % (n, h, w, c, o1, o2))
+    assert o1 < 1e-3 and o2 < 1e-3, (o1, o2)
+    # ---- ECA + BatchNorm apply on the same operands (dy at full resolution)
+    del dx, dp, p, idx, xm
+    dy = (torch.randn(n, h, w, c, generator=g, device=dev) + 0.7).to(torch.bfloat16)
+    gate = torch.sigmoid(torch.randn(n, c, generator=g, device=dev))
+    dmean = torch.randn(n, c, generator=g, device=dev) * 0.05
+    c1 = nhwc.affine_act(x, scale, shift, "relu")
+    p1 = torch.zeros(n, c, dtype=torch.float64, device=dev)
+    p2 = torch.zeros(n, c, dtype=torch.float64, device=dev)
+    m0 = torch.zeros(n, c, dtype=torch.float64, device=dev)
+    vdy, vc1 = view4(dy), view4(c1)
+    check(lib().pmoe_eca_bn_bwd_sums(C.byref(vdy), C.byref(vc1), p1.data_ptr(), p2.data_ptr(), m0.data_ptr(), c, stream_ptr()), "sums")
+    pool = nhwc.channel_sums(c1)[:, :c].double()
+    t1 = (gate.double() * p1 + dmean.double() * m0).sum(0)                 # sum dc1 * [c1 > 0]
+    t2 = (gate.double() * p2 + dmean.double() * pool).sum(0)               # sum dc1 * c1
+    sc, sh = scale.double(), shift.double()
+    sraw = (t2 - sh * t1) / sc                                             # sum dc1 * m * raw through the forward affine
+    b1, b2 = t1.contiguous(), (rstd64 * (sraw - mean64 * t1)).contiguous()
+    del c1
+    draw = torch.empty_like(x)
+    vdr = view4(draw)
+    check(lib().pmoe_eca_bn_bwd_apply(C.byref(vdy), C.byref(vx), gate.data_ptr(), gate.stride(0), dmean.data_ptr(), dmean.stride(0),
+                                      scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                      b1.data_ptr(), b2.data_ptr(), 1.0 / N, C.byref(vdr), None, stream_ptr()), "eca apply")
+    o1, o2 = orthogonality(draw)
+    print("   eca + BatchNorm apply: |sum dx| / sum|dx| = %.2e, |sum dx xhat| / sum|dx| = %.2e" % (o1, o2))
+    assert o1 < 1e-3 and o2 < 1e-3, (o1, o2)

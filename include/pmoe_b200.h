@@ -203,19 +203,39 @@ int pmoe_bn_bwd_apply_sums(const PmoeView4* dz, const PmoeView4* z, const PmoeVi
  *   fwd:    y = maxpool(relu(scale*x + shift)) with (scale, shift) of pmoe_bn_finalize; idx: argmax codes r*3+c as pmoe_maxpool_idx
  *           writes them, x_at_max: x at the argmax, dense bf16 (n, oh, ow, c) — the normalised tensor is never stored.
  *   reduce: sum_dy / sum_dy_xhat of pmoe_bn_bwd_reduce for the gradient routed through pool and ReLU, from the POOLED grid
- *           (both must be zeroed by the caller).
+ *           (both must be zeroed by the caller); sum_dy_xpos (optional, zeroed): the part of sum_dy routed to positions whose
+ *           INPUT x is > 0 (x being a ReLU output itself: what the upstream BatchNorm's closed-form backward needs).
  *   apply:  dx of pmoe_bn_bwd_apply for every input pixel (the routed gradient is gathered from the windows that hold the pixel,
  *           never stored); next_sum_dx / next_sum_dx_x (optional, zeroed by the caller) and param_grads as in
  *           pmoe_bn_bwd_apply_sums. inv_n = 1 / (n*h*w) of x. */
 int pmoe_bn_relu_maxpool_fwd(const PmoeView4* x, const float* scale, const float* shift, const PmoeView4* y, uint8_t* idx,
                              void* x_at_max, pmoe_stream_t stream);
 int pmoe_bn_relu_maxpool_bwd_reduce(const PmoeView4* dy, const void* x_at_max, const float* fwd_scale, const float* fwd_shift,
-                                    const float* mean, const float* rstd, double* sum_dy, double* sum_dy_xhat, pmoe_stream_t stream);
+                                    const float* mean, const float* rstd, double* sum_dy, double* sum_dy_xhat, double* sum_dy_xpos,
+                                    pmoe_stream_t stream);
 int pmoe_bn_relu_maxpool_bwd_apply(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* x, const float* fwd_scale,
                                    const float* fwd_shift, const float* mean, const float* rstd, const float* gamma,
                                    const double* sum_dy, const double* sum_dy_xhat, float inv_n, const PmoeView4* dx,
                                    double* next_sum_dx, double* next_sum_dx_x, const PmoeBnParamGrads* param_grads,
                                    pmoe_stream_t stream);
+/* pmoe_bn_relu_maxpool_bwd_apply continued through the conv + BatchNorm + ReLU in front of it (the stem block's conv2 + BN + ReLU
+ * followed by torchvision's bn1 -> relu -> maxpool, reference backbone.py:57-61 / basics.py:122-125): x = relu(up_scale*raw + up_shift)
+ * is recomputed from the raw conv output exactly as the forward stored it, dx stays in registers and what is written is
+ * draw = up_gamma*up_rstd*([x > 0]*dx - up_sum_dy/N - xhat_up*up_sum_dy_xhat/N): the gradient of the RAW conv output. The upstream
+ * sums are inputs: the caller forms them in closed form from pmoe_bn_relu_maxpool_bwd_reduce's three sums and the forward statistics
+ * of x (pmoe_affine_relu_stats_pos): sum dx*[x>0] = A*sum_dy_xpos + B*sum x + C*count(x>0), sum dx*x = A*sum dy*x + B*sum x^2 + C*sum x
+ * with dx = A*d + B*x + C per channel. Replaces pmoe_bn_relu_maxpool_bwd_apply + pmoe_bn_bwd_apply (5.4 tensor passes) by 2.4.
+ * param_grads / up_param_grads: the affine gradients of the two BatchNorms (optional). Dense bf16, channel groups dividing 128. */
+int pmoe_bn2_relu_maxpool_bwd_apply(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* raw, const float* fwd_scale,
+                                    const float* fwd_shift, const float* mean, const float* rstd, const float* gamma, const double* sum_dy,
+                                    const double* sum_dy_xhat, float inv_n, const PmoeBnParamGrads* param_grads, const float* up_scale,
+                                    const float* up_shift, const float* up_mean, const float* up_rstd, const float* up_gamma,
+                                    const double* up_sum_dy, const double* up_sum_dy_xhat, const PmoeBnParamGrads* up_param_grads,
+                                    const PmoeView4* draw, pmoe_stream_t stream);
+/* pmoe_affine_act_stats for y = relu(scale*x + shift) that also counts the stored values > 0 per channel (out_pos, fp64, zeroed by
+ * the caller). Dense bf16. */
+int pmoe_affine_relu_stats_pos(const PmoeView4* src, const PmoeView4* dst, const float* scale, const float* shift, double* out_sum,
+                               double* out_sqsum, double* out_pos, pmoe_stream_t stream);
 int pmoe_maxpool_bwd(const PmoeView4* x, const PmoeView4* dy, const PmoeView4* dx, int32_t dtype, int32_t k, int32_t stride,
                      int32_t pad, int32_t accumulate, pmoe_stream_t stream);
 int pmoe_maxpool_bwd_idx(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* dx, int32_t dtype, int32_t k,

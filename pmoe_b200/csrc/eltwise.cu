@@ -483,12 +483,15 @@ __global__ void __launch_bounds__(256) affine_act_kernel(V4 src, V4 dst, const f
 // AFFINE: y = act(scale*x + shift) is computed, stored, and the statistics are those of the STORED (bf16-rounded) y —
 // the fused form of affine_act followed by channel_sums (ECA / avg-pool numerators) and/or channel_stats (a BatchNorm that
 // follows directly: ResNet bn1 after the stem block), which would each re-read the tensor.
-template <bool AFFINE, bool RELU, bool POOL, bool STATS>
+// COUNT: also the number of stored values > 0 per channel (a ReLU output feeding a BatchNorm whose backward is taken in closed
+// form, see stem_tail.cu bn2_relu_maxpool_bwd_apply_kernel).
+template <bool AFFINE, bool RELU, bool POOL, bool STATS, bool COUNT = false>
 __global__ void __launch_bounds__(kRedThreads) act_reduce_fast_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, long long pix_per_img,
                                                                       int cg, const float* __restrict__ scale,
                                                                       const float* __restrict__ shift, float* __restrict__ pool,
                                                                       long long pool_stride, double* __restrict__ osum,
-                                                                      double* __restrict__ osq, long long pix_per_block) {
+                                                                      double* __restrict__ osq, long long pix_per_block,
+                                                                      double* __restrict__ opos) {
   __shared__ float sm[kRedThreads * 8];
   const int lanes = blockDim.x / cg;
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
@@ -503,7 +506,7 @@ __global__ void __launch_bounds__(kRedThreads) act_reduce_fast_kernel(const uint
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   long long p1 = p0 + pix_per_block;
   if (p1 > pix_per_img) p1 = pix_per_img;
-  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (lane < lanes) {
     for (long long p = p0 + lane; p < p1; p += 4LL * lanes) {
       uint4 r[4];
@@ -537,13 +540,15 @@ __global__ void __launch_bounds__(kRedThreads) act_reduce_fast_kernel(const uint
         for (int q = 0; q < 8; ++q) {
           a[q] += v[q];
           if (STATS) b[q] = fmaf(v[q], v[q], b[q]);
+          if (COUNT) cnt[q] += v[q] > 0.f ? 1.f : 0.f;   // exact in fp32: a thread sees far fewer than 2^24 pixels
         }
       }
     }
   }
-  float ta[kRedMaxIter], tb[kRedMaxIter];
+  float ta[kRedMaxIter], tb[kRedMaxIter], tc[kRedMaxIter];
   block_channel_sum(a, sm, cg, lanes, ta);
   if (STATS) block_channel_sum(b, sm, cg, lanes, tb);
+  if (COUNT) block_channel_sum(cnt, sm, cg, lanes, tc);
 #pragma unroll
   for (int j = 0; j < kRedMaxIter; ++j) {
     const int c = threadIdx.x + j * kRedThreads;
@@ -553,6 +558,7 @@ __global__ void __launch_bounds__(kRedThreads) act_reduce_fast_kernel(const uint
         atomicAdd(osum + c, (double)ta[j]);
         atomicAdd(osq + c, (double)tb[j]);
       }
+      if (COUNT) atomicAdd(opos + c, (double)tc[j]);
     }
   }
 }
@@ -779,7 +785,7 @@ int pmoe_channel_sums(const PmoeView4* src, int32_t dtype, float* out, int64_t o
     long long ppb;
     const dim3 grid = reduce_grid(hw, src->n, &ppb);
     act_reduce_fast_kernel<false, false, true, false><<<grid, kRedThreads, 0, stream>>>(
-        static_cast<const uint4*>(src->ptr), nullptr, hw, cg, nullptr, nullptr, out, out_stride, nullptr, nullptr, ppb);
+        static_cast<const uint4*>(src->ptr), nullptr, hw, cg, nullptr, nullptr, out, out_stride, nullptr, nullptr, ppb, nullptr);
     return check_launch("channel_sums");
   }
   // fp32 (the parity mode): ONE block per image walks all its pixels, so the per-image sums do not depend on the order in which
@@ -805,7 +811,7 @@ int pmoe_channel_stats(const PmoeView4* src, int32_t dtype, double* sum, double*
     long long ppb1;
     const dim3 grid = reduce_grid(npix, 1, &ppb1);  // dense: the batch is one long image
     act_reduce_fast_kernel<false, false, false, true><<<grid, kRedThreads, 0, stream>>>(
-        static_cast<const uint4*>(src->ptr), nullptr, npix, src->c / 8, nullptr, nullptr, nullptr, 0, sum, sqsum, ppb1);
+        static_cast<const uint4*>(src->ptr), nullptr, npix, src->c / 8, nullptr, nullptr, nullptr, 0, sum, sqsum, ppb1, nullptr);
     return check_launch("channel_stats");
   }
   long long blocks = (long long)num_sms() * 8;
@@ -883,13 +889,38 @@ int pmoe_affine_act_stats(const PmoeView4* src, const PmoeView4* dst, int32_t dt
   const uint4* px = static_cast<const uint4*>(src->ptr);
   uint4* py = static_cast<uint4*>(dst->ptr);
   const int cg = src->c / 8;
-#define PMOE_AAS(R, P, S) act_reduce_fast_kernel<true, R, P, S><<<grid, kRedThreads, 0, stream>>>(px, py, hw, cg, scale, shift, pool_sum, pool_stride, out_sum, out_sqsum, ppb)
+#define PMOE_AAS(R, P, S) act_reduce_fast_kernel<true, R, P, S><<<grid, kRedThreads, 0, stream>>>(px, py, hw, cg, scale, shift, pool_sum, pool_stride, out_sum, out_sqsum, ppb, nullptr)
   const bool relu = act == PMOE_ACT_RELU;
   if (pool_sum && out_sum) { if (relu) PMOE_AAS(true, true, true); else PMOE_AAS(false, true, true); }
   else if (pool_sum) { if (relu) PMOE_AAS(true, true, false); else PMOE_AAS(false, true, false); }
   else { if (relu) PMOE_AAS(true, false, true); else PMOE_AAS(false, false, true); }
 #undef PMOE_AAS
   return check_launch("affine_act_stats");
+}
+
+// pmoe_affine_act_stats for y = relu(scale*x + shift) that also counts the stored values > 0 per channel (out_pos, fp64, accumulated
+// into a zeroed buffer): the third forward statistic a closed-form BatchNorm backward of y's producer needs.
+int pmoe_affine_relu_stats_pos(const PmoeView4* src, const PmoeView4* dst, const float* scale, const float* shift, double* out_sum,
+                               double* out_sqsum, double* out_pos, pmoe_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = check_view(src, PMOE_BF16, "affine_relu_stats_pos src");
+  if (rc) return rc;
+  if ((rc = check_view(dst, PMOE_BF16, "affine_relu_stats_pos dst"))) return rc;
+  if (!scale || !shift || ((uintptr_t)scale % 16) || ((uintptr_t)shift % 16) || !out_sum || !out_sqsum || !out_pos || src->c / 8 > 256) {
+    set_error("affine_relu_stats_pos: scale/shift (16-byte aligned) and the three statistics outputs are required");
+    return PMOE_ERR_ARG;
+  }
+  if (!dense_view(src) || !dense_view(dst) || src->n != dst->n || src->h != dst->h || src->w != dst->w || src->c != dst->c) {
+    set_error("affine_relu_stats_pos: dense bf16 tensors of one shape");
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  const long long hw = (long long)src->h * src->w;
+  long long ppb;
+  const dim3 grid = reduce_grid(hw, src->n, &ppb);
+  act_reduce_fast_kernel<true, true, false, true, true><<<grid, kRedThreads, 0, stream>>>(
+      static_cast<const uint4*>(src->ptr), static_cast<uint4*>(dst->ptr), hw, src->c / 8, scale, shift, nullptr, 0, out_sum, out_sqsum, ppb,
+      out_pos);
+  return check_launch("affine_relu_stats_pos");
 }
 
 }  // extern "C"

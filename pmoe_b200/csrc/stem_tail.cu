@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kRedThreads) bn_relu_maxpool_bwd_reduce_kernel
                                                                                  long long npix, int cg, const float* __restrict__ fsc,
                                                                                  const float* __restrict__ fsh, const float* __restrict__ mean,
                                                                                  const float* __restrict__ rstd, double* __restrict__ sum_dy,
-                                                                                 double* __restrict__ sum_dy_xhat, long long pix_per_block) {
+                                                                                 double* __restrict__ sum_dy_xhat, long long pix_per_block,
+                                                                                 double* __restrict__ sum_dy_xpos) {
   __shared__ float sm[kRedThreads * 8];
   const int lanes = blockDim.x / cg;
   const int g = threadIdx.x % cg, lane = threadIdx.x / cg;
@@ -119,7 +120,7 @@ __global__ void __launch_bounds__(kRedThreads) bn_relu_maxpool_bwd_reduce_kernel
   const long long p0 = (long long)blockIdx.x * pix_per_block;
   long long p1 = p0 + pix_per_block;
   if (p1 > npix) p1 = npix;
-  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0}, e[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (lane < lanes) {
     for (long long p = p0 + lane; p < p1; p += lanes) {
       float d[8], xv[8];
@@ -130,18 +131,21 @@ __global__ void __launch_bounds__(kRedThreads) bn_relu_maxpool_bwd_reduce_kernel
         const float dm = fmaf(xv[q], sc[q], sh[q]) > 0.f ? d[q] : 0.f;
         a[q] += dm;
         b[q] = fmaf(dm, xv[q], b[q]);
+        e[q] += xv[q] > 0.f ? dm : 0.f;   // the part routed to positions where the input itself is > 0 (sum_dy_xpos)
       }
     }
   }
-  float ta[kRedMaxIter], tb[kRedMaxIter];
+  float ta[kRedMaxIter], tb[kRedMaxIter], te[kRedMaxIter];
   block_channel_sum(a, sm, cg, lanes, ta);
   block_channel_sum(b, sm, cg, lanes, tb);
+  if (sum_dy_xpos) block_channel_sum(e, sm, cg, lanes, te);
 #pragma unroll
   for (int j = 0; j < kRedMaxIter; ++j) {
     const int c = threadIdx.x + j * kRedThreads;
     if (c < cg * 8) {
       atomicAdd(sum_dy + c, (double)ta[j]);
       atomicAdd(sum_dy_xhat + c, (double)__ldg(rstd + c) * ((double)tb[j] - (double)__ldg(mean + c) * (double)ta[j]));
+      if (sum_dy_xpos) atomicAdd(sum_dy_xpos + c, (double)te[j]);
     }
   }
 }
@@ -361,6 +365,178 @@ __global__ void __launch_bounds__(BT, (NEXT ? 896 : 1024) / BT) bn_relu_maxpool_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------- two BatchNorms
+// The same backward continued through the conv + BatchNorm + ReLU in FRONT of bn1 (the stem block's conv2, basics.py:122-125): x =
+// relu(BN_up(raw)) is recomputed from the raw conv output exactly as the forward stored it (fma, max, round to bf16), the gradient
+// dx = A*d + B*x + C of the kernel above stays in registers, and what is written is d raw = A'*[x > 0]*dx + B'*raw + C' of the
+// upstream BatchNorm. Its two backward sums are not reduced here: they follow in closed form from the pooled-grid sums of the reduce
+// kernel and the forward statistics of x (sum x, sum x^2, count of x > 0), see train.bn_relu_maxpool_op. One pass of
+// dy/4 + codes/8 + raw + d raw instead of (dy/4 + codes/8 + x + dx) + (dx + raw + d raw).
+struct StUpstream {
+  const float* scale;          // forward affine of the upstream BatchNorm: x = relu(scale*raw + shift)
+  const float* shift;
+  const float* mean;
+  const float* rstd;
+  const float* gamma;
+  const double* sum_dy;        // sum dx*[x > 0]
+  const double* sum_dy_xhat;   // sum dx*[x > 0]*xhat_up
+  float inv_n;
+  StParamGrads pg;
+};
+
+template <int BT>
+__global__ void __launch_bounds__(BT, 640 / BT) bn2_relu_maxpool_bwd_apply_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
+                                                                                 const uint4* __restrict__ raw, uint4* __restrict__ draw, int rows,
+                                                                                 int H, int W, int OH, int OW, int cg, int cg_shift,
+                                                                                 const float* __restrict__ fsc, const float* __restrict__ fsh,
+                                                                                 const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                                 const float* __restrict__ gamma, const double* __restrict__ sum_dy,
+                                                                                 const double* __restrict__ sum_dy_xhat, float inv_n,
+                                                                                 StParamGrads pg, StUpstream up) {
+  extern __shared__ float st_cst[];   // [8][C]: A, B, C of this BatchNorm; scale, shift, A', B', C' of the upstream one
+  __shared__ uint32_t sm_thr[BT * 4], sm_flip[BT * 4];
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < pg.n; c += BT) {
+      if (pg.dbeta) pg.dbeta[c] = (pg.accumulate ? pg.dbeta[c] : 0.f) + (float)sum_dy[c];
+      if (pg.dgamma) pg.dgamma[c] = (pg.accumulate ? pg.dgamma[c] : 0.f) + (float)sum_dy_xhat[c];
+    }
+    for (int c = threadIdx.x; c < up.pg.n; c += BT) {
+      if (up.pg.dbeta) up.pg.dbeta[c] = (up.pg.accumulate ? up.pg.dbeta[c] : 0.f) + (float)up.sum_dy[c];
+      if (up.pg.dgamma) up.pg.dgamma[c] = (up.pg.accumulate ? up.pg.dgamma[c] : 0.f) + (float)up.sum_dy_xhat[c];
+    }
+  }
+  const int C8 = cg * 8;
+  for (int c = threadIdx.x; c < C8; c += BT) {
+    {
+      const double r = (double)__ldg(rstd + c), m = (double)__ldg(mean + c), gm = gamma ? (double)__ldg(gamma + c) : 1.0;
+      const double c1 = sum_dy[c] * (double)inv_n, c2 = sum_dy_xhat[c] * (double)inv_n;
+      st_cst[c] = (float)(gm * r);
+      st_cst[C8 + c] = (float)(-gm * r * r * c2);
+      st_cst[2 * C8 + c] = (float)(gm * r * (r * c2 * m - c1));
+    }
+    {
+      const double r = (double)__ldg(up.rstd + c), m = (double)__ldg(up.mean + c), gm = up.gamma ? (double)__ldg(up.gamma + c) : 1.0;
+      const double c1 = up.sum_dy[c] * (double)up.inv_n, c2 = up.sum_dy_xhat[c] * (double)up.inv_n;
+      st_cst[3 * C8 + c] = __ldg(up.scale + c);
+      st_cst[4 * C8 + c] = __ldg(up.shift + c);
+      st_cst[5 * C8 + c] = (float)(gm * r);
+      st_cst[6 * C8 + c] = (float)(-gm * r * r * c2);
+      st_cst[7 * C8 + c] = (float)(gm * r * (r * c2 * m - c1));
+    }
+  }
+  for (int c2 = threadIdx.x; c2 < cg * 4; c2 += BT) {
+    const float s0 = __ldg(fsc + 2 * c2), s1 = __ldg(fsc + 2 * c2 + 1);
+    sm_thr[c2] = st_relu_threshold(s0, __ldg(fsh + 2 * c2)) | (st_relu_threshold(s1, __ldg(fsh + 2 * c2 + 1)) << 16);
+    sm_flip[c2] = (s0 < 0.f ? 0x00008000u : 0u) | (s1 < 0.f ? 0x80000000u : 0u);
+  }
+  __syncthreads();
+  const int items = (W >> 1) * cg;
+  const int g = threadIdx.x & (cg - 1);
+  uint32_t thr[4], flip[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    thr[q] = sm_thr[g * 4 + q];
+    flip[q] = sm_flip[g * 4 + q];
+  }
+  const uint32_t cst = (uint32_t)__cvta_generic_to_shared(st_cst) + (uint32_t)g * 32u;
+  const uint32_t cst_stride = (uint32_t)cg * 32u;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / H, ih = row - n * H;
+    const bool odd = (ih & 1) != 0;
+    const int oh0 = ih >> 1;
+    const uint32_t r0 = odd ? 6u : 3u;
+    const bool two = odd && (oh0 + 1 < OH);
+    for (int item = threadIdx.x; item < items; item += BT) {
+      const int j = item >> cg_shift;
+      const bool right = j + 1 < OW;
+      const size_t oa = (((size_t)n * OH + oh0) * OW + j) * cg + g;
+      const size_t oc = oa + (size_t)OW * cg;
+      const uint2 zc = make_uint2(0xffffffffu, 0xffffffffu);
+      const uint4 zg = make_uint4(0u, 0u, 0u, 0u);
+      const uint2 cA = __ldg(idx + oa);
+      const uint4 gA = __ldg(dy + oa);
+      const uint2 cB = right ? __ldg(idx + oa + cg) : zc;
+      const uint4 gB = right ? __ldg(dy + oa + cg) : zg;
+      const uint2 cC = two ? __ldg(idx + oc) : zc;
+      const uint4 gC = two ? __ldg(dy + oc) : zg;
+      const uint2 cD = (two && right) ? __ldg(idx + oc + cg) : zc;
+      const uint4 gD = (two && right) ? __ldg(dy + oc + cg) : zg;
+      const size_t od = ((size_t)row * W + 2 * j) * cg + g;
+      const uint4 w0r = __ldg(raw + od), w1r = __ldg(raw + od + cg);
+      uint32_t q0[4] = {0u, 0u, 0u, 0u}, q1[4] = {0u, 0u, 0u, 0u};
+      st_add_masked(q0, cA, gA, r0 + 1u);
+      st_add_masked(q1, cA, gA, r0 + 2u);
+      st_add_masked(q1, cB, gB, r0);
+      if (two) {
+        st_add_masked(q0, cC, gC, 1u);
+        st_add_masked(q1, cC, gC, 2u);
+        st_add_masked(q1, cD, gD, 0u);
+      }
+      float w0[8], w1[8], x0[8], x1[8];
+      st_bf16x8_to_f32(w0r, w0);
+      st_bf16x8_to_f32(w1r, w1);
+      uint4 x0r, x1r;
+      {  // x as the forward stored it: fma, ReLU, round to bf16
+        float usc[8], ush[8];
+        st_lds8(cst + 3u * cst_stride, usc);
+        st_lds8(cst + 4u * cst_stride, ush);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          x0[q] = fmaxf(fmaf(w0[q], usc[q], ush[q]), 0.f);
+          x1[q] = fmaxf(fmaf(w1[q], usc[q], ush[q]), 0.f);
+        }
+        x0r = st_f32_to_bf16x8(x0);
+        x1r = st_f32_to_bf16x8(x1);
+        st_bf16x8_to_f32(x0r, x0);
+        st_bf16x8_to_f32(x1r, x1);
+      }
+      {
+        const uint32_t xa[4] = {x0r.x, x0r.y, x0r.z, x0r.w}, xb[4] = {x1r.x, x1r.y, x1r.z, x1r.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          q0[q] &= st_gt2_mask(xa[q] ^ flip[q], thr[q]);
+          q1[q] &= st_gt2_mask(xb[q] ^ flip[q], thr[q]);
+        }
+      }
+      float o0[8], o1[8];
+      st_bf16x8_to_f32(make_uint4(q0[0], q0[1], q0[2], q0[3]), o0);
+      st_bf16x8_to_f32(make_uint4(q1[0], q1[1], q1[2], q1[3]), o1);
+      {
+        float A[8], Bc[8];
+        st_lds8(cst, A);
+        st_lds8(cst + cst_stride, Bc);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          o0[q] = fmaf(A[q], o0[q], Bc[q] * x0[q]);
+          o1[q] = fmaf(A[q], o1[q], Bc[q] * x1[q]);
+        }
+      }
+      {
+        float Cc[8], A2[8];
+        st_lds8(cst + 2u * cst_stride, Cc);
+        st_lds8(cst + 5u * cst_stride, A2);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {   // dx complete; through the upstream ReLU and the data term of its BatchNorm
+          o0[q] = x0[q] > 0.f ? A2[q] * (o0[q] + Cc[q]) : 0.f;
+          o1[q] = x1[q] > 0.f ? A2[q] * (o1[q] + Cc[q]) : 0.f;
+        }
+      }
+      {
+        float B2[8], C2[8];
+        st_lds8(cst + 6u * cst_stride, B2);
+        st_lds8(cst + 7u * cst_stride, C2);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          o0[q] += fmaf(B2[q], w0[q], C2[q]);
+          o1[q] += fmaf(B2[q], w1[q], C2[q]);
+        }
+      }
+      draw[od] = st_f32_to_bf16x8(o0);
+      draw[od + cg] = st_f32_to_bf16x8(o1);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------- ECA + BatchNorm
 // EfficientConvBlock's second gate in training (basics.py:118-121): c1 = relu(BN(raw)) -> c1s = c1 * gate[n, c] -> conv2. The data
 // gradient of conv2 arrives as dy = d c1s. The separate launches spend three passes of 2 + 3 + 3 tensors on it (gate gradient
@@ -558,7 +734,7 @@ extern "C" int pmoe_bn_relu_maxpool_fwd(const PmoeView4* x, const float* scale, 
 
 extern "C" int pmoe_bn_relu_maxpool_bwd_reduce(const PmoeView4* dy, const void* x_at_max, const float* fwd_scale, const float* fwd_shift,
                                                const float* mean, const float* rstd, double* sum_dy, double* sum_dy_xhat,
-                                               pmoe_stream_t stream_) {
+                                               double* sum_dy_xpos, pmoe_stream_t stream_) {
   if (!st_dense(dy) || !x_at_max || !fwd_scale || !fwd_shift || !mean || !rstd || !sum_dy || !sum_dy_xhat || ((uintptr_t)x_at_max % 16) ||
       ((uintptr_t)fwd_scale % 16) || ((uintptr_t)fwd_shift % 16)) {
     set_error("bn_relu_maxpool_bwd_reduce: dense bf16 pooled gradient and all statistics are required");
@@ -576,7 +752,7 @@ extern "C" int pmoe_bn_relu_maxpool_bwd_reduce(const PmoeView4* dy, const void* 
   blocks = (npix + ppb - 1) / ppb;
   bn_relu_maxpool_bwd_reduce_kernel<<<(unsigned)blocks, kRedThreads, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const uint4*>(dy->ptr), static_cast<const uint4*>(x_at_max), npix, cg, fwd_scale, fwd_shift, mean, rstd, sum_dy, sum_dy_xhat,
-      ppb);
+      ppb, sum_dy_xpos);
   return check_launch("bn_relu_maxpool_bwd_reduce");
 }
 
@@ -707,4 +883,66 @@ extern "C" int pmoe_eca_bn_bwd_apply(const PmoeView4* dy, const PmoeView4* raw, 
       static_cast<const uint4*>(dy->ptr), static_cast<const uint4*>(raw->ptr), static_cast<uint4*>(dx->ptr), dy->n, (int)hw, cg, gate,
       gate_stride, dmean, dmean_stride, fwd_scale, fwd_shift, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, pg);
   return check_launch("eca_bn_bwd_apply");
+}
+
+extern "C" int pmoe_bn2_relu_maxpool_bwd_apply(const PmoeView4* dy, const uint8_t* idx, const PmoeView4* raw, const float* fwd_scale,
+                                               const float* fwd_shift, const float* mean, const float* rstd, const float* gamma,
+                                               const double* sum_dy, const double* sum_dy_xhat, float inv_n,
+                                               const PmoeBnParamGrads* param_grads, const float* up_scale, const float* up_shift,
+                                               const float* up_mean, const float* up_rstd, const float* up_gamma, const double* up_sum_dy,
+                                               const double* up_sum_dy_xhat, const PmoeBnParamGrads* up_param_grads, const PmoeView4* draw,
+                                               pmoe_stream_t stream_) {
+  int rc = st_geometry(raw, dy, "bn2_relu_maxpool_bwd_apply");
+  if (rc) return rc;
+  if (!st_dense(draw) || draw->n != raw->n || draw->h != raw->h || draw->w != raw->w || draw->c != raw->c || !idx || ((uintptr_t)idx % 8) ||
+      !fwd_scale || !fwd_shift || !mean || !rstd || !sum_dy || !sum_dy_xhat || !up_scale || !up_shift || !up_mean || !up_rstd || !up_sum_dy ||
+      !up_sum_dy_xhat) {
+    set_error("bn2_relu_maxpool_bwd_apply: bad arguments");
+    return PMOE_ERR_ARG;
+  }
+  const int cg = raw->c / 8;
+  if (cg > 128 || 128 % cg != 0 || (size_t)8 * raw->c * sizeof(float) > 40 * 1024) {
+    set_error("bn2_relu_maxpool_bwd_apply: channel-group count must divide 128, at most 1280 channels");
+    return PMOE_ERR_UNSUPPORTED;
+  }
+  auto to_pg = [&](const PmoeBnParamGrads* g, StParamGrads* o) {
+    *o = StParamGrads{nullptr, nullptr, 0, 0};
+    if (!g) return true;
+    if (g->n < 0 || g->n > raw->c) return false;
+    o->dgamma = g->dgamma;
+    o->dbeta = g->dbeta;
+    o->n = g->n;
+    o->accumulate = g->accumulate;
+    return true;
+  };
+  StParamGrads pg;
+  StUpstream up;
+  if (!to_pg(param_grads, &pg) || !to_pg(up_param_grads, &up.pg)) {
+    set_error("bn2_relu_maxpool_bwd_apply: parameter-gradient channel count out of range");
+    return PMOE_ERR_ARG;
+  }
+  up.scale = up_scale;
+  up.shift = up_shift;
+  up.mean = up_mean;
+  up.rstd = up_rstd;
+  up.gamma = up_gamma;
+  up.sum_dy = up_sum_dy;
+  up.sum_dy_xhat = up_sum_dy_xhat;
+  up.inv_n = inv_n;
+  constexpr int BT = 128;
+  const size_t cst_bytes = (size_t)8 * raw->c * sizeof(float);
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int q = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, bn2_relu_maxpool_bwd_apply_kernel<BT>, BT, 40 * 1024);
+    per_sm = q < 1 ? 1 : q;
+  }
+  const int rows = raw->n * raw->h;
+  int grid = num_sms() * per_sm;
+  if (grid > rows) grid = rows;
+  bn2_relu_maxpool_bwd_apply_kernel<BT><<<grid, BT, cst_bytes, static_cast<cudaStream_t>(stream_)>>>(
+      static_cast<const uint4*>(dy->ptr), reinterpret_cast<const uint2*>(idx), static_cast<const uint4*>(raw->ptr), static_cast<uint4*>(draw->ptr),
+      rows, raw->h, raw->w, dy->h, dy->w, cg, __builtin_ctz((unsigned)cg), fwd_scale, fwd_shift, mean, rstd, gamma, sum_dy, sum_dy_xhat, inv_n, pg,
+      up);
+  return check_launch("bn2_relu_maxpool_bwd_apply");
 }

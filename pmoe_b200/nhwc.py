@@ -18,13 +18,14 @@ def dtype_code(t):
 
 class Act:
     """An NHWC activation: tensor (N,H,W,Cpad) with `c` logical channels; channels [c, Cpad) are zero."""
-    __slots__ = ("t", "c", "rg", "stats", "bn_relu", "gate_grad")
+    __slots__ = ("t", "c", "rg", "stats", "bn_relu", "bn_ctx", "gate_grad")
 
     def __init__(self, t, c, rg=False):
         self.t, self.c, self.rg = t, c, rg
         self.gate_grad = None  # ECA of a network input: callback(d gate (N, Cpad) fp32) fed by the consuming conv's per-image wgrad
         self.bn_relu = False  # t = relu(BatchNorm(raw conv output)) with batch statistics and nothing added (set by train.conv_op)
-        self.stats = None   # (sum, sum of squares) per channel, fp64, when the producing kernel already reduced them
+        self.bn_ctx = None  # with bn_relu: (bn, raw, mean, rstd, (scale, shift), gamma, cout, cstore) of that BatchNorm (train.conv_op)
+        self.stats = None   # (sum, sum of squares[, count > 0]) per channel, fp64, when the producing kernel already reduced them
 
     @property
     def shape(self):
@@ -142,6 +143,13 @@ def affine_act_stats(t, scale, shift, act, out, pool=None, pool_stride=0, out_st
             or t.shape[3] // 8 > 256:
         return False
     vs, vd = view4(t), view4(out)
+    if out_stats is not None and len(out_stats) > 2:
+        if pool is not None or act != "relu":
+            return False
+        check(profiler.launch("affine_act", lambda: lib().pmoe_affine_relu_stats_pos(
+            C.byref(vs), C.byref(vd), scale.data_ptr(), shift.data_ptr(), out_stats[0].data_ptr(), out_stats[1].data_ptr(),
+            out_stats[2].data_ptr(), stream_ptr()), io=(t, out)), "affine_relu_stats_pos")
+        return True
     check(profiler.launch("affine_act", lambda: lib().pmoe_affine_act_stats(
         C.byref(vs), C.byref(vd), dtype_code(t), scale.data_ptr(), shift.data_ptr(), ACT[act], _lib.ptr(pool),
         (pool.stride(0) if pool_stride == 0 else pool_stride) if pool is not None else 0,

@@ -77,6 +77,7 @@ class Tape:
         self.bucketer = None        # pmoe_b200.dp.GradBucketer during a data-parallel backward
         self.presums = {}           # id(Act) -> (sum dy*[y>0], sum dy*y) reduced by the kernel that wrote the Act's gradient
         self.lazy = {}              # id(Act) -> (dy, gate, dmean): gradient dy*gate[n,c] + dmean[n,c] that is never stored (eca_op)
+        self.raw_grads = {}         # id(Act) -> gradient of the RAW conv output behind the Act's BatchNorm + ReLU, already formed by the consumer (bn_relu_maxpool_op)
         self.arena = {}             # dtype -> [zeroed chunk, elements handed out]
         self.direct = set()         # id(param) whose gradient was accumulated straight into param.grad
         self.branch_stream = None   # side stream of the branch being recorded / replayed (None: the caller's stream)
@@ -224,6 +225,7 @@ class Tape:
         self.alive = []
         self.grads = {}
         self.lazy = {}
+        self.raw_grads = {}
         if self.bucketer is not None:  # gradients whose announced contributions did not all arrive
             for k in self.pgrads:
                 if k not in self.reported:
@@ -556,6 +558,8 @@ def _bn_tail_forward(tape, bn, raw, ssum, ssq, count, cout, cstore, act, residua
             v = view4(z_t)
             check(profiler.launch("channel_stats", lambda: lib().pmoe_channel_stats(
                 C.byref(v), dtype_code(z_t), out_stats[0].data_ptr(), out_stats[1].data_ptr(), stream_ptr()), io=(z_t,)), "channel_stats")
+            if len(out_stats) > 2:
+                out_stats[2].add_((z_t > 0).sum(dim=(0, 1, 2)).double())
     # (scale, shift) let the backward recompute the ReLU mask from `raw` instead of reading z (not with a residual add)
     return z_t, mean, rstd, ((scale, shift) if residual is None else None)
 
@@ -642,6 +646,8 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
                                                                                     ssq.data_ptr(), stream_ptr()), io=(raw,)), "channel_stats")
         if want_out_stats:
             out_stats = (tape.zeros(cstore, torch.float64, dev), tape.zeros(cstore, torch.float64, dev))
+            if act == "relu" and residual is None and not want_pool and dt == torch.bfloat16:
+                out_stats += (tape.zeros(cstore, torch.float64, dev),)   # count of outputs > 0 (closed-form backward of this BatchNorm)
         z_t, mean, rstd, fwd_aff = _bn_tail_forward(tape, bn, raw, ssum, ssq, n * h * w, cout, cstore, act, residual, out,
                                                     pool=pool if want_pool else None, out_stats=out_stats)
         gamma_p = _padded_gamma(bn, cstore)
@@ -653,6 +659,8 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
     z = _new_act(tape, z_t, cout, rg_in)
     z.stats = out_stats
     z.bn_relu = bool(bn_train and act == "relu" and residual is None and fwd_aff is not None)  # z = relu(BN(raw)), nothing added
+    if z.bn_relu:
+        z.bn_ctx = (bn, raw, mean, rstd, fwd_aff, gamma_p, cout, cstore)
     if not (tape.save and rg_in):
         return z, pool
 
@@ -666,15 +674,22 @@ def conv_op(tape, srcs, weight, bias=None, bn=None, act=None, residual=None, wan
                 C.byref(vd), dtype_code(lazy[0]), lazy[1].data_ptr(), lazy[1].stride(0), lazy[2].data_ptr(), lazy[2].stride(0), C.byref(vg),
                 int(existed), stream_ptr()), io=(lazy[0], g, g if existed else None)), "eca_bwd_apply")
             lazy = None
-        dz = None if lazy is not None else tape.grad_of(z)
-        if dz is None and lazy is None:
+        rawg = tape.raw_grads.pop(id(z), None)
+        if rawg is not None and (lazy is not None or id(z) in tape.grads):
+            raise RuntimeError("pmoe_b200 conv_op: the gradient of the raw conv output was formed by the consumer, but another "
+                               "gradient of the activation exists as well (" + tag + ")")
+        dz = None if (lazy is not None or rawg is not None) else tape.grad_of(z)
+        if dz is None and lazy is None and rawg is None:
             return
         z_saved = z_t if act not in (None, "none") else None
         dres, acc_dres = None, False
         if residual is not None and _rg(residual):
             dres, acc_dres = _grad_buffer(tape, residual)
-        dy = torch.empty(n, h, w, cstore, dtype=dt, device=dev)  # gradient w.r.t. the raw conv output
-        if bn_train:
+        # gradient w.r.t. the raw conv output
+        dy = rawg if rawg is not None else torch.empty(n, h, w, cstore, dtype=dt, device=dev)
+        if rawg is not None:
+            pass   # BatchNorm backward (and its affine gradients) done by the consumer: bn_relu_maxpool_op
+        elif bn_train:
             pres = tape.presums.pop(id(z), None)
             if pres is not None and fwd_aff is not None and act == "relu":
                 # the kernel that wrote dz also reduced sum dz*[z>0] and sum dz*z; with z = relu(scale*raw + shift):
@@ -1203,7 +1218,7 @@ def bn_act_op(tape, bn, x, act="relu", tag=""):
     mean = rstd = gamma_p = scale = fwd_aff = None
     if bn_train:
         if x.stats is not None and x.stats[0].numel() == cp:
-            ssum, ssq = x.stats    # reduced by the kernel that wrote x (conv_op(want_out_stats=True))
+            ssum, ssq = x.stats[0], x.stats[1]    # reduced by the kernel that wrote x (conv_op(want_out_stats=True))
         else:
             ssum = tape.zeros(cp, torch.float64, dev)
             ssq = tape.zeros(cp, torch.float64, dev)
@@ -1304,6 +1319,7 @@ def resnet18_eca(tape, net, x, tag="backbone"):
 
 
 FUSE_STEM_TAIL = _os0.environ.get("PMOE_FUSE_STEM_TAIL", "1") != "0"   # tests switch it off to compare with the separate launches
+FUSE_STEM_UP = _os0.environ.get("PMOE_FUSE_STEM_UP", "1") != "0"       # ... and its backward continued through the conv + BN + ReLU in front
 
 
 def bn_relu_maxpool_op(tape, bn, x, tag=""):
@@ -1316,8 +1332,10 @@ def bn_relu_maxpool_op(tape, bn, x, tag=""):
         return maxpool_op(tape, bn_act_op(tape, bn, x, "relu", tag=tag), 3, 2, 1)
     dev, c = x.t.device, x.c
     rg = _rg(x) or _any_rg([bn.weight, bn.bias])
+    npos = None
     if x.stats is not None and x.stats[0].numel() == cp:
-        ssum, ssq = x.stats
+        ssum, ssq = x.stats[0], x.stats[1]
+        npos = x.stats[2] if len(x.stats) > 2 else None
     else:
         ssum = tape.zeros(cp, torch.float64, dev)
         ssq = tape.zeros(cp, torch.float64, dev)
@@ -1337,12 +1355,61 @@ def bn_relu_maxpool_op(tape, bn, x, tag=""):
     if tape.save and rg:
         gamma_p = _padded_gamma(bn, cp)
 
+        def _stem_tail_backward_through_upstream(dp, ctx):
+            """bn1 -> relu -> maxpool backward continued through the ReLU and BatchNorm of the conv that produced x: neither the
+            gradient of x nor x itself is touched; the upstream conv_op receives the gradient of its RAW output (tape.raw_grads)."""
+            ubn, uraw, umean, urstd, uaff, ugamma, ucout, _ = ctx
+            N = float(n * h * w)
+            s1 = tape.zeros(cp, torch.float64, dev)
+            s2 = tape.zeros(cp, torch.float64, dev)
+            e1 = tape.zeros(cp, torch.float64, dev)
+            vdp = view4(dp)
+            check(profiler.launch("bn_relu_maxpool_bwd_reduce", lambda: lib().pmoe_bn_relu_maxpool_bwd_reduce(
+                C.byref(vdp), x_at_max.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                s1.data_ptr(), s2.data_ptr(), e1.data_ptr(), stream_ptr()), io=(dp, x_at_max)), "bn_relu_maxpool_bwd_reduce")
+            # dx = A*d + B*x + C per channel (d: the pooled gradient routed to its argmax and masked by this layer's ReLU), so the two
+            # backward sums of the upstream BatchNorm are linear in sums that exist already:
+            #   sum dx*[x>0] = A*sum d*[x>0] + B*sum x + C*count(x>0)        (x >= 0: x*[x>0] = x)
+            #   sum dx*x     = A*sum d*x     + B*sum x^2 + C*sum x
+            g64, r64, m64 = gamma_p[:cp].double(), rstd[:cp].double(), mean[:cp].double()
+            c1, c2 = s1 / N, s2 / N
+            A = g64 * r64
+            Bq = -g64 * r64 * r64 * c2
+            Cq = g64 * r64 * (r64 * c2 * m64 - c1)
+            sdx = s2 / r64 + m64 * s1                                    # sum d*x back from sum d*xhat
+            n1 = A * e1 + Bq * ssum[:cp] + Cq * npos[:cp]
+            n2 = A * sdx + Bq * ssq[:cp] + Cq * ssum[:cp]
+            # ... and through the upstream forward affine as conv_op does for sums handed down by a consumer (x = scale*raw + shift
+            # wherever x > 0): sum dx*m*raw = (sum dx*x - shift*sum dx*m) / scale
+            usc, ush = uaff[0][:cp].double(), uaff[1][:cp].double()
+            sraw = torch.where(usc != 0, (n2 - ush * n1) / torch.where(usc != 0, usc, torch.ones_like(usc)), torch.zeros_like(usc))
+            u1 = n1.contiguous()
+            u2 = (urstd[:cp].double() * (sraw - umean[:cp].double() * n1)).contiguous()
+            pg, pdone = _bn_pgrads(tape, bn, c)
+            upg, updone = _bn_pgrads(tape, ubn, ucout)
+            draw = torch.empty(uraw.shape, dtype=uraw.dtype, device=dev)
+            vr, vd = view4(uraw), view4(draw)
+            check(profiler.launch("bn2_relu_maxpool_bwd_apply", lambda: lib().pmoe_bn2_relu_maxpool_bwd_apply(
+                C.byref(vdp), idx.data_ptr(), C.byref(vr), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                gamma_p.data_ptr(), s1.data_ptr(), s2.data_ptr(), 1.0 / N, None if pg is None else C.byref(pg),
+                uaff[0].data_ptr(), uaff[1].data_ptr(), umean.data_ptr(), urstd.data_ptr(), ugamma.data_ptr(), u1.data_ptr(), u2.data_ptr(),
+                None if upg is None else C.byref(upg), C.byref(vd), stream_ptr()), io=(dp, idx, uraw, draw)), "bn2_relu_maxpool_bwd_apply")
+            tape.raw_grads[id(x)] = draw
+            for prm in pdone + updone:
+                tape.pgrad_done(prm)
+
         def backward():
             dp = tape.grad_of(pa)
             if dp is None:
                 return
             if not dp.is_contiguous():
                 dp = dp.contiguous()
+            ctx = getattr(x, "bn_ctx", None)
+            if (FUSE_STEM_UP and FUSE_BN_CHAIN_SUMS and ctx is not None and npos is not None and _rg(x) and id(x) not in tape.grads
+                    and id(x) not in tape.lazy and 128 % (cp // 8) == 0 and ctx[1] is not None and ctx[1].is_contiguous()
+                    and ctx[1].shape == x.t.shape and ctx[7] == cp):
+                _stem_tail_backward_through_upstream(dp, ctx)
+                return
             g, existed = _grad_buffer(tape, x)
             tmp = g if (not existed and g.is_contiguous()) else torch.empty(x.t.shape, dtype=x.t.dtype, device=dev)
             s1 = tape.zeros(cp, torch.float64, dev)
@@ -1350,7 +1417,7 @@ def bn_relu_maxpool_op(tape, bn, x, tag=""):
             vdp, vxx, vdx = view4(dp), view4(x.t), view4(tmp)
             check(profiler.launch("bn_relu_maxpool_bwd_reduce", lambda: lib().pmoe_bn_relu_maxpool_bwd_reduce(
                 C.byref(vdp), x_at_max.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                s1.data_ptr(), s2.data_ptr(), stream_ptr()), io=(dp, x_at_max)), "bn_relu_maxpool_bwd_reduce")
+                s1.data_ptr(), s2.data_ptr(), None, stream_ptr()), io=(dp, x_at_max)), "bn_relu_maxpool_bwd_reduce")
             pg, pdone = _bn_pgrads(tape, bn, c)
             chain = getattr(x, "bn_relu", False) and not existed and tmp is g and FUSE_BN_CHAIN_SUMS
             n1 = tape.zeros(cp, torch.float64, dev) if chain else None

@@ -49,7 +49,7 @@ def fwd():
 
 def reduce():
     check(lib().pmoe_bn_relu_maxpool_bwd_reduce(C.byref(vdp), xm.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
-                                                rstd.data_ptr(), s1.data_ptr(), s2.data_ptr(), stream_ptr()), "reduce")
+                                                rstd.data_ptr(), s1.data_ptr(), s2.data_ptr(), None, stream_ptr()), "reduce")
 
 
 def apply(chain):

@@ -32,7 +32,7 @@ s1 = torch.zeros(c, dtype=torch.float64, device=dev)
 s2 = torch.zeros(c, dtype=torch.float64, device=dev)
 vdp = view4(dp)
 check(lib().pmoe_bn_relu_maxpool_bwd_reduce(C.byref(vdp), xm.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                            s1.data_ptr(), s2.data_ptr(), stream_ptr()), "reduce")
+                                            s1.data_ptr(), s2.data_ptr(), None, stream_ptr()), "reduce")
 dx = torch.empty_like(x)
 vdx = view4(dx)
 check(lib().pmoe_bn_relu_maxpool_bwd_apply(C.byref(vdp), idx.data_ptr(), C.byref(vx), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),

@@ -84,7 +84,7 @@ def test_stem_tail_backward_vs_autograd(n, h, w, c, chain):
     s2 = torch.zeros(c, dtype=torch.float64, device=dev)
     vdp, vx = view4(dp), view4(x)
     check(lib().pmoe_bn_relu_maxpool_bwd_reduce(C.byref(vdp), xm.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
-                                                rstd.data_ptr(), s1.data_ptr(), s2.data_ptr(), stream_ptr()), "reduce")
+                                                rstd.data_ptr(), s1.data_ptr(), s2.data_ptr(), None, stream_ptr()), "reduce")
     dx = torch.empty_like(x)
     vdx = view4(dx)
     n1 = torch.zeros(c, dtype=torch.float64, device=dev) if chain else None
@@ -220,7 +220,7 @@ def test_stem_backward_kernels_at_bench_size_properties():
     s2 = torch.zeros(c, dtype=torch.float64, device=dev)
     vdp = view4(dp)
     check(lib().pmoe_bn_relu_maxpool_bwd_reduce(C.byref(vdp), xm.data_ptr(), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
-                                                rstd.data_ptr(), s1.data_ptr(), s2.data_ptr(), stream_ptr()), "reduce")
+                                                rstd.data_ptr(), s1.data_ptr(), s2.data_ptr(), None, stream_ptr()), "reduce")
     dx = torch.empty_like(x)
     vdx = view4(dx)
     check(lib().pmoe_bn_relu_maxpool_bwd_apply(
@@ -271,3 +271,86 @@ def test_stem_backward_kernels_at_bench_size_properties():
     o1, o2 = orthogonality(draw)
     print("   eca + BatchNorm apply: |sum dx| / sum|dx| = %.2e, |sum dx xhat| / sum|dx| = %.2e" % (o1, o2))
     assert o1 < 1e-3 and o2 < 1e-3, (o1, o2)
+
+
+@pytest.mark.parametrize("n,h,w,c", [(3, 20, 28, 64), (2, 8, 6, 16), (2, 32, 32, 128)])
+def test_stem_tail_backward_through_the_upstream_batchnorm(n, h, w, c):
+    """pmoe_bn2_relu_maxpool_bwd_apply: raw -> BN_up (batch statistics) -> ReLU -> [stored as bf16 = x] -> bn1 (batch statistics)
+    -> ReLU -> MaxPool2d(3, 2, 1), backward to raw in ONE pass with the upstream sums in closed form, against torch autograd in fp64
+    through the same chain (bf16 storage of x as a straight-through rounding). Negative gammas in both BatchNorms."""
+    from pmoe_b200 import train
+    from pmoe_b200._lib import lib, check, view4, stream_ptr
+    g = torch.Generator().manual_seed(13 * n + c)
+    raw = (torch.randn(n, h, w, c, generator=g) * 1.3 - 0.2).to(torch.bfloat16).to(dev)
+    ug = torch.randn(c, generator=g).to(dev)
+    ub = (torch.randn(c, generator=g) * 0.5).to(dev)
+    g1 = torch.randn(c, generator=g).to(dev)
+    b1 = (torch.randn(c, generator=g) * 0.5).to(dev)
+    dp = torch.randn(n, h // 2, w // 2, c, generator=g).to(torch.bfloat16).to(dev)
+    N = n * h * w
+    rd = raw.double()
+    umean = rd.mean(dim=(0, 1, 2))
+    urstd = 1.0 / torch.sqrt(rd.var(dim=(0, 1, 2), unbiased=False) + 1e-5)
+    uscale = (ug.double() * urstd).float()
+    ushift = (ub.double() - umean * ug.double() * urstd).float()
+    x = torch.relu(torch.addcmul(ushift, raw.float(), uscale)).to(torch.bfloat16)        # what the forward stores
+    xd = x.double()
+    mean = xd.mean(dim=(0, 1, 2))
+    rstd = 1.0 / torch.sqrt(xd.var(dim=(0, 1, 2), unbiased=False) + 1e-5)
+    scale = (g1.double() * rstd).float()
+    shift = (b1.double() - mean * g1.double() * rstd).float()
+    meanf, rstdf, umeanf, urstdf = mean.float(), rstd.float(), umean.float(), urstd.float()
+    p, idx, xm = _fused_forward(x, scale, shift)
+    s1 = torch.zeros(c, dtype=torch.float64, device=dev)
+    s2 = torch.zeros(c, dtype=torch.float64, device=dev)
+    e1 = torch.zeros(c, dtype=torch.float64, device=dev)
+    vdp = view4(dp)
+    check(lib().pmoe_bn_relu_maxpool_bwd_reduce(C.byref(vdp), xm.data_ptr(), scale.data_ptr(), shift.data_ptr(), meanf.data_ptr(),
+                                                rstdf.data_ptr(), s1.data_ptr(), s2.data_ptr(), e1.data_ptr(), stream_ptr()), "reduce")
+    # closed-form sums of the upstream BatchNorm (train.bn_relu_maxpool_op)
+    ssum, ssq, npos = xd.sum(dim=(0, 1, 2)), (xd * xd).sum(dim=(0, 1, 2)), (x > 0).double().sum(dim=(0, 1, 2))
+    g64, r64, m64 = g1.double(), rstdf.double(), meanf.double()
+    c1, c2 = s1 / N, s2 / N
+    A, Bq, Cq = g64 * r64, -g64 * r64 * r64 * c2, g64 * r64 * (r64 * c2 * m64 - c1)
+    n1 = A * e1 + Bq * ssum + Cq * npos
+    n2 = A * (s2 / r64 + m64 * s1) + Bq * ssq + Cq * ssum
+    usc, ush = uscale.double(), ushift.double()
+    sraw = torch.where(usc != 0, (n2 - ush * n1) / torch.where(usc != 0, usc, torch.ones_like(usc)), torch.zeros_like(usc))
+    u1 = n1.contiguous()
+    u2 = (urstdf.double() * (sraw - umeanf.double() * n1)).contiguous()
+    draw = torch.empty_like(raw)
+    dgam, dbet, udgam, udbet = [torch.zeros(c, device=dev) for _ in range(4)]
+    pg, upg = train.BnParamGrads(), train.BnParamGrads()
+    pg.dgamma, pg.dbeta, pg.n, pg.accumulate = dgam.data_ptr(), dbet.data_ptr(), c, 0
+    upg.dgamma, upg.dbeta, upg.n, upg.accumulate = udgam.data_ptr(), udbet.data_ptr(), c, 0
+    vr, vd = view4(raw), view4(draw)
+    check(lib().pmoe_bn2_relu_maxpool_bwd_apply(
+        C.byref(vdp), idx.data_ptr(), C.byref(vr), scale.data_ptr(), shift.data_ptr(), meanf.data_ptr(), rstdf.data_ptr(), g1.data_ptr(),
+        s1.data_ptr(), s2.data_ptr(), 1.0 / N, C.byref(pg), uscale.data_ptr(), ushift.data_ptr(), umeanf.data_ptr(), urstdf.data_ptr(),
+        ug.data_ptr(), u1.data_ptr(), u2.data_ptr(), C.byref(upg), C.byref(vd), stream_ptr()), "bn2 apply")
+    # fp64 autograd through the whole chain
+    rr = raw.double().requires_grad_(True)
+    ugd, ubd = ug.double().requires_grad_(True), ub.double().requires_grad_(True)
+    g1d, b1d = g1.double().requires_grad_(True), b1.double().requires_grad_(True)
+    mu = rr.mean(dim=(0, 1, 2))
+    var = rr.var(dim=(0, 1, 2), unbiased=False)
+    xx = torch.relu((rr - mu) / torch.sqrt(var + 1e-5) * ugd + ubd)
+    xx = xx + (x.double() - xx).detach()                                   # bf16 storage of x, straight through
+    xx.retain_grad()
+    mu1 = xx.mean(dim=(0, 1, 2))
+    var1 = xx.var(dim=(0, 1, 2), unbiased=False)
+    z = torch.relu((xx - mu1) / torch.sqrt(var1 + 1e-5) * g1d + b1d)
+    pp = torch.nn.functional.max_pool2d(z.permute(0, 3, 1, 2), 3, 2, 1)
+    pp.backward(dp.double().permute(0, 3, 1, 2))
+    e = _rel(draw.float(), rr.grad)
+    print("\n   two-BatchNorm stem backward %dx%dx%dx%d: d raw %.2e, bn1 %.1e / %.1e, upstream BN %.1e / %.1e" % (
+        n, h, w, c, e, _rel(dgam, g1d.grad), _rel(dbet, b1d.grad), _rel(udgam, ugd.grad), _rel(udbet, ubd.grad)))
+    assert e < 6e-3                                                          # bf16 storage of d raw (and of x inside the chain)
+    assert _rel(dgam, g1d.grad) < 1e-4 and _rel(dbet, b1d.grad) < 1e-4
+    assert _rel(udbet, ubd.grad) < 1e-3
+    # The upstream d gamma = sum dx*m*xhat_up is recovered from sum dx*x through the forward affine (x = gamma_up*xhat_up + beta_up where
+    # x > 0), i.e. through x's bf16 STORAGE: every term carries x's rounding error (<= 2^-9 |x|) divided by gamma_up — the same route
+    # conv_op takes for sums handed down by any consumer. Per channel: a few 2^-9 * sqrt(sum (dx*x)^2) / |gamma_up|.
+    tol = 6 * 2.0 ** -9 * (xx.grad * x.double()).pow(2).sum(dim=(0, 1, 2)).sqrt() / ug.double().abs().clamp_min(1e-12) \
+        + 1e-4 * ugd.grad.abs()
+    assert bool(((udgam.double() - ugd.grad).abs() <= tol).all()), ((udgam.double() - ugd.grad).abs() / tol).max().item()

@@ -160,9 +160,13 @@ struct StParamGrads {
 
 // volatile shared-memory read of 8 floats: per-channel constants are re-read where they are used instead of being hoisted out
 // of the item loop into registers.
-__device__ __forceinline__ void st_lds8(uint32_t addr, float (&v)[8]) {
+// Layout of one per-channel array of C = cg*8 floats: [half][g][4], so that the 8 threads of a quarter warp (g = 0..7) read 8
+// CONSECUTIVE 16-byte chunks per instruction. The natural [g][8] layout puts g and g + 4 on the same banks: ncu showed 8 shared
+// wavefronts per LDS.128 and the L1 pipe at 90 %.
+__device__ __forceinline__ int st_cst_index(int c, int cg) { return ((((c >> 2) & 1) * cg + (c >> 3)) << 2) + (c & 3); }
+__device__ __forceinline__ void st_lds8(uint32_t addr, uint32_t half_stride, float (&v)[8]) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(addr + 16u));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(addr + half_stride));
 }
 // The ReLU mask of the fused layer, fmaf(x, scale, shift) > 0, as a compare of the bf16 input itself: with x' = x for scale > 0
 // and -x for scale < 0 the predicate fmaf(x', |scale|, shift) > 0 is monotone in x' (rounding is monotone), so it equals
@@ -250,9 +254,10 @@ __global__ void __launch_bounds__(BT, (NEXT ? 896 : 1024) / BT) bn_relu_maxpool_
   for (int c = threadIdx.x; c < cg * 8; c += blockDim.x) {  // dx = gamma*rstd*(d - c1 - (x - mean)*rstd*c2) = A*d + B*x + C
     const double r = (double)__ldg(rstd + c), m = (double)__ldg(mean + c), gm = gamma ? (double)__ldg(gamma + c) : 1.0;
     const double c1 = sum_dy[c] * (double)inv_n, c2 = sum_dy_xhat[c] * (double)inv_n;
-    st_cst[c] = (float)(gm * r);
-    st_cst[cg * 8 + c] = (float)(-gm * r * r * c2);
-    st_cst[cg * 16 + c] = (float)(gm * r * (r * c2 * m - c1));
+    const int ci = st_cst_index(c, cg);
+    st_cst[ci] = (float)(gm * r);
+    st_cst[cg * 8 + ci] = (float)(-gm * r * r * c2);
+    st_cst[cg * 16 + ci] = (float)(gm * r * (r * c2 * m - c1));
   }
   for (int c2 = threadIdx.x; c2 < cg * 4; c2 += blockDim.x) {
     const float s0 = __ldg(fsc + 2 * c2), s1 = __ldg(fsc + 2 * c2 + 1);
@@ -268,8 +273,8 @@ __global__ void __launch_bounds__(BT, (NEXT ? 896 : 1024) / BT) bn_relu_maxpool_
     thr[q] = sm_thr[g * 4 + q];
     flip[q] = sm_flip[g * 4 + q];
   }
-  const uint32_t cst = (uint32_t)__cvta_generic_to_shared(st_cst) + (uint32_t)g * 32u;
-  const uint32_t cst_stride = (uint32_t)cg * 32u;
+  const uint32_t cst = (uint32_t)__cvta_generic_to_shared(st_cst) + (uint32_t)g * 16u;
+  const uint32_t cst_stride = (uint32_t)cg * 32u, cst_half = (uint32_t)cg * 16u;
   float na[8] = {0, 0, 0, 0, 0, 0, 0, 0}, nb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // a block walks whole input rows (few blocks, so the upstream sums cost a handful of atomics per channel)
   // (whole rows per block, rows round-robin over the resident blocks; (row, part) jobs measured 10 % slower)
@@ -320,8 +325,8 @@ __global__ void __launch_bounds__(BT, (NEXT ? 896 : 1024) / BT) bn_relu_maxpool_
     st_bf16x8_to_f32(x1r, x1);
     {
       float A[8], Bc[8];
-      st_lds8(cst, A);
-      st_lds8(cst + cst_stride, Bc);
+      st_lds8(cst, cst_half, A);
+      st_lds8(cst + cst_stride, cst_half, Bc);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         o0[q] = fmaf(A[q], o0[q], Bc[q] * x0[q]);
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(BT, (NEXT ? 896 : 1024) / BT) bn_relu_maxpool_
     }
     {
       float Cc[8];
-      st_lds8(cst + 2u * cst_stride, Cc);
+      st_lds8(cst + 2u * cst_stride, cst_half, Cc);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         o0[q] += Cc[q];
@@ -407,21 +412,22 @@ __global__ void __launch_bounds__(BT, 640 / BT) bn2_relu_maxpool_bwd_apply_kerne
   }
   const int C8 = cg * 8;
   for (int c = threadIdx.x; c < C8; c += BT) {
+    const int ci = st_cst_index(c, cg);
     {
       const double r = (double)__ldg(rstd + c), m = (double)__ldg(mean + c), gm = gamma ? (double)__ldg(gamma + c) : 1.0;
       const double c1 = sum_dy[c] * (double)inv_n, c2 = sum_dy_xhat[c] * (double)inv_n;
-      st_cst[c] = (float)(gm * r);
-      st_cst[C8 + c] = (float)(-gm * r * r * c2);
-      st_cst[2 * C8 + c] = (float)(gm * r * (r * c2 * m - c1));
+      st_cst[ci] = (float)(gm * r);
+      st_cst[C8 + ci] = (float)(-gm * r * r * c2);
+      st_cst[2 * C8 + ci] = (float)(gm * r * (r * c2 * m - c1));
     }
     {
       const double r = (double)__ldg(up.rstd + c), m = (double)__ldg(up.mean + c), gm = up.gamma ? (double)__ldg(up.gamma + c) : 1.0;
       const double c1 = up.sum_dy[c] * (double)up.inv_n, c2 = up.sum_dy_xhat[c] * (double)up.inv_n;
-      st_cst[3 * C8 + c] = __ldg(up.scale + c);
-      st_cst[4 * C8 + c] = __ldg(up.shift + c);
-      st_cst[5 * C8 + c] = (float)(gm * r);
-      st_cst[6 * C8 + c] = (float)(-gm * r * r * c2);
-      st_cst[7 * C8 + c] = (float)(gm * r * (r * c2 * m - c1));
+      st_cst[3 * C8 + ci] = __ldg(up.scale + c);
+      st_cst[4 * C8 + ci] = __ldg(up.shift + c);
+      st_cst[5 * C8 + ci] = (float)(gm * r);
+      st_cst[6 * C8 + ci] = (float)(-gm * r * r * c2);
+      st_cst[7 * C8 + ci] = (float)(gm * r * (r * c2 * m - c1));
     }
   }
   for (int c2 = threadIdx.x; c2 < cg * 4; c2 += BT) {
@@ -438,8 +444,8 @@ __global__ void __launch_bounds__(BT, 640 / BT) bn2_relu_maxpool_bwd_apply_kerne
     thr[q] = sm_thr[g * 4 + q];
     flip[q] = sm_flip[g * 4 + q];
   }
-  const uint32_t cst = (uint32_t)__cvta_generic_to_shared(st_cst) + (uint32_t)g * 32u;
-  const uint32_t cst_stride = (uint32_t)cg * 32u;
+  const uint32_t cst = (uint32_t)__cvta_generic_to_shared(st_cst) + (uint32_t)g * 16u;
+  const uint32_t cst_stride = (uint32_t)cg * 32u, cst_half = (uint32_t)cg * 16u;
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const int n = row / H, ih = row - n * H;
     const bool odd = (ih & 1) != 0;
@@ -478,8 +484,8 @@ __global__ void __launch_bounds__(BT, 640 / BT) bn2_relu_maxpool_bwd_apply_kerne
       uint4 x0r, x1r;
       {  // x as the forward stored it: fma, ReLU, round to bf16
         float usc[8], ush[8];
-        st_lds8(cst + 3u * cst_stride, usc);
-        st_lds8(cst + 4u * cst_stride, ush);
+        st_lds8(cst + 3u * cst_stride, cst_half, usc);
+        st_lds8(cst + 4u * cst_stride, cst_half, ush);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           x0[q] = fmaxf(fmaf(w0[q], usc[q], ush[q]), 0.f);
@@ -503,8 +509,8 @@ __global__ void __launch_bounds__(BT, 640 / BT) bn2_relu_maxpool_bwd_apply_kerne
       st_bf16x8_to_f32(make_uint4(q1[0], q1[1], q1[2], q1[3]), o1);
       {
         float A[8], Bc[8];
-        st_lds8(cst, A);
-        st_lds8(cst + cst_stride, Bc);
+        st_lds8(cst, cst_half, A);
+        st_lds8(cst + cst_stride, cst_half, Bc);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           o0[q] = fmaf(A[q], o0[q], Bc[q] * x0[q]);
@@ -513,8 +519,8 @@ __global__ void __launch_bounds__(BT, 640 / BT) bn2_relu_maxpool_bwd_apply_kerne
       }
       {
         float Cc[8], A2[8];
-        st_lds8(cst + 2u * cst_stride, Cc);
-        st_lds8(cst + 5u * cst_stride, A2);
+        st_lds8(cst + 2u * cst_stride, cst_half, Cc);
+        st_lds8(cst + 5u * cst_stride, cst_half, A2);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {   // dx complete; through the upstream ReLU and the data term of its BatchNorm
           o0[q] = x0[q] > 0.f ? A2[q] * (o0[q] + Cc[q]) : 0.f;
@@ -523,8 +529,8 @@ __global__ void __launch_bounds__(BT, 640 / BT) bn2_relu_maxpool_bwd_apply_kerne
       }
       {
         float B2[8], C2[8];
-        st_lds8(cst + 6u * cst_stride, B2);
-        st_lds8(cst + 7u * cst_stride, C2);
+        st_lds8(cst + 6u * cst_stride, cst_half, B2);
+        st_lds8(cst + 7u * cst_stride, cst_half, C2);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           o0[q] += fmaf(B2[q], w0[q], C2[q]);

@@ -390,7 +390,7 @@ struct StUpstream {
 };
 
 template <int BT>
-__global__ void __launch_bounds__(BT, 640 / BT) bn2_relu_maxpool_bwd_apply_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
+__global__ void __launch_bounds__(BT, 768 / BT) bn2_relu_maxpool_bwd_apply_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx,
                                                                                  const uint4* __restrict__ raw, uint4* __restrict__ draw, int rows,
                                                                                  int H, int W, int OH, int OW, int cg, int cg_shift,
                                                                                  const float* __restrict__ fsc, const float* __restrict__ fsh,
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(BT, 640 / BT) bn2_relu_maxpool_bwd_apply_kerne
                                                                                  const float* __restrict__ gamma, const double* __restrict__ sum_dy,
                                                                                  const double* __restrict__ sum_dy_xhat, float inv_n,
                                                                                  StParamGrads pg, StUpstream up) {
-  extern __shared__ float st_cst[];   // [8][C]: A, B, C of this BatchNorm; scale, shift, A', B', C' of the upstream one
+  extern __shared__ float st_cst[];   // [7][C]: A'A, A'B, A'C of this BatchNorm; scale, shift, B', C' of the upstream one
   __shared__ uint32_t sm_thr[BT * 4], sm_flip[BT * 4];
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < pg.n; c += BT) {
@@ -413,22 +413,19 @@ __global__ void __launch_bounds__(BT, 640 / BT) bn2_relu_maxpool_bwd_apply_kerne
   const int C8 = cg * 8;
   for (int c = threadIdx.x; c < C8; c += BT) {
     const int ci = st_cst_index(c, cg);
-    {
-      const double r = (double)__ldg(rstd + c), m = (double)__ldg(mean + c), gm = gamma ? (double)__ldg(gamma + c) : 1.0;
-      const double c1 = sum_dy[c] * (double)inv_n, c2 = sum_dy_xhat[c] * (double)inv_n;
-      st_cst[ci] = (float)(gm * r);
-      st_cst[C8 + ci] = (float)(-gm * r * r * c2);
-      st_cst[2 * C8 + ci] = (float)(gm * r * (r * c2 * m - c1));
-    }
-    {
-      const double r = (double)__ldg(up.rstd + c), m = (double)__ldg(up.mean + c), gm = up.gamma ? (double)__ldg(up.gamma + c) : 1.0;
-      const double c1 = up.sum_dy[c] * (double)up.inv_n, c2 = up.sum_dy_xhat[c] * (double)up.inv_n;
-      st_cst[3 * C8 + ci] = __ldg(up.scale + c);
-      st_cst[4 * C8 + ci] = __ldg(up.shift + c);
-      st_cst[5 * C8 + ci] = (float)(gm * r);
-      st_cst[6 * C8 + ci] = (float)(-gm * r * r * c2);
-      st_cst[7 * C8 + ci] = (float)(gm * r * (r * c2 * m - c1));
-    }
+    // dx = A*d + B*x + C of this BatchNorm and d raw = A'*[x > 0]*dx + B'*raw + C' of the upstream one: A' is folded into (A, B, C)
+    const double ur = (double)__ldg(up.rstd + c), um = (double)__ldg(up.mean + c), ugm = up.gamma ? (double)__ldg(up.gamma + c) : 1.0;
+    const double uc1 = up.sum_dy[c] * (double)up.inv_n, uc2 = up.sum_dy_xhat[c] * (double)up.inv_n;
+    const double a2 = ugm * ur;
+    const double r = (double)__ldg(rstd + c), m = (double)__ldg(mean + c), gm = gamma ? (double)__ldg(gamma + c) : 1.0;
+    const double c1 = sum_dy[c] * (double)inv_n, c2 = sum_dy_xhat[c] * (double)inv_n;
+    st_cst[ci] = (float)(a2 * gm * r);
+    st_cst[C8 + ci] = (float)(-a2 * gm * r * r * c2);
+    st_cst[2 * C8 + ci] = (float)(a2 * gm * r * (r * c2 * m - c1));
+    st_cst[3 * C8 + ci] = __ldg(up.scale + c);
+    st_cst[4 * C8 + ci] = __ldg(up.shift + c);
+    st_cst[5 * C8 + ci] = (float)(-ugm * ur * ur * uc2);
+    st_cst[6 * C8 + ci] = (float)(ugm * ur * (ur * uc2 * um - uc1));
   }
   for (int c2 = threadIdx.x; c2 < cg * 4; c2 += BT) {
     const float s0 = __ldg(fsc + 2 * c2), s1 = __ldg(fsc + 2 * c2 + 1);
@@ -518,19 +515,18 @@ __global__ void __launch_bounds__(BT, 640 / BT) bn2_relu_maxpool_bwd_apply_kerne
         }
       }
       {
-        float Cc[8], A2[8];
+        float Cc[8];
         st_lds8(cst + 2u * cst_stride, cst_half, Cc);
-        st_lds8(cst + 5u * cst_stride, cst_half, A2);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {   // dx complete; through the upstream ReLU and the data term of its BatchNorm
-          o0[q] = x0[q] > 0.f ? A2[q] * (o0[q] + Cc[q]) : 0.f;
-          o1[q] = x1[q] > 0.f ? A2[q] * (o1[q] + Cc[q]) : 0.f;
+        for (int q = 0; q < 8; ++q) {   // A' * dx complete; through the upstream ReLU
+          o0[q] = x0[q] > 0.f ? o0[q] + Cc[q] : 0.f;
+          o1[q] = x1[q] > 0.f ? o1[q] + Cc[q] : 0.f;
         }
       }
       {
         float B2[8], C2[8];
-        st_lds8(cst + 6u * cst_stride, cst_half, B2);
-        st_lds8(cst + 7u * cst_stride, cst_half, C2);
+        st_lds8(cst + 5u * cst_stride, cst_half, B2);
+        st_lds8(cst + 6u * cst_stride, cst_half, C2);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           o0[q] += fmaf(B2[q], w0[q], C2[q]);
@@ -907,7 +903,7 @@ extern "C" int pmoe_bn2_relu_maxpool_bwd_apply(const PmoeView4* dy, const uint8_
     return PMOE_ERR_ARG;
   }
   const int cg = raw->c / 8;
-  if (cg > 128 || 128 % cg != 0 || (size_t)8 * raw->c * sizeof(float) > 40 * 1024) {
+  if (cg > 128 || 128 % cg != 0 || (size_t)7 * raw->c * sizeof(float) > 40 * 1024) {
     set_error("bn2_relu_maxpool_bwd_apply: channel-group count must divide 128, at most 1280 channels");
     return PMOE_ERR_UNSUPPORTED;
   }
@@ -936,7 +932,7 @@ extern "C" int pmoe_bn2_relu_maxpool_bwd_apply(const PmoeView4* dy, const uint8_
   up.sum_dy_xhat = up_sum_dy_xhat;
   up.inv_n = inv_n;
   constexpr int BT = 128;
-  const size_t cst_bytes = (size_t)8 * raw->c * sizeof(float);
+  const size_t cst_bytes = (size_t)7 * raw->c * sizeof(float);
   static int per_sm = 0;
   if (per_sm == 0) {
     int q = 0;

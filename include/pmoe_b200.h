@@ -271,6 +271,12 @@ int pmoe_eca_bn_bwd_apply(const PmoeView4* dy, const PmoeView4* raw, const float
                           int64_t dmean_stride, const float* fwd_scale, const float* fwd_shift, const float* mean, const float* rstd,
                           const float* gamma, const double* sum_dy, const double* sum_dy_xhat, float inv_n, const PmoeView4* dx,
                           const PmoeBnParamGrads* param_grads, pmoe_stream_t stream);
+/* Backward of Linear -> activation without BatchNorm (make_mlp stacks of the expert heads, reference PMoE/model/blocks/basics.py:11-45,
+ * model/moe.py:88-101): dy = dz * act'(z) from the saved OUTPUT z (act: none / ReLU / ELU) fused with the bias gradient, the per-image
+ * channel sum of dy accumulated into the zeroed fp32 (n, bias_stride) buffer (image = expert in the grouped heads). Replaces
+ * pmoe_bn_bwd_apply (no statistics) + pmoe_channel_sums. Dense bf16; otherwise PMOE_ERR_UNSUPPORTED. */
+int pmoe_act_bwd_bias(const PmoeView4* dz, const PmoeView4* z, int32_t act, const PmoeView4* dy, float* bias_sum, int64_t bias_stride,
+                      pmoe_stream_t stream);
 /* dst (+)= alpha*src + bcast[n][c]: gradient accumulation and global-avg-pool backward. */
 int pmoe_axpy(const PmoeView4* src, const PmoeView4* dst, int32_t dtype, float alpha, const float* bcast, int64_t bcast_stride,
               int32_t accumulate, pmoe_stream_t stream);

@@ -1700,9 +1700,26 @@ def grouped_linear_op(tape, srcs, lins, act=None, tag=""):
             return
         z_saved = z_t if act not in (None, "none") else None
         dy = torch.empty(K, 1, B, cstore, dtype=dt, device=dev)
-        _bn_bwd_apply(dz, z_saved, None, act, None, None, None, None, None, 0.0, 0, dy, None, False)
-        if has_bias and any(l.bias.requires_grad for l in lins):
-            bsum = nhwc.channel_sums(dy)                      # (K, cstore): per-expert bias gradients in one launch
+        want_bias = has_bias and any(l.bias.requires_grad for l in lins)
+        bsum = None
+        if (FUSE_ACT_BWD_BIAS and want_bias and act in (None, "none", "relu", "elu") and dt == torch.bfloat16 and dz.is_contiguous()
+                and dz.dtype == dt and 256 % max(cstore // 8, 1) == 0):
+            # activation backward and the per-expert bias gradients (per-image channel sums of dy) in one pass
+            bsum = tape.zeros((K, cstore), torch.float32, dev)
+            vz, vy = view4(dz), view4(dy)
+            vs = view4(z_saved) if z_saved is not None else _lib.null_view()
+            rc = profiler.launch("act_bwd_bias", lambda: lib().pmoe_act_bwd_bias(
+                C.byref(vz), C.byref(vs), ACT[act], C.byref(vy), bsum.data_ptr(), bsum.stride(0), stream_ptr()), io=(dz, z_saved, dy))
+            if rc == -2:
+                profiler.uncount()
+                bsum = None
+            else:
+                check(rc, "act_bwd_bias")
+        if bsum is None:
+            _bn_bwd_apply(dz, z_saved, None, act, None, None, None, None, None, 0.0, 0, dy, None, False)
+            if want_bias:
+                bsum = nhwc.channel_sums(dy)                  # (K, cstore): per-expert bias gradients in one launch
+        if want_bias:
             _group_to_params(tape, bsum if cstore == cop else torch.nn.functional.pad(bsum, (0, cop - cstore)), bias_packs,
                              [l.bias for l in lins])
         if any(l.weight.requires_grad for l in lins):
@@ -1726,6 +1743,7 @@ def grouped_linear_op(tape, srcs, lins, act=None, tag=""):
 
 
 GROUPED_HEADS = True  # tests switch this off to compare against the per-expert launches
+FUSE_ACT_BWD_BIAS = _os0.environ.get("PMOE_FUSE_ACT_BWD_BIAS", "1") != "0"   # head Linears: activation backward + bias gradient in one pass
 
 
 def grouped_supported(experts, alt):

@@ -77,6 +77,7 @@ class Tape:
         self.bucketer = None        # pmoe_b200.dp.GradBucketer during a data-parallel backward
         self.presums = {}           # id(Act) -> (sum dy*[y>0], sum dy*y) reduced by the kernel that wrote the Act's gradient
         self.lazy = {}              # id(Act) -> (dy, gate, dmean): gradient dy*gate[n,c] + dmean[n,c] that is never stored (eca_op)
+        self.pending_dgrad = {}     # id(Act) -> [(dy, packed dgrad weights, Act, ...)]: skinny grouped data gradients of one source, merged into ONE GEMM when the source's gradient is asked for
         self.raw_grads = {}         # id(Act) -> gradient of the RAW conv output behind the Act's BatchNorm + ReLU, already formed by the consumer (bn_relu_maxpool_op)
         self.arena = {}             # dtype -> [zeroed chunk, elements handed out]
         self.direct = set()         # id(param) whose gradient was accumulated straight into param.grad
@@ -149,6 +150,8 @@ class Tape:
         return act
 
     def grad_of(self, act):
+        if self.pending_dgrad and id(act) in self.pending_dgrad:
+            _flush_dgrad(self, id(act))
         g = self.grads.pop(id(act), None)
         if g is not None and self.branch_stream is not None:
             g.record_stream(self.branch_stream)   # may have been produced (allocated) on another stream: keep it until this one is done
@@ -221,11 +224,14 @@ class Tape:
         self.branch_stream = None
         for s_ in forked:
             main.wait_stream(s_)
+        for key in list(self.pending_dgrad):   # (a source nobody asked for: nothing depends on it, the queue is just emptied)
+            self.pending_dgrad.pop(key, None)
         self.ops = []
         self.alive = []
         self.grads = {}
         self.lazy = {}
         self.raw_grads = {}
+        self.pending_dgrad = {}
         if self.bucketer is not None:  # gradients whose announced contributions did not all arrive
             for k in self.pgrads:
                 if k not in self.reported:
@@ -1732,6 +1738,11 @@ def grouped_linear_op(tape, srcs, lins, act=None, tag=""):
             if not _rg(x.act):
                 continue
             wd = _grouped_pack(lins, [x], cstore, dt, "d")[0]
+            if MERGE_SKINNY_DGRAD and cstore <= 16 and len(srcs) == 1 and x.t is x.act.t:
+                # 512 -> 4 and 512 -> 1 heads of one feature tensor (action_pred, alpha): their data gradients are two K = 16 GEMMs that
+                # each write / accumulate the whole (K, B, 512) gradient; queued here, they run as ONE K = 32 GEMM (Tape.grad_of)
+                tape.pending_dgrad.setdefault(id(x.act), []).append((dy, wd, x.act, 2.0 * K * B * cout * x.nlog, tag))
+                continue
             g, existed = _grad_buffer(tape, x.act)
             ops.conv([dy], wd, [(0, 0, 0, 0, cstore // ck_d)], ck_d, g, residual=g if existed else None,
                      flops=2.0 * K * B * cout * x.nlog, tag="dgrad grouped " + tag)
@@ -1743,6 +1754,25 @@ def grouped_linear_op(tape, srcs, lins, act=None, tag=""):
 
 
 GROUPED_HEADS = True  # tests switch this off to compare against the per-expert launches
+MERGE_SKINNY_DGRAD = _os0.environ.get("PMOE_MERGE_SKINNY_DGRAD", "1") != "0"
+
+
+def _flush_dgrad(tape, key):
+    """Run the queued skinny data gradients of one source activation (grouped_linear_op) as one GEMM over their concatenated K."""
+    ents = tape.pending_dgrad.pop(key, None)
+    if not ents:
+        return
+    act = ents[0][2]
+    g, existed = _grad_buffer(tape, act)
+    if len(ents) == 1:
+        dy, wd = ents[0][0], ents[0][1]
+    else:
+        dy = torch.cat([e[0] for e in ents], dim=3)
+        wd = torch.cat([e[1] for e in ents], dim=2)
+    kd = dy.shape[3]
+    ck = ops.choose_ck([kd])
+    ops.conv([dy], wd, [(0, 0, 0, 0, kd // ck)], ck, g, residual=g if existed else None, flops=sum(e[3] for e in ents),
+             tag="dgrad grouped " + "+".join(e[4] for e in ents))
 FUSE_ACT_BWD_BIAS = _os0.environ.get("PMOE_FUSE_ACT_BWD_BIAS", "1") != "0"   # head Linears: activation backward + bias gradient in one pass
 
 

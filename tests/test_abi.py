@@ -58,3 +58,18 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_ctypes_argument_counts_match_the_header():
+    """Every entry point's ctypes argtypes list has as many entries as the C declaration has parameters (a drifted signature would
+    otherwise only show up as a crash on the GPU box)."""
+    from pmoe_b200 import _sigs
+    text = open(os.path.join(ROOT, "include", "pmoe_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decl = {}
+    for m in re.finditer(r"\b(pmoe_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", text, flags=re.S):
+        params = m.group(2).strip()
+        decl[m.group(1)] = 0 if params in ("", "void") else params.count(",") + 1
+    bad = {n: (len(a), decl[n]) for n, a in _sigs.SIGS.items() if n in decl and len(a) != decl[n]}
+    assert not bad, bad
+    assert len([n for n in _sigs.SIGS if n in decl]) >= 50
